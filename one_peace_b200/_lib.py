@@ -1,0 +1,56 @@
+"""ctypes loader for ``csrc/libonepeace_b200.so`` (the C-ABI declared in ``include/onepeace_b200.h``).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing the import of this
+module raises, and every non-zero status from a C entry point raises ``RuntimeError`` (the reference's
+error convention is Python exceptions only).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libonepeace_b200.so")
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol include/onepeace_b200.h declares
+# (tests/test_abi_symbols.py cross-checks this table against the header).
+SIGNATURES = {
+    "opb_abi_version": (c_int, []),
+    "opb_status_string": (ctypes.c_char_p, [c_int]),
+    "opb_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_void_p]),
+    "opb_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p]),
+    "opb_layernorm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int,
+                              c_float, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def build_hint():
+    return ("build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C one_peace_b200/csrc`")
+
+
+def load():
+    """Load the shared library once; raise if it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: the sm_100a extension is required; {build_hint()}")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().opb_status_string(status).decode()
+        raise RuntimeError(f"{what}: {msg} (status {status})")

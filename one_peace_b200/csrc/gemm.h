@@ -1,0 +1,38 @@
+// Internal (C++) interface of the tcgen05 GEMM; the C-ABI wrappers live in c_abi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace opb {
+
+enum GemmEpi : int {
+  EPI_STORE_BF16 = 0,  // out_bf16 = (acc + bias) * colscale
+  EPI_GEGLU_BF16 = 1,  // out_bf16[:, t*128 + j] = gelu(acc[:, j]) * acc[:, 128 + j]   (N/2 output columns)
+  EPI_RESID_F32 = 2,   // out_f32 = resid + gamma * (acc + bias)
+  EPI_STORE_F32 = 3,   // out_f32 = acc + bias
+  EPI_GELU_BF16 = 4,   // out_bf16 = gelu((acc + bias) * colscale)
+};
+
+struct GemmEpilogue {
+  void* out = nullptr;             // bf16 or fp32, see GemmEpi
+  long ldo = 0;                    // output row pitch, elements
+  const float* bias = nullptr;     // [N] or null
+  const float* colscale = nullptr; // [N] or null
+  const float* gamma = nullptr;    // [N] or null (EPI_RESID_F32)
+  const float* resid = nullptr;    // fp32 residual or null (EPI_RESID_F32)
+  long ldr = 0;                    // residual row pitch
+  // optional row remapping: out_row = (m / out_group) * out_group_stride + (m % out_group) + out_row_offset
+  int out_group = 0;
+  int out_group_stride = 0;
+  int out_row_offset = 0;
+  // optional broadcast residual: resid_row = (m % resid_period) + resid_row_offset
+  int resid_period = 0;
+  int resid_row_offset = 0;
+};
+
+// C = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major with pitches lda, ldb (elements).
+// cta_group: 1, 2 or 0 (auto).  Returns an OPB_* status.
+int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep,
+              int cta_group, cudaStream_t stream);
+
+}  // namespace opb

@@ -1,0 +1,392 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )
+//
+//   * operands are K-major bf16 (activations [rows, K], nn.Linear weights [out, in]) and are staged
+//     into shared memory by TMA with the 128-byte swizzle, BLOCK_K = 64;
+//   * tcgen05.mma (kind::f16, fp32 accumulate) issued by one thread, accumulators in TMEM,
+//     two accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of i+1;
+//   * CG = 1: one CTA per 128 x 256 tile.  CG = 2: a CTA pair (cluster of 2) per 256 x 256 tile with
+//     tcgen05.mma.cta_group::2 — each CTA stages its 128 rows of A and its 128 rows of B;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM -> registers
+//     -> fused epilogue -> global).
+//
+// Fused epilogues (what the reference runs as separate ATen kernels, SURVEY.md 2.5 K1'/K3/K4):
+//   EPI_STORE_BF16 : out_bf16 = (acc + bias[n]) * colscale[n]        (q/k/v projection, q pre-scaled;
+//                                                                     multihead_attention.py:103-107)
+//   EPI_GEGLU_BF16 : out_bf16[:, t*128+j] = gelu(acc[:, j]) * acc[:, 128+j] on a W0/W1-interleaved
+//                    weight (transformer_layer.py:54-67) — the 2*ffn wide intermediate never hits HBM
+//   EPI_RESID_F32  : out_f32 = resid + gamma[n] * (acc + bias[n])    (out_proj / fc2 + LayerScale +
+//                                                                     residual, transformer_layer.py:70-88)
+//   EPI_STORE_F32  : out_f32 = acc + bias[n]
+#include "common.cuh"
+#include "gemm.h"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace opb {
+
+constexpr int kBlockM = 128;   // rows of A per CTA
+constexpr int kBlockN = 256;   // accumulator columns per tile
+constexpr int kBlockK = 64;    // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kAccStages = 2;
+constexpr int kNumThreads = 192;
+
+template <int CG>
+struct GemmCfg {
+  static constexpr int kBRows = kBlockN / CG;                       // rows of B staged per CTA
+  static constexpr int kABytes = kBlockM * kBlockK * 2;             // 16 KB
+  static constexpr int kBBytes = kBRows * kBlockK * 2;              // 32 KB (CG=1) / 16 KB (CG=2)
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (CG == 1) ? 4 : 6;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+struct SmemBars {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+template <int CG, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const GemmEpilogue ep, int M, int N, int K) {
+  using Cfg = GemmCfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SmemBars* bars = reinterpret_cast<SmemBars*>(smem + Cfg::kStages * Cfg::kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  const int tile_m_rows = kBlockM * CG;
+  const int num_m_tiles = (M + tile_m_rows - 1) / tile_m_rows;
+  const int num_n_tiles = (N + kBlockN - 1) / kBlockN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int first_tile = blockIdx.x / CG;
+  const int tile_stride = gridDim.x / CG;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], 4 * CG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc<CG>(&bars->tmem_base, kAccStages * kBlockN);
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint64_t* full_bar0 = bars->full;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        const int m_blk = tile % num_m_tiles;
+        const int n_blk = tile / num_m_tiles;
+        const int a_row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
+        const int b_row = n_blk * kBlockN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar0[stage], Cfg::kStageBytes);
+            tma_load_2d(&tm_a, &full_bar0[stage], sa, kb * kBlockK, a_row);
+            tma_load_2d(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
+          } else {
+            if (is_leader) mbar_arrive_expect_tx(&full_bar0[stage], Cfg::kStageBytes * 2);
+            tma_load_2d_2sm(&tm_a, &full_bar0[stage], sa, kb * kBlockK, a_row);
+            tma_load_2d_2sm(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<CG>(&bars->empty[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<CG>(&bars->tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+      const int m_blk = tile % num_m_tiles;
+      const int n_blk = tile / num_m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
+
+      // output / residual row mapping (lets adapters scatter rows behind a CLS slot and broadcast a
+      // positional table over the batch)
+      long out_row = row;
+      if (ep.out_group > 0) out_row = static_cast<long>(row / ep.out_group) * ep.out_group_stride + (row % ep.out_group) + ep.out_row_offset;
+      long res_row = out_row;
+      if (ep.resid_period > 0) res_row = (row % ep.resid_period) + ep.resid_row_offset;
+
+      if constexpr (EPI == EPI_GEGLU_BF16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + n_blk * (kBlockN / 2);
+        const int n_out = N / 2;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 2; c += 32) {
+          uint32_t g[32], l[32];
+          __syncwarp();
+          tmem_ld32(taddr + c, g);
+          tmem_ld32(taddr + kBlockN / 2 + c, l);
+          tmem_ld_wait();
+          if (c + 32 == kBlockN / 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (n_blk * (kBlockN / 2) + c + j < n_out) {
+                uint4 o;
+                uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float a0 = gelu_erf(__uint_as_float(g[j + 2 * e])) * __uint_as_float(l[j + 2 * e]);
+                  float a1 = gelu_erf(__uint_as_float(g[j + 2 * e + 1])) * __uint_as_float(l[j + 2 * e + 1]);
+                  po[e] = pack_bf16x2(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(out + c + j) = o;
+              }
+            }
+          }
+        }
+      } else {
+        const int col0 = n_blk * kBlockN;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (c + 32 == kBlockN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int col = col0 + c + j;
+            if (!row_ok || col >= N) continue;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j + e]);
+            if (ep.bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col);
+              const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
+              if (ep.colscale != nullptr) {
+                const float4 s0 = *reinterpret_cast<const float4*>(ep.colscale + col);
+                const float4 s1 = *reinterpret_cast<const float4*>(ep.colscale + col + 4);
+                x[0] *= s0.x; x[1] *= s0.y; x[2] *= s0.z; x[3] *= s0.w;
+                x[4] *= s1.x; x[5] *= s1.y; x[6] *= s1.z; x[7] *= s1.w;
+              }
+              if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
+              }
+              uint4 o;
+              o.x = pack_bf16x2(x[0], x[1]);
+              o.y = pack_bf16x2(x[2], x[3]);
+              o.z = pack_bf16x2(x[4], x[5]);
+              o.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + col) = o;
+            } else {
+              if constexpr (EPI == EPI_RESID_F32) {
+                if (ep.gamma != nullptr) {
+                  const float4 g0 = *reinterpret_cast<const float4*>(ep.gamma + col);
+                  const float4 g1 = *reinterpret_cast<const float4*>(ep.gamma + col + 4);
+                  x[0] *= g0.x; x[1] *= g0.y; x[2] *= g0.z; x[3] *= g0.w;
+                  x[4] *= g1.x; x[5] *= g1.y; x[6] *= g1.z; x[7] *= g1.w;
+                }
+                if (ep.resid != nullptr) {
+                  const float* r = ep.resid + res_row * ep.ldr + col;
+                  const float4 r0 = *reinterpret_cast<const float4*>(r);
+                  const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+                  x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+                  x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+                }
+              }
+              float* o = reinterpret_cast<float*>(ep.out) + out_row * ep.ldo + col;
+              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base, kAccStages * kBlockN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+  });
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with row pitch ld (elements); box = 64 cols x box_rows, 128B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return OPB_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return OPB_ERR_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OPB_OK : OPB_ERR_CUDA;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int CG, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<CG>;
+  auto kern = gemm_bf16_kernel<CG, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return OPB_ERR_CUDA;
+    configured = true;
+  }
+  const int tile_m_rows = kBlockM * CG;
+  const int num_tiles = ((M + tile_m_rows - 1) / tile_m_rows) * ((N + kBlockN - 1) / kBlockN);
+  int groups = sm_count() / CG;
+  if (groups > num_tiles) groups = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K);
+  return e == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep,
+              int cta_group, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return OPB_ERR_INVALID;
+  if (K % 8 != 0 || N % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) return OPB_ERR_INVALID;
+  if (epi == EPI_GEGLU_BF16 && N % kBlockN != 0) return OPB_ERR_INVALID;
+  if (cta_group == 0) cta_group = (M > 2 * kBlockM) ? 2 : 1;
+  if (cta_group != 1 && cta_group != 2) return OPB_ERR_INVALID;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, kBlockM);
+  if (rc != OPB_OK) return rc;
+  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, kBlockN / cta_group);
+  if (rc != OPB_OK) return rc;
+#define OPB_DISPATCH(CGV)                                                                      \
+  switch (epi) {                                                                               \
+    case EPI_STORE_BF16: return launch_gemm<CGV, EPI_STORE_BF16>(ta, tb, ep, M, N, K, stream); \
+    case EPI_GELU_BF16: return launch_gemm<CGV, EPI_GELU_BF16>(ta, tb, ep, M, N, K, stream);   \
+    case EPI_GEGLU_BF16: return launch_gemm<CGV, EPI_GEGLU_BF16>(ta, tb, ep, M, N, K, stream); \
+    case EPI_RESID_F32: return launch_gemm<CGV, EPI_RESID_F32>(ta, tb, ep, M, N, K, stream);   \
+    case EPI_STORE_F32: return launch_gemm<CGV, EPI_STORE_F32>(ta, tb, ep, M, N, K, stream);   \
+    default: return OPB_ERR_INVALID;                                                           \
+  }
+  if (cta_group == 1) { OPB_DISPATCH(1) } else { OPB_DISPATCH(2) }
+#undef OPB_DISPATCH
+}
+
+}  // namespace opb

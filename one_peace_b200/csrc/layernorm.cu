@@ -1,0 +1,178 @@
+// Row LayerNorm kernels (eps inside the sqrt, biased variance — torch.nn.LayerNorm semantics, which is
+// what one_peace/models/components.py:23-26 builds).  HBM-bound: one pass, the row lives in registers,
+// two-step mean / centred variance in fp32, 16-byte vector loads/stores, one CTA per row.
+//
+//   in : fp32 (residual stream) or bf16 (GEMM / attention outputs), row pitch ld_in
+//   out: bf16 (feeds the next tcgen05 GEMM as its K-major A operand) or fp32
+//   optional affine (gamma/beta may be null: the audio conv-pos LN is non-affine, audio.py:71),
+//   optional exact-erf GELU after the norm (hMLP stem and wav2vec-style conv blocks: LN -> GELU),
+//   optional 2x2 pixel-merge scatter of the output row, which lays the result out as the A operand
+//   of the next stride-2 patch conv (image.py:66-75) so that conv is a plain GEMM.
+#include "common.cuh"
+
+namespace opb {
+
+struct LnArgs {
+  const void* in;
+  void* out;
+  const float* gamma;
+  const float* beta;
+  long ld_in;       // elements
+  long ld_out;      // elements
+  int rows;
+  int dim;
+  float eps;
+  int gelu;
+  // pixel-merge scatter (0 = off): input rows are (b, y, x) over a grid_w x grid_w map
+  int merge_grid_w;
+};
+
+template <typename T>
+OPB_DEVICE void load8(const T* p, float (&v)[8]);
+template <>
+OPB_DEVICE void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+OPB_DEVICE void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+template <typename T>
+OPB_DEVICE void store8(T* p, const float (&v)[8]);
+template <>
+OPB_DEVICE void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+OPB_DEVICE void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+OPB_DEVICE float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nwarps; ++i) t += red[i];   // fixed order: identical in every thread
+  return t;
+}
+
+template <typename TIn, typename TOut, int ITERS>
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const TIn* in = reinterpret_cast<const TIn*>(a.in) + static_cast<long>(row) * a.ld_in;
+  float x[ITERS][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = (i * blockDim.x + threadIdx.x) * 8;
+    if (c < a.dim) {
+      load8<TIn>(in + c, x[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += x[i][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[i][e] = 0.f;
+    }
+  }
+  const float mean = block_sum(sum, red) / a.dim;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = (i * blockDim.x + threadIdx.x) * 8;
+    if (c < a.dim) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = x[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float var = block_sum(sq, red) / a.dim;
+  const float rstd = rsqrtf(var + a.eps);
+
+  long orow = row;
+  long ocol0 = 0;
+  if (a.merge_grid_w > 0) {
+    const int w = a.merge_grid_w;
+    const int xx = row % w;
+    const int yy = (row / w) % w;
+    const int bb = row / (w * w);
+    orow = (static_cast<long>(bb) * (w / 2) + yy / 2) * (w / 2) + xx / 2;
+    ocol0 = static_cast<long>((yy & 1) * 2 + (xx & 1)) * a.dim;
+  }
+  TOut* out = reinterpret_cast<TOut*>(a.out) + orow * a.ld_out + ocol0;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = (i * blockDim.x + threadIdx.x) * 8;
+    if (c < a.dim) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (x[i][e] - mean) * rstd;
+      if (a.gamma != nullptr) {
+        float gm[8], bt[8];
+        load8<float>(a.gamma + c, gm);
+        load8<float>(a.beta + c, bt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = y[e] * gm[e] + bt[e];
+      }
+      if (a.gelu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = gelu_erf(y[e]);
+      }
+      store8<TOut>(out + c, y);
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+static int launch_ln(const LnArgs& a, cudaStream_t stream) {
+  const int vecs = a.dim / 8;
+  // threads: enough for <= 3 vectors per thread, multiple of 32, <= 256
+  int iters = (vecs + 255) / 256;
+  if (iters < 1) iters = 1;
+  int threads = (vecs + iters - 1) / iters;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 256) return OPB_ERR_UNSUPPORTED;
+  switch (iters) {
+    case 1: layernorm_kernel<TIn, TOut, 1><<<a.rows, threads, 0, stream>>>(a); break;
+    case 2: layernorm_kernel<TIn, TOut, 2><<<a.rows, threads, 0, stream>>>(a); break;
+    case 3: layernorm_kernel<TIn, TOut, 3><<<a.rows, threads, 0, stream>>>(a); break;
+    case 4: layernorm_kernel<TIn, TOut, 4><<<a.rows, threads, 0, stream>>>(a); break;
+    default: return OPB_ERR_UNSUPPORTED;
+  }
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// in_dtype / out_dtype: 0 = fp32, 1 = bf16
+int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const float* gamma,
+              const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, cudaStream_t stream) {
+  if (rows <= 0 || dim <= 0 || dim % 8 != 0 || ld_in % 8 != 0 || ld_out % 8 != 0) return OPB_ERR_INVALID;
+  if ((gamma == nullptr) != (beta == nullptr)) return OPB_ERR_INVALID;
+  if (merge_grid_w < 0 || (merge_grid_w & 1)) return OPB_ERR_INVALID;
+  LnArgs a{in, out, gamma, beta, ld_in, ld_out, rows, dim, eps, gelu, merge_grid_w};
+  if (in_dtype == 0 && out_dtype == 1) return launch_ln<float, __nv_bfloat16>(a, stream);
+  if (in_dtype == 1 && out_dtype == 1) return launch_ln<__nv_bfloat16, __nv_bfloat16>(a, stream);
+  if (in_dtype == 0 && out_dtype == 0) return launch_ln<float, float>(a, stream);
+  if (in_dtype == 1 && out_dtype == 0) return launch_ln<__nv_bfloat16, float>(a, stream);
+  return OPB_ERR_INVALID;
+}
+
+}  // namespace opb
