@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement for the ONE-PEACE hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm: sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: the CPU path on host cores)
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on at one GPU):
+    ONE-PEACE 4B vision-branch forward — `extract_image_features` on 64 synthetic 224x224 images per GPU:
+    hMLP stem -> 40 x (d=1536, h=24, ffn=6144) encoder layers -> CLS LayerNorm -> image_proj -> L2 norm.
+    bf16 operands / fp32 accumulate / fp32 residual stream.  Random-init weights of that architecture,
+    synthetic inputs (no network for checkpoints or datasets).
+A "step" is one such forward over one batch.  N > 1 = N independent data-parallel replicas (inference has
+no exchange step: "replicas only", weak scaling); value = all samples / max-over-ranks device time.
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract; `roofline` describes the dominant
+kernel (the tcgen05 GEMM), `cpu_baseline` the oracle port timed on the host cores, `e2e` the same metric
+through the public API with pinned-host inputs (H2D + forward + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64
+RES = 224
+LAYERS, D, H, FFN = 40, 1536, 24, 6144
+SEQ = (RES // 16) ** 2 + 1
+METRIC = "encoder_samples_per_sec"
+UNIT = "samples/s"
+
+
+def flops_per_sample():
+    """8d^2 + 6df + 4Sd per token per layer (+1.97 GFLOP hMLP stem)."""
+    per_tok = 8 * D * D + 6 * D * FFN + 4 * SEQ * D
+    return LAYERS * SEQ * per_tok + 1.97e9
+
+
+def workload_config(n):
+    return {
+        "workload": "ONE-PEACE 4B vision-branch forward (extract_image_features): 64 x 3x224x224 per GPU, "
+                    "40 layers d=1536 h=24 ffn=6144, S=197",
+        "global_batch": BATCH * n, "seq_len": SEQ, "parallelism": f"dp{n} (independent replicas, no collective)",
+        "l2": "no flush needed: one step streams 3.0 GB of bf16 weights + ~0.6 GB activations per layer group, "
+              ">> 126 MB L2",
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def build_model(device):
+    import torch
+    from one_peace_b200.one_peace import OnePeaceRetrievalConfig, OnePeaceRetrievalModel
+    from one_peace_b200.unify_model_config import one_peace_4b_encoder_config
+    cfg = OnePeaceRetrievalConfig()
+    cfg.encoder = one_peace_4b_encoder_config(layers=LAYERS, embed_dim=D, ffn_embed_dim=FFN, attention_heads=H,
+                                              patch_image_size=RES)
+    torch.manual_seed(0)
+    with torch.device(device):
+        model = OnePeaceRetrievalModel(cfg, None, "image")
+        # LayerScale at 1e-6 makes a fresh 4B model an identity map; use O(1) gammas and non-zero relpos
+        # tables so the benchmark arithmetic is the same as with trained weights (timing is unaffected)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if "gamma_" in n:
+                    p.fill_(0.1)
+                elif "rel_pos_table" in n:
+                    p.normal_(0, 0.1)
+    model.eval()
+    return model
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from one_peace_b200 import kernels as K
+    from one_peace_b200.one_peace.hub_interface import OnePeaceHubInterface
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = build_model(dev)
+    hub = OnePeaceHubInterface(model, device=dev)
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_images = torch.randn(BATCH, 3, RES, RES, generator=g).pin_memory()
+    dev_images = host_images.to(dev, non_blocking=True)
+    host_out = torch.empty(BATCH, D, dtype=torch.float32).pin_memory()
+
+    def step_core():
+        with torch.no_grad():
+            return model(src_images=dev_images, encoder_type="image")
+
+    def step_e2e():
+        # public API: host images in, host embeddings out
+        return hub.extract_image_features(host_images, out=host_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = K.LAUNCHES
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler is not None else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, K.LAUNCHES - l0, clocks
+
+    warmup = max(3, args.warmup)
+    ms, launches, clocks = timed(step_core, args.steps, warmup, ClockSampler(local_rank) if rank == 0 else None)
+    value = BATCH * world * args.steps / (ms / 1e3)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, warmup)
+    e2e_value = BATCH * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel device times (CUDA events on the launching stream) for the roofline block ----
+    roof = None
+    if rank == 0:
+        recs = []
+        state = {}
+
+        def hook(kind, flops, shape):
+            if kind == "gemm_begin":
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                state["e0"] = ev
+            else:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                recs.append((state.pop("e0"), ev, flops, shape))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        K.PROFILE_HOOK = hook
+        e0.record()
+        step_core()
+        e1.record()
+        K.PROFILE_HOOK = None
+        torch.cuda.synchronize()
+        step_ms = e0.elapsed_time(e1)
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        gemm_flops = sum(f for _, _, f, _ in recs)
+        by_shape = {}
+        for a, b, f, shp in recs:
+            d = by_shape.setdefault(str(shp), [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += f; d[2] += 1
+        pk, pk_src = peaks()
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all four encoder GEMM shapes + stem/proj)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "peak_source": pk_src + ", sustained figure (kernel timed inside a long step)", "traffic": None,
+                "launches": len(recs), "avg_launch_ms": round(gemm_ms / max(1, len(recs)), 4),
+                "gemm_share_of_step": round(gemm_ms / step_ms, 4),
+                "per_shape_tflops": {k: round(v[1] / (v[0] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
+                "whole_step_tflops": round(flops_per_sample() * BATCH / (ms / args.steps / 1e3) / 1e12, 1)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(steps=1, warmup=0, sample_images=2)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "h2d_bytes_per_step": host_images.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
+            "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (oracle/restated.py) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, sample_images):
+    """Times the CPU restatement of the reference path (fp32, all host threads) on a bounded sample of the same
+    workload: `sample_images` images through the full 40-layer vision branch.  /root/reference does not exist
+    on the GPU box and the reference cannot be pip-installed (Python 3.12, missing omegaconf/hydra/...), so this
+    is kind = "port" (the restatement is pinned to the reference by tests/test_oracle_golden.py)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restated as R
+    import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # distinct weights for 4 layers, cycled over the 40 (6 GB of fp32 weights would take minutes to draw)
+    distinct = 4
+    sd = synth.make_state_dict(embed_dim=D, ffn=FFN, layers=distinct, heads=H, modalities=("image",), seed=0)
+    for i in range(distinct, LAYERS):
+        for k in [k for k in sd if f"layers.{i % distinct}." in k]:
+            sd[k.replace(f"layers.{i % distinct}.", f"layers.{i}.")] = sd[k]
+    cfg = R.OracleConfig(embed_dim=D, ffn_embed_dim=FFN, layers=LAYERS, attention_heads=H)
+    img = torch.randn(sample_images, 3, RES, RES, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        for _ in range(warmup):
+            R.extract_features(sd, cfg, "image", src_images=img)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            R.extract_features(sd, cfg, "image", src_images=img)
+        dt = time.perf_counter() - t0
+    v = sample_images * steps / dt
+    return {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_images} images x {steps} step(s) through the full 40-layer fp32 vision branch "
+                      f"(oracle/restated.py, torch CPU ops, {cores} threads; layer weights cycled over {distinct} distinct sets)",
+            "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.gpus
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    r = cpu_reference(steps=steps, warmup=warmup, sample_images=2)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n, "steps": steps,
+            "warmup": warmup, "ms_per_step": round(1e3 * r["seconds"] / steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+            "cpu_baseline": r, "gpu_launches": 0,
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

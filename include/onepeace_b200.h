@@ -83,6 +83,91 @@ int opb_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int ou
                   const float* gamma, const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w,
                   void* stream);
 
+/*
+ * Text adapter front end: x[b,0,:] = cls + pos[0]; x[b,1+t,:] = embed[tok[b,t]] + pos[1+t]; rows of padded
+ * tokens are zeroed and flagged in pad_mask.  Replaces models/adapter/text.py:125-129,144-146,153 and the
+ * pad zeroing of models/transformer/transformer_encoder.py:139-142.
+ *   tokens int64 [B,T]; table [V,D] (table_dtype OPB_F32/OPB_BF16); pos fp32 [>=T+1, D]; cls fp32 [D]
+ *   x fp32 [B, T+1, D]; pad_mask uint8 [B, T+1]
+ */
+int opb_text_embed(const int64_t* tokens, const void* table, int table_dtype, const float* pos, const float* cls,
+                   float* x, uint8_t* pad_mask, int B, int T, int D, int pad_idx, void* stream);
+
+/*
+ * im2col of the 4x4 / stride-4 stem convolution (models/adapter/image.py:67):
+ * out[(b,oy,ox), (c,ky,kx)] = img[b,c,4oy+ky,4ox+kx], bf16 [B*(R/4)^2, 48]; img [B,3,R,R] fp32 or bf16.
+ */
+int opb_image_patchify4(const void* img, int img_dtype, void* out, int B, int R, void* stream);
+
+/* x[b, 0, :] = cls + pos0 for every batch element (image.py:239-240,253; audio.py:195-197). */
+int opb_cls_row_init(const float* cls, const float* pos0, float* x, int64_t batch_stride, int B, int D,
+                     void* stream);
+
+/*
+ * Relative-position bias for one forward: bias[h,i,j] = table[bucket[i*ld_bucket + j], h], i,j < S, written as
+ * fp32 [H, S, s_pad] (zero padded columns).  Replaces get_rel_pos_bias (text.py:84-91, image.py:164-171,
+ * audio.py:124-131) and the per-batch expansion in transformer_encoder.py:144-158.
+ */
+int opb_relpos_bias_build(const float* table, const int64_t* bucket, float* bias, int S, int s_pad, int H,
+                          int64_t ld_bucket, void* stream);
+
+/*
+ * im2col of the first wav2vec conv (k=10, s=5, C_in=1; models/adapter/audio.py:270-284):
+ * out[(b,t), j] = wav[b, 5t+j] (j<10), zero padded to 16 columns, bf16 [B*pitch, 16]; wav [B, n_samples].
+ */
+int opb_audio_frame10(const void* wav, int wav_dtype, void* out, int B, int64_t n_samples, int64_t pitch,
+                      void* stream);
+
+/* y = x / max(||x||_2, 1e-12) per row (one_peace_retrieval.py:116); y fp32 [rows,D], optional bf16 copy. */
+int opb_l2_normalize_rows(const float* x, int64_t ldx, float* y, void* y_bf16, int rows, int D, void* stream);
+
+/* x[row,:] = 0 where pad_mask[row] (transformer_encoder.py:139-142). */
+int opb_zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, void* stream);
+
+/* bf16 [rows, cols] -> [cols, rows] (used to lay the gathered embeddings out K-major for the gradient GEMM). */
+int opb_transpose_bf16(const void* in, void* out, int rows, int cols, void* stream);
+
+/*
+ * Cross-modal InfoNCE, one direction (criterions/image_text_retrieval_loss.py:91-112, :16-26; pretrain twin
+ * image_text_pretrain_loss.py:164-185).  a_local bf16 [b,d] (this rank's rows), b_all bf16 [n,d] (all ranks'
+ * rows of the other modality in rank-major order, detached), scale = device scalar exp(clamp(logit_scale)).
+ * Targets: row i -> column i + target_offset (target_offset = rank * b).
+ *   opb_infonce_ws_floats : size (floats) of the partial workspace `ws` for opb_infonce_rows
+ *   opb_infonce_rows      : row_lse / row_loss (label-smoothed NLL per row) / row_argmax, all [b]
+ *   opb_infonce_reduce    : out3 = {(mean(loss_a) + mean(loss_b)) / 2, #correct a->b, #correct b->a}
+ *   opb_infonce_grad      : grad_a fp32 [b,d] = d(loss)/d(a_local) (local rows only; no gradient to b_all, :30-38);
+ *                           bT_all bf16 [d,n] = b_all transposed; g_ws bf16 [b,n] scratch; ws_gz [ceil(n/256), b]
+ *   opb_infonce_dscale    : out[0] = d(loss)/d(logit_scale) from the two directions' ws_gz
+ */
+int64_t opb_infonce_ws_floats(int b, int n);
+int opb_infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d,
+                     int target_offset, float label_smoothing, float* ws, float* row_lse, float* row_loss,
+                     int* row_argmax, void* stream);
+int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argmax_a, const int* argmax_b, int b,
+                       int target_offset, float* out3, void* stream);
+int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
+                     const float* row_lse, int b, int n, int d, int target_offset, float label_smoothing,
+                     void* g_ws, float* ws_gz, float* grad_a, void* stream);
+int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream);
+
+/*
+ * Fused multi-tensor Adam (optim/adam.py:173-253 python form; optional fp32 master as optim/adam_fused.py:45-50)
+ * and global grad-norm + clip coefficient (optim/fp16_optimizer_memory_efficent.py:96-116, bf16 branch).
+ *   tensors       device array of n_tensors records {void* p; const void* g; float* m; float* v; float* master;
+ *                 int64 numel; int32 group, p_dtype, g_dtype, pad}  (64 bytes each)
+ *   chunk_tensor / chunk_off   device arrays [n_chunks]: tensor index and element offset of every 8192-element chunk
+ *   lr, wd, bias_corr          HOST arrays [n_groups <= 128]: lr*lr_scale, weight decay, sqrt(1-b2^t)/(1-b1^t)
+ *   grad_scale    device scalar multiplied into every gradient (NULL = 1): out2[1] of opb_grad_norm_clip
+ * opb_grad_norm_clip: out2[0] = multiply_factor * ||g||_2, out2[1] = multiply_factor * min(1, max_norm/(norm+1e-6))
+ * (max_norm <= 0: no clipping); `partial` is an [n_chunks] fp32 scratch.  Deterministic reduction order.
+ */
+int opb_adam_chunk_elems(void);
+int opb_adam_multi_step(const void* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
+                        const float* lr, const float* wd, const float* bias_corr, int n_groups, float beta1,
+                        float beta2, float eps, const float* grad_scale, void* stream);
+int opb_grad_norm_clip(const void* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
+                       float* partial, float multiply_factor, float max_norm, float* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

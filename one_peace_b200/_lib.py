@@ -24,6 +24,26 @@ SIGNATURES = {
                                   c_void_p]),
     "opb_layernorm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int,
                               c_float, c_int, c_int, c_void_p]),
+    "opb_text_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                               c_int, c_void_p]),
+    "opb_image_patchify4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "opb_cls_row_init": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "opb_relpos_bias_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "opb_audio_frame10": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "opb_l2_normalize_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "opb_zero_padded_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "opb_transpose_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "opb_infonce_ws_floats": (c_int64, [c_int, c_int]),
+    "opb_infonce_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "opb_infonce_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "opb_infonce_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "opb_infonce_dscale": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "opb_adam_chunk_elems": (c_int, []),
+    "opb_adam_multi_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                    c_float, c_float, c_void_p, c_void_p]),
+    "opb_grad_norm_clip": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None

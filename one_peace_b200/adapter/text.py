@@ -1,0 +1,80 @@
+"""Drop-in for ``TextAdapter`` (models/adapter/text.py:32-185): token embedding + learned absolute positions
++ CLS, and the log-bucket relative-position bias.  Same parameter / buffer names (cls_embedding,
+embed_tokens, embed_positions, rel_pos_table_list.N, rp_bucket)."""
+import math
+
+import torch
+
+from .. import kernels as K
+from ..components import Embedding, PackCache, f32, trunc_normal_
+
+
+def make_token_bucket_position(bucket_size, max_position):
+    """Log-spaced relative-position buckets — same index math as models/adapter/text.py:18-29 (int64)."""
+    context_pos = torch.arange(max_position, dtype=torch.long)[:, None]
+    memory_pos = torch.arange(max_position, dtype=torch.long)[None, :]
+    rel = context_pos - memory_pos
+    sign = torch.sign(rel)
+    mid = bucket_size // 2
+    abs_pos = torch.where((rel < mid) & (rel > -mid), mid - 1, torch.abs(rel))
+    log_pos = mid + torch.ceil(torch.log(abs_pos / mid) / math.log((max_position - 1) / mid) * (mid - 1)).long()
+    bucket_pos = torch.where(abs_pos.le(mid), rel, log_pos * sign).long()
+    return bucket_pos + bucket_size - 1
+
+
+class TextAdapter(torch.nn.Module):
+    def __init__(self, cfg, embed_dim, attention_heads, src_dict=None, num_layers=None):
+        super().__init__()
+        if cfg.layernorm_embedding or cfg.add_type_embedding or cfg.shrink_alpha != 1.0:
+            raise NotImplementedError("layernorm_embedding / add_type_embedding / shrink_alpha are off in the 4B config")
+        self.attention_heads = attention_heads
+        if src_dict is not None:
+            self.padding_idx = src_dict.pad()
+            self.embed_tokens = Embedding(len(src_dict), embed_dim, self.padding_idx)
+        else:
+            self.embed_tokens = None
+            self.padding_idx = 1
+        self.cls_embedding = torch.nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.embed_positions = Embedding(512 + 2, embed_dim)
+        if cfg.use_attn_bias:
+            num_rel_dis = 2 * cfg.bucket_size - 1
+            rp_bucket = make_token_bucket_position(cfg.bucket_size, max_position=1024)
+            rp_bucket[0, :] = num_rel_dis
+            rp_bucket[:, 0] = num_rel_dis + 1
+            rp_bucket[0, 0] = num_rel_dis + 2
+            self.register_buffer("rp_bucket", rp_bucket)
+            self.rel_pos_table_list = torch.nn.ModuleList(
+                [Embedding(num_rel_dis + 3, attention_heads, zero_init=True) for _ in range(num_layers or 1)])
+        else:
+            self.rel_pos_table_list = None
+        trunc_normal_(self.cls_embedding)
+        trunc_normal_(self.embed_positions.weight)
+        if self.embed_tokens is not None:
+            trunc_normal_(self.embed_tokens.weight)
+            torch.nn.init.constant_(self.embed_tokens.weight[self.padding_idx], 0)
+        self._cache = PackCache()
+
+    def _pack(self):
+        ps = [self.cls_embedding, self.embed_positions.weight] + \
+             ([t.weight for t in self.rel_pos_table_list] if self.rel_pos_table_list is not None else [])
+
+        def build():
+            return dict(cls=f32(self.cls_embedding).view(-1), pos=f32(self.embed_positions.weight),
+                        tables=[f32(t.weight) for t in self.rel_pos_table_list] if self.rel_pos_table_list is not None else None)
+        return self._cache.get(ps, build)
+
+    def get_rel_pos_bias(self, seq_len):
+        p = self._pack()
+        return [K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads) for t in p["tables"]]
+
+    def forward(self, src_tokens, preserve_ids=None, preserve_embed=None, mask_token=None):
+        """-> (x fp32 (B,T+1,d) with padded rows zeroed, padding_mask uint8 (B,T+1), [bias (H,S,S_pad)])"""
+        if preserve_ids is not None or preserve_embed is not None:
+            raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+        p = self._pack()
+        table = self.embed_tokens.weight.detach()
+        if table.dtype not in (torch.float32, torch.bfloat16):
+            table = table.float()
+        x, pad = K.text_embed(src_tokens.contiguous(), table, p["pos"], p["cls"], self.padding_idx)
+        bias = self.get_rel_pos_bias(src_tokens.size(1) + 1) if self.rel_pos_table_list is not None else None
+        return x, pad, bias

@@ -55,4 +55,100 @@ int opb_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int ou
                         merge_grid_w, static_cast<cudaStream_t>(stream));
 }
 
+int opb_text_embed(const int64_t* tokens, const void* table, int table_dtype, const float* pos, const float* cls,
+                   float* x, uint8_t* pad_mask, int B, int T, int D, int pad_idx, void* stream) {
+  if (!tokens || !table || !pos || !cls || !x || !pad_mask) return OPB_ERR_INVALID;
+  return opb::text_embed(tokens, table, table_dtype, pos, cls, x, pad_mask, B, T, D, pad_idx,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int opb_image_patchify4(const void* img, int img_dtype, void* out, int B, int R, void* stream) {
+  if (!img || !out) return OPB_ERR_INVALID;
+  return opb::image_patchify4(img, img_dtype, out, B, R, static_cast<cudaStream_t>(stream));
+}
+
+int opb_cls_row_init(const float* cls, const float* pos0, float* x, int64_t batch_stride, int B, int D,
+                     void* stream) {
+  if (!cls || !pos0 || !x) return OPB_ERR_INVALID;
+  return opb::cls_row_init(cls, pos0, x, batch_stride, B, D, static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_bias_build(const float* table, const int64_t* bucket, float* bias, int S, int s_pad, int H,
+                          int64_t ld_bucket, void* stream) {
+  if (!table || !bucket || !bias) return OPB_ERR_INVALID;
+  return opb::relpos_bias_build(table, bucket, bias, S, s_pad, H, ld_bucket, static_cast<cudaStream_t>(stream));
+}
+
+int opb_audio_frame10(const void* wav, int wav_dtype, void* out, int B, int64_t n_samples, int64_t pitch,
+                      void* stream) {
+  if (!wav || !out) return OPB_ERR_INVALID;
+  return opb::audio_frame10(wav, wav_dtype, out, B, n_samples, pitch, static_cast<cudaStream_t>(stream));
+}
+
+int opb_l2_normalize_rows(const float* x, int64_t ldx, float* y, void* y_bf16, int rows, int D, void* stream) {
+  if (!x || !y) return OPB_ERR_INVALID;
+  return opb::l2_normalize_rows(x, ldx, y, y_bf16, rows, D, static_cast<cudaStream_t>(stream));
+}
+
+int opb_zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, void* stream) {
+  if (!x || !pad_mask) return OPB_ERR_INVALID;
+  return opb::zero_padded_rows(x, pad_mask, rows, D, static_cast<cudaStream_t>(stream));
+}
+
+int opb_transpose_bf16(const void* in, void* out, int rows, int cols, void* stream) {
+  if (!in || !out) return OPB_ERR_INVALID;
+  return opb::transpose_bf16(in, out, rows, cols, static_cast<cudaStream_t>(stream));
+}
+
+int64_t opb_infonce_ws_floats(int b, int n) { return opb::infonce_ws_floats(b, n); }
+
+int opb_infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d,
+                     int target_offset, float label_smoothing, float* ws, float* row_lse, float* row_loss,
+                     int* row_argmax, void* stream) {
+  if (!a_local || !b_all || !scale || !ws || !row_lse || !row_loss || !row_argmax) return OPB_ERR_INVALID;
+  return opb::infonce_rows(a_local, b_all, scale, b, n, d, target_offset, label_smoothing, ws, row_lse, row_loss,
+                           row_argmax, static_cast<cudaStream_t>(stream));
+}
+
+int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argmax_a, const int* argmax_b, int b,
+                       int target_offset, float* out3, void* stream) {
+  if (!loss_a || !loss_b || !argmax_a || !argmax_b || !out3 || b <= 0) return OPB_ERR_INVALID;
+  return opb::infonce_reduce(loss_a, loss_b, argmax_a, argmax_b, b, target_offset, out3,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
+                     const float* row_lse, int b, int n, int d, int target_offset, float label_smoothing,
+                     void* g_ws, float* ws_gz, float* grad_a, void* stream) {
+  if (!a_local || !b_all || !bT_all || !scale || !row_lse || !g_ws || !ws_gz || !grad_a) return OPB_ERR_INVALID;
+  return opb::infonce_grad(a_local, b_all, bT_all, scale, row_lse, b, n, d, target_offset, label_smoothing, g_ws,
+                           ws_gz, grad_a, static_cast<cudaStream_t>(stream));
+}
+
+int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream) {
+  if (!ws_gz_a || !ws_gz_b || !out || b <= 0 || n <= 0) return OPB_ERR_INVALID;
+  return opb::infonce_dscale(ws_gz_a, ws_gz_b, b, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int opb_adam_chunk_elems(void) { return 8192; }
+
+int opb_adam_multi_step(const void* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
+                        const float* lr, const float* wd, const float* bias_corr, int n_groups, float beta1,
+                        float beta2, float eps, const float* grad_scale, void* stream) {
+  if (!tensors || !chunk_tensor || !chunk_off || !lr || !wd || !bias_corr) return OPB_ERR_INVALID;
+  if (n_groups <= 0 || n_groups > opb::kAdamMaxGroups) return OPB_ERR_UNSUPPORTED;
+  opb::AdamGroups g;
+  for (int i = 0; i < n_groups; ++i) { g.lr[i] = lr[i]; g.wd[i] = wd[i]; g.bias_corr[i] = bias_corr[i]; }
+  g.beta1 = beta1; g.beta2 = beta2; g.eps = eps;
+  return opb::adam_multi_step(tensors, chunk_tensor, reinterpret_cast<const long*>(chunk_off), n_chunks, g, grad_scale,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int opb_grad_norm_clip(const void* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
+                       float* partial, float multiply_factor, float max_norm, float* out2, void* stream) {
+  if (!tensors || !chunk_tensor || !chunk_off || !partial || !out2) return OPB_ERR_INVALID;
+  return opb::grad_norm_clip(tensors, chunk_tensor, reinterpret_cast<const long*>(chunk_off), n_chunks, partial,
+                             multiply_factor, max_norm, out2, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

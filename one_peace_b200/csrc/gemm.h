@@ -11,6 +11,9 @@ enum GemmEpi : int {
   EPI_RESID_F32 = 2,   // out_f32 = resid + gamma * (acc + bias)
   EPI_STORE_F32 = 3,   // out_f32 = acc + bias
   EPI_GELU_BF16 = 4,   // out_bf16 = gelu((acc + bias) * colscale)
+  // contrastive head (criterions/image_text_retrieval_loss.py:91-112), z = scale * acc:
+  EPI_LSE_PARTIAL = 5,   // per (row, 256-col tile): running max / sum-exp / sum z / arg-max / target logit -> ws
+  EPI_SOFTMAX_GRAD = 6,  // out_bf16 = coef*scale * (exp(z - lse[row]) - (1-eps-eps_i)[col==target] - eps_i); sum_j g*z -> ws
 };
 
 struct GemmEpilogue {
@@ -28,6 +31,14 @@ struct GemmEpilogue {
   // optional broadcast residual: resid_row = (m % resid_period) + resid_row_offset
   int resid_period = 0;
   int resid_row_offset = 0;
+  // contrastive-head epilogues
+  const float* scale_ptr = nullptr;  // device scalar: exp(clamp(logit_scale))
+  const float* row_lse = nullptr;    // [M] log-sum-exp per row (EPI_SOFTMAX_GRAD)
+  float* ws = nullptr;               // EPI_LSE_PARTIAL: [n_tiles, M, 8];  EPI_SOFTMAX_GRAD: [n_tiles, M]
+  int target_offset = 0;             // target column of row m is m + target_offset (rank * local batch)
+  float eps = 0.f;                   // label smoothing
+  float eps_i = 0.f;                 // eps / (N - 1)
+  float coef = 1.f;                  // 1 / (2 b)
 };
 
 // C = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major with pitches lda, ldb (elements).

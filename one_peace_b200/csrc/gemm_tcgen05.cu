@@ -208,6 +208,93 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
         }
+      } else if constexpr (EPI == EPI_LSE_PARTIAL) {
+        // z = scale * acc.  Each thread owns one row of the tile: all reductions are thread-local.
+        const float scale = *ep.scale_ptr;
+        const int col0 = n_blk * kBlockN;
+        const int tgt = row + ep.target_offset;
+        float m = -INFINITY, ssum = 0.f, zsum = 0.f, best = -INFINITY, ztgt = 0.f;
+        int best_idx = 0;
+        bool has_tgt = false;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (c + 32 == kBlockN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+          }
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + c + j;
+            const float z = (col < N) ? scale * __uint_as_float(v[j]) : -INFINITY;
+            v[j] = __float_as_uint(z);
+            cm = fmaxf(cm, z);
+            if (z > best) { best = z; best_idx = col; }
+            if (col == tgt) { ztgt = z; has_tgt = true; }
+          }
+          if (cm > -INFINITY) {
+            const float mn = fmaxf(m, cm);
+            float add = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float z = __uint_as_float(v[j]);
+              if (z > -INFINITY) { add += __expf(z - mn); zsum += z; }
+            }
+            ssum = ssum * __expf(m - mn) + add;
+            m = mn;
+          }
+        }
+        if (row_ok) {
+          float* w = ep.ws + (static_cast<long>(n_blk) * M + row) * 8;
+          *reinterpret_cast<float4*>(w) = make_float4(m, ssum, zsum, best);
+          *reinterpret_cast<float4*>(w + 4) = make_float4(__int_as_float(best_idx), ztgt, has_tgt ? 1.f : 0.f, 0.f);
+        }
+      } else if constexpr (EPI == EPI_SOFTMAX_GRAD) {
+        const float scale = *ep.scale_ptr;
+        const float gscale = scale * ep.coef;
+        const int col0 = n_blk * kBlockN;
+        const int tgt = row + ep.target_offset;
+        const float lse = row_ok ? ep.row_lse[row] : 0.f;
+        const float hit = 1.f - ep.eps - ep.eps_i;
+        float gz = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (c + 32 == kBlockN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int col = col0 + c + j;
+            if (!row_ok || col >= N) continue;
+            float gq[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float z = scale * __uint_as_float(v[j + e]);
+              float g = __expf(z - lse) - ep.eps_i;
+              if (col + e == tgt) g -= hit;
+              gz += g * z;
+              gq[e] = g * gscale;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(gq[0], gq[1]);
+            o.y = pack_bf16x2(gq[2], gq[3]);
+            o.z = pack_bf16x2(gq[4], gq[5]);
+            o.w = pack_bf16x2(gq[6], gq[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + col) = o;
+          }
+        }
+        if (row_ok) ep.ws[static_cast<long>(n_blk) * M + row] = gz;
       } else {
         const int col0 = n_blk * kBlockN;
 #pragma unroll 1
@@ -383,6 +470,8 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
     case EPI_GEGLU_BF16: return launch_gemm<CGV, EPI_GEGLU_BF16>(ta, tb, ep, M, N, K, stream); \
     case EPI_RESID_F32: return launch_gemm<CGV, EPI_RESID_F32>(ta, tb, ep, M, N, K, stream);   \
     case EPI_STORE_F32: return launch_gemm<CGV, EPI_STORE_F32>(ta, tb, ep, M, N, K, stream);   \
+    case EPI_LSE_PARTIAL: return launch_gemm<CGV, EPI_LSE_PARTIAL>(ta, tb, ep, M, N, K, stream);   \
+    case EPI_SOFTMAX_GRAD: return launch_gemm<CGV, EPI_SOFTMAX_GRAD>(ta, tb, ep, M, N, K, stream); \
     default: return OPB_ERR_INVALID;                                                           \
   }
   if (cta_group == 1) { OPB_DISPATCH(1) } else { OPB_DISPATCH(2) }

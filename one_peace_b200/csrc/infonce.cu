@@ -1,0 +1,173 @@
+// Cross-modal InfoNCE head (criterions/image_text_retrieval_loss.py:91-112; pretrain twin
+// image_text_pretrain_loss.py:164-185).  For one direction with local rows A (b x d), gathered rows
+// B_all (n x d, n = world * b, detached) and s = exp(clamp(logit_scale)):
+//     Z = s * A B_all^T,  loss_i = (1-eps-eps_i) (lse_i - z_{i,t_i}) + eps_i (n lse_i - sum_j z_ij),  t_i = i + rank*b
+//     dL/dA = (s / 2b) G B_all,  G_ij = softmax(Z)_ij - (1-eps-eps_i) [j == t_i] - eps_i      (local rows only,
+//     no gradient to B_all: the gathers are detached, :30-38)
+// The b x n logits are never materialised in fp32: the tcgen05 GEMM epilogues reduce each 128x256 tile to
+// per-row partials (forward) or write the bf16 gradient factor G directly (backward), and a second GEMM
+// contracts G with B_all.  This file holds the small merge / reduction kernels and the host sequencing.
+#include "common.cuh"
+#include "gemm.h"
+#include "ops.h"
+
+namespace opb {
+
+// merge the per-tile partials of one direction: lse, loss and arg-max per row
+__global__ void infonce_merge_kernel(const float* __restrict__ ws, int n_tiles, int b, int n, float eps,
+                                     float* __restrict__ row_lse, float* __restrict__ row_loss,
+                                     int* __restrict__ row_argmax) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= b) return;
+  float m = -INFINITY;
+  for (int t = 0; t < n_tiles; ++t) m = fmaxf(m, ws[(static_cast<long>(t) * b + row) * 8]);
+  float s = 0.f, zsum = 0.f, best = -INFINITY, ztgt = 0.f;
+  int best_idx = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const float* w = ws + (static_cast<long>(t) * b + row) * 8;
+    const float4 p0 = *reinterpret_cast<const float4*>(w);
+    const float4 p1 = *reinterpret_cast<const float4*>(w + 4);
+    s += p0.y * __expf(p0.x - m);
+    zsum += p0.z;
+    if (p0.w > best) { best = p0.w; best_idx = __float_as_int(p1.x); }   // strict >: first maximum wins (torch.argmax)
+    if (p1.z != 0.f) ztgt = p1.y;
+  }
+  const float lse = m + logf(s);
+  const float nll = lse - ztgt;
+  float loss = nll;
+  if (eps != 0.f) {
+    const float eps_i = eps / (n - 1);
+    loss = (1.f - eps - eps_i) * nll + eps_i * (n * lse - zsum);
+  }
+  row_lse[row] = lse;
+  row_loss[row] = loss;
+  row_argmax[row] = best_idx;
+}
+
+// out[0] = (mean(loss_a) + mean(loss_b)) / 2, out[1] = #(argmax_a == target), out[2] = #(argmax_b == target)
+// single block, fixed summation order (deterministic across ranks / runs)
+__global__ void infonce_reduce_kernel(const float* __restrict__ loss_a, const float* __restrict__ loss_b,
+                                      const int* __restrict__ am_a, const int* __restrict__ am_b, int b,
+                                      int target_offset, float* __restrict__ out) {
+  __shared__ float red[3][32];
+  float la = 0.f, ca = 0.f, cb = 0.f;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    la += loss_a[i] + loss_b[i];
+    ca += (am_a[i] == i + target_offset) ? 1.f : 0.f;
+    cb += (am_b[i] == i + target_offset) ? 1.f : 0.f;
+  }
+  la = warp_sum(la); ca = warp_sum(ca); cb = warp_sum(cb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = la; red[1][warp] = ca; red[2][warp] = cb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    out[0] = t0 / (2.f * b);
+    out[1] = t1;
+    out[2] = t2;
+  }
+}
+
+// d(loss)/d(logit_scale) = coef * sum_ij G_ij z_ij over both directions (ws_a / ws_b: [n_tiles, b] partials)
+__global__ void infonce_dscale_kernel(const float* __restrict__ ws_a, const float* __restrict__ ws_b, long count,
+                                      float coef, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long i = threadIdx.x; i < count; i += blockDim.x) acc += ws_a[i] + ws_b[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    out[0] = t * coef;
+  }
+}
+
+// bf16 [rows, cols] -> [cols, rows] through a padded smem tile (coalesced both ways)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
+                                      int cols) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int r = r0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      const int c = c0 + j;
+      tile[i][j] = (r < rows && c < cols) ? in[static_cast<long>(r) * cols + c] : __float2bfloat16(0.f);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int c = c0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      const int r = r0 + j;
+      if (r < rows && c < cols) out[static_cast<long>(c) * rows + r] = tile[j][i];
+    }
+  }
+}
+
+int transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return OPB_ERR_INVALID;
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                    reinterpret_cast<__nv_bfloat16*>(out), rows, cols);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+static int n_tiles_of(int n) { return (n + 255) / 256; }
+
+long infonce_ws_floats(int b, int n) { return static_cast<long>(n_tiles_of(n)) * b * 8; }
+
+// forward for one direction: row_lse / row_loss / row_argmax
+int infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
+                 float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0) return OPB_ERR_INVALID;
+  GemmEpilogue ep;
+  ep.out = ws;            // unused by this epilogue but must be non-null for the generic checks
+  ep.scale_ptr = scale;
+  ep.ws = ws;
+  ep.target_offset = target_offset;
+  int rc = gemm_bf16(a_local, d, b_all, d, b, n, d, EPI_LSE_PARTIAL, ep, 0, stream);
+  if (rc != OPB_OK) return rc;
+  infonce_merge_kernel<<<(b + 127) / 128, 128, 0, stream>>>(ws, n_tiles_of(n), b, n, eps, row_lse, row_loss,
+                                                            row_argmax);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int infonce_reduce(const float* loss_a, const float* loss_b, const int* am_a, const int* am_b, int b,
+                   int target_offset, float* out3, cudaStream_t stream) {
+  infonce_reduce_kernel<<<1, 1024, 0, stream>>>(loss_a, loss_b, am_a, am_b, b, target_offset, out3);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// backward for one direction: grad_a fp32 [b, d] = (s / 2b) G B_all ; ws_gz [n_tiles, b] row partials of sum G z
+int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
+                 const float* row_lse, int b, int n, int d, int target_offset, float eps, void* g_ws, float* ws_gz,
+                 float* grad_a, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0) return OPB_ERR_INVALID;
+  GemmEpilogue ep;
+  ep.out = g_ws;
+  ep.ldo = n;
+  ep.scale_ptr = scale;
+  ep.row_lse = row_lse;
+  ep.ws = ws_gz;
+  ep.target_offset = target_offset;
+  ep.eps = eps;
+  ep.eps_i = (eps != 0.f) ? eps / (n - 1) : 0.f;
+  ep.coef = 1.f / (2.f * b);
+  int rc = gemm_bf16(a_local, d, b_all, d, b, n, d, EPI_SOFTMAX_GRAD, ep, 0, stream);
+  if (rc != OPB_OK) return rc;
+  GemmEpilogue e2;
+  e2.out = grad_a;
+  e2.ldo = d;
+  return gemm_bf16(g_ws, n, bT_all, n, b, d, n, EPI_STORE_F32, e2, 0, stream);
+}
+
+int infonce_dscale(const float* ws_a, const float* ws_b, int b, int n, float* out, cudaStream_t stream) {
+  infonce_dscale_kernel<<<1, 1024, 0, stream>>>(ws_a, ws_b, static_cast<long>(n_tiles_of(n)) * b, 1.f / (2.f * b),
+                                               out);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+}  // namespace opb

@@ -11,4 +11,50 @@ int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, vo
 int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const float* gamma,
               const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, cudaStream_t stream);
 
+int text_embed(const int64_t* tokens, const void* table, int table_dtype, const float* pos, const float* cls,
+               float* x, uint8_t* pad_mask, int B, int T, int D, int pad_idx, cudaStream_t stream);
+int image_patchify4(const void* img, int img_dtype, void* out, int B, int R, cudaStream_t stream);
+int cls_row_init(const float* cls, const float* pos0, float* x, long batch_stride, int B, int D, cudaStream_t stream);
+int relpos_bias_build(const float* table, const int64_t* bucket, float* bias, int S, int s_pad, int H,
+                      long ld_bucket, cudaStream_t stream);
+int audio_frame10(const void* wav, int wav_dtype, void* out, int B, long n_samples, long pitch, cudaStream_t stream);
+int l2_normalize_rows(const float* x, long ldx, float* y, void* y_bf16, int rows, int D, cudaStream_t stream);
+int zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, cudaStream_t stream);
+
+int transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t stream);
+long infonce_ws_floats(int b, int n);
+int infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
+                 float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, cudaStream_t stream);
+int infonce_reduce(const float* loss_a, const float* loss_b, const int* am_a, const int* am_b, int b,
+                   int target_offset, float* out3, cudaStream_t stream);
+int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
+                 const float* row_lse, int b, int n, int d, int target_offset, float eps, void* g_ws, float* ws_gz,
+                 float* grad_a, cudaStream_t stream);
+int infonce_dscale(const float* ws_a, const float* ws_b, int b, int n, float* out, cudaStream_t stream);
+
+// One entry per parameter tensor (device-resident table, 64 bytes; mirrored by ctypes in optim/adam_fused.py)
+struct AdamTensor {
+  void* p;         // parameter (fp32 or bf16)
+  const void* g;   // gradient (fp32 or bf16)
+  float* m;        // exp_avg
+  float* v;        // exp_avg_sq
+  float* master;   // optional fp32 master copy (nullptr: up-cast p)
+  long numel;
+  int group;
+  int p_dtype;     // 0 fp32, 1 bf16
+  int g_dtype;
+  int pad_;
+};
+constexpr int kAdamMaxGroups = 128;
+struct AdamGroups {
+  float lr[kAdamMaxGroups];         // lr * lr_scale of the group (base_optimizer.py:8-13)
+  float wd[kAdamMaxGroups];
+  float bias_corr[kAdamMaxGroups];  // sqrt(1 - b2^t) / (1 - b1^t)
+  float beta1, beta2, eps;
+};
+int adam_multi_step(const void* tensors, const int* chunk_tensor, const long* chunk_off, int n_chunks,
+                    const AdamGroups& groups, const float* grad_scale, cudaStream_t stream);
+int grad_norm_clip(const void* tensors, const int* chunk_tensor, const long* chunk_off, int n_chunks, float* partial,
+                   float multiply_factor, float max_norm, float* out2, cudaStream_t stream);
+
 }  // namespace opb

@@ -11,6 +11,17 @@ F32, BF16 = 0, 1
 EPI_STORE_BF16, EPI_GEGLU_BF16, EPI_RESID_F32, EPI_STORE_F32, EPI_GELU_BF16 = 0, 1, 2, 3, 4
 
 
+# number of kernel launches issued through the C-ABI since import (bench.py reports it per step)
+LAUNCHES = 0
+# optional per-call profiler hook: bench.py installs a callable(name, flops) -> context manager
+PROFILE_HOOK = None
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -45,6 +56,8 @@ def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, ou
     if lda is None:
         lda = a.stride(0)
     N = w.shape[0]
+    if PROFILE_HOOK is not None:
+        PROFILE_HOOK("gemm_begin", 0.0, None)
     assert w.shape[1] == K and w.stride(1) == 1 and a.stride(-1) == 1
     ldr = resid.stride(-2) if resid is not None else 0
     st = _lib.load().opb_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), w.stride(0), M, N, K, epi, out.data_ptr(),
@@ -52,6 +65,9 @@ def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, ou
                                    out_group, out_group_stride, out_row_offset, resid_period, resid_row_offset,
                                    cta_group, _stream())
     _lib.check(st, "opb_gemm_bf16")
+    _count()
+    if PROFILE_HOOK is not None:
+        PROFILE_HOOK("gemm", 2.0 * M * N * K, (M, N, K, epi))
     return out
 
 
@@ -70,6 +86,7 @@ def attention(qkv, bias, key_pad, B, S, H, out=None, lse=None):
     st = _lib.load().opb_attention_fwd(qkv.data_ptr(), _ptr(bias), _ptr(key_pad), out.data_ptr(), _ptr(lse), B, S,
                                        H, s_pad, _stream())
     _lib.check(st, "opb_attention_fwd")
+    _count()
     return out
 
 
@@ -87,4 +104,156 @@ def layernorm(x, gamma, beta, out, *, rows=None, dim=None, ld_in=None, ld_out=No
     st = _lib.load().opb_layernorm(x.data_ptr(), _dt(x), ld_in, out.data_ptr(), _dt(out), ld_out, _ptr(gamma),
                                    _ptr(beta), rows, dim, eps, int(gelu), merge_grid_w, _stream())
     _lib.check(st, "opb_layernorm")
+    _count()
+    return out
+
+
+def text_embed(tokens, table, pos, cls, pad_idx=1):
+    """-> (x fp32 [B,T+1,D], pad_mask uint8 [B,T+1])"""
+    _need_cuda(tokens, table, pos, cls)
+    B, T = tokens.shape
+    D = table.shape[1]
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and table.is_contiguous()
+    assert pos.dtype == torch.float32 and cls.dtype == torch.float32 and pos.shape[0] >= T + 1
+    x = torch.empty(B, T + 1, D, dtype=torch.float32, device=tokens.device)
+    pad = torch.empty(B, T + 1, dtype=torch.uint8, device=tokens.device)
+    st = _lib.load().opb_text_embed(tokens.data_ptr(), table.data_ptr(), _dt(table), pos.data_ptr(), cls.data_ptr(),
+                                    x.data_ptr(), pad.data_ptr(), B, T, D, pad_idx, _stream())
+    _lib.check(st, "opb_text_embed")
+    _count()
+    return x, pad
+
+
+def image_patchify4(img):
+    _need_cuda(img)
+    B, C, R, R2 = img.shape
+    assert C == 3 and R == R2 and img.is_contiguous()
+    out = torch.empty(B * (R // 4) * (R // 4), 48, dtype=torch.bfloat16, device=img.device)
+    st = _lib.load().opb_image_patchify4(img.data_ptr(), _dt(img), out.data_ptr(), B, R, _stream())
+    _lib.check(st, "opb_image_patchify4")
+    _count()
+    return out
+
+
+def cls_row_init(cls, pos0, x):
+    """x fp32 [B,S,D]: x[:,0,:] = cls + pos0"""
+    _need_cuda(cls, pos0, x)
+    B, S, D = x.shape
+    st = _lib.load().opb_cls_row_init(cls.data_ptr(), pos0.data_ptr(), x.data_ptr(), S * D, B, D, _stream())
+    _lib.check(st, "opb_cls_row_init")
+    _count()
+    return x
+
+
+def relpos_bias_build(table, bucket, S, H):
+    """table fp32 [NB,H], bucket int64 [R,R] -> fp32 [H,S,s_pad]"""
+    _need_cuda(table, bucket)
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == H
+    assert bucket.dtype == torch.int64 and bucket.stride(1) == 1 and bucket.shape[0] >= S and bucket.shape[1] >= S
+    s_pad = (S + 7) // 8 * 8
+    bias = torch.empty(H, S, s_pad, dtype=torch.float32, device=table.device)
+    st = _lib.load().opb_relpos_bias_build(table.data_ptr(), bucket.data_ptr(), bias.data_ptr(), S, s_pad, H,
+                                           bucket.stride(0), _stream())
+    _lib.check(st, "opb_relpos_bias_build")
+    _count()
+    return bias
+
+
+def audio_frame10(wav, pitch, out):
+    _need_cuda(wav, out)
+    B, N = wav.shape
+    assert wav.is_contiguous()
+    st = _lib.load().opb_audio_frame10(wav.data_ptr(), _dt(wav), out.data_ptr(), B, N, pitch, _stream())
+    _lib.check(st, "opb_audio_frame10")
+    _count()
+    return out
+
+
+def l2_normalize_rows(x, want_bf16=False):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    rows, D = x.shape
+    y = torch.empty(rows, D, dtype=torch.float32, device=x.device)
+    y16 = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    st = _lib.load().opb_l2_normalize_rows(x.data_ptr(), x.stride(0), y.data_ptr(), _ptr(y16), rows, D, _stream())
+    _lib.check(st, "opb_l2_normalize_rows")
+    _count()
+    return (y, y16) if want_bf16 else y
+
+
+def zero_padded_rows(x, pad_mask):
+    _need_cuda(x, pad_mask)
+    D = x.shape[-1]
+    rows = x.numel() // D
+    assert x.dtype == torch.float32 and x.is_contiguous() and pad_mask.dtype == torch.uint8 and pad_mask.numel() == rows
+    st = _lib.load().opb_zero_padded_rows(x.data_ptr(), pad_mask.data_ptr(), rows, D, _stream())
+    _lib.check(st, "opb_zero_padded_rows")
+    _count()
+    return x
+
+
+# ----------------------------------------------------------------------------------------------------
+# contrastive head
+# ----------------------------------------------------------------------------------------------------
+def transpose_bf16(x):
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 2
+    out = torch.empty(x.shape[1], x.shape[0], dtype=torch.bfloat16, device=x.device)
+    st = _lib.load().opb_transpose_bf16(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream())
+    _lib.check(st, "opb_transpose_bf16")
+    _count()
+    return out
+
+
+def infonce_rows(a_local, b_all, scale, target_offset, eps):
+    """One direction of the InfoNCE forward.  a_local bf16 [b,d], b_all bf16 [n,d], scale fp32 device scalar.
+    -> (row_lse [b], row_loss [b], row_argmax int32 [b])"""
+    _need_cuda(a_local, b_all, scale)
+    b, d = a_local.shape
+    n = b_all.shape[0]
+    assert a_local.dtype == torch.bfloat16 and b_all.dtype == torch.bfloat16 and scale.dtype == torch.float32
+    assert a_local.is_contiguous() and b_all.is_contiguous() and b_all.shape[1] == d
+    lib = _lib.load()
+    dev = a_local.device
+    ws = torch.empty(lib.opb_infonce_ws_floats(b, n), dtype=torch.float32, device=dev)
+    lse = torch.empty(b, dtype=torch.float32, device=dev)
+    loss = torch.empty(b, dtype=torch.float32, device=dev)
+    amax = torch.empty(b, dtype=torch.int32, device=dev)
+    st = lib.opb_infonce_rows(a_local.data_ptr(), b_all.data_ptr(), scale.data_ptr(), b, n, d, target_offset, eps,
+                              ws.data_ptr(), lse.data_ptr(), loss.data_ptr(), amax.data_ptr(), _stream())
+    _lib.check(st, "opb_infonce_rows")
+    _count(2)
+    return lse, loss, amax
+
+
+def infonce_reduce(loss_a, loss_b, am_a, am_b, target_offset):
+    out = torch.empty(3, dtype=torch.float32, device=loss_a.device)
+    st = _lib.load().opb_infonce_reduce(loss_a.data_ptr(), loss_b.data_ptr(), am_a.data_ptr(), am_b.data_ptr(),
+                                        loss_a.numel(), target_offset, out.data_ptr(), _stream())
+    _lib.check(st, "opb_infonce_reduce")
+    _count()
+    return out
+
+
+def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps):
+    """-> (grad_a fp32 [b,d], ws_gz) for one direction"""
+    b, d = a_local.shape
+    n = b_all.shape[0]
+    dev = a_local.device
+    g_ws = torch.empty(b, n, dtype=torch.bfloat16, device=dev)
+    ws_gz = torch.empty((n + 255) // 256 * b, dtype=torch.float32, device=dev)
+    grad = torch.empty(b, d, dtype=torch.float32, device=dev)
+    st = _lib.load().opb_infonce_grad(a_local.data_ptr(), b_all.data_ptr(), bT_all.data_ptr(), scale.data_ptr(),
+                                      row_lse.data_ptr(), b, n, d, target_offset, eps, g_ws.data_ptr(),
+                                      ws_gz.data_ptr(), grad.data_ptr(), _stream())
+    _lib.check(st, "opb_infonce_grad")
+    _count(2)
+    return grad, ws_gz
+
+
+def infonce_dscale(ws_a, ws_b, b, n):
+    out = torch.empty(1, dtype=torch.float32, device=ws_a.device)
+    st = _lib.load().opb_infonce_dscale(ws_a.data_ptr(), ws_b.data_ptr(), b, n, out.data_ptr(), _stream())
+    _lib.check(st, "opb_infonce_dscale")
+    _count()
     return out

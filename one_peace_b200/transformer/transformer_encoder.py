@@ -1,0 +1,71 @@
+"""Drop-in for ``TransformerEncoder`` (models/transformer/transformer_encoder.py:23-251).
+
+Same constructor, same parameter names (layers.N.*, {text,image,audio}_layer_norm).  ``forward`` keeps
+the reference signature (text_info / image_info / audio_info tuples from the adapters + encoder_type);
+the tuples carry the fp32 residual stream (B,S,d), a uint8/bool padding mask (or None) and the
+batch-shared (H,S,S_pad) bias table instead of the reference's expanded (B,H,S,S) tensor.
+"""
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from ..components import LayerNorm, PackCache, f32
+from ..fairseq_compat import FairseqEncoder
+from .transformer_layer import TransformerEncoderLayer
+
+
+class TransformerEncoder(FairseqEncoder):
+    def __init__(self, cfg, dictionary, use_text_norm, use_image_norm, use_audio_norm):
+        self.cfg = cfg
+        super().__init__(dictionary)
+        self.register_buffer("version", torch.Tensor([3]))
+        if cfg.layerdrop > 0.0:
+            raise NotImplementedError("layerdrop is 0 in every ONE-PEACE config")
+        self.max_positions = cfg.max_positions
+        self.num_attention_heads = cfg.attention_heads
+        dpr = [x.item() for x in torch.linspace(0, cfg.drop_path_rate, cfg.layers)]
+        self.layers = nn.ModuleList([TransformerEncoderLayer(cfg, drop_path_rate=dpr[i]) for i in range(cfg.layers)])
+        self.num_layers = len(self.layers)
+        self.text_layer_norm = LayerNorm(cfg.embed_dim) if (cfg.use_text_moe and use_text_norm) else None
+        self.image_layer_norm = LayerNorm(cfg.embed_dim) if (cfg.use_image_moe and use_image_norm) else None
+        self.audio_layer_norm = LayerNorm(cfg.embed_dim) if (cfg.use_audio_moe and use_audio_norm) else None
+        self._cache = PackCache()
+
+    def final_norm_pack(self, modality):
+        ln = getattr(self, f"{modality}_layer_norm")
+        if ln is None:
+            return None
+        return f32(ln.weight), f32(ln.bias), ln.eps
+
+    def run_layers(self, info, encoder_type):
+        """Runs the 40-layer hot loop in place on the residual stream; returns (x [B,S,d] fp32, pad)."""
+        if encoder_type not in ("text", "image", "audio"):
+            # 'vl' / 'al' (concatenated sequences with per-modality FFN) belong to the pretraining path
+            raise NotImplementedError(f"encoder_type={encoder_type!r}: only single-modality encoders are built")
+        x, pad, bias_list = info
+        B, S, d = x.shape
+        x = x.contiguous()
+        key_pad = None
+        if pad is not None:
+            key_pad = pad.to(torch.uint8).contiguous()
+        rows = x.view(B * S, d)
+        for idx, layer in enumerate(self.layers):
+            bias = None
+            if bias_list:
+                bias = bias_list[0] if len(bias_list) == 1 else bias_list[idx]
+            layer.forward_rows(rows, bias, key_pad, B, S, encoder_type)
+        return x, pad
+
+    def forward(self, text_info, image_info, audio_info, return_all_hiddens: bool = False, encoder_type=None):
+        if return_all_hiddens:
+            raise NotImplementedError("return_all_hiddens is only used by the segmentation/detection heads")
+        info = {"text": text_info, "image": image_info, "audio": audio_info}.get(encoder_type)
+        x, pad = self.run_layers(info, encoder_type)
+        B, S, d = x.shape
+        pk = self.final_norm_pack(encoder_type)
+        if pk is not None:
+            out = torch.empty_like(x)
+            K.layernorm(x.view(B * S, d), pk[0], pk[1], out.view(B * S, d), eps=pk[2])
+            x = out
+        return {"encoder_out": [x.transpose(0, 1)], "encoder_padding_mask": pad, "text_encoder_states": [],
+                "image_encoder_states": [], "audio_encoder_states": []}

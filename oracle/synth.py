@@ -1,0 +1,130 @@
+"""TEST INFRASTRUCTURE.  Deterministic synthetic weights and inputs shared by the golden-vector
+generator (oracle/make_golden.py, build container), the CPU oracle tests and the GPU parity tests, so the
+fixtures under tests/golden/ only need to hold OUTPUTS.  Everything is drawn from a seeded CPU
+``torch.Generator`` in a fixed key order (same torch build here and on the GPU box).
+
+``make_state_dict`` produces exactly the parameter names / shapes of the reference
+``OnePeaceRetrievalModel`` (SURVEY.md §8a list; make_golden.py loads it with strict=True into the
+reference model, which is the check that the list is right).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _tn(g, shape, std=0.02):
+    # truncated-normal-like: normal clipped at 2 sigma (shape of the reference's trunc_normal_ init)
+    return (torch.randn(shape, generator=g) * std).clamp_(-2 * std, 2 * std)
+
+
+def make_state_dict(embed_dim=256, ffn=1024, layers=2, heads=4, modalities=("text", "image", "audio"), seed=0,
+                    vocab=50264, text_bucket=256, image_bucket=16, image_rel_bucket=14, audio_bucket=512,
+                    conv_pos_depth=5, conv_pos_width=95, conv_pos_groups=16,
+                    feature_spec=((512, 10, 5),) + ((512, 3, 2),) * 4 + ((512, 2, 2),) * 2, gamma_range=(0.5, 1.5)):
+    g = torch.Generator().manual_seed(seed)
+    d = embed_dim
+    sd = {}
+
+    def ln(prefix, n):
+        sd[prefix + "weight"] = 1.0 + 0.2 * torch.randn(n, generator=g)
+        sd[prefix + "bias"] = 0.1 * torch.randn(n, generator=g)
+
+    def lin(prefix, out_f, in_f, bias=True, std=0.02):
+        sd[prefix + "weight"] = _tn(g, (out_f, in_f), std)
+        if bias:
+            sd[prefix + "bias"] = 0.1 * torch.randn(out_f, generator=g)
+
+    sd["logit_scale"] = torch.tensor(math.log(1 / 0.07))
+    ew = "encoder_wrapper."
+    if "text" in modalities:
+        p = ew + "text_adapter."
+        sd[p + "cls_embedding"] = _tn(g, (1, 1, d))
+        emb = _tn(g, (vocab, d))
+        emb[1] = 0
+        sd[p + "embed_tokens.weight"] = emb
+        sd[p + "embed_positions.weight"] = _tn(g, (514, d))
+        sd[p + "rel_pos_table_list.0.weight"] = 0.5 * torch.randn(2 * text_bucket + 2, heads, generator=g)
+    if "image" in modalities:
+        p = ew + "image_adapter."
+        sd[p + "cls_embedding"] = _tn(g, (1, 1, d))
+        sd[p + "pos_embed"] = _tn(g, (image_bucket ** 2 + 1, d))
+        c4 = d // 4
+        sd[p + "embed_images.0.weight"] = torch.randn(c4, 3, 4, 4, generator=g) * (1.0 / math.sqrt(48))
+        sd[p + "embed_images.0.bias"] = 0.1 * torch.randn(c4, generator=g)
+        ln(p + "embed_images.1.layer_norm.", c4)
+        sd[p + "embed_images.3.weight"] = torch.randn(c4, c4, 2, 2, generator=g) * (1.0 / math.sqrt(4 * c4))
+        sd[p + "embed_images.3.bias"] = 0.1 * torch.randn(c4, generator=g)
+        ln(p + "embed_images.4.layer_norm.", c4)
+        sd[p + "embed_images.6.weight"] = torch.randn(d, c4, 2, 2, generator=g) * (0.5 / math.sqrt(4 * c4))
+        sd[p + "embed_images.6.bias"] = 0.1 * torch.randn(d, generator=g)
+        sd[p + "rel_pos_table_list.0.weight"] = 0.5 * torch.randn((2 * image_rel_bucket - 1) ** 2 + 3, heads, generator=g)
+    if "audio" in modalities:
+        p = ew + "audio_adapter."
+        sd[p + "cls_embedding"] = _tn(g, (1, 1, d))
+        sd[p + "cls_pos_embed"] = _tn(g, (1, 1, d))
+        sd[p + "mask_embedding"] = _tn(g, (1, d))
+        cin = 1
+        for i, (c, k, s) in enumerate(feature_spec):
+            sd[p + f"embed_audios.0.conv_layers.{i}.0.weight"] = torch.randn(c, cin, k, generator=g) * math.sqrt(2.0 / (cin * k))
+            ln(p + f"embed_audios.0.conv_layers.{i}.2.1.", c)
+            cin = c
+        ln(p + "embed_audios.2.", cin)
+        lin(p + "embed_audios.3.", d, cin, std=0.05)
+        kpos = max(3, conv_pos_width // conv_pos_depth)
+        for i in range(conv_pos_depth):
+            sd[p + f"embed_positions.{i + 1}.0.weight"] = torch.randn(d, d // conv_pos_groups, kpos, generator=g) * \
+                math.sqrt(1.0 / (d // conv_pos_groups * kpos))
+            sd[p + f"embed_positions.{i + 1}.0.bias"] = 0.1 * torch.randn(d, generator=g)
+        sd[p + "rel_pos_table_list.0.weight"] = 0.5 * torch.randn(2 * audio_bucket + 2, heads, generator=g)
+    fm = ew + "fusion_model."
+    for i in range(layers):
+        p = fm + f"layers.{i}."
+        lo, hi = gamma_range
+        sd[p + "gamma_1"] = lo + (hi - lo) * torch.rand(d, generator=g)
+        sd[p + "gamma_2"] = lo + (hi - lo) * torch.rand(d, generator=g)
+        ln(p + "self_attn.ln.", d)
+        lin(p + "self_attn.k_proj.", d, d, bias=False, std=0.05)
+        lin(p + "self_attn.v_proj.", d, d, std=0.05)
+        lin(p + "self_attn.q_proj.", d, d, std=0.05)
+        lin(p + "self_attn.out_proj.", d, d, std=0.05)
+        ln(p + "self_attn_layer_norm.", d)
+        for m in modalities:
+            q = p + f"{m}_ffn."
+            lin(q + "0.wi_0.", ffn, d, bias=False, std=0.05)
+            lin(q + "0.wi_1.", ffn, d, bias=False, std=0.05)
+            ln(q + "2.", ffn)
+            lin(q + "3.", d, ffn, std=0.03)
+        ln(p + "final_layer_norm.", d)
+    for m in modalities:
+        ln(fm + f"{m}_layer_norm.", d)
+    for m in modalities:
+        lin(f"{m}_proj.", d, d, std=0.05)
+    return sd
+
+
+def tiny_inputs(seed=0, n_text=32, text_len=16, n_img=2, res=224, n_audio=2, audio_len=16000, vocab=50264):
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.randint(4, vocab, (n_text, text_len), generator=g)
+    for i in range(n_text):
+        k = i % 4
+        if k:
+            tok[i, -k:] = 1
+    img = torch.randn(n_img, 3, res, res, generator=g)
+    aud = F.layer_norm(torch.randn(n_audio, audio_len, generator=g), (audio_len,))
+    frames = audio_len
+    for _, k, s in ((512, 10, 5),) + ((512, 3, 2),) * 4 + ((512, 2, 2),) * 2:
+        frames = (frames - k) // s + 1
+    apm = torch.zeros(n_audio, frames + 1, dtype=torch.bool)
+    if n_audio > 1:
+        aud[1, audio_len * 3 // 4:] = 0.0
+        apm[1, 1 + frames * 3 // 4:] = True
+    return tok, img, aud, apm
+
+
+def contrastive_pair(b, d, seed, noise=0.5):
+    """Unit-norm 'image' embeddings and correlated 'text' embeddings."""
+    g = torch.Generator().manual_seed(seed)
+    a = F.normalize(torch.randn(b, d, generator=g), dim=1)
+    t = F.normalize(a + noise * F.normalize(torch.randn(b, d, generator=g), dim=1), dim=1)
+    return a, t

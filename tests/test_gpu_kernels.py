@@ -1,0 +1,171 @@
+"""GPU: every sm_100a kernel through the C-ABI vs a plain PyTorch fp32 reference of the same op.
+Tolerances are stated per test: operands are bf16 (8 mantissa bits), accumulation fp32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from one_peace_b200 import kernels
+    return kernels
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-9)).item()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,Kd", [(128, 256, 64), (1000, 384, 48), (1576, 1536, 1536), (12608, 4608, 1536), (37, 768, 256)])
+def test_gemm_store(K, cg, M, N, Kd):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = (torch.randn(M, Kd, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, Kd, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    cs = torch.rand(N, device="cuda", generator=g) + 0.5
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    K.gemm(a, w, K.EPI_STORE_BF16, out, bias=bias, colscale=cs, cta_group=cg)
+    want = (a.float() @ w.float().t() + bias) * cs
+    assert relerr(out, want) < 6e-3          # bf16 output rounding: 2^-9 relative
+    out32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    K.gemm(a, w, K.EPI_STORE_F32, out32, bias=bias, cta_group=cg)
+    assert relerr(out32, a.float() @ w.float().t() + bias) < 1e-5   # fp32 accumulate of exact bf16 products
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_geglu_and_residual(K, cg):
+    M, d, F = 1000, 256, 1024
+    g = torch.Generator(device="cuda").manual_seed(7)
+    h = (torch.randn(M, d, device="cuda", generator=g)).bfloat16()
+    w0 = (torch.randn(F, d, device="cuda", generator=g) * 0.05)
+    w1 = (torch.randn(F, d, device="cuda", generator=g) * 0.05)
+    from one_peace_b200.transformer.transformer_layer import interleave_geglu
+    w01 = interleave_geglu(w0, w1)
+    u = torch.empty(M, F, device="cuda", dtype=torch.bfloat16)
+    K.gemm(h, w01, K.EPI_GEGLU_BF16, u, cta_group=cg)
+    want = torch.nn.functional.gelu(h.float() @ w0.bfloat16().float().t()) * (h.float() @ w1.bfloat16().float().t())
+    assert relerr(u, want) < 6e-3
+    w2 = (torch.randn(d, F, device="cuda", generator=g) * 0.05).bfloat16()
+    b2 = torch.randn(d, device="cuda", generator=g)
+    gamma = torch.randn(d, device="cuda", generator=g)
+    x = torch.randn(M, d, device="cuda", generator=g)
+    x0 = x.clone()
+    K.gemm(u, w2, K.EPI_RESID_F32, x, bias=b2, gamma=gamma, resid=x, cta_group=cg)
+    want = x0 + gamma * (u.float() @ w2.float().t() + b2)
+    assert relerr(x, want) < 1e-5
+
+
+def test_gemm_row_remap_and_broadcast_residual(K):
+    B, P, d, Kd = 3, 196, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(B * P, Kd, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(d, Kd, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(d, device="cuda", generator=g)
+    pos = torch.randn(P + 1, d, device="cuda", generator=g)
+    x = torch.full((B, P + 1, d), 7.0, device="cuda")
+    K.gemm(a, w, K.EPI_RESID_F32, x.view(B * (P + 1), d), bias=bias, resid=pos, out_group=P, out_group_stride=P + 1,
+           out_row_offset=1, resid_period=P, resid_row_offset=1)
+    want = (a.float() @ w.float().t() + bias).view(B, P, d) + pos[1:]
+    assert relerr(x[:, 1:], want) < 1e-5
+    assert torch.all(x[:, 0] == 7.0)       # CLS slot untouched
+
+
+def test_gemm_overlapping_strided_rows_is_conv1d(K):
+    """k=3, s=2 Conv1d over channel-last activations == GEMM on an overlapping strided view (audio.py:270-284)."""
+    T_in, C, Co = 41, 64, 128
+    T_out = (T_in - 3) // 2 + 1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(T_in + 4, C, device="cuda", generator=g).bfloat16()     # + slack rows
+    w = (torch.randn(Co, C, 3, device="cuda", generator=g) * 0.1)
+    wp = w.permute(0, 2, 1).reshape(Co, 3 * C).bfloat16().contiguous()       # [out, (j, c)]
+    out = torch.empty(T_out, Co, device="cuda", dtype=torch.float32)
+    K.gemm(x, wp, K.EPI_STORE_F32, out, M=T_out, K=3 * C, lda=2 * C)
+    want = torch.nn.functional.conv1d(x[:T_in].float().t()[None], w.bfloat16().float(), stride=2)[0].t()
+    assert relerr(out, want) < 1e-5
+
+
+@pytest.mark.parametrize("B,S,H,use_bias,use_pad", [(2, 17, 4, True, True), (2, 64, 4, False, False),
+                                                     (3, 197, 24, True, False), (2, 500, 4, True, True), (1, 750, 2, True, True)])
+def test_attention(K, B, S, H, use_bias, use_pad):
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(S)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    s_pad = (S + 7) // 8 * 8
+    bias = None
+    if use_bias:
+        bias = torch.zeros(H, S, s_pad, device="cuda")
+        bias[:, :, :S] = torch.randn(H, S, S, device="cuda", generator=g)
+    kp = None
+    if use_pad:
+        kp = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+        for b in range(B):
+            kp[b, S - 1 - 3 * b:] = 1
+    out = K.attention(qkv, bias, kp, B, S, H)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc = q @ k.transpose(-1, -2)
+    if bias is not None:
+        sc = sc + bias[None, :, :, :S]
+    if kp is not None:
+        sc = sc.masked_fill(kp.bool()[:, None, None, :], float("-inf"))
+    want = (sc.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+    assert relerr(out, want) < 8e-3          # probabilities and output are rounded to bf16
+
+
+@pytest.mark.parametrize("rows,dim,in_dt,out_dt,affine,gelu,merge", [
+    (1000, 1536, torch.float32, torch.bfloat16, True, False, 0), (300, 6144, torch.bfloat16, torch.bfloat16, True, False, 0),
+    (77, 256, torch.float32, torch.bfloat16, True, False, 0), (2 * 56 * 56, 384, torch.bfloat16, torch.bfloat16, True, True, 56),
+    (999, 512, torch.bfloat16, torch.bfloat16, True, True, 0), (50, 1536, torch.bfloat16, torch.float32, False, True, 0),
+    (64, 64, torch.bfloat16, torch.bfloat16, True, True, 8)])
+def test_layernorm(K, rows, dim, in_dt, out_dt, affine, gelu, merge):
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = (torch.randn(rows, dim, device="cuda", generator=g) * 2 + 0.5).to(in_dt)
+    gm = torch.randn(dim, device="cuda", generator=g) if affine else None
+    bt = torch.randn(dim, device="cuda", generator=g) if affine else None
+    out = torch.zeros(rows // 4, dim * 4, device="cuda", dtype=out_dt) if merge else torch.empty(rows, dim, device="cuda", dtype=out_dt)
+    K.layernorm(x, gm, bt, out, rows=rows, dim=dim, gelu=gelu, merge_grid_w=merge)
+    want = torch.nn.functional.layer_norm(x.float(), (dim,), gm, bt, 1e-5)
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    if merge:
+        w = merge
+        want = want.view(rows // (w * w), w // 2, 2, w // 2, 2, dim).permute(0, 1, 3, 2, 4, 5).reshape(rows // 4, 4 * dim)
+    assert relerr(out, want) < (1e-5 if out_dt == torch.float32 else 6e-3)
+
+
+def test_text_embed_and_relpos_bias(K):
+    import restated as R
+    B, T, D, H = 5, 9, 256, 4
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randint(4, 1000, (B, T), generator=g)
+    tok[1, -2:] = 1
+    tok[3, -4:] = 1
+    table = torch.randn(1000, D, generator=g)
+    pos = torch.randn(514, D, generator=g)
+    cls = torch.randn(D, generator=g)
+    x, pad = K.text_embed(tok.cuda(), table.cuda(), pos.cuda(), cls.cuda(), 1)
+    want = torch.cat([cls.expand(B, 1, D), table[tok]], 1) + pos[: T + 1]
+    wpad = torch.zeros(B, T + 1, dtype=torch.bool)
+    wpad[:, 1:] = tok.eq(1)
+    want = want * (~wpad).unsqueeze(-1)
+    assert torch.equal(pad.bool().cpu(), wpad)
+    assert torch.equal(x.cpu(), want)                       # pure gather + one fp32 add: bit exact
+    bucket = R.make_token_bucket_position(256)
+    tab = torch.randn(514, H, generator=g)
+    bias = K.relpos_bias_build(tab.cuda(), bucket.cuda(), T + 1, H)
+    assert torch.equal(bias[:, :, : T + 1].cpu(), R.rel_pos_bias(tab, bucket, T + 1))
+    assert torch.all(bias[:, :, T + 1:] == 0)
+
+
+def test_patchify_and_l2norm(K):
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(2, 3, 32, 32, generator=g)
+    a = K.image_patchify4(img.cuda())
+    want = img.view(2, 3, 8, 4, 8, 4).permute(0, 2, 4, 1, 3, 5).reshape(2 * 64, 48).bfloat16()
+    assert torch.equal(a.cpu(), want)
+    x = torch.randn(7, 300, generator=g)
+    y, y16 = K.l2_normalize_rows(x.cuda(), want_bf16=True)
+    torch.testing.assert_close(y.cpu(), torch.nn.functional.normalize(x, dim=1), atol=1e-6, rtol=1e-6)
+    assert relerr(y16, y) < 4e-3

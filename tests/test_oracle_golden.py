@@ -1,0 +1,105 @@
+"""Pins oracle/restated.py (the CPU oracle) against tests/golden/*.pt, which were produced by executing the
+reference's own module files (oracle/make_golden.py).  CPU only."""
+import math
+import os
+
+import pytest
+import torch
+
+import restated as R
+import synth
+
+
+@pytest.fixture(scope="module")
+def tiny(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "tiny_retrieval.pt"), weights_only=False)
+    c = fx["config"]
+    sd = synth.make_state_dict(**c, seed=fx["weights_seed"])
+    cfg = R.OracleConfig(embed_dim=c["embed_dim"], ffn_embed_dim=c["ffn"], layers=c["layers"], attention_heads=c["heads"])
+    tok, img, aud, apm = synth.tiny_inputs(seed=fx["inputs_seed"])
+    return fx, sd, cfg, (tok, img, aud, apm)
+
+
+def test_bucket_tables_match_reference_shapes():
+    b = R.make_token_bucket_position(256)
+    assert b.shape == (1024, 1024) and int(b.max()) == 2 * 256 + 1 and int(b[0, 0]) == 513
+    i = R.make_image_bucket_position(14)
+    assert i.shape == (197, 197) and int(i.max()) == 27 * 27 + 2
+
+
+def test_text_adapter(tiny):
+    fx, sd, cfg, (tok, _, _, _) = tiny
+    x, pad, bias = R.text_adapter(sd, cfg, tok)
+    assert torch.equal(pad, fx["adapter"]["text_pad"])
+    torch.testing.assert_close(x, fx["adapter"]["text_x"], atol=1e-6, rtol=0)
+    torch.testing.assert_close(bias, fx["adapter"]["text_bias"], atol=0, rtol=0)
+
+
+def test_image_adapter(tiny):
+    fx, sd, cfg, (_, img, _, _) = tiny
+    x, pad, bias = R.image_adapter(sd, cfg, img)
+    assert not pad.any()
+    torch.testing.assert_close(x[:1], fx["adapter"]["image_x"], atol=2e-5, rtol=0)
+    torch.testing.assert_close(bias[:, :40, :40], fx["adapter"]["image_bias"], atol=0, rtol=0)
+
+
+def test_audio_adapter(tiny):
+    fx, sd, cfg, (_, _, aud, apm) = tiny
+    x, pad, bias = R.audio_adapter(sd, cfg, aud, apm)
+    assert x.shape[1] == R.audio_frames(aud.shape[1], cfg.feature_encoder_spec) + 1
+    torch.testing.assert_close(x, fx["adapter"]["audio_x"], atol=5e-5, rtol=1e-5)
+    torch.testing.assert_close(bias, fx["adapter"]["audio_bias"], atol=0, rtol=0)
+
+
+def test_text_layer0(tiny):
+    fx, sd, cfg, (tok, _, _, _) = tiny
+    x, pad, bias = R.text_adapter(sd, cfg, tok)
+    x = x * (1 - pad.unsqueeze(-1).type_as(x))
+    y = R.encoder_layer(sd, cfg, x, bias, pad, "text", "encoder_wrapper.fusion_model.layers.0.")
+    torch.testing.assert_close(y, fx["text_layer0_out"], atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("modality", ["text", "image", "audio"])
+def test_extract_features(tiny, modality):
+    fx, sd, cfg, (tok, img, aud, apm) = tiny
+    out = R.extract_features(sd, cfg, modality, src_tokens=tok, src_images=img, src_audios=aud, audio_padding_masks=apm)
+    want = fx["outputs"][modality]
+    torch.testing.assert_close(out, want, atol=1e-5, rtol=0)
+    torch.testing.assert_close(out.norm(dim=1), torch.ones(out.shape[0]), atol=1e-5, rtol=0)
+
+
+def test_itc_loss_and_grads(golden_dir):
+    cases = torch.load(os.path.join(golden_dir, "itc_loss.pt"), weights_only=False)
+    for c in cases:
+        a, t = synth.contrastive_pair(c["b"], c["d"], c["seed"])
+        a.requires_grad_(True); t.requires_grad_(True)
+        ls = c["logit_scale"].clone().requires_grad_(True)
+        loss, i2t, t2i = R.itc_loss(a, t, a.detach(), t.detach(), R.logit_scale_exp(ls), 0, c["eps"])
+        loss.backward()
+        torch.testing.assert_close(loss.detach(), c["loss"], atol=1e-6, rtol=1e-6)
+        assert float(i2t) == float(c["i2t_ncorrect"]) and float(t2i) == float(c["t2i_ncorrect"])
+        torch.testing.assert_close(a.grad[:8], c["grad_image"], atol=1e-7, rtol=1e-5)
+        torch.testing.assert_close(t.grad[:8], c["grad_text"], atol=1e-7, rtol=1e-5)
+        torch.testing.assert_close(a.grad.norm(), c["grad_image_norm"], atol=0, rtol=1e-5)
+        torch.testing.assert_close(ls.grad, c["grad_logit_scale"], atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["fp32", "bf16"])
+def test_adam(golden_dir, tag):
+    fx = torch.load(os.path.join(golden_dir, "adam.pt"), weights_only=False)[tag]
+    p = fx["p0"].clone()
+    m = torch.zeros(p.shape); v = torch.zeros(p.shape)
+    for step, (g, want) in enumerate(zip(fx["grads"], fx["traj"]), start=1):
+        p32 = p.float()
+        R.adam_step(p32, g.float(), m, v, step, fx["lr"], fx["betas"][0], fx["betas"][1], fx["eps"], fx["weight_decay"])
+        p = p32.to(p.dtype)          # optim/adam.py:250-251: copy back (round to bf16 when params are bf16)
+        assert torch.equal(p, want)
+    torch.testing.assert_close(m, fx["exp_avg"], atol=0, rtol=0)
+    torch.testing.assert_close(v, fx["exp_avg_sq"], atol=0, rtol=0)
+
+
+def test_clip_coefficient_matches_fairseq_known_answer():
+    # fairseq/tests/test_fp16_optimizer.py:57-82 pins grad-norm 2.2361 for grads (w: 2*? ...) of a
+    # Linear(1,1) step: ||[1, 2]|| = sqrt(5).  Same formula (norm, then clamp(max_norm / (norm + 1e-6), max=1)).
+    norm, coef = R.clip_coefficient([torch.tensor([1.0]), torch.tensor([2.0])], max_norm=1.0)
+    assert abs(norm - 2.2361) < 1e-4 and abs(coef - 1.0 / (math.sqrt(5) + 1e-6)) < 1e-7
