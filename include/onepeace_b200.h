@@ -56,12 +56,24 @@ const char* opb_status_string(int status);
  * bias/colscale/gamma/resid may be NULL.  Row remapping: if out_group > 0,
  *   out_row = (m / out_group) * out_group_stride + (m % out_group) + out_row_offset;
  * if resid_period > 0 the residual row is (m % resid_period) + resid_row_offset (broadcast table),
- * otherwise it is out_row.  cta_group: 1, 2 (CTA pair, 256x256 tiles) or 0 = choose.
+ * otherwise it is out_row.  If out_group_valid > 0, rows with (m % out_group) >= out_group_valid are computed but
+ * not stored (allocation slack rows of the audio frame buffers).  cta_group: 1, 2 (CTA pair, 256x256 tiles) or 0.
  */
 int opb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, void* out,
                   int64_t ldo, const float* bias, const float* colscale, const float* gamma, const float* resid,
-                  int64_t ldr, int out_group, int out_group_stride, int out_row_offset, int resid_period,
-                  int resid_row_offset, int cta_group, void* stream);
+                  int64_t ldr, int out_group, int out_group_stride, int out_row_offset, int out_group_valid,
+                  int resid_period, int resid_row_offset, int cta_group, void* stream);
+
+/*
+ * Grouped Conv1d over channel-last activations as one grouped sliding-window tcgen05 GEMM (the positional conv
+ * stack of models/adapter/audio.py:57-80: Conv1d(1536,1536,k=19,pad=9,groups=16)):
+ *   out[r, g*n_per_group + n] = epi( bias + sum_{j<taps} sum_{c<c_pad} X[r + j, g, c] * W[g*n_per_group + n, j*c_pad + c] )
+ * X bf16 [rows + taps - 1, groups, c_pad] (c_pad % 64 == 0; the caller supplies the zero halo / channel padding),
+ * W bf16 [groups*n_per_group, taps*c_pad], out bf16 or fp32 [rows, groups*n_per_group] per `epi`
+ * (OPB_EPI_STORE_BF16 / GELU_BF16 / STORE_F32 / RESID_F32 with the same optional vectors as opb_gemm_bf16).
+ */
+int opb_grouped_conv1d_bf16(const void* X, const void* W, int rows, int groups, int c_pad, int taps, int n_per_group,
+                            int epi, void* out, int64_t ldo, const float* bias, void* stream);
 
 /*
  * Fused self-attention: out = softmax_fp32(q k^T + bias[h] (+ -inf on padded keys)) v.
@@ -78,10 +90,22 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
  * Row LayerNorm (torch.nn.LayerNorm semantics; models/components.py:23-26) with optional exact GELU and
  * optional 2x2 pixel-merge scatter (models/adapter/image.py:37-47 LayerNorm2D + the following stride-2
  * conv's patch gather).  in/out dtype tags: OPB_F32 / OPB_BF16; gamma/beta fp32 or both NULL.
+ * Sequence remap (row_period > 0): input row = b*row_period + t, rows with t >= row_valid are skipped, output row =
+ * b*out_period + t + out_row_shift.  Channel-group padding (group_in > 0): output column = (c / group_in) * group_out
+ * + c % group_in.  accumulate (fp32 output only): out += y.  These serve the audio adapter's halo / CLS layouts
+ * (models/adapter/audio.py:57-80,194-197).
  */
 int opb_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype, int64_t ld_out,
                   const float* gamma, const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w,
-                  void* stream);
+                  int row_period, int row_valid, int out_period, int out_row_shift, int group_in, int group_out,
+                  int accumulate, void* stream);
+
+/*
+ * fp32 feature rows -> bf16 grouped / channel-padded / halo'd operand of opb_grouped_conv1d_bf16:
+ * out[b, halo + t, g, :group_in] = x[b*x_period + x_row_shift + t, g*group_in:(g+1)*group_in] (padding columns zero).
+ */
+int opb_pack_group_halo(const float* x, int64_t ldx, void* out, int B, int T, int x_period, int x_row_shift,
+                        int out_period, int halo, int dim, int group_in, int group_out, void* stream);
 
 /*
  * Text adapter front end: x[b,0,:] = cls + pos[0]; x[b,1+t,:] = embed[tok[b,t]] + pos[1+t]; rows of padded
@@ -124,13 +148,20 @@ int opb_l2_normalize_rows(const float* x, int64_t ldx, float* y, void* y_bf16, i
 /* x[row,:] = 0 where pad_mask[row] (transformer_encoder.py:139-142). */
 int opb_zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, void* stream);
 
-/* bf16 [rows, cols] -> [cols, rows] (used to lay the gathered embeddings out K-major for the gradient GEMM). */
-int opb_transpose_bf16(const void* in, void* out, int rows, int cols, void* stream);
+/* bf16 [rows, cols] (row pitch ld_in) -> [cols, rows] (lays the gathered embeddings out K-major for the gradient GEMM). */
+int opb_transpose_bf16(const void* in, int64_t ld_in, void* out, int rows, int cols, void* stream);
+
+/*
+ * fp32 [rows, d] -> bf16 [rows, 3d] split x = hi + lo: side 0 -> [hi|hi|lo] (local operand), side 1 -> [hi|lo|hi]
+ * (gathered operand).  One K = 3d GEMM then gives hi.hi + hi.lo + lo.hi, i.e. logits accurate to ~2^-16.
+ */
+int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, void* stream);
 
 /*
  * Cross-modal InfoNCE, one direction (criterions/image_text_retrieval_loss.py:91-112, :16-26; pretrain twin
- * image_text_pretrain_loss.py:164-185).  a_local bf16 [b,d] (this rank's rows), b_all bf16 [n,d] (all ranks'
- * rows of the other modality in rank-major order, detached), scale = device scalar exp(clamp(logit_scale)).
+ * image_text_pretrain_loss.py:164-185).  a_local bf16 [b,k] (this rank's rows), b_all bf16 [n,k] (all ranks'
+ * rows of the other modality in rank-major order, detached); k = d for plain bf16 operands or 3d for the
+ * opb_split_bf16x3 layout; scale = device scalar exp(clamp(logit_scale)).
  * Targets: row i -> column i + target_offset (target_offset = rank * b).
  *   opb_infonce_ws_floats : size (floats) of the partial workspace `ws` for opb_infonce_rows
  *   opb_infonce_rows      : row_lse / row_loss (label-smoothed NLL per row) / row_argmax, all [b]
@@ -146,8 +177,8 @@ int opb_infonce_rows(const void* a_local, const void* b_all, const float* scale,
 int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argmax_a, const int* argmax_b, int b,
                        int target_offset, float* out3, void* stream);
 int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
-                     const float* row_lse, int b, int n, int d, int target_offset, float label_smoothing,
-                     void* g_ws, float* ws_gz, float* grad_a, void* stream);
+                     const float* row_lse, int b, int n, int d, int k_logits, int target_offset,
+                     float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, void* stream);
 int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream);
 
 /*

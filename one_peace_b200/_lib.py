@@ -19,11 +19,15 @@ SIGNATURES = {
     "opb_status_string": (ctypes.c_char_p, [c_int]),
     "opb_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
-                              c_int, c_void_p]),
+                              c_int, c_int, c_void_p]),
+    "opb_grouped_conv1d_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                                        c_void_p, c_void_p]),
+    "opb_pack_group_halo": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_void_p]),
     "opb_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p]),
     "opb_layernorm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int,
-                              c_float, c_int, c_int, c_void_p]),
+                              c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "opb_text_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p]),
     "opb_image_patchify4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
@@ -32,13 +36,14 @@ SIGNATURES = {
     "opb_audio_frame10": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "opb_l2_normalize_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "opb_zero_padded_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "opb_transpose_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "opb_transpose_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "opb_split_bf16x3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "opb_infonce_ws_floats": (c_int64, [c_int, c_int]),
     "opb_infonce_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "opb_infonce_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "opb_infonce_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "opb_infonce_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "opb_infonce_dscale": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "opb_adam_chunk_elems": (c_int, []),
     "opb_adam_multi_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float,

@@ -1,8 +1,207 @@
-"""Drop-in for ``AudioAdapter`` (models/adapter/audio.py:35-311) — placeholder until the conv stack lands."""
+"""Drop-in for ``AudioAdapter`` (models/adapter/audio.py:35-311): wav2vec-style conv feature extractor, conv
+positional encoder, CLS, log-bucket relative-position bias.  Same parameter / buffer names
+(embed_audios.0.conv_layers.N.{0,2.1}, embed_audios.{2,3}, embed_positions.{1..5}.0, cls_embedding,
+cls_pos_embed, mask_embedding, rel_pos_table_list.N, rp_bucket).
+
+Every convolution runs on the tcgen05 GEMM over channel-last activations (no transposes — the reference does
+14 of them for the channel LayerNorms):
+  * layer 0 (C_in = 1, k = 10, s = 5): a frame kernel writes the [frames, 16] bf16 operand (K padded 10 -> 16);
+  * layers 1..6 (C = 512, k in {3, 2}, s = 2): the GEMM's A operand is an OVERLAPPING strided view of the previous
+    layer's [frames, 512] output (row pitch s*512, row length k*512) — TMA reads it directly, nothing is
+    materialised.  Per-clip frame buffers are allocated with pitch_k = 2 * pitch_{k+1} so that one uniform row
+    stride covers the whole batch; the few slack rows compute garbage that no valid row ever reads;
+  * the 5 positional convs (1536 ch, k = 19, pad 9, 16 groups) are grouped sliding-window GEMMs over a halo'd,
+    group-padded (96 -> 128 channels) bf16 buffer; LayerNorm(no affine) + GELU re-emits that layout.
+"""
 import torch
+
+from .. import kernels as K
+from ..components import Embedding, LayerNorm, Linear, PackCache, bf16, f32, trunc_normal_
+from .text import make_token_bucket_position
+
+
+class TransposeLast(torch.nn.Module):
+    """Kept only so that Sequential indices (and therefore parameter names) match the reference (audio.py:236-242)."""
+
+    def forward(self, x):
+        return x.transpose(-2, -1)
+
+
+class SamePad(torch.nn.Module):
+    def __init__(self, kernel_size):
+        super().__init__()
+        self.remove = 1 if kernel_size % 2 == 0 else 0
+
+
+class ConvFeatureExtractionModel(torch.nn.Module):
+    """Parameter container with the reference's names (audio.py:254-311): conv_layers.N = Sequential(conv,
+    dropout, Sequential(TransposeLast, LayerNorm, TransposeLast), GELU)."""
+
+    def __init__(self, conv_layers, conv_bias=False):
+        super().__init__()
+        in_d = 1
+        self.conv_layers = torch.nn.ModuleList()
+        for dim, k, stride in conv_layers:
+            conv = torch.nn.Conv1d(in_d, dim, k, stride=stride, bias=conv_bias)
+            torch.nn.init.kaiming_normal_(conv.weight)
+            self.conv_layers.append(torch.nn.Sequential(
+                conv, torch.nn.Dropout(p=0.0), torch.nn.Sequential(TransposeLast(), LayerNorm(dim), TransposeLast()),
+                torch.nn.GELU()))
+            in_d = dim
 
 
 class AudioAdapter(torch.nn.Module):
     def __init__(self, cfg, embed_dim, attention_heads, num_layers=None):
         super().__init__()
-        raise NotImplementedError("audio adapter: under construction")
+        if cfg.layernorm_embedding or cfg.add_type_embedding or cfg.shrink_alpha != 1.0 or cfg.conv_pos_pre_ln:
+            raise NotImplementedError("layernorm_embedding / add_type_embedding / shrink_alpha / conv_pos_pre_ln are off "
+                                      "in the 4B config")
+        if cfg.abs_pos_type != "conv" or cfg.conv_bias:
+            raise NotImplementedError("only abs_pos_type='conv', conv_bias=False (the 4B config) is built")
+        self.embed_dim = embed_dim
+        self.attention_heads = attention_heads
+        self.spec = eval(cfg.feature_encoder_spec)
+        if self.spec[0][1:] != (10, 5) or any(s != 2 or c != self.spec[0][0] for c, _, s in self.spec[1:]):
+            raise NotImplementedError("feature extractor kernels are built for [(C,10,5)] + [(C,k,2)]*n")
+        feat = self.spec[-1][0]
+        self.embed_audios = torch.nn.Sequential(ConvFeatureExtractionModel(self.spec), TransposeLast(),
+                                                LayerNorm(feat), Linear(feat, embed_dim))
+        self.pos_depth = cfg.conv_pos_depth
+        self.pos_k = max(3, cfg.conv_pos_width // cfg.conv_pos_depth)
+        self.pos_groups = cfg.conv_pos_groups
+        if self.pos_k % 2 == 0:
+            raise NotImplementedError("even conv-pos kernel (SamePad trimming) is not used by the 4B config (k = 19)")
+        self.embed_positions = torch.nn.Sequential(
+            TransposeLast(),
+            *[torch.nn.Sequential(
+                torch.nn.Conv1d(embed_dim, embed_dim, kernel_size=self.pos_k, padding=self.pos_k // 2, groups=self.pos_groups),
+                SamePad(self.pos_k), TransposeLast(), torch.nn.LayerNorm(embed_dim, elementwise_affine=False),
+                TransposeLast(), torch.nn.GELU()) for _ in range(self.pos_depth)],
+            TransposeLast())
+        self.cls_pos_embed = torch.nn.Parameter(torch.zeros(1, 1, embed_dim))
+        trunc_normal_(self.cls_pos_embed)
+        self.cls_embedding = torch.nn.Parameter(torch.zeros(1, 1, embed_dim))
+        if cfg.use_attn_bias:
+            num_rel_dis = 2 * cfg.bucket_size - 1
+            rp_bucket = make_token_bucket_position(cfg.bucket_size, max_position=1024)
+            rp_bucket[0, :] = num_rel_dis
+            rp_bucket[:, 0] = num_rel_dis + 1
+            rp_bucket[0, 0] = num_rel_dis + 2
+            self.register_buffer("rp_bucket", rp_bucket)
+            self.rel_pos_table_list = torch.nn.ModuleList(
+                [Embedding(num_rel_dis + 3, attention_heads, zero_init=True) for _ in range(num_layers or 1)])
+        else:
+            self.rel_pos_table_list = None
+        self.mask_embedding = torch.nn.Parameter(torch.zeros(1, embed_dim))
+        trunc_normal_(self.cls_embedding)
+        trunc_normal_(self.mask_embedding)
+        self._cache = PackCache()
+
+    # ------------------------------------------------------------------------------------------------
+    def _pack(self):
+        fe = self.embed_audios[0].conv_layers
+        ps = [l[0].weight for l in fe] + [l[2][1].weight for l in fe] + [l[2][1].bias for l in fe] + \
+             [self.embed_audios[2].weight, self.embed_audios[2].bias, self.embed_audios[3].weight, self.embed_audios[3].bias,
+              self.cls_embedding, self.cls_pos_embed] + \
+             [self.embed_positions[i + 1][0].weight for i in range(self.pos_depth)] + \
+             [self.embed_positions[i + 1][0].bias for i in range(self.pos_depth)] + \
+             ([t.weight for t in self.rel_pos_table_list] if self.rel_pos_table_list is not None else [])
+
+        def build():
+            d, G = self.embed_dim, self.pos_groups
+            cg = d // G
+            cpad = (cg + 63) // 64 * 64
+            conv_w = []
+            for i, l in enumerate(fe):
+                w = l[0].weight.detach()                               # [C_out, C_in, k]
+                if i == 0:
+                    w16 = torch.zeros(w.shape[0], 16, dtype=torch.bfloat16, device=w.device)
+                    w16[:, : w.shape[2]] = w[:, 0, :].to(torch.bfloat16)
+                    conv_w.append(w16.contiguous())
+                else:
+                    conv_w.append(bf16(w.permute(0, 2, 1).reshape(w.shape[0], -1)))     # [out, (tap, c)]
+            pos_w = []
+            for i in range(self.pos_depth):
+                w = self.embed_positions[i + 1][0].weight.detach()      # [d, cg, k]
+                wp = torch.zeros(d, self.pos_k, cpad, dtype=torch.bfloat16, device=w.device)
+                wp[:, :, :cg] = w.permute(0, 2, 1).to(torch.bfloat16)
+                pos_w.append(wp.reshape(d, self.pos_k * cpad).contiguous())
+            return dict(
+                conv_w=conv_w, ln_w=[f32(l[2][1].weight) for l in fe], ln_b=[f32(l[2][1].bias) for l in fe],
+                post_ln_w=f32(self.embed_audios[2].weight), post_ln_b=f32(self.embed_audios[2].bias),
+                proj_w=bf16(self.embed_audios[3].weight), proj_b=f32(self.embed_audios[3].bias),
+                pos_w=pos_w, pos_b=[f32(self.embed_positions[i + 1][0].bias) for i in range(self.pos_depth)],
+                cls=f32(self.cls_embedding).view(-1), cls_pos=f32(self.cls_pos_embed).view(-1), cpad=cpad,
+                tables=[f32(t.weight) for t in self.rel_pos_table_list] if self.rel_pos_table_list is not None else None)
+        return self._cache.get(ps, build)
+
+    def frame_counts(self, n_samples):
+        out, L = [], n_samples
+        for _, k, s in self.spec:
+            L = (L - k) // s + 1
+            out.append(L)
+        return out
+
+    def get_rel_pos_bias(self, seq_len):
+        p = self._pack()
+        return [K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads) for t in p["tables"]]
+
+    def forward(self, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None):
+        """src_audios (B, N) waveform, padding_mask (B, T+1) bool -> (x fp32 (B,T+1,d) with padded rows zeroed,
+        padding_mask uint8, [bias (H,S,S_pad)])"""
+        if preserve_ids is not None or preserve_embed is not None:
+            raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+        p = self._pack()
+        B, N = src_audios.shape
+        dev = src_audios.device
+        d, C = self.embed_dim, self.spec[0][0]
+        frames = self.frame_counts(N)
+        T = frames[-1]
+        S = T + 1
+        if padding_mask.shape != (B, S):
+            raise RuntimeError(f"audio_padding_masks must be (B, frames + 1) = ({B}, {S}), got {tuple(padding_mask.shape)}")
+        nl = len(self.spec)
+        # per-clip row pitch of every layer's frame buffer: pitch_k = 2^(nl-1-k) * P covers frames[k]
+        P = max((frames[k] + (1 << (nl - 1 - k)) - 1) >> (nl - 1 - k) for k in range(nl))
+        pitch = [P << (nl - 1 - k) for k in range(nl)]
+        wav = src_audios if src_audios.dtype in (torch.float32, torch.bfloat16) else src_audios.float()
+        a0 = torch.empty(B * pitch[0], 16, dtype=torch.bfloat16, device=dev)
+        K.audio_frame10(wav.contiguous(), pitch[0], a0)
+        slack = 4                                                   # rows read past the last clip by the widest window
+        y = torch.zeros(B * pitch[0] + slack, C, dtype=torch.bfloat16, device=dev)
+        K.gemm(a0, p["conv_w"][0], K.EPI_STORE_BF16, y, M=B * pitch[0])
+        K.layernorm(y, p["ln_w"][0], p["ln_b"][0], y, rows=B * pitch[0], gelu=True)
+        for k in range(1, nl):
+            kw = self.spec[k][1]
+            yn = torch.zeros(B * pitch[k] + slack, C, dtype=torch.bfloat16, device=dev)
+            K.gemm(y, p["conv_w"][k], K.EPI_STORE_BF16, yn, M=B * pitch[k], K=kw * C, lda=2 * C)
+            K.layernorm(yn, p["ln_w"][k], p["ln_b"][k], yn, rows=B * pitch[k], gelu=True)
+            y = yn
+        K.layernorm(y, p["post_ln_w"], p["post_ln_b"], y, rows=B * P)
+        # features -> residual stream rows 1..T of every clip (fp32), slack rows (t >= T) dropped
+        x = torch.empty(B, S, d, dtype=torch.float32, device=dev)
+        K.gemm(y, p["proj_w"], K.EPI_STORE_F32, x.view(B * S, d), bias=p["proj_b"], M=B * P, out_group=P,
+               out_group_stride=S, out_row_offset=1, out_group_valid=T)
+        # conv positional encoder on the (un-normalised) features
+        G, cg, cpad, kp = self.pos_groups, d // self.pos_groups, p["cpad"], self.pos_k
+        halo = kp // 2
+        Tp = T + 2 * halo
+        bufs = [torch.zeros(B * Tp + kp, G, cpad, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        K.pack_group_halo(x.view(B * S, d), bufs[0], B, T, S, 1, Tp, halo, d, cg, cpad)
+        conv_out = torch.empty(B * Tp, d, dtype=torch.bfloat16, device=dev)
+        for i in range(self.pos_depth):
+            src, dst = bufs[i % 2], bufs[(i + 1) % 2]
+            K.grouped_conv1d(src, p["pos_w"][i], p["pos_b"][i], conv_out, B * Tp, G, cpad, kp, cg)
+            if i + 1 < self.pos_depth:
+                # LN(no affine) + GELU -> next layer's halo'd / group-padded operand (valid rows only)
+                K.layernorm(conv_out, None, None, dst.view(-1, G * cpad), rows=B * Tp, dim=d, gelu=True, row_period=Tp,
+                            row_valid=T, out_period=Tp, out_row_shift=halo, group_in=cg, group_out=cpad)
+            else:
+                # last layer: x[b, 1 + t, :] += gelu(LN(conv))     (audio.py:194-199: x = feats + pos)
+                K.layernorm(conv_out, None, None, x.view(B * S, d), rows=B * Tp, dim=d, gelu=True, row_period=Tp,
+                            row_valid=T, out_period=S, out_row_shift=1, accumulate=True)
+        K.cls_row_init(p["cls"], p["cls_pos"], x)
+        pad = padding_mask.to(torch.uint8).contiguous()
+        K.zero_padded_rows(x, pad)                                  # transformer_encoder.py:139-142
+        bias = self.get_rel_pos_bias(S) if self.rel_pos_table_list is not None else None
+        return x, pad, bias

@@ -66,7 +66,7 @@ OPB_DEVICE void st1<__nv_bfloat16>(__nv_bfloat16* p, long i, float v) { p[i] = _
 OPB_DEVICE void adam_math(float& p, float g, float& m, float& v, float b1, float b2, float eps, float lr_wd,
                           float step_size) {
   m = __fadd_rn(__fmul_rn(m, b1), __fmul_rn(g, 1.f - b1));
-  v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(g, g), 1.f - b2));
+  v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(1.f - b2, g), g));   // addcmul_: value * t1 * t2
   const float denom = __fadd_rn(sqrtf(v), eps);
   if (lr_wd != 0.f) p = __fadd_rn(p, __fmul_rn(p, -lr_wd));
   p = __fadd_rn(p, __fmul_rn(-step_size, __fdiv_rn(m, denom)));

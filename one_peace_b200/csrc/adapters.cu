@@ -226,6 +226,38 @@ int l2_normalize_rows(const float* x, long ldx, float* y, void* y_bf16, int rows
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
+// Lays an fp32 feature sequence out as the bf16 operand of the grouped positional conv (audio.py:57-80):
+// out[b, halo + t, g, :group_in] = x[b*x_period + x_row_shift + t, g*group_in : (g+1)*group_in], zero elsewhere
+// in the written rows' padding columns; halo rows are left untouched (the buffer is zero-initialised once).
+__global__ void pack_group_halo_kernel(const float* __restrict__ x, long ldx, __nv_bfloat16* __restrict__ out, int T,
+                                       int x_period, int x_row_shift, int out_period, int halo, int dim,
+                                       int group_in, int group_out) {
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  const float* xi = x + (static_cast<long>(b) * x_period + x_row_shift + t) * ldx;
+  const int groups = dim / group_in;
+  __nv_bfloat16* o = out + (static_cast<long>(b) * out_period + halo + t) * groups * group_out;
+  for (int c = threadIdx.x * 8; c < groups * group_out; c += blockDim.x * 8) {
+    const int g = c / group_out, ci = c % group_out;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (ci < group_in) {
+      const float4 a = *reinterpret_cast<const float4*>(xi + g * group_in + ci);
+      const float4 bq = *reinterpret_cast<const float4*>(xi + g * group_in + ci + 4);
+      u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+      u.z = pack_bf16x2(bq.x, bq.y); u.w = pack_bf16x2(bq.z, bq.w);
+    }
+    *reinterpret_cast<uint4*>(o + c) = u;
+  }
+}
+
+int pack_group_halo(const float* x, long ldx, void* out, int B, int T, int x_period, int x_row_shift, int out_period,
+                    int halo, int dim, int group_in, int group_out, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || group_in % 8 != 0 || group_out % 8 != 0 || dim % group_in != 0 || group_out < group_in)
+    return OPB_ERR_INVALID;
+  pack_group_halo_kernel<<<B * T, 256, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), T, x_period,
+                                                    x_row_shift, out_period, halo, dim, group_in, group_out);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
 // x[row, :] = 0 where pad_mask[row] != 0   (transformer_encoder.py:139-142)
 __global__ void zero_padded_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ pad, int D) {
   if (pad[blockIdx.x] == 0) return;

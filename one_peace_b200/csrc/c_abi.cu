@@ -21,8 +21,8 @@ const char* opb_status_string(int status) {
 
 int opb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, void* out,
                   int64_t ldo, const float* bias, const float* colscale, const float* gamma, const float* resid,
-                  int64_t ldr, int out_group, int out_group_stride, int out_row_offset, int resid_period,
-                  int resid_row_offset, int cta_group, void* stream) {
+                  int64_t ldr, int out_group, int out_group_stride, int out_row_offset, int out_group_valid,
+                  int resid_period, int resid_row_offset, int cta_group, void* stream) {
   if (A == nullptr || B == nullptr || out == nullptr) return OPB_ERR_INVALID;
   opb::GemmEpilogue ep;
   ep.out = out;
@@ -35,6 +35,7 @@ int opb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
   ep.out_group = out_group;
   ep.out_group_stride = out_group_stride;
   ep.out_row_offset = out_row_offset;
+  ep.out_group_valid = out_group_valid;
   ep.resid_period = resid_period;
   ep.resid_row_offset = resid_row_offset;
   return opb::gemm_bf16(A, static_cast<int>(lda), B, static_cast<int>(ldb), M, N, K, epi, ep, cta_group,
@@ -49,10 +50,32 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
 
 int opb_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype, int64_t ld_out,
                   const float* gamma, const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w,
-                  void* stream) {
+                  int row_period, int row_valid, int out_period, int out_row_shift, int group_in, int group_out,
+                  int accumulate, void* stream) {
   if (in == nullptr || out == nullptr) return OPB_ERR_INVALID;
+  opb::LnRemap rm;
+  rm.row_period = row_period; rm.row_valid = row_valid; rm.out_period = out_period; rm.out_row_shift = out_row_shift;
+  rm.group_in = group_in; rm.group_out = group_out; rm.accumulate = accumulate;
   return opb::layernorm(in, in_dtype, ld_in, out, out_dtype, ld_out, gamma, beta, rows, dim, eps, gelu,
-                        merge_grid_w, static_cast<cudaStream_t>(stream));
+                        merge_grid_w, rm, static_cast<cudaStream_t>(stream));
+}
+
+int opb_grouped_conv1d_bf16(const void* X, const void* W, int rows, int groups, int c_pad, int taps, int n_per_group,
+                            int epi, void* out, int64_t ldo, const float* bias, void* stream) {
+  if (!X || !W || !out) return OPB_ERR_INVALID;
+  opb::GemmEpilogue ep;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.bias = bias;
+  return opb::gemm_bf16_grouped_window(X, W, rows, groups, c_pad, taps, n_per_group, epi, ep,
+                                       static_cast<cudaStream_t>(stream));
+}
+
+int opb_pack_group_halo(const float* x, int64_t ldx, void* out, int B, int T, int x_period, int x_row_shift,
+                        int out_period, int halo, int dim, int group_in, int group_out, void* stream) {
+  if (!x || !out) return OPB_ERR_INVALID;
+  return opb::pack_group_halo(x, ldx, out, B, T, x_period, x_row_shift, out_period, halo, dim, group_in, group_out,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int opb_text_embed(const int64_t* tokens, const void* table, int table_dtype, const float* pos, const float* cls,
@@ -95,9 +118,14 @@ int opb_zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, voi
   return opb::zero_padded_rows(x, pad_mask, rows, D, static_cast<cudaStream_t>(stream));
 }
 
-int opb_transpose_bf16(const void* in, void* out, int rows, int cols, void* stream) {
+int opb_transpose_bf16(const void* in, int64_t ld_in, void* out, int rows, int cols, void* stream) {
   if (!in || !out) return OPB_ERR_INVALID;
-  return opb::transpose_bf16(in, out, rows, cols, static_cast<cudaStream_t>(stream));
+  return opb::transpose_bf16(in, ld_in, out, rows, cols, static_cast<cudaStream_t>(stream));
+}
+
+int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, void* stream) {
+  if (!x || !out) return OPB_ERR_INVALID;
+  return opb::split_bf16x3(x, out, rows, d, side, static_cast<cudaStream_t>(stream));
 }
 
 int64_t opb_infonce_ws_floats(int b, int n) { return opb::infonce_ws_floats(b, n); }
@@ -118,11 +146,11 @@ int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argm
 }
 
 int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
-                     const float* row_lse, int b, int n, int d, int target_offset, float label_smoothing,
-                     void* g_ws, float* ws_gz, float* grad_a, void* stream) {
+                     const float* row_lse, int b, int n, int d, int k_logits, int target_offset,
+                     float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, void* stream) {
   if (!a_local || !b_all || !bT_all || !scale || !row_lse || !g_ws || !ws_gz || !grad_a) return OPB_ERR_INVALID;
-  return opb::infonce_grad(a_local, b_all, bT_all, scale, row_lse, b, n, d, target_offset, label_smoothing, g_ws,
-                           ws_gz, grad_a, static_cast<cudaStream_t>(stream));
+  return opb::infonce_grad(a_local, b_all, bT_all, scale, row_lse, b, n, d, k_logits, target_offset, label_smoothing,
+                           g_ws, ws_gz, grad_a, static_cast<cudaStream_t>(stream));
 }
 
 int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream) {

@@ -139,6 +139,24 @@ OPB_DEVICE void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, 
       : "memory");
 }
 
+OPB_DEVICE void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+OPB_DEVICE void tma_load_3d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2) {
+  uint32_t bar_addr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_addr) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ struct GemmEpilogue {
   int out_group = 0;
   int out_group_stride = 0;
   int out_row_offset = 0;
+  int out_group_valid = 0;         // if > 0: rows with (m % out_group) >= out_group_valid are not stored
   // optional broadcast residual: resid_row = (m % resid_period) + resid_row_offset
   int resid_period = 0;
   int resid_row_offset = 0;
@@ -45,5 +46,11 @@ struct GemmEpilogue {
 // cta_group: 1, 2 or 0 (auto).  Returns an OPB_* status.
 int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep,
               int cta_group, cudaStream_t stream);
+
+// Grouped "sliding window" GEMM = grouped Conv1d over channel-last activations:
+//   out[r, g*n_per_group + n] = epilogue( sum_{j < taps} sum_{c < c_pad} X[(r + j), g, c] * W[g*n_per_group + n, j*c_pad + c] )
+// X is bf16 [rows + taps - 1, groups, c_pad] (c_pad a multiple of 64), W is bf16 [groups*n_per_group, taps*c_pad].
+int gemm_bf16_grouped_window(const void* X, const void* W, int rows, int groups, int c_pad, int taps, int n_per_group,
+                             int epi, const GemmEpilogue& ep, cudaStream_t stream);
 
 }  // namespace opb

@@ -43,6 +43,16 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
 };
 
+struct GemmGeom {
+  int M, N, K;          // per group: rows, output columns, reduction length (= taps * kb_inner * 64 when windowed)
+  int kb_inner;         // k-blocks per tap (inner A coordinate wraps every kb_inner blocks); K-blocks total = taps * kb_inner
+  int num_k_blocks;
+  int groups;           // independent problems sharing A rows (grouped conv); 1 otherwise
+  int a_group_c0;       // inner A coordinate offset per group
+  int b_group_rows;     // B row offset per group (= N)
+  int n_umma;           // UMMA N (256, or N rounded up to 16 when N < 256)
+};
+
 struct SmemBars {
   uint64_t full[8];
   uint64_t empty[8];
@@ -54,7 +64,8 @@ struct SmemBars {
 template <int CG, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const GemmEpilogue ep, int M, int N, int K) {
+                 const GemmEpilogue ep, const GemmGeom geo) {
+  const int M = geo.M, N = geo.N;
   using Cfg = GemmCfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -68,8 +79,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int tile_m_rows = kBlockM * CG;
   const int num_m_tiles = (M + tile_m_rows - 1) / tile_m_rows;
   const int num_n_tiles = (N + kBlockN - 1) / kBlockN;
-  const int num_tiles = num_m_tiles * num_n_tiles;
-  const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int tiles_per_group = num_m_tiles * num_n_tiles;
+  const int num_tiles = tiles_per_group * geo.groups;
+  const int num_k_blocks = geo.num_k_blocks;
   const int first_tile = blockIdx.x / CG;
   const int tile_stride = gridDim.x / CG;
 
@@ -102,23 +114,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       uint64_t* full_bar0 = bars->full;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        const int m_blk = tile % num_m_tiles;
-        const int n_blk = tile / num_m_tiles;
+        const int grp = tile / tiles_per_group;
+        const int tin = tile - grp * tiles_per_group;
+        const int m_blk = tin % num_m_tiles;
+        const int n_blk = tin / num_m_tiles;
         const int a_row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
-        const int b_row = n_blk * kBlockN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        const int b_row = grp * geo.b_group_rows + n_blk * kBlockN + static_cast<int>(cta_rank) * (geo.n_umma / 2);
+        const int a_c0 = grp * geo.a_group_c0;
+        int kin = 0, tap = 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(&full_bar0[stage], Cfg::kStageBytes);
-            tma_load_2d(&tm_a, &full_bar0[stage], sa, kb * kBlockK, a_row);
+            tma_load_3d(&tm_a, &full_bar0[stage], sa, a_c0 + kin * kBlockK, tap, a_row);
             tma_load_2d(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
           } else {
             if (is_leader) mbar_arrive_expect_tx(&full_bar0[stage], Cfg::kStageBytes * 2);
-            tma_load_2d_2sm(&tm_a, &full_bar0[stage], sa, kb * kBlockK, a_row);
+            tma_load_3d_2sm(&tm_a, &full_bar0[stage], sa, a_c0 + kin * kBlockK, tap, a_row);
             tma_load_2d_2sm(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
           }
+          if (++kin == geo.kb_inner) { kin = 0; ++tap; }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -126,7 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (is_leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CG, kBlockN);
+      const uint32_t idesc = make_idesc_bf16(kBlockM * CG, geo.n_umma);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -159,12 +176,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
-      const int m_blk = tile % num_m_tiles;
-      const int n_blk = tile / num_m_tiles;
+      const int grp = tile / tiles_per_group;
+      const int tin = tile - grp * tiles_per_group;
+      const int m_blk = tin % num_m_tiles;
+      const int n_blk = tin / num_m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
-      const bool row_ok = row < M;
+      bool row_ok = row < M;
+      if (ep.out_group > 0 && ep.out_group_valid > 0 && (row % ep.out_group) >= ep.out_group_valid) row_ok = false;
+      const int gcol0 = grp * N;      // first global output column of this group
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
@@ -310,8 +331,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const int col = col0 + c + j;
-            if (!row_ok || col >= N) continue;
+            if (!row_ok || col0 + c + j >= N) continue;
+            const int col = gcol0 + col0 + c + j;
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j + e]);
@@ -410,6 +431,24 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? OPB_OK : OPB_ERR_CUDA;
 }
 
+// 3D view of the A operand: dims {k_inner, taps, rows}; element (c, j, r) lives at ptr + r*row_stride + j*tap_stride + c.
+// A plain [rows, K] matrix is the taps == 1 case.  box = 64 x 1 x box_rows, 128B swizzle (same smem image as 2D).
+int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t k_inner, uint64_t taps, uint64_t tap_stride,
+                      uint64_t rows, uint64_t row_stride, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return OPB_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (tap_stride * 2) % 16 != 0 || (row_stride * 2) % 16 != 0)
+    return OPB_ERR_INVALID;
+  cuuint64_t gdim[3] = {k_inner, taps, rows};
+  cuuint64_t gstride[2] = {tap_stride * 2, row_stride * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OPB_OK : OPB_ERR_CUDA;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -421,7 +460,7 @@ static int sm_count() {
 }
 
 template <int CG, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, const GemmGeom& geo,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<CG>;
   auto kern = gemm_bf16_kernel<CG, EPI>;
@@ -432,11 +471,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     configured = true;
   }
   const int tile_m_rows = kBlockM * CG;
-  const int num_tiles = ((M + tile_m_rows - 1) / tile_m_rows) * ((N + kBlockN - 1) / kBlockN);
-  int groups = sm_count() / CG;
-  if (groups > num_tiles) groups = num_tiles;
+  const int num_tiles = ((geo.M + tile_m_rows - 1) / tile_m_rows) * ((geo.N + kBlockN - 1) / kBlockN) * geo.groups;
+  int clusters = sm_count() / CG;
+  if (clusters > num_tiles) clusters = num_tiles;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * CG);
+  cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -447,8 +486,25 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, M, N, K);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, geo);
   return e == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+static int dispatch_gemm(int cta_group, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep,
+                         const GemmGeom& geo, cudaStream_t stream) {
+#define OPB_DISPATCH(CGV)                                                                       \
+  switch (epi) {                                                                                \
+    case EPI_STORE_BF16: return launch_gemm<CGV, EPI_STORE_BF16>(ta, tb, ep, geo, stream);      \
+    case EPI_GELU_BF16: return launch_gemm<CGV, EPI_GELU_BF16>(ta, tb, ep, geo, stream);        \
+    case EPI_GEGLU_BF16: return launch_gemm<CGV, EPI_GEGLU_BF16>(ta, tb, ep, geo, stream);      \
+    case EPI_RESID_F32: return launch_gemm<CGV, EPI_RESID_F32>(ta, tb, ep, geo, stream);        \
+    case EPI_STORE_F32: return launch_gemm<CGV, EPI_STORE_F32>(ta, tb, ep, geo, stream);        \
+    case EPI_LSE_PARTIAL: return launch_gemm<CGV, EPI_LSE_PARTIAL>(ta, tb, ep, geo, stream);    \
+    case EPI_SOFTMAX_GRAD: return launch_gemm<CGV, EPI_SOFTMAX_GRAD>(ta, tb, ep, geo, stream);  \
+    default: return OPB_ERR_INVALID;                                                            \
+  }
+  if (cta_group == 1) { OPB_DISPATCH(1) } else { OPB_DISPATCH(2) }
+#undef OPB_DISPATCH
 }
 
 int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep,
@@ -458,24 +514,44 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   if (epi == EPI_GEGLU_BF16 && N % kBlockN != 0) return OPB_ERR_INVALID;
   if (cta_group == 0) cta_group = (M > 2 * kBlockM) ? 2 : 1;
   if (cta_group != 1 && cta_group != 2) return OPB_ERR_INVALID;
+  GemmGeom geo;
+  geo.M = M; geo.N = N; geo.K = K;
+  geo.num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  geo.kb_inner = geo.num_k_blocks;      // one "tap": the inner coordinate never wraps
+  geo.groups = 1;
+  geo.a_group_c0 = 0;
+  geo.b_group_rows = 0;
+  geo.n_umma = (N >= kBlockN) ? kBlockN : ((N + 15) / 16) * 16;
+  if (cta_group == 2 && geo.n_umma % 32 != 0) cta_group = 1;   // each CTA of a pair stages n_umma / 2 rows of B
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, kBlockM);
+  int rc = make_tmap_bf16_3d(&ta, A, K, 1, lda, M, lda, kBlockM);
   if (rc != OPB_OK) return rc;
   rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, kBlockN / cta_group);
   if (rc != OPB_OK) return rc;
-#define OPB_DISPATCH(CGV)                                                                      \
-  switch (epi) {                                                                               \
-    case EPI_STORE_BF16: return launch_gemm<CGV, EPI_STORE_BF16>(ta, tb, ep, M, N, K, stream); \
-    case EPI_GELU_BF16: return launch_gemm<CGV, EPI_GELU_BF16>(ta, tb, ep, M, N, K, stream);   \
-    case EPI_GEGLU_BF16: return launch_gemm<CGV, EPI_GEGLU_BF16>(ta, tb, ep, M, N, K, stream); \
-    case EPI_RESID_F32: return launch_gemm<CGV, EPI_RESID_F32>(ta, tb, ep, M, N, K, stream);   \
-    case EPI_STORE_F32: return launch_gemm<CGV, EPI_STORE_F32>(ta, tb, ep, M, N, K, stream);   \
-    case EPI_LSE_PARTIAL: return launch_gemm<CGV, EPI_LSE_PARTIAL>(ta, tb, ep, M, N, K, stream);   \
-    case EPI_SOFTMAX_GRAD: return launch_gemm<CGV, EPI_SOFTMAX_GRAD>(ta, tb, ep, M, N, K, stream); \
-    default: return OPB_ERR_INVALID;                                                           \
-  }
-  if (cta_group == 1) { OPB_DISPATCH(1) } else { OPB_DISPATCH(2) }
-#undef OPB_DISPATCH
+  return dispatch_gemm(cta_group, epi, ta, tb, ep, geo, stream);
+}
+
+int gemm_bf16_grouped_window(const void* X, const void* W, int rows, int groups, int c_pad, int taps, int n_per_group,
+                             int epi, const GemmEpilogue& ep, cudaStream_t stream) {
+  if (rows <= 0 || groups <= 0 || taps <= 0 || n_per_group <= 0) return OPB_ERR_INVALID;
+  if (c_pad % kBlockK != 0 || n_per_group % 8 != 0 || n_per_group > kBlockN) return OPB_ERR_INVALID;
+  if (epi == EPI_GEGLU_BF16 || epi == EPI_LSE_PARTIAL || epi == EPI_SOFTMAX_GRAD) return OPB_ERR_INVALID;
+  GemmGeom geo;
+  geo.M = rows; geo.N = n_per_group; geo.K = taps * c_pad;
+  geo.kb_inner = c_pad / kBlockK;
+  geo.num_k_blocks = taps * geo.kb_inner;
+  geo.groups = groups;
+  geo.a_group_c0 = c_pad;
+  geo.b_group_rows = n_per_group;
+  geo.n_umma = ((n_per_group + 15) / 16) * 16;
+  const long row_stride = static_cast<long>(groups) * c_pad;
+  CUtensorMap ta, tb;
+  // dims {groups*c_pad, taps, rows}: tap j of output row r reads input row r + j (tap stride == row stride)
+  int rc = make_tmap_bf16_3d(&ta, X, row_stride, taps, row_stride, rows, row_stride, kBlockM);
+  if (rc != OPB_OK) return rc;
+  rc = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(groups) * n_per_group, geo.K, geo.K, kBlockN);
+  if (rc != OPB_OK) return rc;
+  return dispatch_gemm(1, epi, ta, tb, ep, geo, stream);
 }
 
 }  // namespace opb

@@ -86,15 +86,15 @@ __global__ void infonce_dscale_kernel(const float* __restrict__ ws_a, const floa
 }
 
 // bf16 [rows, cols] -> [cols, rows] through a padded smem tile (coalesced both ways)
-__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
-                                      int cols) {
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long ld_in,
+                                      __nv_bfloat16* __restrict__ out, int rows, int cols) {
   __shared__ __nv_bfloat16 tile[64][66];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   for (int i = threadIdx.y; i < 64; i += blockDim.y) {
     const int r = r0 + i;
     for (int j = threadIdx.x; j < 64; j += blockDim.x) {
       const int c = c0 + j;
-      tile[i][j] = (r < rows && c < cols) ? in[static_cast<long>(r) * cols + c] : __float2bfloat16(0.f);
+      tile[i][j] = (r < rows && c < cols) ? in[static_cast<long>(r) * ld_in + c] : __float2bfloat16(0.f);
     }
   }
   __syncthreads();
@@ -107,11 +107,41 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv
   }
 }
 
-int transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t stream) {
-  if (rows <= 0 || cols <= 0) return OPB_ERR_INVALID;
+int transpose_bf16(const void* in, long ld_in, void* out, int rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || ld_in < cols) return OPB_ERR_INVALID;
   dim3 grid((cols + 63) / 64, (rows + 63) / 64), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in,
                                                     reinterpret_cast<__nv_bfloat16*>(out), rows, cols);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// fp32 [rows, d] -> bf16 [rows, 3d]: x = hi + lo with hi = bf16(x), lo = bf16(x - hi).
+// side 0 (the local operand): [hi | hi | lo];  side 1 (the gathered operand): [hi | lo | hi], so that one K = 3d
+// tcgen05 GEMM yields hi.hi + hi.lo + lo.hi — the logits to ~2^-16 relative instead of bf16's 2^-9, which is what
+// keeps the loss within 1e-3 of the fp32 oracle at small d / large logit_scale.
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long total, int d,
+                                    int side) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / d;
+    const int c = i % d;
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * 3L * d + c;
+    o[0] = hi;
+    o[d] = side == 0 ? hi : lo;
+    o[2L * d] = side == 0 ? lo : hi;
+  }
+}
+
+int split_bf16x3(const float* x, void* out, long rows, int d, int side, cudaStream_t stream) {
+  if (rows <= 0 || d <= 0 || (side != 0 && side != 1)) return OPB_ERR_INVALID;
+  const long total = rows * d;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  split_bf16x3_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), total,
+                                                                       d, side);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
@@ -143,9 +173,9 @@ int infonce_reduce(const float* loss_a, const float* loss_b, const int* am_a, co
 
 // backward for one direction: grad_a fp32 [b, d] = (s / 2b) G B_all ; ws_gz [n_tiles, b] row partials of sum G z
 int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
-                 const float* row_lse, int b, int n, int d, int target_offset, float eps, void* g_ws, float* ws_gz,
-                 float* grad_a, cudaStream_t stream) {
-  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0) return OPB_ERR_INVALID;
+                 const float* row_lse, int b, int n, int d, int k_logits, int target_offset, float eps, void* g_ws,
+                 float* ws_gz, float* grad_a, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0 || k_logits % 8 != 0) return OPB_ERR_INVALID;
   GemmEpilogue ep;
   ep.out = g_ws;
   ep.ldo = n;
@@ -156,7 +186,7 @@ int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, con
   ep.eps = eps;
   ep.eps_i = (eps != 0.f) ? eps / (n - 1) : 0.f;
   ep.coef = 1.f / (2.f * b);
-  int rc = gemm_bf16(a_local, d, b_all, d, b, n, d, EPI_SOFTMAX_GRAD, ep, 0, stream);
+  int rc = gemm_bf16(a_local, k_logits, b_all, k_logits, b, n, k_logits, EPI_SOFTMAX_GRAD, ep, 0, stream);
   if (rc != OPB_OK) return rc;
   GemmEpilogue e2;
   e2.out = grad_a;

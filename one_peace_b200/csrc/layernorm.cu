@@ -9,6 +9,7 @@
 //   optional 2x2 pixel-merge scatter of the output row, which lays the result out as the A operand
 //   of the next stride-2 patch conv (image.py:66-75) so that conv is a plain GEMM.
 #include "common.cuh"
+#include "ops.h"
 
 namespace opb {
 
@@ -25,6 +26,12 @@ struct LnArgs {
   int gelu;
   // pixel-merge scatter (0 = off): input rows are (b, y, x) over a grid_w x grid_w map
   int merge_grid_w;
+  // sequence remap (0 = off): input row = b * row_period + t; rows with t >= row_valid are skipped;
+  // output row = b * out_period + t + out_row_shift   (halo / CLS offsets of the audio adapter buffers)
+  int row_period, row_valid, out_period, out_row_shift;
+  // channel-group padding (0 = off): output column = (c / group_in) * group_out + c % group_in
+  int group_in, group_out;
+  int accumulate;   // fp32 output only: out += y
 };
 
 template <typename T>
@@ -77,6 +84,7 @@ template <typename TIn, typename TOut, int ITERS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   __shared__ float red[8];
   const int row = blockIdx.x;
+  if (a.row_period > 0 && (row % a.row_period) >= a.row_valid) return;   // whole CTA exits together
   const TIn* in = reinterpret_cast<const TIn*>(a.in) + static_cast<long>(row) * a.ld_in;
   float x[ITERS][8];
   float sum = 0.f;
@@ -118,6 +126,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
     orow = (static_cast<long>(bb) * (w / 2) + yy / 2) * (w / 2) + xx / 2;
     ocol0 = static_cast<long>((yy & 1) * 2 + (xx & 1)) * a.dim;
   }
+  if (a.row_period > 0) orow = static_cast<long>(row / a.row_period) * a.out_period + (row % a.row_period) + a.out_row_shift;
   TOut* out = reinterpret_cast<TOut*>(a.out) + orow * a.ld_out + ocol0;
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
@@ -137,7 +146,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = gelu_erf(y[e]);
       }
-      store8<TOut>(out + c, y);
+      const int oc = a.group_in > 0 ? (c / a.group_in) * a.group_out + (c % a.group_in) : c;
+      if constexpr (sizeof(TOut) == 4) {
+        if (a.accumulate) {
+          float prev[8];
+          load8<float>(reinterpret_cast<const float*>(out) + oc, prev);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] += prev[e];
+        }
+      }
+      store8<TOut>(out + oc, y);
     }
   }
 }
@@ -163,11 +181,16 @@ static int launch_ln(const LnArgs& a, cudaStream_t stream) {
 
 // in_dtype / out_dtype: 0 = fp32, 1 = bf16
 int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const float* gamma,
-              const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, cudaStream_t stream) {
+              const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, const LnRemap& rm,
+              cudaStream_t stream) {
   if (rows <= 0 || dim <= 0 || dim % 8 != 0 || ld_in % 8 != 0 || ld_out % 8 != 0) return OPB_ERR_INVALID;
   if ((gamma == nullptr) != (beta == nullptr)) return OPB_ERR_INVALID;
   if (merge_grid_w < 0 || (merge_grid_w & 1)) return OPB_ERR_INVALID;
-  LnArgs a{in, out, gamma, beta, ld_in, ld_out, rows, dim, eps, gelu, merge_grid_w};
+  if (rm.group_in > 0 && (rm.group_in % 8 != 0 || rm.group_out % 8 != 0 || rm.group_out < rm.group_in)) return OPB_ERR_INVALID;
+  if (rm.accumulate && out_dtype != 0) return OPB_ERR_INVALID;
+  if (rm.row_period > 0 && merge_grid_w > 0) return OPB_ERR_INVALID;
+  LnArgs a{in, out, gamma, beta, ld_in, ld_out, rows, dim, eps, gelu, merge_grid_w, rm.row_period, rm.row_valid,
+           rm.out_period, rm.out_row_shift, rm.group_in, rm.group_out, rm.accumulate};
   if (in_dtype == 0 && out_dtype == 1) return launch_ln<float, __nv_bfloat16>(a, stream);
   if (in_dtype == 1 && out_dtype == 1) return launch_ln<__nv_bfloat16, __nv_bfloat16>(a, stream);
   if (in_dtype == 0 && out_dtype == 0) return launch_ln<float, float>(a, stream);

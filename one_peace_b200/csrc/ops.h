@@ -8,8 +8,16 @@ namespace opb {
 int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, int B, int S,
                   int H, int s_pad, cudaStream_t stream);
 
+struct LnRemap {
+  int row_period = 0, row_valid = 0, out_period = 0, out_row_shift = 0;
+  int group_in = 0, group_out = 0;
+  int accumulate = 0;
+};
 int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const float* gamma,
-              const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, cudaStream_t stream);
+              const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, const LnRemap& rm,
+              cudaStream_t stream);
+int pack_group_halo(const float* x, long ldx, void* out, int B, int T, int x_period, int x_row_shift, int out_period,
+                    int halo, int dim, int group_in, int group_out, cudaStream_t stream);
 
 int text_embed(const int64_t* tokens, const void* table, int table_dtype, const float* pos, const float* cls,
                float* x, uint8_t* pad_mask, int B, int T, int D, int pad_idx, cudaStream_t stream);
@@ -21,15 +29,16 @@ int audio_frame10(const void* wav, int wav_dtype, void* out, int B, long n_sampl
 int l2_normalize_rows(const float* x, long ldx, float* y, void* y_bf16, int rows, int D, cudaStream_t stream);
 int zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, cudaStream_t stream);
 
-int transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t stream);
+int transpose_bf16(const void* in, long ld_in, void* out, int rows, int cols, cudaStream_t stream);
+int split_bf16x3(const float* x, void* out, long rows, int d, int side, cudaStream_t stream);
 long infonce_ws_floats(int b, int n);
 int infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
                  float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, cudaStream_t stream);
 int infonce_reduce(const float* loss_a, const float* loss_b, const int* am_a, const int* am_b, int b,
                    int target_offset, float* out3, cudaStream_t stream);
 int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
-                 const float* row_lse, int b, int n, int d, int target_offset, float eps, void* g_ws, float* ws_gz,
-                 float* grad_a, cudaStream_t stream);
+                 const float* row_lse, int b, int n, int d, int k_logits, int target_offset, float eps, void* g_ws,
+                 float* ws_gz, float* grad_a, cudaStream_t stream);
 int infonce_dscale(const float* ws_a, const float* ws_b, int b, int n, float* out, cudaStream_t stream);
 
 // One entry per parameter tensor (device-resident table, 64 bytes; mirrored by ctypes in optim/adam_fused.py)

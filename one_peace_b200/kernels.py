@@ -45,7 +45,8 @@ def _dt(t):
 
 
 def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, out_group=0, out_group_stride=0,
-         out_row_offset=0, resid_period=0, resid_row_offset=0, cta_group=0, M=None, lda=None, K=None):
+         out_row_offset=0, out_group_valid=0, resid_period=0, resid_row_offset=0, cta_group=0, M=None, lda=None,
+         K=None):
     """out = epilogue(a[M,K] @ w[N,K]^T).  a/w bf16; `lda`/`M`/`K` allow strided (even overlapping) row views."""
     _need_cuda(a, w, out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -62,8 +63,8 @@ def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, ou
     ldr = resid.stride(-2) if resid is not None else 0
     st = _lib.load().opb_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), w.stride(0), M, N, K, epi, out.data_ptr(),
                                    out.stride(-2), _ptr(bias), _ptr(colscale), _ptr(gamma), _ptr(resid), ldr,
-                                   out_group, out_group_stride, out_row_offset, resid_period, resid_row_offset,
-                                   cta_group, _stream())
+                                   out_group, out_group_stride, out_row_offset, out_group_valid, resid_period,
+                                   resid_row_offset, cta_group, _stream())
     _lib.check(st, "opb_gemm_bf16")
     _count()
     if PROFILE_HOOK is not None:
@@ -91,7 +92,8 @@ def attention(qkv, bias, key_pad, B, S, H, out=None, lse=None):
 
 
 def layernorm(x, gamma, beta, out, *, rows=None, dim=None, ld_in=None, ld_out=None, eps=1e-5, gelu=False,
-              merge_grid_w=0):
+              merge_grid_w=0, row_period=0, row_valid=0, out_period=0, out_row_shift=0, group_in=0, group_out=0,
+              accumulate=False):
     _need_cuda(x, out)
     if rows is None:
         rows = x.shape[0]
@@ -102,8 +104,31 @@ def layernorm(x, gamma, beta, out, *, rows=None, dim=None, ld_in=None, ld_out=No
     if ld_out is None:
         ld_out = out.stride(-2)
     st = _lib.load().opb_layernorm(x.data_ptr(), _dt(x), ld_in, out.data_ptr(), _dt(out), ld_out, _ptr(gamma),
-                                   _ptr(beta), rows, dim, eps, int(gelu), merge_grid_w, _stream())
+                                   _ptr(beta), rows, dim, eps, int(gelu), merge_grid_w, row_period, row_valid,
+                                   out_period, out_row_shift, group_in, group_out, int(accumulate), _stream())
     _lib.check(st, "opb_layernorm")
+    _count()
+    return out
+
+
+def grouped_conv1d(x_halo, w, bias, out, rows, groups, c_pad, taps, n_per_group, epi=EPI_STORE_BF16):
+    """out[r, g*n+co] = bias + sum_j sum_c x_halo[r+j, g, c] * w[g*n+co, j*c_pad+c]  (see onepeace_b200.h)."""
+    _need_cuda(x_halo, w, out)
+    assert x_halo.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x_halo.is_contiguous() and w.is_contiguous()
+    assert x_halo.numel() >= (rows + taps - 1) * groups * c_pad and w.shape == (groups * n_per_group, taps * c_pad)
+    st = _lib.load().opb_grouped_conv1d_bf16(x_halo.data_ptr(), w.data_ptr(), rows, groups, c_pad, taps, n_per_group,
+                                             epi, out.data_ptr(), out.stride(-2), _ptr(bias), _stream())
+    _lib.check(st, "opb_grouped_conv1d_bf16")
+    _count()
+    return out
+
+
+def pack_group_halo(x, out, B, T, x_period, x_row_shift, out_period, halo, dim, group_in, group_out):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
+    st = _lib.load().opb_pack_group_halo(x.data_ptr(), x.stride(-2), out.data_ptr(), B, T, x_period, x_row_shift,
+                                         out_period, halo, dim, group_in, group_out, _stream())
+    _lib.check(st, "opb_pack_group_halo")
     _count()
     return out
 
@@ -195,18 +220,33 @@ def zero_padded_rows(x, pad_mask):
 # ----------------------------------------------------------------------------------------------------
 # contrastive head
 # ----------------------------------------------------------------------------------------------------
-def transpose_bf16(x):
+def transpose_bf16(x, rows=None, cols=None):
+    """bf16 [rows, cols] view (row pitch x.stride(0)) -> contiguous [cols, rows]"""
     _need_cuda(x)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 2
-    out = torch.empty(x.shape[1], x.shape[0], dtype=torch.bfloat16, device=x.device)
-    st = _lib.load().opb_transpose_bf16(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream())
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and x.dim() == 2
+    rows = x.shape[0] if rows is None else rows
+    cols = x.shape[1] if cols is None else cols
+    out = torch.empty(cols, rows, dtype=torch.bfloat16, device=x.device)
+    st = _lib.load().opb_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, _stream())
     _lib.check(st, "opb_transpose_bf16")
     _count()
     return out
 
 
+def split_bf16x3(x, side):
+    """fp32 [r,d] -> bf16 [r,3d]; side 0 = [hi|hi|lo] (local operand), side 1 = [hi|lo|hi] (gathered operand)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    r, d = x.shape
+    out = torch.empty(r, 3 * d, dtype=torch.bfloat16, device=x.device)
+    st = _lib.load().opb_split_bf16x3(x.data_ptr(), out.data_ptr(), r, d, side, _stream())
+    _lib.check(st, "opb_split_bf16x3")
+    _count()
+    return out
+
+
 def infonce_rows(a_local, b_all, scale, target_offset, eps):
-    """One direction of the InfoNCE forward.  a_local bf16 [b,d], b_all bf16 [n,d], scale fp32 device scalar.
+    """One direction of the InfoNCE forward.  a_local bf16 [b,k], b_all bf16 [n,k], scale fp32 device scalar.
     -> (row_lse [b], row_loss [b], row_argmax int32 [b])"""
     _need_cuda(a_local, b_all, scale)
     b, d = a_local.shape
@@ -236,15 +276,16 @@ def infonce_reduce(loss_a, loss_b, am_a, am_b, target_offset):
 
 
 def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps):
-    """-> (grad_a fp32 [b,d], ws_gz) for one direction"""
-    b, d = a_local.shape
+    """-> (grad_a fp32 [b,d], ws_gz) for one direction; a_local/b_all [.,k] (k = d or 3d), bT_all bf16 [d,n]"""
+    b, k = a_local.shape
     n = b_all.shape[0]
+    d = bT_all.shape[0]
     dev = a_local.device
     g_ws = torch.empty(b, n, dtype=torch.bfloat16, device=dev)
     ws_gz = torch.empty((n + 255) // 256 * b, dtype=torch.float32, device=dev)
     grad = torch.empty(b, d, dtype=torch.float32, device=dev)
     st = _lib.load().opb_infonce_grad(a_local.data_ptr(), b_all.data_ptr(), bT_all.data_ptr(), scale.data_ptr(),
-                                      row_lse.data_ptr(), b, n, d, target_offset, eps, g_ws.data_ptr(),
+                                      row_lse.data_ptr(), b, n, d, k, target_offset, eps, g_ws.data_ptr(),
                                       ws_gz.data_ptr(), grad.data_ptr(), _stream())
     _lib.check(st, "opb_infonce_grad")
     _count(2)

@@ -26,7 +26,7 @@ class _Dictionary:
 
 def from_pretrained(model_name_or_path=None, model_type="one_peace_retrieval", device="cuda", dtype="float32",
                     state_dict=None, head_type="val", layers=40, embed_dim=1536, ffn_embed_dim=6144,
-                    attention_heads=24, patch_image_size=256):
+                    attention_heads=24, patch_image_size=256, vocab_size=50264):
     """hub_interface.py:53-73.  Loads ``one-peace.pt``-style state dicts (same parameter names, strict except for
     pretraining-only keys) into the sm_100a model.  ``model_name_or_path`` may be a torch checkpoint whose
     'model' entry is the state dict (fairseq layout) or a bare state dict; alternatively pass ``state_dict``."""
@@ -35,7 +35,7 @@ def from_pretrained(model_name_or_path=None, model_type="one_peace_retrieval", d
     cfg = OnePeaceRetrievalConfig()
     cfg.encoder = one_peace_4b_encoder_config(layers, embed_dim, ffn_embed_dim, attention_heads, patch_image_size)
     with torch.device(device):
-        model = OnePeaceRetrievalModel(cfg, _Dictionary(), head_type)
+        model = OnePeaceRetrievalModel(cfg, _Dictionary(vocab_size), head_type)
     if state_dict is None and model_name_or_path is not None:
         ckpt = torch.load(model_name_or_path, map_location="cpu")
         state_dict = ckpt.get("model", ckpt)

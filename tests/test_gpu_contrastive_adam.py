@@ -116,7 +116,7 @@ def test_adam_vs_reference_golden(golden_dir, tag):
             assert (diff > 0).float().mean() < 0.01 and diff.max() <= want.float().abs().max() * 2 ** -7
     st = opt.state[p]
     torch.testing.assert_close(st["exp_avg"].cpu(), fx["exp_avg"], atol=1e-8, rtol=1e-6)
-    torch.testing.assert_close(st["exp_avg_sq"].cpu(), fx["exp_avg_sq"], atol=1e-10, rtol=1e-6)
+    torch.testing.assert_close(st["exp_avg_sq"].cpu(), fx["exp_avg_sq"], atol=1e-10, rtol=2e-6)
 
 
 def test_adam_multi_tensor_groups_clip_and_master():

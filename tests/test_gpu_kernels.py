@@ -169,3 +169,43 @@ def test_patchify_and_l2norm(K):
     y, y16 = K.l2_normalize_rows(x.cuda(), want_bf16=True)
     torch.testing.assert_close(y.cpu(), torch.nn.functional.normalize(x, dim=1), atol=1e-6, rtol=1e-6)
     assert relerr(y16, y) < 4e-3
+
+
+def test_grouped_conv1d_matches_torch(K):
+    """Conv1d(C, C, k=19, padding=9, groups=G) on channel-last data == grouped sliding-window GEMM on the halo'd,
+    group-padded buffer (models/adapter/audio.py:57-80)."""
+    B, T, G, cg, cpad, kp = 2, 45, 4, 24, 64, 19
+    C = G * cg
+    halo = kp // 2
+    Tp = T + 2 * halo
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, T, C, device="cuda", generator=g)
+    w = torch.randn(C, cg, kp, device="cuda", generator=g) * 0.1
+    bias = torch.randn(C, device="cuda", generator=g)
+    buf = torch.zeros(B * Tp + kp, G, cpad, dtype=torch.bfloat16, device="cuda")
+    K.pack_group_halo(x.view(B * T, C), buf, B, T, T, 0, Tp, halo, C, cg, cpad)
+    wp = torch.zeros(C, kp, cpad, dtype=torch.bfloat16, device="cuda")
+    wp[:, :, :cg] = w.permute(0, 2, 1).bfloat16()
+    out = torch.empty(B * Tp, C, dtype=torch.float32, device="cuda")
+    K.grouped_conv1d(buf, wp.view(C, kp * cpad), bias, out, B * Tp, G, cpad, kp, cg, epi=K.EPI_STORE_F32)
+    want = torch.nn.functional.conv1d(x.bfloat16().float().transpose(1, 2), w.bfloat16().float(), bias, padding=halo,
+                                      groups=G).transpose(1, 2)
+    got = out.view(B, Tp, C)[:, :T]
+    assert relerr(got, want) < 1e-5
+
+
+def test_layernorm_remap_group_pad_and_accumulate(K):
+    B, Tp, T, d, cg, cpad, halo = 2, 30, 21, 96, 24, 64, 4
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(B * Tp, d, device="cuda", generator=g).bfloat16()
+    out = torch.zeros(B * Tp, (d // cg) * cpad, dtype=torch.bfloat16, device="cuda")
+    K.layernorm(x, None, None, out, rows=B * Tp, dim=d, gelu=True, row_period=Tp, row_valid=T, out_period=Tp,
+                out_row_shift=halo, group_in=cg, group_out=cpad)
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x.float(), (d,)))
+    o = out.view(B, Tp, d // cg, cpad)
+    assert relerr(o[:, halo:halo + T, :, :cg].reshape(B, T, d), want.view(B, Tp, d)[:, :T]) < 6e-3
+    assert torch.all(o[:, :halo] == 0) and torch.all(o[:, halo + T:] == 0) and torch.all(o[..., cg:] == 0)
+    acc = torch.ones(B, T + 1, d, device="cuda")
+    K.layernorm(x, None, None, acc.view(B * (T + 1), d), rows=B * Tp, dim=d, gelu=True, row_period=Tp, row_valid=T,
+                out_period=T + 1, out_row_shift=1, accumulate=True)
+    assert relerr(acc[:, 1:], 1 + want.view(B, Tp, d)[:, :T]) < 1e-5 and torch.all(acc[:, 0] == 1)

@@ -18,10 +18,22 @@ def need_gpu():
         pytest.skip("needs a GPU")
 
 
-def build_hub(sd, head_type, layers, d, ffn, heads, dtype="float32"):
+def build_hub(sd, head_type, layers, d, ffn, heads, dtype="float32", vocab=50264):
     from one_peace_b200.one_peace.hub_interface import from_pretrained
     return from_pretrained(state_dict=sd, head_type=head_type, layers=layers, embed_dim=d, ffn_embed_dim=ffn,
-                           attention_heads=heads, patch_image_size=224, device="cuda", dtype=dtype)
+                           attention_heads=heads, patch_image_size=224, device="cuda", dtype=dtype, vocab_size=vocab)
+
+
+def assert_same_argmax(got_sim, want_sim, what, margin=2e-3):
+    """Retrieval arg-max must be identical wherever the oracle's top-1 margin exceeds `margin` (cosine units).
+    Random synthetic weights produce near-ties (margins ~1e-4) that bf16 operands may legitimately flip; those rows
+    are reported, and must stay a small minority."""
+    top2 = want_sim.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > margin
+    same = got_sim.argmax(1) == want_sim.argmax(1)
+    print(f"{what}: {int(same.sum())}/{same.numel()} identical arg-max, {int(decided.sum())} rows with margin > {margin}")
+    assert bool(same[decided].all()), what
+    assert decided.float().mean() >= 0.5, "synthetic case has too few decided rows to be a test"
 
 
 def check(got, want, what, min_cos=0.999):
@@ -40,7 +52,7 @@ def tiny(golden_dir):
     fx = torch.load(os.path.join(golden_dir, "tiny_retrieval.pt"), weights_only=False)
     # same generator stream as the golden run (all three modalities); the 'vl' model drops the audio keys
     sd = synth.make_state_dict(**fx["config"], seed=fx["weights_seed"])
-    hub = build_hub(sd, "vl", 2, 256, 1024, 4)
+    hub = build_hub(sd, "val", 2, 256, 1024, 4)
     return fx, sd, hub, synth.tiny_inputs(seed=fx["inputs_seed"])
 
 
@@ -54,6 +66,42 @@ def test_tiny_image_features_vs_reference_golden(tiny):
     fx, sd, hub, (tok, img, aud, apm) = tiny
     got = hub.extract_image_features(img)
     check(got, fx["outputs"]["image"], "tiny image vs reference golden")
+
+
+def test_tiny_audio_features_vs_reference_golden(tiny):
+    fx, sd, hub, (tok, img, aud, apm) = tiny
+    got = hub.extract_audio_features(aud, apm)
+    check(got, fx["outputs"]["audio"], "tiny audio vs reference golden")
+
+
+def test_tiny_audio_adapter_output(tiny):
+    fx, sd, hub, (tok, img, aud, apm) = tiny
+    x, pad, bias = hub.model.encoder_wrapper.audio_adapter(aud.cuda(), apm.cuda())
+    ref = fx["adapter"]["audio_x"] * (~apm).unsqueeze(-1)
+    err = (x.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(x.cpu().flatten(1), ref.flatten(1)).min().item()
+    print("audio adapter rel err", err, "cos", cos)
+    assert err < 3e-2 and cos > 0.9995          # 8 bf16 conv GEMMs + 5 grouped convs, each followed by LN/GELU
+    S = x.shape[1]
+    torch.testing.assert_close(bias[0][:, :, :S].cpu(), fx["adapter"]["audio_bias"], atol=0, rtol=0)
+    assert torch.equal(pad.bool().cpu(), apm)
+
+
+def test_audio_15s_shape_and_oracle():
+    """Full-length clip geometry (240000 samples -> 749 frames + CLS, S = 750) at the tiny width vs the oracle."""
+    need_gpu()
+    sd = synth.make_state_dict(embed_dim=256, ffn=1024, layers=1, heads=4, seed=7, vocab=64)
+    hub = build_hub(sd, "val", 1, 256, 1024, 4, vocab=64)
+    g = torch.Generator().manual_seed(3)
+    aud = torch.nn.functional.layer_norm(torch.randn(2, 240000, generator=g), (240000,))
+    apm = torch.zeros(2, 750, dtype=torch.bool)
+    apm[1, 600:] = True
+    aud[1, 600 * 320:] = 0
+    cfg = R.OracleConfig(embed_dim=256, ffn_embed_dim=1024, layers=1, attention_heads=4)
+    with torch.no_grad():
+        want = R.extract_features(sd, cfg, "audio", src_audios=aud, audio_padding_masks=apm)
+    got = hub.extract_audio_features(aud, apm)
+    check(got, want, "15 s audio vs oracle")
 
 
 def test_tiny_adapter_outputs(tiny):
@@ -83,8 +131,8 @@ def test_tiny_retrieval_argmax_matches_oracle(tiny):
     gt = hub.extract_text_features(tok).float().cpu()
     gi = hub.extract_image_features(imgs).float().cpu()
     check(gt, wt, "text vs oracle"); check(gi, wi, "image vs oracle")
-    assert torch.equal((gt @ gi.t()).argmax(1), (wt @ wi.t()).argmax(1))
-    assert torch.equal((gi @ gt.t()).argmax(1), (wi @ wt.t()).argmax(1))
+    assert_same_argmax(gt @ gi.t(), wt @ wi.t(), "t2i")
+    assert_same_argmax(gi @ gt.t(), wi @ wt.t(), "i2t")
 
 
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
@@ -93,7 +141,7 @@ def test_4b_width_slice_vs_oracle(dtype):
     need_gpu()
     sd = synth.make_state_dict(embed_dim=1536, ffn=6144, layers=3, heads=24, modalities=("text", "image"), seed=4,
                                vocab=2048)
-    hub = build_hub(sd, "vl", 3, 1536, 6144, 24, dtype=dtype)
+    hub = build_hub(sd, "vl", 3, 1536, 6144, 24, dtype=dtype, vocab=2048)
     cfg = R.OracleConfig(embed_dim=1536, ffn_embed_dim=6144, layers=3, attention_heads=24)
     tok, img, _, _ = synth.tiny_inputs(seed=2, n_text=6, text_len=20, n_img=4, vocab=2048)
     with torch.no_grad():
@@ -107,7 +155,7 @@ def test_4b_width_slice_vs_oracle(dtype):
     gi = hub.extract_image_features(img)
     check(gt, wt, f"4B-width text ({dtype})"); check(gi, wi, f"4B-width image ({dtype})")
     gt, gi = gt.float().cpu(), gi.float().cpu()
-    assert torch.equal((gt @ gi.t()).argmax(1), (wt @ wi.t()).argmax(1))
+    assert_same_argmax(gt @ gi.t(), wt @ wi.t(), "t2i (4B width)")
 
 
 def test_forward_refuses_to_build_a_fake_graph(tiny):
