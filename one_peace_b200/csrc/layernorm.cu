@@ -1,6 +1,6 @@
 // Row LayerNorm kernels (eps inside the sqrt, biased variance — torch.nn.LayerNorm semantics, which is
 // what one_peace/models/components.py:23-26 builds).  HBM-bound: one pass, the row lives in registers,
-// two-step mean / centred variance in fp32, 16-byte vector loads/stores, one CTA per row.
+// two-step mean / centred variance in fp32, 16-byte vector loads/stores, one warp per row.
 //
 //   in : fp32 (residual stream) or bf16 (GEMM / attention outputs), row pitch ld_in
 //   out: bf16 (feeds the next tcgen05 GEMM as its K-major A operand) or fp32
@@ -68,52 +68,74 @@ OPB_DEVICE void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-OPB_DEVICE float block_sum(float v, float* red) {
-  v = warp_sum(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (blockDim.x + 31) >> 5;
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int i = 0; i < nwarps; ++i) t += red[i];   // fixed order: identical in every thread
-  return t;
-}
-
-template <typename TIn, typename TOut, int ITERS>
-__global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
-  __shared__ float red[8];
-  const int row = blockIdx.x;
-  if (a.row_period > 0 && (row % a.row_period) >= a.row_valid) return;   // whole CTA exits together
+// One WARP per row: the whole row is fetched with all of the lane's 16-byte loads in flight at once (VPL vectors
+// of 8 elements per lane), reduced with shuffles only (no shared memory, no block barriers), normalised from
+// registers and written once.  4 rows per 128-thread CTA.  (The first version used one CTA per row with a single
+// outstanding load per thread and reached only ~3.5 TB/s; a row of 1536 fp32 is 6 KB, so ~50 KB must be in flight
+// per SM to cover HBM latency.)
+template <typename TIn, typename TOut, int VPL>
+__global__ void __launch_bounds__(128) layernorm_kernel(const LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  if (a.row_period > 0 && (row % a.row_period) >= a.row_valid) return;   // warp-uniform
   const TIn* in = reinterpret_cast<const TIn*>(a.in) + static_cast<long>(row) * a.ld_in;
-  float x[ITERS][8];
-  float sum = 0.f;
+  const int nvec = a.dim >> 3;
+
+  // raw loads first (kept packed), then convert
+  constexpr bool kInF32 = sizeof(TIn) == 4;
+  uint4 raw[VPL * (kInF32 ? 2 : 1)];
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const int c = (i * blockDim.x + threadIdx.x) * 8;
-    if (c < a.dim) {
-      load8<TIn>(in + c, x[i]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += x[i][e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[i][e] = 0.f;
+  for (int i = 0; i < VPL; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      if constexpr (kInF32) {
+        raw[2 * i] = *reinterpret_cast<const uint4*>(in + v * 8);
+        raw[2 * i + 1] = *reinterpret_cast<const uint4*>(in + v * 8 + 4);
+      } else {
+        raw[i] = *reinterpret_cast<const uint4*>(in + v * 8);
+      }
     }
   }
-  const float mean = block_sum(sum, red) / a.dim;
+  auto unpack = [&](int i, float (&x)[8]) {
+    if constexpr (kInF32) {
+      x[0] = __uint_as_float(raw[2 * i].x); x[1] = __uint_as_float(raw[2 * i].y);
+      x[2] = __uint_as_float(raw[2 * i].z); x[3] = __uint_as_float(raw[2 * i].w);
+      x[4] = __uint_as_float(raw[2 * i + 1].x); x[5] = __uint_as_float(raw[2 * i + 1].y);
+      x[6] = __uint_as_float(raw[2 * i + 1].z); x[7] = __uint_as_float(raw[2 * i + 1].w);
+    } else {
+      float2 f;
+      f = unpack_bf16x2(raw[i].x); x[0] = f.x; x[1] = f.y;
+      f = unpack_bf16x2(raw[i].y); x[2] = f.x; x[3] = f.y;
+      f = unpack_bf16x2(raw[i].z); x[4] = f.x; x[5] = f.y;
+      f = unpack_bf16x2(raw[i].w); x[6] = f.x; x[7] = f.y;
+    }
+  };
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (i * 32 + lane < nvec) {
+      float x[8];
+      unpack(i, x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += x[e];
+    }
+  }
+  const float mean = warp_sum(sum) / a.dim;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const int c = (i * blockDim.x + threadIdx.x) * 8;
-    if (c < a.dim) {
+  for (int i = 0; i < VPL; ++i) {
+    if (i * 32 + lane < nvec) {
+      float x[8];
+      unpack(i, x);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float d = x[i][e] - mean;
+        const float d = x[e] - mean;
         sq += d * d;
       }
     }
   }
-  const float var = block_sum(sq, red) / a.dim;
+  const float var = warp_sum(sq) / a.dim;
   const float rstd = rsqrtf(var + a.eps);
 
   long orow = row;
@@ -129,12 +151,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   if (a.row_period > 0) orow = static_cast<long>(row / a.row_period) * a.out_period + (row % a.row_period) + a.out_row_shift;
   TOut* out = reinterpret_cast<TOut*>(a.out) + orow * a.ld_out + ocol0;
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const int c = (i * blockDim.x + threadIdx.x) * 8;
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 8;
     if (c < a.dim) {
       float y[8];
+      unpack(i, y);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = (x[i][e] - mean) * rstd;
+      for (int e = 0; e < 8; ++e) y[e] = (y[e] - mean) * rstd;
       if (a.gamma != nullptr) {
         float gm[8], bt[8];
         load8<float>(a.gamma + c, gm);
@@ -162,20 +185,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 
 template <typename TIn, typename TOut>
 static int launch_ln(const LnArgs& a, cudaStream_t stream) {
-  const int vecs = a.dim / 8;
-  // threads: enough for <= 3 vectors per thread, multiple of 32, <= 256
-  int iters = (vecs + 255) / 256;
-  if (iters < 1) iters = 1;
-  int threads = (vecs + iters - 1) / iters;
-  threads = ((threads + 31) / 32) * 32;
-  if (threads > 256) return OPB_ERR_UNSUPPORTED;
-  switch (iters) {
-    case 1: layernorm_kernel<TIn, TOut, 1><<<a.rows, threads, 0, stream>>>(a); break;
-    case 2: layernorm_kernel<TIn, TOut, 2><<<a.rows, threads, 0, stream>>>(a); break;
-    case 3: layernorm_kernel<TIn, TOut, 3><<<a.rows, threads, 0, stream>>>(a); break;
-    case 4: layernorm_kernel<TIn, TOut, 4><<<a.rows, threads, 0, stream>>>(a); break;
-    default: return OPB_ERR_UNSUPPORTED;
-  }
+  const int need = (a.dim / 8 + 31) / 32;      // vectors per lane
+  const unsigned grid = (a.rows + 3) / 4;
+#define OPB_LN(V) layernorm_kernel<TIn, TOut, V><<<grid, 128, 0, stream>>>(a)
+  if (need <= 1) OPB_LN(1);
+  else if (need <= 2) OPB_LN(2);
+  else if (need <= 4) OPB_LN(4);
+  else if (need <= 6) OPB_LN(6);
+  else if (need <= 8) OPB_LN(8);
+  else if (sizeof(TIn) == 2 && need <= 12) OPB_LN(12);
+  else if (sizeof(TIn) == 2 && need <= 24) OPB_LN(24);
+  else return OPB_ERR_UNSUPPORTED;            // rows wider than 6144 (bf16) / 2048 (fp32) are not on this path
+#undef OPB_LN
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
