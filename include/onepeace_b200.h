@@ -82,9 +82,47 @@ int opb_grouped_conv1d_bf16(const void* X, const void* W, int rows, int groups, 
  *   qkv  bf16 [B*S, 3*H*64] (q | k | v, q already scaled), out bf16 [B*S, H*64]
  *   bias fp32 [H, S, s_pad] or NULL (s_pad even, >= S);  key_pad uint8 [B, S] (1 = pad) or NULL
  *   lse  fp32 [B, H, S] or NULL (log-sum-exp per query row, kept for the backward pass)
+ *   ln_stats fp32 [H, B*S, 2] or NULL: per-(head, row) partial (sum, sum of squares) of the output row, from which
+ *        opb_ln_stats_finalize derives the statistics of the inner LayerNorm (multihead_attention.py:122-123) that
+ *        the out_proj GEMM then applies in its epilogue
  */
-int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, int B,
-                      int S, int H, int s_pad, void* stream);
+int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse,
+                      float* ln_stats, int B, int S, int H, int s_pad, void* stream);
+
+/*
+ * GEMM with the full epilogue description (superset of opb_gemm_bf16).  Adds the fused-LayerNorm form
+ *   LN(x) W^T + b  =  rstd[m] * (acc - mu[m] * colsum[n]) + bias'[n]
+ * where A holds the UN-normalised rows (bf16), B = W * diag(ln_weight) (bf16), colsum[n] = sum_k B[n,k],
+ * bias'[n] = sum_k ln_bias[k] W[n,k] + b[n]; and the side outputs that feed the NEXT LayerNorm: stats_out
+ * [ceil(N/256) (or N/256 for GEGLU), M, 2] partial (sum, sum of squares) of the stored values, and out_bf16 (a bf16
+ * copy of the fp32 output of OPB_EPI_RESID_F32).  This replaces the four LayerNorm passes per encoder layer of
+ * models/transformer/transformer_layer.py:185,202 / multihead_attention.py:122-123 / transformer_layer.py:154.
+ */
+typedef struct opb_gemm_args {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  int32_t M, N, K, epi;
+  void* out; int64_t ldo;
+  const float* bias; const float* colscale; const float* gamma; const float* resid; int64_t ldr;
+  int32_t out_group, out_group_stride, out_row_offset, out_group_valid, resid_period, resid_row_offset;
+  const float* ln_mu; const float* ln_rstd; const float* ln_colsum;
+  float* stats_out;
+  void* out_bf16; int64_t ldo_bf16;
+  int32_t cta_group; int32_t reserved;
+} opb_gemm_args;
+int opb_gemm_bf16_ex(const opb_gemm_args* args, void* stream);
+
+/*
+ * Row statistics + cast: out_bf16[r,:] = bf16(x[r,:]) (UN-normalised), mu[r] = mean, rstd[r] = 1/sqrt(var + eps).
+ * Prepares the first encoder layer's input for the fused-LayerNorm GEMMs (later layers get the same three tensors
+ * from the preceding GEMM's epilogue).
+ */
+int opb_row_stats_cast(const float* x, int64_t ld_in, void* out_bf16, int64_t ld_out, float* mu, float* rstd,
+                       int rows, int dim, float eps, void* stream);
+
+/* mu[r], rstd[r] from `parts` partial (sum, sumsq) records per row (layout [parts, rows, 2]); deterministic order. */
+int opb_ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
+                          void* stream);
 
 /*
  * Row LayerNorm (torch.nn.LayerNorm semantics; models/components.py:23-26) with optional exact GELU and

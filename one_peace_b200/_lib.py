@@ -24,8 +24,11 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     "opb_pack_group_halo": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_void_p]),
-    "opb_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                  c_void_p]),
+    "opb_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_void_p]),
+    "opb_gemm_bf16_ex": (c_int, [c_void_p, c_void_p]),
+    "opb_row_stats_cast": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "opb_ln_stats_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "opb_layernorm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int,
                               c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "opb_text_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -50,6 +53,19 @@ SIGNATURES = {
                                     c_float, c_float, c_void_p, c_void_p]),
     "opb_grad_norm_clip": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p]),
 }
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of `opb_gemm_args` (include/onepeace_b200.h)."""
+    _fields_ = [("A", c_void_p), ("lda", c_int64), ("B", c_void_p), ("ldb", c_int64),
+                ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("epi", ctypes.c_int32),
+                ("out", c_void_p), ("ldo", c_int64),
+                ("bias", c_void_p), ("colscale", c_void_p), ("gamma", c_void_p), ("resid", c_void_p), ("ldr", c_int64),
+                ("out_group", ctypes.c_int32), ("out_group_stride", ctypes.c_int32), ("out_row_offset", ctypes.c_int32),
+                ("out_group_valid", ctypes.c_int32), ("resid_period", ctypes.c_int32), ("resid_row_offset", ctypes.c_int32),
+                ("ln_mu", c_void_p), ("ln_rstd", c_void_p), ("ln_colsum", c_void_p),
+                ("stats_out", c_void_p), ("out_bf16", c_void_p), ("ldo_bf16", c_int64),
+                ("cta_group", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
 
 _lib = None
 

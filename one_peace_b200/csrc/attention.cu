@@ -17,6 +17,8 @@
 // tiles).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace opb {
 
 constexpr int kHd = 64;          // head dim (all ONE-PEACE configs: 1536/24 = 256/4 = 64)
@@ -64,10 +66,11 @@ __host__ __device__ inline int bias_stride_for(int s_pad) {
   return st;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
                      const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                     int B, int S, int H, int s_pad, int batch_per_cta, int stage_bias) {
+                     float* __restrict__ ln_stats, int B, int S, int H, int s_pad, int batch_per_cta,
+                     int stage_bias) {
   extern __shared__ __align__(16) uint8_t attn_smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(attn_smem_raw);
 
@@ -261,6 +264,26 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
       l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
       const float inv_lo = l_lo > 0.f ? 1.f / l_lo : 0.f;
       const float inv_hi = l_hi > 0.f ? 1.f / l_hi : 0.f;
+      if (ln_stats != nullptr) {
+        // per-(head, row) partial (sum, sum of squares) of the output row: the inner LayerNorm over all heads
+        // (multihead_attention.py:122-123) is finished inside the out_proj GEMM epilogue
+        float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+          const float a0 = o[nd][0] * inv_lo, a1 = o[nd][1] * inv_lo, a2 = o[nd][2] * inv_hi, a3 = o[nd][3] * inv_hi;
+          s_lo += a0 + a1; q_lo += a0 * a0 + a1 * a1;
+          s_hi += a2 + a3; q_hi += a2 * a2 + a3 * a3;
+        }
+        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+        q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1); q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 2);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+        q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1); q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 2);
+        const long rows_total = static_cast<long>(B) * S;
+        if (t == 0 && qrow_lo < S)
+          *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow_lo) * 2) = make_float2(s_lo, q_lo);
+        if (t == 0 && qrow_hi < S)
+          *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow_hi) * 2) = make_float2(s_hi, q_hi);
+      }
       if (qrow_lo < S) {
         __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow_lo) * D + h * kHd + 2 * t;
 #pragma unroll
@@ -279,11 +302,16 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   }
 }
 
-int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, int B, int S,
-                  int H, int s_pad, cudaStream_t stream) {
+int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, float* ln_stats,
+                  int B, int S, int H, int s_pad, cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0) return OPB_ERR_INVALID;
   if (bias != nullptr && (s_pad < S || (s_pad & 3))) return OPB_ERR_INVALID;
-  const int stage_bias = (bias != nullptr && s_pad <= kMaxStagedBiasCols) ? 1 : 0;
+  // Staging the bias tile in shared memory costs occupancy (100 KB / CTA -> 2 CTAs per SM) and measured SLOWER on
+  // B200 (240-255 us vs 202 us per layer at B=64, S=197, H=24 — profiles/r01_attention_sweep.log): the kernel is
+  // latency- not bandwidth-bound.  It stays available behind OPB_ATTN_STAGE_BIAS=1 for experiments.
+  static const char* env_stage = getenv("OPB_ATTN_STAGE_BIAS");
+  static const char* env_bpc = getenv("OPB_ATTN_BPC");
+  int stage_bias = (bias != nullptr && s_pad <= kMaxStagedBiasCols && env_stage != nullptr && env_stage[0] == '1') ? 1 : 0;
   const size_t smem = sizeof(AttnSmem) + (stage_bias ? sizeof(float) * kQTile * bias_stride_for(s_pad) : 0);
   static size_t configured_smem = 0;
   if (smem > configured_smem) {
@@ -298,10 +326,11 @@ int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, vo
   if (stage_bias) {
     while (bpc < 8 && static_cast<long>(H) * q_chunks * ((B + 2 * bpc - 1) / (2 * bpc)) >= 148L * 4) bpc *= 2;
   }
+  if (env_bpc != nullptr) bpc = max(1, atoi(env_bpc));
   const long grid = static_cast<long>(H) * q_chunks * ((B + bpc - 1) / bpc);
   attention_fwd_kernel<<<static_cast<unsigned>(grid), 128, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), bias, key_pad, reinterpret_cast<__nv_bfloat16*>(out), lse, B, S,
-      H, s_pad, bpc, stage_bias);
+      reinterpret_cast<const __nv_bfloat16*>(qkv), bias, key_pad, reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats,
+      B, S, H, s_pad, bpc, stage_bias);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

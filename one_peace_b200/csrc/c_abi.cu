@@ -42,10 +42,41 @@ int opb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
                         static_cast<cudaStream_t>(stream));
 }
 
-int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, int B,
-                      int S, int H, int s_pad, void* stream) {
+int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse,
+                      float* ln_stats, int B, int S, int H, int s_pad, void* stream) {
   if (qkv == nullptr || out == nullptr) return OPB_ERR_INVALID;
-  return opb::attention_fwd(qkv, bias, key_pad, out, lse, B, S, H, s_pad, static_cast<cudaStream_t>(stream));
+  return opb::attention_fwd(qkv, bias, key_pad, out, lse, ln_stats, B, S, H, s_pad,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int opb_gemm_bf16_ex(const opb_gemm_args* a, void* stream) {
+  if (a == nullptr || a->A == nullptr || a->B == nullptr || a->out == nullptr) return OPB_ERR_INVALID;
+  if ((a->ln_mu == nullptr) != (a->ln_rstd == nullptr) || (a->ln_mu == nullptr) != (a->ln_colsum == nullptr))
+    return OPB_ERR_INVALID;
+  opb::GemmEpilogue ep;
+  ep.out = a->out; ep.ldo = a->ldo;
+  ep.bias = a->bias; ep.colscale = a->colscale; ep.gamma = a->gamma; ep.resid = a->resid; ep.ldr = a->ldr;
+  ep.out_group = a->out_group; ep.out_group_stride = a->out_group_stride; ep.out_row_offset = a->out_row_offset;
+  ep.out_group_valid = a->out_group_valid; ep.resid_period = a->resid_period; ep.resid_row_offset = a->resid_row_offset;
+  ep.ln_mu = a->ln_mu; ep.ln_rstd = a->ln_rstd; ep.ln_colsum = a->ln_colsum;
+  ep.stats_out = a->stats_out; ep.out_bf16 = a->out_bf16; ep.ldo_bf16 = a->ldo_bf16;
+  return opb::gemm_bf16(a->A, static_cast<int>(a->lda), a->B, static_cast<int>(a->ldb), a->M, a->N, a->K, a->epi, ep,
+                        a->cta_group, static_cast<cudaStream_t>(stream));
+}
+
+int opb_row_stats_cast(const float* x, int64_t ld_in, void* out_bf16, int64_t ld_out, float* mu, float* rstd,
+                       int rows, int dim, float eps, void* stream) {
+  if (!x || !out_bf16 || !mu || !rstd) return OPB_ERR_INVALID;
+  opb::LnRemap rm;
+  rm.raw = 1; rm.mu_out = mu; rm.rstd_out = rstd;
+  return opb::layernorm(x, 0, ld_in, out_bf16, 1, ld_out, nullptr, nullptr, rows, dim, eps, 0, 0, rm,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int opb_ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
+                          void* stream) {
+  if (!partial || !mu || !rstd) return OPB_ERR_INVALID;
+  return opb::ln_stats_finalize(partial, parts, rows, dim, eps, mu, rstd, static_cast<cudaStream_t>(stream));
 }
 
 int opb_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype, int64_t ld_out,

@@ -32,6 +32,17 @@ struct GemmEpilogue {
   // optional broadcast residual: resid_row = (m % resid_period) + resid_row_offset
   int resid_period = 0;
   int resid_row_offset = 0;
+  // Fused LayerNorm of the A operand (A holds the UN-normalised rows in bf16, B holds W * diag(ln_weight)):
+  //   LN(x) W^T + b = rstd[m] * (acc - mu[m] * colsum[n]) + bias'[n],  colsum[n] = sum_k B[n,k],
+  //   bias'[n] = sum_k ln_bias[k] W[n,k] + b[n]  (passed through `bias`)
+  const float* ln_mu = nullptr;      // [M]
+  const float* ln_rstd = nullptr;    // [M]
+  const float* ln_colsum = nullptr;  // [N]
+  // side outputs for the NEXT LayerNorm (EPI_RESID_F32 / EPI_GEGLU_BF16): per (n-tile, row) partial (sum, sum of
+  // squares) of the stored values, and (EPI_RESID_F32) a bf16 copy of the output that feeds the next GEMM
+  float* stats_out = nullptr;        // [n_tiles, M, 2]
+  void* out_bf16 = nullptr;
+  long ldo_bf16 = 0;
   // contrastive-head epilogues
   const float* scale_ptr = nullptr;  // device scalar: exp(clamp(logit_scale))
   const float* row_lse = nullptr;    // [M] log-sum-exp per row (EPI_SOFTMAX_GRAD)

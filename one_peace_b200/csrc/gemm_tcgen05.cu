@@ -196,6 +196,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (ep.out_group > 0) out_row = static_cast<long>(row / ep.out_group) * ep.out_group_stride + (row % ep.out_group) + ep.out_row_offset;
       long res_row = out_row;
       if (ep.resid_period > 0) res_row = (row % ep.resid_period) + ep.resid_row_offset;
+      float ln_mu = 0.f, ln_rs = 1.f;
+      if (ep.ln_mu != nullptr) {
+        const int rc = row < M ? row : M - 1;
+        ln_mu = ep.ln_mu[rc];
+        ln_rs = ep.ln_rstd[rc];
+      }
+      float st_sum = 0.f, st_sq = 0.f;   // partial statistics of the stored values (next LayerNorm)
 
       if constexpr (EPI == EPI_GEGLU_BF16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + n_blk * (kBlockN / 2);
@@ -216,19 +223,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (n_blk * (kBlockN / 2) + c + j < n_out) {
-                uint4 o;
-                uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+                float ga[8], li[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float a0 = gelu_erf(__uint_as_float(g[j + 2 * e])) * __uint_as_float(l[j + 2 * e]);
-                  float a1 = gelu_erf(__uint_as_float(g[j + 2 * e + 1])) * __uint_as_float(l[j + 2 * e + 1]);
-                  po[e] = pack_bf16x2(a0, a1);
+                for (int e = 0; e < 8; ++e) { ga[e] = __uint_as_float(g[j + e]); li[e] = __uint_as_float(l[j + e]); }
+                const int pc = n_blk * kBlockN + c + j;          // packed (interleaved) weight row of the gate half
+                if (ep.ln_mu != nullptr) {
+                  float cg[8], cl[8];
+                  *reinterpret_cast<float4*>(cg) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc);
+                  *reinterpret_cast<float4*>(cg + 4) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc + 4);
+                  *reinterpret_cast<float4*>(cl) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc + kBlockN / 2);
+                  *reinterpret_cast<float4*>(cl + 4) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc + kBlockN / 2 + 4);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    ga[e] = ln_rs * (ga[e] - ln_mu * cg[e]);
+                    li[e] = ln_rs * (li[e] - ln_mu * cl[e]);
+                  }
                 }
+                if (ep.bias != nullptr) {
+                  float bg[8], bl[8];
+                  *reinterpret_cast<float4*>(bg) = *reinterpret_cast<const float4*>(ep.bias + pc);
+                  *reinterpret_cast<float4*>(bg + 4) = *reinterpret_cast<const float4*>(ep.bias + pc + 4);
+                  *reinterpret_cast<float4*>(bl) = *reinterpret_cast<const float4*>(ep.bias + pc + kBlockN / 2);
+                  *reinterpret_cast<float4*>(bl + 4) = *reinterpret_cast<const float4*>(ep.bias + pc + kBlockN / 2 + 4);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { ga[e] += bg[e]; li[e] += bl[e]; }
+                }
+                float u[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  u[e] = gelu_erf(ga[e]) * li[e];
+                  st_sum += u[e];
+                  st_sq += u[e] * u[e];
+                }
+                uint4 o;
+                o.x = pack_bf16x2(u[0], u[1]);
+                o.y = pack_bf16x2(u[2], u[3]);
+                o.z = pack_bf16x2(u[4], u[5]);
+                o.w = pack_bf16x2(u[6], u[7]);
                 *reinterpret_cast<uint4*>(out + c + j) = o;
               }
             }
           }
         }
+        if (row_ok && ep.stats_out != nullptr)
+          *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
       } else if constexpr (EPI == EPI_LSE_PARTIAL) {
         // z = scale * acc.  Each thread owns one row of the tile: all reductions are thread-local.
         const float scale = *ep.scale_ptr;
@@ -336,6 +374,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j + e]);
+            if (ep.ln_mu != nullptr) {
+              const float4 c0 = *reinterpret_cast<const float4*>(ep.ln_colsum + col);
+              const float4 c1 = *reinterpret_cast<const float4*>(ep.ln_colsum + col + 4);
+              x[0] = ln_rs * (x[0] - ln_mu * c0.x); x[1] = ln_rs * (x[1] - ln_mu * c0.y);
+              x[2] = ln_rs * (x[2] - ln_mu * c0.z); x[3] = ln_rs * (x[3] - ln_mu * c0.w);
+              x[4] = ln_rs * (x[4] - ln_mu * c1.x); x[5] = ln_rs * (x[5] - ln_mu * c1.y);
+              x[6] = ln_rs * (x[6] - ln_mu * c1.z); x[7] = ln_rs * (x[7] - ln_mu * c1.w);
+            }
             if (ep.bias != nullptr) {
               const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col);
               const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
@@ -378,8 +424,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               float* o = reinterpret_cast<float*>(ep.out) + out_row * ep.ldo + col;
               *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              if constexpr (EPI == EPI_RESID_F32) {
+                if (ep.stats_out != nullptr) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { st_sum += x[e]; st_sq += x[e] * x[e]; }
+                }
+                if (ep.out_bf16 != nullptr) {
+                  uint4 ob;
+                  ob.x = pack_bf16x2(x[0], x[1]);
+                  ob.y = pack_bf16x2(x[2], x[3]);
+                  ob.z = pack_bf16x2(x[4], x[5]);
+                  ob.w = pack_bf16x2(x[6], x[7]);
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + out_row * ep.ldo_bf16 + col) = ob;
+                }
+              }
             }
           }
+        }
+        if constexpr (EPI == EPI_RESID_F32) {
+          if (row_ok && ep.stats_out != nullptr)
+            *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
         }
       }
     }

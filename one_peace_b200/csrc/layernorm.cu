@@ -32,6 +32,10 @@ struct LnArgs {
   // channel-group padding (0 = off): output column = (c / group_in) * group_out + c % group_in
   int group_in, group_out;
   int accumulate;   // fp32 output only: out += y
+  // statistics-only mode: write the UN-normalised row (cast to TOut) plus mean / rstd, for the fused-LN GEMMs
+  int raw;
+  float* mu_out;
+  float* rstd_out;
 };
 
 template <typename T>
@@ -138,6 +142,20 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const LnArgs a) {
   const float var = warp_sum(sq) / a.dim;
   const float rstd = rsqrtf(var + a.eps);
 
+  if (a.raw) {
+    if (lane == 0) { a.mu_out[row] = mean; a.rstd_out[row] = rstd; }
+    TOut* o = reinterpret_cast<TOut*>(a.out) + static_cast<long>(row) * a.ld_out;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < a.dim) {
+        float y[8];
+        unpack(i, y);
+        store8<TOut>(o + c, y);
+      }
+    }
+    return;
+  }
   long orow = row;
   long ocol0 = 0;
   if (a.merge_grid_w > 0) {
@@ -200,6 +218,32 @@ static int launch_ln(const LnArgs& a, cudaStream_t stream) {
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
+// Reduces the per-(part, row) partial (sum, sum of squares) written by the producing GEMM / attention epilogues to
+// the row mean and 1/sqrt(var + eps) the consuming GEMM epilogue applies (fused LayerNorm, see gemm.h).  Parts are
+// summed in index order (deterministic).  var = E[x^2] - mean^2 in fp32, clamped at 0.
+__global__ void ln_stats_finalize_kernel(const float* __restrict__ partial, int parts, int rows, int dim, float eps,
+                                         float* __restrict__ mu, float* __restrict__ rstd) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f, q = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    const float2 v = *reinterpret_cast<const float2*>(partial + (static_cast<long>(p) * rows + r) * 2);
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s / dim;
+  const float var = fmaxf(q / dim - mean * mean, 0.f);
+  mu[r] = mean;
+  rstd[r] = rsqrtf(var + eps);
+}
+
+int ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
+                      cudaStream_t stream) {
+  if (parts <= 0 || rows <= 0 || dim <= 0) return OPB_ERR_INVALID;
+  ln_stats_finalize_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(partial, parts, rows, dim, eps, mu, rstd);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
 // in_dtype / out_dtype: 0 = fp32, 1 = bf16
 int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const float* gamma,
               const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, const LnRemap& rm,
@@ -211,7 +255,8 @@ int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype
   if (rm.accumulate && out_dtype != 0) return OPB_ERR_INVALID;
   if (rm.row_period > 0 && merge_grid_w > 0) return OPB_ERR_INVALID;
   LnArgs a{in, out, gamma, beta, ld_in, ld_out, rows, dim, eps, gelu, merge_grid_w, rm.row_period, rm.row_valid,
-           rm.out_period, rm.out_row_shift, rm.group_in, rm.group_out, rm.accumulate};
+           rm.out_period, rm.out_row_shift, rm.group_in, rm.group_out, rm.accumulate, rm.raw, rm.mu_out, rm.rstd_out};
+  if (rm.raw && (rm.mu_out == nullptr || rm.rstd_out == nullptr)) return OPB_ERR_INVALID;
   if (in_dtype == 0 && out_dtype == 1) return launch_ln<float, __nv_bfloat16>(a, stream);
   if (in_dtype == 1 && out_dtype == 1) return launch_ln<__nv_bfloat16, __nv_bfloat16>(a, stream);
   if (in_dtype == 0 && out_dtype == 0) return launch_ln<float, float>(a, stream);

@@ -5,13 +5,18 @@
 
 namespace opb {
 
-int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, int B, int S,
-                  int H, int s_pad, cudaStream_t stream);
+int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, float* ln_stats,
+                  int B, int S, int H, int s_pad, cudaStream_t stream);
+int ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
+                      cudaStream_t stream);
 
 struct LnRemap {
   int row_period = 0, row_valid = 0, out_period = 0, out_row_shift = 0;
   int group_in = 0, group_out = 0;
   int accumulate = 0;
+  int raw = 0;
+  float* mu_out = nullptr;
+  float* rstd_out = nullptr;
 };
 int layernorm(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const float* gamma,
               const float* beta, int rows, int dim, float eps, int gelu, int merge_grid_w, const LnRemap& rm,

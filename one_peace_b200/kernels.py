@@ -72,7 +72,51 @@ def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, ou
     return out
 
 
-def attention(qkv, bias, key_pad, B, S, H, out=None, lse=None):
+def gemm_ln(a, w, epi, out, *, ln_mu=None, ln_rstd=None, ln_colsum=None, bias=None, colscale=None, gamma=None,
+            resid=None, stats_out=None, out_bf16=None, cta_group=0):
+    """GEMM through `opb_gemm_bf16_ex`: fused LayerNorm of the A operand (ln_*), statistics / bf16 side outputs."""
+    _need_cuda(a, w, out)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(-1) == 1 and w.stride(1) == 1
+    M, Kd = a.shape
+    N = w.shape[0]
+    args = _lib.GemmArgs()
+    args.A, args.lda, args.B, args.ldb = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+    args.M, args.N, args.K, args.epi = M, N, Kd, epi
+    args.out, args.ldo = out.data_ptr(), out.stride(-2)
+    args.bias, args.colscale, args.gamma, args.resid = _ptr(bias) or None, _ptr(colscale) or None, _ptr(gamma) or None, _ptr(resid) or None
+    args.ldr = resid.stride(-2) if resid is not None else 0
+    args.ln_mu, args.ln_rstd, args.ln_colsum = _ptr(ln_mu) or None, _ptr(ln_rstd) or None, _ptr(ln_colsum) or None
+    args.stats_out = _ptr(stats_out) or None
+    args.out_bf16 = _ptr(out_bf16) or None
+    args.ldo_bf16 = out_bf16.stride(-2) if out_bf16 is not None else 0
+    args.cta_group = cta_group
+    if PROFILE_HOOK is not None:
+        PROFILE_HOOK("gemm_begin", 0.0, None)
+    import ctypes as _ct
+    st = _lib.load().opb_gemm_bf16_ex(_ct.addressof(args), _stream())
+    _lib.check(st, "opb_gemm_bf16_ex")
+    _count()
+    if PROFILE_HOOK is not None:
+        PROFILE_HOOK("gemm", 2.0 * M * N * Kd, (M, N, Kd, epi))
+    return out
+
+
+def row_stats_cast(x, out_bf16, mu, rstd, eps=1e-5):
+    rows, dim = x.shape
+    st = _lib.load().opb_row_stats_cast(x.data_ptr(), x.stride(0), out_bf16.data_ptr(), out_bf16.stride(0), mu.data_ptr(),
+                                        rstd.data_ptr(), rows, dim, eps, _stream())
+    _lib.check(st, "opb_row_stats_cast")
+    _count()
+
+
+def ln_stats_finalize(partial, parts, rows, dim, eps, mu, rstd):
+    st = _lib.load().opb_ln_stats_finalize(partial.data_ptr(), parts, rows, dim, eps, mu.data_ptr(), rstd.data_ptr(),
+                                           _stream())
+    _lib.check(st, "opb_ln_stats_finalize")
+    _count()
+
+
+def attention(qkv, bias, key_pad, B, S, H, out=None, lse=None, ln_stats=None):
     _need_cuda(qkv, bias, key_pad)
     D = H * 64
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
@@ -84,8 +128,8 @@ def attention(qkv, bias, key_pad, B, S, H, out=None, lse=None):
         s_pad = bias.shape[2]
     if key_pad is not None:
         assert key_pad.dtype == torch.uint8 and key_pad.shape == (B, S) and key_pad.is_contiguous()
-    st = _lib.load().opb_attention_fwd(qkv.data_ptr(), _ptr(bias), _ptr(key_pad), out.data_ptr(), _ptr(lse), B, S,
-                                       H, s_pad, _stream())
+    st = _lib.load().opb_attention_fwd(qkv.data_ptr(), _ptr(bias), _ptr(key_pad), out.data_ptr(), _ptr(lse),
+                                       _ptr(ln_stats), B, S, H, s_pad, _stream())
     _lib.check(st, "opb_attention_fwd")
     _count()
     return out

@@ -5,6 +5,8 @@ the reference signature (text_info / image_info / audio_info tuples from the ada
 the tuples carry the fp32 residual stream (B,S,d), a uint8/bool padding mask (or None) and the
 batch-shared (H,S,S_pad) bias table instead of the reference's expanded (B,H,S,S) tensor.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -49,11 +51,18 @@ class TransformerEncoder(FairseqEncoder):
         if pad is not None:
             key_pad = pad.to(torch.uint8).contiguous()
         rows = x.view(B * S, d)
+        fused = os.environ.get("OPB_FUSED_LN", "1") != "0" and all(l.fused_ln_supported() for l in self.layers)
+        if fused:
+            ws = TransformerEncoderLayer.fused_workspace(B * S, d, self.cfg.ffn_embed_dim, self.num_attention_heads, x.device)
+            K.row_stats_cast(rows, ws["xb"], ws["mu"], ws["rstd"], eps=self.layers[0].self_attn_layer_norm.eps)
         for idx, layer in enumerate(self.layers):
             bias = None
             if bias_list:
                 bias = bias_list[0] if len(bias_list) == 1 else bias_list[idx]
-            layer.forward_rows(rows, bias, key_pad, B, S, encoder_type)
+            if fused:
+                layer.forward_rows_fused(rows, ws["xb"], ws["mu"], ws["rstd"], ws, bias, key_pad, B, S, encoder_type)
+            else:
+                layer.forward_rows(rows, bias, key_pad, B, S, encoder_type)
         return x, pad
 
     def forward(self, text_info, image_info, audio_info, return_all_hiddens: bool = False, encoder_type=None):

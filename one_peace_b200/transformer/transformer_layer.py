@@ -5,6 +5,8 @@ Parameter names match the reference (self_attn.*, self_attn_layer_norm, {text,im
 kernel + 4 LayerNorm kernels; the residual stream stays fp32 in HBM and is updated in place by the
 out_proj / fc2 GEMM epilogues (gamma * (acc + bias) + residual — `fused_dropout_res`, :70-88, eval mode).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -86,6 +88,108 @@ class TransformerEncoderLayer(nn.Module):
                 out["g1"], out["g2"] = f32(self.gamma_1), f32(self.gamma_2)
             return out
         return cache.get(ps, build)
+
+    # ------------------------------------------------------------------------------------------------
+    # fused-LayerNorm path: the four LayerNorms of the layer never run as kernels.  Each GEMM consumes the
+    # UN-normalised bf16 rows and applies  rstd * (acc - mu * colsum) + bias'  in its epilogue (gemm.h); the row
+    # statistics come from the epilogue of the kernel that produced those rows.
+    # ------------------------------------------------------------------------------------------------
+    def fused_ln_supported(self):
+        ffn_ok = all(isinstance(getattr(self, f"{m}_ffn")[2], nn.LayerNorm) for m in ("text", "image", "audio")
+                     if hasattr(self, f"{m}_ffn"))
+        return self.self_attn.ln is not None and ffn_ok and self.attn_ln is None and self.self_attn.c_attn is None
+
+    @staticmethod
+    def _fold(weight, ln_w, ln_b, bias):
+        """W [N,K] fp32, LN affine over K -> (bf16 W*diag(g), colsum of the bf16 matrix, bias' = W @ beta + b)."""
+        wf = weight.detach().float()
+        wg = (wf * ln_w.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        colsum = wg.float().sum(dim=1).contiguous()
+        d = wf @ ln_b.detach().float()
+        if bias is not None:
+            d = d + bias.detach().float()
+        return wg, colsum, d.contiguous()
+
+    def _fused_attn_pack(self):
+        cache = self._cache.setdefault("_fused_attn", PackCache())
+        a = self.self_attn
+        ps = [a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.v_proj.weight, a.v_proj.bias, a.out_proj.weight,
+              a.out_proj.bias, a.ln.weight, a.ln.bias, self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias] + \
+             ([self.gamma_1] if self.gamma_1 is not None else [])
+
+        def build():
+            d = self.embed_dim
+            dev = a.q_proj.weight.device
+            wqkv = torch.cat([a.q_proj.weight.detach().float(), a.k_proj.weight.detach().float(),
+                              a.v_proj.weight.detach().float()], 0)
+            bqkv = torch.cat([a.q_proj.bias.detach().float(), torch.zeros(d, device=dev), a.v_proj.bias.detach().float()])
+            w, c, dd = self._fold(wqkv, self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias, bqkv)
+            qs = torch.ones(3 * d, device=dev)
+            qs[:d] = a.scaling
+            wo, co, do = self._fold(a.out_proj.weight, a.ln.weight, a.ln.bias, a.out_proj.bias)
+            return dict(wqkv=w, cqkv=c, dqkv=dd, qscale=qs, wo=wo, co=co, do=do,
+                        g1=f32(self.gamma_1) if self.gamma_1 is not None else None)
+        return cache.get(ps, build)
+
+    def _fused_ffn_pack(self, modality):
+        cache = self._cache.setdefault("_fused_" + modality, PackCache())
+        ffn = getattr(self, f"{modality}_ffn")
+        ln2, lnf = self.final_layer_norm, ffn[2]
+        ps = [ffn[0].wi_0.weight, ffn[0].wi_1.weight, ffn[3].weight, ffn[3].bias, lnf.weight, lnf.bias, ln2.weight,
+              ln2.bias] + ([self.gamma_2] if self.gamma_2 is not None else [])
+
+        def build():
+            g2 = ln2.weight.detach().float()
+            w0 = ffn[0].wi_0.weight.detach().float()
+            w1 = ffn[0].wi_1.weight.detach().float()
+            w01 = interleave_geglu(w0 * g2[None, :], w1 * g2[None, :])
+            c01 = w01.float().sum(dim=1).contiguous()
+            b2 = ln2.bias.detach().float()
+            F_ = w0.shape[0]
+            d01 = torch.stack([(w0 @ b2).view(F_ // 128, 128), (w1 @ b2).view(F_ // 128, 128)], dim=1).reshape(2 * F_).contiguous()
+            w2, c2, d2 = self._fold(ffn[3].weight, lnf.weight, lnf.bias, ffn[3].bias)
+            return dict(w01=w01, c01=c01, d01=d01, w2=w2, c2=c2, d2=d2,
+                        g2=f32(self.gamma_2) if self.gamma_2 is not None else None)
+        return cache.get(ps, build)
+
+    def forward_rows_fused(self, x, xb, mu, rstd, ws, bias, key_pad, B, S, modality):
+        """x fp32 [M,d] residual (in place), xb bf16 [M,d] copy of x, (mu, rstd) [M] row statistics of x.
+        On return x / xb / mu / rstd describe the layer output (ready for the next layer).  `ws` = workspace dict."""
+        if self.training and (self.dropout_prob > 0 or self.drop_path_prob > 0):
+            raise NotImplementedError("training-time dropout / drop-path: backward pass is not built yet")
+        d, F_, H = self.embed_dim, self.ffn_embed_dim, self.self_attn.num_heads
+        M = B * S
+        a = self._fused_attn_pack()
+        f = self._fused_ffn_pack(modality)
+        eps = self.self_attn_layer_norm.eps
+        # LN1 -> QKV (+bias, q scale)
+        K.gemm_ln(xb, a["wqkv"], K.EPI_STORE_BF16, ws["qkv"], ln_mu=mu, ln_rstd=rstd, ln_colsum=a["cqkv"],
+                  bias=a["dqkv"], colscale=a["qscale"])
+        # attention (+ per-head partial statistics of its output rows)
+        K.attention(ws["qkv"], bias, key_pad, B, S, H, out=ws["o"], ln_stats=ws["part"])
+        K.ln_stats_finalize(ws["part"], H, M, d, self.self_attn.ln.eps, ws["mu2"], ws["rstd2"])
+        # inner LN -> out_proj -> LayerScale + residual; emits x, xb and the statistics for LN2
+        n_t = (d + 255) // 256
+        K.gemm_ln(ws["o"], a["wo"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=a["co"],
+                  bias=a["do"], gamma=a["g1"], resid=x, stats_out=ws["part"], out_bf16=xb)
+        K.ln_stats_finalize(ws["part"], n_t, M, d, self.final_layer_norm.eps, mu, rstd)
+        # LN2 -> GeGLU; emits u and the statistics for the FFN LayerNorm
+        K.gemm_ln(xb, f["w01"], K.EPI_GEGLU_BF16, ws["u"], ln_mu=mu, ln_rstd=rstd, ln_colsum=f["c01"], bias=f["d01"],
+                  stats_out=ws["part"])
+        K.ln_stats_finalize(ws["part"], (2 * F_) // 256, M, F_, 1e-5, ws["mu2"], ws["rstd2"])
+        # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the statistics for the next layer's LN1
+        K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=f["c2"],
+                  bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part"], out_bf16=xb)
+        K.ln_stats_finalize(ws["part"], n_t, M, d, eps, mu, rstd)
+        return x
+
+    @staticmethod
+    def fused_workspace(M, d, F_, H, device):
+        parts = max(H, (2 * F_) // 256, (d + 255) // 256)
+        e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=device)
+        return dict(qkv=e(M, 3 * d), o=e(M, d), u=e(M, F_), xb=e(M, d), part=e(parts * M * 2, dt=torch.float32),
+                    mu=e(M, dt=torch.float32), rstd=e(M, dt=torch.float32), mu2=e(M, dt=torch.float32),
+                    rstd2=e(M, dt=torch.float32))
 
     def forward_rows(self, x, bias, key_pad, B, S, modality):
         """x: fp32 [B*S, d] residual stream, updated IN PLACE.  Single-modality sequence

@@ -209,3 +209,55 @@ def test_layernorm_remap_group_pad_and_accumulate(K):
     K.layernorm(x, None, None, acc.view(B * (T + 1), d), rows=B * Tp, dim=d, gelu=True, row_period=Tp, row_valid=T,
                 out_period=T + 1, out_row_shift=1, accumulate=True)
     assert relerr(acc[:, 1:], 1 + want.view(B, Tp, d)[:, :T]) < 1e-5 and torch.all(acc[:, 0] == 1)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_fused_layernorm_and_stats(K, cg):
+    """LN(x) W^T + b computed as rstd*(acc - mu*colsum) + bias' on un-normalised bf16 rows, plus the (sum, sumsq)
+    side output and bf16 copy of the RESID epilogue (fused-LN chain of the encoder layer)."""
+    from one_peace_b200.transformer.transformer_layer import TransformerEncoderLayer as L
+    M, d, N = 777, 512, 768
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(M, d, device="cuda", generator=g) * 1.5 + 0.3
+    lw = 1 + 0.2 * torch.randn(d, device="cuda", generator=g)
+    lb = 0.1 * torch.randn(d, device="cuda", generator=g)
+    W = torch.randn(N, d, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    xb = torch.empty(M, d, dtype=torch.bfloat16, device="cuda")
+    mu = torch.empty(M, device="cuda"); rstd = torch.empty(M, device="cuda")
+    K.row_stats_cast(x, xb, mu, rstd)
+    torch.testing.assert_close(mu, x.mean(1), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(rstd, (x.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-5, rtol=1e-4)
+    wg, colsum, dd = L._fold(W, lw, lb, b)
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    K.gemm_ln(xb, wg, K.EPI_STORE_F32, out, ln_mu=mu, ln_rstd=rstd, ln_colsum=colsum, bias=dd, cta_group=cg)
+    want = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (d,), lw, lb), W, b)
+    assert relerr(out, want) < 8e-3
+    # RESID epilogue with statistics + bf16 copy
+    gamma = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    y = res.clone()
+    part = torch.zeros(((N + 255) // 256) * M * 2, device="cuda")
+    yb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    K.gemm_ln(xb, wg, K.EPI_RESID_F32, y, ln_mu=mu, ln_rstd=rstd, ln_colsum=colsum, bias=dd, gamma=gamma, resid=y,
+              stats_out=part, out_bf16=yb, cta_group=cg)
+    assert relerr(y, res + gamma * want) < 8e-3
+    assert torch.equal(yb, y.bfloat16())
+    m2 = torch.empty(M, device="cuda"); r2 = torch.empty(M, device="cuda")
+    K.ln_stats_finalize(part, (N + 255) // 256, M, N, 1e-5, m2, r2)
+    torch.testing.assert_close(m2, y.mean(1), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(r2, (y.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-4, rtol=1e-3)
+
+
+def test_attention_ln_stats(K):
+    B, S, H = 2, 70, 4
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    part = torch.zeros(H * B * S * 2, device="cuda")
+    out = K.attention(qkv, None, None, B, S, H, ln_stats=part)
+    mu = torch.empty(B * S, device="cuda"); rstd = torch.empty(B * S, device="cuda")
+    K.ln_stats_finalize(part, H, B * S, D, 1e-5, mu, rstd)
+    o = out.float()
+    torch.testing.assert_close(mu, o.mean(1), atol=2e-3, rtol=1e-2)      # stats are of the pre-rounding fp32 rows
+    torch.testing.assert_close(rstd, (o.var(1, unbiased=False) + 1e-5).rsqrt(), atol=0, rtol=1e-2)
