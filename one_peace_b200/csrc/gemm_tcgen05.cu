@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -32,15 +34,34 @@ constexpr int kUmmaK = 16;
 constexpr int kAccStages = 2;
 constexpr int kNumThreads = 192;
 
-template <int CG>
+// Epilogue staging (TMA-store path): per epilogue warp a ring of 4 KB chunk buffers ([32 rows][128 B], 128B swizzle)
+//   RESID_F32 / STORE_F32 : 3 x fp32 chunk (32 cols; the residual chunk is TMA-prefetched two chunks ahead and
+//                           overwritten in place) + 2 x bf16-copy chunk (64 cols)            = 20 KB / warp
+//   STORE_BF16 / GELU_BF16 / GEGLU_BF16 : 2 x bf16 chunk (64 cols)                            =  8 KB / warp
+// plus 4 KB / warp holding the tile's per-column epilogue vectors (LayerNorm column sums, bias, scale / gamma):
+// fetched once per tile BEFORE the accumulator is ready, so no epilogue FMA ever waits on a global load (the
+// first version issued those loads just-in-time and ncu showed 30 % of all samples on the dependent FFMA).
+template <int EPI, bool TMAEPI>
+struct EpiCfg {
+  static constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32);
+  static constexpr int kRing = TMAEPI ? (kF32 ? 3 : 2) : 0;
+  static constexpr int kColVecOff = kRing * 4096 + (kF32 ? 2 * 4096 : 0);
+  static constexpr int kWarpBytes = TMAEPI ? (kColVecOff + 4096) : 0;
+  static constexpr int kBytes = 4 * kWarpBytes;
+};
+
+template <int CG, int EPI = 0, bool TMAEPI = false>
 struct GemmCfg {
   static constexpr int kBRows = kBlockN / CG;                       // rows of B staged per CTA
   static constexpr int kABytes = kBlockM * kBlockK * 2;             // 16 KB
   static constexpr int kBBytes = kBRows * kBlockK * 2;              // 32 KB (CG=1) / 16 KB (CG=2)
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CG == 1) ? 4 : 6;
+  static constexpr int kEpiBytes = EpiCfg<EPI, TMAEPI>::kBytes;
+  static constexpr int kBudget = 227 * 1024 - 2048 - kEpiBytes;     // barriers + alignment slack
+  static constexpr int kStagesMax = (CG == 1) ? 4 : 6;
+  static constexpr int kStages = (kBudget / kStageBytes) < kStagesMax ? (kBudget / kStageBytes) : kStagesMax;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // + alignment slack
 };
 
 struct GemmGeom {
@@ -58,15 +79,18 @@ struct SmemBars {
   uint64_t empty[8];
   uint64_t tmem_full[kAccStages];
   uint64_t tmem_empty[kAccStages];
+  uint64_t resid_full[4][4];   // per epilogue warp: residual-chunk ring (TMA-epilogue path)
   uint32_t tmem_base;
 };
 
-template <int CG, int EPI>
+template <int CG, int EPI, bool TMAEPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                  const GemmEpilogue ep, const GemmGeom geo) {
   const int M = geo.M, N = geo.N;
-  using Cfg = GemmCfg<CG>;
+  using Cfg = GemmCfg<CG, EPI, TMAEPI>;
+  using ECfg = EpiCfg<EPI, TMAEPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   SmemBars* bars = reinterpret_cast<SmemBars*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -95,6 +119,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
       mbar_init(&bars->tmem_empty[i], 4 * CG);
+    }
+    for (int w = 0; w < 4; ++w)
+      for (int i = 0; i < 4; ++i) mbar_init(&bars->resid_full[w][i], 1);
+    if constexpr (TMAEPI) {
+      tma_prefetch_desc(&tm_o);
+      tma_prefetch_desc(&tm_o2);
     }
     fence_barrier_init();
   }
@@ -186,6 +216,266 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       bool row_ok = row < M;
       if (ep.out_group > 0 && ep.out_group_valid > 0 && (row % ep.out_group) >= ep.out_group_valid) row_ok = false;
       const int gcol0 = grp * N;      // first global output column of this group
+      if constexpr (TMAEPI) {
+        // ---------------------------------------------------------------------------------------------
+        // Coalesced epilogue: every global access is a TMA bulk copy of a [32 rows][128 B] chunk staged in this
+        // warp's swizzled shared-memory ring; threads only touch TMEM, registers and their own smem row.
+        // (The direct path below issues 16-byte accesses at a 3-24 KB row pitch — 32 L1 wavefronts per
+        // instruction — and made the K = 1536 GEMMs epilogue-bound.)
+        // ---------------------------------------------------------------------------------------------
+        const int ew = warp - 2;                                        // 0..3: staging slot of this warp
+        uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + ew * ECfg::kWarpBytes;
+        const int row0 = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32;   // warp's first row
+        const int col0 = n_blk * kBlockN;
+        float ln_mu = 0.f, ln_rs = 1.f;
+        if (ep.ln_mu != nullptr) {
+          const int rc = row < M ? row : M - 1;
+          ln_mu = ep.ln_mu[rc];
+          ln_rs = ep.ln_rstd[rc];
+        }
+        float st_sum = 0.f, st_sq = 0.f;
+        // per-column vectors of this tile -> this warp's smem copy ([3][256] fp32): colsum | bias | scale-or-gamma
+        float* cv = reinterpret_cast<float*>(stg + ECfg::kColVecOff);
+        {
+          const float* v2 = (EPI == EPI_RESID_F32) ? ep.gamma : ep.colscale;
+          const float* vecs[3] = {ep.ln_colsum, ep.bias, v2};
+          __syncwarp();
+#pragma unroll
+          for (int vv = 0; vv < 3; ++vv) {
+            if (vecs[vv] != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int idx = k * 128 + lane * 4;
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col0 + idx < N) t4 = *reinterpret_cast<const float4*>(vecs[vv] + col0 + idx);
+                *reinterpret_cast<float4*>(cv + vv * 256 + idx) = t4;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if constexpr (ECfg::kF32) {
+          uint8_t* bufB0 = stg + ECfg::kRing * 4096;
+          uint64_t* rbar = bars->resid_full[ew];
+          const bool has_res = (EPI == EPI_RESID_F32) && ep.resid != nullptr;
+          // ring slot / barrier phase bookkeeping is continuous across tiles: chunk counter gc = it * 8 + c
+          const int gc0 = it * 8;
+          if (lane == 0) bulk_wait_read<0>();   // slots refilled below may still be read by the previous tile's stores
+          __syncwarp();
+          if (has_res && lane == 0) {
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+              const int slot = (gc0 + pc) % 3;
+              mbar_arrive_expect_tx(&rbar[slot], 4096);
+              tma_load_2d(&tm_o, &rbar[slot], stg + slot * 4096, col0 + 32 * pc, row0);
+            }
+          }
+          mbar_wait(&bars->tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            const int gc = gc0 + c;
+            const int slot = gc % 3;
+            uint8_t* buf = stg + slot * 4096;
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (c == 7) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+            }
+            if (lane == 0) {
+              // the slot of chunk c+2 was last stored from by chunk c-1 (issued one TMEM load ago): its shared-memory
+              // read must have finished before the residual prefetch overwrites it
+              bulk_wait_read<0>();
+              if (has_res && c + 2 < 8) {
+                const int ns = (gc + 2) % 3;
+                mbar_arrive_expect_tx(&rbar[ns], 4096);
+                tma_load_2d(&tm_o, &rbar[ns], stg + ns * 4096, col0 + 32 * (c + 2), row0);
+              }
+            }
+            __syncwarp();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int col = col0 + c * 32 + j;
+              float4 xv = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3]));
+              if (col < N) {
+                const int tc = c * 32 + j;      // column inside the tile
+                if (ep.ln_mu != nullptr) {
+                  const float4 cs = *reinterpret_cast<const float4*>(cv + tc);
+                  xv.x = ln_rs * (xv.x - ln_mu * cs.x); xv.y = ln_rs * (xv.y - ln_mu * cs.y);
+                  xv.z = ln_rs * (xv.z - ln_mu * cs.z); xv.w = ln_rs * (xv.w - ln_mu * cs.w);
+                }
+                if (ep.bias != nullptr) {
+                  const float4 bb = *reinterpret_cast<const float4*>(cv + 256 + tc);
+                  xv.x += bb.x; xv.y += bb.y; xv.z += bb.z; xv.w += bb.w;
+                }
+                if constexpr (EPI == EPI_RESID_F32) {
+                  if (ep.gamma != nullptr) {
+                    const float4 gg = *reinterpret_cast<const float4*>(cv + 512 + tc);
+                    xv.x *= gg.x; xv.y *= gg.y; xv.z *= gg.z; xv.w *= gg.w;
+                  }
+                }
+              }
+              x[j] = xv.x; x[j + 1] = xv.y; x[j + 2] = xv.z; x[j + 3] = xv.w;
+            }
+            if (has_res) {
+              mbar_wait(&rbar[slot], (gc / 3) & 1);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 r = *reinterpret_cast<const float4*>(buf + sw128_off(lane, k));
+                x[4 * k] += r.x; x[4 * k + 1] += r.y; x[4 * k + 2] += r.z; x[4 * k + 3] += r.w;
+              }
+            }
+            if (ep.stats_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + c * 32 + j < N) { st_sum += x[j]; st_sq += x[j] * x[j]; }
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(buf + sw128_off(lane, k)) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+            uint8_t* bufB = bufB0 + ((c >> 1) & 1) * 4096;     // alternate per 64-column pair
+            if (ep.out_bf16 != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 o;
+                o.x = pack_bf16x2(x[8 * k], x[8 * k + 1]);
+                o.y = pack_bf16x2(x[8 * k + 2], x[8 * k + 3]);
+                o.z = pack_bf16x2(x[8 * k + 4], x[8 * k + 5]);
+                o.w = pack_bf16x2(x[8 * k + 6], x[8 * k + 7]);
+                *reinterpret_cast<uint4*>(bufB + sw128_off(lane, (c & 1) * 4 + k)) = o;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tm_o, buf, col0 + c * 32, row0);
+              if (ep.out_bf16 != nullptr && (c & 1)) tma_store_2d(&tm_o2, bufB, col0 + (c - 1) * 32, row0);
+              bulk_commit();
+            }
+          }
+          if (row_ok && ep.stats_out != nullptr)
+            *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
+        } else {
+          // ---- bf16 outputs: 64-column chunks ----
+          mbar_wait(&bars->tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
+          constexpr int kChunks = (EPI == EPI_GEGLU_BF16) ? 2 : 4;
+          const int gc0 = it * kChunks;
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c) {
+            uint8_t* buf = stg + ((gc0 + c) & 1) * 4096;
+            if (lane == 0) bulk_wait_read<1>();     // slot last used two chunks ago
+            __syncwarp();
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {        // two 32-column halves of the 64-column output chunk
+              float y[32];
+              if constexpr (EPI == EPI_GEGLU_BF16) {
+                uint32_t g[32], l[32];
+                const int ac = c * 64 + hh * 32;    // accumulator column of the gate half
+                __syncwarp();
+                tmem_ld32(taddr + ac, g);
+                tmem_ld32(taddr + kBlockN / 2 + ac, l);
+                tmem_ld_wait();
+                if (c == kChunks - 1 && hh == 1) {
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 ga = make_float4(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), __uint_as_float(g[j + 2]), __uint_as_float(g[j + 3]));
+                  float4 li = make_float4(__uint_as_float(l[j]), __uint_as_float(l[j + 1]), __uint_as_float(l[j + 2]), __uint_as_float(l[j + 3]));
+                  if (ep.ln_mu != nullptr) {
+                    const float4 cg = *reinterpret_cast<const float4*>(cv + ac + j);
+                    const float4 cl = *reinterpret_cast<const float4*>(cv + kBlockN / 2 + ac + j);
+                    ga.x = ln_rs * (ga.x - ln_mu * cg.x); ga.y = ln_rs * (ga.y - ln_mu * cg.y);
+                    ga.z = ln_rs * (ga.z - ln_mu * cg.z); ga.w = ln_rs * (ga.w - ln_mu * cg.w);
+                    li.x = ln_rs * (li.x - ln_mu * cl.x); li.y = ln_rs * (li.y - ln_mu * cl.y);
+                    li.z = ln_rs * (li.z - ln_mu * cl.z); li.w = ln_rs * (li.w - ln_mu * cl.w);
+                  }
+                  if (ep.bias != nullptr) {
+                    const float4 bg = *reinterpret_cast<const float4*>(cv + 256 + ac + j);
+                    const float4 bl = *reinterpret_cast<const float4*>(cv + 256 + kBlockN / 2 + ac + j);
+                    ga.x += bg.x; ga.y += bg.y; ga.z += bg.z; ga.w += bg.w;
+                    li.x += bl.x; li.y += bl.y; li.z += bl.z; li.w += bl.w;
+                  }
+                  y[j] = gelu_erf(ga.x) * li.x; y[j + 1] = gelu_erf(ga.y) * li.y;
+                  y[j + 2] = gelu_erf(ga.z) * li.z; y[j + 3] = gelu_erf(ga.w) * li.w;
+                }
+                if (ep.stats_out != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) { st_sum += y[j]; st_sq += y[j] * y[j]; }
+                }
+              } else {
+                uint32_t v[32];
+                const int ac = c * 64 + hh * 32;
+                __syncwarp();
+                tmem_ld32(taddr + ac, v);
+                tmem_ld_wait();
+                if (c == kChunks - 1 && hh == 1) {
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const int col = col0 + ac + j;
+                  float4 xv = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                  if (col < N) {
+                    if (ep.ln_mu != nullptr) {
+                      const float4 cs = *reinterpret_cast<const float4*>(cv + ac + j);
+                      xv.x = ln_rs * (xv.x - ln_mu * cs.x); xv.y = ln_rs * (xv.y - ln_mu * cs.y);
+                      xv.z = ln_rs * (xv.z - ln_mu * cs.z); xv.w = ln_rs * (xv.w - ln_mu * cs.w);
+                    }
+                    if (ep.bias != nullptr) {
+                      const float4 bb = *reinterpret_cast<const float4*>(cv + 256 + ac + j);
+                      xv.x += bb.x; xv.y += bb.y; xv.z += bb.z; xv.w += bb.w;
+                    }
+                    if (ep.colscale != nullptr) {
+                      const float4 sc = *reinterpret_cast<const float4*>(cv + 512 + ac + j);
+                      xv.x *= sc.x; xv.y *= sc.y; xv.z *= sc.z; xv.w *= sc.w;
+                    }
+                    if constexpr (EPI == EPI_GELU_BF16) {
+                      xv.x = gelu_erf(xv.x); xv.y = gelu_erf(xv.y); xv.z = gelu_erf(xv.z); xv.w = gelu_erf(xv.w);
+                    }
+                  }
+                  y[j] = xv.x; y[j + 1] = xv.y; y[j + 2] = xv.z; y[j + 3] = xv.w;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 o;
+                o.x = pack_bf16x2(y[8 * k], y[8 * k + 1]);
+                o.y = pack_bf16x2(y[8 * k + 2], y[8 * k + 3]);
+                o.z = pack_bf16x2(y[8 * k + 4], y[8 * k + 5]);
+                o.w = pack_bf16x2(y[8 * k + 6], y[8 * k + 7]);
+                *reinterpret_cast<uint4*>(buf + sw128_off(lane, hh * 4 + k)) = o;
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int ocol = (EPI == EPI_GEGLU_BF16) ? n_blk * (kBlockN / 2) + c * 64 : col0 + c * 64;
+              tma_store_2d(&tm_o, buf, ocol, row0);
+              bulk_commit();
+            }
+          }
+          if constexpr (EPI == EPI_GEGLU_BF16) {
+            if (row_ok && ep.stats_out != nullptr)
+              *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
+          }
+        }
+        continue;
+      }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
@@ -450,6 +740,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 
   // ===================== teardown =====================
+  if constexpr (TMAEPI) {
+    if (warp >= 2 && lane == 0) bulk_wait_all<0>();
+  }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 0) {
@@ -495,6 +788,22 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? OPB_OK : OPB_ERR_CUDA;
 }
 
+// generic 2D row-major tensor map for the epilogue's TMA loads / stores: box = box_cols x box_rows, 128B swizzle
+static int make_tmap_2d_out(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return OPB_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0) return OPB_ERR_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OPB_OK : OPB_ERR_CUDA;
+}
+
 // 3D view of the A operand: dims {k_inner, taps, rows}; element (c, j, r) lives at ptr + r*row_stride + j*tap_stride + c.
 // A plain [rows, K] matrix is the taps == 1 case.  box = 64 x 1 x box_rows, 128B swizzle (same smem image as 2D).
 int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t k_inner, uint64_t taps, uint64_t tap_stride,
@@ -523,11 +832,11 @@ static int sm_count() {
   return n;
 }
 
-template <int CG, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, const GemmGeom& geo,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<CG>;
-  auto kern = gemm_bf16_kernel<CG, EPI>;
+template <int CG, int EPI, bool TMAEPI>
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                         const GemmEpilogue& ep, const GemmGeom& geo, cudaStream_t stream) {
+  using Cfg = GemmCfg<CG, EPI, TMAEPI>;
+  auto kern = gemm_bf16_kernel<CG, EPI, TMAEPI>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
@@ -550,8 +859,41 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, geo);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, ep, geo);
   return e == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// Chooses the coalesced TMA-store epilogue whenever the output is a plain [M, N] matrix (no row remapping,
+// residual updated in place); the direct-store epilogue handles the adapter scatter cases and the InfoNCE epilogues.
+template <int CG, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, const GemmGeom& geo,
+                       cudaStream_t stream) {
+  constexpr bool kCanTma = (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_GEGLU_BF16 ||
+                            EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32);
+  if constexpr (kCanTma) {
+    static const char* env = getenv("OPB_GEMM_TMA_EPILOGUE");
+    const bool f32 = (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32);
+    const int eb = f32 ? 4 : 2;
+    const long n_out = (EPI == EPI_GEGLU_BF16) ? geo.N / 2 : geo.N;
+    bool ok = !(env != nullptr && env[0] == '0') && geo.groups == 1 && ep.out_group == 0 && ep.resid_period == 0 &&
+              (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (ep.ldo * eb) % 16 == 0 && (n_out * eb) % 16 == 0;
+    if (EPI == EPI_RESID_F32 && ep.resid != nullptr && (ep.resid != ep.out || ep.ldr != ep.ldo)) ok = false;
+    if (ep.out_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) != 0 || (ep.ldo_bf16 * 2) % 16 != 0))
+      ok = false;
+    if (ok) {
+      CUtensorMap to, to2;
+      int rc = make_tmap_2d_out(&to, ep.out, eb, geo.M, n_out, ep.ldo, f32 ? 32 : 64, 32);
+      if (rc != OPB_OK) return rc;
+      if (ep.out_bf16 != nullptr) {
+        rc = make_tmap_2d_out(&to2, ep.out_bf16, 2, geo.M, geo.N, ep.ldo_bf16, 64, 32);
+        if (rc != OPB_OK) return rc;
+      } else {
+        to2 = to;
+      }
+      return launch_gemm_t<CG, EPI, true>(ta, tb, to, to2, ep, geo, stream);
+    }
+  }
+  return launch_gemm_t<CG, EPI, false>(ta, tb, ta, ta, ep, geo, stream);
 }
 
 static int dispatch_gemm(int cta_group, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep,
