@@ -94,7 +94,8 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
  *   LN(x) W^T + b  =  rstd[m] * (acc - mu[m] * colsum[n]) + bias'[n]
  * where A holds the UN-normalised rows (bf16), B = W * diag(ln_weight) (bf16), colsum[n] = sum_k B[n,k],
  * bias'[n] = sum_k ln_bias[k] W[n,k] + b[n]; and the side outputs that feed the NEXT LayerNorm: stats_out
- * [ceil(N/256) (or N/256 for GEGLU), M, 2] partial (sum, sum of squares) of the stored values, and out_bf16 (a bf16
+ * [ceil(N/256) (RESID) or 2*N/256 (GEGLU: one record per 64 output columns), M, 2] partial (sum, sum of squares)
+ * of the stored values, and out_bf16 (a bf16
  * copy of the fp32 output of OPB_EPI_RESID_F32).  This replaces the four LayerNorm passes per encoder layer of
  * models/transformer/transformer_layer.py:185,202 / multihead_attention.py:122-123 / transformer_layer.py:154.
  */

@@ -32,7 +32,6 @@ constexpr int kBlockN = 256;   // accumulator columns per tile
 constexpr int kBlockK = 64;    // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kAccStages = 2;
-constexpr int kNumThreads = 192;
 
 // Epilogue staging (TMA-store path): per epilogue warp a ring of 4 KB chunk buffers ([32 rows][128 B], 128B swizzle)
 //   RESID_F32 / STORE_F32 : 3 x fp32 chunk (32 cols; the residual chunk is TMA-prefetched two chunks ahead and
@@ -41,13 +40,23 @@ constexpr int kNumThreads = 192;
 // plus 4 KB / warp holding the tile's per-column epilogue vectors (LayerNorm column sums, bias, scale / gamma):
 // fetched once per tile BEFORE the accumulator is ready, so no epilogue FMA ever waits on a global load (the
 // first version issued those loads just-in-time and ncu showed 30 % of all samples on the dependent FFMA).
+#ifndef OPB_EPI_WARPS_BF16
+#define OPB_EPI_WARPS_BF16 4   // 8 was measured no faster (profiles/r01_bench_*): the extra staging costs a pipeline stage
+#endif
 template <int EPI, bool TMAEPI>
 struct EpiCfg {
+  static constexpr bool kRegular = (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_GEGLU_BF16 ||
+                                    EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32);
   static constexpr bool kF32 = (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32);
+  // bf16-output TMA epilogues run 8 epilogue warps (two per TMEM lane quarter, each taking half of the tile's
+  // columns): the GeGLU / QKV epilogues are instruction-bound and a single warp per SM sub-partition cannot hide the
+  // TMEM-load -> math -> smem -> TMA-store chain.  The fp32 residual epilogue keeps 4 (its staging is 24 KB / warp).
+  static constexpr int kWarps = (TMAEPI && !kF32 && OPB_EPI_WARPS_BF16 == 8) ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kWarps;
   static constexpr int kRing = TMAEPI ? (kF32 ? 3 : 2) : 0;
   static constexpr int kColVecOff = kRing * 4096 + (kF32 ? 2 * 4096 : 0);
-  static constexpr int kWarpBytes = TMAEPI ? (kColVecOff + 4096) : 0;
-  static constexpr int kBytes = 4 * kWarpBytes;
+  static constexpr int kWarpBytes = TMAEPI ? (kColVecOff + 4096) : (kRegular ? 4096 : 0);   // direct path: column vectors only
+  static constexpr int kBytes = kWarps * kWarpBytes;
 };
 
 template <int CG, int EPI = 0, bool TMAEPI = false>
@@ -84,7 +93,7 @@ struct SmemBars {
 };
 
 template <int CG, int EPI, bool TMAEPI>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI, TMAEPI>::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                  const GemmEpilogue ep, const GemmGeom geo) {
@@ -118,7 +127,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 4 * CG);
+      mbar_init(&bars->tmem_empty[i], EpiCfg<EPI, TMAEPI>::kWarps * CG);
     }
     for (int w = 0; w < 4; ++w)
       for (int i = 0; i < 4; ++i) mbar_init(&bars->resid_full[w][i], 1);
@@ -223,7 +232,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // (The direct path below issues 16-byte accesses at a 3-24 KB row pitch — 32 L1 wavefronts per
         // instruction — and made the K = 1536 GEMMs epilogue-bound.)
         // ---------------------------------------------------------------------------------------------
-        const int ew = warp - 2;                                        // 0..3: staging slot of this warp
+        const int ew = warp - 2;                                        // staging slot of this warp
+        const int hf = ew >> 2;                                         // column half (8-warp epilogues only)
         uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + ew * ECfg::kWarpBytes;
         const int row0 = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32;   // warp's first row
         const int col0 = n_blk * kBlockN;
@@ -235,7 +245,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         float st_sum = 0.f, st_sq = 0.f;
         // per-column vectors of this tile -> this warp's smem copy ([3][256] fp32): colsum | bias | scale-or-gamma
-        float* cv = reinterpret_cast<float*>(stg + ECfg::kColVecOff);
+        const uint32_t cv_s = smem_u32(stg + ECfg::kColVecOff);
         {
           const float* v2 = (EPI == EPI_RESID_F32) ? ep.gamma : ep.colscale;
           const float* vecs[3] = {ep.ln_colsum, ep.bias, v2};
@@ -248,7 +258,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int idx = k * 128 + lane * 4;
                 float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (col0 + idx < N) t4 = *reinterpret_cast<const float4*>(vecs[vv] + col0 + idx);
-                *reinterpret_cast<float4*>(cv + vv * 256 + idx) = t4;
+                sts128(cv_s + 4 * (vv * 256 + idx), t4);
               }
             }
           }
@@ -307,17 +317,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               if (col < N) {
                 const int tc = c * 32 + j;      // column inside the tile
                 if (ep.ln_mu != nullptr) {
-                  const float4 cs = *reinterpret_cast<const float4*>(cv + tc);
+                  const float4 cs = lds128(cv_s + 4 * tc);
                   xv.x = ln_rs * (xv.x - ln_mu * cs.x); xv.y = ln_rs * (xv.y - ln_mu * cs.y);
                   xv.z = ln_rs * (xv.z - ln_mu * cs.z); xv.w = ln_rs * (xv.w - ln_mu * cs.w);
                 }
                 if (ep.bias != nullptr) {
-                  const float4 bb = *reinterpret_cast<const float4*>(cv + 256 + tc);
+                  const float4 bb = lds128(cv_s + 4 * (256 + tc));
                   xv.x += bb.x; xv.y += bb.y; xv.z += bb.z; xv.w += bb.w;
                 }
                 if constexpr (EPI == EPI_RESID_F32) {
                   if (ep.gamma != nullptr) {
-                    const float4 gg = *reinterpret_cast<const float4*>(cv + 512 + tc);
+                    const float4 gg = lds128(cv_s + 4 * (512 + tc));
                     xv.x *= gg.x; xv.y *= gg.y; xv.z *= gg.z; xv.w *= gg.w;
                   }
                 }
@@ -328,7 +338,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               mbar_wait(&rbar[slot], (gc / 3) & 1);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const float4 r = *reinterpret_cast<const float4*>(buf + sw128_off(lane, k));
+                const float4 r = lds128(smem_u32(buf) + sw128_off(lane, k));
                 x[4 * k] += r.x; x[4 * k + 1] += r.y; x[4 * k + 2] += r.z; x[4 * k + 3] += r.w;
               }
             }
@@ -340,7 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              *reinterpret_cast<float4*>(buf + sw128_off(lane, k)) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+              sts128(smem_u32(buf) + sw128_off(lane, k), make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
             uint8_t* bufB = bufB0 + ((c >> 1) & 1) * 4096;     // alternate per 64-column pair
             if (ep.out_bf16 != nullptr) {
 #pragma unroll
@@ -350,7 +360,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 o.y = pack_bf16x2(x[8 * k + 2], x[8 * k + 3]);
                 o.z = pack_bf16x2(x[8 * k + 4], x[8 * k + 5]);
                 o.w = pack_bf16x2(x[8 * k + 6], x[8 * k + 7]);
-                *reinterpret_cast<uint4*>(bufB + sw128_off(lane, (c & 1) * 4 + k)) = o;
+                sts128u(smem_u32(bufB) + sw128_off(lane, (c & 1) * 4 + k), o);
               }
             }
             fence_proxy_async();
@@ -369,9 +379,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
           constexpr int kChunks = (EPI == EPI_GEGLU_BF16) ? 2 : 4;
-          const int gc0 = it * kChunks;
+          constexpr int kMine = kChunks / 2;                       // chunks per warp (two warps share a lane quarter)
+          const int gc0 = it * kMine;
 #pragma unroll 1
-          for (int c = 0; c < kChunks; ++c) {
+          for (int c = hf * kMine; c < (hf + 1) * kMine; ++c) {
             uint8_t* buf = stg + ((gc0 + c) & 1) * 4096;
             if (lane == 0) bulk_wait_read<1>();     // slot last used two chunks ago
             __syncwarp();
@@ -385,7 +396,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 tmem_ld32(taddr + ac, g);
                 tmem_ld32(taddr + kBlockN / 2 + ac, l);
                 tmem_ld_wait();
-                if (c == kChunks - 1 && hh == 1) {
+                if (c == (hf + 1) * kMine - 1 && hh == 1) {
                   tc_fence_before();
                   __syncwarp();
                   if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
@@ -395,16 +406,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   float4 ga = make_float4(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), __uint_as_float(g[j + 2]), __uint_as_float(g[j + 3]));
                   float4 li = make_float4(__uint_as_float(l[j]), __uint_as_float(l[j + 1]), __uint_as_float(l[j + 2]), __uint_as_float(l[j + 3]));
                   if (ep.ln_mu != nullptr) {
-                    const float4 cg = *reinterpret_cast<const float4*>(cv + ac + j);
-                    const float4 cl = *reinterpret_cast<const float4*>(cv + kBlockN / 2 + ac + j);
+                    const float4 cg = lds128(cv_s + 4 * (ac + j));
+                    const float4 cl = lds128(cv_s + 4 * (kBlockN / 2 + ac + j));
                     ga.x = ln_rs * (ga.x - ln_mu * cg.x); ga.y = ln_rs * (ga.y - ln_mu * cg.y);
                     ga.z = ln_rs * (ga.z - ln_mu * cg.z); ga.w = ln_rs * (ga.w - ln_mu * cg.w);
                     li.x = ln_rs * (li.x - ln_mu * cl.x); li.y = ln_rs * (li.y - ln_mu * cl.y);
                     li.z = ln_rs * (li.z - ln_mu * cl.z); li.w = ln_rs * (li.w - ln_mu * cl.w);
                   }
                   if (ep.bias != nullptr) {
-                    const float4 bg = *reinterpret_cast<const float4*>(cv + 256 + ac + j);
-                    const float4 bl = *reinterpret_cast<const float4*>(cv + 256 + kBlockN / 2 + ac + j);
+                    const float4 bg = lds128(cv_s + 4 * (256 + ac + j));
+                    const float4 bl = lds128(cv_s + 4 * (256 + kBlockN / 2 + ac + j));
                     ga.x += bg.x; ga.y += bg.y; ga.z += bg.z; ga.w += bg.w;
                     li.x += bl.x; li.y += bl.y; li.z += bl.z; li.w += bl.w;
                   }
@@ -421,7 +432,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 __syncwarp();
                 tmem_ld32(taddr + ac, v);
                 tmem_ld_wait();
-                if (c == kChunks - 1 && hh == 1) {
+                if (c == (hf + 1) * kMine - 1 && hh == 1) {
                   tc_fence_before();
                   __syncwarp();
                   if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
@@ -432,16 +443,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   float4 xv = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                   if (col < N) {
                     if (ep.ln_mu != nullptr) {
-                      const float4 cs = *reinterpret_cast<const float4*>(cv + ac + j);
+                      const float4 cs = lds128(cv_s + 4 * (ac + j));
                       xv.x = ln_rs * (xv.x - ln_mu * cs.x); xv.y = ln_rs * (xv.y - ln_mu * cs.y);
                       xv.z = ln_rs * (xv.z - ln_mu * cs.z); xv.w = ln_rs * (xv.w - ln_mu * cs.w);
                     }
                     if (ep.bias != nullptr) {
-                      const float4 bb = *reinterpret_cast<const float4*>(cv + 256 + ac + j);
+                      const float4 bb = lds128(cv_s + 4 * (256 + ac + j));
                       xv.x += bb.x; xv.y += bb.y; xv.z += bb.z; xv.w += bb.w;
                     }
                     if (ep.colscale != nullptr) {
-                      const float4 sc = *reinterpret_cast<const float4*>(cv + 512 + ac + j);
+                      const float4 sc = lds128(cv_s + 4 * (512 + ac + j));
                       xv.x *= sc.x; xv.y *= sc.y; xv.z *= sc.z; xv.w *= sc.w;
                     }
                     if constexpr (EPI == EPI_GELU_BF16) {
@@ -458,7 +469,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 o.y = pack_bf16x2(y[8 * k + 2], y[8 * k + 3]);
                 o.z = pack_bf16x2(y[8 * k + 4], y[8 * k + 5]);
                 o.w = pack_bf16x2(y[8 * k + 6], y[8 * k + 7]);
-                *reinterpret_cast<uint4*>(buf + sw128_off(lane, hh * 4 + k)) = o;
+                sts128u(smem_u32(buf) + sw128_off(lane, hh * 4 + k), o);
               }
             }
             fence_proxy_async();
@@ -471,13 +482,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           if constexpr (EPI == EPI_GEGLU_BF16) {
             if (row_ok && ep.stats_out != nullptr)
-              *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
+              *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk * 2 + hf) * M + row) * 2) = make_float2(st_sum, st_sq);
           }
         }
         continue;
       }
-      mbar_wait(&bars->tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
 
       // output / residual row mapping (lets adapters scatter rows behind a CLS slot and broadcast a
@@ -493,6 +502,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ln_rs = ep.ln_rstd[rc];
       }
       float st_sum = 0.f, st_sq = 0.f;   // partial statistics of the stored values (next LayerNorm)
+      // per-column epilogue vectors of this tile in shared memory (see the TMA path); grouped GEMMs index them by
+      // global column and keep reading global memory
+      bool use_cv = false;
+      uint32_t cv_s = 0;
+      if constexpr (ECfg::kRegular && !TMAEPI) {
+        use_cv = (geo.groups == 1);
+        if (use_cv) {
+          cv_s = smem_u32(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 2) * ECfg::kWarpBytes);
+          const float* v2 = (EPI == EPI_RESID_F32) ? ep.gamma : ep.colscale;
+          const float* vecs[3] = {ep.ln_colsum, ep.bias, v2};
+          const int tcol0 = n_blk * kBlockN;
+          __syncwarp();
+#pragma unroll
+          for (int vv = 0; vv < 3; ++vv) {
+            if (vecs[vv] != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int idx = k * 128 + lane * 4;
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tcol0 + idx < N) t4 = *reinterpret_cast<const float4*>(vecs[vv] + tcol0 + idx);
+                sts128(cv_s + 4 * (vv * 256 + idx), t4);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
 
       if constexpr (EPI == EPI_GEGLU_BF16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + n_blk * (kBlockN / 2);
@@ -519,10 +557,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int pc = n_blk * kBlockN + c + j;          // packed (interleaved) weight row of the gate half
                 if (ep.ln_mu != nullptr) {
                   float cg[8], cl[8];
+                  if (use_cv) {
+                    *reinterpret_cast<float4*>(cg) = lds128(cv_s + 4 * (c + j));
+                    *reinterpret_cast<float4*>(cg + 4) = lds128(cv_s + 4 * (c + j + 4));
+                    *reinterpret_cast<float4*>(cl) = lds128(cv_s + 4 * (kBlockN / 2 + c + j));
+                    *reinterpret_cast<float4*>(cl + 4) = lds128(cv_s + 4 * (kBlockN / 2 + c + j + 4));
+                  } else {
                   *reinterpret_cast<float4*>(cg) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc);
                   *reinterpret_cast<float4*>(cg + 4) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc + 4);
                   *reinterpret_cast<float4*>(cl) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc + kBlockN / 2);
                   *reinterpret_cast<float4*>(cl + 4) = *reinterpret_cast<const float4*>(ep.ln_colsum + pc + kBlockN / 2 + 4);
+                  }
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     ga[e] = ln_rs * (ga[e] - ln_mu * cg[e]);
@@ -531,10 +576,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 if (ep.bias != nullptr) {
                   float bg[8], bl[8];
+                  if (use_cv) {
+                    *reinterpret_cast<float4*>(bg) = lds128(cv_s + 4 * (256 + c + j));
+                    *reinterpret_cast<float4*>(bg + 4) = lds128(cv_s + 4 * (256 + c + j + 4));
+                    *reinterpret_cast<float4*>(bl) = lds128(cv_s + 4 * (256 + kBlockN / 2 + c + j));
+                    *reinterpret_cast<float4*>(bl + 4) = lds128(cv_s + 4 * (256 + kBlockN / 2 + c + j + 4));
+                  } else {
                   *reinterpret_cast<float4*>(bg) = *reinterpret_cast<const float4*>(ep.bias + pc);
                   *reinterpret_cast<float4*>(bg + 4) = *reinterpret_cast<const float4*>(ep.bias + pc + 4);
                   *reinterpret_cast<float4*>(bl) = *reinterpret_cast<const float4*>(ep.bias + pc + kBlockN / 2);
                   *reinterpret_cast<float4*>(bl + 4) = *reinterpret_cast<const float4*>(ep.bias + pc + kBlockN / 2 + 4);
+                  }
 #pragma unroll
                   for (int e = 0; e < 8; ++e) { ga[e] += bg[e]; li[e] += bl[e]; }
                 }
@@ -555,8 +607,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
         }
-        if (row_ok && ep.stats_out != nullptr)
-          *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
+        if (row_ok && ep.stats_out != nullptr) {   // same [2 * n_tiles, M] layout as the 8-warp TMA epilogue
+          *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk * 2) * M + row) * 2) = make_float2(st_sum, st_sq);
+          *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk * 2 + 1) * M + row) * 2) = make_float2(0.f, 0.f);
+        }
       } else if constexpr (EPI == EPI_LSE_PARTIAL) {
         // z = scale * acc.  Each thread owns one row of the tile: all reductions are thread-local.
         const float scale = *ep.scale_ptr;
@@ -664,24 +718,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j + e]);
+            const int tcc = c + j;   // column inside the tile
             if (ep.ln_mu != nullptr) {
-              const float4 c0 = *reinterpret_cast<const float4*>(ep.ln_colsum + col);
-              const float4 c1 = *reinterpret_cast<const float4*>(ep.ln_colsum + col + 4);
+              const float4 c0 = use_cv ? lds128(cv_s + 4 * tcc) : *reinterpret_cast<const float4*>(ep.ln_colsum + col);
+              const float4 c1 = use_cv ? lds128(cv_s + 4 * (tcc + 4)) : *reinterpret_cast<const float4*>(ep.ln_colsum + col + 4);
               x[0] = ln_rs * (x[0] - ln_mu * c0.x); x[1] = ln_rs * (x[1] - ln_mu * c0.y);
               x[2] = ln_rs * (x[2] - ln_mu * c0.z); x[3] = ln_rs * (x[3] - ln_mu * c0.w);
               x[4] = ln_rs * (x[4] - ln_mu * c1.x); x[5] = ln_rs * (x[5] - ln_mu * c1.y);
               x[6] = ln_rs * (x[6] - ln_mu * c1.z); x[7] = ln_rs * (x[7] - ln_mu * c1.w);
             }
             if (ep.bias != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col);
-              const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
+              const float4 b0 = use_cv ? lds128(cv_s + 4 * (256 + tcc)) : *reinterpret_cast<const float4*>(ep.bias + col);
+              const float4 b1 = use_cv ? lds128(cv_s + 4 * (256 + tcc + 4)) : *reinterpret_cast<const float4*>(ep.bias + col + 4);
               x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
               x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
             }
             if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
               if (ep.colscale != nullptr) {
-                const float4 s0 = *reinterpret_cast<const float4*>(ep.colscale + col);
-                const float4 s1 = *reinterpret_cast<const float4*>(ep.colscale + col + 4);
+                const float4 s0 = use_cv ? lds128(cv_s + 4 * (512 + tcc)) : *reinterpret_cast<const float4*>(ep.colscale + col);
+                const float4 s1 = use_cv ? lds128(cv_s + 4 * (512 + tcc + 4)) : *reinterpret_cast<const float4*>(ep.colscale + col + 4);
                 x[0] *= s0.x; x[1] *= s0.y; x[2] *= s0.z; x[3] *= s0.w;
                 x[4] *= s1.x; x[5] *= s1.y; x[6] *= s1.z; x[7] *= s1.w;
               }
@@ -698,8 +753,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             } else {
               if constexpr (EPI == EPI_RESID_F32) {
                 if (ep.gamma != nullptr) {
-                  const float4 g0 = *reinterpret_cast<const float4*>(ep.gamma + col);
-                  const float4 g1 = *reinterpret_cast<const float4*>(ep.gamma + col + 4);
+                  const float4 g0 = use_cv ? lds128(cv_s + 4 * (512 + tcc)) : *reinterpret_cast<const float4*>(ep.gamma + col);
+                  const float4 g1 = use_cv ? lds128(cv_s + 4 * (512 + tcc + 4)) : *reinterpret_cast<const float4*>(ep.gamma + col + 4);
                   x[0] *= g0.x; x[1] *= g0.y; x[2] *= g0.z; x[3] *= g0.w;
                   x[4] *= g1.x; x[5] *= g1.y; x[6] *= g1.z; x[7] *= g1.w;
                 }
@@ -849,7 +904,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   if (clusters > num_tiles) clusters = num_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(EpiCfg<EPI, TMAEPI>::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -875,7 +930,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     const bool f32 = (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32);
     const int eb = f32 ? 4 : 2;
     const long n_out = (EPI == EPI_GEGLU_BF16) ? geo.N / 2 : geo.N;
-    bool ok = !(env != nullptr && env[0] == '0') && geo.groups == 1 && ep.out_group == 0 && ep.resid_period == 0 &&
+    // OPB_GEMM_TMA_EPILOGUE: 0 = direct stores everywhere, 1 = TMA-store epilogue everywhere, 2 = TMA only for the fp32
+    // residual epilogues
+    const char mode = env != nullptr ? env[0] : '1';
+    bool ok = mode != '0' && !(mode == '2' && !f32) && geo.groups == 1 && ep.out_group == 0 && ep.resid_period == 0 &&
               (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (ep.ldo * eb) % 16 == 0 && (n_out * eb) % 16 == 0;
     if (EPI == EPI_RESID_F32 && ep.resid != nullptr && (ep.resid != ep.out || ep.ldr != ep.ldo)) ok = false;
     if (ep.out_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) != 0 || (ep.ldo_bf16 * 2) % 16 != 0))

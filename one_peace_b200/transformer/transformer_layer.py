@@ -176,7 +176,7 @@ class TransformerEncoderLayer(nn.Module):
         # LN2 -> GeGLU; emits u and the statistics for the FFN LayerNorm
         K.gemm_ln(xb, f["w01"], K.EPI_GEGLU_BF16, ws["u"], ln_mu=mu, ln_rstd=rstd, ln_colsum=f["c01"], bias=f["d01"],
                   stats_out=ws["part"])
-        K.ln_stats_finalize(ws["part"], (2 * F_) // 256, M, F_, 1e-5, ws["mu2"], ws["rstd2"])
+        K.ln_stats_finalize(ws["part"], 2 * ((2 * F_) // 256), M, F_, 1e-5, ws["mu2"], ws["rstd2"])   # 2 records / tile
         # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the statistics for the next layer's LN1
         K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=f["c2"],
                   bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part"], out_bf16=xb)
@@ -185,7 +185,7 @@ class TransformerEncoderLayer(nn.Module):
 
     @staticmethod
     def fused_workspace(M, d, F_, H, device):
-        parts = max(H, (2 * F_) // 256, (d + 255) // 256)
+        parts = max(H, 2 * ((2 * F_) // 256), (d + 255) // 256)
         e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=device)
         return dict(qkv=e(M, 3 * d), o=e(M, d), u=e(M, F_), xb=e(M, d), part=e(parts * M * 2, dt=torch.float32),
                     mu=e(M, dt=torch.float32), rstd=e(M, dt=torch.float32), mu2=e(M, dt=torch.float32),
