@@ -16,6 +16,7 @@ Every convolution runs on the tcgen05 GEMM over channel-last activations (no tra
 import torch
 
 from .. import kernels as K
+from .. import relpos
 from ..components import Embedding, LayerNorm, Linear, PackCache, bf16, f32, trunc_normal_
 from .text import make_token_bucket_position
 
@@ -143,8 +144,18 @@ class AudioAdapter(torch.nn.Module):
         return out
 
     def get_rel_pos_bias(self, seq_len):
+        """One RelPosBias per table: LUT form for the tcgen05 attention kernel when S <= 384, dense (H,S,S_pad) otherwise."""
         p = self._pack()
-        return [K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads) for t in p["tables"]]
+        if not hasattr(self, "_lut_cache"):
+            self._lut_cache = relpos.LutCache()
+        lut = self._lut_cache.get(seq_len, self.rp_bucket.device, self.rp_bucket, lambda S: relpos.text_codes(S)) if seq_len <= 384 else None
+        out = []
+        for t in p["tables"]:
+            if lut is not None:
+                out.append(K.RelPosBias(lut=K.relpos_lut_build(t, lut[0]), code_row=lut[1], code_col=lut[2]))
+            else:
+                out.append(K.RelPosBias(dense=K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads)))
+        return out
 
     def forward(self, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None):
         """src_audios (B, N) waveform, padding_mask (B, T+1) bool -> (x fp32 (B,T+1,d) with padded rows zeroed,

@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import kernels as K
+from .. import relpos
 from ..components import Embedding, LayerNorm, PackCache, bf16, f32, trunc_normal_
 
 
@@ -103,8 +104,20 @@ class ImageAdapter(torch.nn.Module):
         return self._pos_cache[window_size]
 
     def get_rel_pos_bias(self, seq_len):
+        """One RelPosBias per table: LUT form for the tcgen05 attention kernel when S <= 384, dense (H,S,S_pad) otherwise."""
         p = self._pack()
-        return [K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads) for t in p["tables"]]
+        if not hasattr(self, "_lut_cache"):
+            self._lut_cache = relpos.LutCache()
+        w = self.rel_bucket_size
+        lut = self._lut_cache.get(seq_len, self.rp_bucket.device, self.rp_bucket, lambda S: relpos.image_codes(S, w)) \
+            if seq_len <= 384 else None
+        out = []
+        for t in p["tables"]:
+            if lut is not None:
+                out.append(K.RelPosBias(lut=K.relpos_lut_build(t, lut[0]), code_row=lut[1], code_col=lut[2]))
+            else:
+                out.append(K.RelPosBias(dense=K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads)))
+        return out
 
     def forward(self, src_images, preserve_ids=None, preserve_embed=None, mask_token=None, is_second_image=False):
         """-> (x fp32 (B, w*w+1, d), None (images are never padded), [bias (H,S,S_pad)])"""

@@ -1,0 +1,351 @@
+// tcgen05 self-attention for sequences of up to 384 keys (vision S = 197 / 257, text S <= 72):
+//     P = softmax_fp32(q k^T + relpos_bias[h] (+ -inf on padded keys)),  o = P v            (multihead_attention.py:107-115)
+//
+// One CTA = (batch, head, 128-query tile).  Warp 0 issues TMA (Q, all K blocks, all V blocks of this (b, h) straight
+// from the QKV GEMM output), warp 1 issues the MMAs, warps 2-5 own one query row per thread:
+//   S_kb = Q K_kb^T            tcgen05.mma  M=128 N=128 K=64, accumulators in TMEM (one 128-column slot per key block)
+//   phase A  (row thread)      tcgen05.ld S, add the relative-position bias, mask, running max, tcgen05.st the biased
+//                              scores back — no shuffles, no block barriers: a row never leaves its thread
+//   phase B  (row thread)      p = exp2(s log2e - max log2e), row sum, P (bf16) -> shared memory in the K-major 128B-
+//                              swizzled layout the next MMA reads
+//   O += P_kb V_kb             tcgen05.mma  M=128 N=64 K=128, V consumed as an MN-major operand exactly as TMA wrote
+//                              it ([key][d] rows of 128 B) — no transpose;  O aliases the first 64 columns of S_0
+//   epilogue (row thread)      tcgen05.ld O, scale by 1/l, bf16, 128-byte row store (+ inner-LN partial statistics)
+//
+// Relative-position bias without the (H,S,S) table: every ONE-PEACE bias is table[bucket(i, j)] with the bucket a
+// function of a per-position code difference (text / audio: i - j; image: 2-D offset) plus three CLS ids
+// (adapter/text.py:18-29,62-68, adapter/image.py:19-34).  The host folds that into a per-head 1-D LUT with
+//     bias[h][i][j] = lut[h][code_row[i] - code_col[j]]
+// (CLS row / column / corner are mapped to constant LUT regions by offsetting code_row[0] / code_col[0]), so a score
+// costs one shared-memory gather instead of a 4-byte read of a 1.9 MB table per (batch, head) — that L2 stream and the
+// shuffle / barrier-bound online softmax made the mma.sync kernel (attention.cu) latency-bound at ~200 us per layer.
+//
+// Shared memory 112 KB (Q 16 + K 32 + V 32 + P 32; the LUT and code tables live in the P buffer during phase A) and
+// 256 TMEM columns per CTA -> two CTAs per SM overlap each other's TMA / MMA / softmax phases.
+#include "common.cuh"
+#include "ops.h"
+
+namespace opb {
+
+constexpr int kTcQ = 128;        // query rows per CTA
+constexpr int kTcK = 128;        // keys per block
+constexpr int kTcD = 64;         // head dim
+constexpr int kTcMaxBlocks = 3;  // S <= 384
+
+struct TcBars {
+  uint64_t qk;                   // Q + all K landed
+  uint64_t v;                    // all V landed
+  uint64_t s[kTcMaxBlocks];      // S_kb accumulated
+  uint64_t p[kTcMaxBlocks];      // P_kb written by the 4 row warps
+  uint64_t pv[kTcMaxBlocks];     // P_kb V_kb accumulated (P buffer reusable; after the last: O complete)
+  uint32_t tmem_base;
+};
+
+OPB_DEVICE float ex2_approx(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+OPB_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+OPB_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+OPB_DEVICE void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// MN-major bf16 operand stored as [k rows][64 elements = 128 B] with the 128-byte swizzle (what TMA writes for a
+// {64, rows} box): 8-row groups are 1024 B apart (SBO); a single 64-wide MN chunk, so LBO is unused.
+OPB_DEVICE uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int umma_m, int umma_n) {
+  return make_idesc_bf16(umma_m, umma_n) | (1u << 16);     // B operand MN-major
+}
+
+template <bool HAS_PAD>
+__global__ void __launch_bounds__(192, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, int lut_len,
+                    const int* __restrict__ code_row, const int* __restrict__ code_col,
+                    const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
+                    float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols) {
+  // no static shared memory in this kernel: the dynamic window starts at the (1024-aligned) base of the CTA's shared
+  // memory.  The 112 KB + barriers must fit twice per SM, so there is no room for alignment slack; verify instead.
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTcQ * 128;
+  uint8_t* sV = sK + nkb * kTcK * 128;
+  uint8_t* sP = sV + nkb * kTcK * 128;                  // 32 KB: LUT + codes (+ pad mask) in phase A, P afterwards
+  TcBars* bars = reinterpret_cast<TcBars*>(sP + kTcQ * kTcK * 2);
+
+  const int q_tiles = (S + kTcQ - 1) / kTcQ;
+  const int qt = blockIdx.x % q_tiles;
+  const int h = (blockIdx.x / q_tiles) % H;
+  const int b = blockIdx.x / (q_tiles * H);
+  const int D = H * kTcD;
+  const int q0 = qt * kTcQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(&bars->qk, 1);
+    mbar_init(&bars->v, 1);
+    for (int i = 0; i < kTcMaxBlocks; ++i) {
+      mbar_init(&bars->s[i], 1);
+      mbar_init(&bars->p[i], 4);
+      mbar_init(&bars->pv[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc<1>(&bars->tmem_base, tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int row0 = b * S;
+      mbar_arrive_expect_tx(&bars->qk, (kTcQ + nkb * kTcK) * 128);
+      tma_load_2d(&tm_qkv, &bars->qk, sQ, h * kTcD, row0 + q0);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->qk, sK + kb * kTcK * 128, D + h * kTcD, row0 + kb * kTcK);
+      mbar_arrive_expect_tx(&bars->v, nkb * kTcK * 128);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->v, sV + kb * kTcK * 128, 2 * D + h * kTcD, row0 + kb * kTcK);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTcQ, kTcK);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_bmn(kTcQ, kTcD);
+      mbar_wait(&bars->qk, 0);
+      tc_fence_after();
+      const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ));
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + kb * kTcK * 128));
+#pragma unroll
+        for (int k = 0; k < kTcD / 16; ++k) umma_bf16<1>(tmem_base + kb * kTcK, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        umma_commit<1>(&bars->s[kb]);
+      }
+      mbar_wait(&bars->v, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&bars->p[kb], 0);
+        tc_fence_after();
+        const uint32_t pbase = smem_u32(sP);
+        const uint32_t vbase = smem_u32(sV + kb * kTcK * 128);
+#pragma unroll
+        for (int k = 0; k < kTcK / 16; ++k) {
+          // A = P (K-major): two 64-key atoms of [128 rows][128 B]; +32 B per 16 keys inside an atom
+          const uint64_t dp = make_sw128_kmajor_desc(pbase + (k >> 2) * (kTcQ * 128) + (k & 3) * 32);
+          // B = V (MN-major): 16 keys = 16 rows of 128 B
+          const uint64_t dv = make_sw128_mnmajor_desc(vbase + k * 16 * 128);
+          umma_bf16<1>(tmem_base, dp, dv, idesc_pv, (kb | k) != 0);
+        }
+        umma_commit<1>(&bars->pv[kb]);
+      }
+    }
+  } else {
+    // ===================== row threads =====================
+    const int qw = warp & 3;                                 // TMEM lane quarter
+    const int r = qw * 32 + lane;                            // row inside the tile
+    const int qrow = q0 + r;
+    const bool row_valid = qrow < S;
+    const bool warp_valid = (q0 + qw * 32) < S;              // warp-uniform
+    const int tid4 = threadIdx.x - 64;                       // 0..127
+    // phase-A tables in the P buffer: lut [lut_len] | code_col [S] (| key_pad [S] bytes)
+    float* s_lut = reinterpret_cast<float*>(sP);
+    int* s_ccol = reinterpret_cast<int*>(sP) + lut_len;
+    uint8_t* s_pad = reinterpret_cast<uint8_t*>(s_ccol + S);
+    for (int i = tid4; i < lut_len; i += 128) s_lut[i] = lut[static_cast<long>(h) * lut_len + i];
+    for (int i = tid4; i < S; i += 128) s_ccol[i] = code_col[i];
+    if constexpr (HAS_PAD) {
+      for (int i = tid4; i < S; i += 128) s_pad[i] = key_pad[static_cast<long>(b) * S + i];
+    }
+    const int crow = code_row[row_valid ? qrow : 0];
+    named_bar_sync(1, 128);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
+
+    // ---- phase A: bias, mask, row max; biased scores written back to TMEM ----
+    float m = -INFINITY;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&bars->s[kb], 0);
+      tc_fence_after();
+      if (warp_valid) {
+        const int kvalid = min(kTcK, S - kb * kTcK);
+        for (int c = 0; c < kvalid; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(lane_base + kb * kTcK + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = kb * kTcK + c + j;
+            float sc = -INFINITY;
+            if (key < S) {
+              sc = __uint_as_float(v[j]) + s_lut[crow - s_ccol[key]];
+              if constexpr (HAS_PAD) {
+                if (s_pad[key] != 0) sc = -INFINITY;
+              }
+            }
+            m = fmaxf(m, sc);
+            v[j] = __float_as_uint(sc);
+          }
+          __syncwarp();
+          tmem_st32(lane_base + kb * kTcK + c, v);
+        }
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    named_bar_sync(1, 128);            // every row thread is done with the LUT: the buffer becomes P
+    tc_fence_after();
+
+    // ---- phase B: exp, row sum, P -> shared memory ----
+    const float mb = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
+    float l = 0.f;
+    const uint32_t sP_u = smem_u32(sP);
+    for (int kb = 0; kb < nkb; ++kb) {
+      if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);     // previous P consumed by the tensor core
+      const int kvalid = min(kTcK, S - kb * kTcK);
+#pragma unroll 1
+      for (int c = 0; c < kTcK; c += 32) {
+        uint32_t pk[16];
+        if (warp_valid && c < kvalid) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(lane_base + kb * kTcK + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), 1.4426950408889634f, -mb));
+            l += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        }
+        // 32 keys = 64 B = chunks (c/8 .. c/8 + 3) of this row in atom c / 64
+        const uint32_t atom = sP_u + (c >> 6) * (kTcQ * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sts128u(atom + sw128_off(r, ((c & 63) >> 3) + k), make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p[kb]);
+    }
+
+    // ---- epilogue: O / l -> bf16 rows ----
+    mbar_wait(&bars->pv[nkb - 1], 0);
+    tc_fence_after();
+    if (warp_valid) {
+      uint32_t o0[32], o1[32];
+      __syncwarp();
+      tmem_ld32(lane_base, o0);
+      tmem_ld32(lane_base + 32, o1);
+      tmem_ld_wait();
+      if (row_valid) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        float ssum = 0.f, ssq = 0.f;
+        __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o0[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
+          *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                             pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o1[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
+          *reinterpret_cast<uint4*>(op + 32 + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                                  pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+        if (ln_stats != nullptr) {
+          const long rows_total = static_cast<long>(B) * S;
+          *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, tmem_cols);
+  }
+}
+
+// lut[h][l] = table[idx[l]][h]
+__global__ void relpos_lut_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ lut,
+                                  int L, int H) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const long bk = idx[l];
+  for (int h = 0; h < H; ++h) lut[static_cast<long>(h) * L + l] = table[bk * H + h];
+}
+
+int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int H, cudaStream_t stream) {
+  if (L <= 0 || H <= 0) return OPB_ERR_INVALID;
+  relpos_lut_kernel<<<(L + 255) / 256, 256, 0, stream>>>(table, idx, lut, L, H);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
+                     const uint8_t* key_pad, void* out, float* ln_stats, int B, int S, int H, cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
+  const int nkb = (S + kTcK - 1) / kTcK;
+  if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
+  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>(S) * 4 + S;
+  if (table_bytes > kTcQ * kTcK * 2) return OPB_ERR_UNSUPPORTED;
+  const int D = H * kTcD;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, kTcQ);
+  if (rc != OPB_OK) return rc;
+  const size_t smem = kTcQ * 128 + 2ull * nkb * kTcK * 128 + kTcQ * kTcK * 2 + sizeof(TcBars);
+  const uint32_t tmem_cols = nkb == 1 ? 128 : (nkb == 2 ? 256 : 512);
+  static size_t configured[2] = {0, 0};
+  const int v = key_pad != nullptr ? 1 : 0;
+  if (smem > configured[v]) {
+    cudaError_t e = v ? cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                      : cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return OPB_ERR_CUDA;
+    configured[v] = smem;
+  }
+  const int q_tiles = (S + kTcQ - 1) / kTcQ;
+  const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
+  if (v)
+    attention_tc_kernel<true><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
+                                                          reinterpret_cast<__nv_bfloat16*>(out), ln_stats, B, S, H, nkb, tmem_cols);
+  else
+    attention_tc_kernel<false><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
+                                                           reinterpret_cast<__nv_bfloat16*>(out), ln_stats, B, S, H, nkb, tmem_cols);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+}  // namespace opb

@@ -49,6 +49,19 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
                             static_cast<cudaStream_t>(stream));
 }
 
+int opb_attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int32_t* code_row,
+                         const int32_t* code_col, const uint8_t* key_pad, void* out, float* ln_stats, int B, int S,
+                         int H, void* stream) {
+  if (!qkv || !lut || !code_row || !code_col || !out) return OPB_ERR_INVALID;
+  return opb::attention_tc_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, ln_stats, B, S, H,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_lut_build(const float* table, const int32_t* idx, float* lut, int L, int H, void* stream) {
+  if (!table || !idx || !lut) return OPB_ERR_INVALID;
+  return opb::relpos_lut_build(table, idx, lut, L, H, static_cast<cudaStream_t>(stream));
+}
+
 int opb_gemm_bf16_ex(const opb_gemm_args* a, void* stream) {
   if (a == nullptr || a->A == nullptr || a->B == nullptr || a->out == nullptr) return OPB_ERR_INVALID;
   if ((a->ln_mu == nullptr) != (a->ln_rstd == nullptr) || (a->ln_mu == nullptr) != (a->ln_colsum == nullptr))

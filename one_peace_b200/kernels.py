@@ -72,6 +72,38 @@ def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, ou
     return out
 
 
+class RelPosBias:
+    """Relative-position bias of one forward in both forms the attention kernels take: the dense fp32 (H,S,S_pad)
+    table (mma.sync kernel, any S) and the LUT form (tcgen05 kernel, S <= 384)."""
+
+    def __init__(self, dense=None, lut=None, code_row=None, code_col=None):
+        self.dense, self.lut, self.code_row, self.code_col = dense, lut, code_row, code_col
+
+
+def relpos_lut_build(table, idx):
+    """table fp32 [NB,H], idx int32 [L] -> lut fp32 [H, L]"""
+    L, H = idx.numel(), table.shape[1]
+    lut = torch.empty(H, L, dtype=torch.float32, device=table.device)
+    st = _lib.load().opb_relpos_lut_build(table.data_ptr(), idx.data_ptr(), lut.data_ptr(), L, H, _stream())
+    _lib.check(st, "opb_relpos_lut_build")
+    _count()
+    return lut
+
+
+def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None):
+    """tcgen05 attention (S <= 384).  rp: RelPosBias with the LUT form."""
+    D = H * 64
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
+    if out is None:
+        out = torch.empty(B * S, D, dtype=torch.bfloat16, device=qkv.device)
+    st = _lib.load().opb_attention_tc_fwd(qkv.data_ptr(), rp.lut.data_ptr(), rp.lut.shape[1], rp.code_row.data_ptr(),
+                                          rp.code_col.data_ptr(), _ptr(key_pad), out.data_ptr(), _ptr(ln_stats), B, S, H,
+                                          _stream())
+    _lib.check(st, "opb_attention_tc_fwd")
+    _count()
+    return out
+
+
 def gemm_ln(a, w, epi, out, *, ln_mu=None, ln_rstd=None, ln_colsum=None, bias=None, colscale=None, gamma=None,
             resid=None, stats_out=None, out_bf16=None, cta_group=0):
     """GEMM through `opb_gemm_bf16_ex`: fused LayerNorm of the A operand (ln_*), statistics / bf16 side outputs."""

@@ -49,6 +49,13 @@ class MultiheadAttention(nn.Module):
               self.out_proj.weight, self.out_proj.bias] + ([self.ln.weight, self.ln.bias] if self.ln is not None else [])
         return self._cache.get(ps, build)
 
+    def run_attention(self, qkv, bias, key_pad, B, S, out=None, ln_stats=None):
+        """bias: kernels.RelPosBias (or None).  tcgen05 kernel when the bias is in LUT form (S <= 384), else mma.sync."""
+        if bias is not None and bias.lut is not None:
+            return K.attention_tc(qkv, bias, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats)
+        dense = bias.dense if bias is not None else None
+        return K.attention(qkv, dense, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats)
+
     def attend(self, h, bias, key_pad, B, S):
         """h: bf16 [B*S, d] (already layer-normed).  Returns the pre-out_proj tensor (after the inner LN), bf16."""
         if self.c_attn is not None:
@@ -59,7 +66,7 @@ class MultiheadAttention(nn.Module):
         d = self.embed_dim
         qkv = torch.empty(B * S, 3 * d, dtype=torch.bfloat16, device=h.device)
         K.gemm(h, p["wqkv"], K.EPI_STORE_BF16, qkv, bias=p["bqkv"], colscale=p["qscale"])
-        o = K.attention(qkv, bias, key_pad, B, S, self.num_heads)
+        o = self.run_attention(qkv, bias, key_pad, B, S)
         if self.ln is not None:
             K.layernorm(o, p["ln_w"], p["ln_b"], o, eps=self.ln.eps)
         return o

@@ -166,7 +166,7 @@ class TransformerEncoderLayer(nn.Module):
         K.gemm_ln(xb, a["wqkv"], K.EPI_STORE_BF16, ws["qkv"], ln_mu=mu, ln_rstd=rstd, ln_colsum=a["cqkv"],
                   bias=a["dqkv"], colscale=a["qscale"])
         # attention (+ per-head partial statistics of its output rows)
-        K.attention(ws["qkv"], bias, key_pad, B, S, H, out=ws["o"], ln_stats=ws["part"])
+        self.self_attn.run_attention(ws["qkv"], bias, key_pad, B, S, out=ws["o"], ln_stats=ws["part"])
         K.ln_stats_finalize(ws["part"], H, M, d, self.self_attn.ln.eps, ws["mu2"], ws["rstd2"])
         # inner LN -> out_proj -> LayerScale + residual; emits x, xb and the statistics for LN2
         n_t = (d + 255) // 256

@@ -261,3 +261,47 @@ def test_attention_ln_stats(K):
     o = out.float()
     torch.testing.assert_close(mu, o.mean(1), atol=2e-3, rtol=1e-2)      # stats are of the pre-rounding fp32 rows
     torch.testing.assert_close(rstd, (o.var(1, unbiased=False) + 1e-5).rsqrt(), atol=0, rtol=1e-2)
+
+
+@pytest.mark.parametrize("kind,B,S,H,use_pad", [("text", 3, 17, 4, True), ("text", 2, 72, 4, True), ("image", 3, 197, 24, False),
+                                                 ("image", 2, 257, 4, False), ("text", 2, 384, 2, True), ("text", 5, 128, 4, False)])
+def test_attention_tc(K, kind, B, S, H, use_pad):
+    """tcgen05 attention with the LUT-form relative-position bias vs a plain fp32 reference on the dense bias."""
+    import numpy as np
+    import restated as R
+    from one_peace_b200 import relpos
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(S + H)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    if kind == "text":
+        bucket = R.make_token_bucket_position(256)[:S, :S]
+        codes = relpos.text_codes(S)
+        ntab = 514
+    else:
+        w = int(round((S - 1) ** 0.5))
+        bucket = R.make_image_bucket_position(w)
+        codes = relpos.image_codes(S, w)
+        ntab = (2 * w - 1) ** 2 + 3
+    table = torch.randn(ntab, H, device="cuda", generator=g)
+    li = relpos.build_lut_index(bucket.numpy(), codes)
+    assert li is not None
+    lut_idx, crow, ccol = (torch.from_numpy(a).cuda() for a in li)
+    rp = K.RelPosBias(lut=K.relpos_lut_build(table, lut_idx), code_row=crow, code_col=ccol)
+    dense = table[bucket.cuda()].permute(2, 0, 1)                     # (H,S,S)
+    assert torch.equal(rp.lut[:, (crow[:, None] - ccol[None, :]).long()], dense)
+    kp = None
+    if use_pad:
+        kp = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+        for b in range(B):
+            kp[b, S - 1 - 2 * b:] = 1
+    part = torch.zeros(H * B * S * 2, device="cuda")
+    out = K.attention_tc(qkv, rp, kp, B, S, H, ln_stats=part)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc = q @ k.transpose(-1, -2) + dense[None]
+    if kp is not None:
+        sc = sc.masked_fill(kp.bool()[:, None, None, :], float("-inf"))
+    want = (sc.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+    assert relerr(out, want) < 8e-3
+    mu = torch.empty(B * S, device="cuda"); rstd = torch.empty(B * S, device="cuda")
+    K.ln_stats_finalize(part, H, B * S, D, 1e-5, mu, rstd)
+    torch.testing.assert_close(mu, out.float().mean(1), atol=2e-3, rtol=1e-2)

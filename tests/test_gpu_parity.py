@@ -36,6 +36,14 @@ def assert_same_argmax(got_sim, want_sim, what, margin=2e-3):
     assert decided.float().mean() >= 0.5, "synthetic case has too few decided rows to be a test"
 
 
+def dense_bias(rp, S):
+    """(H,S,S) fp32 CPU view of a kernels.RelPosBias in either form."""
+    if rp.lut is not None:
+        idx = (rp.code_row[:, None] - rp.code_col[None, :]).long()
+        return rp.lut[:, idx].cpu()
+    return rp.dense[:, :, :S].cpu()
+
+
 def check(got, want, what, min_cos=0.999):
     got = got.float().cpu()
     cos = torch.nn.functional.cosine_similarity(got, want).min().item()
@@ -83,7 +91,7 @@ def test_tiny_audio_adapter_output(tiny):
     print("audio adapter rel err", err, "cos", cos)
     assert err < 3e-2 and cos > 0.9995          # 8 bf16 conv GEMMs + 5 grouped convs, each followed by LN/GELU
     S = x.shape[1]
-    torch.testing.assert_close(bias[0][:, :, :S].cpu(), fx["adapter"]["audio_bias"], atol=0, rtol=0)
+    torch.testing.assert_close(dense_bias(bias[0], S), fx["adapter"]["audio_bias"], atol=0, rtol=0)
     assert torch.equal(pad.bool().cpu(), apm)
 
 
@@ -111,13 +119,13 @@ def test_tiny_adapter_outputs(tiny):
     want = fx["adapter"]["text_x"] * (~fx["adapter"]["text_pad"]).unsqueeze(-1)
     torch.testing.assert_close(x.cpu(), want, atol=1e-6, rtol=0)
     S = x.shape[1]
-    torch.testing.assert_close(bias[0][:, :, :S].cpu(), fx["adapter"]["text_bias"], atol=0, rtol=0)
+    torch.testing.assert_close(dense_bias(bias[0], S), fx["adapter"]["text_bias"], atol=0, rtol=0)
     xi, _, bi = ew.image_adapter(img.cuda())
     ref = fx["adapter"]["image_x"]
     err = (xi[:1].cpu() - ref).abs().max().item() / ref.abs().max().item()
     print("image adapter rel err", err)
     assert err < 2e-2       # three bf16 GEMMs + two LN/GELU stages
-    torch.testing.assert_close(bi[0][:, :40, :40].cpu(), fx["adapter"]["image_bias"], atol=0, rtol=0)
+    torch.testing.assert_close(dense_bias(bi[0], 197)[:, :40, :40], fx["adapter"]["image_bias"], atol=0, rtol=0)
 
 
 def test_tiny_retrieval_argmax_matches_oracle(tiny):
