@@ -219,7 +219,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     // ---- phase B: exp, row sum, P -> shared memory ----
     const float mb = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
     float l = 0.f;
-    const uint32_t sP_u = smem_u32(sP);
     for (int kb = 0; kb < nkb; ++kb) {
       if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);     // previous P consumed by the tensor core
       const int kvalid = min(kTcK, S - kb * kTcK);
@@ -243,7 +242,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
           for (int j = 0; j < 16; ++j) pk[j] = 0u;
         }
         // 32 keys = 64 B = chunks (c/8 .. c/8 + 3) of this row in atom c / 64
-        const uint32_t atom = sP_u + (c >> 6) * (kTcQ * 128);
+        uint8_t* atom = sP + (c >> 6) * (kTcQ * 128);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           sts128u(atom + sw128_off(r, ((c & 63) >> 3) + k), make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));

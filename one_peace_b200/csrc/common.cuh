@@ -289,13 +289,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int umma_m, int umma_n) {
 // the GeGLU GEMM evaluates it 16 M times per layer and was epilogue-compute-bound with erff.
 OPB_DEVICE float fast_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
   const float r = fmaf(-p, e, 1.0f);
   return copysignf(r, x);
 }
@@ -303,17 +305,12 @@ OPB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70
 
 // explicit shared-state-space vector accesses (pointers derived from the dynamic smem base otherwise compile to
 // generic LD/ST with 64-bit addresses)
-OPB_DEVICE float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-OPB_DEVICE void sts128(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-OPB_DEVICE void sts128u(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+// (Plain pointer accesses: volatile inline-asm ld/st.shared would pin every access in program order and serialise the
+// epilogue on shared-memory latency; the pointers must derive directly from the `extern __shared__` array so that the
+// compiler keeps the shared state space and emits LDS / STS rather than generic LD / ST.)
+OPB_DEVICE float4 lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+OPB_DEVICE void sts128(uint8_t* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+OPB_DEVICE void sts128u(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
 OPB_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

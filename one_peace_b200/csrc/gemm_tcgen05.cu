@@ -100,8 +100,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int M = geo.M, N = geo.N;
   using Cfg = GemmCfg<CG, EPI, TMAEPI>;
   using ECfg = EpiCfg<EPI, TMAEPI>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no static shared memory: the dynamic window starts at the 1024-aligned base of the CTA's shared memory (checked);
+  // deriving every pointer from this array keeps the shared state space visible to the compiler (LDS / STS)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   SmemBars* bars = reinterpret_cast<SmemBars*>(smem + Cfg::kStages * Cfg::kStageBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -245,7 +248,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         float st_sum = 0.f, st_sq = 0.f;
         // per-column vectors of this tile -> this warp's smem copy ([3][256] fp32): colsum | bias | scale-or-gamma
-        const uint32_t cv_s = smem_u32(stg + ECfg::kColVecOff);
+        uint8_t* cv_s = stg + ECfg::kColVecOff;
         {
           const float* v2 = (EPI == EPI_RESID_F32) ? ep.gamma : ep.colscale;
           const float* vecs[3] = {ep.ln_colsum, ep.bias, v2};
@@ -338,7 +341,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               mbar_wait(&rbar[slot], (gc / 3) & 1);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const float4 r = lds128(smem_u32(buf) + sw128_off(lane, k));
+                const float4 r = lds128(buf + sw128_off(lane, k));
                 x[4 * k] += r.x; x[4 * k + 1] += r.y; x[4 * k + 2] += r.z; x[4 * k + 3] += r.w;
               }
             }
@@ -350,7 +353,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              sts128(smem_u32(buf) + sw128_off(lane, k), make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
+              sts128(buf + sw128_off(lane, k), make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
             uint8_t* bufB = bufB0 + ((c >> 1) & 1) * 4096;     // alternate per 64-column pair
             if (ep.out_bf16 != nullptr) {
 #pragma unroll
@@ -360,7 +363,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 o.y = pack_bf16x2(x[8 * k + 2], x[8 * k + 3]);
                 o.z = pack_bf16x2(x[8 * k + 4], x[8 * k + 5]);
                 o.w = pack_bf16x2(x[8 * k + 6], x[8 * k + 7]);
-                sts128u(smem_u32(bufB) + sw128_off(lane, (c & 1) * 4 + k), o);
+                sts128u(bufB + sw128_off(lane, (c & 1) * 4 + k), o);
               }
             }
             fence_proxy_async();
@@ -379,7 +382,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
           constexpr int kChunks = (EPI == EPI_GEGLU_BF16) ? 2 : 4;
-          constexpr int kMine = kChunks / 2;                       // chunks per warp (two warps share a lane quarter)
+          constexpr int kMine = kChunks / (ECfg::kWarps / 4);      // chunks per warp (8-warp mode: two warps share a lane quarter)
           const int gc0 = it * kMine;
 #pragma unroll 1
           for (int c = hf * kMine; c < (hf + 1) * kMine; ++c) {
@@ -469,7 +472,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 o.y = pack_bf16x2(y[8 * k + 2], y[8 * k + 3]);
                 o.z = pack_bf16x2(y[8 * k + 4], y[8 * k + 5]);
                 o.w = pack_bf16x2(y[8 * k + 6], y[8 * k + 7]);
-                sts128u(smem_u32(buf) + sw128_off(lane, hh * 4 + k), o);
+                sts128u(buf + sw128_off(lane, hh * 4 + k), o);
               }
             }
             fence_proxy_async();
@@ -482,7 +485,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           if constexpr (EPI == EPI_GEGLU_BF16) {
             if (row_ok && ep.stats_out != nullptr)
+            {
               *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk * 2 + hf) * M + row) * 2) = make_float2(st_sum, st_sq);
+              if constexpr (ECfg::kWarps == 4)      // keep the [2 * n_tiles, M] record layout of the 8-warp mode
+                *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk * 2 + 1) * M + row) * 2) = make_float2(0.f, 0.f);
+            }
           }
         }
         continue;
@@ -505,11 +512,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // per-column epilogue vectors of this tile in shared memory (see the TMA path); grouped GEMMs index them by
       // global column and keep reading global memory
       bool use_cv = false;
-      uint32_t cv_s = 0;
+      uint8_t* cv_s = smem;
       if constexpr (ECfg::kRegular && !TMAEPI) {
         use_cv = (geo.groups == 1);
         if (use_cv) {
-          cv_s = smem_u32(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 2) * ECfg::kWarpBytes);
+          cv_s = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 2) * ECfg::kWarpBytes;
           const float* v2 = (EPI == EPI_RESID_F32) ? ep.gamma : ep.colscale;
           const float* vecs[3] = {ep.ln_colsum, ep.bias, v2};
           const int tcol0 = n_blk * kBlockN;

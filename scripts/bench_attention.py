@@ -1,18 +1,27 @@
-"""Times the attention kernel alone at the 4B vision shape (B=64, S=197, H=24) under the current env overrides."""
+"""Times the attention kernels alone at the 4B vision shape (B=64, S=197, H=24): mma.sync (dense bias) vs tcgen05 (LUT)."""
 import os, sys, torch
-sys.path.insert(0, ".")
-from one_peace_b200 import kernels as K
+sys.path.insert(0, "."); sys.path.insert(0, "oracle")
+from one_peace_b200 import kernels as K, relpos
+import restated as R
 B, S, H = 64, 197, 24
 D = H * 64
 qkv = (torch.randn(B * S, 3 * D, device="cuda") * 0.5).bfloat16()
-bias = torch.randn(H, S, 200, device="cuda")
+bucket = R.make_image_bucket_position(14)
+table = torch.randn(732, H, device="cuda")
+li = relpos.build_lut_index(bucket.numpy(), relpos.image_codes(S, 14))
+rp = K.RelPosBias(lut=K.relpos_lut_build(table, torch.from_numpy(li[0]).cuda()), code_row=torch.from_numpy(li[1]).cuda(), code_col=torch.from_numpy(li[2]).cuda())
+dense = K.relpos_bias_build(table, bucket.cuda(), S, H)
 out = torch.empty(B * S, D, dtype=torch.bfloat16, device="cuda")
-for _ in range(3):
-    K.attention(qkv, bias, None, B, S, H, out=out)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20):
-    K.attention(qkv, bias, None, B, S, H, out=out)
-e1.record(); torch.cuda.synchronize()
-print(f"stage={os.environ.get('OPB_ATTN_STAGE_BIAS')} bpc={os.environ.get('OPB_ATTN_BPC')}: {e0.elapsed_time(e1)/20*1000:.1f} us")
+part = torch.empty(H * B * S * 2, device="cuda")
+def timeit(f, n=30):
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1000
+t_old = timeit(lambda: K.attention(qkv, dense, None, B, S, H, out=out, ln_stats=part))
+o_old = out.clone()
+t_new = timeit(lambda: K.attention_tc(qkv, rp, None, B, S, H, out=out, ln_stats=part))
+print(f"mma.sync {t_old:.1f} us | tcgen05 {t_new:.1f} us | max diff {(out.float()-o_old.float()).abs().max().item():.3e}")

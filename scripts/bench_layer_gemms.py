@@ -49,4 +49,26 @@ for k in range(4):
     ms = sum(a.elapsed_time(b) for a, b in evs[k][40:]) / len(evs[k][40:])
     tot += ms
     out.append(f"{names[k]} {ms*1000:.0f}us {flops[k]/ms/1e9:.0f}TF")
+# calibration: cuBLAS (torch.matmul, bf16, no epilogue work at all) on the same shapes, same in-situ loop
+ref_out = [torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev), torch.empty(M, d, dtype=torch.bfloat16, device=dev),
+           torch.empty(M, 2 * F, dtype=torch.bfloat16, device=dev), torch.empty(M, d, dtype=torch.bfloat16, device=dev)]
+def ref_layer(i, evs=None):
+    wq, wo, w01, w2 = W[i % NL]
+    ops = [(xb, wq), (o, wo), (xb, w01), (u, w2)]
+    for k, (a, b) in enumerate(ops):
+        if evs is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        torch.matmul(a, b.t(), out=ref_out[k])
+        if evs is not None:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(); evs[k].append((e0, e1))
+for i in range(20): ref_layer(i)
+torch.cuda.synchronize()
+revs = [[], [], [], []]
+for i in range(80): ref_layer(i, revs)
+torch.cuda.synchronize()
+rtot = 0; rout = []
+for k in range(4):
+    ms = sum(a.elapsed_time(b) for a, b in revs[k][20:]) / len(revs[k][20:]); rtot += ms
+    rout.append(f"{names[k]} {ms*1000:.0f}us {flops[k]/ms/1e9:.0f}TF")
+print("cuBLAS (no epilogue): " + " | ".join(rout) + f" | layer {rtot*1000:.0f}us ({sum(flops)/rtot/1e9:.0f} TF)")
 print(f"mode={os.environ.get('OPB_GEMM_TMA_EPILOGUE','-')}: " + " | ".join(out) + f" | layer {tot*1000:.0f}us ({sum(flops)/tot/1e9:.0f} TF) wall/layer {t0.elapsed_time(t1)/120*1000:.0f}us")
