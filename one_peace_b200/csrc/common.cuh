@@ -170,6 +170,8 @@ OPB_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %
 template <int N>
 OPB_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// byte offset of 16-byte chunk `chunk` (0..3) of row `row` in a [rows][64 B] tile stored with the 64-byte swizzle
+OPB_DEVICE uint32_t sw64_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 // byte offset of 16-byte chunk `chunk` of row `row` in a [rows][128 B] tile stored with the 128-byte swizzle
 OPB_DEVICE uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 

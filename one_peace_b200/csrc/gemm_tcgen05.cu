@@ -34,8 +34,11 @@ constexpr int kUmmaK = 16;
 constexpr int kAccStages = 2;
 
 // Epilogue staging (TMA-store path): per epilogue warp a ring of 4 KB chunk buffers ([32 rows][128 B], 128B swizzle)
-//   RESID_F32 / STORE_F32 : 3 x fp32 chunk (32 cols; the residual chunk is TMA-prefetched two chunks ahead and
-//                           overwritten in place) + 2 x bf16-copy chunk (64 cols)            = 20 KB / warp
+//   RESID_F32 / STORE_F32 : 4 x fp32 chunk (32 cols; the residual chunk is TMA-prefetched two chunks ahead and
+//                           overwritten in place; with 4 slots a slot is refilled two stores after it was stored
+//                           from, so the producer never waits for the NEWEST bulk store — waiting on it cost ~1.5 us
+//                           per chunk and made out_proj 3x slower than cuBLAS) + 2 x 2 KB bf16-copy chunk (32 cols,
+//                           64-byte rows, 64B swizzle)                                         = 20 KB / warp
 //   STORE_BF16 / GELU_BF16 / GEGLU_BF16 : 2 x bf16 chunk (64 cols)                            =  8 KB / warp
 // plus 4 KB / warp holding the tile's per-column epilogue vectors (LayerNorm column sums, bias, scale / gamma):
 // fetched once per tile BEFORE the accumulator is ready, so no epilogue FMA ever waits on a global load (the
@@ -53,8 +56,8 @@ struct EpiCfg {
   // TMEM-load -> math -> smem -> TMA-store chain.  The fp32 residual epilogue keeps 4 (its staging is 24 KB / warp).
   static constexpr int kWarps = (TMAEPI && !kF32 && OPB_EPI_WARPS_BF16 == 8) ? 8 : 4;
   static constexpr int kThreads = 64 + 32 * kWarps;
-  static constexpr int kRing = TMAEPI ? (kF32 ? 3 : 2) : 0;
-  static constexpr int kColVecOff = kRing * 4096 + (kF32 ? 2 * 4096 : 0);
+  static constexpr int kRing = TMAEPI ? (kF32 ? 4 : 2) : 0;
+  static constexpr int kColVecOff = kRing * 4096 + (kF32 ? 2 * 2048 : 0);
   static constexpr int kWarpBytes = TMAEPI ? (kColVecOff + 4096) : (kRegular ? 4096 : 0);   // direct path: column vectors only
   static constexpr int kBytes = kWarps * kWarpBytes;
 };
@@ -247,26 +250,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           ln_rs = ep.ln_rstd[rc];
         }
         float st_sum = 0.f, st_sq = 0.f;
-        // per-column vectors of this tile -> this warp's smem copy ([3][256] fp32): colsum | bias | scale-or-gamma
+        // Per-column epilogue coefficients of this tile -> this warp's smem copy ([3][256] fp32), in AFFINE form so the
+        // inner loops are branch-free and every load is unconditional (the compiler can batch them):
+        //     x = acc * (ln_rs * P[n]) + (nlm * Q[n] + R[n]),   nlm = -ln_rs * ln_mu
+        //     P = colscale | gamma | 1,   Q = colsum * P,   R = bias * P;   columns >= N get P = Q = R = 0
         uint8_t* cv_s = stg + ECfg::kColVecOff;
         {
           const float* v2 = (EPI == EPI_RESID_F32) ? ep.gamma : ep.colscale;
-          const float* vecs[3] = {ep.ln_colsum, ep.bias, v2};
           __syncwarp();
 #pragma unroll
-          for (int vv = 0; vv < 3; ++vv) {
-            if (vecs[vv] != nullptr) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const int idx = k * 128 + lane * 4;
-                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col0 + idx < N) t4 = *reinterpret_cast<const float4*>(vecs[vv] + col0 + idx);
-                sts128(cv_s + 4 * (vv * 256 + idx), t4);
+          for (int k = 0; k < 2; ++k) {
+            const int idx = k * 128 + lane * 4;
+            float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = p4, r4 = p4;
+            if (col0 + idx < N) {
+              p4 = v2 != nullptr ? *reinterpret_cast<const float4*>(v2 + col0 + idx) : make_float4(1.f, 1.f, 1.f, 1.f);
+              if (ep.ln_colsum != nullptr) {
+                const float4 c4 = *reinterpret_cast<const float4*>(ep.ln_colsum + col0 + idx);
+                q4 = make_float4(c4.x * p4.x, c4.y * p4.y, c4.z * p4.z, c4.w * p4.w);
+              }
+              if (ep.bias != nullptr) {
+                const float4 b4 = *reinterpret_cast<const float4*>(ep.bias + col0 + idx);
+                r4 = make_float4(b4.x * p4.x, b4.y * p4.y, b4.z * p4.z, b4.w * p4.w);
               }
             }
+            sts128(cv_s + 4 * idx, p4);
+            sts128(cv_s + 4 * (256 + idx), q4);
+            sts128(cv_s + 4 * (512 + idx), r4);
           }
           __syncwarp();
         }
+        const float nlm = -ln_rs * ln_mu;
         if constexpr (ECfg::kF32) {
           uint8_t* bufB0 = stg + ECfg::kRing * 4096;
           uint64_t* rbar = bars->resid_full[ew];
@@ -278,7 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (has_res && lane == 0) {
 #pragma unroll
             for (int pc = 0; pc < 2; ++pc) {
-              const int slot = (gc0 + pc) % 3;
+              const int slot = (gc0 + pc) & 3;
               mbar_arrive_expect_tx(&rbar[slot], 4096);
               tma_load_2d(&tm_o, &rbar[slot], stg + slot * 4096, col0 + 32 * pc, row0);
             }
@@ -289,7 +302,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
             const int gc = gc0 + c;
-            const int slot = gc % 3;
+            const int slot = gc & 3;
             uint8_t* buf = stg + slot * 4096;
             uint32_t v[32];
             __syncwarp();
@@ -301,60 +314,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
             }
             if (lane == 0) {
-              // the slot of chunk c+2 was last stored from by chunk c-1 (issued one TMEM load ago): its shared-memory
-              // read must have finished before the residual prefetch overwrites it
-              bulk_wait_read<0>();
+              // the slot of chunk c+2 was last stored from by chunk c-2: every store group except the newest one must
+              // have finished reading shared memory (this also covers the bf16-copy buffer written below)
+              bulk_wait_read<1>();
               if (has_res && c + 2 < 8) {
-                const int ns = (gc + 2) % 3;
+                const int ns = (gc + 2) & 3;
                 mbar_arrive_expect_tx(&rbar[ns], 4096);
                 tma_load_2d(&tm_o, &rbar[ns], stg + ns * 4096, col0 + 32 * (c + 2), row0);
               }
             }
             __syncwarp();
             float x[32];
+            {
+              float4 pp[8], qq[8], rr[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int col = col0 + c * 32 + j;
-              float4 xv = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                      __uint_as_float(v[j + 3]));
-              if (col < N) {
-                const int tc = c * 32 + j;      // column inside the tile
-                if (ep.ln_mu != nullptr) {
-                  const float4 cs = lds128(cv_s + 4 * tc);
-                  xv.x = ln_rs * (xv.x - ln_mu * cs.x); xv.y = ln_rs * (xv.y - ln_mu * cs.y);
-                  xv.z = ln_rs * (xv.z - ln_mu * cs.z); xv.w = ln_rs * (xv.w - ln_mu * cs.w);
-                }
-                if (ep.bias != nullptr) {
-                  const float4 bb = lds128(cv_s + 4 * (256 + tc));
-                  xv.x += bb.x; xv.y += bb.y; xv.z += bb.z; xv.w += bb.w;
-                }
-                if constexpr (EPI == EPI_RESID_F32) {
-                  if (ep.gamma != nullptr) {
-                    const float4 gg = lds128(cv_s + 4 * (512 + tc));
-                    xv.x *= gg.x; xv.y *= gg.y; xv.z *= gg.z; xv.w *= gg.w;
-                  }
-                }
+              for (int k = 0; k < 8; ++k) {
+                pp[k] = lds128(cv_s + 4 * (c * 32 + 4 * k));
+                qq[k] = lds128(cv_s + 4 * (256 + c * 32 + 4 * k));
+                rr[k] = lds128(cv_s + 4 * (512 + c * 32 + 4 * k));
               }
-              x[j] = xv.x; x[j + 1] = xv.y; x[j + 2] = xv.z; x[j + 3] = xv.w;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                x[4 * k] = fmaf(__uint_as_float(v[4 * k]), ln_rs * pp[k].x, fmaf(nlm, qq[k].x, rr[k].x));
+                x[4 * k + 1] = fmaf(__uint_as_float(v[4 * k + 1]), ln_rs * pp[k].y, fmaf(nlm, qq[k].y, rr[k].y));
+                x[4 * k + 2] = fmaf(__uint_as_float(v[4 * k + 2]), ln_rs * pp[k].z, fmaf(nlm, qq[k].z, rr[k].z));
+                x[4 * k + 3] = fmaf(__uint_as_float(v[4 * k + 3]), ln_rs * pp[k].w, fmaf(nlm, qq[k].w, rr[k].w));
+              }
             }
             if (has_res) {
-              mbar_wait(&rbar[slot], (gc / 3) & 1);
+              mbar_wait(&rbar[slot], (gc >> 2) & 1);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const float4 r = lds128(buf + sw128_off(lane, k));
                 x[4 * k] += r.x; x[4 * k + 1] += r.y; x[4 * k + 2] += r.z; x[4 * k + 3] += r.w;
               }
             }
-            if (ep.stats_out != nullptr) {
+            if (ep.stats_out != nullptr) {      // columns >= N hold zeros (P = Q = R = 0 and zero-filled residual)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (col0 + c * 32 + j < N) { st_sum += x[j]; st_sq += x[j] * x[j]; }
-              }
+              for (int j = 0; j < 32; ++j) { st_sum += x[j]; st_sq += x[j] * x[j]; }
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               sts128(buf + sw128_off(lane, k), make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
-            uint8_t* bufB = bufB0 + ((c >> 1) & 1) * 4096;     // alternate per 64-column pair
+            uint8_t* bufB = bufB0 + (c & 1) * 2048;            // [32 rows][64 B], alternating per chunk
             if (ep.out_bf16 != nullptr) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -363,14 +365,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 o.y = pack_bf16x2(x[8 * k + 2], x[8 * k + 3]);
                 o.z = pack_bf16x2(x[8 * k + 4], x[8 * k + 5]);
                 o.w = pack_bf16x2(x[8 * k + 6], x[8 * k + 7]);
-                sts128u(bufB + sw128_off(lane, (c & 1) * 4 + k), o);
+                sts128u(bufB + sw64_off(lane, k), o);
               }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
               tma_store_2d(&tm_o, buf, col0 + c * 32, row0);
-              if (ep.out_bf16 != nullptr && (c & 1)) tma_store_2d(&tm_o2, bufB, col0 + (c - 1) * 32, row0);
+              if (ep.out_bf16 != nullptr) tma_store_2d(&tm_o2, bufB, col0 + c * 32, row0);
               bulk_commit();
             }
           }
@@ -404,26 +406,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   __syncwarp();
                   if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
                 }
+                {
+                  float4 qg[8], rg[8], ql[8], rl[8];     // GeGLU: P == 1
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 ga = make_float4(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), __uint_as_float(g[j + 2]), __uint_as_float(g[j + 3]));
-                  float4 li = make_float4(__uint_as_float(l[j]), __uint_as_float(l[j + 1]), __uint_as_float(l[j + 2]), __uint_as_float(l[j + 3]));
-                  if (ep.ln_mu != nullptr) {
-                    const float4 cg = lds128(cv_s + 4 * (ac + j));
-                    const float4 cl = lds128(cv_s + 4 * (kBlockN / 2 + ac + j));
-                    ga.x = ln_rs * (ga.x - ln_mu * cg.x); ga.y = ln_rs * (ga.y - ln_mu * cg.y);
-                    ga.z = ln_rs * (ga.z - ln_mu * cg.z); ga.w = ln_rs * (ga.w - ln_mu * cg.w);
-                    li.x = ln_rs * (li.x - ln_mu * cl.x); li.y = ln_rs * (li.y - ln_mu * cl.y);
-                    li.z = ln_rs * (li.z - ln_mu * cl.z); li.w = ln_rs * (li.w - ln_mu * cl.w);
+                  for (int k = 0; k < 8; ++k) {
+                    qg[k] = lds128(cv_s + 4 * (256 + ac + 4 * k));
+                    rg[k] = lds128(cv_s + 4 * (512 + ac + 4 * k));
+                    ql[k] = lds128(cv_s + 4 * (256 + kBlockN / 2 + ac + 4 * k));
+                    rl[k] = lds128(cv_s + 4 * (512 + kBlockN / 2 + ac + 4 * k));
                   }
-                  if (ep.bias != nullptr) {
-                    const float4 bg = lds128(cv_s + 4 * (256 + ac + j));
-                    const float4 bl = lds128(cv_s + 4 * (256 + kBlockN / 2 + ac + j));
-                    ga.x += bg.x; ga.y += bg.y; ga.z += bg.z; ga.w += bg.w;
-                    li.x += bl.x; li.y += bl.y; li.z += bl.z; li.w += bl.w;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float g0 = fmaf(__uint_as_float(g[4 * k]), ln_rs, fmaf(nlm, qg[k].x, rg[k].x));
+                    const float g1 = fmaf(__uint_as_float(g[4 * k + 1]), ln_rs, fmaf(nlm, qg[k].y, rg[k].y));
+                    const float g2 = fmaf(__uint_as_float(g[4 * k + 2]), ln_rs, fmaf(nlm, qg[k].z, rg[k].z));
+                    const float g3 = fmaf(__uint_as_float(g[4 * k + 3]), ln_rs, fmaf(nlm, qg[k].w, rg[k].w));
+                    const float l0 = fmaf(__uint_as_float(l[4 * k]), ln_rs, fmaf(nlm, ql[k].x, rl[k].x));
+                    const float l1 = fmaf(__uint_as_float(l[4 * k + 1]), ln_rs, fmaf(nlm, ql[k].y, rl[k].y));
+                    const float l2 = fmaf(__uint_as_float(l[4 * k + 2]), ln_rs, fmaf(nlm, ql[k].z, rl[k].z));
+                    const float l3 = fmaf(__uint_as_float(l[4 * k + 3]), ln_rs, fmaf(nlm, ql[k].w, rl[k].w));
+                    y[4 * k] = gelu_erf(g0) * l0; y[4 * k + 1] = gelu_erf(g1) * l1;
+                    y[4 * k + 2] = gelu_erf(g2) * l2; y[4 * k + 3] = gelu_erf(g3) * l3;
                   }
-                  y[j] = gelu_erf(ga.x) * li.x; y[j + 1] = gelu_erf(ga.y) * li.y;
-                  y[j + 2] = gelu_erf(ga.z) * li.z; y[j + 3] = gelu_erf(ga.w) * li.w;
                 }
                 if (ep.stats_out != nullptr) {
 #pragma unroll
@@ -440,29 +444,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   __syncwarp();
                   if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
                 }
+                {
+                  float4 pp[8], qq[8], rr[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const int col = col0 + ac + j;
-                  float4 xv = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                  if (col < N) {
-                    if (ep.ln_mu != nullptr) {
-                      const float4 cs = lds128(cv_s + 4 * (ac + j));
-                      xv.x = ln_rs * (xv.x - ln_mu * cs.x); xv.y = ln_rs * (xv.y - ln_mu * cs.y);
-                      xv.z = ln_rs * (xv.z - ln_mu * cs.z); xv.w = ln_rs * (xv.w - ln_mu * cs.w);
-                    }
-                    if (ep.bias != nullptr) {
-                      const float4 bb = lds128(cv_s + 4 * (256 + ac + j));
-                      xv.x += bb.x; xv.y += bb.y; xv.z += bb.z; xv.w += bb.w;
-                    }
-                    if (ep.colscale != nullptr) {
-                      const float4 sc = lds128(cv_s + 4 * (512 + ac + j));
-                      xv.x *= sc.x; xv.y *= sc.y; xv.z *= sc.z; xv.w *= sc.w;
-                    }
-                    if constexpr (EPI == EPI_GELU_BF16) {
-                      xv.x = gelu_erf(xv.x); xv.y = gelu_erf(xv.y); xv.z = gelu_erf(xv.z); xv.w = gelu_erf(xv.w);
-                    }
+                  for (int k = 0; k < 8; ++k) {
+                    pp[k] = lds128(cv_s + 4 * (ac + 4 * k));
+                    qq[k] = lds128(cv_s + 4 * (256 + ac + 4 * k));
+                    rr[k] = lds128(cv_s + 4 * (512 + ac + 4 * k));
                   }
-                  y[j] = xv.x; y[j + 1] = xv.y; y[j + 2] = xv.z; y[j + 3] = xv.w;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    y[4 * k] = fmaf(__uint_as_float(v[4 * k]), ln_rs * pp[k].x, fmaf(nlm, qq[k].x, rr[k].x));
+                    y[4 * k + 1] = fmaf(__uint_as_float(v[4 * k + 1]), ln_rs * pp[k].y, fmaf(nlm, qq[k].y, rr[k].y));
+                    y[4 * k + 2] = fmaf(__uint_as_float(v[4 * k + 2]), ln_rs * pp[k].z, fmaf(nlm, qq[k].z, rr[k].z));
+                    y[4 * k + 3] = fmaf(__uint_as_float(v[4 * k + 3]), ln_rs * pp[k].w, fmaf(nlm, qq[k].w, rr[k].w));
+                  }
+                  if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
+                  }
                 }
               }
 #pragma unroll
@@ -852,7 +852,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 
 // generic 2D row-major tensor map for the epilogue's TMA loads / stores: box = box_cols x box_rows, 128B swizzle
 static int make_tmap_2d_out(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
-                            uint32_t box_cols, uint32_t box_rows) {
+                            uint32_t box_cols, uint32_t box_rows, bool swizzle64 = false) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) return OPB_ERR_CUDA;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0) return OPB_ERR_INVALID;
@@ -862,7 +862,8 @@ static int make_tmap_2d_out(CUtensorMap* out, const void* ptr, int elem_bytes, u
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? OPB_OK : OPB_ERR_CUDA;
 }
 
@@ -950,7 +951,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
       int rc = make_tmap_2d_out(&to, ep.out, eb, geo.M, n_out, ep.ldo, f32 ? 32 : 64, 32);
       if (rc != OPB_OK) return rc;
       if (ep.out_bf16 != nullptr) {
-        rc = make_tmap_2d_out(&to2, ep.out_bf16, 2, geo.M, geo.N, ep.ldo_bf16, 64, 32);
+        rc = make_tmap_2d_out(&to2, ep.out_bf16, 2, geo.M, geo.N, ep.ldo_bf16, 32, 32, true);
         if (rc != OPB_OK) return rc;
       } else {
         to2 = to;
