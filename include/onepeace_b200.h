@@ -124,6 +124,9 @@ typedef struct opb_gemm_args {
   float* stats_out;
   void* out_bf16; int64_t ldo_bf16;
   int32_t cta_group; int32_t reserved;
+  /* optional fp32 scratch of >= 256 * N * 4 bytes: lets OPB_EPI_RESID_F32 GEMMs schedule the partially filled last
+   * row of tiles as split-K pieces (removes a whole wave when (M / 256) * ceil(N / 256) just fits the SM pairs) */
+  void* workspace; int64_t workspace_bytes;
 } opb_gemm_args;
 int opb_gemm_bf16_ex(const opb_gemm_args* args, void* stream);
 

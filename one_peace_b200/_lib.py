@@ -67,7 +67,8 @@ class GemmArgs(ctypes.Structure):
                 ("out_group_valid", ctypes.c_int32), ("resid_period", ctypes.c_int32), ("resid_row_offset", ctypes.c_int32),
                 ("ln_mu", c_void_p), ("ln_rstd", c_void_p), ("ln_colsum", c_void_p),
                 ("stats_out", c_void_p), ("out_bf16", c_void_p), ("ldo_bf16", c_int64),
-                ("cta_group", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("cta_group", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("workspace", c_void_p), ("workspace_bytes", c_int64)]
 
 
 _lib = None

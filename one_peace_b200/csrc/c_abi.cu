@@ -73,6 +73,7 @@ int opb_gemm_bf16_ex(const opb_gemm_args* a, void* stream) {
   ep.out_group_valid = a->out_group_valid; ep.resid_period = a->resid_period; ep.resid_row_offset = a->resid_row_offset;
   ep.ln_mu = a->ln_mu; ep.ln_rstd = a->ln_rstd; ep.ln_colsum = a->ln_colsum;
   ep.stats_out = a->stats_out; ep.out_bf16 = a->out_bf16; ep.ldo_bf16 = a->ldo_bf16;
+  ep.workspace = a->workspace; ep.workspace_bytes = a->workspace_bytes;
   return opb::gemm_bf16(a->A, static_cast<int>(a->lda), a->B, static_cast<int>(a->ldb), a->M, a->N, a->K, a->epi, ep,
                         a->cta_group, static_cast<cudaStream_t>(stream));
 }

@@ -43,6 +43,9 @@ struct GemmEpilogue {
   float* stats_out = nullptr;        // [n_tiles, M, 2]
   void* out_bf16 = nullptr;
   long ldo_bf16 = 0;
+  // optional fp32 scratch (>= 256 * N * 4 bytes) enabling the M-tail split-K schedule of EPI_RESID_F32 GEMMs
+  void* workspace = nullptr;
+  long workspace_bytes = 0;
   // contrastive-head epilogues
   const float* scale_ptr = nullptr;  // device scalar: exp(clamp(logit_scale))
   const float* row_lse = nullptr;    // [M] log-sum-exp per row (EPI_SOFTMAX_GRAD)

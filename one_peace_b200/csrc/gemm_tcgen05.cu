@@ -84,6 +84,13 @@ struct GemmGeom {
   int a_group_c0;       // inner A coordinate offset per group
   int b_group_rows;     // B row offset per group (= N)
   int n_umma;           // UMMA N (256, or N rounded up to 16 when N < 256)
+  // M-tail split-K (EPI_RESID_F32 only): the partially filled last row of tiles is not scheduled as full tiles (which
+  // would cost a whole extra wave when (M / tile_m) * n_tiles is a multiple of the cluster count, e.g. 49 * 6 = 294 on
+  // 74 clusters) but as n_tiles * tail_pieces short work items, each covering kb_per_piece K-blocks, whose raw
+  // accumulators are added (fp32 atomics) into `tail_ws` [tile rows, N]; a small kernel then applies the epilogue.
+  int tail_pieces;      // 0 = off
+  int kb_per_piece;
+  float* tail_ws;
 };
 
 struct SmemBars {
@@ -116,10 +123,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const bool is_leader = (cta_rank == 0);
 
   const int tile_m_rows = kBlockM * CG;
-  const int num_m_tiles = (M + tile_m_rows - 1) / tile_m_rows;
+  const int num_m_tiles = (geo.tail_pieces > 0) ? M / tile_m_rows : (M + tile_m_rows - 1) / tile_m_rows;   // full tiles only when the tail is split
   const int num_n_tiles = (N + kBlockN - 1) / kBlockN;
   const int tiles_per_group = num_m_tiles * num_n_tiles;
-  const int num_tiles = tiles_per_group * geo.groups;
+  const int num_main = tiles_per_group * geo.groups;
+  const int num_tiles = num_main + num_n_tiles * geo.tail_pieces;
   const int num_k_blocks = geo.num_k_blocks;
   const int first_tile = blockIdx.x / CG;
   const int tile_stride = gridDim.x / CG;
@@ -159,15 +167,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       uint64_t* full_bar0 = bars->full;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        const int grp = tile / tiles_per_group;
-        const int tin = tile - grp * tiles_per_group;
-        const int m_blk = tin % num_m_tiles;
-        const int n_blk = tin / num_m_tiles;
+        int grp = 0, m_blk, n_blk, kb0 = 0, kb1 = num_k_blocks;
+        if (tile < num_main) {
+          grp = tile / tiles_per_group;
+          const int tin = tile - grp * tiles_per_group;
+          m_blk = tin % num_m_tiles;
+          n_blk = tin / num_m_tiles;
+        } else {            // M-tail piece (groups == 1, one tap)
+          const int t = tile - num_main;
+          n_blk = t / geo.tail_pieces;
+          m_blk = num_m_tiles;
+          kb0 = (t % geo.tail_pieces) * geo.kb_per_piece;
+          kb1 = min(num_k_blocks, kb0 + geo.kb_per_piece);
+        }
         const int a_row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
         const int b_row = grp * geo.b_group_rows + n_blk * kBlockN + static_cast<int>(cta_rank) * (geo.n_umma / 2);
         const int a_c0 = grp * geo.a_group_c0;
-        int kin = 0, tap = 0;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        int kin = kb0, tap = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -198,7 +215,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kBlockN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        int kb0 = 0, kb1 = num_k_blocks;
+        if (tile >= num_main) {
+          kb0 = ((tile - num_main) % geo.tail_pieces) * geo.kb_per_piece;
+          kb1 = min(num_k_blocks, kb0 + geo.kb_per_piece);
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -208,7 +230,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit<CG>(&bars->empty[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -221,12 +243,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (tile >= num_main) {
+        // ---- M-tail piece: add the raw partial accumulators of the valid rows into the fp32 workspace ----
+        const int n_blk_t = (tile - num_main) / geo.tail_pieces;
+        const int rl = static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;     // row inside the tail tile
+        const bool rv = rl < (M - num_m_tiles * tile_m_rows);
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr_t = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
+        float* wrow = geo.tail_ws + static_cast<long>(rl) * N + n_blk_t * kBlockN;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(taddr_t + c, v);
+          tmem_ld_wait();
+          if (c + 32 == kBlockN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+          }
+          if (rv) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n_blk_t * kBlockN + c + j < N)
+                atomicAdd(reinterpret_cast<float4*>(wrow + c + j),
+                          make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            }
+          }
+        }
+        continue;
+      }
       const int grp = tile / tiles_per_group;
       const int tin = tile - grp * tiles_per_group;
       const int m_blk = tin % num_m_tiles;
       const int n_blk = tin / num_m_tiles;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
       bool row_ok = row < M;
       if (ep.out_group > 0 && ep.out_group_valid > 0 && (row % ep.out_group) >= ep.out_group_valid) row_ok = false;
@@ -813,6 +866,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
+// Epilogue of the split-K M-tail rows: x = resid + gamma * (rstd * (acc - mu * colsum) + bias) from the summed raw
+// accumulators; writes the fp32 row, its bf16 copy and the per-256-column (sum, sum of squares) statistics records.
+// One CTA (256 threads) per tail row; thread t owns column t of every 256-column tile.
+__global__ void __launch_bounds__(256)
+gemm_tail_epilogue_kernel(const float* __restrict__ ws, const GemmEpilogue ep, int M, int N, int row0, int n_tiles) {
+  __shared__ float red[2][8];
+  const int row = row0 + blockIdx.x;
+  const float mu = ep.ln_mu ? ep.ln_mu[row] : 0.f;
+  const float rs = ep.ln_rstd ? ep.ln_rstd[row] : 1.f;
+  const float* w = ws + static_cast<long>(blockIdx.x) * N;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int col = t * kBlockN + threadIdx.x;
+    float x = 0.f;
+    if (col < N) {
+      x = w[col];
+      if (ep.ln_colsum) x = rs * (x - mu * ep.ln_colsum[col]);
+      if (ep.bias) x += ep.bias[col];
+      if (ep.gamma) x *= ep.gamma[col];
+      if (ep.resid) x += ep.resid[static_cast<long>(row) * ep.ldr + col];
+      reinterpret_cast<float*>(ep.out)[static_cast<long>(row) * ep.ldo + col] = x;
+      if (ep.out_bf16) reinterpret_cast<__nv_bfloat16*>(ep.out_bf16)[static_cast<long>(row) * ep.ldo_bf16 + col] = __float2bfloat16(x);
+    }
+    if (ep.stats_out != nullptr) {
+      float s1 = warp_sum(x), s2 = warp_sum(x * x);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+        *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(t) * M + row) * 2) = make_float2(a, b);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -907,7 +996,9 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     configured = true;
   }
   const int tile_m_rows = kBlockM * CG;
-  const int num_tiles = ((geo.M + tile_m_rows - 1) / tile_m_rows) * ((geo.N + kBlockN - 1) / kBlockN) * geo.groups;
+  const int n_tiles_n = (geo.N + kBlockN - 1) / kBlockN;
+  const int num_tiles = geo.tail_pieces > 0 ? (geo.M / tile_m_rows) * n_tiles_n + n_tiles_n * geo.tail_pieces
+                                            : ((geo.M + tile_m_rows - 1) / tile_m_rows) * n_tiles_n * geo.groups;
   int clusters = sm_count() / CG;
   if (clusters > num_tiles) clusters = num_tiles;
   cudaLaunchConfig_t cfg = {};
@@ -994,13 +1085,41 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   geo.a_group_c0 = 0;
   geo.b_group_rows = 0;
   geo.n_umma = (N >= kBlockN) ? kBlockN : ((N + 15) / 16) * 16;
+  geo.tail_pieces = 0;
+  geo.kb_per_piece = 0;
+  geo.tail_ws = nullptr;
   if (cta_group == 2 && geo.n_umma % 32 != 0) cta_group = 1;   // each CTA of a pair stages n_umma / 2 rows of B
+  // M-tail split-K: worth it when dropping the partial row of tiles saves a whole wave
+  const int tile_m = kBlockM * cta_group;
+  const int m_full = M / tile_m, tail_rows = M % tile_m;
+  const int n_t = (N + kBlockN - 1) / kBlockN;
+  static const char* env_tail = getenv("OPB_GEMM_TAIL_SPLITK");
+  if (epi == EPI_RESID_F32 && tail_rows > 0 && m_full > 0 && ep.workspace != nullptr &&
+      ep.workspace_bytes >= static_cast<long>(tile_m) * N * 4 && ep.out_group == 0 && ep.resid_period == 0 &&
+      !(env_tail != nullptr && env_tail[0] == '0')) {
+    const int clusters = sm_count() / cta_group;
+    const int waves_all = ((m_full + 1) * n_t + clusters - 1) / clusters;
+    const int waves_main = (m_full * n_t + clusters - 1) / clusters;
+    if (waves_main < waves_all) {
+      int pieces = clusters / n_t;
+      if (pieces > geo.num_k_blocks) pieces = geo.num_k_blocks;
+      if (pieces >= 2) {
+        geo.kb_per_piece = (geo.num_k_blocks + pieces - 1) / pieces;
+        geo.tail_pieces = (geo.num_k_blocks + geo.kb_per_piece - 1) / geo.kb_per_piece;
+        geo.tail_ws = reinterpret_cast<float*>(ep.workspace);
+        if (cudaMemsetAsync(ep.workspace, 0, static_cast<size_t>(tail_rows) * N * 4, stream) != cudaSuccess) return OPB_ERR_CUDA;
+      }
+    }
+  }
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_3d(&ta, A, K, 1, lda, M, lda, kBlockM);
   if (rc != OPB_OK) return rc;
   rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, kBlockN / cta_group);
   if (rc != OPB_OK) return rc;
-  return dispatch_gemm(cta_group, epi, ta, tb, ep, geo, stream);
+  rc = dispatch_gemm(cta_group, epi, ta, tb, ep, geo, stream);
+  if (rc != OPB_OK || geo.tail_pieces == 0) return rc;
+  gemm_tail_epilogue_kernel<<<tail_rows, 256, 0, stream>>>(geo.tail_ws, ep, M, N, m_full * tile_m, n_t);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
 int gemm_bf16_grouped_window(const void* X, const void* W, int rows, int groups, int c_pad, int taps, int n_per_group,
@@ -1016,6 +1135,9 @@ int gemm_bf16_grouped_window(const void* X, const void* W, int rows, int groups,
   geo.a_group_c0 = c_pad;
   geo.b_group_rows = n_per_group;
   geo.n_umma = ((n_per_group + 15) / 16) * 16;
+  geo.tail_pieces = 0;
+  geo.kb_per_piece = 0;
+  geo.tail_ws = nullptr;
   const long row_stride = static_cast<long>(groups) * c_pad;
   CUtensorMap ta, tb;
   // dims {groups*c_pad, taps, rows}: tap j of output row r reads input row r + j (tap stride == row stride)

@@ -105,7 +105,7 @@ def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None):
 
 
 def gemm_ln(a, w, epi, out, *, ln_mu=None, ln_rstd=None, ln_colsum=None, bias=None, colscale=None, gamma=None,
-            resid=None, stats_out=None, out_bf16=None, cta_group=0):
+            resid=None, stats_out=None, out_bf16=None, cta_group=0, workspace=None):
     """GEMM through `opb_gemm_bf16_ex`: fused LayerNorm of the A operand (ln_*), statistics / bf16 side outputs."""
     _need_cuda(a, w, out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(-1) == 1 and w.stride(1) == 1
@@ -122,6 +122,8 @@ def gemm_ln(a, w, epi, out, *, ln_mu=None, ln_rstd=None, ln_colsum=None, bias=No
     args.out_bf16 = _ptr(out_bf16) or None
     args.ldo_bf16 = out_bf16.stride(-2) if out_bf16 is not None else 0
     args.cta_group = cta_group
+    if workspace is not None:
+        args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     if PROFILE_HOOK is not None:
         PROFILE_HOOK("gemm_begin", 0.0, None)
     import ctypes as _ct

@@ -171,7 +171,7 @@ class TransformerEncoderLayer(nn.Module):
         # inner LN -> out_proj -> LayerScale + residual; emits x, xb and the statistics for LN2
         n_t = (d + 255) // 256
         K.gemm_ln(ws["o"], a["wo"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=a["co"],
-                  bias=a["do"], gamma=a["g1"], resid=x, stats_out=ws["part"], out_bf16=xb)
+                  bias=a["do"], gamma=a["g1"], resid=x, stats_out=ws["part"], out_bf16=xb, workspace=ws["tail"])
         K.ln_stats_finalize(ws["part"], n_t, M, d, self.final_layer_norm.eps, mu, rstd)
         # LN2 -> GeGLU; emits u and the statistics for the FFN LayerNorm
         K.gemm_ln(xb, f["w01"], K.EPI_GEGLU_BF16, ws["u"], ln_mu=mu, ln_rstd=rstd, ln_colsum=f["c01"], bias=f["d01"],
@@ -179,7 +179,7 @@ class TransformerEncoderLayer(nn.Module):
         K.ln_stats_finalize(ws["part"], 2 * ((2 * F_) // 256), M, F_, 1e-5, ws["mu2"], ws["rstd2"])   # 2 records / tile
         # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the statistics for the next layer's LN1
         K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=f["c2"],
-                  bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part"], out_bf16=xb)
+                  bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part"], out_bf16=xb, workspace=ws["tail"])
         K.ln_stats_finalize(ws["part"], n_t, M, d, eps, mu, rstd)
         return x
 
@@ -188,6 +188,7 @@ class TransformerEncoderLayer(nn.Module):
         parts = max(H, 2 * ((2 * F_) // 256), (d + 255) // 256)
         e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=device)
         return dict(qkv=e(M, 3 * d), o=e(M, d), u=e(M, F_), xb=e(M, d), part=e(parts * M * 2, dt=torch.float32),
+                    tail=e(256 * d, dt=torch.float32),
                     mu=e(M, dt=torch.float32), rstd=e(M, dt=torch.float32), mu2=e(M, dt=torch.float32),
                     rstd2=e(M, dt=torch.float32))
 

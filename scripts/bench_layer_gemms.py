@@ -20,14 +20,15 @@ u = torch.empty(M, F, dtype=torch.bfloat16, device=dev)
 x = torch.randn(M, d, device=dev, generator=g)
 xb2 = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
 part = torch.empty(96 * M * 2, device=dev)
+tail_ws = torch.empty(256 * d, device=dev)
 names = ["qkv", "out_proj", "geglu", "fc2"]
 flops = [2.0 * M * 3 * d * d, 2.0 * M * d * d, 2.0 * M * 2 * F * d, 2.0 * M * d * F]
 def layer(i, evs=None):
     wq, wo, w01, w2 = W[i % NL]
     calls = [lambda: K.gemm_ln(xb, wq, K.EPI_STORE_BF16, qkv, ln_mu=mu, ln_rstd=rs, ln_colsum=c3, bias=b3, colscale=s3),
-             lambda: K.gemm_ln(o, wo, K.EPI_RESID_F32, x, ln_mu=mu, ln_rstd=rs, ln_colsum=c1, bias=b1, gamma=g1, resid=x, stats_out=part, out_bf16=xb2),
+             lambda: K.gemm_ln(o, wo, K.EPI_RESID_F32, x, ln_mu=mu, ln_rstd=rs, ln_colsum=c1, bias=b1, gamma=g1, resid=x, stats_out=part, out_bf16=xb2, workspace=tail_ws),
              lambda: K.gemm_ln(xb, w01, K.EPI_GEGLU_BF16, u, ln_mu=mu, ln_rstd=rs, ln_colsum=c2, bias=b2, stats_out=part),
-             lambda: K.gemm_ln(u, w2, K.EPI_RESID_F32, x, ln_mu=mu, ln_rstd=rs, ln_colsum=c1, bias=b1, gamma=g1, resid=x, stats_out=part, out_bf16=xb2)]
+             lambda: K.gemm_ln(u, w2, K.EPI_RESID_F32, x, ln_mu=mu, ln_rstd=rs, ln_colsum=c1, bias=b1, gamma=g1, resid=x, stats_out=part, out_bf16=xb2, workspace=tail_ws)]
     for k, f in enumerate(calls):
         if evs is not None:
             e0 = torch.cuda.Event(enable_timing=True); e0.record()

@@ -305,3 +305,34 @@ def test_attention_tc(K, kind, B, S, H, use_pad):
     mu = torch.empty(B * S, device="cuda"); rstd = torch.empty(B * S, device="cuda")
     K.ln_stats_finalize(part, H, B * S, D, 1e-5, mu, rstd)
     torch.testing.assert_close(mu, out.float().mean(1), atol=2e-3, rtol=1e-2)
+
+
+def test_gemm_resid_m_tail_splitk(K):
+    """M = 49 * 256 + 64 rows, N = 1536: the 64-row tail is scheduled as split-K pieces (fp32 atomics into a scratch tile)
+    and finished by the tail-epilogue kernel; result, bf16 copy and LN statistics must match the plain path."""
+    M, d, N = 49 * 256 + 64, 512, 1536
+    g = torch.Generator(device="cuda").manual_seed(33)
+    a = (torch.randn(M, d, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, d, device="cuda", generator=g) * 0.05).bfloat16()
+    mu = torch.randn(M, device="cuda", generator=g) * 0.1
+    rs = torch.rand(M, device="cuda", generator=g) + 0.5
+    cs = torch.randn(N, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    outs = []
+    for use_ws in (False, True):
+        y = res.clone()
+        yb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        part = torch.zeros(6 * M * 2, device="cuda")
+        wsb = torch.empty(256 * N, device="cuda") if use_ws else None
+        K.gemm_ln(a, w, K.EPI_RESID_F32, y, ln_mu=mu, ln_rstd=rs, ln_colsum=cs, bias=bias, gamma=gamma, resid=y,
+                  stats_out=part, out_bf16=yb, workspace=wsb)
+        outs.append((y, yb, part))
+    want = res + gamma * (rs[:, None] * (a.float() @ w.float().t() - mu[:, None] * cs) + bias)
+    for y, yb, part in outs:
+        assert relerr(y, want) < 1e-4
+        assert torch.equal(yb, y.bfloat16())
+    assert relerr(outs[1][0], outs[0][0]) < 1e-5
+    p0 = outs[0][2].view(6, M, 2); p1 = outs[1][2].view(6, M, 2)
+    torch.testing.assert_close(p1, p0, atol=2e-2, rtol=1e-4)
