@@ -171,8 +171,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (tile < num_main) {
           grp = tile / tiles_per_group;
           const int tin = tile - grp * tiles_per_group;
-          m_blk = tin % num_m_tiles;
-          n_blk = tin / num_m_tiles;
+          m_blk = tin / num_n_tiles;      // n-fastest rasterisation: the tiles running concurrently share a few A row
+          n_blk = tin % num_n_tiles;      // panels (L2-resident) and sweep B; m-fastest re-streamed A from HBM per n-tile
         } else {            // M-tail piece (groups == 1, one tap)
           const int t = tile - num_main;
           n_blk = t / geo.tail_pieces;
@@ -278,8 +278,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       const int grp = tile / tiles_per_group;
       const int tin = tile - grp * tiles_per_group;
-      const int m_blk = tin % num_m_tiles;
-      const int n_blk = tin / num_m_tiles;
+      const int m_blk = tin / num_n_tiles;
+      const int n_blk = tin % num_n_tiles;
       const int row = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
       bool row_ok = row < M;
       if (ep.out_group > 0 && ep.out_group_valid > 0 && (row % ep.out_group) >= ep.out_group_valid) row_ok = false;
@@ -1094,7 +1094,9 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   const int m_full = M / tile_m, tail_rows = M % tile_m;
   const int n_t = (N + kBlockN - 1) / kBlockN;
   static const char* env_tail = getenv("OPB_GEMM_TAIL_SPLITK");
-  if (epi == EPI_RESID_F32 && tail_rows > 0 && m_full > 0 && ep.workspace != nullptr &&
+  // (measured: pays for K >= 3072 — fc2 232 -> 212 us; for K = 1536 the memset + atomics + tail kernel cost more than
+  //  the saved wave — out_proj 78 -> 89 us — so short-K GEMMs keep the plain schedule)
+  if (epi == EPI_RESID_F32 && tail_rows > 0 && m_full > 0 && ep.workspace != nullptr && geo.num_k_blocks >= 48 &&
       ep.workspace_bytes >= static_cast<long>(tile_m) * N * 4 && ep.out_group == 0 && ep.resid_period == 0 &&
       !(env_tail != nullptr && env_tail[0] == '0')) {
     const int clusters = sm_count() / cta_group;
