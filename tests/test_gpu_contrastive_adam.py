@@ -160,3 +160,18 @@ def test_adam_multi_tensor_groups_clip_and_master():
     n1 = opt.optimizer.grad_norm_and_scale(1.0, 0.0)[0].item()
     n2 = opt.optimizer.grad_norm_and_scale(1.0, 0.0)[0].item()
     assert n1 == n2
+
+
+def test_two_rank_contrastive_step_nccl():
+    """configs[3] at W = 2 on real GPUs: NCCL all-gather + InfoNCE fwd/bwd vs the oracle (skipped on a 1-GPU box;
+    profiles/r01_dist_contrastive_2gpu.log holds the round-1 run)."""
+    need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_contrastive.py"), "--b", "256",
+                        "--steps", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok=True" in r.stdout
