@@ -38,6 +38,7 @@ struct TcBars {
   uint64_t s[kTcMaxBlocks];      // S_kb accumulated
   uint64_t p[kTcMaxBlocks];      // P_kb written by the 4 row warps
   uint64_t pv[kTcMaxBlocks];     // P_kb V_kb accumulated (P buffer reusable; after the last: O complete)
+  uint64_t lut;                  // LUT + column codes landed (bulk copy)
   uint32_t tmem_base;
 };
 
@@ -76,6 +77,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int umma_m, int umma_
   return make_idesc_bf16(umma_m, umma_n) | (1u << 16);     // B operand MN-major
 }
 
+#ifdef OPB_ATTN_TIMING
+__device__ unsigned long long g_attn_t[8];
+__device__ unsigned int g_attn_n;
+#define OPB_T(i) do { if (threadIdx.x == 64) tt[i] = globaltimer_ns(); } while (0)
+#else
+#define OPB_T(i) do {} while (0)
+#endif
+
 template <bool HAS_PAD>
 __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, int lut_len,
@@ -100,11 +109,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
   const int D = H * kTcD;
   const int q0 = qt * kTcQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef OPB_ATTN_TIMING
+  unsigned long long tt[8];
+  OPB_T(0);
+#endif
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     mbar_init(&bars->qk, 1);
     mbar_init(&bars->v, 1);
+    mbar_init(&bars->lut, 1);
     for (int i = 0; i < kTcMaxBlocks; ++i) {
       mbar_init(&bars->s[i], 1);
       mbar_init(&bars->p[i], 4);
@@ -124,6 +138,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
   if (warp == 0) {
     if (lane == 0) {
       const int row0 = b * S;
+      // phase-A tables: lut [lut_len] | code_col [s4] (both padded to 16-byte multiples by the host)
+      const int s4 = (S + 3) & ~3;
+      mbar_arrive_expect_tx(&bars->lut, static_cast<uint32_t>(lut_len + s4) * 4);
+      bulk_load_1d(sP, lut + static_cast<long>(h) * lut_len, static_cast<uint32_t>(lut_len) * 4, &bars->lut);
+      bulk_load_1d(sP + static_cast<long>(lut_len) * 4, code_col, static_cast<uint32_t>(s4) * 4, &bars->lut);
       mbar_arrive_expect_tx(&bars->qk, (kTcQ + nkb * kTcK) * 128);
       tma_load_2d(&tm_qkv, &bars->qk, sQ, h * kTcD, row0 + q0);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->qk, sK + kb * kTcK * 128, D + h * kTcD, row0 + kb * kTcK);
@@ -168,17 +187,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     const bool row_valid = qrow < S;
     const bool warp_valid = (q0 + qw * 32) < S;              // warp-uniform
     const int tid4 = threadIdx.x - 64;                       // 0..127
-    // phase-A tables in the P buffer: lut [lut_len] | code_col [S] (| key_pad [S] bytes)
-    float* s_lut = reinterpret_cast<float*>(sP);
-    int* s_ccol = reinterpret_cast<int*>(sP) + lut_len;
-    uint8_t* s_pad = reinterpret_cast<uint8_t*>(s_ccol + S);
-    for (int i = tid4; i < lut_len; i += 128) s_lut[i] = lut[static_cast<long>(h) * lut_len + i];
-    for (int i = tid4; i < S; i += 128) s_ccol[i] = code_col[i];
+    // phase-A tables in the P buffer: lut [lut_len] | code_col [S padded to 4] (| key_pad [S] bytes)
+    const float* s_lut = reinterpret_cast<const float*>(sP);
+    const int* s_ccol = reinterpret_cast<const int*>(sP) + lut_len;
+    uint8_t* s_pad = sP + static_cast<long>(lut_len + ((S + 3) & ~3)) * 4;
     if constexpr (HAS_PAD) {
       for (int i = tid4; i < S; i += 128) s_pad[i] = key_pad[static_cast<long>(b) * S + i];
+      named_bar_sync(1, 128);
     }
     const int crow = code_row[row_valid ? qrow : 0];
-    named_bar_sync(1, 128);
+    mbar_wait(&bars->lut, 0);
+    OPB_T(1);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
 
     // ---- phase A: bias, mask, row max; biased scores written back to TMEM ----
@@ -186,22 +205,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     for (int kb = 0; kb < nkb; ++kb) {
       mbar_wait(&bars->s[kb], 0);
       tc_fence_after();
+      if (kb == 0) OPB_T(2);
       if (warp_valid) {
         const int kvalid = min(kTcK, S - kb * kTcK);
         for (int c = 0; c < kvalid; c += 32) {
           uint32_t v[32];
           __syncwarp();
           tmem_ld32(lane_base + kb * kTcK + c, v);
+          // gather the 32 biases of this row while the TMEM load is in flight: column codes (broadcast, vectorised),
+          // then 32 independent LUT reads
+          const int key0 = kb * kTcK + c;
+          int idx[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int4 cc = *reinterpret_cast<const int4*>(s_ccol + key0 + j);     // rows past S: padded / stale but in-bounds
+            idx[j] = crow - cc.x; idx[j + 1] = crow - cc.y; idx[j + 2] = crow - cc.z; idx[j + 3] = crow - cc.w;
+          }
+          float bia[32];
+          const bool full = key0 + 32 <= S;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bia[j] = (full || key0 + j < S) ? s_lut[idx[j]] : 0.f;
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int key = kb * kTcK + c + j;
-            float sc = -INFINITY;
-            if (key < S) {
-              sc = __uint_as_float(v[j]) + s_lut[crow - s_ccol[key]];
-              if constexpr (HAS_PAD) {
-                if (s_pad[key] != 0) sc = -INFINITY;
-              }
+            float sc = __uint_as_float(v[j]) + bia[j];
+            if (!full && key0 + j >= S) sc = -INFINITY;
+            if constexpr (HAS_PAD) {
+              if (key0 + j < S && s_pad[key0 + j] != 0) sc = -INFINITY;
             }
             m = fmaxf(m, sc);
             v[j] = __float_as_uint(sc);
@@ -215,6 +245,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     tc_fence_before();
     named_bar_sync(1, 128);            // every row thread is done with the LUT: the buffer becomes P
     tc_fence_after();
+    OPB_T(3);
 
     // ---- phase B: exp, row sum, P -> shared memory ----
     const float mb = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
@@ -254,8 +285,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     }
 
     // ---- epilogue: O / l -> bf16 rows ----
+    OPB_T(4);
     mbar_wait(&bars->pv[nkb - 1], 0);
     tc_fence_after();
+    OPB_T(5);
     if (warp_valid) {
       uint32_t o0[32], o1[32];
       __syncwarp();
@@ -290,6 +323,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     }
   }
 
+#ifdef OPB_ATTN_TIMING
+  if (threadIdx.x == 64) {
+    tt[6] = globaltimer_ns();
+    for (int i = 1; i <= 6; ++i) atomicAdd(&g_attn_t[i], tt[i] - tt[0]);
+    atomicAdd(&g_attn_n, 1u);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -297,6 +337,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     tmem_dealloc<1>(tmem_base, tmem_cols);
   }
 }
+
+#ifdef OPB_ATTN_TIMING
+extern "C" void opb_attn_timing_dump() {
+  unsigned long long t[8]; unsigned int n;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(t, g_attn_t, sizeof(t)); cudaMemcpyFromSymbol(&n, g_attn_n, sizeof(n));
+  printf("[attn timing] ctas=%u  avg ns since CTA start: tables_ready=%.0f S0_ready=%.0f phaseA_done=%.0f phaseB_done=%.0f O_ready=%.0f end=%.0f\n",
+         n, (double)t[1] / n, (double)t[2] / n, (double)t[3] / n, (double)t[4] / n, (double)t[5] / n, (double)t[6] / n);
+}
+#endif
 
 // lut[h][l] = table[idx[l]][h]
 __global__ void relpos_lut_kernel(const float* __restrict__ table, const int* __restrict__ idx, float* __restrict__ lut,
@@ -320,7 +370,9 @@ int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* 
   if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
   const int nkb = (S + kTcK - 1) / kTcK;
   if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
-  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>(S) * 4 + S;
+  if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col) & 15) != 0)
+    return OPB_ERR_INVALID;     // bulk-copied: 16-byte granularity (code_col must hold (S + 3) & ~3 entries)
+  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((S + 3) & ~3) * 4 + S + 128;
   if (table_bytes > kTcQ * kTcK * 2) return OPB_ERR_UNSUPPORTED;
   const int D = H * kTcD;
   CUtensorMap tm;

@@ -157,6 +157,13 @@ OPB_DEVICE void tma_load_3d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, 
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (size multiple of 16 B, both addresses 16-B aligned), completion on an mbarrier
+OPB_DEVICE void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // TMA store (shared -> global), bulk-group completion
 OPB_DEVICE void tma_store_2d(const CUtensorMap* m, const void* src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

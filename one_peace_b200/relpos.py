@@ -34,7 +34,7 @@ def build_lut_index(bucket, codes):
     Returns (lut_idx int32 [L], code_row int32 [S], code_col int32 [S]) or None if the scheme is not a code-difference one."""
     S = bucket.shape[0]
     if S == 1:
-        return np.array([bucket[0, 0]], dtype=np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32)
+        return np.array([bucket[0, 0]] * 4, dtype=np.int32), np.zeros(4, np.int32), np.zeros(4, np.int32)
     c = codes.astype(np.int64)
     maxc = int(c[1:].max())
     R1 = 2 * maxc + 1                 # CLS-row region  [R1, R1 + maxc]
@@ -55,7 +55,9 @@ def build_lut_index(bucket, codes):
     rebuilt = lut_idx[code_row[:, None] - code_col[None, :]]
     if not np.array_equal(rebuilt, bucket):
         return None
-    return lut_idx.astype(np.int32), code_row.astype(np.int32), code_col.astype(np.int32)
+    # the kernel bulk-copies the LUT row and the column codes: lengths padded to 16-byte multiples
+    pad4 = lambda a: np.concatenate([a, np.zeros((-a.size) % 4, dtype=a.dtype)])
+    return pad4(lut_idx.astype(np.int32)), pad4(code_row.astype(np.int32)), pad4(code_col.astype(np.int32))
 
 
 class LutCache:

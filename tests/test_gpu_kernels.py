@@ -288,7 +288,7 @@ def test_attention_tc(K, kind, B, S, H, use_pad):
     lut_idx, crow, ccol = (torch.from_numpy(a).cuda() for a in li)
     rp = K.RelPosBias(lut=K.relpos_lut_build(table, lut_idx), code_row=crow, code_col=ccol)
     dense = table[bucket.cuda()].permute(2, 0, 1)                     # (H,S,S)
-    assert torch.equal(rp.lut[:, (crow[:, None] - ccol[None, :]).long()], dense)
+    assert torch.equal(rp.lut[:, (crow[:S, None] - ccol[None, :S]).long()], dense)
     kp = None
     if use_pad:
         kp = torch.zeros(B, S, dtype=torch.uint8, device="cuda")

@@ -39,7 +39,7 @@ def assert_same_argmax(got_sim, want_sim, what, margin=2e-3):
 def dense_bias(rp, S):
     """(H,S,S) fp32 CPU view of a kernels.RelPosBias in either form."""
     if rp.lut is not None:
-        idx = (rp.code_row[:, None] - rp.code_col[None, :]).long()
+        idx = (rp.code_row[:S, None] - rp.code_col[None, :S]).long()
         return rp.lut[:, idx].cpu()
     return rp.dense[:, :, :S].cpu()
 

@@ -14,8 +14,8 @@ def test_token_buckets(bucket_size, S):
     r = relpos.build_lut_index(bucket, relpos.text_codes(S))
     assert r is not None
     lut_idx, crow, ccol = r
-    assert np.array_equal(lut_idx[crow[:, None] - ccol[None, :]], bucket)
-    assert lut_idx.size * 4 + S * 5 <= 32768
+    assert np.array_equal(lut_idx[crow[:S, None] - ccol[None, :S]], bucket)
+    assert lut_idx.size % 4 == 0 and ccol.size % 4 == 0 and lut_idx.size * 4 + S * 5 <= 32768
 
 
 @pytest.mark.parametrize("w", [14, 16])
@@ -25,7 +25,7 @@ def test_image_buckets(w):
     r = relpos.build_lut_index(bucket, relpos.image_codes(S, w))
     assert r is not None
     lut_idx, crow, ccol = r
-    assert np.array_equal(lut_idx[crow[:, None] - ccol[None, :]], bucket)
+    assert np.array_equal(lut_idx[crow[:S, None] - ccol[None, :S]], bucket)
     assert lut_idx.size * 4 + S * 5 <= 32768
 
 
