@@ -127,6 +127,9 @@ typedef struct opb_gemm_args {
   /* optional fp32 scratch of >= 256 * N * 4 bytes: lets OPB_EPI_RESID_F32 GEMMs schedule the partially filled last
    * row of tiles as split-K pieces (removes a whole wave when (M / 256) * ceil(N / 256) just fits the SM pairs) */
   void* workspace; int64_t workspace_bytes;
+  /* alternative to ln_mu / ln_rstd: partial (sum, sum of squares) records [ln_parts, M, 2] of the A rows written by the
+   * producing kernel; each epilogue thread reduces its row's records itself (no opb_ln_stats_finalize launch) */
+  const float* ln_partial; int32_t ln_parts; int32_t ln_dim; float ln_eps; int32_t reserved2;
 } opb_gemm_args;
 int opb_gemm_bf16_ex(const opb_gemm_args* args, void* stream);
 

@@ -68,7 +68,9 @@ class GemmArgs(ctypes.Structure):
                 ("ln_mu", c_void_p), ("ln_rstd", c_void_p), ("ln_colsum", c_void_p),
                 ("stats_out", c_void_p), ("out_bf16", c_void_p), ("ldo_bf16", c_int64),
                 ("cta_group", ctypes.c_int32), ("reserved", ctypes.c_int32),
-                ("workspace", c_void_p), ("workspace_bytes", c_int64)]
+                ("workspace", c_void_p), ("workspace_bytes", c_int64),
+                ("ln_partial", c_void_p), ("ln_parts", ctypes.c_int32), ("ln_dim", ctypes.c_int32), ("ln_eps", c_float),
+                ("reserved2", ctypes.c_int32)]
 
 
 _lib = None

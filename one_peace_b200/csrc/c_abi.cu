@@ -64,8 +64,10 @@ int opb_relpos_lut_build(const float* table, const int32_t* idx, float* lut, int
 
 int opb_gemm_bf16_ex(const opb_gemm_args* a, void* stream) {
   if (a == nullptr || a->A == nullptr || a->B == nullptr || a->out == nullptr) return OPB_ERR_INVALID;
-  if ((a->ln_mu == nullptr) != (a->ln_rstd == nullptr) || (a->ln_mu == nullptr) != (a->ln_colsum == nullptr))
-    return OPB_ERR_INVALID;
+  if ((a->ln_mu == nullptr) != (a->ln_rstd == nullptr)) return OPB_ERR_INVALID;
+  if (a->ln_mu != nullptr && a->ln_partial != nullptr) return OPB_ERR_INVALID;
+  if ((a->ln_colsum != nullptr) != (a->ln_mu != nullptr || a->ln_partial != nullptr)) return OPB_ERR_INVALID;
+  if (a->ln_partial != nullptr && (a->ln_parts <= 0 || a->ln_dim <= 0)) return OPB_ERR_INVALID;
   opb::GemmEpilogue ep;
   ep.out = a->out; ep.ldo = a->ldo;
   ep.bias = a->bias; ep.colscale = a->colscale; ep.gamma = a->gamma; ep.resid = a->resid; ep.ldr = a->ldr;
@@ -74,6 +76,7 @@ int opb_gemm_bf16_ex(const opb_gemm_args* a, void* stream) {
   ep.ln_mu = a->ln_mu; ep.ln_rstd = a->ln_rstd; ep.ln_colsum = a->ln_colsum;
   ep.stats_out = a->stats_out; ep.out_bf16 = a->out_bf16; ep.ldo_bf16 = a->ldo_bf16;
   ep.workspace = a->workspace; ep.workspace_bytes = a->workspace_bytes;
+  ep.ln_partial = a->ln_partial; ep.ln_parts = a->ln_parts; ep.ln_dim = a->ln_dim; ep.ln_eps = a->ln_eps;
   return opb::gemm_bf16(a->A, static_cast<int>(a->lda), a->B, static_cast<int>(a->ldb), a->M, a->N, a->K, a->epi, ep,
                         a->cta_group, static_cast<cudaStream_t>(stream));
 }

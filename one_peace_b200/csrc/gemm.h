@@ -38,6 +38,13 @@ struct GemmEpilogue {
   const float* ln_mu = nullptr;      // [M]
   const float* ln_rstd = nullptr;    // [M]
   const float* ln_colsum = nullptr;  // [N]
+  // alternative to ln_mu / ln_rstd: the producer's partial (sum, sum of squares) records [ln_parts, M, 2]; each
+  // epilogue thread reduces the records of its row itself (index order -> deterministic), which removes the separate
+  // ln_stats_finalize launch for small part counts (6 for the residual GEMMs, 24 for attention)
+  const float* ln_partial = nullptr;
+  int ln_parts = 0;
+  int ln_dim = 0;
+  float ln_eps = 1e-5f;
   // side outputs for the NEXT LayerNorm (EPI_RESID_F32 / EPI_GEGLU_BF16): per (n-tile, row) partial (sum, sum of
   // squares) of the stored values, and (EPI_RESID_F32) a bf16 copy of the output that feeds the next GEMM
   float* stats_out = nullptr;        // [n_tiles, M, 2]

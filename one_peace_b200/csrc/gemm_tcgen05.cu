@@ -102,6 +102,24 @@ struct SmemBars {
   uint32_t tmem_base;
 };
 
+// row statistics for the fused-LayerNorm epilogue: either precomputed (mu, rstd) or reduced here from partial records
+OPB_DEVICE void load_ln_stats(const GemmEpilogue& ep, int row, int M, float& mu, float& rs) {
+  mu = 0.f; rs = 1.f;
+  const int rc = row < M ? row : M - 1;
+  if (ep.ln_partial != nullptr) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = 0; p < ep.ln_parts; ++p) {
+      const float2 v = *reinterpret_cast<const float2*>(ep.ln_partial + (static_cast<long>(p) * M + rc) * 2);
+      s1 += v.x; s2 += v.y;
+    }
+    mu = s1 / ep.ln_dim;
+    rs = rsqrtf(fmaxf(s2 / ep.ln_dim - mu * mu, 0.f) + ep.ln_eps);
+  } else if (ep.ln_mu != nullptr) {
+    mu = ep.ln_mu[rc];
+    rs = ep.ln_rstd[rc];
+  }
+}
+
 template <int CG, int EPI, bool TMAEPI>
 __global__ void __launch_bounds__(EpiCfg<EPI, TMAEPI>::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -296,12 +314,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + ew * ECfg::kWarpBytes;
         const int row0 = m_blk * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + q * 32;   // warp's first row
         const int col0 = n_blk * kBlockN;
-        float ln_mu = 0.f, ln_rs = 1.f;
-        if (ep.ln_mu != nullptr) {
-          const int rc = row < M ? row : M - 1;
-          ln_mu = ep.ln_mu[rc];
-          ln_rs = ep.ln_rstd[rc];
-        }
+        float ln_mu, ln_rs;
+        load_ln_stats(ep, row, M, ln_mu, ln_rs);
         float st_sum = 0.f, st_sq = 0.f;
         // Per-column epilogue coefficients of this tile -> this warp's smem copy ([3][256] fp32), in AFFINE form so the
         // inner loops are branch-free and every load is unconditional (the compiler can batch them):
@@ -555,12 +569,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (ep.out_group > 0) out_row = static_cast<long>(row / ep.out_group) * ep.out_group_stride + (row % ep.out_group) + ep.out_row_offset;
       long res_row = out_row;
       if (ep.resid_period > 0) res_row = (row % ep.resid_period) + ep.resid_row_offset;
-      float ln_mu = 0.f, ln_rs = 1.f;
-      if (ep.ln_mu != nullptr) {
-        const int rc = row < M ? row : M - 1;
-        ln_mu = ep.ln_mu[rc];
-        ln_rs = ep.ln_rstd[rc];
-      }
+      float ln_mu, ln_rs;
+      load_ln_stats(ep, row, M, ln_mu, ln_rs);
+      const bool has_ln = ep.ln_colsum != nullptr;
       float st_sum = 0.f, st_sq = 0.f;   // partial statistics of the stored values (next LayerNorm)
       // per-column epilogue vectors of this tile in shared memory (see the TMA path); grouped GEMMs index them by
       // global column and keep reading global memory
@@ -615,7 +626,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { ga[e] = __uint_as_float(g[j + e]); li[e] = __uint_as_float(l[j + e]); }
                 const int pc = n_blk * kBlockN + c + j;          // packed (interleaved) weight row of the gate half
-                if (ep.ln_mu != nullptr) {
+                if (has_ln) {
                   float cg[8], cl[8];
                   if (use_cv) {
                     *reinterpret_cast<float4*>(cg) = lds128(cv_s + 4 * (c + j));
@@ -779,7 +790,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j + e]);
             const int tcc = c + j;   // column inside the tile
-            if (ep.ln_mu != nullptr) {
+            if (has_ln) {
               const float4 c0 = use_cv ? lds128(cv_s + 4 * tcc) : *reinterpret_cast<const float4*>(ep.ln_colsum + col);
               const float4 c1 = use_cv ? lds128(cv_s + 4 * (tcc + 4)) : *reinterpret_cast<const float4*>(ep.ln_colsum + col + 4);
               x[0] = ln_rs * (x[0] - ln_mu * c0.x); x[1] = ln_rs * (x[1] - ln_mu * c0.y);
@@ -873,8 +884,8 @@ __global__ void __launch_bounds__(256)
 gemm_tail_epilogue_kernel(const float* __restrict__ ws, const GemmEpilogue ep, int M, int N, int row0, int n_tiles) {
   __shared__ float red[2][8];
   const int row = row0 + blockIdx.x;
-  const float mu = ep.ln_mu ? ep.ln_mu[row] : 0.f;
-  const float rs = ep.ln_rstd ? ep.ln_rstd[row] : 1.f;
+  float mu, rs;
+  load_ln_stats(ep, row, M, mu, rs);
   const float* w = ws + static_cast<long>(blockIdx.x) * N;
   for (int t = 0; t < n_tiles; ++t) {
     const int col = t * kBlockN + threadIdx.x;

@@ -105,7 +105,7 @@ def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None):
 
 
 def gemm_ln(a, w, epi, out, *, ln_mu=None, ln_rstd=None, ln_colsum=None, bias=None, colscale=None, gamma=None,
-            resid=None, stats_out=None, out_bf16=None, cta_group=0, workspace=None):
+            resid=None, stats_out=None, out_bf16=None, cta_group=0, workspace=None, ln_partial=None):
     """GEMM through `opb_gemm_bf16_ex`: fused LayerNorm of the A operand (ln_*), statistics / bf16 side outputs."""
     _need_cuda(a, w, out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(-1) == 1 and w.stride(1) == 1
@@ -122,6 +122,8 @@ def gemm_ln(a, w, epi, out, *, ln_mu=None, ln_rstd=None, ln_colsum=None, bias=No
     args.out_bf16 = _ptr(out_bf16) or None
     args.ldo_bf16 = out_bf16.stride(-2) if out_bf16 is not None else 0
     args.cta_group = cta_group
+    if ln_partial is not None:      # (records tensor, parts, dim, eps)
+        args.ln_partial, args.ln_parts, args.ln_dim, args.ln_eps = ln_partial[0].data_ptr(), ln_partial[1], ln_partial[2], ln_partial[3]
     if workspace is not None:
         args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     if PROFILE_HOOK is not None:

@@ -55,12 +55,13 @@ class TransformerEncoder(FairseqEncoder):
         if fused:
             ws = TransformerEncoderLayer.fused_workspace(B * S, d, self.cfg.ffn_embed_dim, self.num_attention_heads, x.device)
             K.row_stats_cast(rows, ws["xb"], ws["mu"], ws["rstd"], eps=self.layers[0].self_attn_layer_norm.eps)
+            ln1 = dict(ln_mu=ws["mu"], ln_rstd=ws["rstd"])
         for idx, layer in enumerate(self.layers):
             bias = None
             if bias_list:
                 bias = bias_list[0] if len(bias_list) == 1 else bias_list[idx]
             if fused:
-                layer.forward_rows_fused(rows, ws["xb"], ws["mu"], ws["rstd"], ws, bias, key_pad, B, S, encoder_type)
+                ln1 = layer.forward_rows_fused(rows, ws["xb"], ln1, ws, bias, key_pad, B, S, encoder_type)
             else:
                 layer.forward_rows(rows, bias, key_pad, B, S, encoder_type)
         return x, pad

@@ -152,42 +152,41 @@ class TransformerEncoderLayer(nn.Module):
                         g2=f32(self.gamma_2) if self.gamma_2 is not None else None)
         return cache.get(ps, build)
 
-    def forward_rows_fused(self, x, xb, mu, rstd, ws, bias, key_pad, B, S, modality):
-        """x fp32 [M,d] residual (in place), xb bf16 [M,d] copy of x, (mu, rstd) [M] row statistics of x.
-        On return x / xb / mu / rstd describe the layer output (ready for the next layer).  `ws` = workspace dict."""
+    def forward_rows_fused(self, x, xb, ln1, ws, bias, key_pad, B, S, modality):
+        """x fp32 [M,d] residual (in place), xb bf16 [M,d] copy of x, ln1 = LayerNorm-1 statistics of x: either
+        dict(ln_mu=, ln_rstd=) (first layer) or dict(ln_partial=(records, parts, dim, eps)) (from the previous fc2).
+        Returns the same for the layer output.  `ws` = workspace dict."""
         if self.training and (self.dropout_prob > 0 or self.drop_path_prob > 0):
             raise NotImplementedError("training-time dropout / drop-path: backward pass is not built yet")
         d, F_, H = self.embed_dim, self.ffn_embed_dim, self.self_attn.num_heads
         M = B * S
         a = self._fused_attn_pack()
         f = self._fused_ffn_pack(modality)
-        eps = self.self_attn_layer_norm.eps
-        # LN1 -> QKV (+bias, q scale)
-        K.gemm_ln(xb, a["wqkv"], K.EPI_STORE_BF16, ws["qkv"], ln_mu=mu, ln_rstd=rstd, ln_colsum=a["cqkv"],
-                  bias=a["dqkv"], colscale=a["qscale"])
-        # attention (+ per-head partial statistics of its output rows)
-        self.self_attn.run_attention(ws["qkv"], bias, key_pad, B, S, out=ws["o"], ln_stats=ws["part"])
-        K.ln_stats_finalize(ws["part"], H, M, d, self.self_attn.ln.eps, ws["mu2"], ws["rstd2"])
-        # inner LN -> out_proj -> LayerScale + residual; emits x, xb and the statistics for LN2
         n_t = (d + 255) // 256
-        K.gemm_ln(ws["o"], a["wo"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=a["co"],
-                  bias=a["do"], gamma=a["g1"], resid=x, stats_out=ws["part"], out_bf16=xb, workspace=ws["tail"])
-        K.ln_stats_finalize(ws["part"], n_t, M, d, self.final_layer_norm.eps, mu, rstd)
-        # LN2 -> GeGLU; emits u and the statistics for the FFN LayerNorm
-        K.gemm_ln(xb, f["w01"], K.EPI_GEGLU_BF16, ws["u"], ln_mu=mu, ln_rstd=rstd, ln_colsum=f["c01"], bias=f["d01"],
-                  stats_out=ws["part"])
-        K.ln_stats_finalize(ws["part"], 2 * ((2 * F_) // 256), M, F_, 1e-5, ws["mu2"], ws["rstd2"])   # 2 records / tile
-        # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the statistics for the next layer's LN1
+        # LN1 -> QKV (+bias, q scale)
+        K.gemm_ln(xb, a["wqkv"], K.EPI_STORE_BF16, ws["qkv"], ln_colsum=a["cqkv"], bias=a["dqkv"], colscale=a["qscale"], **ln1)
+        # attention; emits per-head partial statistics of its output rows (inner LN)
+        self.self_attn.run_attention(ws["qkv"], bias, key_pad, B, S, out=ws["o"], ln_stats=ws["part_a"])
+        # inner LN -> out_proj -> LayerScale + residual; emits x, xb and the partial statistics for LN2
+        K.gemm_ln(ws["o"], a["wo"], K.EPI_RESID_F32, x, ln_partial=(ws["part_a"], H, d, self.self_attn.ln.eps),
+                  ln_colsum=a["co"], bias=a["do"], gamma=a["g1"], resid=x, stats_out=ws["part_b"], out_bf16=xb,
+                  workspace=ws["tail"])
+        # LN2 -> GeGLU; emits u and the partial statistics for the FFN LayerNorm (96 records / row: reduced by a kernel)
+        K.gemm_ln(xb, f["w01"], K.EPI_GEGLU_BF16, ws["u"], ln_partial=(ws["part_b"], n_t, d, self.final_layer_norm.eps),
+                  ln_colsum=f["c01"], bias=f["d01"], stats_out=ws["part_c"])
+        K.ln_stats_finalize(ws["part_c"], 2 * ((2 * F_) // 256), M, F_, 1e-5, ws["mu2"], ws["rstd2"])   # 2 records / tile
+        # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the partial statistics for the next layer's LN1
         K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=f["c2"],
-                  bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part"], out_bf16=xb, workspace=ws["tail"])
-        K.ln_stats_finalize(ws["part"], n_t, M, d, eps, mu, rstd)
-        return x
+                  bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part_d"], out_bf16=xb, workspace=ws["tail"])
+        return dict(ln_partial=(ws["part_d"], n_t, d, self.self_attn_layer_norm.eps))
 
     @staticmethod
     def fused_workspace(M, d, F_, H, device):
-        parts = max(H, 2 * ((2 * F_) // 256), (d + 255) // 256)
+        n_t = (d + 255) // 256
         e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=device)
-        return dict(qkv=e(M, 3 * d), o=e(M, d), u=e(M, F_), xb=e(M, d), part=e(parts * M * 2, dt=torch.float32),
+        f32 = torch.float32
+        return dict(qkv=e(M, 3 * d), o=e(M, d), u=e(M, F_), xb=e(M, d), part_a=e(H * M * 2, dt=f32),
+                    part_b=e(n_t * M * 2, dt=f32), part_c=e(2 * ((2 * F_) // 256) * M * 2, dt=f32), part_d=e(n_t * M * 2, dt=f32),
                     tail=e(256 * d, dt=torch.float32),
                     mu=e(M, dt=torch.float32), rstd=e(M, dt=torch.float32), mu2=e(M, dt=torch.float32),
                     rstd2=e(M, dt=torch.float32))

@@ -247,6 +247,20 @@ def test_gemm_fused_layernorm_and_stats(K, cg):
     K.ln_stats_finalize(part, (N + 255) // 256, M, N, 1e-5, m2, r2)
     torch.testing.assert_close(m2, y.mean(1), atol=1e-4, rtol=1e-4)
     torch.testing.assert_close(r2, (y.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-4, rtol=1e-3)
+    # consumer reduces the partial records itself (no finalize launch): LN(y) W2^T via ln_partial
+    W2 = torch.randn(640, N, device="cuda", generator=g) * 0.05
+    lw2 = 1 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    lb2 = 0.1 * torch.randn(N, device="cuda", generator=g)
+    b2 = torch.randn(640, device="cuda", generator=g)
+    wg2, cs2, dd2 = L._fold(W2, lw2, lb2, b2)
+    want2 = torch.nn.functional.linear(torch.nn.functional.layer_norm(yb.float(), (N,), lw2, lb2), W2, b2)
+    for epi, dt in ((K.EPI_STORE_F32, torch.float32), (K.EPI_STORE_BF16, torch.bfloat16)):
+        o_arr = torch.empty(M, 640, dtype=dt, device="cuda")
+        o_par = torch.empty(M, 640, dtype=dt, device="cuda")
+        K.gemm_ln(yb, wg2, epi, o_arr, ln_mu=m2, ln_rstd=r2, ln_colsum=cs2, bias=dd2, cta_group=cg)
+        K.gemm_ln(yb, wg2, epi, o_par, ln_partial=(part, (N + 255) // 256, N, 1e-5), ln_colsum=cs2, bias=dd2, cta_group=cg)
+        assert relerr(o_par, want2) < 1e-2
+        assert relerr(o_par, o_arr) < 1e-5
 
 
 def test_attention_ln_stats(K):
