@@ -258,6 +258,65 @@ int opb_adam_multi_step(const void* tensors, const int32_t* chunk_tensor, const 
 int opb_grad_norm_clip(const void* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
                        float* partial, float multiply_factor, float max_norm, float* out2, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward pass of the encoder layer (autograd of models/transformer/transformer_layer.py:165-228 and
+ * multihead_attention.py:103-126; the reference relies on torch autograd, these are the hand-written adjoints).
+ * Column-reduction entry points take `ws`: fp32 scratch of opb_bwd_ws_floats(dim) floats.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t opb_bwd_ws_floats(int dim);
+
+/* LayerNorm backward (components.py:23-26): y = LN(x) * gamma + beta, or y = gelu(LN(x) * gamma + beta) when gelu != 0
+ * (adapter/image.py:66-75).  dx = assign or (accumulate != 0, fp32 only) add;  dgamma / dbeta fp32 [dim] or NULL.
+ * dy_merge_w > 0: dy is the gradient of the NEXT conv's 2x2 pixel-merged operand [rows / 4, 4 * dim] (the forward's
+ * opb_layernorm merge_grid_w scatter) and is gathered accordingly.
+ * Dtype tags OPB_F32 / OPB_BF16; dim % 4 == 0, dim <= 6144. */
+int opb_layernorm_bwd(const void* x, int x_dtype, int64_t ldx, const void* dy, int dy_dtype, int64_t ld_dy,
+                      const float* gamma, const float* beta, void* dx, int dx_dtype, int64_t ld_dx, int accumulate,
+                      int rows, int dim, float eps, int gelu, int dy_merge_w, float* ws, float* dgamma, float* dbeta,
+                      void* stream);
+
+/* GeGLU on the un-fused projection gl = [g | l] bf16 [rows, 2F] (transformer_layer.py:54-67): u = gelu_erf(g) * l and
+ * its adjoint dgl = [du * l * gelu'(g) | du * gelu(g)]. */
+int opb_geglu_fwd(const void* gl, void* u, int64_t rows, int F, void* stream);
+int opb_geglu_bwd(const void* gl, const void* du, void* dgl, int64_t rows, int F, void* stream);
+
+/* LayerScale + drop-path residual (transformer_layer.py:70-88): out = x + row_scale[r] * gamma[n] * o  (o bf16; gamma /
+ * row_scale may be NULL = 1) and its adjoint: d_o = bf16(row_scale * gamma * dx), dgamma = sum_r row_scale * dx * o,
+ * dbias = sum_r d_o (the bias gradient of the Linear that produced o). */
+int opb_scale_resid_fwd(const float* x, const void* o, const float* gamma, const float* row_scale, float* out,
+                        int64_t rows, int n, void* stream);
+int opb_scale_resid_bwd(const float* dx, const void* o, const float* gamma, const float* row_scale, void* d_o, float* ws,
+                        float* dgamma, float* dbias, int rows, int n, int in_period, int in_valid, int in_shift,
+                        void* stream);   /* in_valid > 0: output row r reads dx row (r / in_valid) * in_period + in_shift + r % in_valid */
+
+/* out[n] = sum over rows of y bf16 [rows, n] (bias gradients). */
+int opb_colsum_bf16(const void* y, int64_t ldy, float* ws, float* out, int rows, int n, void* stream);
+
+/* Attention backward (multihead_attention.py:107-115): from qkv (q scaled), the forward output `out`, its gradient
+ * `d_out` and the forward's log-sum-exp, writes dqkv bf16 [B*S, 3*H*64] (dq already multiplied by q_scale, i.e. the
+ * gradient of the un-scaled projection) and adds the relative-position-bias gradient into dbias fp32 [H,S,s_pad]
+ * (or NULL).  delta: fp32 scratch [B,H,S]. */
+int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
+                      const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
+                      float q_scale, void* stream);
+
+/* out[c] (+)= sum_b in[b * ld + c]: gradients of batch-broadcast parameters (cls_embedding, pos_embed). */
+int opb_batch_sum_f32(const float* in, int64_t ld, float* out, int B, int64_t n, int accumulate, void* stream);
+
+/* Adjoint of opb_l2_normalize_rows (F.normalize, one_peace_retrieval.py:116): dx = (dy - y (y.dy)) / |x|; fp32 and / or
+ * bf16 output (the bf16 copy feeds the projection's dW / dX GEMMs). */
+int opb_l2_normalize_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, float* dx, void* dx_bf16, int rows,
+                         int D, void* stream);
+
+/* Adjoint of opb_text_embed (adapter/text.py:125-129,144-146): scatter-adds dx [B,T+1,D] into the fp32 gradients of
+ * embed_tokens.weight [V,D], embed_positions.weight [>=T+1,D] and cls_embedding [D]; padded tokens get none. */
+int opb_text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T,
+                       int D, int pad_idx, void* stream);
+
+/* dtable[bucket[i,j], h] += dbias[h,i,j]  (adjoint of opb_relpos_bias_build; adapter/text.py:84-91, image.py:164-171) */
+int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H,
+                        int64_t ld_bucket, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

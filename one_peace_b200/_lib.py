@@ -57,6 +57,26 @@ SIGNATURES = {
     "opb_grad_norm_clip": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p]),
 }
 
+SIGNATURES.update({
+    "opb_bwd_ws_floats": (c_int64, [c_int]),
+    "opb_layernorm_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int64, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "opb_batch_sum_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "opb_l2_normalize_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "opb_text_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "opb_geglu_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "opb_geglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "opb_scale_resid_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "opb_scale_resid_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                    c_int, c_int, c_int, c_int, c_void_p]),
+    "opb_colsum_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "opb_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "opb_relpos_bias_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+})
+
+
 class GemmArgs(ctypes.Structure):
     """Mirror of `opb_gemm_args` (include/onepeace_b200.h)."""
     _fields_ = [("A", c_void_p), ("lda", c_int64), ("B", c_void_p), ("ldb", c_int64),

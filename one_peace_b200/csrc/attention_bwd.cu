@@ -1,0 +1,382 @@
+// Backward of the fused self-attention (reference: autograd through multihead_attention.py:103-115):
+//     S = q k^T + bias (+ -inf on padded keys),  P = softmax(S),  O = P v
+//     dV = P^T dO,   dP = dO V^T,   dS = P o (dP - delta),  delta_i = sum_d dO_id O_id = sum_j P_ij dP_ij
+//     dQ = dS K,     dK = dS^T Q,   dbias[h] += sum_b dS[b,h]
+// P is recomputed from the saved log-sum-exp of the forward kernel (attention.cu writes it), never stored.
+// Two kernels with the forward kernel's tiling (64-row tiles, 4 warps x 16 rows, mma.sync.m16n8k16 bf16, fp32
+// accumulate; attention is 1.6 % of the layer FLOPs):
+//   * attention_bwd_dq_kernel: CTA = (batch, head, 64 queries), streams key blocks; dQ in registers; the
+//     relative-position-bias gradient is added straight into the batch-shared (H,S,S_pad) fp32 table (atomics).
+//   * attention_bwd_dkv_kernel: CTA = (batch, head, 64 keys), streams query blocks with S^T = K Q^T so that P^T / dS^T
+//     are already the A-operand fragments of dV += P^T dO and dK += dS^T Q.
+// q in `qkv` is the SCALED query (the QKV GEMM epilogue applies head_dim^-0.5); dQ is multiplied by the same factor so
+// `dqkv` is the gradient of the un-scaled projection output, ready for the dW / dX GEMMs.
+#include "common.cuh"
+#include "ops.h"
+
+namespace opb {
+
+namespace {
+
+constexpr int kHd = 64;
+constexpr int kTile = 64;
+constexpr int kRowPad = 72;
+
+OPB_DEVICE void cp_async16(void* dst, const void* src, bool valid) {
+  uint32_t d = smem_u32(dst);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+OPB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+OPB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+OPB_DEVICE void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+OPB_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+OPB_DEVICE void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+typedef __nv_bfloat16 Tile[kTile][kRowPad];
+
+// 64 x 64 bf16 tile: rows row0.. of a matrix with `pitch` elements per row, zero-filled past `rows_total`
+OPB_DEVICE void load_tile(Tile& dst, const __nv_bfloat16* base, long pitch, int row0, int rows_total, int tid) {
+  for (int i = tid; i < kTile * 8; i += 128) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    const bool ok = (row0 + r) < rows_total;
+    cp_async16(&dst[r][c], base + static_cast<long>(ok ? row0 + r : 0) * pitch + c, ok);
+  }
+}
+
+// C[16 x 64] (+)= A[16 x 64(d)] * B^T where B rows (64 of them) are [n][d] in smem (the "K" pattern of the forward)
+OPB_DEVICE void mma_a_bt(float (&c)[8][4], const uint32_t (&af)[4][4], const Tile& bt, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t f0[4], f1[4];
+    const int r = nt * 8 + (lane & 7);
+    const int cc = (lane >> 3) * 8;
+    ldmatrix_x4(f0, &bt[r][cc]);
+    ldmatrix_x4(f1, &bt[r][cc + 32]);
+    mma16816(c[nt], af[0], f0[0], f0[1]);
+    mma16816(c[nt], af[1], f0[2], f0[3]);
+    mma16816(c[nt], af[2], f1[0], f1[1]);
+    mma16816(c[nt], af[3], f1[2], f1[3]);
+  }
+}
+
+// C[16 x 64(d)] += P[16 x 64(k)] * B where B is [k][d] in smem (the "V" pattern), P given as packed bf16 fragments
+OPB_DEVICE void mma_p_b(float (&c)[8][4], const uint32_t (&pf)[8][2], const Tile& b, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t a[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
+#pragma unroll
+    for (int ndp = 0; ndp < 4; ++ndp) {
+      uint32_t f[4];
+      const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int cc = ndp * 16 + (lane >> 4) * 8;
+      ldmatrix_x4_trans(f, &b[r][cc]);
+      mma16816(c[2 * ndp], a, f[0], f[1]);
+      mma16816(c[2 * ndp + 1], a, f[2], f[3]);
+    }
+  }
+}
+
+OPB_DEVICE void load_a_frags(uint32_t (&af)[4][4], const Tile& a, int warp, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int c = ks * 16 + (lane >> 4) * 8;
+    ldmatrix_x4(af[ks], &a[r][c]);
+  }
+}
+
+struct SmemDq {
+  Tile q, d_o;
+  Tile k[2], v[2];
+};
+
+__global__ void __launch_bounds__(128)
+attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_out,
+                        const float* __restrict__ bias, const uint8_t* __restrict__ key_pad,
+                        const float* __restrict__ lse, const float* __restrict__ delta,
+                        __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int B, int S, int H, int s_pad,
+                        float q_scale) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SmemDq& sm = *reinterpret_cast<SmemDq*>(smem_raw);
+  const int q_chunks = (S + kTile - 1) / kTile;
+  const int chunk = blockIdx.x % q_chunks;
+  const int h = (blockIdx.x / q_chunks) % H;
+  const int b = blockIdx.x / (q_chunks * H);
+  const int D = H * kHd;
+  const long row_pitch = 3L * D;
+  const int q0 = chunk * kTile;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int num_kblocks = (S + kTile - 1) / kTile;
+
+  const __nv_bfloat16* qbase = qkv + (static_cast<long>(b) * S) * row_pitch + h * kHd;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const __nv_bfloat16* dobase = d_out + (static_cast<long>(b) * S) * D + h * kHd;
+
+  load_tile(sm.q, qbase, row_pitch, q0, S, tid);
+  load_tile(sm.d_o, dobase, D, q0, S, tid);
+  load_tile(sm.k[0], kbase, row_pitch, 0, S, tid);
+  load_tile(sm.v[0], vbase, row_pitch, 0, S, tid);
+  cp_async_commit();
+
+  const int qrow_lo = q0 + warp * 16 + g, qrow_hi = qrow_lo + 8;
+  const bool ok_lo = qrow_lo < S, ok_hi = qrow_hi < S;
+  const long stat = (static_cast<long>(b) * H + h) * S;
+  float lse_lo = ok_lo ? lse[stat + qrow_lo] : 0.f, lse_hi = ok_hi ? lse[stat + qrow_hi] : 0.f;
+  const float dl_lo = ok_lo ? delta[stat + qrow_lo] : 0.f, dl_hi = ok_hi ? delta[stat + qrow_hi] : 0.f;
+  const bool live_lo = ok_lo && lse_lo > -INFINITY, live_hi = ok_hi && lse_hi > -INFINITY;
+  const float* bias_lo = bias ? bias + (static_cast<long>(h) * S + (ok_lo ? qrow_lo : 0)) * s_pad : nullptr;
+  const float* bias_hi = bias ? bias + (static_cast<long>(h) * S + (ok_hi ? qrow_hi : 0)) * s_pad : nullptr;
+  float* db_lo = dbias ? dbias + (static_cast<long>(h) * S + (ok_lo ? qrow_lo : 0)) * s_pad : nullptr;
+  float* db_hi = dbias ? dbias + (static_cast<long>(h) * S + (ok_hi ? qrow_hi : 0)) * s_pad : nullptr;
+  const uint8_t* kp = key_pad ? key_pad + static_cast<long>(b) * S : nullptr;
+
+  uint32_t qf[4][4], dof[4][4];
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+  for (int kb = 0; kb < num_kblocks; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < num_kblocks) {
+      load_tile(sm.k[buf ^ 1], kbase, row_pitch, (kb + 1) * kTile, S, tid);
+      load_tile(sm.v[buf ^ 1], vbase, row_pitch, (kb + 1) * kTile, S, tid);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (kb == 0) {
+      load_a_frags(qf, sm.q, warp, lane);
+      load_a_frags(dof, sm.d_o, warp, lane);
+    }
+    const int k0 = kb * kTile;
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+    mma_a_bt(s, qf, sm.k[buf], lane);
+    mma_a_bt(dp, dof, sm.v[buf], lane);
+
+    uint32_t dsf[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = k0 + nt * 8 + 2 * t;
+      float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+      if (bias != nullptr && key < S) {       // s_pad is even and >= S: key + 1 is readable
+        const float2 x = *reinterpret_cast<const float2*>(bias_lo + key);
+        const float2 y = *reinterpret_cast<const float2*>(bias_hi + key);
+        b00 = x.x; b01 = x.y; b10 = y.x; b11 = y.y;
+      }
+      const bool dead0 = (key >= S) || (kp != nullptr && kp[key] != 0);
+      const bool dead1 = (key + 1 >= S) || (kp != nullptr && kp[key + 1] != 0);
+      const float p0 = (dead0 || !live_lo) ? 0.f : __expf(s[nt][0] + b00 - lse_lo);
+      const float p1 = (dead1 || !live_lo) ? 0.f : __expf(s[nt][1] + b01 - lse_lo);
+      const float p2 = (dead0 || !live_hi) ? 0.f : __expf(s[nt][2] + b10 - lse_hi);
+      const float p3 = (dead1 || !live_hi) ? 0.f : __expf(s[nt][3] + b11 - lse_hi);
+      const float d0 = p0 * (dp[nt][0] - dl_lo), d1 = p1 * (dp[nt][1] - dl_lo);
+      const float d2 = p2 * (dp[nt][2] - dl_hi), d3 = p3 * (dp[nt][3] - dl_hi);
+      if (dbias != nullptr) {
+        if (!dead0 && live_lo) atomicAdd(db_lo + key, d0);
+        if (!dead1 && live_lo) atomicAdd(db_lo + key + 1, d1);
+        if (!dead0 && live_hi) atomicAdd(db_hi + key, d2);
+        if (!dead1 && live_hi) atomicAdd(db_hi + key + 1, d3);
+      }
+      dsf[nt][0] = pack_bf16x2(d0, d1);
+      dsf[nt][1] = pack_bf16x2(d2, d3);
+    }
+    mma_p_b(dq, dsf, sm.k[buf], lane);
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  if (ok_lo) {
+    __nv_bfloat16* op = dqkv + (static_cast<long>(b) * S + qrow_lo) * row_pitch + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+      *reinterpret_cast<uint32_t*>(op + nd * 8) = pack_bf16x2(dq[nd][0] * q_scale, dq[nd][1] * q_scale);
+  }
+  if (ok_hi) {
+    __nv_bfloat16* op = dqkv + (static_cast<long>(b) * S + qrow_hi) * row_pitch + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+      *reinterpret_cast<uint32_t*>(op + nd * 8) = pack_bf16x2(dq[nd][2] * q_scale, dq[nd][3] * q_scale);
+  }
+}
+
+struct SmemDkv {
+  Tile k, v;
+  Tile q[2], d_o[2];
+  float lse[2][kTile];
+  float delta[2][kTile];
+};
+
+__global__ void __launch_bounds__(128)
+attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_out,
+                         const float* __restrict__ bias, const uint8_t* __restrict__ key_pad,
+                         const float* __restrict__ lse, const float* __restrict__ delta,
+                         __nv_bfloat16* __restrict__ dqkv, int B, int S, int H, int s_pad) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SmemDkv& sm = *reinterpret_cast<SmemDkv*>(smem_raw);
+  const int k_chunks = (S + kTile - 1) / kTile;
+  const int chunk = blockIdx.x % k_chunks;
+  const int h = (blockIdx.x / k_chunks) % H;
+  const int b = blockIdx.x / (k_chunks * H);
+  const int D = H * kHd;
+  const long row_pitch = 3L * D;
+  const int kc0 = chunk * kTile;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int num_qblocks = (S + kTile - 1) / kTile;
+
+  const __nv_bfloat16* qbase = qkv + (static_cast<long>(b) * S) * row_pitch + h * kHd;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const __nv_bfloat16* dobase = d_out + (static_cast<long>(b) * S) * D + h * kHd;
+  const long stat = (static_cast<long>(b) * H + h) * S;
+
+  auto load_q = [&](int qb, int buf) {
+    load_tile(sm.q[buf], qbase, row_pitch, qb * kTile, S, tid);
+    load_tile(sm.d_o[buf], dobase, D, qb * kTile, S, tid);
+    if (tid < kTile) {
+      const int qr = qb * kTile + tid;
+      sm.lse[buf][tid] = qr < S ? lse[stat + qr] : -INFINITY;
+      sm.delta[buf][tid] = qr < S ? delta[stat + qr] : 0.f;
+    }
+  };
+  load_tile(sm.k, kbase, row_pitch, kc0, S, tid);
+  load_tile(sm.v, vbase, row_pitch, kc0, S, tid);
+  load_q(0, 0);
+  cp_async_commit();
+
+  const int key_lo = kc0 + warp * 16 + g, key_hi = key_lo + 8;
+  const uint8_t* kp = key_pad ? key_pad + static_cast<long>(b) * S : nullptr;
+  const bool dead_lo = key_lo >= S || (kp != nullptr && kp[key_lo] != 0);
+  const bool dead_hi = key_hi >= S || (kp != nullptr && kp[key_hi] != 0);
+
+  uint32_t kf[4][4], vf[4][4];
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+
+  for (int qb = 0; qb < num_qblocks; ++qb) {
+    const int buf = qb & 1;
+    if (qb + 1 < num_qblocks) load_q(qb + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (qb == 0) {
+      load_a_frags(kf, sm.k, warp, lane);
+      load_a_frags(vf, sm.v, warp, lane);
+    }
+    const int q0 = qb * kTile;
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+    mma_a_bt(st, kf, sm.q[buf], lane);        // S^T[key, query]
+    mma_a_bt(dpt, vf, sm.d_o[buf], lane);     // dP^T[key, query]
+
+    uint32_t pf[8][2], dsf[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int ql = nt * 8 + 2 * t;          // query (local) of elements [0] / [2]; ql + 1 of [1] / [3]
+      const int qg = q0 + ql;
+      const float l0 = sm.lse[buf][ql], l1 = sm.lse[buf][ql + 1];
+      const float e0 = sm.delta[buf][ql], e1 = sm.delta[buf][ql + 1];
+      const bool q_ok0 = qg < S && l0 > -INFINITY, q_ok1 = (qg + 1) < S && l1 > -INFINITY;
+      float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+      if (bias != nullptr) {
+        const float* br0 = bias + (static_cast<long>(h) * S + (qg < S ? qg : 0)) * s_pad;
+        const float* br1 = bias + (static_cast<long>(h) * S + (qg + 1 < S ? qg + 1 : 0)) * s_pad;
+        if (!dead_lo) { b00 = br0[key_lo]; b01 = br1[key_lo]; }
+        if (!dead_hi) { b10 = br0[key_hi]; b11 = br1[key_hi]; }
+      }
+      const float p0 = (dead_lo || !q_ok0) ? 0.f : __expf(st[nt][0] + b00 - l0);
+      const float p1 = (dead_lo || !q_ok1) ? 0.f : __expf(st[nt][1] + b01 - l1);
+      const float p2 = (dead_hi || !q_ok0) ? 0.f : __expf(st[nt][2] + b10 - l0);
+      const float p3 = (dead_hi || !q_ok1) ? 0.f : __expf(st[nt][3] + b11 - l1);
+      pf[nt][0] = pack_bf16x2(p0, p1);
+      pf[nt][1] = pack_bf16x2(p2, p3);
+      dsf[nt][0] = pack_bf16x2(p0 * (dpt[nt][0] - e0), p1 * (dpt[nt][1] - e1));
+      dsf[nt][1] = pack_bf16x2(p2 * (dpt[nt][2] - e0), p3 * (dpt[nt][3] - e1));
+    }
+    mma_p_b(dv, pf, sm.d_o[buf], lane);       // dV += P^T dO
+    mma_p_b(dk, dsf, sm.q[buf], lane);        // dK += dS^T Q
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  if (key_lo < S) {
+    __nv_bfloat16* op = dqkv + (static_cast<long>(b) * S + key_lo) * row_pitch + D + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      *reinterpret_cast<uint32_t*>(op + nd * 8) = pack_bf16x2(dk[nd][0], dk[nd][1]);
+      *reinterpret_cast<uint32_t*>(op + D + nd * 8) = pack_bf16x2(dv[nd][0], dv[nd][1]);
+    }
+  }
+  if (key_hi < S) {
+    __nv_bfloat16* op = dqkv + (static_cast<long>(b) * S + key_hi) * row_pitch + D + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      *reinterpret_cast<uint32_t*>(op + nd * 8) = pack_bf16x2(dk[nd][2], dk[nd][3]);
+      *reinterpret_cast<uint32_t*>(op + D + nd * 8) = pack_bf16x2(dv[nd][2], dv[nd][3]);
+    }
+  }
+}
+
+}  // namespace
+
+int attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
+                  const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
+                  float q_scale, cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || H <= 0 || lse == nullptr || delta == nullptr) return OPB_ERR_INVALID;
+  if (bias != nullptr && (s_pad < S || (s_pad & 3))) return OPB_ERR_INVALID;
+  if (dbias != nullptr && bias == nullptr) return OPB_ERR_INVALID;
+  int rc = attn_delta(d_out, out, delta, B, S, H, stream);
+  if (rc != OPB_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(SmemDq))) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(SmemDkv))) != cudaSuccess)
+      return OPB_ERR_CUDA;
+    configured = true;
+  }
+  const int chunks = (S + kTile - 1) / kTile;
+  const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * chunks);
+  attention_bwd_dq_kernel<<<grid, 128, sizeof(SmemDq), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), bias, key_pad, lse,
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, B, S, H, s_pad, q_scale);
+  if (cudaGetLastError() != cudaSuccess) return OPB_ERR_CUDA;
+  attention_bwd_dkv_kernel<<<grid, 128, sizeof(SmemDkv), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), bias, key_pad, lse,
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), B, S, H, s_pad);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+}  // namespace opb

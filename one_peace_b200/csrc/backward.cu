@@ -1,0 +1,523 @@
+// Row-wise / column-reduction kernels of the encoder BACKWARD pass (reference: autograd through
+// transformer_layer.py:165-228, multihead_attention.py:103-126, components.py:23-44):
+//   layernorm_bwd     dx, dgamma, dbeta of  y = LN(x) * gamma + beta  (optionally y = gelu(LN(x)...), the hMLP stem)
+//   geglu_fwd/bwd     u = gelu_erf(g) * l  on the un-fused [M, 2F] projection (transformer_layer.py:54-67)
+//   scale_resid_fwd   x_out = x + row_scale * gamma * o           (LayerScale + drop-path residual, :70-88)
+//   scale_resid_bwd   do = row_scale * gamma * dx, dgamma = sum_rows row_scale * dx * o, dbias = sum_rows do
+//   colsum            bias gradients: sum over rows of a bf16 [M, n] matrix
+//   attn_delta        delta[b,h,s] = sum_d dO * O  (softmax backward row term)
+//   relpos_bias_bwd   dtable[bucket[i,j], h] += dbias[h,i,j]      (adapter/text.py:84-91, image.py:164-171)
+// All are HBM-bound: one CTA walks rows grid-stride, every thread owns fixed 4-column groups, so the column
+// reductions (dgamma / dbeta / dbias) accumulate in registers over the CTA's rows and are finished by a second tiny
+// kernel over the per-CTA partials (deterministic: fixed row -> CTA assignment, fixed summation order).
+#include "common.cuh"
+#include "ops.h"
+
+namespace opb {
+
+namespace {
+
+constexpr int kBwdThreads = 256;
+constexpr int kMaxGroups = 6;          // 4-column groups per thread: dim <= 6 * 256 * 4 = 6144
+constexpr int kBwdMaxBlocks = 148 * 4;
+
+OPB_DEVICE float gelu_grad(float z) {
+  // d/dz [ z * Phi(z) ] = Phi(z) + z * phi(z)
+  const float cdf = 0.5f * (1.f + fast_erf(z * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+  return cdf + z * pdf;
+}
+
+template <typename T>
+OPB_DEVICE float4 load4(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    return *reinterpret_cast<const float4*>(p);
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 lo = unpack_bf16x2(v.x), hi = unpack_bf16x2(v.y);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+template <typename T>
+OPB_DEVICE void store4(T* p, float4 v) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = v;
+  } else {
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = o;
+  }
+}
+
+// sums two values over the CTA; every thread gets both totals
+OPB_DEVICE float2 block_sum2(float a, float b, float2* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();                       // previous use of `red` finished
+  if (lane == 0) red[warp] = make_float2(a, b);
+  __syncthreads();
+  float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < kBwdThreads / 32; ++w) { t.x += red[w].x; t.y += red[w].y; }
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TX, typename TDY, typename TDX>
+__global__ void __launch_bounds__(kBwdThreads)
+layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__ dy, long ld_dy,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, TDX* __restrict__ dx, long ld_dx,
+                     int accumulate, float* __restrict__ partial, int rows, int dim, float eps, int gelu,
+                     int dy_merge_w) {
+  __shared__ float2 red[kBwdThreads / 32];
+  const int ngroups = dim >> 2;
+  float4 dg[kMaxGroups], db[kMaxGroups], gm[kMaxGroups], bt[kMaxGroups];
+#pragma unroll
+  for (int k = 0; k < kMaxGroups; ++k) {
+    dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int g = threadIdx.x + k * kBwdThreads;
+    gm[k] = (g < ngroups && gamma != nullptr) ? *reinterpret_cast<const float4*>(gamma + 4 * g) : make_float4(1.f, 1.f, 1.f, 1.f);
+    bt[k] = (g < ngroups && beta != nullptr) ? *reinterpret_cast<const float4*>(beta + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_dim = 1.f / dim;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    float4 xv[kMaxGroups], gv[kMaxGroups];
+    float s1 = 0.f;
+    // the forward's 2x2 pixel-merge scatter (layernorm.cu, adapter/image.py:37-47): row (b, y, x) of the w x w grid
+    // went to row (b, y/2, x/2), column block (y%2)*2 + x%2 of the next conv's operand
+    const TDY* dyr = dy + row * ld_dy;
+    if (dy_merge_w > 0) {
+      const int w = dy_merge_w;
+      const int xx = row % w, yy = (row / w) % w, bb = row / (w * w);
+      dyr = dy + ((static_cast<long>(bb) * (w / 2) + yy / 2) * (w / 2) + xx / 2) * ld_dy + ((yy & 1) * 2 + (xx & 1)) * dim;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        xv[k] = load4(x + row * ldx + 4 * g);
+        gv[k] = load4(dyr + 4 * g);
+        s1 += xv[k].x + xv[k].y + xv[k].z + xv[k].w;
+      } else {
+        xv[k] = gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float mean = block_sum2(s1, 0.f, red).x * inv_dim;
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        xv[k].x -= mean; xv[k].y -= mean; xv[k].z -= mean; xv[k].w -= mean;
+        s2 += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+      }
+    }
+    const float rstd = rsqrtf(block_sum2(s2, 0.f, red).x * inv_dim + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        xv[k].x *= rstd; xv[k].y *= rstd; xv[k].z *= rstd; xv[k].w *= rstd;       // x-hat
+        if (gelu) {
+          gv[k].x *= gelu_grad(fmaf(xv[k].x, gm[k].x, bt[k].x));
+          gv[k].y *= gelu_grad(fmaf(xv[k].y, gm[k].y, bt[k].y));
+          gv[k].z *= gelu_grad(fmaf(xv[k].z, gm[k].z, bt[k].z));
+          gv[k].w *= gelu_grad(fmaf(xv[k].w, gm[k].w, bt[k].w));
+        }
+        dg[k].x += gv[k].x * xv[k].x; dg[k].y += gv[k].y * xv[k].y; dg[k].z += gv[k].z * xv[k].z; dg[k].w += gv[k].w * xv[k].w;
+        db[k].x += gv[k].x; db[k].y += gv[k].y; db[k].z += gv[k].z; db[k].w += gv[k].w;
+        gv[k].x *= gm[k].x; gv[k].y *= gm[k].y; gv[k].z *= gm[k].z; gv[k].w *= gm[k].w;   // dy * gamma
+        c1 += gv[k].x + gv[k].y + gv[k].z + gv[k].w;
+        c2 += gv[k].x * xv[k].x + gv[k].y * xv[k].y + gv[k].z * xv[k].z + gv[k].w * xv[k].w;
+      }
+    }
+    const float2 c = block_sum2(c1, c2, red);
+    const float m1 = c.x * inv_dim, m2 = c.y * inv_dim;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        float4 o;
+        o.x = rstd * (gv[k].x - m1 - xv[k].x * m2);
+        o.y = rstd * (gv[k].y - m1 - xv[k].y * m2);
+        o.z = rstd * (gv[k].z - m1 - xv[k].z * m2);
+        o.w = rstd * (gv[k].w - m1 - xv[k].w * m2);
+        TDX* p = dx + row * ld_dx + 4 * g;
+        if (accumulate) {
+          const float4 old = load4(p);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        store4(p, o);
+      }
+    }
+  }
+  if (partial != nullptr) {
+    float* pg = partial + static_cast<long>(blockIdx.x) * 2 * dim;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        *reinterpret_cast<float4*>(pg + 4 * g) = dg[k];
+        *reinterpret_cast<float4*>(pg + dim + 4 * g) = db[k];
+      }
+    }
+  }
+}
+
+// out[c] = sum_p partial[p * stride + c]   (c < n)
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int parts, long stride, float* __restrict__ out,
+                                      int n, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += partial[p * stride + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+int grid_for_rows(int rows) { return rows < kBwdMaxBlocks ? rows : kBwdMaxBlocks; }
+
+int reduce_partials(const float* partial, int parts, long stride, float* out, int n, cudaStream_t stream) {
+  partial_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(partial, parts, stride, out, n, 0);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ gl, __nv_bfloat16* __restrict__ u, long rows, int F) {
+  const long total = rows * (F / 4);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / (F / 4);
+    const int c = static_cast<int>(i % (F / 4)) * 4;
+    const float4 g = load4(gl + r * 2 * F + c);
+    const float4 l = load4(gl + r * 2 * F + F + c);
+    store4(u + r * F + c, make_float4(gelu_erf(g.x) * l.x, gelu_erf(g.y) * l.y, gelu_erf(g.z) * l.z, gelu_erf(g.w) * l.w));
+  }
+}
+
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ gl, const __nv_bfloat16* __restrict__ du,
+                                 __nv_bfloat16* __restrict__ dgl, long rows, int F) {
+  const long total = rows * (F / 4);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / (F / 4);
+    const int c = static_cast<int>(i % (F / 4)) * 4;
+    const float4 g = load4(gl + r * 2 * F + c);
+    const float4 l = load4(gl + r * 2 * F + F + c);
+    const float4 d = load4(du + r * F + c);
+    store4(dgl + r * 2 * F + c, make_float4(d.x * l.x * gelu_grad(g.x), d.y * l.y * gelu_grad(g.y), d.z * l.z * gelu_grad(g.z),
+                                            d.w * l.w * gelu_grad(g.w)));
+    store4(dgl + r * 2 * F + F + c, make_float4(d.x * gelu_erf(g.x), d.y * gelu_erf(g.y), d.z * gelu_erf(g.z), d.w * gelu_erf(g.w)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void scale_resid_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ o,
+                                       const float* __restrict__ gamma, const float* __restrict__ row_scale,
+                                       float* __restrict__ out, long rows, int n) {
+  const long total = rows * (n / 4);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / (n / 4);
+    const int c = static_cast<int>(i % (n / 4)) * 4;
+    const float rs = row_scale != nullptr ? row_scale[r] : 1.f;
+    const float4 g = gamma != nullptr ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * n + c);
+    const float4 ov = load4(o + r * n + c);
+    *reinterpret_cast<float4*>(out + r * n + c) =
+        make_float4(fmaf(rs * g.x, ov.x, xv.x), fmaf(rs * g.y, ov.y, xv.y), fmaf(rs * g.z, ov.z, xv.z), fmaf(rs * g.w, ov.w, xv.w));
+  }
+}
+
+// partial layout: [block][2][n] = (dgamma, dbias)
+__global__ void __launch_bounds__(kBwdThreads)
+scale_resid_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ o, const float* __restrict__ gamma,
+                       const float* __restrict__ row_scale, __nv_bfloat16* __restrict__ d_o, float* __restrict__ partial,
+                       int rows, int n, int in_period, int in_valid, int in_shift) {
+  const int ngroups = n >> 2;
+  float4 dg[kMaxGroups], db[kMaxGroups], gm[kMaxGroups];
+#pragma unroll
+  for (int k = 0; k < kMaxGroups; ++k) {
+    dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int g = threadIdx.x + k * kBwdThreads;
+    gm[k] = (g < ngroups && gamma != nullptr) ? *reinterpret_cast<const float4*>(gamma + 4 * g) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float rs = row_scale != nullptr ? row_scale[row] : 1.f;
+    // optional gather of the input rows: output row r reads dx row (r / in_valid) * in_period + in_shift + r % in_valid
+    // (the token rows behind the CLS slot of every batch element)
+    const long irow = in_valid > 0 ? static_cast<long>(row / in_valid) * in_period + in_shift + row % in_valid : row;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        float4 d = *reinterpret_cast<const float4*>(dx + irow * n + 4 * g);
+        d.x *= rs; d.y *= rs; d.z *= rs; d.w *= rs;
+        if (o != nullptr) {
+          const float4 ov = load4(o + static_cast<long>(row) * n + 4 * g);
+          dg[k].x += d.x * ov.x; dg[k].y += d.y * ov.y; dg[k].z += d.z * ov.z; dg[k].w += d.w * ov.w;
+        }
+        d.x *= gm[k].x; d.y *= gm[k].y; d.z *= gm[k].z; d.w *= gm[k].w;
+        // the bias gradient sums the bf16-rounded values the dW GEMM also consumes
+        uint2 pk;
+        pk.x = pack_bf16x2(d.x, d.y);
+        pk.y = pack_bf16x2(d.z, d.w);
+        *reinterpret_cast<uint2*>(d_o + static_cast<long>(row) * n + 4 * g) = pk;
+        db[k].x += d.x; db[k].y += d.y; db[k].z += d.z; db[k].w += d.w;
+      }
+    }
+  }
+  float* pg = partial + static_cast<long>(blockIdx.x) * 2 * n;
+#pragma unroll
+  for (int k = 0; k < kMaxGroups; ++k) {
+    const int g = threadIdx.x + k * kBwdThreads;
+    if (g < ngroups) {
+      *reinterpret_cast<float4*>(pg + 4 * g) = dg[k];
+      *reinterpret_cast<float4*>(pg + n + 4 * g) = db[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+colsum_kernel(const __nv_bfloat16* __restrict__ y, long ldy, float* __restrict__ partial, int rows, int n) {
+  const int ngroups = n >> 2;
+  float4 acc[kMaxGroups];
+#pragma unroll
+  for (int k = 0; k < kMaxGroups; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      const int g = threadIdx.x + k * kBwdThreads;
+      if (g < ngroups) {
+        const float4 v = load4(y + row * ldy + 4 * g);
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+  }
+  float* pg = partial + static_cast<long>(blockIdx.x) * n;
+#pragma unroll
+  for (int k = 0; k < kMaxGroups; ++k) {
+    const int g = threadIdx.x + k * kBwdThreads;
+    if (g < ngroups) *reinterpret_cast<float4*>(pg + 4 * g) = acc[k];
+  }
+}
+
+// one warp per row: delta[(b*H + h)*S + s] = sum_d dO[row, h*64 + d] * O[row, h*64 + d]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o,
+                                  float* __restrict__ delta, int B, int S, int H) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * S) return;
+  const int b = warp / S, s = warp % S;
+  const long base = static_cast<long>(warp) * H * 64;
+  for (int h = 0; h < H; ++h) {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(d_o + base + h * 64 + 2 * lane);
+    const uint32_t c = *reinterpret_cast<const uint32_t*>(o + base + h * 64 + 2 * lane);
+    const float2 af = unpack_bf16x2(a), cf = unpack_bf16x2(c);
+    const float t = warp_sum(af.x * cf.x + af.y * cf.y);
+    if (lane == 0) delta[(static_cast<long>(b) * H + h) * S + s] = t;
+  }
+}
+
+__global__ void relpos_bias_bwd_kernel(const float* __restrict__ dbias, const int64_t* __restrict__ bucket,
+                                       float* __restrict__ dtable, int S, int s_pad, int H, long ld_bucket) {
+  const int i = blockIdx.x;
+  for (int idx = threadIdx.x; idx < S * H; idx += blockDim.x) {
+    const int h = idx / S, j = idx % S;
+    const long bk = bucket[i * ld_bucket + j];
+    atomicAdd(dtable + bk * H + h, dbias[(static_cast<long>(h) * S + i) * s_pad + j]);
+  }
+}
+
+// out[c] (+)= sum_b in[b * ld + c]
+__global__ void batch_sum_kernel(const float* __restrict__ in, long ld, float* __restrict__ out, int B, long n, int accumulate) {
+  const long c = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += in[b * ld + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// y = x / max(|x|, 1e-12) (F.normalize): dx = (dy - y (y . dy)) / |x|;  one warp per row
+__global__ void l2_normalize_bwd_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dy, long ld_dy,
+                                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, int rows, int D) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  const float* gr = dy + row * ld_dy;
+  float ss = 0.f, dot = 0.f;
+  for (int c = lane; c < D; c += 32) { ss += xr[c] * xr[c]; dot += xr[c] * gr[c]; }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  const float inv = 1.f / nrm;
+  const float k = dot * inv * inv * inv;       // (y . dy) / |x| * (1 / |x|) with y = x / |x|
+  for (int c = lane; c < D; c += 32) {
+    const float v = gr[c] * inv - xr[c] * k;
+    if (dx != nullptr) dx[static_cast<long>(row) * D + c] = v;
+    if (dx_bf16 != nullptr) dx_bf16[static_cast<long>(row) * D + c] = __float2bfloat16(v);
+  }
+}
+
+// adjoint of text_embed (adapters.cu; adapter/text.py:125-129,144-146): one CTA per (b, s) row of dx [B, T+1, D]
+__global__ void text_embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ tokens,
+                                      float* __restrict__ dtable, float* __restrict__ dpos, float* __restrict__ dcls,
+                                      int B, int T, int D, int pad_idx) {
+  const int row = blockIdx.x;
+  const int S = T + 1;
+  const int b = row / S, s = row % S;
+  const float* g = dx + static_cast<long>(row) * D;
+  if (s == 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      atomicAdd(dcls + c, g[c]);
+      atomicAdd(dpos + c, g[c]);
+    }
+    return;
+  }
+  const long tok = tokens[static_cast<long>(b) * T + (s - 1)];
+  if (tok == pad_idx) return;                 // padded rows were zeroed in the forward: no gradient
+  float* dt = dtable + tok * D;
+  float* dp = dpos + static_cast<long>(s) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(dt + c, g[c]);
+    atomicAdd(dp + c, g[c]);
+  }
+}
+
+}  // namespace
+
+// ws: at least layernorm_bwd_ws_floats(dim) floats
+long bwd_ws_floats(int dim) { return static_cast<long>(kBwdMaxBlocks) * 2 * dim; }
+
+int layernorm_bwd(const void* x, int x_dtype, long ldx, const void* dy, int dy_dtype, long ld_dy, const float* gamma,
+                  const float* beta, void* dx, int dx_dtype, long ld_dx, int accumulate, int rows, int dim, float eps,
+                  int gelu, int dy_merge_w, float* ws, float* dgamma, float* dbeta, cudaStream_t stream) {
+  if (rows <= 0 || dim <= 0 || (dim & 3) || dim > kMaxGroups * kBwdThreads * 4) return OPB_ERR_INVALID;
+  if (dy_merge_w < 0 || (dy_merge_w & 1) || (dy_merge_w > 0 && rows % (dy_merge_w * dy_merge_w) != 0)) return OPB_ERR_INVALID;
+  if ((ldx & 3) || (ld_dy & 3) || (ld_dx & 3)) return OPB_ERR_INVALID;
+  if (accumulate && dx_dtype != 0) return OPB_ERR_INVALID;
+  const bool want_param_grads = (dgamma != nullptr || dbeta != nullptr);
+  if (want_param_grads && ws == nullptr) return OPB_ERR_INVALID;
+  const int grid = grid_for_rows(rows);
+  float* partial = want_param_grads ? ws : nullptr;
+#define OPB_LNB(TX, TDY, TDX)                                                                                         \
+  layernorm_bwd_kernel<TX, TDY, TDX><<<grid, kBwdThreads, 0, stream>>>(                                               \
+      reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TDY*>(dy), ld_dy, gamma, beta,                      \
+      reinterpret_cast<TDX*>(dx), ld_dx, accumulate, partial, rows, dim, eps, gelu, dy_merge_w)
+  const int key = (x_dtype != 0) * 4 + (dy_dtype != 0) * 2 + (dx_dtype != 0);
+  switch (key) {
+    case 0: OPB_LNB(float, float, float); break;
+    case 1: OPB_LNB(float, float, __nv_bfloat16); break;
+    case 2: OPB_LNB(float, __nv_bfloat16, float); break;
+    case 3: OPB_LNB(float, __nv_bfloat16, __nv_bfloat16); break;
+    case 4: OPB_LNB(__nv_bfloat16, float, float); break;
+    case 5: OPB_LNB(__nv_bfloat16, float, __nv_bfloat16); break;
+    case 6: OPB_LNB(__nv_bfloat16, __nv_bfloat16, float); break;
+    default: OPB_LNB(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+  }
+#undef OPB_LNB
+  if (cudaGetLastError() != cudaSuccess) return OPB_ERR_CUDA;
+  if (dgamma != nullptr) {
+    const int rc = reduce_partials(ws, grid, 2L * dim, dgamma, dim, stream);
+    if (rc != OPB_OK) return rc;
+  }
+  if (dbeta != nullptr) {
+    const int rc = reduce_partials(ws + dim, grid, 2L * dim, dbeta, dim, stream);
+    if (rc != OPB_OK) return rc;
+  }
+  return OPB_OK;
+}
+
+static int elementwise_grid(long total) {
+  long g = (total + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+int geglu_fwd(const void* gl, void* u, long rows, int F, cudaStream_t stream) {
+  if (rows <= 0 || F <= 0 || (F & 3)) return OPB_ERR_INVALID;
+  geglu_fwd_kernel<<<elementwise_grid(rows * (F / 4)), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(gl),
+                                                                        reinterpret_cast<__nv_bfloat16*>(u), rows, F);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int geglu_bwd(const void* gl, const void* du, void* dgl, long rows, int F, cudaStream_t stream) {
+  if (rows <= 0 || F <= 0 || (F & 3)) return OPB_ERR_INVALID;
+  geglu_bwd_kernel<<<elementwise_grid(rows * (F / 4)), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gl), reinterpret_cast<const __nv_bfloat16*>(du),
+      reinterpret_cast<__nv_bfloat16*>(dgl), rows, F);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int scale_resid_fwd(const float* x, const void* o, const float* gamma, const float* row_scale, float* out, long rows,
+                    int n, cudaStream_t stream) {
+  if (rows <= 0 || n <= 0 || (n & 3)) return OPB_ERR_INVALID;
+  scale_resid_fwd_kernel<<<elementwise_grid(rows * (n / 4)), 256, 0, stream>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(o), gamma, row_scale, out, rows, n);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int scale_resid_bwd(const float* dx, const void* o, const float* gamma, const float* row_scale, void* d_o, float* ws,
+                    float* dgamma, float* dbias, int rows, int n, int in_period, int in_valid, int in_shift,
+                    cudaStream_t stream) {
+  if (rows <= 0 || n <= 0 || (n & 3) || n > kMaxGroups * kBwdThreads * 4 || ws == nullptr) return OPB_ERR_INVALID;
+  if (dgamma != nullptr && o == nullptr) return OPB_ERR_INVALID;
+  const int grid = grid_for_rows(rows);
+  scale_resid_bwd_kernel<<<grid, kBwdThreads, 0, stream>>>(dx, reinterpret_cast<const __nv_bfloat16*>(o), gamma, row_scale,
+                                                           reinterpret_cast<__nv_bfloat16*>(d_o), ws, rows, n, in_period,
+                                                           in_valid, in_shift);
+  if (cudaGetLastError() != cudaSuccess) return OPB_ERR_CUDA;
+  if (dgamma != nullptr) {
+    const int rc = reduce_partials(ws, grid, 2L * n, dgamma, n, stream);
+    if (rc != OPB_OK) return rc;
+  }
+  if (dbias != nullptr) {
+    const int rc = reduce_partials(ws + n, grid, 2L * n, dbias, n, stream);
+    if (rc != OPB_OK) return rc;
+  }
+  return OPB_OK;
+}
+
+int colsum_bf16(const void* y, long ldy, float* ws, float* out, int rows, int n, cudaStream_t stream) {
+  if (rows <= 0 || n <= 0 || (n & 3) || (ldy & 3) || n > kMaxGroups * kBwdThreads * 4 || ws == nullptr) return OPB_ERR_INVALID;
+  const int grid = grid_for_rows(rows);
+  colsum_kernel<<<grid, kBwdThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(y), ldy, ws, rows, n);
+  if (cudaGetLastError() != cudaSuccess) return OPB_ERR_CUDA;
+  return reduce_partials(ws, grid, n, out, n, stream);
+}
+
+int attn_delta(const void* d_o, const void* o, float* delta, int B, int S, int H, cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || H <= 0) return OPB_ERR_INVALID;
+  const long warps = static_cast<long>(B) * S;
+  attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_o), reinterpret_cast<const __nv_bfloat16*>(o), delta, B, S, H);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H, long ld_bucket,
+                    cudaStream_t stream) {
+  if (S <= 0 || s_pad < S || H <= 0) return OPB_ERR_INVALID;
+  relpos_bias_bwd_kernel<<<S, 256, 0, stream>>>(dbias, bucket, dtable, S, s_pad, H, ld_bucket);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int batch_sum_f32(const float* in, long ld, float* out, int B, long n, int accumulate, cudaStream_t stream) {
+  if (B <= 0 || n <= 0) return OPB_ERR_INVALID;
+  batch_sum_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, ld, out, B, n, accumulate);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int l2_normalize_bwd(const float* x, long ldx, const float* dy, long ld_dy, float* dx, void* dx_bf16, int rows, int D,
+                     cudaStream_t stream) {
+  if (rows <= 0 || D <= 0 || (dx == nullptr && dx_bf16 == nullptr)) return OPB_ERR_INVALID;
+  l2_normalize_bwd_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(x, ldx, dy, ld_dy, dx,
+                                                                       reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows, D);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T, int D,
+                   int pad_idx, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || D <= 0) return OPB_ERR_INVALID;
+  text_embed_bwd_kernel<<<B * (T + 1), 256, 0, stream>>>(dx, tokens, dtable, dpos, dcls, B, T, D, pad_idx);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+}  // namespace opb

@@ -227,4 +227,75 @@ int opb_grad_norm_clip(const void* tensors, const int32_t* chunk_tensor, const i
                              multiply_factor, max_norm, out2, static_cast<cudaStream_t>(stream));
 }
 
+int64_t opb_bwd_ws_floats(int dim) { return opb::bwd_ws_floats(dim); }
+
+int opb_layernorm_bwd(const void* x, int x_dtype, int64_t ldx, const void* dy, int dy_dtype, int64_t ld_dy,
+                      const float* gamma, const float* beta, void* dx, int dx_dtype, int64_t ld_dx, int accumulate,
+                      int rows, int dim, float eps, int gelu, int dy_merge_w, float* ws, float* dgamma, float* dbeta,
+                      void* stream) {
+  if (!x || !dy || !dx) return OPB_ERR_INVALID;
+  return opb::layernorm_bwd(x, x_dtype, ldx, dy, dy_dtype, ld_dy, gamma, beta, dx, dx_dtype, ld_dx, accumulate, rows, dim,
+                            eps, gelu, dy_merge_w, ws, dgamma, dbeta, static_cast<cudaStream_t>(stream));
+}
+
+int opb_geglu_fwd(const void* gl, void* u, int64_t rows, int F, void* stream) {
+  if (!gl || !u) return OPB_ERR_INVALID;
+  return opb::geglu_fwd(gl, u, rows, F, static_cast<cudaStream_t>(stream));
+}
+
+int opb_geglu_bwd(const void* gl, const void* du, void* dgl, int64_t rows, int F, void* stream) {
+  if (!gl || !du || !dgl) return OPB_ERR_INVALID;
+  return opb::geglu_bwd(gl, du, dgl, rows, F, static_cast<cudaStream_t>(stream));
+}
+
+int opb_scale_resid_fwd(const float* x, const void* o, const float* gamma, const float* row_scale, float* out,
+                        int64_t rows, int n, void* stream) {
+  if (!x || !o || !out) return OPB_ERR_INVALID;
+  return opb::scale_resid_fwd(x, o, gamma, row_scale, out, rows, n, static_cast<cudaStream_t>(stream));
+}
+
+int opb_scale_resid_bwd(const float* dx, const void* o, const float* gamma, const float* row_scale, void* d_o, float* ws,
+                        float* dgamma, float* dbias, int rows, int n, int in_period, int in_valid, int in_shift,
+                        void* stream) {
+  if (!dx || !d_o) return OPB_ERR_INVALID;
+  return opb::scale_resid_bwd(dx, o, gamma, row_scale, d_o, ws, dgamma, dbias, rows, n, in_period, in_valid, in_shift,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int opb_batch_sum_f32(const float* in, int64_t ld, float* out, int B, int64_t n, int accumulate, void* stream) {
+  if (!in || !out) return OPB_ERR_INVALID;
+  return opb::batch_sum_f32(in, ld, out, B, n, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int opb_l2_normalize_bwd(const float* x, int64_t ldx, const float* dy, int64_t ld_dy, float* dx, void* dx_bf16, int rows,
+                         int D, void* stream) {
+  if (!x || !dy) return OPB_ERR_INVALID;
+  return opb::l2_normalize_bwd(x, ldx, dy, ld_dy, dx, dx_bf16, rows, D, static_cast<cudaStream_t>(stream));
+}
+
+int opb_text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T,
+                       int D, int pad_idx, void* stream) {
+  if (!dx || !tokens || !dtable || !dpos || !dcls) return OPB_ERR_INVALID;
+  return opb::text_embed_bwd(dx, tokens, dtable, dpos, dcls, B, T, D, pad_idx, static_cast<cudaStream_t>(stream));
+}
+
+int opb_colsum_bf16(const void* y, int64_t ldy, float* ws, float* out, int rows, int n, void* stream) {
+  if (!y || !out) return OPB_ERR_INVALID;
+  return opb::colsum_bf16(y, ldy, ws, out, rows, n, static_cast<cudaStream_t>(stream));
+}
+
+int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
+                      const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
+                      float q_scale, void* stream) {
+  if (!qkv || !out || !d_out || !dqkv) return OPB_ERR_INVALID;
+  return opb::attention_bwd(qkv, out, d_out, bias, key_pad, lse, delta, dqkv, dbias, B, S, H, s_pad, q_scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H,
+                        int64_t ld_bucket, void* stream) {
+  if (!dbias || !bucket || !dtable) return OPB_ERR_INVALID;
+  return opb::relpos_bias_bwd(dbias, bucket, dtable, S, s_pad, H, ld_bucket, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -78,6 +78,14 @@ OPB_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Same without the cluster-scope release fence (MEMBAR.ALL.CTA + ERRBAR, ~10 % of the epilogue warps' time in ncu):
+// for signalling "accumulator drained", where the only prior accesses that matter are tcgen05.ld's already completed
+// by tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync — no generic-proxy data is handed over.
+OPB_DEVICE void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 
 OPB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

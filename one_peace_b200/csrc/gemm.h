@@ -41,6 +41,7 @@ struct GemmEpilogue {
   // alternative to ln_mu / ln_rstd: the producer's partial (sum, sum of squares) records [ln_parts, M, 2]; each
   // epilogue thread reduces the records of its row itself (index order -> deterministic), which removes the separate
   // ln_stats_finalize launch for small part counts (6 for the residual GEMMs, 24 for attention)
+  int dbg = 0;   // A/B switches for measurements (env OPB_GEMM_DBG): 1 = release-fenced accumulator hand-back, 2 = full store drain per tile
   const float* ln_partial = nullptr;
   int ln_parts = 0;
   int ln_dim = 0;

@@ -281,7 +281,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (c + 32 == kBlockN) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+            if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
           }
           if (rv) {
 #pragma unroll
@@ -353,7 +353,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const bool has_res = (EPI == EPI_RESID_F32) && ep.resid != nullptr;
           // ring slot / barrier phase bookkeeping is continuous across tiles: chunk counter gc = it * 8 + c
           const int gc0 = it * 8;
-          if (lane == 0) bulk_wait_read<0>();   // slots refilled below may still be read by the previous tile's stores
+          // the two slots refilled below were last stored from by chunks 4 and 5 of the previous tile: everything but
+          // the two newest store groups (chunks 6, 7 -> the other two slots) must have finished reading shared memory
+          if (lane == 0) { if (ep.dbg & 2) bulk_wait_read<0>(); else bulk_wait_read<2>(); }
           __syncwarp();
           if (has_res && lane == 0) {
 #pragma unroll
@@ -378,7 +380,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (c == 7) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+              if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
             }
             if (lane == 0) {
               // the slot of chunk c+2 was last stored from by chunk c-2: every store group except the newest one must
@@ -471,7 +473,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (c == (hf + 1) * kMine - 1 && hh == 1) {
                   tc_fence_before();
                   __syncwarp();
-                  if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+                  if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
                 }
                 {
                   float4 qg[8], rg[8], ql[8], rl[8];     // GeGLU: P == 1
@@ -509,7 +511,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (c == (hf + 1) * kMine - 1 && hh == 1) {
                   tc_fence_before();
                   __syncwarp();
-                  if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+                  if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
                 }
                 {
                   float4 pp[8], qq[8], rr[8];
@@ -616,7 +618,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (c + 32 == kBlockN / 2) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+            if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
           }
           if (row_ok) {
 #pragma unroll
@@ -699,7 +701,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (c + 32 == kBlockN) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+            if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
           }
           float cm = -INFINITY;
 #pragma unroll
@@ -745,7 +747,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (c + 32 == kBlockN) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+            if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -780,7 +782,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (c + 32 == kBlockN) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+            if (lane == 0) { if (ep.dbg & 1) mbar_arrive_cluster(&bars->tmem_empty[acc], 0); else mbar_arrive_cluster_relaxed(&bars->tmem_empty[acc], 0); }
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -1081,9 +1083,12 @@ static int dispatch_gemm(int cta_group, int epi, const CUtensorMap& ta, const CU
 #undef OPB_DISPATCH
 }
 
-int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep,
+int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep_in,
               int cta_group, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return OPB_ERR_INVALID;
+  GemmEpilogue ep = ep_in;
+  static const char* env_dbg = getenv("OPB_GEMM_DBG");
+  if (env_dbg != nullptr) ep.dbg = atoi(env_dbg);
   if (K % 8 != 0 || N % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) return OPB_ERR_INVALID;
   if (epi == EPI_GEGLU_BF16 && N % kBlockN != 0) return OPB_ERR_INVALID;
   if (cta_group == 0) cta_group = (M > 2 * kBlockM) ? 2 : 1;

@@ -74,4 +74,29 @@ int adam_multi_step(const void* tensors, const int* chunk_tensor, const long* ch
 int grad_norm_clip(const void* tensors, const int* chunk_tensor, const long* chunk_off, int n_chunks, float* partial,
                    float multiply_factor, float max_norm, float* out2, cudaStream_t stream);
 
+// ---- backward pass (backward.cu, attention_bwd.cu) ----
+long bwd_ws_floats(int dim);
+int layernorm_bwd(const void* x, int x_dtype, long ldx, const void* dy, int dy_dtype, long ld_dy, const float* gamma,
+                  const float* beta, void* dx, int dx_dtype, long ld_dx, int accumulate, int rows, int dim, float eps,
+                  int gelu, int dy_merge_w, float* ws, float* dgamma, float* dbeta, cudaStream_t stream);
+int geglu_fwd(const void* gl, void* u, long rows, int F, cudaStream_t stream);
+int geglu_bwd(const void* gl, const void* du, void* dgl, long rows, int F, cudaStream_t stream);
+int scale_resid_fwd(const float* x, const void* o, const float* gamma, const float* row_scale, float* out, long rows,
+                    int n, cudaStream_t stream);
+int scale_resid_bwd(const float* dx, const void* o, const float* gamma, const float* row_scale, void* d_o, float* ws,
+                    float* dgamma, float* dbias, int rows, int n, int in_period, int in_valid, int in_shift,
+                    cudaStream_t stream);
+int batch_sum_f32(const float* in, long ld, float* out, int B, long n, int accumulate, cudaStream_t stream);
+int l2_normalize_bwd(const float* x, long ldx, const float* dy, long ld_dy, float* dx, void* dx_bf16, int rows, int D,
+                     cudaStream_t stream);
+int text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T, int D,
+                   int pad_idx, cudaStream_t stream);
+int colsum_bf16(const void* y, long ldy, float* ws, float* out, int rows, int n, cudaStream_t stream);
+int attn_delta(const void* d_o, const void* o, float* delta, int B, int S, int H, cudaStream_t stream);
+int relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H, long ld_bucket,
+                    cudaStream_t stream);
+int attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
+                  const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
+                  float q_scale, cudaStream_t stream);
+
 }  // namespace opb

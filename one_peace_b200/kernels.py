@@ -378,3 +378,131 @@ def infonce_dscale(ws_a, ws_b, b, n):
     _lib.check(st, "opb_infonce_dscale")
     _count()
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# backward pass
+# ----------------------------------------------------------------------------------------------------------------
+_BWD_WS = {}
+
+
+def bwd_ws(dim, device):
+    """fp32 scratch for the column-reduction kernels (per device, grown on demand)."""
+    need = _lib.load().opb_bwd_ws_floats(int(dim))
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _BWD_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=device)
+        _BWD_WS[key] = ws
+    return ws
+
+
+def layernorm_bwd(x, dy, gamma, beta, dx, *, eps=1e-5, gelu=False, accumulate=False, dgamma=None, dbeta=None, rows=None,
+                  dim=None, ldx=None, ld_dx=None, dy_merge_w=0):
+    """x, dy, dx: [rows, dim] (fp32 / bf16, row stride free); dgamma / dbeta fp32 [dim] outputs (optional)."""
+    _need_cuda(x, dy, dx)
+    rows = x.shape[0] if rows is None else rows
+    dim = x.shape[-1] if dim is None else dim
+    ws = bwd_ws(dim, x.device) if (dgamma is not None or dbeta is not None) else None
+    st = _lib.load().opb_layernorm_bwd(x.data_ptr(), _dt(x), x.stride(-2) if ldx is None else ldx, dy.data_ptr(), _dt(dy),
+                                       dy.stride(-2), _ptr(gamma), _ptr(beta), dx.data_ptr(), _dt(dx),
+                                       dx.stride(-2) if ld_dx is None else ld_dx, int(accumulate), rows, dim, eps,
+                                       int(gelu), dy_merge_w, _ptr(ws), _ptr(dgamma), _ptr(dbeta), _stream())
+    _lib.check(st, "opb_layernorm_bwd")
+    _count(1 + (dgamma is not None) + (dbeta is not None))
+    return dx
+
+
+def geglu_fwd(gl, u):
+    rows, F2 = gl.shape
+    st = _lib.load().opb_geglu_fwd(gl.data_ptr(), u.data_ptr(), rows, F2 // 2, _stream())
+    _lib.check(st, "opb_geglu_fwd")
+    _count()
+    return u
+
+
+def geglu_bwd(gl, du, dgl):
+    rows, F2 = gl.shape
+    st = _lib.load().opb_geglu_bwd(gl.data_ptr(), du.data_ptr(), dgl.data_ptr(), rows, F2 // 2, _stream())
+    _lib.check(st, "opb_geglu_bwd")
+    _count()
+    return dgl
+
+
+def scale_resid_fwd(x, o, gamma, row_scale, out):
+    rows, n = x.shape
+    st = _lib.load().opb_scale_resid_fwd(x.data_ptr(), o.data_ptr(), _ptr(gamma), _ptr(row_scale), out.data_ptr(), rows, n,
+                                         _stream())
+    _lib.check(st, "opb_scale_resid_fwd")
+    _count()
+    return out
+
+
+def scale_resid_bwd(dx, o, gamma, row_scale, d_o, dgamma=None, dbias=None, in_period=0, in_valid=0, in_shift=0):
+    """d_o bf16 [rows, n] = row_scale * gamma * dx (rows of dx optionally gathered, see onepeace_b200.h)."""
+    rows, n = d_o.shape
+    ws = bwd_ws(n, dx.device)
+    st = _lib.load().opb_scale_resid_bwd(dx.data_ptr(), _ptr(o), _ptr(gamma), _ptr(row_scale), d_o.data_ptr(), ws.data_ptr(),
+                                         _ptr(dgamma), _ptr(dbias), rows, n, in_period, in_valid, in_shift, _stream())
+    _lib.check(st, "opb_scale_resid_bwd")
+    _count(1 + (dgamma is not None) + (dbias is not None))
+    return d_o
+
+
+def colsum(y, out):
+    rows, n = y.shape
+    ws = bwd_ws(n, y.device)
+    st = _lib.load().opb_colsum_bf16(y.data_ptr(), y.stride(0), ws.data_ptr(), out.data_ptr(), rows, n, _stream())
+    _lib.check(st, "opb_colsum_bf16")
+    _count(2)
+    return out
+
+
+def attention_bwd(qkv, out, d_out, bias, key_pad, lse, dqkv, dbias, B, S, H, q_scale):
+    """bias / dbias: dense fp32 (H,S,S_pad) tables (or None); lse fp32 [B,H,S] from `attention(..., lse=)`."""
+    delta = torch.empty(B * H * S, dtype=torch.float32, device=qkv.device)
+    s_pad = bias.shape[-1] if bias is not None else 0
+    st = _lib.load().opb_attention_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), _ptr(bias), _ptr(key_pad),
+                                       lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), _ptr(dbias), B, S, H, s_pad,
+                                       float(q_scale), _stream())
+    _lib.check(st, "opb_attention_bwd")
+    _count(3)
+    return dqkv
+
+
+def relpos_bias_bwd(dbias, bucket, dtable, S):
+    H, s_pad = dbias.shape[0], dbias.shape[-1]
+    st = _lib.load().opb_relpos_bias_bwd(dbias.data_ptr(), bucket.data_ptr(), dtable.data_ptr(), S, s_pad, H, bucket.stride(0),
+                                         _stream())
+    _lib.check(st, "opb_relpos_bias_bwd")
+    _count()
+    return dtable
+
+
+def batch_sum(x, out, B, n, ld, accumulate=False):
+    """out[c] (+)= sum_b x[b * ld + c], c < n (x is addressed through its data pointer: pass a view of the first row)"""
+    st = _lib.load().opb_batch_sum_f32(x.data_ptr(), ld, out.data_ptr(), B, n, int(accumulate), _stream())
+    _lib.check(st, "opb_batch_sum_f32")
+    _count()
+    return out
+
+
+def l2_normalize_bwd(x, dy, want_f32=False):
+    """x fp32 [rows, D] (the un-normalised rows), dy fp32 -> bf16 dx (and fp32 when asked)"""
+    rows, D = x.shape
+    dx16 = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+    dx32 = torch.empty(rows, D, dtype=torch.float32, device=x.device) if want_f32 else None
+    st = _lib.load().opb_l2_normalize_bwd(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), _ptr(dx32), dx16.data_ptr(),
+                                          rows, D, _stream())
+    _lib.check(st, "opb_l2_normalize_bwd")
+    _count()
+    return (dx16, dx32) if want_f32 else dx16
+
+
+def text_embed_bwd(dx, tokens, dtable, dpos, dcls, pad_idx=1):
+    B, T = tokens.shape
+    D = dx.shape[-1]
+    st = _lib.load().opb_text_embed_bwd(dx.data_ptr(), tokens.data_ptr(), dtable.data_ptr(), dpos.data_ptr(), dcls.data_ptr(),
+                                        B, T, D, pad_idx, _stream())
+    _lib.check(st, "opb_text_embed_bwd")
+    _count()

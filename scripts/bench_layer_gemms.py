@@ -23,9 +23,18 @@ part = torch.empty(96 * M * 2, device=dev)
 tail_ws = torch.empty(256 * d, device=dev)
 names = ["qkv", "out_proj", "geglu", "fc2"]
 flops = [2.0 * M * 3 * d * d, 2.0 * M * d * d, 2.0 * M * 2 * F * d, 2.0 * M * d * F]
+VARIANT = os.environ.get("OPB_EXP", "")
+plain_out = [torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev), torch.empty(M, d, dtype=torch.bfloat16, device=dev),
+             torch.empty(M, 2 * F, dtype=torch.bfloat16, device=dev), torch.empty(M, d, dtype=torch.bfloat16, device=dev)]
 def layer(i, evs=None):
     wq, wo, w01, w2 = W[i % NL]
-    calls = [lambda: K.gemm_ln(xb, wq, K.EPI_STORE_BF16, qkv, ln_mu=mu, ln_rstd=rs, ln_colsum=c3, bias=b3, colscale=s3),
+    if VARIANT == "plain":       # same mainloops, bare bf16-store epilogue (no LN / bias / GELU / residual): epilogue cost probe
+        calls = [lambda: K.gemm_ln(xb, wq, K.EPI_STORE_BF16, plain_out[0]),
+                 lambda: K.gemm_ln(o, wo, K.EPI_STORE_BF16, plain_out[1]),
+                 lambda: K.gemm_ln(xb, w01, K.EPI_STORE_BF16, plain_out[2]),
+                 lambda: K.gemm_ln(u, w2, K.EPI_STORE_BF16, plain_out[3])]
+    else:
+      calls = [lambda: K.gemm_ln(xb, wq, K.EPI_STORE_BF16, qkv, ln_mu=mu, ln_rstd=rs, ln_colsum=c3, bias=b3, colscale=s3),
              lambda: K.gemm_ln(o, wo, K.EPI_RESID_F32, x, ln_mu=mu, ln_rstd=rs, ln_colsum=c1, bias=b1, gamma=g1, resid=x, stats_out=part, out_bf16=xb2, workspace=tail_ws),
              lambda: K.gemm_ln(xb, w01, K.EPI_GEGLU_BF16, u, ln_mu=mu, ln_rstd=rs, ln_colsum=c2, bias=b2, stats_out=part),
              lambda: K.gemm_ln(u, w2, K.EPI_RESID_F32, x, ln_mu=mu, ln_rstd=rs, ln_colsum=c1, bias=b1, gamma=g1, resid=x, stats_out=part, out_bf16=xb2, workspace=tail_ws)]
@@ -72,4 +81,4 @@ for k in range(4):
     ms = sum(a.elapsed_time(b) for a, b in revs[k][20:]) / len(revs[k][20:]); rtot += ms
     rout.append(f"{names[k]} {ms*1000:.0f}us {flops[k]/ms/1e9:.0f}TF")
 print("cuBLAS (no epilogue): " + " | ".join(rout) + f" | layer {rtot*1000:.0f}us ({sum(flops)/rtot/1e9:.0f} TF)")
-print(f"mode={os.environ.get('OPB_GEMM_TMA_EPILOGUE','-')}: " + " | ".join(out) + f" | layer {tot*1000:.0f}us ({sum(flops)/tot/1e9:.0f} TF) wall/layer {t0.elapsed_time(t1)/120*1000:.0f}us")
+print(f"mode={os.environ.get('OPB_GEMM_TMA_EPILOGUE','-')} exp={VARIANT or '-'}: " + " | ".join(out) + f" | layer {tot*1000:.0f}us ({sum(flops)/tot/1e9:.0f} TF) wall/layer {t0.elapsed_time(t1)/120*1000:.0f}us")
