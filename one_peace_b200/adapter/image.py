@@ -123,6 +123,8 @@ class ImageAdapter(torch.nn.Module):
         """-> (x fp32 (B, w*w+1, d), None (images are never padded), [bias (H,S,S_pad)])"""
         if preserve_ids is not None or preserve_embed is not None:
             raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            return self.forward_train(src_images)
         p = self._pack()
         B, _, R, _ = src_images.shape
         d, c4 = self.embed_dim, self.embed_dim // 4
@@ -147,4 +149,27 @@ class ImageAdapter(torch.nn.Module):
                out_group_stride=S, out_row_offset=1, resid_period=w * w, resid_row_offset=1)
         K.cls_row_init(p["cls"], pos, x)
         bias = self.get_rel_pos_bias(S) if self.rel_pos_table_list is not None else None
+        return x, None, bias
+
+    def forward_train(self, src_images):
+        """Same outputs, recorded for autograd (autograd.ImageEmbedFn / RelPosBiasFn); the positional table is resized
+        by torch ops so its gradient reaches pos_embed through torch's own bicubic adjoint (parameter preprocessing)."""
+        from ..autograd import ImageEmbedFn, RelPosBiasFn
+        R = src_images.shape[-1]
+        w = R // 16
+        S = w * w + 1
+        if self.rel_pos_table_list is not None and S != self.rp_bucket.shape[0]:
+            raise RuntimeError("image size must match rel_bucket_size * 16 (one_peace_retrieval.py:128)")
+        pe = self.pos_embed
+        if w != self.bucket_size:
+            old = pe[1:].reshape(1, self.bucket_size, self.bucket_size, -1).permute(0, 3, 1, 2).float()
+            new = F.interpolate(old, size=(w, w), mode="bicubic").type_as(pe)
+            pe = torch.cat([pe[:1], new.permute(0, 2, 3, 1).reshape(w * w, -1)], dim=0)
+        e = self.embed_images
+        x = ImageEmbedFn.apply(src_images, pe, e[0].weight, e[0].bias, e[1].layer_norm.weight, e[1].layer_norm.bias,
+                               e[3].weight, e[3].bias, e[4].layer_norm.weight, e[4].layer_norm.bias, e[6].weight, e[6].bias,
+                               self.cls_embedding)
+        bias = None
+        if self.rel_pos_table_list is not None:
+            bias = [RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads) for t in self.rel_pos_table_list]
         return x, None, bias

@@ -82,10 +82,23 @@ class TextAdapter(torch.nn.Module):
         """-> (x fp32 (B,T+1,d) with padded rows zeroed, padding_mask uint8 (B,T+1), [bias (H,S,S_pad)])"""
         if preserve_ids is not None or preserve_embed is not None:
             raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            return self.forward_train(src_tokens)
         p = self._pack()
         table = self.embed_tokens.weight.detach()
         if table.dtype not in (torch.float32, torch.bfloat16):
             table = table.float()
         x, pad = K.text_embed(src_tokens.contiguous(), table, p["pos"], p["cls"], self.padding_idx)
         bias = self.get_rel_pos_bias(src_tokens.size(1) + 1) if self.rel_pos_table_list is not None else None
+        return x, pad, bias
+
+    def forward_train(self, src_tokens):
+        """Same outputs, recorded for autograd: the bias list holds dense (H,S,S_pad) tensors (autograd.RelPosBiasFn)."""
+        from ..autograd import RelPosBiasFn, TextEmbedFn
+        x, pad = TextEmbedFn.apply(src_tokens, self.embed_tokens.weight, self.embed_positions.weight, self.cls_embedding,
+                                   self.padding_idx)
+        bias = None
+        if self.rel_pos_table_list is not None:
+            S = src_tokens.size(1) + 1
+            bias = [RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads) for t in self.rel_pos_table_list]
         return x, pad, bias

@@ -1,0 +1,370 @@
+"""Training path: hand-written backward of the modality-shared encoder, wired into ``torch.autograd``.
+
+The reference trains through torch autograd (transformer_layer.py:165-228, multihead_attention.py:103-126, with
+``checkpoint_activations`` in the 4B recipes).  Here every adjoint is an sm_100a kernel behind the C-ABI
+(csrc/backward.cu, csrc/attention_bwd.cu + the tcgen05 GEMM for all dX / dW products); autograd only carries the
+graph edges between five ``Function`` nodes:
+
+    TextEmbedFn / ImageEmbedFn  ->  EncoderStackFn (L layers, activation recompute)  ->  HeadFn  ->  criterion
+    RelPosBiasFn (table -> dense (H,S,S_pad) bias, shared by the layers) ----^
+
+Activation policy = the reference's checkpointing: the forward keeps only each layer's fp32 input rows; the backward
+re-runs one layer forward (un-fused LayerNorm form, so the normalised operands the dW GEMMs need exist in HBM) and
+walks its adjoint.  dW = dY^T X is an M-reduction: both operands are transposed to K-major by the transpose kernel
+and go through the same TMA + tcgen05 GEMM as everything else.
+"""
+import torch
+
+from . import kernels as K
+from .components import PackCache, bf16, f32
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _tr(x):
+    """bf16 [M, n] -> [n, pad8(M)]: K-major operand of an M-reduction GEMM (zero columns past M)."""
+    M, n = x.shape
+    if M % 8 == 0:
+        return K.transpose_bf16(x)
+    xp = torch.zeros(_pad8(M), n, dtype=x.dtype, device=x.device)
+    xp[:M].copy_(x)
+    return K.transpose_bf16(xp)
+
+
+def _dw(dy, x, dtype):
+    """dW [N, Kw] = dy[M, N]^T x[M, Kw]  (fp32 accumulate; stored in the parameter's dtype)."""
+    dyT, xT = _tr(dy), _tr(x)
+    out = torch.empty(dy.shape[1], x.shape[1], dtype=torch.float32 if dtype == torch.float32 else torch.bfloat16,
+                      device=dy.device)
+    K.gemm(dyT, xT, K.EPI_STORE_F32 if out.dtype == torch.float32 else K.EPI_STORE_BF16, out)
+    return out if out.dtype == dtype else out.to(dtype)
+
+
+def _dx(dy, wT, n_out):
+    """dX [M, n_out] = dy[M, N] W[N, n_out], with wT = W^T as a K-major [n_out, N] bf16 operand."""
+    out = torch.empty(dy.shape[0], n_out, dtype=torch.bfloat16, device=dy.device)
+    K.gemm(dy, wT, K.EPI_STORE_BF16, out)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# one encoder layer
+# ----------------------------------------------------------------------------------------------------------------
+LAYER_PARAM_NAMES = ("q_proj.weight", "q_proj.bias", "k_proj.weight", "v_proj.weight", "v_proj.bias", "out_proj.weight",
+                     "out_proj.bias", "ln.weight", "ln.bias", "self_attn_layer_norm.weight", "self_attn_layer_norm.bias",
+                     "final_layer_norm.weight", "final_layer_norm.bias", "gamma_1", "gamma_2", "wi_0.weight", "wi_1.weight",
+                     "ffn_ln.weight", "ffn_ln.bias", "fc2.weight", "fc2.bias")
+
+
+def layer_params(layer, modality):
+    """The 21 parameters of one layer on the `modality` path, in LAYER_PARAM_NAMES order."""
+    a = layer.self_attn
+    ffn = getattr(layer, f"{modality}_ffn")
+    if a.ln is None or layer.gamma_1 is None or not isinstance(ffn[2], torch.nn.LayerNorm) or layer.attn_ln is not None \
+            or a.c_attn is not None:
+        raise NotImplementedError("the backward pass is built for the 4B layer structure (magneto_scale_attn, scale_fc, "
+                                  "use_layer_scale on; scale_attn, scale_heads off — finetune_3B.yaml:114-132)")
+    return [a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.v_proj.weight, a.v_proj.bias, a.out_proj.weight,
+            a.out_proj.bias, a.ln.weight, a.ln.bias, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias,
+            layer.final_layer_norm.weight, layer.final_layer_norm.bias, layer.gamma_1, layer.gamma_2, ffn[0].wi_0.weight,
+            ffn[0].wi_1.weight, ffn[2].weight, ffn[2].bias, ffn[3].weight, ffn[3].bias]
+
+
+def layer_train_pack(layer, modality):
+    """bf16 operands of the layer in both orientations (W for the forward / dW, W^T for dX), rebuilt after each
+    optimizer step."""
+    cache = layer._cache.setdefault("_train_" + modality, PackCache())
+    ps = layer_params(layer, modality)
+
+    def build():
+        d = layer.embed_dim
+        dev = ps[0].device
+        wqkv = torch.cat([bf16(ps[0]), bf16(ps[2]), bf16(ps[3])], 0).contiguous()
+        bqkv = torch.cat([f32(ps[1]), torch.zeros(d, device=dev), f32(ps[4])]).contiguous()
+        qs = torch.ones(3 * d, device=dev)
+        qs[:d] = layer.self_attn.scaling
+        wo = bf16(ps[5])
+        w01 = torch.cat([bf16(ps[15]), bf16(ps[16])], 0).contiguous()      # [g | l] halves, not tile-interleaved
+        w2 = bf16(ps[19])
+        return dict(wqkv=wqkv, wqkvT=K.transpose_bf16(wqkv), bqkv=bqkv, qscale=qs, wo=wo, woT=K.transpose_bf16(wo),
+                    bo=f32(ps[6]), lni_w=f32(ps[7]), lni_b=f32(ps[8]), ln1_w=f32(ps[9]), ln1_b=f32(ps[10]),
+                    ln2_w=f32(ps[11]), ln2_b=f32(ps[12]), g1=f32(ps[13]), g2=f32(ps[14]), w01=w01,
+                    w01T=K.transpose_bf16(w01), lnf_w=f32(ps[17]), lnf_b=f32(ps[18]), w2=w2, w2T=K.transpose_bf16(w2),
+                    b2=f32(ps[20]))
+    return cache.get(ps, build)
+
+
+def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep):
+    """x fp32 [M, d] -> (x_out fp32 [M, d], saved activations or None).  Un-fused LayerNorm form of
+    transformer_layer.py:165-228; `row_scale` [M] = drop-path keep mask / keep_prob (:80-86) or None."""
+    p = layer_train_pack(layer, modality)
+    d, F_, H = layer.embed_dim, layer.ffn_embed_dim, layer.self_attn.num_heads
+    M = B * S
+    dev = x.device
+
+    def e(n):
+        return torch.empty(M, n, dtype=torch.bfloat16, device=dev)
+    h1 = K.layernorm(x, p["ln1_w"], p["ln1_b"], e(d), eps=layer.self_attn_layer_norm.eps)
+    qkv = K.gemm(h1, p["wqkv"], K.EPI_STORE_BF16, e(3 * d), bias=p["bqkv"], colscale=p["qscale"])
+    lse = torch.empty(B * H * S, dtype=torch.float32, device=dev)
+    att = K.attention(qkv, bias, key_pad, B, S, H, out=e(d), lse=lse)
+    a2 = K.layernorm(att, p["lni_w"], p["lni_b"], e(d), eps=layer.self_attn.ln.eps)
+    o = K.gemm(a2, p["wo"], K.EPI_STORE_BF16, e(d), bias=p["bo"])
+    x2 = K.scale_resid_fwd(x, o, p["g1"], row_scale, torch.empty_like(x))
+    h2 = K.layernorm(x2, p["ln2_w"], p["ln2_b"], e(d), eps=layer.final_layer_norm.eps)
+    gl = K.gemm(h2, p["w01"], K.EPI_STORE_BF16, e(2 * F_))
+    u = K.geglu_fwd(gl, e(F_))
+    u2 = K.layernorm(u, p["lnf_w"], p["lnf_b"], e(F_), eps=1e-5)
+    f = K.gemm(u2, p["w2"], K.EPI_STORE_BF16, e(d), bias=p["b2"])
+    x3 = K.scale_resid_fwd(x2, f, p["g2"], row_scale, torch.empty_like(x))
+    saved = dict(h1=h1, qkv=qkv, lse=lse, att=att, a2=a2, o=o, x2=x2, h2=h2, gl=gl, u=u, u2=u2, f=f) if keep else None
+    return x3, saved
+
+
+def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_scale):
+    """Adjoint of layer_forward_train.  `dx` (fp32 [M, d]) holds dL/dx_out on entry and dL/dx_in on return (in place);
+    `dbias` (fp32 (H,S,S_pad) or None) accumulates the relative-position-bias gradient.  Returns the 21 parameter
+    gradients in LAYER_PARAM_NAMES order, in each parameter's dtype."""
+    p = layer_train_pack(layer, modality)
+    ps = layer_params(layer, modality)
+    d, F_, H = layer.embed_dim, layer.ffn_embed_dim, layer.self_attn.num_heads
+    M = B * S
+    dev = x.device
+
+    def e(n):
+        return torch.empty(M, n, dtype=torch.bfloat16, device=dev)
+
+    def g(n):
+        return torch.empty(n, dtype=torch.float32, device=dev)
+    # ---- FFN branch: x3 = x2 + rs * g2 * f ----
+    dg2, db2 = g(d), g(d)
+    df = K.scale_resid_bwd(dx, s["f"], p["g2"], row_scale, e(d), dgamma=dg2, dbias=db2)
+    dW2 = _dw(df, s["u2"], ps[19].dtype)
+    du2 = _dx(df, p["w2T"], F_)
+    dlnf_w, dlnf_b = g(F_), g(F_)
+    du = K.layernorm_bwd(s["u"], du2, p["lnf_w"], p["lnf_b"], e(F_), eps=1e-5, dgamma=dlnf_w, dbeta=dlnf_b)
+    dgl = K.geglu_bwd(s["gl"], du, e(2 * F_))
+    dW01 = _dw(dgl, s["h2"], ps[15].dtype)
+    dh2 = _dx(dgl, p["w01T"], d)
+    dln2_w, dln2_b = g(d), g(d)
+    K.layernorm_bwd(s["x2"], dh2, p["ln2_w"], p["ln2_b"], dx, eps=layer.final_layer_norm.eps, accumulate=True,
+                    dgamma=dln2_w, dbeta=dln2_b)                                   # dx = dL/dx2
+    # ---- attention branch: x2 = x + rs * g1 * o ----
+    dg1, dbo = g(d), g(d)
+    do = K.scale_resid_bwd(dx, s["o"], p["g1"], row_scale, e(d), dgamma=dg1, dbias=dbo)
+    dWo = _dw(do, s["a2"], ps[5].dtype)
+    da2 = _dx(do, p["woT"], d)
+    dlni_w, dlni_b = g(d), g(d)
+    datt = K.layernorm_bwd(s["att"], da2, p["lni_w"], p["lni_b"], e(d), eps=layer.self_attn.ln.eps, dgamma=dlni_w,
+                           dbeta=dlni_b)
+    dqkv = K.attention_bwd(s["qkv"], s["att"], datt, bias, key_pad, s["lse"], e(3 * d), dbias, B, S, H,
+                           layer.self_attn.scaling)
+    dbqkv = K.colsum(dqkv, g(3 * d))
+    dWqkv = _dw(dqkv, s["h1"], ps[0].dtype)
+    dh1 = _dx(dqkv, p["wqkvT"], d)
+    dln1_w, dln1_b = g(d), g(d)
+    K.layernorm_bwd(x, dh1, p["ln1_w"], p["ln1_b"], dx, eps=layer.self_attn_layer_norm.eps, accumulate=True,
+                    dgamma=dln1_w, dbeta=dln1_b)                                   # dx = dL/dx
+    grads = [dWqkv[:d], dbqkv[:d], dWqkv[d:2 * d], dWqkv[2 * d:], dbqkv[2 * d:], dWo, dbo, dlni_w, dlni_b, dln1_w, dln1_b,
+             dln2_w, dln2_b, dg1, dg2, dW01[:F_], dW01[F_:], dlnf_w, dlnf_b, dW2, db2]
+    return [gr if gr.dtype == prm.dtype else gr.to(prm.dtype) for gr, prm in zip(grads, ps)]
+
+
+class EncoderStackFn(torch.autograd.Function):
+    """x0 [M, d] fp32 -> x_L [M, d] fp32 through all layers (transformer_encoder.py:172-188)."""
+
+    @staticmethod
+    def forward(ctx, encoder, meta, x0, n_bias, *tensors):
+        B, S, modality, key_pad = meta
+        biases = list(tensors[:n_bias])
+        layers = list(encoder.layers)
+        x = x0.contiguous()
+        xs, scales = [], []
+        for i, layer in enumerate(layers):
+            bias = None if n_bias == 0 else (biases[0] if n_bias == 1 else biases[i])
+            rs = None
+            if layer.training and layer.drop_path_prob > 0:
+                # per-sample keep mask / keep_prob, one value per batch column (transformer_layer.py:80-86)
+                keep = 1.0 - layer.drop_path_prob
+                rs = ((torch.rand(B, device=x.device) < keep).float() / keep).repeat_interleave(S).contiguous()
+            if layer.training and layer.dropout_prob > 0:
+                raise NotImplementedError("dropout > 0 (every ONE-PEACE recipe trains with dropout 0.0)")
+            xs.append(x)
+            scales.append(rs)
+            x, _ = layer_forward_train(layer, x, bias, key_pad, B, S, modality, rs, keep=False)
+        ctx.encoder, ctx.meta, ctx.n_bias = encoder, meta, n_bias
+        ctx.xs, ctx.scales, ctx.biases = xs, scales, biases
+        return x
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, S, modality, key_pad = ctx.meta
+        layers = list(ctx.encoder.layers)
+        n_bias, biases = ctx.n_bias, ctx.biases
+        dx = grad_out.to(torch.float32).contiguous().clone()
+        dbiases = [torch.zeros_like(b) for b in biases]
+        grads = [None] * len(layers)
+        for i in reversed(range(len(layers))):
+            layer = layers[i]
+            bias = None if n_bias == 0 else (biases[0] if n_bias == 1 else biases[i])
+            dbias = None if n_bias == 0 else (dbiases[0] if n_bias == 1 else dbiases[i])
+            _, saved = layer_forward_train(layer, ctx.xs[i], bias, key_pad, B, S, modality, ctx.scales[i], keep=True)
+            grads[i] = layer_backward(layer, ctx.xs[i], saved, dx, bias, dbias, key_pad, B, S, modality, ctx.scales[i])
+            ctx.xs[i] = None
+        flat = [g for lg in grads for g in lg]
+        return (None, None, dx, None, *dbiases, *flat)
+
+
+def run_encoder_stack(encoder, x, bias_list, key_pad, modality):
+    """x fp32 [B, S, d] (autograd-tracked) -> fp32 [B, S, d]."""
+    B, S, d = x.shape
+    params = [p for layer in encoder.layers for p in layer_params(layer, modality)]
+    biases = list(bias_list) if bias_list else []
+    out = EncoderStackFn.apply(encoder, (B, S, modality, key_pad), x.reshape(B * S, d), len(biases), *biases, *params)
+    return out.view(B, S, d)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# relative-position bias, heads, adapters
+# ----------------------------------------------------------------------------------------------------------------
+class RelPosBiasFn(torch.autograd.Function):
+    """rel_pos_table.weight [NB, H] -> dense fp32 (H, S, S_pad) bias (adapter/text.py:84-91, image.py:164-171)."""
+
+    @staticmethod
+    def forward(ctx, table, bucket, S, H):
+        ctx.bucket, ctx.S, ctx.shape, ctx.dtype = bucket, S, table.shape, table.dtype
+        return K.relpos_bias_build(f32(table), bucket, S, H)
+
+    @staticmethod
+    def backward(ctx, dbias):
+        dtable = torch.zeros(ctx.shape, dtype=torch.float32, device=dbias.device)
+        K.relpos_bias_bwd(dbias.contiguous(), ctx.bucket, dtable, ctx.S)
+        return dtable.to(ctx.dtype), None, None, None
+
+
+class HeadFn(torch.autograd.Function):
+    """CLS row -> modality LayerNorm -> *_proj -> F.normalize (one_peace_retrieval.py:107-119)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, b, eps):
+        B, S, d = x.shape
+        x = x.contiguous()
+        cls = torch.empty(B, d, dtype=torch.bfloat16, device=x.device)
+        K.layernorm(x, f32(ln_w), f32(ln_b), cls, rows=B, dim=d, ld_in=S * d, ld_out=d, eps=eps)
+        logits = torch.empty(B, w.shape[0], dtype=torch.float32, device=x.device)
+        K.gemm(cls, bf16(w), K.EPI_STORE_F32, logits, bias=f32(b))
+        ctx.save_for_backward(x, ln_w, ln_b, w, b, cls, logits)
+        ctx.eps = eps
+        return K.l2_normalize_rows(logits)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ln_w, ln_b, w, b, cls, logits = ctx.saved_tensors
+        B, S, d = x.shape
+        dlog = K.l2_normalize_bwd(logits, dy.to(torch.float32).contiguous())
+        db = K.colsum(dlog, torch.empty(w.shape[0], dtype=torch.float32, device=x.device))
+        dW = _dw(dlog, cls, w.dtype)
+        dcls = _dx(dlog, K.transpose_bf16(bf16(w)), d)
+        dxf = torch.zeros_like(x)
+        dg = torch.empty(d, dtype=torch.float32, device=x.device)
+        dbt = torch.empty(d, dtype=torch.float32, device=x.device)
+        K.layernorm_bwd(x, dcls, f32(ln_w), f32(ln_b), dxf, eps=ctx.eps, dgamma=dg, dbeta=dbt, rows=B, dim=d, ldx=S * d,
+                        ld_dx=S * d)
+        return dxf, dg.to(ln_w.dtype), dbt.to(ln_b.dtype), dW, db.to(b.dtype), None
+
+
+class TextEmbedFn(torch.autograd.Function):
+    """tokens -> x [B, T+1, d] fp32 with padded rows zeroed (adapter/text.py:125-129,144-146,153)."""
+
+    @staticmethod
+    def forward(ctx, tokens, table, pos, cls, pad_idx):
+        tab = table.detach()
+        if tab.dtype not in (torch.float32, torch.bfloat16):
+            tab = tab.float()
+        x, pad = K.text_embed(tokens.contiguous(), tab.contiguous(), f32(pos), f32(cls).view(-1), pad_idx)
+        ctx.save_for_backward(tokens)
+        ctx.pad_idx = pad_idx
+        ctx.meta = (table.shape, table.dtype, pos.shape, pos.dtype, cls.shape, cls.dtype)
+        ctx.mark_non_differentiable(pad)
+        return x, pad
+
+    @staticmethod
+    def backward(ctx, dx, _dpad):
+        (tokens,) = ctx.saved_tensors
+        tshape, tdt, pshape, pdt, cshape, cdt = ctx.meta
+        dev = dx.device
+        dtable = torch.zeros(tshape, dtype=torch.float32, device=dev)
+        dpos = torch.zeros(pshape, dtype=torch.float32, device=dev)
+        dcls = torch.zeros(cshape[-1], dtype=torch.float32, device=dev)
+        K.text_embed_bwd(dx.to(torch.float32).contiguous(), tokens.contiguous(), dtable, dpos, dcls, ctx.pad_idx)
+        return None, dtable.to(tdt), dpos.to(pdt), dcls.view(cshape).to(cdt), None
+
+
+class ImageEmbedFn(torch.autograd.Function):
+    """hMLP stem + CLS + positions (adapter/image.py:66-75,239-253) as three patch GEMMs; `pos` [S, d] is the
+    (possibly bicubic-resized, by torch autograd) positional table."""
+
+    @staticmethod
+    def forward(ctx, img, pos, w1, b1, ln1w, ln1b, w2, b2, ln2w, ln2b, w3, b3, cls):
+        B, _, R, _ = img.shape
+        d = w3.shape[0]
+        c4 = w1.shape[0]
+        g1, g2, w = R // 4, R // 8, R // 16
+        S = w * w + 1
+        dev = img.device
+        pk = dict(w1=bf16(w1.reshape(c4, 48)), w2=bf16(w2.permute(0, 2, 3, 1).reshape(c4, 4 * c4)),
+                  w3=bf16(w3.permute(0, 2, 3, 1).reshape(d, 4 * c4)))
+        im = img if img.dtype in (torch.float32, torch.bfloat16) else img.float()
+        a1 = K.image_patchify4(im.contiguous())
+        y1 = K.gemm(a1, pk["w1"], K.EPI_STORE_BF16, torch.empty(B * g1 * g1, c4, dtype=torch.bfloat16, device=dev), bias=f32(b1))
+        a2 = K.layernorm(y1, f32(ln1w), f32(ln1b), torch.empty(B * g2 * g2, 4 * c4, dtype=torch.bfloat16, device=dev),
+                         gelu=True, merge_grid_w=g1)
+        y2 = K.gemm(a2, pk["w2"], K.EPI_STORE_BF16, torch.empty(B * g2 * g2, c4, dtype=torch.bfloat16, device=dev), bias=f32(b2))
+        a3 = K.layernorm(y2, f32(ln2w), f32(ln2b), torch.empty(B * w * w, 4 * c4, dtype=torch.bfloat16, device=dev),
+                         gelu=True, merge_grid_w=g2)
+        posf = f32(pos)
+        x = torch.empty(B, S, d, dtype=torch.float32, device=dev)
+        K.gemm(a3, pk["w3"], K.EPI_RESID_F32, x.view(B * S, d), bias=f32(b3), resid=posf, out_group=w * w,
+               out_group_stride=S, out_row_offset=1, resid_period=w * w, resid_row_offset=1)
+        K.cls_row_init(f32(cls).view(-1), posf, x)
+        ctx.save_for_backward(im, ln1w, ln1b, ln2w, ln2b, w1, w2, w3, y1, a2, y2, a3)
+        ctx.pk = pk
+        ctx.meta = (B, R, d, c4, pos.dtype, b1.dtype, cls.shape, cls.dtype)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        im, ln1w, ln1b, ln2w, ln2b, w1, w2, w3, y1, a2, y2, a3 = ctx.saved_tensors
+        B, R, d, c4, pos_dt, b_dt, cls_shape, cls_dt = ctx.meta
+        g1, g2, w = R // 4, R // 8, R // 16
+        S = w * w + 1
+        dev = dx.device
+        pk = ctx.pk
+        dx = dx.to(torch.float32).contiguous()
+
+        def g(n):
+            return torch.empty(n, dtype=torch.float32, device=dev)
+        dcls = K.batch_sum(dx, g(d), B, d, S * d)
+        dpos = K.batch_sum(dx, torch.empty(S, d, dtype=torch.float32, device=dev), B, S * d, S * d)
+        db3 = g(d)
+        dy3 = K.scale_resid_bwd(dx, None, None, None, torch.empty(B * w * w, d, dtype=torch.bfloat16, device=dev), dbias=db3,
+                                in_period=S, in_valid=w * w, in_shift=1)
+        dW3 = _dw(dy3, a3, w3.dtype).view(d, 2, 2, c4).permute(0, 3, 1, 2)
+        da3 = _dx(dy3, K.transpose_bf16(pk["w3"]), 4 * c4)
+        dln2w, dln2b = g(c4), g(c4)
+        dy2 = K.layernorm_bwd(y2, da3, f32(ln2w), f32(ln2b), torch.empty_like(y2), gelu=True, dgamma=dln2w, dbeta=dln2b,
+                              dy_merge_w=g2)
+        db2 = K.colsum(dy2, g(c4))
+        dW2 = _dw(dy2, a2, w2.dtype).view(c4, 2, 2, c4).permute(0, 3, 1, 2)
+        da2 = _dx(dy2, K.transpose_bf16(pk["w2"]), 4 * c4)
+        dln1w, dln1b = g(c4), g(c4)
+        dy1 = K.layernorm_bwd(y1, da2, f32(ln1w), f32(ln1b), torch.empty_like(y1), gelu=True, dgamma=dln1w, dbeta=dln1b,
+                              dy_merge_w=g1)
+        db1 = K.colsum(dy1, g(c4))
+        a1 = K.image_patchify4(im)
+        dW1 = _dw(dy1, a1, w1.dtype).view(c4, 3, 4, 4)
+        return (None, dpos.to(pos_dt), dW1, db1.to(b_dt), dln1w.to(ln1w.dtype), dln1b.to(ln1b.dtype), dW2.contiguous(),
+                db2.to(b_dt), dln2w.to(ln2w.dtype), dln2b.to(ln2b.dtype), dW3.contiguous(), db3.to(b_dt),
+                dcls.view(cls_shape).to(cls_dt))

@@ -62,10 +62,8 @@ class OnePeaceRetrievalModel(OnePeaceBaseModel):
         if encoder_type not in ("text", "image", "audio"):
             raise NotImplementedError
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # The encoder backward kernels are not built yet: refuse rather than return a graph-less tensor
-            # that would silently train nothing.
-            raise NotImplementedError("encoder backward is not implemented yet: call under torch.no_grad() "
-                                      "(hub_interface.extract_*_features does)")
+            return self.forward_train(encoder_type, src_tokens=src_tokens, src_images=src_images, src_audios=src_audios,
+                                      audio_padding_masks=audio_padding_masks)
         cls = self.encoder_wrapper.encode_cls(encoder_type, src_tokens=src_tokens, src_images=src_images,
                                               src_audios=src_audios, audio_padding_masks=audio_padding_masks)
         w, b = self._proj_pack(encoder_type)
@@ -73,6 +71,19 @@ class OnePeaceRetrievalModel(OnePeaceBaseModel):
         K.gemm(cls, w, K.EPI_STORE_F32, logits, bias=b)
         out = K.l2_normalize_rows(logits)
         return out.to(getattr(self, f"{encoder_type}_proj").weight.dtype)
+
+    def forward_train(self, encoder_type, **inputs):
+        """Training forward: the same kernels recorded as autograd nodes (one_peace_b200/autograd.py)."""
+        from ..autograd import HeadFn
+        if encoder_type == "audio":
+            raise NotImplementedError("audio-branch backward (wav2vec feature extractor + conv positions) is not built yet")
+        ew = self.encoder_wrapper
+        info = ew.adapt(encoder_type, **inputs)
+        x, _ = ew.fusion_model.run_layers(info, encoder_type)
+        ln = getattr(ew.fusion_model, f"{encoder_type}_layer_norm")
+        proj = getattr(self, f"{encoder_type}_proj")
+        out = HeadFn.apply(x, ln.weight, ln.bias, proj.weight, proj.bias, ln.eps)
+        return out.to(proj.weight.dtype)
 
     @classmethod
     def build_model(cls, cfg, task):

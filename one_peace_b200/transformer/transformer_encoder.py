@@ -50,6 +50,11 @@ class TransformerEncoder(FairseqEncoder):
         key_pad = None
         if pad is not None:
             key_pad = pad.to(torch.uint8).contiguous()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.layers.parameters())):
+            # training: hand-written backward behind torch.autograd (one_peace_b200/autograd.py); bias_list holds dense
+            # (H,S,S_pad) tensors here
+            from ..autograd import run_encoder_stack
+            return run_encoder_stack(self, x, bias_list, key_pad, encoder_type), pad
         rows = x.view(B * S, d)
         fused = os.environ.get("OPB_FUSED_LN", "1") != "0" and all(l.fused_ln_supported() for l in self.layers)
         if fused:
@@ -71,6 +76,9 @@ class TransformerEncoder(FairseqEncoder):
             raise NotImplementedError("return_all_hiddens is only used by the segmentation/detection heads")
         info = {"text": text_info, "image": image_info, "audio": audio_info}.get(encoder_type)
         x, pad = self.run_layers(info, encoder_type)
+        if x.requires_grad:
+            raise NotImplementedError("per-token features with gradients (pretraining decoder / DCL path) are not built; "
+                                      "the retrieval heads train through OnePeaceRetrievalModel.forward")
         B, S, d = x.shape
         pk = self.final_norm_pack(encoder_type)
         if pk is not None:

@@ -145,7 +145,8 @@ def test_attention_bwd(K, B, S, H, pad, use_bias):
         err = relerr(dqkv[:, lo:lo + D], want[:, lo:lo + D])
         assert err < 1.5e-2, (name, err)
     if use_bias:
-        assert relerr(dbias[:, :, :S], br.grad[:, :, :S]) < 1e-3       # fp32 atomics of fp32 dS
+        # fp32 atomics of fp32 dS; delta = sum(dO * O) uses the bf16-rounded forward output (2^-9 per element)
+        assert relerr(dbias[:, :, :S], br.grad[:, :, :S]) < 1e-2
         if s_pad > S:
             assert torch.all(dbias[:, :, S:] == 0)
 

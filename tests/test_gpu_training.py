@@ -1,0 +1,116 @@
+"""GPU: the hand-written backward (one_peace_b200/autograd.py) vs torch autograd through the CPU fp32 oracle
+(oracle/restated.py) on the same seeded weights and inputs.
+
+Bars: every parameter gradient must point the same way as the oracle's (cosine >= 0.99 over the whole tensor) with
+a matching norm (within 3 %).  Activations and matmul operands are bf16 in the product path (2^-9 per rounding), so
+element-wise equality is not the bar; the training forward obeys the forward bars (cosine >= 0.999, InfoNCE loss 1e-3)."""
+import pytest
+import torch
+
+import restated as R
+import synth
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(embed_dim=256, ffn=1024, layers=2, heads=4)
+
+
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+
+
+def build_model(sd, head_type):
+    from one_peace_b200.one_peace.hub_interface import from_pretrained
+    hub = from_pretrained(state_dict=sd, head_type=head_type, layers=CFG["layers"], embed_dim=CFG["embed_dim"],
+                          ffn_embed_dim=CFG["ffn"], attention_heads=CFG["heads"], patch_image_size=224, device="cuda",
+                          dtype="float32")
+    return hub.model
+
+
+def oracle_grads(sd, modality, inp, proj_target):
+    cfg = R.OracleConfig(embed_dim=CFG["embed_dim"], ffn_embed_dim=CFG["ffn"], layers=CFG["layers"],
+                         attention_heads=CFG["heads"])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    kw = {"src_tokens": inp} if modality == "text" else {"src_images": inp}
+    emb = R.extract_features(sdg, cfg, modality, **kw)
+    loss = (emb * proj_target).sum()
+    loss.backward()
+    return emb.detach(), {k: v.grad for k, v in sdg.items() if v.is_floating_point() and v.grad is not None}
+
+
+def compare(model, want, min_cos=0.99, norm_tol=0.03):
+    worst = (1.0, None)
+    n = 0
+    for name, p in model.named_parameters():
+        if name not in want:
+            continue
+        w = want[name]
+        if w.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max() < 1e-6, name
+            continue
+        assert p.grad is not None, f"{name}: no gradient"
+        g = p.grad.float().cpu()
+        assert g.shape == w.shape, name
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), w.flatten(), dim=0).item()
+        ratio = (g.norm() / w.norm()).item()
+        if cos < worst[0]:
+            worst = (cos, name)
+        assert cos >= min_cos, (name, cos, ratio)
+        assert abs(ratio - 1) <= norm_tol, (name, cos, ratio)
+        n += 1
+    print(f"{n} parameter gradients compared; worst cosine {worst[0]:.5f} ({worst[1]})")
+    assert n > 20
+
+
+@pytest.mark.parametrize("modality", ["text", "image"])
+def test_encoder_backward_vs_oracle(modality):
+    need_gpu()
+    sd = synth.make_state_dict(**CFG, modalities=("text", "image"), seed=3)
+    tok, img, _, _ = synth.tiny_inputs(seed=5, n_text=8, n_img=2, n_audio=1)
+    inp = tok if modality == "text" else img
+    g = torch.Generator().manual_seed(9)
+    target = torch.randn(inp.shape[0], CFG["embed_dim"], generator=g)
+    want_emb, want = oracle_grads(sd, modality, inp, target)
+
+    model = build_model(sd, "vl")
+    model.train()
+    kw = {"src_tokens": inp.cuda()} if modality == "text" else {"src_images": inp.cuda()}
+    emb = model(encoder_type=modality, **kw)
+    assert emb.requires_grad
+    cos = torch.nn.functional.cosine_similarity(emb.detach().float().cpu(), want_emb).min().item()
+    assert cos >= 0.999, cos            # the training forward (un-fused LayerNorm form) obeys the forward bar
+    loss = (emb.float() * target.cuda()).sum()
+    loss.backward()
+    compare(model, want)
+    # parameters of the other modality's branch must be untouched
+    other = "image" if modality == "text" else "text"
+    for name, p in model.named_parameters():
+        if f"{other}_" in name:
+            assert p.grad is None, name
+
+
+def test_contrastive_step_backward_vs_oracle():
+    """Image-text InfoNCE through both encoders (criterions/image_text_retrieval_loss.py:55-112): loss and gradients."""
+    need_gpu()
+    from one_peace_b200.criterions.image_text_retrieval_loss import itc_loss
+    sd = synth.make_state_dict(**CFG, modalities=("text", "image"), seed=4)
+    tok, img, _, _ = synth.tiny_inputs(seed=6, n_text=8, n_img=8, n_audio=1)   # InfoNCE kernel: b % 8 == 0
+    cfg = R.OracleConfig(embed_dim=CFG["embed_dim"], ffn_embed_dim=CFG["ffn"], layers=CFG["layers"],
+                         attention_heads=CFG["heads"])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    te = R.extract_features(sdg, cfg, "text", src_tokens=tok)
+    ie = R.extract_features(sdg, cfg, "image", src_images=img)
+    want_loss, _, _ = R.itc_loss(ie, te, ie.detach(), te.detach(), R.logit_scale_exp(sdg["logit_scale"]), 0, 0.0)
+    want_loss.backward()
+    want = {k: v.grad for k, v in sdg.items() if v.is_floating_point() and v.grad is not None}
+
+    model = build_model(sd, "vl")
+    model.train()
+    t = model(src_tokens=tok.cuda(), encoder_type="text")
+    i = model(src_images=img.cuda(), encoder_type="image")
+    scale = model(return_logit_scale=True)
+    loss, _, _ = itc_loss(i, t, i.detach(), t.detach(), scale, 0, 0.0)
+    assert abs(loss.item() - want_loss.item()) <= 1e-3 * abs(want_loss.item()), (loss.item(), want_loss.item())
+    loss.backward()
+    compare(model, want, min_cos=0.985, norm_tol=0.04)
