@@ -54,6 +54,23 @@ def main():
         "text_layer0_out": l0,
     }, os.path.join(OUT, "tiny_retrieval.pt"))
 
+    # ---- gradients of the reference modules (torch autograd through the reference's own forward) ----
+    # Summaries only (norm, seeded random projection, first 256 elements per parameter): they pin the oracle's
+    # backward (tests/test_oracle_golden.py), which in turn checks the hand-written CUDA backward on the GPU.
+    for p in model.parameters():
+        p.requires_grad_(True)
+    gt = torch.Generator().manual_seed(100)
+    targets = dict(text=torch.randn(8, 256, generator=gt), image=torch.randn(2, 256, generator=gt))
+    grads = {}
+    for modality, kw in (("text", dict(src_tokens=tok[:8])), ("image", dict(src_images=img))):
+        model.zero_grad(set_to_none=True)
+        emb = model(encoder_type=modality, **kw)
+        (emb * targets[modality]).sum().backward()
+        grads[modality] = {n: synth.grad_summary(n, p.grad) for n, p in model.named_parameters() if p.grad is not None}
+    torch.save({"config": cfgd, "weights_seed": 0, "inputs_seed": 0, "targets_seed": 100, "n_text": 8, "grads": grads},
+               os.path.join(OUT, "tiny_train_grads.pt"))
+    model.zero_grad(set_to_none=True)
+
     # ---- contrastive head (criterion file executed as-is; single process: .data path) ----
     crit_mod = ref_stub.ref_module("one_peace.criterions.image_text_retrieval_loss")
     cases = []

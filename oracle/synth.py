@@ -128,3 +128,12 @@ def contrastive_pair(b, d, seed, noise=0.5):
     a = F.normalize(torch.randn(b, d, generator=g), dim=1)
     t = F.normalize(a + noise * F.normalize(torch.randn(b, d, generator=g), dim=1), dim=1)
     return a, t
+
+
+def grad_summary(name, g):
+    """Compact fingerprint of a gradient tensor: L2 norm, projection on a seeded random direction, first 256 values."""
+    import zlib
+    flat = g.detach().float().flatten()
+    r = torch.randn(flat.numel(), generator=torch.Generator().manual_seed(zlib.crc32(name.encode())))
+    return dict(shape=tuple(g.shape), norm=flat.norm().item(), proj=(flat * r).sum().item() / math.sqrt(flat.numel()),
+                head=flat[:256].clone())

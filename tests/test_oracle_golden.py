@@ -68,6 +68,34 @@ def test_extract_features(tiny, modality):
     torch.testing.assert_close(out.norm(dim=1), torch.ones(out.shape[0]), atol=1e-5, rtol=0)
 
 
+@pytest.mark.parametrize("modality", ["text", "image"])
+def test_backward_vs_reference_autograd(golden_dir, modality):
+    """torch autograd through the restatement == torch autograd through the reference's own modules
+    (tests/golden/tiny_train_grads.pt, written by oracle/make_golden.py): pins the oracle the CUDA backward is checked
+    against."""
+    fx = torch.load(os.path.join(golden_dir, "tiny_train_grads.pt"), weights_only=False)
+    sd = synth.make_state_dict(**fx["config"], seed=fx["weights_seed"])
+    tok, img, _, _ = synth.tiny_inputs(seed=fx["inputs_seed"])
+    gt = torch.Generator().manual_seed(fx["targets_seed"])
+    targets = dict(text=torch.randn(8, 256, generator=gt), image=torch.randn(2, 256, generator=gt))
+    cfg = R.OracleConfig(embed_dim=256, ffn_embed_dim=1024, layers=2, attention_heads=4)
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    kw = dict(src_tokens=tok[:fx["n_text"]]) if modality == "text" else dict(src_images=img)
+    (R.extract_features(sdg, cfg, modality, **kw) * targets[modality]).sum().backward()
+    want = fx["grads"][modality]
+    n = 0
+    for name, ref in want.items():
+        if ref["norm"] == 0:
+            continue
+        got = synth.grad_summary(name, sdg[name].grad)
+        assert got["shape"] == ref["shape"], name
+        assert abs(got["norm"] - ref["norm"]) <= 2e-4 * ref["norm"] + 1e-9, (name, got["norm"], ref["norm"])
+        assert abs(got["proj"] - ref["proj"]) <= 2e-4 * ref["norm"] + 1e-9, (name, got["proj"], ref["proj"])
+        torch.testing.assert_close(got["head"], ref["head"], rtol=2e-3, atol=2e-5 * ref["norm"] + 1e-9)
+        n += 1
+    assert n >= 45, n          # 2 layers x 21 + adapter + head parameters on the modality's path
+
+
 def test_itc_loss_and_grads(golden_dir):
     cases = torch.load(os.path.join(golden_dir, "itc_loss.pt"), weights_only=False)
     for c in cases:
