@@ -19,7 +19,7 @@ namespace {
 
 constexpr int kBwdThreads = 256;
 constexpr int kMaxGroups = 6;          // 4-column groups per thread: dim <= 6 * 256 * 4 = 6144
-constexpr int kBwdMaxBlocks = 148 * 4;
+constexpr int kBwdMaxBlocks = 148 * 8;
 
 OPB_DEVICE float gelu_grad(float z) {
   // d/dz [ z * Phi(z) ] = Phi(z) + z * phi(z)
@@ -51,6 +51,7 @@ OPB_DEVICE void store4(T* p, float4 v) {
 }
 
 // sums two values over the CTA; every thread gets both totals
+template <int THREADS>
 OPB_DEVICE float2 block_sum2(float a, float b, float2* red) {
   a = warp_sum(a);
   b = warp_sum(b);
@@ -60,30 +61,28 @@ OPB_DEVICE float2 block_sum2(float a, float b, float2* red) {
   __syncthreads();
   float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int w = 0; w < kBwdThreads / 32; ++w) { t.x += red[w].x; t.y += red[w].y; }
+  for (int w = 0; w < THREADS / 32; ++w) { t.x += red[w].x; t.y += red[w].y; }
   return t;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <typename TX, typename TDY, typename TDX>
-__global__ void __launch_bounds__(kBwdThreads)
+// One CTA per row (grid-stride); THREADS x GROUPS float4 column groups cover `dim`.  gamma / beta are re-read per row
+// (L1 hits) instead of living in registers: the kernel is HBM-bound and needs the occupancy (first version: 170
+// registers, one 256-thread CTA per SM, 8x off the HBM roofline).
+template <typename TX, typename TDY, typename TDX, int THREADS, int GROUPS>
+__global__ void __launch_bounds__(THREADS, (THREADS * GROUPS >= 1536) ? 2 : 4)
 layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__ dy, long ld_dy,
                      const float* __restrict__ gamma, const float* __restrict__ beta, TDX* __restrict__ dx, long ld_dx,
                      int accumulate, float* __restrict__ partial, int rows, int dim, float eps, int gelu,
                      int dy_merge_w) {
-  __shared__ float2 red[kBwdThreads / 32];
+  __shared__ float2 red[THREADS / 32];
   const int ngroups = dim >> 2;
-  float4 dg[kMaxGroups], db[kMaxGroups], gm[kMaxGroups], bt[kMaxGroups];
+  float4 dg[GROUPS], db[GROUPS];
 #pragma unroll
-  for (int k = 0; k < kMaxGroups; ++k) {
-    dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int g = threadIdx.x + k * kBwdThreads;
-    gm[k] = (g < ngroups && gamma != nullptr) ? *reinterpret_cast<const float4*>(gamma + 4 * g) : make_float4(1.f, 1.f, 1.f, 1.f);
-    bt[k] = (g < ngroups && beta != nullptr) ? *reinterpret_cast<const float4*>(beta + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int k = 0; k < GROUPS; ++k) dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_dim = 1.f / dim;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    float4 xv[kMaxGroups], gv[kMaxGroups];
+    float4 xv[GROUPS], gv[GROUPS];
     float s1 = 0.f;
     // the forward's 2x2 pixel-merge scatter (layernorm.cu, adapter/image.py:37-47): row (b, y, x) of the w x w grid
     // went to row (b, y/2, x/2), column block (y%2)*2 + x%2 of the next conv's operand
@@ -94,8 +93,8 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
       dyr = dy + ((static_cast<long>(bb) * (w / 2) + yy / 2) * (w / 2) + xx / 2) * ld_dy + ((yy & 1) * 2 + (xx & 1)) * dim;
     }
 #pragma unroll
-    for (int k = 0; k < kMaxGroups; ++k) {
-      const int g = threadIdx.x + k * kBwdThreads;
+    for (int k = 0; k < GROUPS; ++k) {
+      const int g = threadIdx.x + k * THREADS;
       if (g < ngroups) {
         xv[k] = load4(x + row * ldx + 4 * g);
         gv[k] = load4(dyr + 4 * g);
@@ -104,41 +103,43 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
         xv[k] = gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const float mean = block_sum2(s1, 0.f, red).x * inv_dim;
+    const float mean = block_sum2<THREADS>(s1, 0.f, red).x * inv_dim;
     float s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxGroups; ++k) {
-      const int g = threadIdx.x + k * kBwdThreads;
+    for (int k = 0; k < GROUPS; ++k) {
+      const int g = threadIdx.x + k * THREADS;
       if (g < ngroups) {
         xv[k].x -= mean; xv[k].y -= mean; xv[k].z -= mean; xv[k].w -= mean;
         s2 += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
       }
     }
-    const float rstd = rsqrtf(block_sum2(s2, 0.f, red).x * inv_dim + eps);
+    const float rstd = rsqrtf(block_sum2<THREADS>(s2, 0.f, red).x * inv_dim + eps);
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxGroups; ++k) {
-      const int g = threadIdx.x + k * kBwdThreads;
+    for (int k = 0; k < GROUPS; ++k) {
+      const int g = threadIdx.x + k * THREADS;
       if (g < ngroups) {
+        const float4 gm = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + 4 * g)) : make_float4(1.f, 1.f, 1.f, 1.f);
         xv[k].x *= rstd; xv[k].y *= rstd; xv[k].z *= rstd; xv[k].w *= rstd;       // x-hat
         if (gelu) {
-          gv[k].x *= gelu_grad(fmaf(xv[k].x, gm[k].x, bt[k].x));
-          gv[k].y *= gelu_grad(fmaf(xv[k].y, gm[k].y, bt[k].y));
-          gv[k].z *= gelu_grad(fmaf(xv[k].z, gm[k].z, bt[k].z));
-          gv[k].w *= gelu_grad(fmaf(xv[k].w, gm[k].w, bt[k].w));
+          const float4 bt = beta != nullptr ? __ldg(reinterpret_cast<const float4*>(beta + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gv[k].x *= gelu_grad(fmaf(xv[k].x, gm.x, bt.x));
+          gv[k].y *= gelu_grad(fmaf(xv[k].y, gm.y, bt.y));
+          gv[k].z *= gelu_grad(fmaf(xv[k].z, gm.z, bt.z));
+          gv[k].w *= gelu_grad(fmaf(xv[k].w, gm.w, bt.w));
         }
         dg[k].x += gv[k].x * xv[k].x; dg[k].y += gv[k].y * xv[k].y; dg[k].z += gv[k].z * xv[k].z; dg[k].w += gv[k].w * xv[k].w;
         db[k].x += gv[k].x; db[k].y += gv[k].y; db[k].z += gv[k].z; db[k].w += gv[k].w;
-        gv[k].x *= gm[k].x; gv[k].y *= gm[k].y; gv[k].z *= gm[k].z; gv[k].w *= gm[k].w;   // dy * gamma
+        gv[k].x *= gm.x; gv[k].y *= gm.y; gv[k].z *= gm.z; gv[k].w *= gm.w;   // dy * gamma
         c1 += gv[k].x + gv[k].y + gv[k].z + gv[k].w;
         c2 += gv[k].x * xv[k].x + gv[k].y * xv[k].y + gv[k].z * xv[k].z + gv[k].w * xv[k].w;
       }
     }
-    const float2 c = block_sum2(c1, c2, red);
+    const float2 c = block_sum2<THREADS>(c1, c2, red);
     const float m1 = c.x * inv_dim, m2 = c.y * inv_dim;
 #pragma unroll
-    for (int k = 0; k < kMaxGroups; ++k) {
-      const int g = threadIdx.x + k * kBwdThreads;
+    for (int k = 0; k < GROUPS; ++k) {
+      const int g = threadIdx.x + k * THREADS;
       if (g < ngroups) {
         float4 o;
         o.x = rstd * (gv[k].x - m1 - xv[k].x * m2);
@@ -157,8 +158,8 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
   if (partial != nullptr) {
     float* pg = partial + static_cast<long>(blockIdx.x) * 2 * dim;
 #pragma unroll
-    for (int k = 0; k < kMaxGroups; ++k) {
-      const int g = threadIdx.x + k * kBwdThreads;
+    for (int k = 0; k < GROUPS; ++k) {
+      const int g = threadIdx.x + k * THREADS;
       if (g < ngroups) {
         *reinterpret_cast<float4*>(pg + 4 * g) = dg[k];
         *reinterpret_cast<float4*>(pg + dim + 4 * g) = db[k];
@@ -167,20 +168,30 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
   }
 }
 
-// out[c] = sum_p partial[p * stride + c]   (c < n)
+// out[c] = sum_p partial[p * stride + c]   (c < n).  CTA = 32 columns x 8 part-lanes: the `parts` (up to ~1200) records
+// of a column are summed by 8 threads in a fixed interleaved order, then combined in a fixed order (deterministic).
 __global__ void partial_reduce_kernel(const float* __restrict__ partial, int parts, long stride, float* __restrict__ out,
                                       int n, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += partial[p * stride + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < n)
+    for (int p = py; p < parts; p += 8) s += partial[p * stride + c];
+  red[py][cx] = s;
+  __syncthreads();
+  if (py == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 int grid_for_rows(int rows) { return rows < kBwdMaxBlocks ? rows : kBwdMaxBlocks; }
 
 int reduce_partials(const float* partial, int parts, long stride, float* out, int n, cudaStream_t stream) {
-  partial_reduce_kernel<<<(n + 127) / 128, 128, 0, stream>>>(partial, parts, stride, out, n, 0);
+  partial_reduce_kernel<<<(n + 31) / 32, 256, 0, stream>>>(partial, parts, stride, out, n, 0);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
@@ -396,12 +407,23 @@ int layernorm_bwd(const void* x, int x_dtype, long ldx, const void* dy, int dy_d
   if (accumulate && dx_dtype != 0) return OPB_ERR_INVALID;
   const bool want_param_grads = (dgamma != nullptr || dbeta != nullptr);
   if (want_param_grads && ws == nullptr) return OPB_ERR_INVALID;
-  const int grid = grid_for_rows(rows);
   float* partial = want_param_grads ? ws : nullptr;
-#define OPB_LNB(TX, TDY, TDX)                                                                                         \
-  layernorm_bwd_kernel<TX, TDY, TDX><<<grid, kBwdThreads, 0, stream>>>(                                               \
+  // (threads, float4 groups per thread): 128 x 1 (dim <= 512), 128 x 3 (<= 1536), 256 x 3 (<= 3072), 256 x 6 (<= 6144)
+  const int cfg = dim <= 512 ? 0 : (dim <= 1536 ? 1 : (dim <= 3072 ? 2 : 3));
+  const int per_sm = cfg <= 1 ? 8 : (cfg == 2 ? 4 : 2);
+  int grid = 148 * per_sm;
+  if (grid > rows) grid = rows;
+#define OPB_LNB_CFG(TX, TDY, TDX, TH, GR)                                                                             \
+  layernorm_bwd_kernel<TX, TDY, TDX, TH, GR><<<grid, TH, 0, stream>>>(                                                \
       reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TDY*>(dy), ld_dy, gamma, beta,                      \
       reinterpret_cast<TDX*>(dx), ld_dx, accumulate, partial, rows, dim, eps, gelu, dy_merge_w)
+#define OPB_LNB(TX, TDY, TDX)                                                                                         \
+  do {                                                                                                                \
+    if (cfg == 0) OPB_LNB_CFG(TX, TDY, TDX, 128, 1);                                                                  \
+    else if (cfg == 1) OPB_LNB_CFG(TX, TDY, TDX, 128, 3);                                                             \
+    else if (cfg == 2) OPB_LNB_CFG(TX, TDY, TDX, 256, 3);                                                             \
+    else OPB_LNB_CFG(TX, TDY, TDX, 256, 6);                                                                           \
+  } while (0)
   const int key = (x_dtype != 0) * 4 + (dy_dtype != 0) * 2 + (dx_dtype != 0);
   switch (key) {
     case 0: OPB_LNB(float, float, float); break;
@@ -413,6 +435,7 @@ int layernorm_bwd(const void* x, int x_dtype, long ldx, const void* dy, int dy_d
     case 6: OPB_LNB(__nv_bfloat16, __nv_bfloat16, float); break;
     default: OPB_LNB(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
   }
+#undef OPB_LNB_CFG
 #undef OPB_LNB
   if (cudaGetLastError() != cudaSuccess) return OPB_ERR_CUDA;
   if (dgamma != nullptr) {

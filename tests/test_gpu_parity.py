@@ -37,7 +37,9 @@ def assert_same_argmax(got_sim, want_sim, what, margin=2e-3):
 
 
 def dense_bias(rp, S):
-    """(H,S,S) fp32 CPU view of a kernels.RelPosBias in either form."""
+    """(H,S,S) fp32 CPU view of a kernels.RelPosBias in either form (or of the training path's dense tensor)."""
+    if torch.is_tensor(rp):
+        return rp[:, :, :S].detach().cpu()
     if rp.lut is not None:
         idx = (rp.code_row[:S, None] - rp.code_col[None, :S]).long()
         return rp.lut[:, idx].cpu()
@@ -112,15 +114,21 @@ def test_audio_15s_shape_and_oracle():
     check(got, want, "15 s audio vs oracle")
 
 
-def test_tiny_adapter_outputs(tiny):
+@pytest.mark.parametrize("grad", [False, True])
+def test_tiny_adapter_outputs(tiny, grad):
+    """grad=True takes the autograd-recorded training path of the adapters (dense bias tensors), grad=False the
+    inference path (LUT-form bias)."""
     fx, sd, hub, (tok, img, aud, apm) = tiny
     ew = hub.model.encoder_wrapper
-    x, pad, bias = ew.text_adapter(tok.cuda())
+    with torch.set_grad_enabled(grad):
+        x, pad, bias = ew.text_adapter(tok.cuda())
+        xi, _, bi = ew.image_adapter(img.cuda())
+    assert x.requires_grad == grad and xi.requires_grad == grad
+    x, xi = x.detach(), xi.detach()
     want = fx["adapter"]["text_x"] * (~fx["adapter"]["text_pad"]).unsqueeze(-1)
     torch.testing.assert_close(x.cpu(), want, atol=1e-6, rtol=0)
     S = x.shape[1]
     torch.testing.assert_close(dense_bias(bias[0], S), fx["adapter"]["text_bias"], atol=0, rtol=0)
-    xi, _, bi = ew.image_adapter(img.cuda())
     ref = fx["adapter"]["image_x"]
     err = (xi[:1].cpu() - ref).abs().max().item() / ref.abs().max().item()
     print("image adapter rel err", err)
