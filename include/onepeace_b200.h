@@ -94,11 +94,12 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
  * position bias is given in LUT form:  bias[h][i][j] = lut[h][code_row[i] - code_col[j]]  (lut fp32 [H, lut_len],
  * code_row / code_col int32 [S]; built by the adapters from rel_pos_table + rp_bucket — every ONE-PEACE bucket scheme is
  * a function of a per-position code difference plus three CLS ids, adapter/text.py:18-29,62-68, image.py:19-34).
+ * lse / ln_stats as in opb_attention_fwd (either may be NULL).
  * Returns OPB_ERR_UNSUPPORTED for S > 384 or a LUT larger than 32 KB (callers then use opb_attention_fwd).
  */
 int opb_attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int32_t* code_row,
-                         const int32_t* code_col, const uint8_t* key_pad, void* out, float* ln_stats, int B, int S,
-                         int H, void* stream);
+                         const int32_t* code_col, const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B,
+                         int S, int H, void* stream);
 
 /* lut[h][l] = table[idx[l]][h]  (table fp32 [num_buckets, H], idx int32 [L], lut fp32 [H, L]) */
 int opb_relpos_lut_build(const float* table, const int32_t* idx, float* lut, int L, int H, void* stream);

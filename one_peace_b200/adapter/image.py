@@ -163,7 +163,7 @@ class ImageAdapter(torch.nn.Module):
     def forward_train(self, src_images):
         """Same outputs, recorded for autograd (autograd.ImageEmbedFn / RelPosBiasFn); the positional table is resized
         by torch ops so its gradient reaches pos_embed through torch's own bicubic adjoint (parameter preprocessing)."""
-        from ..autograd import ImageEmbedFn, RelPosBiasFn
+        from ..autograd import ImageEmbedFn, RelPosBiasFn, TrainBias
         R = src_images.shape[-1]
         w = R // 16
         S = w * w + 1
@@ -181,5 +181,7 @@ class ImageAdapter(torch.nn.Module):
                                self.cls_embedding)
         bias = None
         if self.rel_pos_table_list is not None:
-            bias = [RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads) for t in self.rel_pos_table_list]
+            fast = self.get_rel_pos_bias(S)            # LUT form for the tcgen05 attention kernel (S <= 384), same values
+            bias = [TrainBias(RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads),
+                              f if f.lut is not None else None) for t, f in zip(self.rel_pos_table_list, fast)]
         return x, None, bias

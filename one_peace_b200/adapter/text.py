@@ -94,11 +94,13 @@ class TextAdapter(torch.nn.Module):
 
     def forward_train(self, src_tokens):
         """Same outputs, recorded for autograd: the bias list holds dense (H,S,S_pad) tensors (autograd.RelPosBiasFn)."""
-        from ..autograd import RelPosBiasFn, TextEmbedFn
+        from ..autograd import RelPosBiasFn, TextEmbedFn, TrainBias
         x, pad = TextEmbedFn.apply(src_tokens, self.embed_tokens.weight, self.embed_positions.weight, self.cls_embedding,
                                    self.padding_idx)
         bias = None
         if self.rel_pos_table_list is not None:
             S = src_tokens.size(1) + 1
-            bias = [RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads) for t in self.rel_pos_table_list]
+            fast = self.get_rel_pos_bias(S)            # LUT form for the tcgen05 attention kernel (S <= 384), same values
+            bias = [TrainBias(RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads),
+                              f if f.lut is not None else None) for t, f in zip(self.rel_pos_table_list, fast)]
         return x, pad, bias

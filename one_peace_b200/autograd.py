@@ -19,6 +19,15 @@ from . import kernels as K
 from .components import PackCache, bf16, f32
 
 
+class TrainBias:
+    """Relative-position bias of a training forward: `dense` = autograd-tracked fp32 (H,S,S_pad) tensor (what the
+    backward kernels read and what receives the gradient), `fast` = the same values as a kernels.RelPosBias in LUT
+    form for the tcgen05 attention kernel (None when S > 384)."""
+
+    def __init__(self, dense, fast=None):
+        self.dense, self.fast, self.lut = dense, fast, None
+
+
 def _pad8(n):
     return (n + 7) // 8 * 8
 
@@ -96,7 +105,7 @@ def layer_train_pack(layer, modality):
     return cache.get(ps, build)
 
 
-def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep):
+def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep, fast_bias=None):
     """x fp32 [M, d] -> (x_out fp32 [M, d], saved activations or None).  Un-fused LayerNorm form of
     transformer_layer.py:165-228; `row_scale` [M] = drop-path keep mask / keep_prob (:80-86) or None."""
     p = layer_train_pack(layer, modality)
@@ -109,7 +118,10 @@ def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep
     h1 = K.layernorm(x, p["ln1_w"], p["ln1_b"], e(d), eps=layer.self_attn_layer_norm.eps)
     qkv = K.gemm(h1, p["wqkv"], K.EPI_STORE_BF16, e(3 * d), bias=p["bqkv"], colscale=p["qscale"])
     lse = torch.empty(B * H * S, dtype=torch.float32, device=dev)
-    att = K.attention(qkv, bias, key_pad, B, S, H, out=e(d), lse=lse)
+    if fast_bias is not None:      # tcgen05 kernel, LUT-form bias (same table values as the dense form)
+        att = K.attention_tc(qkv, fast_bias, key_pad, B, S, H, out=e(d), lse=lse)
+    else:
+        att = K.attention(qkv, bias, key_pad, B, S, H, out=e(d), lse=lse)
     a2 = K.layernorm(att, p["lni_w"], p["lni_b"], e(d), eps=layer.self_attn.ln.eps)
     o = K.gemm(a2, p["wo"], K.EPI_STORE_BF16, e(d), bias=p["bo"])
     x2 = K.scale_resid_fwd(x, o, p["g1"], row_scale, torch.empty_like(x))
@@ -173,17 +185,19 @@ def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_sc
 
 
 class EncoderStackFn(torch.autograd.Function):
-    """x0 [M, d] fp32 -> x_L [M, d] fp32 through all layers (transformer_encoder.py:172-188)."""
+    """x0 [M, d] fp32 -> x_L [M, d] fp32 through all layers (transformer_encoder.py:172-188).
+
+    Forward: when no drop-path is active the layers run the inference kernels (fused-LayerNorm GEMM chain, tcgen05
+    attention) and only each layer's input rows are kept.  Backward: per layer, recompute (un-fused form) + adjoint."""
 
     @staticmethod
     def forward(ctx, encoder, meta, x0, n_bias, *tensors):
-        B, S, modality, key_pad = meta
+        B, S, modality, key_pad, fast = meta
         biases = list(tensors[:n_bias])
         layers = list(encoder.layers)
         x = x0.contiguous()
         xs, scales = [], []
-        for i, layer in enumerate(layers):
-            bias = None if n_bias == 0 else (biases[0] if n_bias == 1 else biases[i])
+        for layer in layers:
             rs = None
             if layer.training and layer.drop_path_prob > 0:
                 # per-sample keep mask / keep_prob, one value per batch column (transformer_layer.py:80-86)
@@ -191,26 +205,48 @@ class EncoderStackFn(torch.autograd.Function):
                 rs = ((torch.rand(B, device=x.device) < keep).float() / keep).repeat_interleave(S).contiguous()
             if layer.training and layer.dropout_prob > 0:
                 raise NotImplementedError("dropout > 0 (every ONE-PEACE recipe trains with dropout 0.0)")
-            xs.append(x)
             scales.append(rs)
-            x, _ = layer_forward_train(layer, x, bias, key_pad, B, S, modality, rs, keep=False)
+
+        def pick(lst, i):
+            return None if not lst else (lst[0] if len(lst) == 1 else lst[i])
+        fused = all(r is None for r in scales) and all(l.fused_ln_supported() for l in layers) and \
+            (n_bias == 0 or (fast is not None and all(f is not None for f in fast)))
+        if fused:
+            from .transformer.transformer_layer import TransformerEncoderLayer
+            d = x.shape[1]
+            rows = x.clone()                      # the fused path updates the residual stream in place
+            ws = TransformerEncoderLayer.fused_workspace(B * S, d, encoder.cfg.ffn_embed_dim, encoder.num_attention_heads, x.device)
+            K.row_stats_cast(rows, ws["xb"], ws["mu"], ws["rstd"], eps=layers[0].self_attn_layer_norm.eps)
+            ln1 = dict(ln_mu=ws["mu"], ln_rstd=ws["rstd"])
+            for i, layer in enumerate(layers):
+                xs.append(rows.clone())
+                ln1 = layer.forward_rows_fused(rows, ws["xb"], ln1, ws, pick(fast, i), key_pad, B, S, modality)
+            x = rows
+        else:
+            for i, layer in enumerate(layers):
+                xs.append(x)
+                x, _ = layer_forward_train(layer, x, pick(biases, i), key_pad, B, S, modality, scales[i], keep=False,
+                                           fast_bias=pick(fast, i))
         ctx.encoder, ctx.meta, ctx.n_bias = encoder, meta, n_bias
         ctx.xs, ctx.scales, ctx.biases = xs, scales, biases
         return x
 
     @staticmethod
     def backward(ctx, grad_out):
-        B, S, modality, key_pad = ctx.meta
+        B, S, modality, key_pad, fast = ctx.meta
         layers = list(ctx.encoder.layers)
         n_bias, biases = ctx.n_bias, ctx.biases
         dx = grad_out.to(torch.float32).contiguous().clone()
         dbiases = [torch.zeros_like(b) for b in biases]
+
+        def pick(lst, i):
+            return None if not lst else (lst[0] if len(lst) == 1 else lst[i])
         grads = [None] * len(layers)
         for i in reversed(range(len(layers))):
             layer = layers[i]
-            bias = None if n_bias == 0 else (biases[0] if n_bias == 1 else biases[i])
-            dbias = None if n_bias == 0 else (dbiases[0] if n_bias == 1 else dbiases[i])
-            _, saved = layer_forward_train(layer, ctx.xs[i], bias, key_pad, B, S, modality, ctx.scales[i], keep=True)
+            bias, dbias = pick(biases, i), pick(dbiases, i)
+            _, saved = layer_forward_train(layer, ctx.xs[i], bias, key_pad, B, S, modality, ctx.scales[i], keep=True,
+                                           fast_bias=pick(fast, i))
             grads[i] = layer_backward(layer, ctx.xs[i], saved, dx, bias, dbias, key_pad, B, S, modality, ctx.scales[i])
             ctx.xs[i] = None
         flat = [g for lg in grads for g in lg]
@@ -221,8 +257,12 @@ def run_encoder_stack(encoder, x, bias_list, key_pad, modality):
     """x fp32 [B, S, d] (autograd-tracked) -> fp32 [B, S, d]."""
     B, S, d = x.shape
     params = [p for layer in encoder.layers for p in layer_params(layer, modality)]
-    biases = list(bias_list) if bias_list else []
-    out = EncoderStackFn.apply(encoder, (B, S, modality, key_pad), x.reshape(B * S, d), len(biases), *biases, *params)
+    tb = list(bias_list) if bias_list else []
+    biases = [b.dense if isinstance(b, TrainBias) else b for b in tb]
+    fast = [b.fast if isinstance(b, TrainBias) else None for b in tb]
+    if any(not torch.is_tensor(b) for b in biases):
+        raise RuntimeError("training needs the dense relative-position bias (adapters' forward_train provides it)")
+    out = EncoderStackFn.apply(encoder, (B, S, modality, key_pad, fast), x.reshape(B * S, d), len(biases), *biases, *params)
     return out.view(B, S, d)
 
 

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, int lut_len,
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
-                    float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols) {
+                    float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols) {
   // no static shared memory in this kernel: the dynamic window starts at the (1024-aligned) base of the CTA's shared
   // memory.  The 112 KB + barriers must fit twice per SM, so there is no room for alignment slack; verify instead.
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
@@ -315,6 +315,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
           *reinterpret_cast<uint4*>(op + 32 + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
                                                                   pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
         }
+        // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
+        if (lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
         if (ln_stats != nullptr) {
           const long rows_total = static_cast<long>(B) * S;
           *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
@@ -366,7 +368,7 @@ int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
-                     const uint8_t* key_pad, void* out, float* ln_stats, int B, int S, int H, cudaStream_t stream) {
+                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
   const int nkb = (S + kTcK - 1) / kTcK;
   if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
@@ -392,10 +394,10 @@ int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* 
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
   if (v)
     attention_tc_kernel<true><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
-                                                          reinterpret_cast<__nv_bfloat16*>(out), ln_stats, B, S, H, nkb, tmem_cols);
+                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols);
   else
     attention_tc_kernel<false><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
-                                                           reinterpret_cast<__nv_bfloat16*>(out), ln_stats, B, S, H, nkb, tmem_cols);
+                                                           reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

@@ -8,7 +8,8 @@ namespace opb {
 int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, float* ln_stats,
                   int B, int S, int H, int s_pad, cudaStream_t stream);
 int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
-                     const uint8_t* key_pad, void* out, float* ln_stats, int B, int S, int H, cudaStream_t stream);
+                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H,
+                     cudaStream_t stream);
 int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int H, cudaStream_t stream);
 int ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
                       cudaStream_t stream);

@@ -90,15 +90,15 @@ def relpos_lut_build(table, idx):
     return lut
 
 
-def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None):
+def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None, lse=None):
     """tcgen05 attention (S <= 384).  rp: RelPosBias with the LUT form."""
     D = H * 64
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
     if out is None:
         out = torch.empty(B * S, D, dtype=torch.bfloat16, device=qkv.device)
     st = _lib.load().opb_attention_tc_fwd(qkv.data_ptr(), rp.lut.data_ptr(), rp.lut.shape[1], rp.code_row.data_ptr(),
-                                          rp.code_col.data_ptr(), _ptr(key_pad), out.data_ptr(), _ptr(ln_stats), B, S, H,
-                                          _stream())
+                                          rp.code_col.data_ptr(), _ptr(key_pad), out.data_ptr(), _ptr(lse), _ptr(ln_stats), B, S,
+                                          H, _stream())
     _lib.check(st, "opb_attention_tc_fwd")
     _count()
     return out

@@ -49,12 +49,12 @@ class MultiheadAttention(nn.Module):
               self.out_proj.weight, self.out_proj.bias] + ([self.ln.weight, self.ln.bias] if self.ln is not None else [])
         return self._cache.get(ps, build)
 
-    def run_attention(self, qkv, bias, key_pad, B, S, out=None, ln_stats=None):
+    def run_attention(self, qkv, bias, key_pad, B, S, out=None, ln_stats=None, lse=None):
         """bias: kernels.RelPosBias (or None).  tcgen05 kernel when the bias is in LUT form (S <= 384), else mma.sync."""
         if bias is not None and bias.lut is not None:
-            return K.attention_tc(qkv, bias, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats)
+            return K.attention_tc(qkv, bias, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats, lse=lse)
         dense = bias.dense if bias is not None else None
-        return K.attention(qkv, dense, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats)
+        return K.attention(qkv, dense, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats, lse=lse)
 
     def attend(self, h, bias, key_pad, B, S):
         """h: bf16 [B*S, d] (already layer-normed).  Returns the pre-out_proj tensor (after the inner LN), bf16."""

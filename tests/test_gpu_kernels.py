@@ -309,13 +309,16 @@ def test_attention_tc(K, kind, B, S, H, use_pad):
         for b in range(B):
             kp[b, S - 1 - 2 * b:] = 1
     part = torch.zeros(H * B * S * 2, device="cuda")
-    out = K.attention_tc(qkv, rp, kp, B, S, H, ln_stats=part)
+    lse = torch.empty(B * H * S, device="cuda")
+    out = K.attention_tc(qkv, rp, kp, B, S, H, ln_stats=part, lse=lse)
     q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     sc = q @ k.transpose(-1, -2) + dense[None]
     if kp is not None:
         sc = sc.masked_fill(kp.bool()[:, None, None, :], float("-inf"))
     want = (sc.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * S, D)
     assert relerr(out, want) < 8e-3
+    # log-sum-exp per (batch, head, query), consumed by the attention backward
+    torch.testing.assert_close(lse.view(B, H, S), torch.logsumexp(sc, dim=-1), atol=2e-3, rtol=1e-4)
     mu = torch.empty(B * S, device="cuda"); rstd = torch.empty(B * S, device="cuda")
     K.ln_stats_finalize(part, H, B * S, D, 1e-5, mu, rstd)
     torch.testing.assert_close(mu, out.float().mean(1), atol=2e-3, rtol=1e-2)

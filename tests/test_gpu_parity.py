@@ -38,12 +38,10 @@ def assert_same_argmax(got_sim, want_sim, what, margin=2e-3):
 
 def dense_bias(rp, S):
     """(H,S,S) fp32 CPU view of a kernels.RelPosBias in either form (or of the training path's dense tensor)."""
-    if torch.is_tensor(rp):
-        return rp[:, :, :S].detach().cpu()
     if rp.lut is not None:
         idx = (rp.code_row[:S, None] - rp.code_col[None, :S]).long()
         return rp.lut[:, idx].cpu()
-    return rp.dense[:, :, :S].cpu()
+    return rp.dense[:, :, :S].detach().cpu()         # RelPosBias dense form, or the training path's TrainBias
 
 
 def check(got, want, what, min_cos=0.999):
