@@ -172,7 +172,11 @@ def test_4b_width_slice_vs_oracle(dtype):
     assert_same_argmax(gt @ gi.t(), wt @ wi.t(), "t2i (4B width)")
 
 
-def test_forward_refuses_to_build_a_fake_graph(tiny):
+def test_forward_with_grad_is_recorded_or_refused(tiny):
+    """With grad enabled the model must return an autograd-recorded tensor (text / image: hand-written backward) or
+    refuse (audio: backward not built) — never a graph-less tensor that would silently train nothing."""
     fx, sd, hub, (tok, img, aud, apm) = tiny
+    out = hub.model(src_tokens=tok[:4].cuda(), encoder_type="text")
+    assert out.requires_grad and out.grad_fn is not None
     with pytest.raises(NotImplementedError):
-        hub.model(src_tokens=tok.cuda(), encoder_type="text")        # grad enabled: backward not built yet
+        hub.model(src_audios=aud.cuda(), audio_padding_masks=apm.cuda(), encoder_type="audio")

