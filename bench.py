@@ -223,7 +223,11 @@ def run_b200(args):
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all four encoder GEMM shapes + stem/proj)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "peak_source": pk_src + ", sustained figure (kernel timed inside a long step)", "traffic": None,
+                "peak_source": pk_src + ", sustained figure (kernel timed inside a long step)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE GeGLU launch (the dominant shape, 12608x12288x1536)
+                # from the `ncu --set full` capture summarised in profiles/r01_ncu_gemm_full_final.summary.txt; its
+                # algorithmic bytes are A 38.7 + W 37.7 + out 154.9 = 231.4 MB: no wasted re-reads
+                "traffic": 225.08e6, "traffic_kernel": "gemm_bf16_kernel<2,GEGLU,TMA> (12608 x 12288 x 1536)",
                 "launches": len(recs), "avg_launch_ms": round(gemm_ms / max(1, len(recs)), 4),
                 "gemm_share_of_step": round(gemm_ms / step_ms, 4),
                 "per_shape_tflops": {k: round(v[1] / (v[0] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
