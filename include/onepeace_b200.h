@@ -314,6 +314,17 @@ int opb_l2_normalize_bwd(const float* x, int64_t ldx, const float* dy, int64_t l
 int opb_text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T,
                        int D, int pad_idx, void* stream);
 
+/* Channel-last 1-D convolution windows for the audio adapter's TRAINING path (adapter/audio.py:57-80 conv positions:
+ * k = 19, pad 9, 16 groups; :254-311 feature extractor: k in {3, 2}, stride 2).  The inference path feeds the GEMM with
+ * overlapping TMA views; training materialises the window matrix because dW = dY^T . windows needs it K-major.
+ *   opb_window_gather : out[g][(b,t)][j*cg + c] = in[b, t*stride + j - pad, g*cg + c]  (0 outside the clip)
+ *                       in bf16 [B*t_in, groups*cg] -> out bf16 [groups][B*t_out][kw*cg]
+ *   opb_window_scatter: its adjoint (col2im), dx bf16 [B*t_in, groups*cg], gather form (deterministic)  */
+int opb_window_gather(const void* in, void* out, int B, int t_in, int t_out, int stride, int kw, int pad, int groups,
+                      int cg, void* stream);
+int opb_window_scatter(const void* dwin, void* dx, int B, int t_in, int t_out, int stride, int kw, int pad, int groups,
+                       int cg, void* stream);
+
 /* dtable[bucket[i,j], h] += dbias[h,i,j]  (adjoint of opb_relpos_bias_build; adapter/text.py:84-91, image.py:164-171) */
 int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H,
                         int64_t ld_bucket, void* stream);

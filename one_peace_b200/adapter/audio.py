@@ -162,6 +162,8 @@ class AudioAdapter(torch.nn.Module):
         padding_mask uint8, [bias (H,S,S_pad)])"""
         if preserve_ids is not None or preserve_embed is not None:
             raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            return self.forward_train(src_audios, padding_mask)
         p = self._pack()
         B, N = src_audios.shape
         dev = src_audios.device
@@ -215,4 +217,26 @@ class AudioAdapter(torch.nn.Module):
         pad = padding_mask.to(torch.uint8).contiguous()
         K.zero_padded_rows(x, pad)                                  # transformer_encoder.py:139-142
         bias = self.get_rel_pos_bias(S) if self.rel_pos_table_list is not None else None
+        return x, pad, bias
+
+    def forward_train(self, src_audios, padding_mask):
+        """Same outputs, recorded for autograd (autograd.AudioEmbedFn: materialised-window GEMMs + col2im adjoints)."""
+        from ..autograd import AudioEmbedFn, RelPosBiasFn, TrainBias
+        B, N = src_audios.shape
+        T = self.frame_counts(N)[-1]
+        S = T + 1
+        if padding_mask.shape != (B, S):
+            raise RuntimeError(f"audio_padding_masks must be (B, frames + 1) = ({B}, {S}), got {tuple(padding_mask.shape)}")
+        fe = self.embed_audios[0].conv_layers
+        ps = [l[0].weight for l in fe] + [l[2][1].weight for l in fe] + [l[2][1].bias for l in fe] + \
+             [self.embed_audios[2].weight, self.embed_audios[2].bias, self.embed_audios[3].weight, self.embed_audios[3].bias] + \
+             [self.embed_positions[i + 1][0].weight for i in range(self.pos_depth)] + \
+             [self.embed_positions[i + 1][0].bias for i in range(self.pos_depth)] + [self.cls_embedding, self.cls_pos_embed]
+        meta = (tuple(self.spec), self.pos_k, self.pos_groups, self.embed_dim)
+        x, pad = AudioEmbedFn.apply(src_audios, padding_mask, meta, *ps)
+        bias = None
+        if self.rel_pos_table_list is not None:
+            fast = self.get_rel_pos_bias(S)
+            bias = [TrainBias(RelPosBiasFn.apply(t.weight, self.rp_bucket, S, self.attention_heads),
+                              f if f.lut is not None else None) for t, f in zip(self.rel_pos_table_list, fast)]
         return x, pad, bias

@@ -393,6 +393,60 @@ __global__ void text_embed_bwd_kernel(const float* __restrict__ dx, const int64_
   }
 }
 
+// im2col of a channel-last 1-D convolution (audio adapter, adapter/audio.py:57-80,254-311), grouped:
+//   out[g][(b, t)][j * cg + c] = in[b, t * stride + j - pad, g * cg + c]   (zero outside [0, t_in))
+// in: bf16 [B * t_in, groups * cg]; out: bf16 [groups][B * t_out][kw * cg].  8 channels (16 bytes) per thread.
+__global__ void window_gather_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int t_in,
+                                     int t_out, int stride, int kw, int pad, int groups, int cg) {
+  const int vpr = cg / 8;                                   // vectors per (row, tap)
+  const long per_group = static_cast<long>(B) * t_out * kw * vpr;
+  const long total = per_group * groups;
+  const int C = groups * cg;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i / per_group);
+    long r = i % per_group;
+    const int v = static_cast<int>(r % vpr); r /= vpr;
+    const int j = static_cast<int>(r % kw); r /= kw;
+    const int t = static_cast<int>(r % t_out);
+    const int b = static_cast<int>(r / t_out);
+    const int s = t * stride + j - pad;
+    uint4 d = make_uint4(0u, 0u, 0u, 0u);
+    if (s >= 0 && s < t_in) d = *reinterpret_cast<const uint4*>(in + (static_cast<long>(b) * t_in + s) * C + g * cg + 8 * v);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long>(g) * B * t_out + static_cast<long>(b) * t_out + t) * kw + j) * cg + 8 * v) = d;
+  }
+}
+
+// col2im (adjoint of window_gather): dx[b, s, g * cg + c] = sum over (t, j) with t * stride + j - pad == s of
+// dwin[g][(b, t)][j * cg + c];  fp32 accumulation, bf16 output.  Gather form: no atomics, deterministic.
+__global__ void window_scatter_kernel(const __nv_bfloat16* __restrict__ dwin, __nv_bfloat16* __restrict__ dx, int B, int t_in,
+                                      int t_out, int stride, int kw, int pad, int groups, int cg) {
+  const int vpr = cg / 8;
+  const int C = groups * cg;
+  const long total = static_cast<long>(B) * t_in * groups * vpr;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    long r = i;
+    const int v = static_cast<int>(r % vpr); r /= vpr;
+    const int g = static_cast<int>(r % groups); r /= groups;
+    const int s = static_cast<int>(r % t_in);
+    const int b = static_cast<int>(r / t_in);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < kw; ++j) {
+      const int num = s + pad - j;
+      if (num < 0 || num % stride != 0) continue;
+      const int t = num / stride;
+      if (t >= t_out) continue;
+      const uint4 d = *reinterpret_cast<const uint4*>(
+          dwin + ((static_cast<long>(g) * B * t_out + static_cast<long>(b) * t_out + t) * kw + j) * cg + 8 * v);
+      const float2 a0 = unpack_bf16x2(d.x), a1 = unpack_bf16x2(d.y), a2 = unpack_bf16x2(d.z), a3 = unpack_bf16x2(d.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y; acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dx + (static_cast<long>(b) * t_in + s) * C + g * cg + 8 * v) = o;
+  }
+}
+
 }  // namespace
 
 // ws: at least layernorm_bwd_ws_floats(dim) floats
@@ -540,6 +594,34 @@ int text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float*
                    int pad_idx, cudaStream_t stream) {
   if (B <= 0 || T <= 0 || D <= 0) return OPB_ERR_INVALID;
   text_embed_bwd_kernel<<<B * (T + 1), 256, 0, stream>>>(dx, tokens, dtable, dpos, dcls, B, T, D, pad_idx);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+static int window_check(int B, int t_in, int t_out, int stride, int kw, int pad, int groups, int cg) {
+  if (B <= 0 || t_in <= 0 || t_out <= 0 || stride <= 0 || kw <= 0 || pad < 0 || groups <= 0 || cg <= 0 || (cg & 7)) return OPB_ERR_INVALID;
+  if (static_cast<long>(t_out - 1) * stride + kw - 1 - pad > static_cast<long>(t_in) - 1 + pad) return OPB_ERR_INVALID;   // windows stay inside the padded input
+  return OPB_OK;
+}
+
+int window_gather(const void* in, void* out, int B, int t_in, int t_out, int stride, int kw, int pad, int groups, int cg,
+                  cudaStream_t stream) {
+  const int rc = window_check(B, t_in, t_out, stride, kw, pad, groups, cg);
+  if (rc != OPB_OK) return rc;
+  const long total = static_cast<long>(B) * t_out * kw * (cg / 8) * groups;
+  window_gather_kernel<<<elementwise_grid(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                  reinterpret_cast<__nv_bfloat16*>(out), B, t_in, t_out, stride,
+                                                                  kw, pad, groups, cg);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int window_scatter(const void* dwin, void* dx, int B, int t_in, int t_out, int stride, int kw, int pad, int groups, int cg,
+                   cudaStream_t stream) {
+  const int rc = window_check(B, t_in, t_out, stride, kw, pad, groups, cg);
+  if (rc != OPB_OK) return rc;
+  const long total = static_cast<long>(B) * t_in * groups * (cg / 8);
+  window_scatter_kernel<<<elementwise_grid(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dwin),
+                                                                   reinterpret_cast<__nv_bfloat16*>(dx), B, t_in, t_out, stride,
+                                                                   kw, pad, groups, cg);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

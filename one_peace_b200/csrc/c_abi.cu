@@ -273,6 +273,18 @@ int opb_l2_normalize_bwd(const float* x, int64_t ldx, const float* dy, int64_t l
   return opb::l2_normalize_bwd(x, ldx, dy, ld_dy, dx, dx_bf16, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+int opb_window_gather(const void* in, void* out, int B, int t_in, int t_out, int stride, int kw, int pad, int groups,
+                      int cg, void* stream) {
+  if (!in || !out) return OPB_ERR_INVALID;
+  return opb::window_gather(in, out, B, t_in, t_out, stride, kw, pad, groups, cg, static_cast<cudaStream_t>(stream));
+}
+
+int opb_window_scatter(const void* dwin, void* dx, int B, int t_in, int t_out, int stride, int kw, int pad, int groups,
+                       int cg, void* stream) {
+  if (!dwin || !dx) return OPB_ERR_INVALID;
+  return opb::window_scatter(dwin, dx, B, t_in, t_out, stride, kw, pad, groups, cg, static_cast<cudaStream_t>(stream));
+}
+
 int opb_text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T,
                        int D, int pad_idx, void* stream) {
   if (!dx || !tokens || !dtable || !dpos || !dcls) return OPB_ERR_INVALID;

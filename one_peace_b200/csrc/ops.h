@@ -90,6 +90,10 @@ int scale_resid_bwd(const float* dx, const void* o, const float* gamma, const fl
 int batch_sum_f32(const float* in, long ld, float* out, int B, long n, int accumulate, cudaStream_t stream);
 int l2_normalize_bwd(const float* x, long ldx, const float* dy, long ld_dy, float* dx, void* dx_bf16, int rows, int D,
                      cudaStream_t stream);
+int window_gather(const void* in, void* out, int B, int t_in, int t_out, int stride, int kw, int pad, int groups, int cg,
+                  cudaStream_t stream);
+int window_scatter(const void* dwin, void* dx, int B, int t_in, int t_out, int stride, int kw, int pad, int groups, int cg,
+                   cudaStream_t stream);
 int text_embed_bwd(const float* dx, const int64_t* tokens, float* dtable, float* dpos, float* dcls, int B, int T, int D,
                    int pad_idx, cudaStream_t stream);
 int colsum_bf16(const void* y, long ldy, float* ws, float* out, int rows, int n, cudaStream_t stream);

@@ -506,3 +506,25 @@ def text_embed_bwd(dx, tokens, dtable, dpos, dcls, pad_idx=1):
                                         B, T, D, pad_idx, _stream())
     _lib.check(st, "opb_text_embed_bwd")
     _count()
+
+
+def window_gather(x, B, t_in, t_out, stride, kw, pad, groups):
+    """bf16 [B*t_in, C] -> [groups, B*t_out, kw*(C/groups)] convolution windows (see onepeace_b200.h)"""
+    C = x.shape[1]
+    cg = C // groups
+    out = torch.empty(groups, B * t_out, kw * cg, dtype=torch.bfloat16, device=x.device)
+    st = _lib.load().opb_window_gather(x.data_ptr(), out.data_ptr(), B, t_in, t_out, stride, kw, pad, groups, cg, _stream())
+    _lib.check(st, "opb_window_gather")
+    _count()
+    return out
+
+
+def window_scatter(dwin, B, t_in, t_out, stride, kw, pad):
+    """adjoint of window_gather: bf16 [groups, B*t_out, kw*cg] -> [B*t_in, groups*cg]"""
+    groups = dwin.shape[0]
+    cg = dwin.shape[2] // kw
+    dx = torch.empty(B * t_in, groups * cg, dtype=torch.bfloat16, device=dwin.device)
+    st = _lib.load().opb_window_scatter(dwin.data_ptr(), dx.data_ptr(), B, t_in, t_out, stride, kw, pad, groups, cg, _stream())
+    _lib.check(st, "opb_window_scatter")
+    _count()
+    return dx

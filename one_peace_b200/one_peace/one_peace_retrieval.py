@@ -75,8 +75,6 @@ class OnePeaceRetrievalModel(OnePeaceBaseModel):
     def forward_train(self, encoder_type, **inputs):
         """Training forward: the same kernels recorded as autograd nodes (one_peace_b200/autograd.py)."""
         from ..autograd import HeadFn
-        if encoder_type == "audio":
-            raise NotImplementedError("audio-branch backward (wav2vec feature extractor + conv positions) is not built yet")
         ew = self.encoder_wrapper
         info = ew.adapt(encoder_type, **inputs)
         x, _ = ew.fusion_model.run_layers(info, encoder_type)

@@ -162,3 +162,23 @@ def test_relpos_bias_bwd(K):
     want = torch.zeros(NB, H, device="cuda")
     want.index_add_(0, bucket[:S, :S].reshape(-1), dbias[:, :, :S].permute(1, 2, 0).reshape(S * S, H))
     assert relerr(dtable, want) < 1e-5
+
+
+@pytest.mark.parametrize("B,t_in,stride,kw,pad,groups,cg", [(2, 49, 1, 19, 9, 16, 16), (3, 99, 2, 3, 0, 1, 64), (2, 24, 2, 2, 0, 1, 512)])
+def test_window_gather_scatter(K, B, t_in, stride, kw, pad, groups, cg):
+    """im2col / col2im of the audio adapter's training path vs an index-built reference and its autograd adjoint."""
+    t_out = (t_in + 2 * pad - kw) // stride + 1
+    C = groups * cg
+    g = gen(t_in + kw)
+    x = torch.randn(B * t_in, C, device="cuda", generator=g).bfloat16()
+    win = K.window_gather(x, B, t_in, t_out, stride, kw, pad, groups)
+    xr = x.float().view(B, t_in, groups, cg).requires_grad_(True)
+    xp = torch.nn.functional.pad(xr, (0, 0, 0, 0, pad, pad))                       # pad the time axis
+    idx = (torch.arange(t_out, device="cuda")[:, None] * stride + torch.arange(kw, device="cuda")[None, :])   # [t_out, kw]
+    ref = xp[:, idx]                                                                # [B, t_out, kw, groups, cg]
+    ref = ref.permute(3, 0, 1, 2, 4).reshape(groups, B * t_out, kw * cg)
+    assert torch.equal(win.float(), ref.detach())
+    dwin = torch.randn(groups, B * t_out, kw * cg, device="cuda", generator=g).bfloat16()
+    ref.backward(dwin.float())
+    dx = K.window_scatter(dwin, B, t_in, t_out, stride, kw, pad)
+    assert relerr(dx, xr.grad.reshape(B * t_in, C)) < 6e-3

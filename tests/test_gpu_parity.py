@@ -173,10 +173,12 @@ def test_4b_width_slice_vs_oracle(dtype):
 
 
 def test_forward_with_grad_is_recorded_or_refused(tiny):
-    """With grad enabled the model must return an autograd-recorded tensor (text / image: hand-written backward) or
-    refuse (audio: backward not built) — never a graph-less tensor that would silently train nothing."""
+    """With grad enabled the model must return an autograd-recorded tensor (hand-written backward behind it) or refuse
+    (concatenated vl / al encoders: not built) — never a graph-less tensor that would silently train nothing."""
     fx, sd, hub, (tok, img, aud, apm) = tiny
     out = hub.model(src_tokens=tok[:4].cuda(), encoder_type="text")
     assert out.requires_grad and out.grad_fn is not None
+    out = hub.model(src_audios=aud.cuda(), audio_padding_masks=apm.cuda(), encoder_type="audio")
+    assert out.requires_grad and out.grad_fn is not None
     with pytest.raises(NotImplementedError):
-        hub.model(src_audios=aud.cuda(), audio_padding_masks=apm.cuda(), encoder_type="audio")
+        hub.model(src_tokens=tok[:4].cuda(), src_images=img.cuda(), encoder_type="vl")

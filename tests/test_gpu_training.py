@@ -32,7 +32,8 @@ def oracle_grads(sd, modality, inp, proj_target):
     cfg = R.OracleConfig(embed_dim=CFG["embed_dim"], ffn_embed_dim=CFG["ffn"], layers=CFG["layers"],
                          attention_heads=CFG["heads"])
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
-    kw = {"src_tokens": inp} if modality == "text" else {"src_images": inp}
+    kw = {"src_tokens": inp} if modality == "text" else ({"src_images": inp} if modality == "image" else
+                                                        {"src_audios": inp[0], "audio_padding_masks": inp[1]})
     emb = R.extract_features(sdg, cfg, modality, **kw)
     loss = (emb * proj_target).sum()
     loss.backward()
@@ -67,19 +68,22 @@ def compare(model, want, min_cos=0.99, norm_tol=0.03, relpos=None):
     assert len(rows) > 20
 
 
-@pytest.mark.parametrize("modality", ["text", "image"])
+@pytest.mark.parametrize("modality", ["text", "image", "audio"])
 def test_encoder_backward_vs_oracle(modality):
     need_gpu()
-    sd = synth.make_state_dict(**CFG, modalities=("text", "image"), seed=3)
-    tok, img, _, _ = synth.tiny_inputs(seed=5, n_text=8, n_img=2, n_audio=1)
-    inp = tok if modality == "text" else img
+    mods = ("text", "audio") if modality == "audio" else ("text", "image")
+    sd = synth.make_state_dict(**CFG, modalities=mods, seed=3)
+    tok, img, aud, apm = synth.tiny_inputs(seed=5, n_text=8, n_img=2, n_audio=2)
+    inp = {"text": tok, "image": img, "audio": (aud, apm)}[modality]
     g = torch.Generator().manual_seed(9)
-    target = torch.randn(inp.shape[0], CFG["embed_dim"], generator=g)
+    nrow = aud.shape[0] if modality == "audio" else inp.shape[0]
+    target = torch.randn(nrow, CFG["embed_dim"], generator=g)
     want_emb, want = oracle_grads(sd, modality, inp, target)
 
-    model = build_model(sd, "vl")
+    model = build_model(sd, "al" if modality == "audio" else "vl")
     model.train()
-    kw = {"src_tokens": inp.cuda()} if modality == "text" else {"src_images": inp.cuda()}
+    kw = {"src_tokens": inp.cuda()} if modality == "text" else ({"src_images": inp.cuda()} if modality == "image" else
+                                                               {"src_audios": aud.cuda(), "audio_padding_masks": apm.cuda()})
     emb = model(encoder_type=modality, **kw)
     assert emb.requires_grad
     cos = torch.nn.functional.cosine_similarity(emb.detach().float().cpu(), want_emb).min().item()
@@ -91,7 +95,7 @@ def test_encoder_backward_vs_oracle(modality):
     # inherits that rounding — measured 0.98-0.99 cosine, every other tensor >= 0.996
     compare(model, want, relpos=(0.97, 0.06))
     # parameters of the other modality's branch must be untouched
-    other = "image" if modality == "text" else "text"
+    other = {"text": "image" if "image" in mods else "audio", "image": "text", "audio": "text"}[modality]
     for name, p in model.named_parameters():
         if f"{other}_" in name:
             assert p.grad is None, name
