@@ -329,6 +329,17 @@ int opb_window_scatter(const void* dwin, void* dx, int B, int t_in, int t_out, i
 int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H,
                         int64_t ld_bucket, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Retrieval evaluation (one_peace/metrics/recall.py:22-78; SURVEY.md 8f "next" row 3).
+ *   opb_topk10_rows : idx int32 [R,10] (and val fp32 [R,10] unless NULL) = the 10 largest entries of every row of
+ *                     sim fp32 [R,C] (row pitch ld), descending; ties -> smaller column first  (scores.topk(k=10), :39,:50)
+ *   opb_recall_hits : hits[0..2] += number of rows whose own id (row_ids[r]) appears among the candidate ids of its first
+ *                     1 / 5 / 10 ranked columns  (:41, :52); hits int32[3], caller zeroes it
+ * ------------------------------------------------------------------------------------------------------------------ */
+int opb_topk10_rows(const float* sim, int64_t ld, int32_t* idx, float* val, int R, int C, void* stream);
+int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* row_ids, int R, int32_t* hits,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,4 +310,15 @@ int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable
   return opb::relpos_bias_bwd(dbias, bucket, dtable, S, s_pad, H, ld_bucket, static_cast<cudaStream_t>(stream));
 }
 
+int opb_topk10_rows(const float* sim, int64_t ld, int32_t* idx, float* val, int R, int C, void* stream) {
+  if (!sim || !idx) return OPB_ERR_INVALID;
+  return opb::topk10_rows(sim, ld, idx, val, R, C, static_cast<cudaStream_t>(stream));
+}
+
+int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* row_ids, int R, int32_t* hits,
+                    void* stream) {
+  if (!idx || !cand_ids || !row_ids || !hits) return OPB_ERR_INVALID;
+  return opb::recall_hits(idx, cand_ids, row_ids, R, hits, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

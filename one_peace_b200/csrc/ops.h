@@ -104,4 +104,8 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
                   const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
                   float q_scale, cudaStream_t stream);
 
+// ---- retrieval evaluation (recall.cu) ----
+int topk10_rows(const float* sim, long ld, int* idx, float* val, int R, int C, cudaStream_t stream);
+int recall_hits(const int* idx, const int64_t* cand_ids, const int64_t* row_ids, int R, int* hits3, cudaStream_t stream);
+
 }  // namespace opb

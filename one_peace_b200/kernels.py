@@ -528,3 +528,26 @@ def window_scatter(dwin, B, t_in, t_out, stride, kw, pad):
     _lib.check(st, "opb_window_scatter")
     _count()
     return dx
+
+
+def topk10_rows(sim, want_values=False):
+    """fp32 [R, C] -> int32 [R, 10] column indices of the 10 largest entries per row (descending)"""
+    _need_cuda(sim)
+    assert sim.dtype == torch.float32 and sim.stride(1) == 1
+    R, C = sim.shape
+    idx = torch.empty(R, 10, dtype=torch.int32, device=sim.device)
+    val = torch.empty(R, 10, dtype=torch.float32, device=sim.device) if want_values else None
+    st = _lib.load().opb_topk10_rows(sim.data_ptr(), sim.stride(0), idx.data_ptr(), _ptr(val), R, C, _stream())
+    _lib.check(st, "opb_topk10_rows")
+    _count()
+    return (idx, val) if want_values else idx
+
+
+def recall_hits(idx, cand_ids, row_ids):
+    """-> int32 [3]: rows whose id is among the ids of their top-1 / top-5 / top-10 candidates"""
+    hits = torch.zeros(3, dtype=torch.int32, device=idx.device)
+    st = _lib.load().opb_recall_hits(idx.data_ptr(), cand_ids.data_ptr(), row_ids.data_ptr(), idx.shape[0], hits.data_ptr(),
+                                     _stream())
+    _lib.check(st, "opb_recall_hits")
+    _count()
+    return hits

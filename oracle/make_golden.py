@@ -88,6 +88,19 @@ def main():
                           grad_logit_scale=ls.grad.clone()))
     torch.save(cases, os.path.join(OUT, "itc_loss.pt"))
 
+    # ---- retrieval evaluation (metrics/recall.py executed as-is, single process) ----
+    rec_mod = ref_stub.ref_module("one_peace.metrics.recall")
+    rcases = []
+    for (n_img, cap, dd, seed, noise) in [(40, 5, 64, 21, 0.8), (64, 3, 256, 22, 1.5)]:
+        img_e, txt_e, img_ids, txt_ids = synth.retrieval_set(n_img, cap, dd, seed, noise)
+        rec = rec_mod.Recall()
+        rec.initialize(txt_ids, txt_e)
+        for lo in range(0, n_img, 16):                  # batches, as the eval loop feeds them (image_text_retrieval.py:62-111)
+            rec.compute(img_ids[lo:lo + 16], img_e[lo:lo + 16])
+        log = rec.merge_results(output_predict=True)
+        rcases.append(dict(n_img=n_img, cap=cap, d=dd, seed=seed, noise=noise, log=log))
+    torch.save(rcases, os.path.join(OUT, "recall.pt"))
+
     # ---- python Adam (optim/adam.py executed as-is) ----
     # adam.py imports omegaconf (absent) and its apex-probing siblings at module scope: provide shells.
     # adam_fused.py / distributed_fused_adam.py / base_optimizer.py themselves import fine under the stub

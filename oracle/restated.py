@@ -307,3 +307,21 @@ def clip_coefficient(grads, max_norm, multiply_factor=1.0):
     if max_norm > 0:
         coef = min(1.0, max_norm / (float(norm) + 1e-6))
     return float(norm), coef
+
+
+# ----------------------------------------------------------------------------------------------------
+# retrieval evaluation
+# ----------------------------------------------------------------------------------------------------
+def recall_eval(image_ids, image_logits, text_ids, text_logits):
+    """metrics/recall.py:22-78 (single process): Recall@{1,5,10} both ways from the full similarity matrix."""
+    sim_i2t = image_logits @ text_logits.t()
+    out = {}
+    for tag, scores, cand, own in (("txt", sim_i2t, text_ids, image_ids), ("img", sim_i2t.t(), image_ids, text_ids)):
+        rank = scores.topk(k=min(10, scores.size(1)), dim=1).indices
+        pred = cand[rank]
+        rs = [100.0 * pred[:, :r].eq(own[:, None]).any(1).sum().item() / scores.size(0) for r in (1, 5, 10)]
+        out[f"{tag}_r1"], out[f"{tag}_r5"], out[f"{tag}_r10"] = rs
+        out[f"{tag}_r_mean"] = sum(rs) / 3
+        out[f"predict_{tag}"] = pred
+    out["r_mean"] = (out["txt_r_mean"] + out["img_r_mean"]) / 2
+    return out

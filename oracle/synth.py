@@ -137,3 +137,15 @@ def grad_summary(name, g):
     r = torch.randn(flat.numel(), generator=torch.Generator().manual_seed(zlib.crc32(name.encode())))
     return dict(shape=tuple(g.shape), norm=flat.norm().item(), proj=(flat * r).sum().item() / math.sqrt(flat.numel()),
                 head=flat[:256].clone())
+
+
+def retrieval_set(n_img, captions_per_image, d, seed, noise=0.8):
+    """Unit-norm image embeddings, `captions_per_image` noisy text embeddings per image, and the id vectors the
+    retrieval evaluation compares (text id = id of its image; metrics/recall.py:39-52)."""
+    g = torch.Generator().manual_seed(seed)
+    img = F.normalize(torch.randn(n_img, d, generator=g), dim=1)
+    img_ids = torch.arange(100, 100 + n_img)
+    txt = F.normalize(img.repeat_interleave(captions_per_image, 0) + noise * torch.randn(n_img * captions_per_image, d, generator=g) / math.sqrt(d) * 4, dim=1)
+    txt_ids = img_ids.repeat_interleave(captions_per_image)
+    perm = torch.randperm(txt.shape[0], generator=g)
+    return img, txt[perm].contiguous(), img_ids, txt_ids[perm].contiguous()

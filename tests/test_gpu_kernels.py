@@ -353,3 +353,39 @@ def test_gemm_resid_m_tail_splitk(K):
     assert relerr(outs[1][0], outs[0][0]) < 1e-5
     p0 = outs[0][2].view(6, M, 2); p1 = outs[1][2].view(6, M, 2)
     torch.testing.assert_close(p1, p0, atol=2e-2, rtol=1e-4)
+
+
+def test_topk10_rows_and_recall_hits(K):
+    g = torch.Generator(device="cuda").manual_seed(77)
+    sim = torch.randn(37, 1003, device="cuda", generator=g)
+    idx, val = K.topk10_rows(sim, want_values=True)
+    tv, ti = sim.topk(10, dim=1)
+    assert torch.equal(val, tv) and torch.equal(idx.long(), ti)
+    # strided rows (a column-sliced view) and a row with fewer than 10 columns
+    wide = torch.randn(5, 64, device="cuda", generator=g)
+    idx2 = K.topk10_rows(wide[:, :7])
+    assert torch.equal(idx2[:, :7].long(), wide[:, :7].topk(7, dim=1).indices) and torch.all(idx2[:, 7:] == -1)
+    cand = torch.randint(0, 50, (1003,), device="cuda", generator=g)
+    own = torch.randint(0, 50, (37,), device="cuda", generator=g)
+    hits = K.recall_hits(idx, cand, own)
+    pred = cand[ti]
+    want = [int(pred[:, :r].eq(own[:, None]).any(1).sum()) for r in (1, 5, 10)]
+    assert hits.tolist() == want
+
+
+def test_recall_metric_vs_reference_golden(K, golden_dir):
+    """metrics/recall.py protocol through the sm_100a kernels vs the eval_log of the reference's own Recall class."""
+    import os
+    import synth
+    from one_peace_b200.metrics import Recall
+    for c in torch.load(os.path.join(golden_dir, "recall.pt"), weights_only=False):
+        img, txt, img_ids, txt_ids = synth.retrieval_set(c["n_img"], c["cap"], c["d"], c["seed"], c["noise"])
+        rec = Recall()
+        rec.initialize(txt_ids.cuda(), txt.cuda())
+        for lo in range(0, c["n_img"], 16):
+            rec.compute(img_ids[lo:lo + 16].cuda(), img[lo:lo + 16].cuda())
+        log = rec.merge_results(output_predict=True)
+        for k in ("txt_r1", "txt_r5", "txt_r10", "txt_r_mean", "img_r1", "img_r5", "img_r10", "img_r_mean", "r_mean"):
+            assert abs(log[k] - c["log"][k]) < 1e-9, (k, log[k], c["log"][k])
+        assert log["img_count"] == c["log"]["img_count"] and log["txt_count"] == c["log"]["txt_count"]
+        assert log["predict_txt"] == c["log"]["predict_txt"] and log["predict_img"] == c["log"]["predict_img"]

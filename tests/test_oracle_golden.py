@@ -96,6 +96,18 @@ def test_backward_vs_reference_autograd(golden_dir, modality):
     assert n >= 45, n          # 2 layers x 21 + adapter + head parameters on the modality's path
 
 
+def test_recall_eval_vs_reference(golden_dir):
+    """oracle recall_eval == the reference's Recall metric executed on the same synthetic retrieval sets."""
+    for c in torch.load(os.path.join(golden_dir, "recall.pt"), weights_only=False):
+        img, txt, img_ids, txt_ids = synth.retrieval_set(c["n_img"], c["cap"], c["d"], c["seed"], c["noise"])
+        got = R.recall_eval(img_ids, img, txt_ids, txt)
+        for k in ("txt_r1", "txt_r5", "txt_r10", "img_r1", "img_r5", "img_r10", "r_mean"):
+            assert abs(got[k] - c["log"][k]) < 1e-9, (k, got[k], c["log"][k])
+        assert 5.0 < c["log"]["txt_r1"] < 99.0                     # the synthetic set is neither trivial nor hopeless
+        for row, iid in enumerate(img_ids.tolist()):
+            assert got["predict_txt"][row].tolist() == c["log"]["predict_txt"][iid]
+
+
 def test_itc_loss_and_grads(golden_dir):
     cases = torch.load(os.path.join(golden_dir, "itc_loss.pt"), weights_only=False)
     for c in cases:
