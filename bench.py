@@ -235,7 +235,7 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(steps=1, warmup=0, sample_images=2)
+        cpu = cpu_reference(steps=1, warmup=0, sample_images=8)
 
     if rank == 0:
         line = {
@@ -258,16 +258,17 @@ def run_b200(args):
 # reference arm / cpu baseline: the oracle port (oracle/restated.py) on the host cores
 # ----------------------------------------------------------------------------------------------------
 def cpu_reference(steps, warmup, sample_images):
-    """Times the CPU restatement of the reference path (fp32, all host threads) on a bounded sample of the same
+    """Times the CPU restatement of the reference path (fp32 torch CPU ops) on a bounded sample of the same
     workload: `sample_images` images through the full 40-layer vision branch.  /root/reference does not exist
     on the GPU box and the reference cannot be pip-installed (Python 3.12, missing omegaconf/hydra/...), so this
-    is kind = "port" (the restatement is pinned to the reference by tests/test_oracle_golden.py)."""
+    is kind = "port" (the restatement is pinned to the reference by tests/test_oracle_golden.py).
+    Thread count: the fastest of {all cores, 64, 32, 16} on a one-layer probe (torch's CPU GEMMs on a few hundred rows
+    do not scale to 128 threads; taking the best setting keeps the baseline honest)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import restated as R
     import synth
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     # distinct weights for 4 layers, cycled over the 40 (6 GB of fp32 weights would take minutes to draw)
     distinct = 4
     sd = synth.make_state_dict(embed_dim=D, ffn=FFN, layers=distinct, heads=H, modalities=("image",), seed=0)
@@ -277,6 +278,19 @@ def cpu_reference(steps, warmup, sample_images):
     cfg = R.OracleConfig(embed_dim=D, ffn_embed_dim=FFN, layers=LAYERS, attention_heads=H)
     img = torch.randn(sample_images, 3, RES, RES, generator=torch.Generator().manual_seed(5))
     with torch.no_grad():
+        xp = torch.randn(sample_images, 197, D, generator=torch.Generator().manual_seed(6))
+        padp = torch.zeros(sample_images, 197, dtype=torch.bool)
+        best = (None, float("inf"))
+        for th in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+            torch.set_num_threads(th)
+            R.encoder_layer(sd, cfg, xp, None, padp, "image", "encoder_wrapper.fusion_model.layers.0.")
+            t0 = time.perf_counter()
+            R.encoder_layer(sd, cfg, xp, None, padp, "image", "encoder_wrapper.fusion_model.layers.1.")
+            dt = time.perf_counter() - t0
+            if dt < best[1]:
+                best = (th, dt)
+        threads = best[0]
+        torch.set_num_threads(threads)
         for _ in range(warmup):
             R.extract_features(sd, cfg, "image", src_images=img)
         t0 = time.perf_counter()
@@ -284,9 +298,10 @@ def cpu_reference(steps, warmup, sample_images):
             R.extract_features(sd, cfg, "image", src_images=img)
         dt = time.perf_counter() - t0
     v = sample_images * steps / dt
-    return {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{sample_images} images x {steps} step(s) through the full 40-layer fp32 vision branch "
-                      f"(oracle/restated.py, torch CPU ops, {cores} threads; layer weights cycled over {distinct} distinct sets)",
+                      f"(oracle/restated.py, torch CPU ops, {threads} of {cores} host threads = fastest on a one-layer probe; "
+                      f"layer weights cycled over {distinct} distinct sets)",
             "seconds": round(dt, 2)}
 
 
@@ -295,8 +310,8 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.gpus
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    r = cpu_reference(steps=steps, warmup=warmup, sample_images=2)
+    steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    r = cpu_reference(steps=steps, warmup=warmup, sample_images=8)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n, "steps": steps,
             "warmup": warmup, "ms_per_step": round(1e3 * r["seconds"] / steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n),
