@@ -108,6 +108,9 @@ OPB_DEVICE void load_ln_stats(const GemmEpilogue& ep, int row, int M, float& mu,
   const int rc = row < M ? row : M - 1;
   if (ep.ln_partial != nullptr) {
     float s1 = 0.f, s2 = 0.f;
+    // independent 8-byte loads (coalesced over the warp's 32 rows); unrolled so that several are in flight — this runs
+    // before the wait on the accumulator, i.e. in the epilogue warps' idle time
+#pragma unroll 8
     for (int p = 0; p < ep.ln_parts; ++p) {
       const float2 v = *reinterpret_cast<const float2*>(ep.ln_partial + (static_cast<long>(p) * M + rc) * 2);
       s1 += v.x; s2 += v.y;

@@ -174,10 +174,16 @@ class TransformerEncoderLayer(nn.Module):
         # LN2 -> GeGLU; emits u and the partial statistics for the FFN LayerNorm (96 records / row: reduced by a kernel)
         K.gemm_ln(xb, f["w01"], K.EPI_GEGLU_BF16, ws["u"], ln_partial=(ws["part_b"], n_t, d, self.final_layer_norm.eps),
                   ln_colsum=f["c01"], bias=f["d01"], stats_out=ws["part_c"])
-        K.ln_stats_finalize(ws["part_c"], 2 * ((2 * F_) // 256), M, F_, 1e-5, ws["mu2"], ws["rstd2"])   # 2 records / tile
-        # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the partial statistics for the next layer's LN1
-        K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_mu=ws["mu2"], ln_rstd=ws["rstd2"], ln_colsum=f["c2"],
-                  bias=f["d2"], gamma=f["g2"], resid=x, stats_out=ws["part_d"], out_bf16=xb, workspace=ws["tail"])
+        # FFN LN -> fc2 -> LayerScale + residual; emits x, xb and the partial statistics for the next layer's LN1.
+        # OPB_FC2_INLINE_STATS=0 restores the separate ln_stats_finalize launch (96 records / row) for A/B runs.
+        n_rec = 2 * ((2 * F_) // 256)                                                                     # 2 records / tile
+        if os.environ.get("OPB_FC2_INLINE_STATS", "1") != "0":
+            ln_ffn = dict(ln_partial=(ws["part_c"], n_rec, F_, 1e-5))
+        else:
+            K.ln_stats_finalize(ws["part_c"], n_rec, M, F_, 1e-5, ws["mu2"], ws["rstd2"])
+            ln_ffn = dict(ln_mu=ws["mu2"], ln_rstd=ws["rstd2"])
+        K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_colsum=f["c2"], bias=f["d2"], gamma=f["g2"], resid=x,
+                  stats_out=ws["part_d"], out_bf16=xb, workspace=ws["tail"], **ln_ffn)
         return dict(ln_partial=(ws["part_d"], n_t, d, self.self_attn_layer_norm.eps))
 
     @staticmethod
