@@ -163,7 +163,15 @@ class AdjustAdam(FairseqOptimizer):
 
     def __init__(self, cfg, params):
         super().__init__(cfg)
-        self._optimizer = Adam(params, **self.optimizer_config)
+        import torch.distributed as dist
+        if bool(getattr(cfg, "use_distributed_fused_adam", False)) and dist.is_initialized() and dist.get_world_size() > 1:
+            # adam.py:68-70 hands this case to Apex DistributedFusedAdam; here: first-party ZeRO-1 sharded step
+            from .distributed_adam import DistributedAdam
+            oc = self.optimizer_config
+            oc.pop("master_weights")
+            self._optimizer = DistributedAdam(params, **oc)
+        else:
+            self._optimizer = Adam(params, **self.optimizer_config)
 
     @property
     def optimizer_config(self):

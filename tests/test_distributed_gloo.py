@@ -50,3 +50,66 @@ def test_gather_and_sharded_targets_gloo(tmp_path):
     # (mean over b local rows vs mean over W*b rows)
     for r, o in enumerate(outs):
         torch.testing.assert_close(o["grad"] / world, a_all.grad[r * b:(r + 1) * b], atol=1e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ZeRO-1 sharded optimizer step (optim/distributed_adam.py): partition arithmetic + the exchange pattern
+# (reduce-scatter of the flat gradient, shard update, all-gather of the flat parameters) on CPU over gloo, with the
+# oracle's adam_step standing in for the sm_100a kernel.  Must equal plain Adam on the rank-averaged gradients.
+# ------------------------------------------------------------------------------------------------------------------
+def test_shard_layout_covers_every_element_once():
+    from one_peace_b200.optim.distributed_adam import shard_layout, shard_segments
+    numels = [7, 64, 1, 1000, 33, 8]
+    for world in (1, 2, 3, 8):
+        offsets, total, shard = shard_layout(numels, world)
+        assert total == shard * world and shard % 8 == 0 and all(o % 8 == 0 for o in offsets)
+        seen = [torch.zeros(n, dtype=torch.int32) for n in numels]
+        for r in range(world):
+            for pi, start, ln, so in shard_segments(offsets, numels, r * shard, (r + 1) * shard):
+                assert 0 <= so and so + ln <= shard and (offsets[pi] + start) - r * shard == so
+                seen[pi][start:start + ln] += 1
+        assert all(bool((s == 1).all()) for s in seen)
+
+
+def _zero_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from one_peace_b200.optim.distributed_adam import shard_layout, shard_segments
+    g = torch.Generator().manual_seed(5)
+    shapes = [(13,), (4, 9), (1,), (50, 3)]
+    params = [torch.randn(s, generator=g) for s in shapes]
+    grads = [torch.randn(s, generator=torch.Generator().manual_seed(100 + rank * 10 + i)) for i, s in enumerate(shapes)]
+    numels = [p.numel() for p in params]
+    offsets, total, shard = shard_layout(numels, world)
+    lo, hi = rank * shard, (rank + 1) * shard
+    flat_p, flat_g = torch.zeros(total), torch.zeros(total)
+    for p, gr, off in zip(params, grads, offsets):
+        flat_p[off:off + p.numel()] = p.reshape(-1)
+        flat_g[off:off + p.numel()] = gr.reshape(-1)
+    # reduce-scatter (mean) — gloo has no reduce_scatter_tensor: all_reduce + slice is the same exchange result
+    dist.all_reduce(flat_g)
+    gsh = flat_g[lo:hi] / world
+    psh, m, v = flat_p[lo:hi].clone(), torch.zeros(shard), torch.zeros(shard)
+    for pi, start, ln, so in shard_segments(offsets, numels, lo, hi):
+        sl = slice(so, so + ln)
+        R.adam_step(psh[sl], gsh[sl], m[sl], v[sl], 1, 1e-2, 0.9, 0.98, 1e-8, 0.05)      # in place on the shard views
+    out = [torch.zeros(shard) for _ in range(world)]
+    dist.all_gather(out, psh)
+    flat_new = torch.cat(out)
+    torch.save([flat_new[off:off + n].view(s) for off, n, s in zip(offsets, numels, shapes)], os.path.join(out_dir, f"z{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_adam_step_equals_plain_adam_gloo(tmp_path):
+    world = 2
+    mp.spawn(_zero_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(5)
+    shapes = [(13,), (4, 9), (1,), (50, 3)]
+    params = [torch.randn(s, generator=g) for s in shapes]
+    outs = [torch.load(tmp_path / f"z{r}.pt", weights_only=False) for r in range(world)]
+    for i, (p, s) in enumerate(zip(params, shapes)):
+        gavg = sum(torch.randn(s, generator=torch.Generator().manual_seed(100 + r * 10 + i)) for r in range(world)) / world
+        want = R.adam_step(p.clone(), gavg, torch.zeros(s), torch.zeros(s), 1, 1e-2, 0.9, 0.98, 1e-8, 0.05)
+        for r in range(world):
+            torch.testing.assert_close(outs[r][i], want, atol=1e-7, rtol=1e-6)       # every rank holds the same new parameters

@@ -175,3 +175,18 @@ def test_two_rank_contrastive_step_nccl():
                         "--steps", "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok=True" in r.stdout
+
+
+def test_two_rank_sharded_adam_nccl():
+    """optim/distributed_adam.py at W = 2 on real GPUs: reduce-scatter + fused shard step + all-gather == un-sharded fused
+    Adam on the averaged gradients, incl. global-norm clipping (skipped on a 1-GPU box)."""
+    need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dist_zero_adam.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok=True" in r.stdout
