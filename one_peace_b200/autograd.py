@@ -12,6 +12,9 @@ Activation policy = the reference's checkpointing: the forward keeps only each l
 re-runs one layer forward (un-fused LayerNorm form, so the normalised operands the dW GEMMs need exist in HBM) and
 walks its adjoint.  dW = dY^T X is an M-reduction: both operands are transposed to K-major by the transpose kernel
 and go through the same TMA + tcgen05 GEMM as everything else.
+
+torch is used here for what the task calls plumbing only: allocation, dtype / layout copies (`.to`, `cat`, slicing
+`copy_`), the drop-path Bernoulli draw, and autograd's own accumulation of gradients that reach a tensor twice.
 """
 import torch
 
