@@ -102,6 +102,17 @@ struct SmemBars {
   uint32_t tmem_base;
 };
 
+// Optional per-phase cycle accounting of the fp32 residual epilogue (build with EXTRA=-DOPB_GEMM_TIMING; read with
+// opb_gemm_timing_dump()): lane 0 of epilogue warp 0 of every CTA accumulates clock64() deltas.
+#ifdef OPB_GEMM_TIMING
+__device__ unsigned long long g_gemm_t[12];
+#define OPB_GT(var) const long long var = clock64()
+#define OPB_GACC(i, a, b) do { gt_acc[i] += (b) - (a); } while (0)
+#else
+#define OPB_GT(var) do {} while (0)
+#define OPB_GACC(i, a, b) do {} while (0)
+#endif
+
 // row statistics for the fused-LayerNorm epilogue: either precomputed (mu, rstd) or reduced here from partial records
 OPB_DEVICE void load_ln_stats(const GemmEpilogue& ep, int row, int M, float& mu, float& rs) {
   mu = 0.f; rs = 1.f;
@@ -263,6 +274,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
+#ifdef OPB_GEMM_TIMING
+    long long gt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -356,6 +370,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const bool has_res = (EPI == EPI_RESID_F32) && ep.resid != nullptr;
           // ring slot / barrier phase bookkeeping is continuous across tiles: chunk counter gc = it * 8 + c
           const int gc0 = it * 8;
+          OPB_GT(g_t0);
           // the two slots refilled below were last stored from by chunks 4 and 5 of the previous tile: everything but
           // the two newest store groups (chunks 6, 7 -> the other two slots) must have finished reading shared memory
           if (lane == 0) { if (ep.dbg & 2) bulk_wait_read<0>(); else bulk_wait_read<2>(); }
@@ -368,8 +383,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               tma_load_2d(&tm_o, &rbar[slot], stg + slot * 4096, col0 + 32 * pc, row0);
             }
           }
+          OPB_GT(g_t1);
           mbar_wait(&bars->tmem_full[acc], acc_phase);
           tc_fence_after();
+          OPB_GT(g_t2);
+          OPB_GACC(0, g_t0, g_t1); OPB_GACC(1, g_t1, g_t2); OPB_GACC(10, 0, 1);
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
@@ -378,8 +396,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             uint8_t* buf = stg + slot * 4096;
             uint32_t v[32];
             __syncwarp();
+            OPB_GT(g_c0);
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
+            OPB_GT(g_c1);
             if (c == 7) {
               tc_fence_before();
               __syncwarp();
@@ -396,6 +416,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               }
             }
             __syncwarp();
+            OPB_GT(g_c2);
             float x[32];
             {
               float4 pp[8], qq[8], rr[8];
@@ -413,8 +434,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 x[4 * k + 3] = fmaf(__uint_as_float(v[4 * k + 3]), ln_rs * pp[k].w, fmaf(nlm, qq[k].w, rr[k].w));
               }
             }
+            OPB_GT(g_c3);
             if (has_res) {
               mbar_wait(&rbar[slot], (gc >> 2) & 1);
+              OPB_GT(g_c4);
+              OPB_GACC(5, g_c3, g_c4);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const float4 r = lds128(buf + sw128_off(lane, k));
@@ -440,6 +464,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 sts128u(bufB + sw64_off(lane, k), o);
               }
             }
+            OPB_GT(g_c5);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -447,7 +472,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               if (ep.out_bf16 != nullptr) tma_store_2d(&tm_o2, bufB, col0 + c * 32, row0);
               bulk_commit();
             }
+            OPB_GT(g_c6);
+            OPB_GACC(2, g_c0, g_c1); OPB_GACC(3, g_c1, g_c2); OPB_GACC(4, g_c2, g_c3); OPB_GACC(6, g_c3, g_c5);
+            OPB_GACC(7, g_c5, g_c6); OPB_GACC(8, g_c0, g_c6);
           }
+          OPB_GT(g_t3);
+          OPB_GACC(9, g_t0, g_t3);
           if (row_ok && ep.stats_out != nullptr)
             *reinterpret_cast<float2*>(ep.stats_out + (static_cast<long>(n_blk) * M + row) * 2) = make_float2(st_sum, st_sq);
         } else {
@@ -868,6 +898,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
+#ifdef OPB_GEMM_TIMING
+    if (warp == 2 && lane == 0) {
+      for (int i = 0; i < 12; ++i) atomicAdd(&g_gemm_t[i], static_cast<unsigned long long>(gt_acc[i]));
+    }
+#endif
   }
 
   // ===================== teardown =====================
@@ -881,6 +916,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tmem_dealloc<CG>(tmem_base, kAccStages * kBlockN);
   }
 }
+
+#ifdef OPB_GEMM_TIMING
+extern "C" void opb_gemm_timing_dump(int reset) {
+  unsigned long long t[12];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(t, g_gemm_t, sizeof(t));
+  const double n = t[10] > 0 ? static_cast<double>(t[10]) : 1.0;
+  printf("[gemm timing] fp32-residual epilogue, warp 0 of every CTA, %.0f tiles; avg cycles / tile: pre(store drain+prefetch)=%.0f "
+         "wait_acc=%.0f | per tile over 8 chunks: tmem_ld=%.0f drain+prefetch=%.0f coef_math=%.0f resid_wait=%.0f "
+         "resid_add+stats+sts=%.0f fence+store=%.0f chunks_total=%.0f | tile_total=%.0f\n",
+         n, t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n, t[5] / n, (double)(t[6] - t[5]) / n, t[7] / n, t[8] / n, t[9] / n);
+  if (reset) {
+    unsigned long long z[12] = {0};
+    cudaMemcpyToSymbol(g_gemm_t, z, sizeof(z));
+  }
+}
+#endif
 
 // Epilogue of the split-K M-tail rows: x = resid + gamma * (rstd * (acc - mu * colsum) + bias) from the summed raw
 // accumulators; writes the fp32 row, its bf16 copy and the per-256-column (sum, sum of squares) statistics records.
