@@ -942,7 +942,24 @@ gemm_tail_epilogue_kernel(const float* __restrict__ ws, const GemmEpilogue ep, i
   __shared__ float red[2][8];
   const int row = row0 + blockIdx.x;
   float mu, rs;
-  load_ln_stats(ep, row, M, mu, rs);
+  if (ep.ln_partial != nullptr) {
+    // the whole CTA works on ONE row: reduce its partial records cooperatively (a per-thread loop over up to 96
+    // records made this kernel 3x slower than the separate finalize launch it replaced)
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = threadIdx.x; p < ep.ln_parts; p += blockDim.x) {
+      const float2 v = *reinterpret_cast<const float2*>(ep.ln_partial + (static_cast<long>(p) * M + row) * 2);
+      s1 += v.x; s2 += v.y;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    s1 = s2 = 0.f;
+    for (int i = 0; i < 8; ++i) { s1 += red[0][i]; s2 += red[1][i]; }
+    mu = s1 / ep.ln_dim;
+    rs = rsqrtf(fmaxf(s2 / ep.ln_dim - mu * mu, 0.f) + ep.ln_eps);
+  } else {
+    load_ln_stats(ep, row, M, mu, rs);
+  }
   const float* w = ws + static_cast<long>(blockIdx.x) * N;
   for (int t = 0; t < n_tiles; ++t) {
     const int col = t * kBlockN + threadIdx.x;

@@ -326,8 +326,9 @@ def test_attention_tc(K, kind, B, S, H, use_pad):
 
 def test_gemm_resid_m_tail_splitk(K):
     """M = 49 * 256 + 64 rows, N = 1536: the 64-row tail is scheduled as split-K pieces (fp32 atomics into a scratch tile)
-    and finished by the tail-epilogue kernel; result, bf16 copy and LN statistics must match the plain path."""
-    M, d, N = 49 * 256 + 64, 512, 1536
+    and finished by the tail-epilogue kernel; result, bf16 copy and LN statistics must match the plain path.
+    K = 3072 = 48 k-blocks: the smallest reduction length for which the host enables the split (gemm_bf16)."""
+    M, d, N = 49 * 256 + 64, 3072, 1536
     g = torch.Generator(device="cuda").manual_seed(33)
     a = (torch.randn(M, d, device="cuda", generator=g) * 0.5).bfloat16()
     w = (torch.randn(N, d, device="cuda", generator=g) * 0.05).bfloat16()
@@ -353,6 +354,20 @@ def test_gemm_resid_m_tail_splitk(K):
     assert relerr(outs[1][0], outs[0][0]) < 1e-5
     p0 = outs[0][2].view(6, M, 2); p1 = outs[1][2].view(6, M, 2)
     torch.testing.assert_close(p1, p0, atol=2e-2, rtol=1e-4)
+    # same GEMM with the A-row statistics given as 96 partial records (the GeGLU -> fc2 hand-over): the split-K tail
+    # kernel reduces them per row itself; must equal the run on the finalized (mu, rstd) arrays
+    parts, dim = 96, 6144
+    rec = torch.rand(parts, M, 2, device="cuda", generator=g)
+    rec[..., 0] = (rec[..., 0] - 0.5) * 8
+    rec[..., 1] = rec[..., 1] * 400 + 64
+    m2 = torch.empty(M, device="cuda"); r2 = torch.empty(M, device="cuda")
+    K.ln_stats_finalize(rec.view(-1), parts, M, dim, 1e-5, m2, r2)
+    res2 = []
+    for kw in (dict(ln_mu=m2, ln_rstd=r2), dict(ln_partial=(rec.view(-1), parts, dim, 1e-5))):
+        y = res.clone()
+        K.gemm_ln(a, w, K.EPI_RESID_F32, y, ln_colsum=cs, bias=bias, gamma=gamma, resid=y, workspace=torch.empty(256 * N, device="cuda"), **kw)
+        res2.append(y)
+    assert relerr(res2[1], res2[0]) < 1e-5
 
 
 def test_topk10_rows_and_recall_hits(K):
