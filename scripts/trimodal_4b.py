@@ -13,11 +13,13 @@ from one_peace_b200.criterions.image_text_retrieval_loss import itc_loss
 from one_peace_b200.one_peace.hub_interface import from_pretrained
 
 D, FFN, H, L, VOCAB, B = 1536, 6144, 24, 40, 4096, 8
+if os.environ.get("OPB_TRIMODAL_TINY"):          # CPU dry-run of the oracle half (no GPU in the build container)
+    D, FFN, H, L = 256, 1024, 4, 6
 distinct = 4
 sd = synth.make_state_dict(embed_dim=D, ffn=FFN, layers=distinct, heads=H, seed=2, vocab=VOCAB)
 for i in range(distinct, L):
-    for k in [k for k in sd if f"layers.{i % distinct}." in k]:
-        sd[k.replace(f"layers.{i % distinct}.", f"layers.{i}.")] = sd[k]
+    for k in [k for k in sd if f"fusion_model.layers.{i % distinct}." in k]:
+        sd[k.replace(f"fusion_model.layers.{i % distinct}.", f"fusion_model.layers.{i}.")] = sd[k]
 g = torch.Generator().manual_seed(11)
 tok = torch.randint(4, VOCAB, (B, 71), generator=g)
 for i in range(B):
@@ -42,6 +44,9 @@ with torch.no_grad():
     w_itc, _, _ = R.itc_loss(wi, wt, wi, wt, scale, 0, 0.0)
     w_atc, _, _ = R.itc_loss(wa, wt, wa, wt, scale, 0, 0.0)
 cpu_s = time.perf_counter() - t0
+if not torch.cuda.is_available():
+    print("oracle half ok:", wt.shape, wi.shape, wa.shape, round(w_itc.item(), 4), round(w_atc.item(), 4), f"{cpu_s:.1f}s")
+    sys.exit(0)
 
 hub = from_pretrained(state_dict=sd, head_type="val", layers=L, embed_dim=D, ffn_embed_dim=FFN, attention_heads=H,
                       patch_image_size=224, device="cuda", dtype="bfloat16", vocab_size=VOCAB)
