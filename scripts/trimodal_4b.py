@@ -44,6 +44,15 @@ with torch.no_grad():
     w_itc, _, _ = R.itc_loss(wi, wt, wi, wt, scale, 0, 0.0)
     w_atc, _, _ = R.itc_loss(wa, wt, wa, wt, scale, 0, 0.0)
 cpu_s = time.perf_counter() - t0
+# second oracle pass with every floating-point parameter rounded to bf16 (what `dtype="bfloat16"` does to the model):
+# separates weight quantisation — amplified by 40 random layers with O(1) LayerScale — from the kernels' own arithmetic
+sdq = {k: (v.to(torch.bfloat16).float() if v.is_floating_point() else v) for k, v in sd.items()}
+with torch.no_grad():
+    qt = R.extract_features(sdq, cfg, "text", src_tokens=tok)
+    qi = R.extract_features(sdq, cfg, "image", src_images=img)
+    qa = R.extract_features(sdq, cfg, "audio", src_audios=aud, audio_padding_masks=apm)
+    q_itc, _, _ = R.itc_loss(qi, qt, qi, qt, R.logit_scale_exp(sdq["logit_scale"]), 0, 0.0)
+    q_atc, _, _ = R.itc_loss(qa, qt, qa, qt, R.logit_scale_exp(sdq["logit_scale"]), 0, 0.0)
 if not torch.cuda.is_available():
     print("oracle half ok:", wt.shape, wi.shape, wa.shape, round(w_itc.item(), 4), round(w_atc.item(), 4), f"{cpu_s:.1f}s")
     sys.exit(0)
@@ -79,6 +88,13 @@ line = {"config": "ONE-PEACE 4B tri-modal embedding, 8 images + 8 texts + 8 x 10
         "argmax_identical_on_decided_rows": {"i2t": [i2t_ok, i2t_n], "a2t": [a2t_ok, a2t_n]},
         "itc_loss": [round(g_itc.item(), 6), round(w_itc.item(), 6), f"rel {rel(g_itc, w_itc):.2e}"],
         "atc_loss": [round(g_atc.item(), 6), round(w_atc.item(), 6), f"rel {rel(g_atc, w_atc):.2e}"],
+        "vs_oracle_with_bf16_rounded_weights": {
+            "min_cosine": {"text": round(cos(gt, qt), 6), "image": round(cos(gi, qi), 6), "audio": round(cos(ga, qa), 6)},
+            "text_cosine_per_row": [round(x, 5) for x in torch.nn.functional.cosine_similarity(gt.float().cpu(), qt).tolist()],
+            "itc_loss_rel": f"{rel(g_itc, q_itc):.2e}", "atc_loss_rel": f"{rel(g_atc, q_atc):.2e}",
+            "oracle_fp32_vs_oracle_bf16_weights_min_cosine": {"text": round(torch.nn.functional.cosine_similarity(wt, qt).min().item(), 6),
+                                                              "image": round(torch.nn.functional.cosine_similarity(wi, qi).min().item(), 6),
+                                                              "audio": round(torch.nn.functional.cosine_similarity(wa, qa).min().item(), 6)}},
         "gpu_ms": {"text": round(ms_t, 2), "image": round(ms_i, 2), "audio": round(ms_a, 2)},
         "samples_per_sec": {"text": round(B / ms_t * 1e3, 1), "image": round(B / ms_i * 1e3, 1), "audio": round(B / ms_a * 1e3, 1)},
         "cpu_oracle_seconds": round(cpu_s, 1), "audio_tokens": T + 1}
