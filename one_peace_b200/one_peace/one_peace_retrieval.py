@@ -20,25 +20,28 @@ class OnePeaceRetrievalConfig(UnifyModelConfig):
     copy_rel_pos_table: bool = False
 
 
+# modalities behind every head type (one_peace_retrieval.py:40-46)
+_HEAD_MODALITIES = {"text": ("text",), "image": ("image",), "audio": ("audio",), "vl": ("text", "image"),
+                    "al": ("text", "audio"), "val": ("text", "image", "audio")}
+_ALL_MODALITIES = ("text", "image", "audio")
+
+
 @register_model("one_peace_retrieval", dataclass=OnePeaceRetrievalConfig)
 class OnePeaceRetrievalModel(OnePeaceBaseModel):
     def __init__(self, cfg: OnePeaceRetrievalConfig, src_dict, head_type):
         super().__init__(cfg, src_dict)
-        embed_dim = self.cfg.encoder.embed_dim
+        if head_type not in _HEAD_MODALITIES:
+            raise ValueError(f"head_type must be one of {sorted(_HEAD_MODALITIES)}, got {head_type!r}")
         self.head_type = head_type
-        cfg.encoder.use_text_moe = head_type in ("text", "vl", "al", "val")
-        cfg.encoder.use_image_moe = head_type in ("image", "vl", "val")
-        cfg.encoder.use_audio_moe = head_type in ("audio", "al", "val")
-        self.encoder_wrapper = ModelWrapper(cfg.encoder, src_dict, use_text_norm=cfg.encoder.use_text_moe,
-                                            use_image_norm=cfg.encoder.use_image_moe,
-                                            use_audio_norm=cfg.encoder.use_audio_moe,
-                                            num_layers=cfg.encoder.layers if cfg.copy_rel_pos_table else None)
-        if cfg.encoder.use_text_moe:
-            self.text_proj = Linear(embed_dim, embed_dim)
-        if cfg.encoder.use_image_moe:
-            self.image_proj = Linear(embed_dim, embed_dim)
-        if cfg.encoder.use_audio_moe:
-            self.audio_proj = Linear(embed_dim, embed_dim)
+        self.modalities = _HEAD_MODALITIES[head_type]
+        enc = cfg.encoder
+        for m in _ALL_MODALITIES:
+            setattr(enc, f"use_{m}_moe", m in self.modalities)
+        self.encoder_wrapper = ModelWrapper(enc, src_dict, num_layers=enc.layers if cfg.copy_rel_pos_table else None,
+                                            **{f"use_{m}_norm": m in self.modalities for m in _ALL_MODALITIES})
+        for m in _ALL_MODALITIES:                              # registration order = the reference's parameter order
+            if m in self.modalities:
+                setattr(self, f"{m}_proj", Linear(enc.embed_dim, enc.embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self.apply(init_one_peace_params)
         self._proj_cache = {}
@@ -89,18 +92,15 @@ class OnePeaceRetrievalModel(OnePeaceBaseModel):
         return cls(cfg, task.source_dictionary, task.cfg.head_type)
 
     def upgrade_state_dict_named(self, state_dict, name):
+        """one_peace_retrieval.py:133-150: prune what this head does not use, then let parameters absent from the
+        checkpoint (e.g. a freshly added head) keep their initial values so that the strict load succeeds."""
         super().upgrade_state_dict_named(state_dict, name)
         self.remove_pretraining_modules(state_dict)
-        prefix = name + "." if name != "" else ""
-        for param_name, _ in self.state_dict().items():
-            if (prefix + param_name) not in state_dict:
-                state_dict[prefix + param_name] = self.state_dict()[param_name]
+        prefix = f"{name}." if name else ""
+        for key, value in self.state_dict().items():
+            state_dict.setdefault(prefix + key, value)
 
     def remove_pretraining_modules(self, state_dict):
-        for param_name in list(state_dict.keys()):
-            if self.head_type not in ("text", "vl", "al", "val") and "text_" in param_name:
-                del state_dict[param_name]
-            elif self.head_type not in ("image", "vl", "val") and "image_" in param_name:
-                del state_dict[param_name]
-            elif self.head_type not in ("audio", "al", "val") and "audio_" in param_name:
-                del state_dict[param_name]
+        unused = [f"{m}_" for m in _ALL_MODALITIES if m not in self.modalities]
+        for key in [k for k in state_dict if any(tag in k for tag in unused)]:
+            del state_dict[key]
