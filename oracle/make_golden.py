@@ -88,6 +88,28 @@ def main():
                           grad_logit_scale=ls.grad.clone()))
     torch.save(cases, os.path.join(OUT, "itc_loss.pt"))
 
+    # ---- concatenated encoders ('vl' / 'al', ModelWrapper.forward one_peace_base.py:68-129) and the DCL loss ----
+    with torch.no_grad():
+        vt, vi, _ = model.encoder_wrapper(src_tokens=tok[:2], src_images=img, encoder_type="vl")
+        at, _, aa = model.encoder_wrapper(src_tokens=tok[2:4], src_audios=aud, audio_padding_masks=apm, encoder_type="al")
+    pre_mod = ref_stub.ref_module("one_peace.criterions.image_text_pretrain_loss")
+    crit = object.__new__(pre_mod.ImageTextPretrainLossCriterion)          # only the two scalars below are read (:187-208)
+    crit.dcl_logit_scale, crit.label_smoothing = 2.5, 0.1
+    gd = torch.Generator().manual_seed(31)
+    stu = torch.randn(3, 9, 64, generator=gd, requires_grad=True)
+    tea = stu.detach() + 0.7 * torch.randn(3, 9, 64, generator=gd)
+    msk = torch.rand(3, 9, generator=gd) < 0.4
+    msk[:, 0] = False
+    padm = torch.zeros(3, 8, dtype=torch.bool)
+    padm[1, 6:] = True
+    msk[1, 7:] = False
+    dcl_a = crit.compute_dcl_loss(stu, tea, msk)
+    dcl_b = crit.compute_dcl_loss(stu, tea, msk, padm)
+    dcl_b.backward()
+    torch.save({"vl_text": vt, "vl_image": vi, "al_text": at, "al_audio": aa, "dcl": dict(seed=31, no_pad=dcl_a.detach(),
+                with_pad=dcl_b.detach(), grad_norm=stu.grad.norm(), grad_head=stu.grad[0, 1:3].clone())},
+               os.path.join(OUT, "pretrain_path.pt"))
+
     # ---- retrieval evaluation (metrics/recall.py executed as-is, single process) ----
     rec_mod = ref_stub.ref_module("one_peace.metrics.recall")
     rcases = []

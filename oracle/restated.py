@@ -310,6 +310,61 @@ def clip_coefficient(grads, max_norm, multiply_factor=1.0):
 
 
 # ----------------------------------------------------------------------------------------------------
+# concatenated ('vl' / 'al') encoders and the DCL loss — SURVEY.md 8f "next" rows 1-2.  Restated and pinned now so
+# that the CUDA side of the pretraining path has its checker; no product code uses them yet.
+# ----------------------------------------------------------------------------------------------------
+def encoder_multi(sd, cfg, parts, prefix="encoder_wrapper.fusion_model."):
+    """models/transformer/transformer_encoder.py:116-232 for encoder_type 'vl' / 'al': `parts` = [(x, pad, bias,
+    modality), ...] in sequence order (text first).  Sequences are concatenated, the per-modality relative-position
+    biases sit on the diagonal blocks of one (H, S, S) bias (zero across modalities, :148-158), padded keys are -inf
+    (:159-160); every layer runs shared attention and the FFN of each modality on its own rows
+    (transformer_layer.py:203-219); each modality gets its own final LayerNorm (:207-220).  Returns the per-modality
+    feature tensors."""
+    x = torch.cat([p[0] for p in parts], dim=1)
+    pad = torch.cat([p[1] for p in parts], dim=1)
+    if pad.any():
+        x = x * (1 - pad.unsqueeze(-1).type_as(x))
+    H, S = cfg.attention_heads, x.size(1)
+    bias = x.new_zeros(H, S, S)
+    bounds, lo = [], 0
+    for px, _, pb, _ in parts:
+        hi = lo + px.size(1)
+        if pb is not None:
+            bias[:, lo:hi, lo:hi] += pb
+        bounds.append((lo, hi))
+        lo = hi
+    d = x.size(-1)
+    for i in range(cfg.layers):
+        p = prefix + f"layers.{i}."
+        h = F.layer_norm(x, (d,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], cfg.ln_eps)
+        x = x + sd[p + "gamma_1"] * attention(sd, cfg, h, bias, pad, p + "self_attn.")
+        h = F.layer_norm(x, (d,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], cfg.ln_eps)
+        f = torch.cat([geglu_ffn(sd, cfg, h[:, a:b], p + f"{m}_ffn.") for (a, b), (_, _, _, m) in zip(bounds, parts)], dim=1)
+        x = x + sd[p + "gamma_2"] * f
+    outs = []
+    for (a, b), (_, _, _, m) in zip(bounds, parts):
+        outs.append(F.layer_norm(x[:, a:b], (d,), sd[prefix + f"{m}_layer_norm.weight"], sd[prefix + f"{m}_layer_norm.bias"],
+                                 cfg.ln_eps))
+    return outs
+
+
+def dcl_loss(student_features, teacher_features, mask_indices, padding_masks=None, dcl_logit_scale=2.5, label_smoothing=0.1):
+    """criterions/image_text_pretrain_loss.py:187-208: masked student tokens vs ALL (non-padded) teacher tokens of the local
+    batch; CLS dropped; both sides L2-normalised in fp32; label-smoothed NLL, mean over the masked rows."""
+    d = student_features.size(-1)
+    stu = student_features[:, 1:, :].reshape(-1, d)
+    tea = teacher_features.detach()[:, 1:, :].reshape(-1, d)
+    mask = mask_indices[:, 1:].flatten()
+    if padding_masks is not None:
+        keep = torch.nonzero((~padding_masks).flatten(), as_tuple=False).flatten()
+        stu, tea, mask = stu[keep], tea[keep], mask[keep]
+    idx = torch.nonzero(mask, as_tuple=False).flatten()
+    targets = torch.arange(stu.size(0))[idx]
+    sim = dcl_logit_scale * F.normalize(stu[idx].float(), dim=1) @ F.normalize(tea.float(), dim=1).t()
+    return label_smoothed_nll(F.log_softmax(sim, dim=-1, dtype=torch.float32), targets, label_smoothing)
+
+
+# ----------------------------------------------------------------------------------------------------
 # retrieval evaluation
 # ----------------------------------------------------------------------------------------------------
 def recall_eval(image_ids, image_logits, text_ids, text_logits):

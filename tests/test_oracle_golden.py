@@ -96,6 +96,40 @@ def test_backward_vs_reference_autograd(golden_dir, modality):
     assert n >= 45, n          # 2 layers x 21 + adapter + head parameters on the modality's path
 
 
+def test_concatenated_encoders_vs_reference(tiny, golden_dir):
+    """'vl' / 'al' sequences (text + image / text + audio through shared attention, per-modality FFN and final norm):
+    oracle encoder_multi vs the reference's ModelWrapper.forward (tests/golden/pretrain_path.pt)."""
+    fx, sd, cfg, (tok, img, aud, apm) = tiny
+    ref = torch.load(os.path.join(golden_dir, "pretrain_path.pt"), weights_only=False)
+    with torch.no_grad():
+        tx, tp, tb = R.text_adapter(sd, cfg, tok[:2])
+        ix, ip, ib = R.image_adapter(sd, cfg, img)
+        vt, vi = R.encoder_multi(sd, cfg, [(tx, tp, tb, "text"), (ix, ip, ib, "image")])
+        tx, tp, tb = R.text_adapter(sd, cfg, tok[2:4])
+        ax, ap, ab = R.audio_adapter(sd, cfg, aud, apm)
+        at, aa = R.encoder_multi(sd, cfg, [(tx, tp, tb, "text"), (ax, ap, ab, "audio")])
+    for got, key in ((vt, "vl_text"), (vi, "vl_image"), (at, "al_text"), (aa, "al_audio")):
+        torch.testing.assert_close(got, ref[key], atol=3e-5, rtol=1e-4)
+
+
+def test_dcl_loss_vs_reference(golden_dir):
+    ref = torch.load(os.path.join(golden_dir, "pretrain_path.pt"), weights_only=False)["dcl"]
+    gd = torch.Generator().manual_seed(ref["seed"])
+    stu = torch.randn(3, 9, 64, generator=gd, requires_grad=True)
+    tea = stu.detach() + 0.7 * torch.randn(3, 9, 64, generator=gd)
+    msk = torch.rand(3, 9, generator=gd) < 0.4
+    msk[:, 0] = False
+    padm = torch.zeros(3, 8, dtype=torch.bool)
+    padm[1, 6:] = True
+    msk[1, 7:] = False
+    torch.testing.assert_close(R.dcl_loss(stu, tea, msk), ref["no_pad"], atol=1e-6, rtol=1e-6)
+    loss = R.dcl_loss(stu, tea, msk, padm)
+    torch.testing.assert_close(loss, ref["with_pad"], atol=1e-6, rtol=1e-6)
+    loss.backward()
+    torch.testing.assert_close(stu.grad.norm(), ref["grad_norm"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(stu.grad[0, 1:3], ref["grad_head"], atol=1e-6, rtol=1e-5)
+
+
 def test_recall_eval_vs_reference(golden_dir):
     """oracle recall_eval == the reference's Recall metric executed on the same synthetic retrieval sets."""
     for c in torch.load(os.path.join(golden_dir, "recall.pt"), weights_only=False):
