@@ -37,6 +37,8 @@ extern "C" {
 #define OPB_EPI_STORE_F32 3
 #define OPB_EPI_GELU_BF16 4
 
+/* ABI version / status names: the host raises RuntimeError on any non-zero status — the reference's error convention is
+ * Python exceptions only (e.g. transformer_encoder.py:136-137, multihead_attention.py:55-57). */
 int opb_abi_version(void);
 const char* opb_status_string(int status);
 
@@ -101,7 +103,8 @@ int opb_attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const i
                          const int32_t* code_col, const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B,
                          int S, int H, void* stream);
 
-/* lut[h][l] = table[idx[l]][h]  (table fp32 [num_buckets, H], idx int32 [L], lut fp32 [H, L]) */
+/* lut[h][l] = table[idx[l]][h]  (table fp32 [num_buckets, H], idx int32 [L], lut fp32 [H, L]): the rel_pos_table lookup of
+ * adapter/text.py:84-91 / image.py:164-171 restricted to the distinct (code_row - code_col) values. */
 int opb_relpos_lut_build(const float* table, const int32_t* idx, float* lut, int L, int H, void* stream);
 
 /*
@@ -132,17 +135,22 @@ typedef struct opb_gemm_args {
    * producing kernel; each epilogue thread reduces its row's records itself (no opb_ln_stats_finalize launch) */
   const float* ln_partial; int32_t ln_parts; int32_t ln_dim; float ln_eps; int32_t reserved2;
 } opb_gemm_args;
+/* opb_gemm_bf16 plus the fused-LayerNorm / statistics / bf16-copy options: one call = LayerNorm + Linear (+ GeGLU |
+ * + LayerScale + residual) of transformer_layer.py:185-224 / multihead_attention.py:103-107,122-124. */
 int opb_gemm_bf16_ex(const opb_gemm_args* args, void* stream);
 
 /*
  * Row statistics + cast: out_bf16[r,:] = bf16(x[r,:]) (UN-normalised), mu[r] = mean, rstd[r] = 1/sqrt(var + eps).
  * Prepares the first encoder layer's input for the fused-LayerNorm GEMMs (later layers get the same three tensors
- * from the preceding GEMM's epilogue).
+ * from the preceding GEMM's epilogue): the statistics half of self_attn_layer_norm, transformer_layer.py:185,
+ * components.py:23-26.
  */
 int opb_row_stats_cast(const float* x, int64_t ld_in, void* out_bf16, int64_t ld_out, float* mu, float* rstd,
                        int rows, int dim, float eps, void* stream);
 
-/* mu[r], rstd[r] from `parts` partial (sum, sumsq) records per row (layout [parts, rows, 2]); deterministic order. */
+/* mu[r], rstd[r] from `parts` partial (sum, sumsq) records per row (layout [parts, rows, 2]); deterministic order.
+ * Statistics of the FFN LayerNorm over the 6144-wide GeGLU output (transformer_layer.py:154) and of the inner attention
+ * LayerNorm (multihead_attention.py:122-123) when they are not reduced inside the consumer GEMM. */
 int opb_ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
                           void* stream);
 
@@ -161,7 +169,8 @@ int opb_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int ou
                   int accumulate, void* stream);
 
 /*
- * fp32 feature rows -> bf16 grouped / channel-padded / halo'd operand of opb_grouped_conv1d_bf16:
+ * fp32 feature rows -> bf16 grouped / channel-padded / halo'd operand of opb_grouped_conv1d_bf16 (the zero padding of
+ * Conv1d(padding = k // 2, groups = 16) in adapter/audio.py:57-80):
  * out[b, halo + t, g, :group_in] = x[b*x_period + x_row_shift + t, g*group_in:(g+1)*group_in] (padding columns zero).
  */
 int opb_pack_group_halo(const float* x, int64_t ldx, void* out, int B, int T, int x_period, int x_row_shift,
@@ -208,12 +217,15 @@ int opb_l2_normalize_rows(const float* x, int64_t ldx, float* y, void* y_bf16, i
 /* x[row,:] = 0 where pad_mask[row] (transformer_encoder.py:139-142). */
 int opb_zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, void* stream);
 
-/* bf16 [rows, cols] (row pitch ld_in) -> [cols, rows] (lays the gathered embeddings out K-major for the gradient GEMM). */
+/* bf16 [rows, cols] (row pitch ld_in) -> [cols, rows]: lays the gathered embeddings out K-major for the gradient GEMM of
+ * criterions/image_text_retrieval_loss.py:95-96 (autograd of `logits @ logits_all.t()`), and every dW = dY^T X operand of
+ * the encoder backward. */
 int opb_transpose_bf16(const void* in, int64_t ld_in, void* out, int rows, int cols, void* stream);
 
 /*
  * fp32 [rows, d] -> bf16 [rows, 3d] split x = hi + lo: side 0 -> [hi|hi|lo] (local operand), side 1 -> [hi|lo|hi]
- * (gathered operand).  One K = 3d GEMM then gives hi.hi + hi.lo + lo.hi, i.e. logits accurate to ~2^-16.
+ * (gathered operand).  One K = 3d GEMM then gives hi.hi + hi.lo + lo.hi, i.e. logits accurate to ~2^-16 — the similarity
+ * matrices of criterions/image_text_retrieval_loss.py:95-96 and metrics/recall.py:33 are fp32 products in the reference.
  */
 int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, void* stream);
 
@@ -290,7 +302,8 @@ int opb_scale_resid_bwd(const float* dx, const void* o, const float* gamma, cons
                         float* dgamma, float* dbias, int rows, int n, int in_period, int in_valid, int in_shift,
                         void* stream);   /* in_valid > 0: output row r reads dx row (r / in_valid) * in_period + in_shift + r % in_valid */
 
-/* out[n] = sum over rows of y bf16 [rows, n] (bias gradients). */
+/* out[n] = sum over rows of y bf16 [rows, n]: bias gradients of the nn.Linear layers (components.py:29-35; q / v / out_proj,
+ * multihead_attention.py:40-43). */
 int opb_colsum_bf16(const void* y, int64_t ldy, float* ws, float* out, int rows, int n, void* stream);
 
 /* Attention backward (multihead_attention.py:107-115): from qkv (q scaled), the forward output `out`, its gradient
@@ -301,7 +314,8 @@ int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const
                       const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
                       float q_scale, void* stream);
 
-/* out[c] (+)= sum_b in[b * ld + c]: gradients of batch-broadcast parameters (cls_embedding, pos_embed). */
+/* out[c] (+)= sum_b in[b * ld + c]: gradients of batch-broadcast parameters (cls_embedding / pos_embed expanded over the
+ * batch, adapter/image.py:239-253, audio.py:194-197). */
 int opb_batch_sum_f32(const float* in, int64_t ld, float* out, int B, int64_t n, int accumulate, void* stream);
 
 /* Adjoint of opb_l2_normalize_rows (F.normalize, one_peace_retrieval.py:116): dx = (dy - y (y.dy)) / |x|; fp32 and / or
