@@ -83,13 +83,16 @@ int opb_grouped_conv1d_bf16(const void* X, const void* W, int rows, int groups, 
  * materialisation of models/transformer/transformer_encoder.py:144-162.
  *   qkv  bf16 [B*S, 3*H*64] (q | k | v, q already scaled), out bf16 [B*S, H*64]
  *   bias fp32 [H, S, s_pad] or NULL (s_pad even, >= S);  key_pad uint8 [B, S] (1 = pad) or NULL
+ *   bias_batch_stride  0: one table shared by the batch; > 0: element stride between per-sample tables [B, H, S, s_pad]
+ *        (the preserve_ids gathers of the pretraining student passes make the bias sample-dependent,
+ *        models/adapter/text.py:92-101, image.py:188-204)
  *   lse  fp32 [B, H, S] or NULL (log-sum-exp per query row, kept for the backward pass)
  *   ln_stats fp32 [H, B*S, 2] or NULL: per-(head, row) partial (sum, sum of squares) of the output row, from which
  *        opb_ln_stats_finalize derives the statistics of the inner LayerNorm (multihead_attention.py:122-123) that
  *        the out_proj GEMM then applies in its epilogue
  */
 int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse,
-                      float* ln_stats, int B, int S, int H, int s_pad, void* stream);
+                      float* ln_stats, int B, int S, int H, int s_pad, int64_t bias_batch_stride, void* stream);
 
 /*
  * tcgen05 / TMEM self-attention for S <= 384 keys (vision, text).  Same math as opb_attention_fwd; the relative-
@@ -97,11 +100,13 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
  * code_row / code_col int32 [S]; built by the adapters from rel_pos_table + rp_bucket — every ONE-PEACE bucket scheme is
  * a function of a per-position code difference plus three CLS ids, adapter/text.py:18-29,62-68, image.py:19-34).
  * lse / ln_stats as in opb_attention_fwd (either may be NULL).
+ * seg_split > 0: the sequence is a concatenation of two modalities ('vl' / 'al', transformer_encoder.py:116-137) with
+ * rows [0, seg_split) and [seg_split, S); the bias is block-diagonal (zero between modalities, :148-158).
  * Returns OPB_ERR_UNSUPPORTED for S > 384 or a LUT larger than 32 KB (callers then use opb_attention_fwd).
  */
 int opb_attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int32_t* code_row,
                          const int32_t* code_col, const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B,
-                         int S, int H, void* stream);
+                         int S, int H, int seg_split, void* stream);
 
 /* lut[h][l] = table[idx[l]][h]  (table fp32 [num_buckets, H], idx int32 [L], lut fp32 [H, L]): the rel_pos_table lookup of
  * adapter/text.py:84-91 / image.py:164-171 restricted to the distinct (code_row - code_col) values. */
@@ -235,6 +240,10 @@ int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, v
  * rows of the other modality in rank-major order, detached); k = d for plain bf16 operands or 3d for the
  * opb_split_bf16x3 layout; scale = device scalar exp(clamp(logit_scale)).
  * Targets: row i -> column i + target_offset (target_offset = rank * b).
+ * n_valid (0 = n): number of real classes when b_all was zero-padded to n % 8 == 0 rows; columns >= n_valid are ignored
+ * (-inf logits, zero gradient).  coef (0 = 1 / (2 b)): weight of a row's loss in the gradient.  These two serve the
+ * single-direction DCL loss (image_text_pretrain_loss.py:187-208: masked student rows vs the local batch's teacher rows,
+ * mean over rows -> coef = 1 / b), which is the same tiled similarity + log-softmax as one InfoNCE direction.
  *   opb_infonce_ws_floats : size (floats) of the partial workspace `ws` for opb_infonce_rows
  *   opb_infonce_rows      : row_lse / row_loss (label-smoothed NLL per row) / row_argmax, all [b]
  *   opb_infonce_reduce    : out3 = {(mean(loss_a) + mean(loss_b)) / 2, #correct a->b, #correct b->a}
@@ -245,12 +254,13 @@ int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, v
 int64_t opb_infonce_ws_floats(int b, int n);
 int opb_infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d,
                      int target_offset, float label_smoothing, float* ws, float* row_lse, float* row_loss,
-                     int* row_argmax, void* stream);
+                     int* row_argmax, int n_valid, void* stream);
 int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argmax_a, const int* argmax_b, int b,
                        int target_offset, float* out3, void* stream);
 int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
                      const float* row_lse, int b, int n, int d, int k_logits, int target_offset,
-                     float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, void* stream);
+                     float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, int n_valid, float coef,
+                     void* stream);
 int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream);
 
 /*
@@ -309,10 +319,11 @@ int opb_colsum_bf16(const void* y, int64_t ldy, float* ws, float* out, int rows,
 /* Attention backward (multihead_attention.py:107-115): from qkv (q scaled), the forward output `out`, its gradient
  * `d_out` and the forward's log-sum-exp, writes dqkv bf16 [B*S, 3*H*64] (dq already multiplied by q_scale, i.e. the
  * gradient of the un-scaled projection) and adds the relative-position-bias gradient into dbias fp32 [H,S,s_pad]
- * (or NULL).  delta: fp32 scratch [B,H,S]. */
+ * (or NULL).  delta: fp32 scratch [B,H,S].  bias_batch_stride as in opb_attention_fwd (bias and dbias then hold one
+ * table per sample). */
 int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
                       const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
-                      float q_scale, void* stream);
+                      float q_scale, int64_t bias_batch_stride, void* stream);
 
 /* out[c] (+)= sum_b in[b * ld + c]: gradients of batch-broadcast parameters (cls_embedding / pos_embed expanded over the
  * batch, adapter/image.py:239-253, audio.py:194-197). */
@@ -353,6 +364,31 @@ int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable
 int opb_topk10_rows(const float* sim, int64_t ld, int32_t* idx, float* val, int R, int C, void* stream);
 int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* row_ids, int R, int32_t* hits,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Pretraining path: preserve_ids gathers, mask-token canvas, sample-dependent / block-diagonal
+ * dense relative-position bias.
+ *   opb_row_gather      : out[r, :dim] = idx[r] >= 0 ? src[idx[r], :dim] : (fill ? fill[:dim] : 0)   (dtype tags OPB_F32 /
+ *                         OPB_BF16; dim % 4 == 0).  Replaces adapter_embedding.gather / pos_embed.gather of
+ *                         models/adapter/text.py:92-95 (image.py:188-192, audio.py:126-128), the decoder canvas
+ *                         `mask_token.repeat(...)[left_preserve_indices] = preserve_embed[...]` (text.py:135-142) and the
+ *                         masked-row / non-padded-row selections of compute_dcl_loss (image_text_pretrain_loss.py:190-202).
+ *   opb_row_scatter_add : dsrc[idx[r], :] += dout[r, :] for idx[r] >= 0 (fp32 accumulation): its adjoint.
+ *   opb_relpos_bias_block : bias[bb, h, lo+i, lo+j] = table[bucket[p_i, p_j], h] for i, j < n, with p_i = ids[bb, i]
+ *                         (negative -> n - 1, the reference's masked_fill of padded slots, text.py:148) or p_i = i when ids
+ *                         is NULL (then Bb = 1).  bias fp32 [Bb, H, S, s_pad], caller zeroes it: one call per modality places
+ *                         that modality's block on the diagonal (transformer_encoder.py:148-158) and, with ids, performs the
+ *                         two-axis bias gather of gather_features (text.py:96-101).
+ *   opb_relpos_bias_block_bwd : dtable[bucket[p_i, p_j], h] += dbias[bb, h, lo+i, lo+j].
+ * ------------------------------------------------------------------------------------------------------------------ */
+int opb_row_gather(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, const float* fill, void* out,
+                   int out_dtype, int64_t ld_out, int64_t rows, int dim, void* stream);
+int opb_row_scatter_add(const void* dout, int dout_dtype, int64_t ld_dout, const int64_t* idx, float* dsrc, int64_t ld_dsrc,
+                        int64_t rows, int dim, void* stream);
+int opb_relpos_bias_block(const float* table, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids, int64_t ids_ld,
+                          int Bb, int n, int lo, float* bias, int S, int s_pad, int H, void* stream);
+int opb_relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids,
+                              int64_t ids_ld, int Bb, int n, int lo, float* dtable, int S, int s_pad, int H, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,9 +25,9 @@ SIGNATURES = {
     "opb_pack_group_halo": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_void_p]),
     "opb_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                  c_int, c_void_p]),
+                                  c_int, c_int64, c_void_p]),
     "opb_attention_tc_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_int, c_int, c_int, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_void_p]),
     "opb_relpos_lut_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "opb_gemm_bf16_ex": (c_int, [c_void_p, c_void_p]),
     "opb_row_stats_cast": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
@@ -46,10 +46,10 @@ SIGNATURES = {
     "opb_split_bf16x3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "opb_infonce_ws_floats": (c_int64, [c_int, c_int]),
     "opb_infonce_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_int, c_void_p]),
     "opb_infonce_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "opb_infonce_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_float, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     "opb_infonce_dscale": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "opb_adam_chunk_elems": (c_int, []),
     "opb_adam_multi_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float,
@@ -76,7 +76,13 @@ SIGNATURES.update({
                                     c_int, c_int, c_int, c_int, c_void_p]),
     "opb_colsum_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "opb_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_int, c_int, c_int, c_int, c_float, c_void_p]),
+                                  c_int, c_int, c_int, c_int, c_float, c_int64, c_void_p]),
+    "opb_row_gather": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "opb_row_scatter_add": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "opb_relpos_bias_block": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int,
+                                      c_int, c_int, c_void_p]),
+    "opb_relpos_bias_block_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int,
+                                          c_int, c_int, c_void_p]),
     "opb_relpos_bias_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
 })
 

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, 4)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
                      const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                      float* __restrict__ ln_stats, int B, int S, int H, int s_pad, int batch_per_cta,
-                     int stage_bias) {
+                     int stage_bias, long bias_bstride) {
   extern __shared__ __align__(16) uint8_t attn_smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(attn_smem_raw);
 
@@ -102,6 +102,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 
   const int qrow_lo = q0 + warp * 16 + g;   // this thread's two query rows
   const int qrow_hi = qrow_lo + 8;
+  // bias_bstride != 0: one (H,S,s_pad) table per batch element (preserve_ids gathers, adapter/text.py:92-101)
   const float* bias_lo;
   const float* bias_hi;
   if (bias != nullptr && stage_bias) {
@@ -112,7 +113,10 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
     bias_hi = bias ? bias + (static_cast<long>(h) * S + (qrow_hi < S ? qrow_hi : 0)) * s_pad : nullptr;
   }
 
+  const float* bias_lo0 = bias_lo;
+  const float* bias_hi0 = bias_hi;
   for (int b = b_begin; b < b_end; ++b) {
+    if (bias != nullptr && !stage_bias) { bias_lo = bias_lo0 + b * bias_bstride; bias_hi = bias_hi0 + b * bias_bstride; }
     const __nv_bfloat16* qbase = qkv + (static_cast<long>(b) * S) * row_pitch + h * kHd;
     const __nv_bfloat16* kbase = qbase + D;
     const __nv_bfloat16* vbase = qbase + 2 * D;
@@ -303,7 +307,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 }
 
 int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, float* ln_stats,
-                  int B, int S, int H, int s_pad, cudaStream_t stream) {
+                  int B, int S, int H, int s_pad, long bias_bstride, cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0) return OPB_ERR_INVALID;
   if (bias != nullptr && (s_pad < S || (s_pad & 3))) return OPB_ERR_INVALID;
   // Staging the bias tile in shared memory costs occupancy (100 KB / CTA -> 2 CTAs per SM) and measured SLOWER on
@@ -311,7 +315,7 @@ int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, vo
   // latency- not bandwidth-bound.  It stays available behind OPB_ATTN_STAGE_BIAS=1 for experiments.
   static const char* env_stage = getenv("OPB_ATTN_STAGE_BIAS");
   static const char* env_bpc = getenv("OPB_ATTN_BPC");
-  int stage_bias = (bias != nullptr && s_pad <= kMaxStagedBiasCols && env_stage != nullptr && env_stage[0] == '1') ? 1 : 0;
+  int stage_bias = (bias != nullptr && bias_bstride == 0 && s_pad <= kMaxStagedBiasCols && env_stage != nullptr && env_stage[0] == '1') ? 1 : 0;
   const size_t smem = sizeof(AttnSmem) + (stage_bias ? sizeof(float) * kQTile * bias_stride_for(s_pad) : 0);
   static size_t configured_smem = 0;
   if (smem > configured_smem) {
@@ -330,7 +334,7 @@ int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, vo
   const long grid = static_cast<long>(H) * q_chunks * ((B + bpc - 1) / bpc);
   attention_fwd_kernel<<<static_cast<unsigned>(grid), 128, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), bias, key_pad, reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats,
-      B, S, H, s_pad, bpc, stage_bias);
+      B, S, H, s_pad, bpc, stage_bias, bias_bstride);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

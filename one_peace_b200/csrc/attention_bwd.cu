@@ -111,7 +111,7 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
                         const float* __restrict__ bias, const uint8_t* __restrict__ key_pad,
                         const float* __restrict__ lse, const float* __restrict__ delta,
                         __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int B, int S, int H, int s_pad,
-                        float q_scale) {
+                        float q_scale, long bias_bstride) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmemDq& sm = *reinterpret_cast<SmemDq*>(smem_raw);
   const int q_chunks = (S + kTile - 1) / kTile;
@@ -142,10 +142,11 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
   float lse_lo = ok_lo ? lse[stat + qrow_lo] : 0.f, lse_hi = ok_hi ? lse[stat + qrow_hi] : 0.f;
   const float dl_lo = ok_lo ? delta[stat + qrow_lo] : 0.f, dl_hi = ok_hi ? delta[stat + qrow_hi] : 0.f;
   const bool live_lo = ok_lo && lse_lo > -INFINITY, live_hi = ok_hi && lse_hi > -INFINITY;
-  const float* bias_lo = bias ? bias + (static_cast<long>(h) * S + (ok_lo ? qrow_lo : 0)) * s_pad : nullptr;
-  const float* bias_hi = bias ? bias + (static_cast<long>(h) * S + (ok_hi ? qrow_hi : 0)) * s_pad : nullptr;
-  float* db_lo = dbias ? dbias + (static_cast<long>(h) * S + (ok_lo ? qrow_lo : 0)) * s_pad : nullptr;
-  float* db_hi = dbias ? dbias + (static_cast<long>(h) * S + (ok_hi ? qrow_hi : 0)) * s_pad : nullptr;
+  const long boff = b * bias_bstride;       // != 0: one (H,S,s_pad) table (and gradient table) per batch element
+  const float* bias_lo = bias ? bias + boff + (static_cast<long>(h) * S + (ok_lo ? qrow_lo : 0)) * s_pad : nullptr;
+  const float* bias_hi = bias ? bias + boff + (static_cast<long>(h) * S + (ok_hi ? qrow_hi : 0)) * s_pad : nullptr;
+  float* db_lo = dbias ? dbias + boff + (static_cast<long>(h) * S + (ok_lo ? qrow_lo : 0)) * s_pad : nullptr;
+  float* db_hi = dbias ? dbias + boff + (static_cast<long>(h) * S + (ok_hi ? qrow_hi : 0)) * s_pad : nullptr;
   const uint8_t* kp = key_pad ? key_pad + static_cast<long>(b) * S : nullptr;
 
   uint32_t qf[4][4], dof[4][4];
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(128)
 attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_out,
                          const float* __restrict__ bias, const uint8_t* __restrict__ key_pad,
                          const float* __restrict__ lse, const float* __restrict__ delta,
-                         __nv_bfloat16* __restrict__ dqkv, int B, int S, int H, int s_pad) {
+                         __nv_bfloat16* __restrict__ dqkv, int B, int S, int H, int s_pad, long bias_bstride) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmemDkv& sm = *reinterpret_cast<SmemDkv*>(smem_raw);
   const int k_chunks = (S + kTile - 1) / kTile;
@@ -310,8 +311,8 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
       const bool q_ok0 = qg < S && l0 > -INFINITY, q_ok1 = (qg + 1) < S && l1 > -INFINITY;
       float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
       if (bias != nullptr) {
-        const float* br0 = bias + (static_cast<long>(h) * S + (qg < S ? qg : 0)) * s_pad;
-        const float* br1 = bias + (static_cast<long>(h) * S + (qg + 1 < S ? qg + 1 : 0)) * s_pad;
+        const float* br0 = bias + b * bias_bstride + (static_cast<long>(h) * S + (qg < S ? qg : 0)) * s_pad;
+        const float* br1 = bias + b * bias_bstride + (static_cast<long>(h) * S + (qg + 1 < S ? qg + 1 : 0)) * s_pad;
         if (!dead_lo) { b00 = br0[key_lo]; b01 = br1[key_lo]; }
         if (!dead_hi) { b10 = br0[key_hi]; b11 = br1[key_hi]; }
       }
@@ -352,7 +353,7 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
 
 int attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
                   const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
-                  float q_scale, cudaStream_t stream) {
+                  float q_scale, long bias_bstride, cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0 || lse == nullptr || delta == nullptr) return OPB_ERR_INVALID;
   if (bias != nullptr && (s_pad < S || (s_pad & 3))) return OPB_ERR_INVALID;
   if (dbias != nullptr && bias == nullptr) return OPB_ERR_INVALID;
@@ -371,11 +372,11 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * chunks);
   attention_bwd_dq_kernel<<<grid, 128, sizeof(SmemDq), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), bias, key_pad, lse,
-      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, B, S, H, s_pad, q_scale);
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, B, S, H, s_pad, q_scale, bias_bstride);
   if (cudaGetLastError() != cudaSuccess) return OPB_ERR_CUDA;
   attention_bwd_dkv_kernel<<<grid, 128, sizeof(SmemDkv), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), bias, key_pad, lse,
-      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), B, S, H, s_pad);
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), B, S, H, s_pad, bias_bstride);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, int lut_len,
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
-                    float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols) {
+                    float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols,
+                    int seg_split) {
   // no static shared memory in this kernel: the dynamic window starts at the (1024-aligned) base of the CTA's shared
   // memory.  The 112 KB + barriers must fit twice per SM, so there is no room for alignment slack; verify instead.
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
@@ -196,6 +197,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       named_bar_sync(1, 128);
     }
     const int crow = code_row[row_valid ? qrow : 0];
+    // concatenated sequences ('vl' / 'al', transformer_encoder.py:148-158): the relative-position bias is block-diagonal —
+    // a row only sees the bias of the keys of its own modality segment [seg_lo, seg_hi); zero across segments
+    const int seg_lo = (seg_split > 0 && qrow >= seg_split) ? seg_split : 0;
+    const int seg_hi = (seg_split > 0 && qrow < seg_split) ? seg_split : S;
     mbar_wait(&bars->lut, 0);
     OPB_T(1);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
@@ -223,8 +228,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
           }
           float bia[32];
           const bool full = key0 + 32 <= S;
+          const bool in_seg = key0 >= seg_lo && key0 + 32 <= seg_hi;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) bia[j] = (full || key0 + j < S) ? s_lut[idx[j]] : 0.f;
+          for (int j = 0; j < 32; ++j) bia[j] = (in_seg || (key0 + j >= seg_lo && key0 + j < seg_hi)) ? s_lut[idx[j]] : 0.f;
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -368,8 +374,10 @@ int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
-                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, cudaStream_t stream) {
+                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
+                     cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
+  if (seg_split < 0 || seg_split >= S) return OPB_ERR_INVALID;
   const int nkb = (S + kTcK - 1) / kTcK;
   if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
   if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col) & 15) != 0)
@@ -394,10 +402,10 @@ int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* 
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
   if (v)
     attention_tc_kernel<true><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
-                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols);
+                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   else
     attention_tc_kernel<false><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
-                                                           reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols);
+                                                           reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

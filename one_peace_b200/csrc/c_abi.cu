@@ -7,7 +7,7 @@
 
 extern "C" {
 
-int opb_abi_version(void) { return 1; }
+int opb_abi_version(void) { return 2; }
 
 const char* opb_status_string(int status) {
   switch (status) {
@@ -43,17 +43,17 @@ int opb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
 }
 
 int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse,
-                      float* ln_stats, int B, int S, int H, int s_pad, void* stream) {
-  if (qkv == nullptr || out == nullptr) return OPB_ERR_INVALID;
-  return opb::attention_fwd(qkv, bias, key_pad, out, lse, ln_stats, B, S, H, s_pad,
+                      float* ln_stats, int B, int S, int H, int s_pad, int64_t bias_batch_stride, void* stream) {
+  if (qkv == nullptr || out == nullptr || bias_batch_stride < 0) return OPB_ERR_INVALID;
+  return opb::attention_fwd(qkv, bias, key_pad, out, lse, ln_stats, B, S, H, s_pad, bias_batch_stride,
                             static_cast<cudaStream_t>(stream));
 }
 
 int opb_attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int32_t* code_row,
                          const int32_t* code_col, const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B,
-                         int S, int H, void* stream) {
+                         int S, int H, int seg_split, void* stream) {
   if (!qkv || !lut || !code_row || !code_col || !out) return OPB_ERR_INVALID;
-  return opb::attention_tc_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H,
+  return opb::attention_tc_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split,
                                static_cast<cudaStream_t>(stream));
 }
 
@@ -180,10 +180,10 @@ int64_t opb_infonce_ws_floats(int b, int n) { return opb::infonce_ws_floats(b, n
 
 int opb_infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d,
                      int target_offset, float label_smoothing, float* ws, float* row_lse, float* row_loss,
-                     int* row_argmax, void* stream) {
+                     int* row_argmax, int n_valid, void* stream) {
   if (!a_local || !b_all || !scale || !ws || !row_lse || !row_loss || !row_argmax) return OPB_ERR_INVALID;
   return opb::infonce_rows(a_local, b_all, scale, b, n, d, target_offset, label_smoothing, ws, row_lse, row_loss,
-                           row_argmax, static_cast<cudaStream_t>(stream));
+                           row_argmax, n_valid, static_cast<cudaStream_t>(stream));
 }
 
 int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argmax_a, const int* argmax_b, int b,
@@ -195,10 +195,11 @@ int opb_infonce_reduce(const float* loss_a, const float* loss_b, const int* argm
 
 int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
                      const float* row_lse, int b, int n, int d, int k_logits, int target_offset,
-                     float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, void* stream) {
+                     float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, int n_valid, float coef,
+                     void* stream) {
   if (!a_local || !b_all || !bT_all || !scale || !row_lse || !g_ws || !ws_gz || !grad_a) return OPB_ERR_INVALID;
   return opb::infonce_grad(a_local, b_all, bT_all, scale, row_lse, b, n, d, k_logits, target_offset, label_smoothing,
-                           g_ws, ws_gz, grad_a, static_cast<cudaStream_t>(stream));
+                           g_ws, ws_gz, grad_a, n_valid, coef, static_cast<cudaStream_t>(stream));
 }
 
 int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream) {
@@ -298,10 +299,10 @@ int opb_colsum_bf16(const void* y, int64_t ldy, float* ws, float* out, int rows,
 
 int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
                       const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
-                      float q_scale, void* stream) {
-  if (!qkv || !out || !d_out || !dqkv) return OPB_ERR_INVALID;
+                      float q_scale, int64_t bias_batch_stride, void* stream) {
+  if (!qkv || !out || !d_out || !dqkv || bias_batch_stride < 0) return OPB_ERR_INVALID;
   return opb::attention_bwd(qkv, out, d_out, bias, key_pad, lse, delta, dqkv, dbias, B, S, H, s_pad, q_scale,
-                            static_cast<cudaStream_t>(stream));
+                            bias_batch_stride, static_cast<cudaStream_t>(stream));
 }
 
 int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H,
@@ -319,6 +320,33 @@ int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* 
                     void* stream) {
   if (!idx || !cand_ids || !row_ids || !hits) return OPB_ERR_INVALID;
   return opb::recall_hits(idx, cand_ids, row_ids, R, hits, static_cast<cudaStream_t>(stream));
+}
+
+int opb_row_gather(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, const float* fill, void* out,
+                   int out_dtype, int64_t ld_out, int64_t rows, int dim, void* stream) {
+  if (!src || !idx || !out) return OPB_ERR_INVALID;
+  return opb::row_gather(src, src_dtype, ld_src, idx, fill, out, out_dtype, ld_out, rows, dim,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int opb_row_scatter_add(const void* dout, int dout_dtype, int64_t ld_dout, const int64_t* idx, float* dsrc, int64_t ld_dsrc,
+                        int64_t rows, int dim, void* stream) {
+  if (!dout || !idx || !dsrc) return OPB_ERR_INVALID;
+  return opb::row_scatter_add(dout, dout_dtype, ld_dout, idx, dsrc, ld_dsrc, rows, dim, static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_bias_block(const float* table, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids, int64_t ids_ld,
+                          int Bb, int n, int lo, float* bias, int S, int s_pad, int H, void* stream) {
+  if (!table || !bucket || !bias) return OPB_ERR_INVALID;
+  return opb::relpos_bias_block(table, bucket, ld_bucket, ids, ids_ld, Bb, n, lo, bias, S, s_pad, H,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids,
+                              int64_t ids_ld, int Bb, int n, int lo, float* dtable, int S, int s_pad, int H, void* stream) {
+  if (!dbias || !bucket || !dtable) return OPB_ERR_INVALID;
+  return opb::relpos_bias_block_bwd(dbias, bucket, ld_bucket, ids, ids_ld, Bb, n, lo, dtable, S, s_pad, H,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

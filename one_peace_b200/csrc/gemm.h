@@ -62,6 +62,7 @@ struct GemmEpilogue {
   float eps = 0.f;                   // label smoothing
   float eps_i = 0.f;                 // eps / (N - 1)
   float coef = 1.f;                  // 1 / (2 b)
+  int n_valid = 0;                   // > 0: only columns < n_valid are classes (B rows beyond it are zero padding up to N % 8 == 0)
 };
 
 // C = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major with pitches lda, ldb (elements).

@@ -722,6 +722,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const float scale = *ep.scale_ptr;
         const int col0 = n_blk * kBlockN;
         const int tgt = row + ep.target_offset;
+        const int nv = ep.n_valid > 0 ? ep.n_valid : N;
         float m = -INFINITY, ssum = 0.f, zsum = 0.f, best = -INFINITY, ztgt = 0.f;
         int best_idx = 0;
         bool has_tgt = false;
@@ -740,7 +741,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + c + j;
-            const float z = (col < N) ? scale * __uint_as_float(v[j]) : -INFINITY;
+            const float z = (col < nv) ? scale * __uint_as_float(v[j]) : -INFINITY;
             v[j] = __float_as_uint(z);
             cm = fmaxf(cm, z);
             if (z > best) { best = z; best_idx = col; }
@@ -770,6 +771,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int tgt = row + ep.target_offset;
         const float lse = row_ok ? ep.row_lse[row] : 0.f;
         const float hit = 1.f - ep.eps - ep.eps_i;
+        const int nv = ep.n_valid > 0 ? ep.n_valid : N;
         float gz = 0.f;
 #pragma unroll 1
         for (int c = 0; c < kBlockN; c += 32) {
@@ -792,6 +794,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               const float z = scale * __uint_as_float(v[j + e]);
               float g = __expf(z - lse) - ep.eps_i;
               if (col + e == tgt) g -= hit;
+              if (col + e >= nv) g = 0.f;
               gz += g * z;
               gq[e] = g * gscale;
             }

@@ -186,16 +186,18 @@ long infonce_ws_floats(int b, int n) { return static_cast<long>(n_tiles_of(n)) *
 
 // forward for one direction: row_lse / row_loss / row_argmax
 int infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
-                 float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, cudaStream_t stream) {
-  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0) return OPB_ERR_INVALID;
+                 float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, int n_valid, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0 || n_valid < 0 || n_valid > n) return OPB_ERR_INVALID;
+  const int n_cls = n_valid > 0 ? n_valid : n;
   GemmEpilogue ep;
   ep.out = ws;            // unused by this epilogue but must be non-null for the generic checks
   ep.scale_ptr = scale;
   ep.ws = ws;
   ep.target_offset = target_offset;
+  ep.n_valid = n_valid;
   int rc = gemm_bf16(a_local, d, b_all, d, b, n, d, EPI_LSE_PARTIAL, ep, 0, stream);
   if (rc != OPB_OK) return rc;
-  infonce_merge_kernel<<<(b + 127) / 128, 128, 0, stream>>>(ws, n_tiles_of(n), b, n, eps, row_lse, row_loss,
+  infonce_merge_kernel<<<(b + 127) / 128, 128, 0, stream>>>(ws, n_tiles_of(n), b, n_cls, eps, row_lse, row_loss,
                                                             row_argmax);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
@@ -209,8 +211,10 @@ int infonce_reduce(const float* loss_a, const float* loss_b, const int* am_a, co
 // backward for one direction: grad_a fp32 [b, d] = (s / 2b) G B_all ; ws_gz [n_tiles, b] row partials of sum G z
 int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
                  const float* row_lse, int b, int n, int d, int k_logits, int target_offset, float eps, void* g_ws,
-                 float* ws_gz, float* grad_a, cudaStream_t stream) {
-  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0 || k_logits % 8 != 0) return OPB_ERR_INVALID;
+                 float* ws_gz, float* grad_a, int n_valid, float coef, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0 || k_logits % 8 != 0 || n_valid < 0 || n_valid > n)
+    return OPB_ERR_INVALID;
+  const int n_cls = n_valid > 0 ? n_valid : n;
   GemmEpilogue ep;
   ep.out = g_ws;
   ep.ldo = n;
@@ -219,8 +223,9 @@ int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, con
   ep.ws = ws_gz;
   ep.target_offset = target_offset;
   ep.eps = eps;
-  ep.eps_i = (eps != 0.f) ? eps / (n - 1) : 0.f;
-  ep.coef = 1.f / (2.f * b);
+  ep.n_valid = n_valid;
+  ep.eps_i = (eps != 0.f) ? eps / (n_cls - 1) : 0.f;
+  ep.coef = coef > 0.f ? coef : 1.f / (2.f * b);
   int rc = gemm_bf16(a_local, k_logits, b_all, k_logits, b, n, k_logits, EPI_SOFTMAX_GRAD, ep, 0, stream);
   if (rc != OPB_OK) return rc;
   GemmEpilogue e2;

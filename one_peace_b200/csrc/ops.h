@@ -6,9 +6,9 @@
 namespace opb {
 
 int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, float* ln_stats,
-                  int B, int S, int H, int s_pad, cudaStream_t stream);
+                  int B, int S, int H, int s_pad, long bias_bstride, cudaStream_t stream);
 int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
-                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H,
+                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
                      cudaStream_t stream);
 int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int H, cudaStream_t stream);
 int ln_stats_finalize(const float* partial, int parts, int rows, int dim, float eps, float* mu, float* rstd,
@@ -42,12 +42,12 @@ int transpose_bf16(const void* in, long ld_in, void* out, int rows, int cols, cu
 int split_bf16x3(const float* x, void* out, long rows, int d, int side, cudaStream_t stream);
 long infonce_ws_floats(int b, int n);
 int infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
-                 float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, cudaStream_t stream);
+                 float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, int n_valid, cudaStream_t stream);
 int infonce_reduce(const float* loss_a, const float* loss_b, const int* am_a, const int* am_b, int b,
                    int target_offset, float* out3, cudaStream_t stream);
 int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, const float* scale,
                  const float* row_lse, int b, int n, int d, int k_logits, int target_offset, float eps, void* g_ws,
-                 float* ws_gz, float* grad_a, cudaStream_t stream);
+                 float* ws_gz, float* grad_a, int n_valid, float coef, cudaStream_t stream);
 int infonce_dscale(const float* ws_a, const float* ws_b, int b, int n, float* out, cudaStream_t stream);
 
 // One entry per parameter tensor (device-resident table, 64 bytes; mirrored by ctypes in optim/adam_fused.py)
@@ -102,7 +102,17 @@ int relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, in
                     cudaStream_t stream);
 int attention_bwd(const void* qkv, const void* out, const void* d_out, const float* bias, const uint8_t* key_pad,
                   const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
-                  float q_scale, cudaStream_t stream);
+                  float q_scale, long bias_bstride, cudaStream_t stream);
+
+// ---- pretraining path: row gathers, sample-dependent / block-diagonal dense relative-position bias (gather.cu) ----
+int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, void* out, int out_dtype,
+               long ld_out, long rows, int dim, cudaStream_t stream);
+int row_scatter_add(const void* dout, int dout_dtype, long ld_dout, const int64_t* idx, float* dsrc, long ld_dsrc, long rows,
+                    int dim, cudaStream_t stream);
+int relpos_bias_block(const float* table, const int64_t* bucket, long ld_bucket, const int64_t* ids, long ids_ld, int Bb,
+                      int n, int lo, float* bias, int S, int s_pad, int H, cudaStream_t stream);
+int relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, long ld_bucket, const int64_t* ids, long ids_ld, int Bb,
+                          int n, int lo, float* dtable, int S, int s_pad, int H, cudaStream_t stream);
 
 // ---- retrieval evaluation (recall.cu) ----
 int topk10_rows(const float* sim, long ld, int* idx, float* val, int R, int C, cudaStream_t stream);

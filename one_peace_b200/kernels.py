@@ -76,8 +76,26 @@ class RelPosBias:
     """Relative-position bias of one forward in both forms the attention kernels take: the dense fp32 (H,S,S_pad)
     table (mma.sync kernel, any S) and the LUT form (tcgen05 kernel, S <= 384)."""
 
-    def __init__(self, dense=None, lut=None, code_row=None, code_col=None):
-        self.dense, self.lut, self.code_row, self.code_col = dense, lut, code_row, code_col
+    def __init__(self, dense=None, lut=None, code_row=None, code_col=None, seg_split=0):
+        self.dense, self.lut, self.code_row, self.code_col, self.seg_split = dense, lut, code_row, code_col, seg_split
+
+
+def build_segmented_lut(parts, device):
+    """Concatenated ('vl' / 'al') LUT-form bias for `attention_tc`.  parts = [(table fp32 [NB,H], lut_index, n)] per modality
+    in sequence order, lut_index = relpos.build_lut_index(...) result (numpy lut_idx, code_row, code_col) or device tensors.
+    The per-modality LUTs are laid end to end; row codes of the second modality are shifted by the length of the first LUT
+    so that same-modality code differences land in that modality's LUT; the kernel zeroes the cross-modality bias."""
+    assert len(parts) == 2, "two concatenated modalities (transformer_encoder.py:127-134)"
+    luts, rows, cols, off = [], [], [], 0
+    for table, li, n in parts:
+        idx, cr, cc = (torch.as_tensor(a, device=device).to(torch.int32) for a in li)
+        luts.append(relpos_lut_build(table, idx.contiguous()))
+        rows.append(cr[:n] + off)
+        cols.append(cc[:n])
+        off += idx.numel()
+    lut = torch.cat(luts, dim=1).contiguous()
+    pad4 = lambda t: torch.cat([t, torch.zeros((-t.numel()) % 4, dtype=t.dtype, device=t.device)]).contiguous()
+    return RelPosBias(lut=lut, code_row=pad4(torch.cat(rows)), code_col=pad4(torch.cat(cols)), seg_split=parts[0][2])
 
 
 def relpos_lut_build(table, idx):
@@ -91,14 +109,15 @@ def relpos_lut_build(table, idx):
 
 
 def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None, lse=None):
-    """tcgen05 attention (S <= 384).  rp: RelPosBias with the LUT form."""
+    """tcgen05 attention (S <= 384).  rp: RelPosBias with the LUT form (rp.seg_split > 0: two concatenated modalities,
+    block-diagonal bias)."""
     D = H * 64
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
     if out is None:
         out = torch.empty(B * S, D, dtype=torch.bfloat16, device=qkv.device)
     st = _lib.load().opb_attention_tc_fwd(qkv.data_ptr(), rp.lut.data_ptr(), rp.lut.shape[1], rp.code_row.data_ptr(),
                                           rp.code_col.data_ptr(), _ptr(key_pad), out.data_ptr(), _ptr(lse), _ptr(ln_stats), B, S,
-                                          H, _stream())
+                                          H, int(getattr(rp, "seg_split", 0)), _stream())
     _lib.check(st, "opb_attention_tc_fwd")
     _count()
     return out
@@ -153,19 +172,23 @@ def ln_stats_finalize(partial, parts, rows, dim, eps, mu, rstd):
 
 
 def attention(qkv, bias, key_pad, B, S, H, out=None, lse=None, ln_stats=None):
+    """mma.sync attention, any S.  bias: dense fp32 (H,S,S_pad) shared by the batch, or (B,H,S,S_pad) per sample."""
     _need_cuda(qkv, bias, key_pad)
     D = H * 64
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
     if out is None:
         out = torch.empty(B * S, D, dtype=torch.bfloat16, device=qkv.device)
-    s_pad = 0
+    s_pad, bstride = 0, 0
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape[0] == H and bias.shape[1] == S
-        s_pad = bias.shape[2]
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape[-3] == H and bias.shape[-2] == S
+        s_pad = bias.shape[-1]
+        if bias.dim() == 4:
+            assert bias.shape[0] == B
+            bstride = H * S * s_pad
     if key_pad is not None:
         assert key_pad.dtype == torch.uint8 and key_pad.shape == (B, S) and key_pad.is_contiguous()
     st = _lib.load().opb_attention_fwd(qkv.data_ptr(), _ptr(bias), _ptr(key_pad), out.data_ptr(), _ptr(lse),
-                                       _ptr(ln_stats), B, S, H, s_pad, _stream())
+                                       _ptr(ln_stats), B, S, H, s_pad, bstride, _stream())
     _lib.check(st, "opb_attention_fwd")
     _count()
     return out
@@ -325,8 +348,9 @@ def split_bf16x3(x, side):
     return out
 
 
-def infonce_rows(a_local, b_all, scale, target_offset, eps):
+def infonce_rows(a_local, b_all, scale, target_offset, eps, n_valid=0):
     """One direction of the InfoNCE forward.  a_local bf16 [b,k], b_all bf16 [n,k], scale fp32 device scalar.
+    n_valid > 0: only the first n_valid rows of b_all are classes (the rest is zero padding to n % 8 == 0).
     -> (row_lse [b], row_loss [b], row_argmax int32 [b])"""
     _need_cuda(a_local, b_all, scale)
     b, d = a_local.shape
@@ -340,7 +364,7 @@ def infonce_rows(a_local, b_all, scale, target_offset, eps):
     loss = torch.empty(b, dtype=torch.float32, device=dev)
     amax = torch.empty(b, dtype=torch.int32, device=dev)
     st = lib.opb_infonce_rows(a_local.data_ptr(), b_all.data_ptr(), scale.data_ptr(), b, n, d, target_offset, eps,
-                              ws.data_ptr(), lse.data_ptr(), loss.data_ptr(), amax.data_ptr(), _stream())
+                              ws.data_ptr(), lse.data_ptr(), loss.data_ptr(), amax.data_ptr(), int(n_valid), _stream())
     _lib.check(st, "opb_infonce_rows")
     _count(2)
     return lse, loss, amax
@@ -355,8 +379,9 @@ def infonce_reduce(loss_a, loss_b, am_a, am_b, target_offset):
     return out
 
 
-def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps):
-    """-> (grad_a fp32 [b,d], ws_gz) for one direction; a_local/b_all [.,k] (k = d or 3d), bT_all bf16 [d,n]"""
+def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps, n_valid=0, coef=0.0):
+    """-> (grad_a fp32 [b,d], ws_gz) for one direction; a_local/b_all [.,k] (k = d or 3d), bT_all bf16 [d,n];
+    coef = weight of one row's loss (0 -> 1 / (2 b), the two-direction InfoNCE mean)"""
     b, k = a_local.shape
     n = b_all.shape[0]
     d = bT_all.shape[0]
@@ -366,7 +391,7 @@ def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps):
     grad = torch.empty(b, d, dtype=torch.float32, device=dev)
     st = _lib.load().opb_infonce_grad(a_local.data_ptr(), b_all.data_ptr(), bT_all.data_ptr(), scale.data_ptr(),
                                       row_lse.data_ptr(), b, n, d, k, target_offset, eps, g_ws.data_ptr(),
-                                      ws_gz.data_ptr(), grad.data_ptr(), _stream())
+                                      ws_gz.data_ptr(), grad.data_ptr(), int(n_valid), float(coef), _stream())
     _lib.check(st, "opb_infonce_grad")
     _count(2)
     return grad, ws_gz
@@ -459,12 +484,16 @@ def colsum(y, out):
 
 
 def attention_bwd(qkv, out, d_out, bias, key_pad, lse, dqkv, dbias, B, S, H, q_scale):
-    """bias / dbias: dense fp32 (H,S,S_pad) tables (or None); lse fp32 [B,H,S] from `attention(..., lse=)`."""
+    """bias / dbias: dense fp32 (H,S,S_pad) tables shared by the batch, (B,H,S,S_pad) per-sample tables, or None;
+    lse fp32 [B,H,S] from `attention(..., lse=)`."""
     delta = torch.empty(B * H * S, dtype=torch.float32, device=qkv.device)
     s_pad = bias.shape[-1] if bias is not None else 0
+    bstride = H * S * s_pad if (bias is not None and bias.dim() == 4) else 0
+    if dbias is not None:
+        assert dbias.shape == bias.shape
     st = _lib.load().opb_attention_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), _ptr(bias), _ptr(key_pad),
                                        lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), _ptr(dbias), B, S, H, s_pad,
-                                       float(q_scale), _stream())
+                                       float(q_scale), bstride, _stream())
     _lib.check(st, "opb_attention_bwd")
     _count(3)
     return dqkv
@@ -551,3 +580,65 @@ def recall_hits(idx, cand_ids, row_ids):
     _lib.check(st, "opb_recall_hits")
     _count()
     return hits
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pretraining path: row gathers, general dense relative-position bias
+# ----------------------------------------------------------------------------------------------------------------
+def row_gather(src, idx, out=None, fill=None, out_dtype=None):
+    """out[r] = src[idx[r]] (idx[r] >= 0) else fill (fp32 [dim]) / 0.  src [n, dim] fp32 / bf16 (row stride free),
+    idx int64 [rows]."""
+    _need_cuda(src, idx)
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and src.stride(-1) == 1 and src.dim() == 2
+    rows, dim = idx.numel(), src.shape[1]
+    if out is None:
+        out = torch.empty(rows, dim, dtype=out_dtype or src.dtype, device=src.device)
+    if rows == 0:
+        return out
+    assert out.stride(-1) == 1 and (fill is None or (fill.dtype == torch.float32 and fill.is_contiguous()))
+    st = _lib.load().opb_row_gather(src.data_ptr(), _dt(src), src.stride(0), idx.data_ptr(), _ptr(fill), out.data_ptr(),
+                                    _dt(out), out.stride(-2), rows, dim, _stream())
+    _lib.check(st, "opb_row_gather")
+    _count()
+    return out
+
+
+def row_scatter_add(dout, idx, dsrc):
+    """dsrc[idx[r]] += dout[r] for idx[r] >= 0; dsrc fp32 [n, dim] (caller zero-initialises)."""
+    _need_cuda(dout, idx, dsrc)
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and dsrc.dtype == torch.float32 and dout.dim() == 2
+    rows, dim = idx.numel(), dout.shape[1]
+    if rows == 0:
+        return dsrc
+    st = _lib.load().opb_row_scatter_add(dout.data_ptr(), _dt(dout), dout.stride(0), idx.data_ptr(), dsrc.data_ptr(),
+                                         dsrc.stride(-2), rows, dim, _stream())
+    _lib.check(st, "opb_row_scatter_add")
+    _count()
+    return dsrc
+
+
+def relpos_bias_block(table, bucket, ids, n, lo, bias, S, H):
+    """Writes one modality's diagonal block of the dense bias canvas `bias` fp32 [Bb, H, S, s_pad] (Bb = 1 when ids is None):
+    bias[bb, h, lo+i, lo+j] = table[bucket[p_i, p_j], h], p = ids[bb] (int64 [Bb, n], -1 = padded slot) or arange(n)."""
+    _need_cuda(table, bucket, bias)
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == H and bias.is_contiguous()
+    assert bucket.dtype == torch.int64 and bucket.stride(1) == 1 and bias.dim() == 4 and bias.shape[1] == H and bias.shape[2] == S
+    Bb = bias.shape[0]
+    if ids is not None:
+        assert ids.dtype == torch.int64 and ids.shape == (Bb, n) and ids.stride(1) == 1
+    st = _lib.load().opb_relpos_bias_block(table.data_ptr(), bucket.data_ptr(), bucket.stride(0), _ptr(ids),
+                                           ids.stride(0) if ids is not None else 0, Bb, n, lo, bias.data_ptr(), S,
+                                           bias.shape[3], H, _stream())
+    _lib.check(st, "opb_relpos_bias_block")
+    _count()
+    return bias
+
+
+def relpos_bias_block_bwd(dbias, bucket, ids, n, lo, dtable, S, H):
+    Bb = dbias.shape[0]
+    st = _lib.load().opb_relpos_bias_block_bwd(dbias.data_ptr(), bucket.data_ptr(), bucket.stride(0), _ptr(ids),
+                                               ids.stride(0) if ids is not None else 0, Bb, n, lo, dtable.data_ptr(), S,
+                                               dbias.shape[3], H, _stream())
+    _lib.check(st, "opb_relpos_bias_block_bwd")
+    _count()
+    return dtable

@@ -13,10 +13,23 @@ from .. import kernels as K
 
 
 def _all_gather_cat(t):
-    """utils/data_utils.py:50-85 semantics for equal-sized shards: rank-major concatenation."""
-    out = torch.empty(dist.get_world_size() * t.shape[0], *t.shape[1:], dtype=t.dtype, device=t.device)
+    """utils/data_utils.py:50-85: rank-major concatenation of shards that may differ in length (the last evaluation batch
+    is uneven when the set is not divisible by the world size): exchange the sizes, pad to the longest, gather, trim."""
+    world = dist.get_world_size()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(sizes, n)
+    sizes = sizes.tolist()
+    longest = max(sizes)
+    if t.shape[0] != longest:
+        padded = torch.zeros(longest, *t.shape[1:], dtype=t.dtype, device=t.device)
+        padded[:t.shape[0]].copy_(t)
+        t = padded
+    out = torch.empty(world * longest, *t.shape[1:], dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t.contiguous())
-    return out
+    if all(sz == longest for sz in sizes):
+        return out
+    return torch.cat([out[r * longest:r * longest + sz] for r, sz in enumerate(sizes)], dim=0)
 
 
 class Recall:

@@ -20,6 +20,7 @@ _REC = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("maste
                  ("group", "<i4"), ("p_dtype", "<i4"), ("g_dtype", "<i4"), ("pad", "<i4")])
 assert _REC.itemsize == 64
 _DT = {torch.float32: 0, torch.bfloat16: 1}
+_MAX_GROUPS = 128      # opb_adam_multi_step: n_groups <= 128 (include/onepeace_b200.h)
 
 
 class _Table:
@@ -72,14 +73,17 @@ class Adam(torch.optim.Optimizer):
         return True
 
     def _entries(self):
-        entries, groups = [], []
+        """-> (entries, groups, betas, eps).  `groups` are VIRTUAL groups, one per (param group, step count): the
+        reference keeps the step per parameter (adam.py:207-213), so a parameter that receives its first gradient later
+        than its group-mates (an unused modality branch) gets its own bias correction."""
+        entries, groups, vmap = [], [], {}
         betas = eps = None
         for gi, group in enumerate(self.param_groups):
             if betas is None:
                 betas, eps = tuple(group["betas"]), group["eps"]
             elif tuple(group["betas"]) != betas or group["eps"] != eps:
                 raise NotImplementedError("per-group betas / eps (the reference uses one setting for all groups)")
-            step = None
+            b1, b2 = group["betas"]
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -94,20 +98,20 @@ class Adam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
                     if self.master_weights and p.dtype != torch.float32:
                         st["master"] = p.detach().float().clone()
-                for k in ("exp_avg", "exp_avg_sq"):      # state restored from a checkpoint may be bf16 / on CPU
-                    if st[k].dtype != torch.float32 or st[k].device != p.device:
+                for k in ("exp_avg", "exp_avg_sq", "master"):      # state restored from a checkpoint may be bf16 / on CPU
+                    if k in st and (st[k].dtype != torch.float32 or st[k].device != p.device):
                         st[k] = st[k].to(device=p.device, dtype=torch.float32)
-                st["step"] += 1
-                step = st["step"] if step is None else step
-                if st["step"] != step:
-                    raise NotImplementedError("parameters of one group at different step counts")
+                t = int(st["step"]) + 1
+                vg = vmap.get((gi, t))
+                if vg is None:
+                    if len(groups) >= _MAX_GROUPS:
+                        raise NotImplementedError("more (param group, step count) combinations than the kernel's group table")
+                    vg = vmap[(gi, t)] = len(groups)
+                    groups.append((group["lr"], group["weight_decay"], math.sqrt(1 - b2 ** t) / (1 - b1 ** t)))
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 if g is not p.grad:
                     p.grad = g
-                entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], st.get("master"), gi))
-            t = step or 1
-            b1, b2 = group["betas"]
-            groups.append((group["lr"], group["weight_decay"], math.sqrt(1 - b2 ** t) / (1 - b1 ** t)))
+                entries.append((p.data, g, st["exp_avg"], st["exp_avg_sq"], st.get("master"), vg, p))
         return entries, groups, betas, eps
 
     @torch.no_grad()
@@ -119,7 +123,7 @@ class Adam(torch.optim.Optimizer):
         if not entries:
             return loss
         dev = entries[0][0].device
-        self._table.build(entries, dev)
+        self._table.build([e[:6] for e in entries], dev)
         n = len(groups)
         lr = (ctypes.c_float * n)(*[g[0] for g in groups])
         wd = (ctypes.c_float * n)(*[g[1] for g in groups])
@@ -130,8 +134,34 @@ class Adam(torch.optim.Optimizer):
                                              ctypes.cast(bc, ctypes.c_void_p), n, betas[0], betas[1], eps,
                                              0 if grad_scale is None else grad_scale.data_ptr(),
                                              torch.cuda.current_stream().cuda_stream)
-        _lib.check(st, "opb_adam_multi_step")
+        _lib.check(st, "opb_adam_multi_step")       # state is only advanced once the launch was accepted
+        params = [e[6] for e in entries]
+        for p in params:
+            self.state[p]["step"] += 1
+        # the kernel wrote the parameters through raw pointers: tell autograd / PackCache (components.py) that they changed
+        torch.autograd.graph.increment_version(params)
         return loss
+
+    def load_state_dict(self, state_dict):
+        """torch's Optimizer.load_state_dict casts floating-point state to the PARAMETER dtype; with bf16 parameters that
+        would round exp_avg / exp_avg_sq / the fp32 master to bf16.  Put the saved fp32 tensors back afterwards, as the
+        reference wrapper does (fp16_optimizer_memory_efficent.py:44-62)."""
+        super().load_state_dict(state_dict)
+        from itertools import chain
+        saved_ids = chain(*(g["params"] for g in state_dict["param_groups"]))
+        params = chain(*(g["params"] for g in self.param_groups))
+        id_map = dict(zip(saved_ids, params))
+        for k, v in state_dict["state"].items():
+            p = id_map.get(k)
+            if p is None:
+                continue
+            st = dict(v)
+            for name in ("exp_avg", "exp_avg_sq", "master"):
+                if name in st and torch.is_tensor(st[name]):
+                    st[name] = st[name].detach().to(device=p.device, dtype=torch.float32).clone()
+            if torch.is_tensor(st.get("step")):
+                st["step"] = int(st["step"].item())
+            self.state[p] = st
 
     @torch.no_grad()
     def grad_norm_and_scale(self, multiply_factor=1.0, max_norm=0.0):
@@ -198,7 +228,13 @@ class AdjustAdam(FairseqOptimizer):
         return self.param_groups[0]["lr"]
 
     def step(self, closure=None, scale=1.0, groups=None):
-        return self._optimizer.step(closure)
+        """fairseq_optimizer.py:114-127: `scale` divides the gradients (FusedAdam-style optimizers take it as a kwarg);
+        here it is folded into the kernel's grad_scale."""
+        gs = None
+        if scale != 1.0:
+            dev = next(p for g in self.param_groups for p in g["params"]).device
+            gs = torch.full((1,), 1.0 / float(scale), dtype=torch.float32, device=dev)
+        return self._optimizer.step(closure, grad_scale=gs)
 
     def zero_grad(self):
         for g in self.param_groups:

@@ -81,6 +81,8 @@ class DistributedAdam(torch.optim.Optimizer):
         self.segs = shard_segments(self.offsets, numels, self.lo, self.hi)
         self._table, self._norm_table = _Table(), _Table()
         self.step_count = 0
+        self._pending = None
+        self._has_grad = [True] * len(self._plist)
 
     @property
     def supports_memory_efficient_fp16(self):
@@ -91,8 +93,12 @@ class DistributedAdam(torch.optim.Optimizer):
         return True
 
     def _entries(self):
+        """Shard segments of the parameters that received a gradient this step (the reference's python Adam skips
+        `p.grad is None`, adam.py:188-190; every data-parallel rank runs the same graph, so the set is rank-invariant)."""
         out = []
         for pi, _, ln, so in self.segs:
+            if not self._has_grad[pi]:
+                continue
             gi = self._plist[pi][0]
             sl = slice(so, so + ln)
             out.append((self.pshard[sl], self.gshard[sl], self.exp_avg[sl], self.exp_avg_sq[sl],
@@ -100,10 +106,10 @@ class DistributedAdam(torch.optim.Optimizer):
         return out
 
     @torch.no_grad()
-    def step(self, closure=None, max_norm=0.0, multiply_factor=1.0):
-        """Returns the global gradient norm (fp32 device scalar, after `multiply_factor`); `max_norm` > 0 clips like
-        fairseq's clip_grad_norm_ (coefficient max_norm / (norm + 1e-6), capped at 1)."""
-        loss = closure() if closure is not None else None
+    def _exchange_grads(self):
+        """flat gradient buffer -> reduce-scatter (mean) -> this rank's shard; then the global gradient norm from the
+        shard norms (deterministic two-stage kernel + one scalar all-reduce).  -> fp32 device scalar ||g||_2."""
+        self._has_grad = [p.grad is not None for _, p in self._plist]
         for (gi, p), off in zip(self._plist, self.offsets):
             dst = self.flat_grad[off:off + p.numel()]
             if p.grad is None:
@@ -115,22 +121,54 @@ class DistributedAdam(torch.optim.Optimizer):
         else:
             self.gshard.copy_(self.flat_grad)
         entries = self._entries()
-        lib = _lib.load()
-        stream = torch.cuda.current_stream().cuda_stream
-        # shard norm (deterministic two-stage kernel) -> global norm: one scalar all-reduce of the squared norms
-        nt = self._norm_table
-        nt.build([(e[0], e[1], e[1], e[1], None, e[5]) for e in entries], self.device)
-        out2 = torch.empty(2, dtype=torch.float32, device=self.device)
-        st = lib.opb_grad_norm_clip(nt.tensors.data_ptr(), nt.chunk_tensor.data_ptr(), nt.chunk_off.data_ptr(), nt.n_chunks,
-                                    nt.partial.data_ptr(), 1.0, 0.0, out2.data_ptr(), stream)
-        _lib.check(st, "opb_grad_norm_clip")
-        sq = out2[0:1] * out2[0:1]
+        sq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if entries:
+            nt = self._norm_table
+            nt.build([(e[0], e[1], e[1], e[1], None, e[5]) for e in entries], self.device)
+            out2 = torch.empty(2, dtype=torch.float32, device=self.device)
+            st = _lib.load().opb_grad_norm_clip(nt.tensors.data_ptr(), nt.chunk_tensor.data_ptr(), nt.chunk_off.data_ptr(),
+                                                nt.n_chunks, nt.partial.data_ptr(), 1.0, 0.0, out2.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "opb_grad_norm_clip")
+            sq = out2[0:1] * out2[0:1]
         if self.world > 1:
             dist.all_reduce(sq, group=self.pg)
-        norm = sq.sqrt() * multiply_factor
+        self._pending = (entries, sq.sqrt())
+        return self._pending
+
+    @torch.no_grad()
+    def grad_norm_and_scale(self, multiply_factor=1.0, max_norm=0.0):
+        """Same contract as optim/adam.py `Adam.grad_norm_and_scale` (used by MemoryEfficientBF16Optimizer.clip_grad_norm):
+        fp32 device tensor [2] = {multiply_factor * ||mean-reduced g||_2, grad_scale}.  Performs the gradient exchange;
+        the following step() re-uses it."""
+        _, norm = self._exchange_grads()
+        norm = norm * float(multiply_factor)
         scale = torch.full((1,), float(multiply_factor), dtype=torch.float32, device=self.device)
         if max_norm > 0:
             scale = scale * (max_norm / (norm + 1e-6)).clamp(max=1.0)
+        return torch.cat([norm, scale])
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm=0.0, multiply_factor=1.0, grad_scale=None):
+        """Returns the global gradient norm (fp32 device scalar, after `multiply_factor`); `max_norm` > 0 clips like
+        fairseq's clip_grad_norm_ (coefficient max_norm / (norm + 1e-6), capped at 1).  `grad_scale` (fp32 device scalar)
+        is the wrapper's deferred multiply_grads * clip coefficient (fp16_optimizer_memory_efficent.py:118-130); when it
+        is given `max_norm` / `multiply_factor` are ignored."""
+        loss = closure() if closure is not None else None
+        entries, norm = self._pending if self._pending is not None else self._exchange_grads()
+        self._pending = None
+        norm = norm * multiply_factor
+        if grad_scale is not None:
+            scale = grad_scale.to(torch.float32).reshape(1)
+        else:
+            scale = torch.full((1,), float(multiply_factor), dtype=torch.float32, device=self.device)
+            if max_norm > 0:
+                scale = scale * (max_norm / (norm + 1e-6)).clamp(max=1.0)
+        self.last_grad_norm = norm
+        if not entries:
+            return loss if loss is not None else norm
+        lib = _lib.load()
+        stream = torch.cuda.current_stream().cuda_stream
         # fused Adam on the shard
         self.step_count += 1
         t = self._table
@@ -152,9 +190,35 @@ class DistributedAdam(torch.optim.Optimizer):
             dist.all_gather_into_tensor(self.flat_param, self.pshard, group=self.pg)
         else:
             self.flat_param.copy_(self.pshard)
-        self.last_grad_norm = norm
+        # parameters are views of flat_param written by a collective / raw pointers: bump their version counters so
+        # cached kernel-ready packs (components.PackCache) are rebuilt
+        torch.autograd.graph.increment_version([p for _, p in self._plist])
         return loss if loss is not None else norm
 
     def state_bytes_per_rank(self):
         per = 8 + (4 if self.master is not None else 0)
         return self.shard * per
+
+    # ---- checkpointing: rank-local shard state (Apex DistributedFusedAdam also saves per-rank shards) ----
+    def state_dict(self):
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        return {"distributed_adam": {"world": self.world, "rank": self.rank, "total": self.total, "shard": self.shard,
+                                     "step": self.step_count, "exp_avg": self.exp_avg.clone(),
+                                     "exp_avg_sq": self.exp_avg_sq.clone(),
+                                     "master": None if self.master is None else self.master.clone()},
+                "param_groups": groups}
+
+    def load_state_dict(self, state_dict):
+        st = state_dict["distributed_adam"]
+        if (st["world"], st["rank"], st["total"], st["shard"]) != (self.world, self.rank, self.total, self.shard):
+            raise ValueError("DistributedAdam state was saved with a different world size / rank / parameter layout")
+        self.step_count = int(st["step"])
+        self.exp_avg.copy_(st["exp_avg"].to(torch.float32))
+        self.exp_avg_sq.copy_(st["exp_avg_sq"].to(torch.float32))
+        if self.master is not None:
+            if st["master"] is None:
+                raise ValueError("state has no fp32 master shard")
+            self.master.copy_(st["master"].to(torch.float32))
+            self.pshard.copy_(self.master)
+        for g, saved in zip(self.param_groups, state_dict["param_groups"]):
+            g.update(saved)

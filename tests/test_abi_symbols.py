@@ -33,4 +33,4 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     lib = _lib.load()
     # null pointers / bad shapes are refused before any CUDA call
     assert lib.opb_layernorm(None, 0, 8, None, 1, 8, None, None, 4, 8, ctypes.c_float(1e-5), 0, 0, 0, 0, 0, 0, 0, 0, 0, None) == 1
-    assert lib.opb_attention_fwd(None, None, None, None, None, None, 1, 1, 1, 0, None) == 1
+    assert lib.opb_attention_fwd(None, None, None, None, None, None, 1, 1, 1, 0, 0, None) == 1

@@ -190,3 +190,104 @@ def test_two_rank_sharded_adam_nccl():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok=True" in r.stdout
+
+
+def test_forward_after_optimizer_steps_uses_updated_weights():
+    """the fused Adam kernel writes parameters through raw pointers; every cached kernel-ready pack
+    (concatenated QKV, LN-folded weights, fp32 LayerNorm copies, rel-pos LUTs) must be rebuilt.  Two steps, then the
+    inference forward and the training forward must both equal the oracle evaluated on the optimizer's own parameters."""
+    need_gpu()
+    import synth
+    from one_peace_b200.one_peace.hub_interface import from_pretrained
+    from one_peace_b200.optim import Adam
+    cfgd = dict(embed_dim=256, ffn=1024, layers=2, heads=4)
+    sd = synth.make_state_dict(**cfgd, modalities=("text",), seed=3)
+    hub = from_pretrained(state_dict=sd, head_type="text", layers=2, embed_dim=256, ffn_embed_dim=1024, attention_heads=4,
+                          device="cuda", dtype="float32")
+    model = hub.model
+    tok, _, _, _ = synth.tiny_inputs(seed=0, n_text=8)
+    tok = tok.cuda()
+    opt = Adam(model.parameters(), lr=3e-2, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0)
+    g = torch.Generator().manual_seed(5)
+    target = torch.randn(8, 256, generator=g).cuda()
+    with torch.no_grad():
+        before = model(src_tokens=tok, encoder_type="text").float().clone()
+    model.train()
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        (model(src_tokens=tok, encoder_type="text").float() * target).sum().backward()
+        opt.step()
+    model.eval()
+    with torch.no_grad():
+        got = model(src_tokens=tok, encoder_type="text").float().cpu()
+    model.train()
+    got_train = model(src_tokens=tok, encoder_type="text").float().detach().cpu()
+    assert torch.nn.functional.cosine_similarity(got, before.cpu()).min() < 0.999, "lr 3e-2 x 2 steps must move the embeddings"
+    cfg = R.OracleConfig(embed_dim=256, ffn_embed_dim=1024, layers=2, attention_heads=4)
+    sd_now = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        want = R.extract_features(sd_now, cfg, "text", src_tokens=tok.cpu())
+    assert torch.nn.functional.cosine_similarity(got, want).min() > 0.999
+    assert torch.nn.functional.cosine_similarity(got_train, want).min() > 0.999
+
+
+def test_adam_state_survives_load_state_dict_with_bf16_params():
+    """torch's Optimizer.load_state_dict casts state to the parameter dtype; exp_avg / exp_avg_sq / the
+    fp32 master must come back as the saved fp32 tensors (reference: fp16_optimizer_memory_efficent.py:44-62)."""
+    need_gpu()
+    from one_peace_b200.optim import Adam
+    g = torch.Generator().manual_seed(1)
+    mk = lambda: [torch.nn.Parameter(torch.randn(1000, generator=torch.Generator().manual_seed(2)).bfloat16().cuda()),
+                  torch.nn.Parameter(torch.randn(37, 5, generator=torch.Generator().manual_seed(3)).bfloat16().cuda())]
+    grads = [[torch.randn(p.shape, generator=g).bfloat16().cuda() for p in mk()] for _ in range(3)]
+    pa = mk()
+    oa = Adam(pa, lr=1e-2, betas=(0.9, 0.98), weight_decay=0.05, master_weights=True)
+    for p, gr in zip(pa, grads[0]):
+        p.grad = gr.clone()
+    oa.step()
+    state = oa.state_dict()
+    state = {"state": {k: {n: (t.clone() if torch.is_tensor(t) else t) for n, t in v.items()} for k, v in state["state"].items()},
+             "param_groups": state["param_groups"]}
+    pb = mk()
+    with torch.no_grad():
+        for q, p in zip(pb, pa):
+            q.copy_(p)
+    ob = Adam(pb, lr=1e-2, betas=(0.9, 0.98), weight_decay=0.05, master_weights=True)
+    ob.load_state_dict(state)
+    for q, p in zip(pb, pa):
+        for n in ("exp_avg", "exp_avg_sq", "master"):
+            assert ob.state[q][n].dtype == torch.float32 and torch.equal(ob.state[q][n], oa.state[p][n]), n
+        assert ob.state[q]["step"] == 1
+    for step in (1, 2):
+        for p, q, gr in zip(pa, pb, grads[step]):
+            p.grad = gr.clone(); q.grad = gr.clone()
+        oa.step(); ob.step()
+    for p, q in zip(pa, pb):
+        assert torch.equal(p.detach(), q.detach()) and torch.equal(oa.state[p]["master"], ob.state[q]["master"])
+
+
+def test_adam_per_parameter_step_counts():
+    """a parameter that gets its first gradient later than its group-mates keeps its own bias correction
+    (optim/adam.py:207-213 tracks `step` per parameter)."""
+    need_gpu()
+    from one_peace_b200.optim import Adam
+    g = torch.Generator().manual_seed(4)
+    a0, b0 = torch.randn(300, generator=g), torch.randn(200, generator=g)
+    ga = [torch.randn(300, generator=g) for _ in range(3)]
+    gb = [None, torch.randn(200, generator=g), torch.randn(200, generator=g)]
+    pa, pb = torch.nn.Parameter(a0.clone().cuda()), torch.nn.Parameter(b0.clone().cuda())
+    opt = Adam([pa, pb], lr=1e-2, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    wa, wb = a0.clone(), b0.clone()
+    ma, va, mb, vb = torch.zeros(300), torch.zeros(300), torch.zeros(200), torch.zeros(200)
+    tb = 0
+    for t in range(3):
+        pa.grad = ga[t].cuda()
+        pb.grad = None if gb[t] is None else gb[t].cuda()
+        opt.step()
+        R.adam_step(wa, ga[t], ma, va, t + 1, 1e-2, 0.9, 0.98, 1e-8, 0.05)
+        if gb[t] is not None:
+            tb += 1
+            R.adam_step(wb, gb[t], mb, vb, tb, 1e-2, 0.9, 0.98, 1e-8, 0.05)
+    torch.testing.assert_close(pa.detach().cpu(), wa, atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(pb.detach().cpu(), wb, atol=1e-6, rtol=1e-5)
+    assert opt.state[pa]["step"] == 3 and opt.state[pb]["step"] == 2

@@ -404,3 +404,157 @@ def test_recall_metric_vs_reference_golden(K, golden_dir):
             assert abs(log[k] - c["log"][k]) < 1e-9, (k, log[k], c["log"][k])
         assert log["img_count"] == c["log"]["img_count"] and log["txt_count"] == c["log"]["txt_count"]
         assert log["predict_txt"] == c["log"]["predict_txt"] and log["predict_img"] == c["log"]["predict_img"]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pretraining-path kernels (csrc/gather.cu, attention segment / per-sample bias, DCL form of the InfoNCE epilogues)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sdt,odt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+def test_row_gather_and_scatter_add(K, sdt, odt):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, dim, rows = 57, 264, 91
+    src = torch.randn(n, dim, device="cuda", generator=g).to(sdt)
+    idx = torch.randint(-1, n, (rows,), device="cuda", generator=g)
+    fill = torch.randn(dim, device="cuda", generator=g)
+    out = K.row_gather(src, idx, fill=fill, out_dtype=odt)
+    want = torch.where((idx >= 0)[:, None], src.float()[idx.clamp_min(0)], fill[None]).to(odt)
+    assert torch.equal(out, want)                                       # a pure copy: bit-exact
+    out0 = K.row_gather(src, idx, out_dtype=odt)
+    assert torch.equal(out0[idx < 0], torch.zeros_like(out0[idx < 0]))
+    # strided source view (rows of a wider matrix)
+    wide = torch.randn(n, dim + 24, device="cuda", generator=g).to(sdt)
+    assert torch.equal(K.row_gather(wide[:, 8:8 + dim], idx.clamp_min(0), out_dtype=sdt), wide[:, 8:8 + dim][idx.clamp_min(0)])
+    # adjoint (duplicates accumulate)
+    dout = torch.randn(rows, dim, device="cuda", generator=g).to(odt)
+    dsrc = torch.zeros(n, dim, device="cuda")
+    K.row_scatter_add(dout, idx, dsrc)
+    ref = torch.zeros(n, dim, device="cuda").index_add_(0, idx[idx >= 0], dout.float()[idx >= 0])
+    torch.testing.assert_close(dsrc, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_relpos_bias_block_with_ids_and_adjoint(K):
+    """bias gather of gather_features (adapter/text.py:96-101) + block-diagonal placement (transformer_encoder.py:148-158)."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    H, n_full, B, n1, n2 = 4, 40, 3, 9, 13
+    S = n1 + n2
+    s_pad = (S + 7) // 8 * 8
+    bucket = torch.randint(0, 50, (n_full, n_full), device="cuda", generator=g)
+    t1 = torch.randn(50, H, device="cuda", generator=g)
+    t2 = torch.randn(50, H, device="cuda", generator=g)
+    ids1 = torch.stack([torch.randperm(n_full, device="cuda", generator=g)[:n1].sort().values for _ in range(B)])
+    ids1[1, -2:] = -1
+    bias = torch.zeros(B, H, S, s_pad, device="cuda")
+    K.relpos_bias_block(t1, bucket, ids1, n1, 0, bias, S, H)
+    bias_shared = torch.zeros(1, H, S, s_pad, device="cuda")
+    K.relpos_bias_block(t2, bucket, None, n2, n1, bias_shared, S, H)
+    pos = ids1.masked_fill(ids1.eq(-1), n1 - 1)
+    full = t1[bucket].permute(2, 0, 1)[None].expand(B, -1, -1, -1)                                   # (B,H,n_full,n_full)
+    want1 = full.gather(2, pos[:, None, :, None].expand(-1, H, -1, n_full)).gather(3, pos[:, None, None, :].expand(-1, H, n1, -1))
+    assert torch.equal(bias[:, :, :n1, :n1], want1)
+    assert torch.count_nonzero(bias[:, :, n1:]) == 0 and torch.count_nonzero(bias[:, :, :, n1:]) == 0
+    assert torch.equal(bias_shared[0, :, n1:S, n1:S], t2[bucket[:n2, :n2]].permute(2, 0, 1))
+    dbias = torch.randn(B, H, S, s_pad, device="cuda", generator=g)
+    dt = torch.zeros_like(t1)
+    K.relpos_bias_block_bwd(dbias, bucket, ids1, n1, 0, dt, S, H)
+    tt = t1.clone().requires_grad_(True)
+    full = tt[bucket].permute(2, 0, 1)[None].expand(B, -1, -1, -1)
+    w = full.gather(2, pos[:, None, :, None].expand(-1, H, -1, n_full)).gather(3, pos[:, None, None, :].expand(-1, H, n1, -1))
+    (w * dbias[:, :, :n1, :n1]).sum().backward()
+    torch.testing.assert_close(dt, tt.grad, atol=1e-4, rtol=1e-4)
+
+
+def _attn_ref(qkv, bias, key_pad, B, S, H):
+    D = H * 64
+    q, k, v = (qkv.float().view(B, S, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    a = q @ k.transpose(-1, -2)
+    if bias is not None:
+        a = a + (bias if bias.dim() == 4 else bias[None])[..., :S]
+    if key_pad is not None:
+        a = a.masked_fill(key_pad.bool()[:, None, None, :], float("-inf"))
+    return (torch.softmax(a, -1) @ v).transpose(1, 2).reshape(B * S, D)
+
+
+def test_attention_per_sample_bias_forward_backward(K):
+    """bias_batch_stride form of opb_attention_fwd / _bwd: one (H,S,S_pad) table per sample."""
+    g = torch.Generator(device="cuda").manual_seed(13)
+    B, S, H = 3, 45, 4
+    s_pad = 48
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    bias = torch.zeros(B, H, S, s_pad, device="cuda")
+    bias[..., :S] = torch.randn(B, H, S, S, device="cuda", generator=g)
+    pad = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+    pad[1, -5:] = 1
+    lse = torch.empty(B * H * S, device="cuda")
+    out = K.attention(qkv, bias, pad, B, S, H, lse=lse)
+    want = _attn_ref(qkv, bias, pad, B, S, H)
+    assert relerr(out, want) < 2e-2
+    # backward vs torch autograd
+    d_out = (torch.randn(B * S, D, device="cuda", generator=g) * 0.1).bfloat16()
+    dqkv = torch.empty_like(qkv)
+    dbias = torch.zeros_like(bias)
+    K.attention_bwd(qkv, out, d_out, bias, pad, lse, dqkv, dbias, B, S, H, 1.0)
+    qf = qkv.float().clone().requires_grad_(True)
+    bf = bias.clone().requires_grad_(True)
+    (_attn_ref(qf, bf, pad, B, S, H) * d_out.float()).sum().backward()
+    assert relerr(dqkv, qf.grad) < 3e-2
+    assert relerr(dbias[..., :S], bf.grad[..., :S]) < 3e-2
+
+
+def test_attention_tc_two_segments(K):
+    """'vl' form of the tcgen05 attention: concatenated LUTs, block-diagonal bias (zero across modalities)."""
+    import numpy as np
+    from one_peace_b200 import relpos
+    g = torch.Generator(device="cuda").manual_seed(14)
+    B, H, S1, w = 2, 4, 21, 6
+    S2 = w * w + 1
+    S = S1 + S2
+    D = H * 64
+    # buckets: text-style (difference) and image-style (2-D) with CLS ids
+    b1 = (torch.arange(S1)[:, None] - torch.arange(S1)[None, :] + S1).clone()
+    b1[0, :] = 2 * S1 + 1; b1[:, 0] = 2 * S1 + 2; b1[0, 0] = 2 * S1 + 3
+    from one_peace_b200.adapter.image import make_image_bucket_position
+    nrd = (2 * w - 1) ** 2 + 3
+    b2 = make_image_bucket_position(w, nrd)
+    t1 = torch.randn(2 * S1 + 4, H, device="cuda", generator=g)
+    t2 = torch.randn(nrd, H, device="cuda", generator=g)
+    rp = K.build_segmented_lut([(t1, relpos.build_lut_index(b1.numpy(), relpos.text_codes(S1)), S1),
+                                (t2, relpos.build_lut_index(b2.numpy(), relpos.image_codes(S2, w)), S2)], "cuda")
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    pad = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+    pad[1, S1 - 4:S1] = 1
+    out = K.attention_tc(qkv, rp, pad, B, S, H)
+    dense = torch.zeros(H, S, S, device="cuda")
+    dense[:, :S1, :S1] = t1[b1.cuda()].permute(2, 0, 1)
+    dense[:, S1:, S1:] = t2[b2.cuda()].permute(2, 0, 1)
+    want = _attn_ref(qkv, dense, pad, B, S, H)
+    assert relerr(out, want) < 2e-2
+
+
+def test_dcl_form_of_infonce_kernels(K):
+    """n_valid / coef form: single-direction label-smoothed NLL over a ragged number of classes
+    (compute_dcl_loss, image_text_pretrain_loss.py:187-208)."""
+    g = torch.Generator(device="cuda").manual_seed(15)
+    nm, nt, d = 37, 101, 256
+    stu = torch.nn.functional.normalize(torch.randn(nm, d, device="cuda", generator=g), dim=1)
+    tea = torch.nn.functional.normalize(torch.randn(nt, d, device="cuda", generator=g), dim=1)
+    tea[:nm] = torch.nn.functional.normalize(stu + 0.4 * tea[:nm], dim=1)
+    n8 = (nt + 7) // 8 * 8
+    tea_p = torch.zeros(n8, d, device="cuda")
+    tea_p[:nt] = tea
+    scale = torch.tensor([2.5], device="cuda")
+    a3, b3 = K.split_bf16x3(stu, 0), K.split_bf16x3(tea_p, 1)
+    lse, loss, am = K.infonce_rows(a3, b3, scale, 0, 0.1, n_valid=nt)
+    sa = stu.clone().requires_grad_(True)
+    sim = 2.5 * sa @ tea.t()
+    lp = torch.log_softmax(sim, -1)
+    tgt = torch.arange(nm, device="cuda")
+    nll = -lp.gather(1, tgt[:, None]).squeeze(1)
+    eps_i = 0.1 / (nt - 1)
+    want_rows = (1 - 0.1 - eps_i) * nll + eps_i * (-lp.sum(-1))
+    torch.testing.assert_close(loss, want_rows.detach(), atol=2e-4, rtol=2e-4)
+    assert torch.equal(am.long(), sim.argmax(1))
+    grad, _ = K.infonce_grad(a3, b3, K.transpose_bf16(b3, cols=d), scale, lse, 0, 0.1, n_valid=nt, coef=1.0 / nm)
+    want_rows.mean().backward()
+    assert relerr(grad, sa.grad) < 2e-2
