@@ -368,8 +368,9 @@ int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* 
 /* ------------------------------------------------------------------------------------------------------------------
  * Pretraining path: preserve_ids gathers, mask-token canvas, sample-dependent / block-diagonal
  * dense relative-position bias.
- *   opb_row_gather      : out[r, :dim] = idx[r] >= 0 ? src[idx[r], :dim] : (fill ? fill[:dim] : 0)   (dtype tags OPB_F32 /
- *                         OPB_BF16; dim % 4 == 0).  Replaces adapter_embedding.gather / pos_embed.gather of
+ *   opb_row_gather      : out[r, :dim] = (idx[r] >= 0 ? src[idx[r], :dim] : (fill ? fill[:dim] : 0)) + (add ?
+ *                         add[r % add_period, :dim] : 0)   (dtype tags OPB_F32 / OPB_BF16; dim % 4 == 0; fill / add fp32; `add`
+ *                         is the positional table of `x = adapter_embedding + pos_embed`, text.py:157).  Replaces adapter_embedding.gather / pos_embed.gather of
  *                         models/adapter/text.py:92-95 (image.py:188-192, audio.py:126-128), the decoder canvas
  *                         `mask_token.repeat(...)[left_preserve_indices] = preserve_embed[...]` (text.py:135-142) and the
  *                         masked-row / non-padded-row selections of compute_dcl_loss (image_text_pretrain_loss.py:190-202).
@@ -381,8 +382,8 @@ int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* 
  *                         two-axis bias gather of gather_features (text.py:96-101).
  *   opb_relpos_bias_block_bwd : dtable[bucket[p_i, p_j], h] += dbias[bb, h, lo+i, lo+j].
  * ------------------------------------------------------------------------------------------------------------------ */
-int opb_row_gather(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, const float* fill, void* out,
-                   int out_dtype, int64_t ld_out, int64_t rows, int dim, void* stream);
+int opb_row_gather(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, const float* fill, const float* add,
+                   int64_t add_period, void* out, int out_dtype, int64_t ld_out, int64_t rows, int dim, void* stream);
 int opb_row_scatter_add(const void* dout, int dout_dtype, int64_t ld_dout, const int64_t* idx, float* dsrc, int64_t ld_dsrc,
                         int64_t rows, int dim, void* stream);
 int opb_relpos_bias_block(const float* table, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids, int64_t ids_ld,

@@ -77,7 +77,8 @@ SIGNATURES.update({
     "opb_colsum_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "opb_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int, c_float, c_int64, c_void_p]),
-    "opb_row_gather": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "opb_row_gather": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64,
+                               c_int64, c_int, c_void_p]),
     "opb_row_scatter_add": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "opb_relpos_bias_block": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int,
                                       c_int, c_int, c_void_p]),

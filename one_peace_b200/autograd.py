@@ -70,25 +70,41 @@ LAYER_PARAM_NAMES = ("q_proj.weight", "q_proj.bias", "k_proj.weight", "v_proj.we
                      "ffn_ln.weight", "ffn_ln.bias", "fc2.weight", "fc2.bias")
 
 
-def layer_params(layer, modality):
-    """The 21 parameters of one layer on the `modality` path, in LAYER_PARAM_NAMES order."""
+def _check_structure(layer, ffn):
     a = layer.self_attn
-    ffn = getattr(layer, f"{modality}_ffn")
-    if a.ln is None or layer.gamma_1 is None or not isinstance(ffn[2], torch.nn.LayerNorm) or layer.attn_ln is not None \
-            or a.c_attn is not None:
-        raise NotImplementedError("the backward pass is built for the 4B layer structure (magneto_scale_attn, scale_fc, "
-                                  "use_layer_scale on; scale_attn, scale_heads off — finetune_3B.yaml:114-132)")
+    if a.ln is None or not isinstance(ffn[2], torch.nn.LayerNorm) or layer.attn_ln is not None or a.c_attn is not None:
+        raise NotImplementedError("the backward pass is built for the 4B layer structure (magneto_scale_attn, scale_fc on; "
+                                  "scale_attn, scale_heads off — finetune_3B.yaml:114-132)")
+
+
+def shared_params(layer):
+    """The 15 modality-shared parameters of a layer (LAYER_PARAM_NAMES[:15]); gamma_1 / gamma_2 are None when the layer was
+    built with use_layer_scale=False (the pretraining decoder, pretrain_vl_3B.yaml:168)."""
+    a = layer.self_attn
     return [a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.v_proj.weight, a.v_proj.bias, a.out_proj.weight,
             a.out_proj.bias, a.ln.weight, a.ln.bias, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias,
-            layer.final_layer_norm.weight, layer.final_layer_norm.bias, layer.gamma_1, layer.gamma_2, ffn[0].wi_0.weight,
-            ffn[0].wi_1.weight, ffn[2].weight, ffn[2].bias, ffn[3].weight, ffn[3].bias]
+            layer.final_layer_norm.weight, layer.final_layer_norm.bias, layer.gamma_1, layer.gamma_2]
 
 
-def layer_train_pack(layer, modality):
-    """bf16 operands of the layer in both orientations (W for the forward / dW, W^T for dX), rebuilt after each
-    optimizer step."""
-    cache = layer._cache.setdefault("_train_" + modality, PackCache())
-    ps = layer_params(layer, modality)
+def ffn_params(layer, modality):
+    """The 6 parameters of one modality's FFN (LAYER_PARAM_NAMES[15:])."""
+    ffn = getattr(layer, f"{modality}_ffn")
+    _check_structure(layer, ffn)
+    return [ffn[0].wi_0.weight, ffn[0].wi_1.weight, ffn[2].weight, ffn[2].bias, ffn[3].weight, ffn[3].bias]
+
+
+def layer_params(layer, modality):
+    """The 21 parameters of one layer on the `modality` path, in LAYER_PARAM_NAMES order."""
+    if layer.gamma_1 is None:
+        raise NotImplementedError("single-modality fast path expects use_layer_scale (the encoder of every recipe)")
+    return shared_params(layer) + ffn_params(layer, modality)
+
+
+def shared_train_pack(layer):
+    """bf16 operands of the modality-shared half of a layer in both orientations (W for the forward / dW, W^T for dX),
+    rebuilt after each optimizer step."""
+    cache = layer._cache.setdefault("_train_shared", PackCache())
+    ps = shared_params(layer)
 
     def build():
         d = layer.embed_dim
@@ -98,14 +114,28 @@ def layer_train_pack(layer, modality):
         qs = torch.ones(3 * d, device=dev)
         qs[:d] = layer.self_attn.scaling
         wo = bf16(ps[5])
-        w01 = torch.cat([bf16(ps[15]), bf16(ps[16])], 0).contiguous()      # [g | l] halves, not tile-interleaved
-        w2 = bf16(ps[19])
         return dict(wqkv=wqkv, wqkvT=K.transpose_bf16(wqkv), bqkv=bqkv, qscale=qs, wo=wo, woT=K.transpose_bf16(wo),
                     bo=f32(ps[6]), lni_w=f32(ps[7]), lni_b=f32(ps[8]), ln1_w=f32(ps[9]), ln1_b=f32(ps[10]),
-                    ln2_w=f32(ps[11]), ln2_b=f32(ps[12]), g1=f32(ps[13]), g2=f32(ps[14]), w01=w01,
-                    w01T=K.transpose_bf16(w01), lnf_w=f32(ps[17]), lnf_b=f32(ps[18]), w2=w2, w2T=K.transpose_bf16(w2),
-                    b2=f32(ps[20]))
+                    ln2_w=f32(ps[11]), ln2_b=f32(ps[12]), g1=f32(ps[13]) if ps[13] is not None else None,
+                    g2=f32(ps[14]) if ps[14] is not None else None)
+    return cache.get([q for q in ps if q is not None], build)
+
+
+def ffn_train_pack(layer, modality):
+    cache = layer._cache.setdefault("_train_ffn_" + modality, PackCache())
+    ps = ffn_params(layer, modality)
+
+    def build():
+        w01 = torch.cat([bf16(ps[0]), bf16(ps[1])], 0).contiguous()      # [g | l] halves, not tile-interleaved
+        w2 = bf16(ps[4])
+        return dict(w01=w01, w01T=K.transpose_bf16(w01), lnf_w=f32(ps[2]), lnf_b=f32(ps[3]), w2=w2, w2T=K.transpose_bf16(w2),
+                    b2=f32(ps[5]), lnf_eps=getattr(layer, f"{modality}_ffn")[2].eps)
     return cache.get(ps, build)
+
+
+def layer_train_pack(layer, modality):
+    """Shared + FFN packs merged (the shared half is built once per layer, whatever number of modalities train)."""
+    return {**shared_train_pack(layer), **ffn_train_pack(layer, modality)}
 
 
 def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep, fast_bias=None):
@@ -131,7 +161,7 @@ def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep
     h2 = K.layernorm(x2, p["ln2_w"], p["ln2_b"], e(d), eps=layer.final_layer_norm.eps)
     gl = K.gemm(h2, p["w01"], K.EPI_STORE_BF16, e(2 * F_))
     u = K.geglu_fwd(gl, e(F_))
-    u2 = K.layernorm(u, p["lnf_w"], p["lnf_b"], e(F_), eps=1e-5)
+    u2 = K.layernorm(u, p["lnf_w"], p["lnf_b"], e(F_), eps=p["lnf_eps"])
     f = K.gemm(u2, p["w2"], K.EPI_STORE_BF16, e(d), bias=p["b2"])
     x3 = K.scale_resid_fwd(x2, f, p["g2"], row_scale, torch.empty_like(x))
     saved = dict(h1=h1, qkv=qkv, lse=lse, att=att, a2=a2, o=o, x2=x2, h2=h2, gl=gl, u=u, u2=u2, f=f) if keep else None
@@ -159,7 +189,7 @@ def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_sc
     dW2 = _dw(df, s["u2"], ps[19].dtype)
     du2 = _dx(df, p["w2T"], F_)
     dlnf_w, dlnf_b = g(F_), g(F_)
-    du = K.layernorm_bwd(s["u"], du2, p["lnf_w"], p["lnf_b"], e(F_), eps=1e-5, dgamma=dlnf_w, dbeta=dlnf_b)
+    du = K.layernorm_bwd(s["u"], du2, p["lnf_w"], p["lnf_b"], e(F_), eps=p["lnf_eps"], dgamma=dlnf_w, dbeta=dlnf_b)
     dgl = K.geglu_bwd(s["gl"], du, e(2 * F_))
     dW01 = _dw(dgl, s["h2"], ps[15].dtype)
     dh2 = _dx(dgl, p["w01T"], d)

@@ -322,10 +322,10 @@ int opb_recall_hits(const int32_t* idx, const int64_t* cand_ids, const int64_t* 
   return opb::recall_hits(idx, cand_ids, row_ids, R, hits, static_cast<cudaStream_t>(stream));
 }
 
-int opb_row_gather(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, const float* fill, void* out,
-                   int out_dtype, int64_t ld_out, int64_t rows, int dim, void* stream) {
+int opb_row_gather(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, const float* fill, const float* add,
+                   int64_t add_period, void* out, int out_dtype, int64_t ld_out, int64_t rows, int dim, void* stream) {
   if (!src || !idx || !out) return OPB_ERR_INVALID;
-  return opb::row_gather(src, src_dtype, ld_src, idx, fill, out, out_dtype, ld_out, rows, dim,
+  return opb::row_gather(src, src_dtype, ld_src, idx, fill, add, add_period, out, out_dtype, ld_out, rows, dim,
                          static_cast<cudaStream_t>(stream));
 }
 

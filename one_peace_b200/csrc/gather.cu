@@ -45,19 +45,23 @@ OPB_DEVICE void st4g(T* p, const float4 v) {
 template <typename TS, typename TO>
 __global__ void __launch_bounds__(256)
 row_gather_kernel(const TS* __restrict__ src, long ld_src, const int64_t* __restrict__ idx, const float* __restrict__ fill,
-                  TO* __restrict__ out, long ld_out, long rows, int dim) {
+                  const float* __restrict__ add, long add_period, TO* __restrict__ out, long ld_out, long rows, int dim) {
   const long row = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const long s = idx[row];
   TO* o = out + row * ld_out;
-  if (s >= 0) {
-    const TS* p = src + s * ld_src;
-    for (int c = lane * 4; c < dim; c += 128) st4g<TO>(o + c, ld4g<TS>(p + c));
-  } else if (fill != nullptr) {
-    for (int c = lane * 4; c < dim; c += 128) st4g<TO>(o + c, *reinterpret_cast<const float4*>(fill + c));
-  } else {
-    for (int c = lane * 4; c < dim; c += 128) st4g<TO>(o + c, make_float4(0.f, 0.f, 0.f, 0.f));
+  const float* a = add ? add + (row % add_period) * dim : nullptr;      // broadcast addend (positional table)
+  const TS* p = s >= 0 ? src + s * ld_src : nullptr;
+  for (int c = lane * 4; c < dim; c += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p != nullptr) v = ld4g<TS>(p + c);
+    else if (fill != nullptr) v = *reinterpret_cast<const float4*>(fill + c);
+    if (a != nullptr) {
+      const float4 w = *reinterpret_cast<const float4*>(a + c);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    st4g<TO>(o + c, v);
   }
 }
 
@@ -115,16 +119,16 @@ relpos_bias_block_bwd_kernel(const float* __restrict__ dbias, const int64_t* __r
 
 }  // namespace
 
-int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, void* out, int out_dtype,
-               long ld_out, long rows, int dim, cudaStream_t stream) {
+int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, const float* add,
+               long add_period, void* out, int out_dtype, long ld_out, long rows, int dim, cudaStream_t stream) {
   if (rows <= 0 || dim <= 0 || (dim & 3) || (ld_src & 3) || (ld_out & 3)) return OPB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
-      (reinterpret_cast<uintptr_t>(fill) & 15))
+      (reinterpret_cast<uintptr_t>(fill) & 15) || (reinterpret_cast<uintptr_t>(add) & 15) || (add && add_period <= 0))
     return OPB_ERR_INVALID;
   const unsigned blocks = static_cast<unsigned>((rows * 32 + 255) / 256);
 #define OPB_RG(TS, TO)                                                                                              \
-  row_gather_kernel<TS, TO><<<blocks, 256, 0, stream>>>(reinterpret_cast<const TS*>(src), ld_src, idx, fill,        \
-                                                       reinterpret_cast<TO*>(out), ld_out, rows, dim)
+  row_gather_kernel<TS, TO><<<blocks, 256, 0, stream>>>(reinterpret_cast<const TS*>(src), ld_src, idx, fill, add,   \
+                                                       add_period, reinterpret_cast<TO*>(out), ld_out, rows, dim)
   if (src_dtype == 0 && out_dtype == 0) OPB_RG(float, float);
   else if (src_dtype == 0 && out_dtype == 1) OPB_RG(float, __nv_bfloat16);
   else if (src_dtype == 1 && out_dtype == 0) OPB_RG(__nv_bfloat16, float);

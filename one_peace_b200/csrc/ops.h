@@ -105,8 +105,8 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
                   float q_scale, long bias_bstride, cudaStream_t stream);
 
 // ---- pretraining path: row gathers, sample-dependent / block-diagonal dense relative-position bias (gather.cu) ----
-int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, void* out, int out_dtype,
-               long ld_out, long rows, int dim, cudaStream_t stream);
+int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, const float* add,
+               long add_period, void* out, int out_dtype, long ld_out, long rows, int dim, cudaStream_t stream);
 int row_scatter_add(const void* dout, int dout_dtype, long ld_dout, const int64_t* idx, float* dsrc, long ld_dsrc, long rows,
                     int dim, cudaStream_t stream);
 int relpos_bias_block(const float* table, const int64_t* bucket, long ld_bucket, const int64_t* ids, long ids_ld, int Bb,

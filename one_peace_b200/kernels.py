@@ -585,9 +585,9 @@ def recall_hits(idx, cand_ids, row_ids):
 # ----------------------------------------------------------------------------------------------------------------
 # pretraining path: row gathers, general dense relative-position bias
 # ----------------------------------------------------------------------------------------------------------------
-def row_gather(src, idx, out=None, fill=None, out_dtype=None):
-    """out[r] = src[idx[r]] (idx[r] >= 0) else fill (fp32 [dim]) / 0.  src [n, dim] fp32 / bf16 (row stride free),
-    idx int64 [rows]."""
+def row_gather(src, idx, out=None, fill=None, out_dtype=None, add=None):
+    """out[r] = (src[idx[r]] if idx[r] >= 0 else fill (fp32 [dim]) / 0) + add[r % period] (add fp32 [period, dim] or None).
+    src [n, dim] fp32 / bf16 (row stride free), idx int64 [rows]."""
     _need_cuda(src, idx)
     assert idx.dtype == torch.int64 and idx.is_contiguous() and src.stride(-1) == 1 and src.dim() == 2
     rows, dim = idx.numel(), src.shape[1]
@@ -596,8 +596,10 @@ def row_gather(src, idx, out=None, fill=None, out_dtype=None):
     if rows == 0:
         return out
     assert out.stride(-1) == 1 and (fill is None or (fill.dtype == torch.float32 and fill.is_contiguous()))
-    st = _lib.load().opb_row_gather(src.data_ptr(), _dt(src), src.stride(0), idx.data_ptr(), _ptr(fill), out.data_ptr(),
-                                    _dt(out), out.stride(-2), rows, dim, _stream())
+    assert add is None or (add.dtype == torch.float32 and add.is_contiguous() and add.shape[-1] == dim)
+    st = _lib.load().opb_row_gather(src.data_ptr(), _dt(src), src.stride(0), idx.data_ptr(), _ptr(fill), _ptr(add),
+                                    add.numel() // dim if add is not None else 0, out.data_ptr(), _dt(out), out.stride(-2),
+                                    rows, dim, _stream())
     _lib.check(st, "opb_row_gather")
     _count()
     return out

@@ -148,7 +148,7 @@ class TransformerEncoderLayer(nn.Module):
             F_ = w0.shape[0]
             d01 = torch.stack([(w0 @ b2).view(F_ // 128, 128), (w1 @ b2).view(F_ // 128, 128)], dim=1).reshape(2 * F_).contiguous()
             w2, c2, d2 = self._fold(ffn[3].weight, lnf.weight, lnf.bias, ffn[3].bias)
-            return dict(w01=w01, c01=c01, d01=d01, w2=w2, c2=c2, d2=d2,
+            return dict(w01=w01, c01=c01, d01=d01, w2=w2, c2=c2, d2=d2, lnf_eps=lnf.eps,
                         g2=f32(self.gamma_2) if self.gamma_2 is not None else None)
         return cache.get(ps, build)
 
@@ -178,9 +178,9 @@ class TransformerEncoderLayer(nn.Module):
         # OPB_FC2_INLINE_STATS=0 restores the separate ln_stats_finalize launch (96 records / row) for A/B runs.
         n_rec = 2 * ((2 * F_) // 256)                                                                     # 2 records / tile
         if os.environ.get("OPB_FC2_INLINE_STATS", "1") != "0":
-            ln_ffn = dict(ln_partial=(ws["part_c"], n_rec, F_, 1e-5))
+            ln_ffn = dict(ln_partial=(ws["part_c"], n_rec, F_, f["lnf_eps"]))
         else:
-            K.ln_stats_finalize(ws["part_c"], n_rec, M, F_, 1e-5, ws["mu2"], ws["rstd2"])
+            K.ln_stats_finalize(ws["part_c"], n_rec, M, F_, f["lnf_eps"], ws["mu2"], ws["rstd2"])
             ln_ffn = dict(ln_mu=ws["mu2"], ln_rstd=ws["rstd2"])
         K.gemm_ln(ws["u"], f["w2"], K.EPI_RESID_F32, x, ln_colsum=f["c2"], bias=f["d2"], gamma=f["g2"], resid=x,
                   stats_out=ws["part_d"], out_bf16=xb, workspace=ws["tail"], **ln_ffn)
@@ -218,6 +218,6 @@ class TransformerEncoderLayer(nn.Module):
         u = torch.empty(M, F_, dtype=torch.bfloat16, device=dev)
         K.gemm(h, f["w01"], K.EPI_GEGLU_BF16, u)
         if "ln_w" in f:
-            K.layernorm(u, f["ln_w"], f["ln_b"], u, eps=1e-5)
+            K.layernorm(u, f["ln_w"], f["ln_b"], u, eps=getattr(self, f"{modality}_ffn")[2].eps)
         K.gemm(u, f["w2"], K.EPI_RESID_F32, x, bias=f["b2"], gamma=n.get("g2"), resid=x)
         return x

@@ -224,7 +224,7 @@ def test_forward_after_optimizer_steps_uses_updated_weights():
     got_train = model(src_tokens=tok, encoder_type="text").float().detach().cpu()
     assert torch.nn.functional.cosine_similarity(got, before.cpu()).min() < 0.999, "lr 3e-2 x 2 steps must move the embeddings"
     cfg = R.OracleConfig(embed_dim=256, ffn_embed_dim=1024, layers=2, attention_heads=4)
-    sd_now = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    sd_now = {k: (v.detach().float() if v.is_floating_point() else v.detach()).cpu() for k, v in model.state_dict().items()}
     with torch.no_grad():
         want = R.extract_features(sd_now, cfg, "text", src_tokens=tok.cpu())
     assert torch.nn.functional.cosine_similarity(got, want).min() > 0.999
