@@ -157,6 +157,19 @@ class AudioAdapter(torch.nn.Module):
                 out.append(K.RelPosBias(dense=K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads)))
         return out
 
+    def bias_source(self, n, ids=None):
+        if self.rel_pos_table_list is None:
+            return None
+        return dict(tables=[t.weight for t in self.rel_pos_table_list], bucket=self.rp_bucket, n=n, ids=ids)
+
+    def embed_general(self, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None):
+        """General form for the concatenated 'al' encoder (full sequences; the audio preserve_ids / mask-token student passes
+        of audio_text_pretrain_loss.py gather BEFORE the conv positional encoder, audio.py:184-189, and are not built)."""
+        if preserve_ids is not None or preserve_embed is not None:
+            raise NotImplementedError("audio preserve_ids / mask-token student passes are not built")
+        x, pad, _ = self.forward(src_audios, padding_mask)
+        return x, pad, self.bias_source(x.shape[1])
+
     def forward(self, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None):
         """src_audios (B, N) waveform, padding_mask (B, T+1) bool -> (x fp32 (B,T+1,d) with padded rows zeroed,
         padding_mask uint8, [bias (H,S,S_pad)])"""

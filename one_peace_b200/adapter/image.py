@@ -42,14 +42,14 @@ class LayerNorm2D(torch.nn.Module):
 class ImageAdapter(torch.nn.Module):
     def __init__(self, cfg, embed_dim, attention_heads, num_layers=None):
         super().__init__()
-        if cfg.vision_encoder_type != "hmlp":
-            raise NotImplementedError("only the hMLP stem (the 4B config) is built")
+        if cfg.vision_encoder_type not in ("hmlp", "none"):
+            raise NotImplementedError("only the hMLP stem (the 4B config) and 'none' (the pretraining decoder) are built")
         if cfg.layernorm_embedding or cfg.add_type_embedding or cfg.shrink_alpha != 1.0:
             raise NotImplementedError("layernorm_embedding / add_type_embedding / shrink_alpha are off in the 4B config")
         self.attention_heads = attention_heads
         self.embed_dim = embed_dim
         c4 = embed_dim // 4
-        self.embed_images = torch.nn.Sequential(
+        self.embed_images = None if cfg.vision_encoder_type == "none" else torch.nn.Sequential(
             torch.nn.Conv2d(3, c4, kernel_size=4, stride=4), LayerNorm2D(c4), torch.nn.GELU(),
             torch.nn.Conv2d(c4, c4, kernel_size=2, stride=2), LayerNorm2D(c4), torch.nn.GELU(),
             torch.nn.Conv2d(c4, embed_dim, kernel_size=2, stride=2))
@@ -119,10 +119,42 @@ class ImageAdapter(torch.nn.Module):
                 out.append(K.RelPosBias(dense=K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads)))
         return out
 
+    def bias_source(self, n, ids=None):
+        if self.rel_pos_table_list is None:
+            return None
+        return dict(tables=[t.weight for t in self.rel_pos_table_list], bucket=self.rp_bucket, n=n, ids=ids)
+
+    def _pos_table(self, w):
+        """(w*w+1, d) positional table as an autograd function of pos_embed (bicubic resize as a cached linear operator)."""
+        pe = self.pos_embed
+        if w != self.bucket_size:
+            new = (self._resize_matrix(w, pe.device) @ pe[1:].float()).type_as(pe)
+            pe = torch.cat([pe[:1], new], dim=0)
+        return pe
+
+    def embed_general(self, src_images, preserve_ids=None, preserve_embed=None, mask_token=None):
+        """General (pretraining) form of forward (models/adapter/image.py:206-260); see TextAdapter.embed_general."""
+        from ..autograd_general import RowGatherFn
+        from .text import canvas_index, flat_ids
+        B, R = src_images.shape[0], src_images.shape[-1]
+        w = R // 16
+        S = w * w + 1
+        d = self.embed_dim
+        if preserve_embed is not None:
+            x = RowGatherFn.apply(preserve_embed.reshape(-1, d), canvas_index(preserve_ids, S), mask_token,
+                                  self._pos_table(w)).view(B, S, d)
+            return x, None, self.bias_source(S)
+        x, _, _ = self.forward(src_images)                   # full sequence (autograd-tracked when training)
+        if preserve_ids is None:
+            return x, None, self.bias_source(S)
+        Kk = preserve_ids.shape[1]
+        xg = RowGatherFn.apply(x.reshape(B * S, d), flat_ids(preserve_ids, S), None, None).view(B, Kk, d)
+        return xg, preserve_ids.eq(-1).to(torch.uint8).contiguous(), self.bias_source(Kk, preserve_ids.contiguous())
+
     def forward(self, src_images, preserve_ids=None, preserve_embed=None, mask_token=None, is_second_image=False):
         """-> (x fp32 (B, w*w+1, d), None (images are never padded), [bias (H,S,S_pad)])"""
         if preserve_ids is not None or preserve_embed is not None:
-            raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+            return self.embed_general(src_images, preserve_ids, preserve_embed, mask_token)
         if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             return self.forward_train(src_images)
         p = self._pack()

@@ -23,6 +23,26 @@ def make_token_bucket_position(bucket_size, max_position):
     return bucket_pos + bucket_size - 1
 
 
+def flat_ids(preserve_ids, seq_len):
+    """(B,K) position ids (-1 = padded slot) -> int64 [B*K] flat row indices b * seq_len + id, -1 kept."""
+    B = preserve_ids.shape[0]
+    base = torch.arange(B, device=preserve_ids.device)[:, None] * seq_len
+    return torch.where(preserve_ids >= 0, preserve_ids + base, preserve_ids).reshape(-1).contiguous()
+
+
+def canvas_index(preserve_ids, seq_len):
+    """Inverse of the preserve map for the decoder canvas (adapter/text.py:135-142): int64 [B*seq_len], entry (b, s) = row
+    b*K + k of preserve_embed if preserve_ids[b, k] == s, else -1 (mask token)."""
+    B, Kk = preserve_ids.shape
+    dev = preserve_ids.device
+    out = torch.full((B * seq_len,), -1, dtype=torch.int64, device=dev)
+    src = torch.arange(B * Kk, device=dev).view(B, Kk)
+    dst = preserve_ids + torch.arange(B, device=dev)[:, None] * seq_len
+    valid = preserve_ids >= 0
+    out[dst[valid]] = src[valid]
+    return out
+
+
 class TextAdapter(torch.nn.Module):
     def __init__(self, cfg, embed_dim, attention_heads, src_dict=None, num_layers=None):
         super().__init__()
@@ -78,10 +98,49 @@ class TextAdapter(torch.nn.Module):
                 out.append(K.RelPosBias(dense=K.relpos_bias_build(t, self.rp_bucket, seq_len, self.attention_heads)))
         return out
 
+    def bias_source(self, n, ids=None):
+        """What the encoder needs to place this modality's relative-position bias block (autograd_general.BlockBiasFn)."""
+        if self.rel_pos_table_list is None:
+            return None
+        return dict(tables=[t.weight for t in self.rel_pos_table_list], bucket=self.rp_bucket, n=n, ids=ids)
+
+    def embed_general(self, src_tokens, preserve_ids=None, preserve_embed=None, mask_token=None):
+        """General (pretraining) form of forward (models/adapter/text.py:111-164) -> (x fp32 (B,S,d), pad uint8 (B,S), bias
+        source).  preserve_ids (B,K) int64, -1 padded: encoder student pass = rows of (embedding + position) gathered by id
+        (:92-95,146-151); with preserve_embed (B,K,d): decoder canvas = mask token everywhere, the preserved rows scattered
+        to their positions, plus the positional table (:135-142,157)."""
+        from ..autograd import TextEmbedFn
+        from ..autograd_general import RowGatherFn
+        B, T = src_tokens.shape
+        S = T + 1
+        d = self.embed_positions.weight.shape[1]
+        dev = src_tokens.device
+        if preserve_embed is not None:
+            src_idx = canvas_index(preserve_ids, S)
+            x = RowGatherFn.apply(preserve_embed.reshape(-1, d), src_idx, mask_token, self.embed_positions.weight[:S]).view(B, S, d)
+            pad = torch.zeros(B, S, dtype=torch.uint8, device=dev)
+            pad[:, 1:] = src_tokens.eq(self.padding_idx)
+            return x, pad, self.bias_source(S)
+        train = torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters())
+        if train:
+            x, pad = TextEmbedFn.apply(src_tokens, self.embed_tokens.weight, self.embed_positions.weight, self.cls_embedding,
+                                       self.padding_idx)
+        else:
+            p = self._pack()
+            table = self.embed_tokens.weight.detach()
+            if table.dtype not in (torch.float32, torch.bfloat16):
+                table = table.float()
+            x, pad = K.text_embed(src_tokens.contiguous(), table, p["pos"], p["cls"], self.padding_idx)
+        if preserve_ids is None:
+            return x, pad, self.bias_source(S)
+        Kk = preserve_ids.shape[1]
+        xg = RowGatherFn.apply(x.reshape(B * S, d), flat_ids(preserve_ids, S), None, None).view(B, Kk, d)
+        return xg, preserve_ids.eq(-1).to(torch.uint8).contiguous(), self.bias_source(Kk, preserve_ids.contiguous())
+
     def forward(self, src_tokens, preserve_ids=None, preserve_embed=None, mask_token=None):
         """-> (x fp32 (B,T+1,d) with padded rows zeroed, padding_mask uint8 (B,T+1), [bias (H,S,S_pad)])"""
         if preserve_ids is not None or preserve_embed is not None:
-            raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+            return self.embed_general(src_tokens, preserve_ids, preserve_embed, mask_token)
         if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             return self.forward_train(src_tokens)
         p = self._pack()

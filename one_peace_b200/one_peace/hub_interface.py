@@ -6,8 +6,9 @@ part of the accelerated path: ``process_*`` delegate to user-supplied callables.
 """
 import torch
 
+from .one_peace_pretrain import OnePeacePretrainConfig, OnePeacePretrainModel
 from .one_peace_retrieval import OnePeaceRetrievalConfig, OnePeaceRetrievalModel
-from ..unify_model_config import one_peace_4b_encoder_config
+from ..unify_model_config import one_peace_4b_decoder_config, one_peace_4b_encoder_config
 
 
 class _Dictionary:
@@ -26,16 +27,28 @@ class _Dictionary:
 
 def from_pretrained(model_name_or_path=None, model_type="one_peace_retrieval", device="cuda", dtype="float32",
                     state_dict=None, head_type="val", layers=40, embed_dim=1536, ffn_embed_dim=6144,
-                    attention_heads=24, patch_image_size=256, vocab_size=50264):
+                    attention_heads=24, patch_image_size=256, vocab_size=50264, decoder=None, use_audio=None):
     """hub_interface.py:53-73.  Loads ``one-peace.pt``-style state dicts (same parameter names, strict except for
     pretraining-only keys) into the sm_100a model.  ``model_name_or_path`` may be a torch checkpoint whose
     'model' entry is the state dict (fairseq layout) or a bare state dict; alternatively pass ``state_dict``."""
-    if model_type != "one_peace_retrieval":
-        raise NotImplementedError("only the retrieval (embedding) model is built")
-    cfg = OnePeaceRetrievalConfig()
-    cfg.encoder = one_peace_4b_encoder_config(layers, embed_dim, ffn_embed_dim, attention_heads, patch_image_size)
-    with torch.device(device):
-        model = OnePeaceRetrievalModel(cfg, _Dictionary(vocab_size), head_type)
+    if model_type == "one_peace_pretrain":
+        # models/one_peace/one_peace_pretrain.py: encoder + lightweight decoder (pretrain_vl_3B.yaml:92-168); `decoder` =
+        # dict(embed_dim=, ffn_embed_dim=, layers=, attention_heads=) or None for the 4B recipe's 768 / 2048 / 2 / 12
+        cfg = OnePeacePretrainConfig()
+        cfg.encoder = one_peace_4b_encoder_config(layers, embed_dim, ffn_embed_dim, attention_heads, patch_image_size)
+        cfg.encoder.image_adapter.bucket_size = patch_image_size // 16
+        cfg.decoder = one_peace_4b_decoder_config(patch_image_size=patch_image_size, **(decoder or {}))
+        cfg.encoder.use_audio_moe = cfg.decoder.use_audio_moe = bool(use_audio)
+        with torch.device(device):
+            model = OnePeacePretrainModel(cfg, _Dictionary(vocab_size))
+    elif model_type == "one_peace_retrieval":
+        cfg = OnePeaceRetrievalConfig()
+        cfg.encoder = one_peace_4b_encoder_config(layers, embed_dim, ffn_embed_dim, attention_heads, patch_image_size)
+        with torch.device(device):
+            model = OnePeaceRetrievalModel(cfg, _Dictionary(vocab_size), head_type)
+    else:
+        raise NotImplementedError("model_type must be one_peace_retrieval or one_peace_pretrain (the classification heads of "
+                                  "one_peace_classify are outside the accelerated path)")
     if state_dict is None and model_name_or_path is not None:
         ckpt = torch.load(model_name_or_path, map_location="cpu")
         state_dict = ckpt.get("model", ckpt)

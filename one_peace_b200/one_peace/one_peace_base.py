@@ -58,9 +58,14 @@ class ModelWrapper(nn.Module):
                 audio_preserve_ids=None, audio_preserve_embed=None, audio_mask_token=None,
                 encoder_type: Optional[str] = None, return_padding_mask: bool = False):
         """Reference signature (one_peace_base.py:68-129); returns per-token features (B,S,d) fp32."""
-        if any(v is not None for v in (text_preserve_ids, text_preserve_embed, image_preserve_ids, image_preserve_embed,
-                                       audio_preserve_ids, audio_preserve_embed)):
-            raise NotImplementedError("preserve_ids / mask-token inputs belong to the pretraining (DCL) path")
+        general = any(v is not None for v in (text_preserve_ids, text_preserve_embed, image_preserve_ids, image_preserve_embed,
+                                              audio_preserve_ids, audio_preserve_embed)) or encoder_type in ("vl", "al") or \
+            (torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()))
+        if general:
+            return self.forward_general(src_tokens, text_preserve_ids, text_preserve_embed, text_mask_token, src_images,
+                                        image_preserve_ids, image_preserve_embed, image_mask_token, src_audios,
+                                        audio_padding_masks, audio_preserve_ids, audio_preserve_embed, audio_mask_token,
+                                        encoder_type, return_padding_mask)
         info = self.adapt(encoder_type, src_tokens=src_tokens, src_images=src_images, src_audios=src_audios,
                           audio_padding_masks=audio_padding_masks)
         infos = {"text": None, "image": None, "audio": None}
@@ -73,6 +78,32 @@ class ModelWrapper(nn.Module):
         i = ("text", "image", "audio").index(encoder_type)
         res[i], pads[i] = feats, pad
         return (*res, *pads) if return_padding_mask else tuple(res)
+
+
+    def forward_general(self, src_tokens, text_preserve_ids, text_preserve_embed, text_mask_token, src_images,
+                        image_preserve_ids, image_preserve_embed, image_mask_token, src_audios, audio_padding_masks,
+                        audio_preserve_ids, audio_preserve_embed, audio_mask_token, encoder_type, return_padding_mask):
+        """one_peace_base.py:68-129 for every case the single-modality inference path does not cover: concatenated 'vl' / 'al'
+        sequences, preserve_ids student passes, the decoder's mask-token canvas, and per-token features with gradients."""
+        if encoder_type not in ("text", "image", "audio", "vl", "al"):
+            raise NotImplementedError(f"encoder_type={encoder_type!r}")        # 'val' raises in the reference too (:136-137)
+        parts = []
+        if encoder_type in ("text", "vl", "al"):
+            parts.append(("text",) + tuple(self.text_adapter.embed_general(src_tokens, text_preserve_ids, text_preserve_embed,
+                                                                           text_mask_token)))
+        if encoder_type in ("image", "vl"):
+            parts.append(("image",) + tuple(self.image_adapter.embed_general(src_images, image_preserve_ids,
+                                                                             image_preserve_embed, image_mask_token)))
+        if encoder_type in ("audio", "al"):
+            parts.append(("audio",) + tuple(self.audio_adapter.embed_general(src_audios, audio_padding_masks, audio_preserve_ids,
+                                                                             audio_preserve_embed, audio_mask_token)))
+        feats, pads = self.fusion_model.forward_general(parts)
+        res, pmask = [None, None, None], [None, None, None]
+        for (m, x, _, _), f, p in zip(parts, feats, pads):
+            i = ("text", "image", "audio").index(m)
+            res[i] = f
+            pmask[i] = p.bool() if p is not None else torch.zeros(x.shape[:2], dtype=torch.bool, device=x.device)
+        return (*res, *pmask) if return_padding_mask else tuple(res)
 
 
 @register_model("one_peace_base_b200", dataclass=UnifyModelConfig)

@@ -71,6 +71,42 @@ class TransformerEncoder(FairseqEncoder):
                 layer.forward_rows(rows, bias, key_pad, B, S, encoder_type)
         return x, pad
 
+    def forward_general(self, parts):
+        """General encoder forward (transformer_encoder.py:73-232) for concatenated modalities ('vl' / 'al'), preserve_ids
+        student passes and the decoder.  parts = [(modality, x fp32 (B,S_p,d), pad uint8 (B,S_p) or None, bias source or None)]
+        in sequence order.  Returns ([features fp32 (B,S_p,d) per part, after that modality's final LayerNorm], [pad per part]).
+        Differentiable end to end (one_peace_b200/autograd_general.py)."""
+        from ..autograd_general import BlockBiasFn, FinalNormFn, SeqLayout, ZeroPadFn, run_general_stack
+        B, d = parts[0][1].shape[0], parts[0][1].shape[2]
+        dev = parts[0][1].device
+        H = self.num_attention_heads
+        lay = SeqLayout(B, [(m, x.shape[1]) for m, x, _, _ in parts], dev)
+        x_mm = torch.cat([x.reshape(-1, d) for _, x, _, _ in parts], dim=0) if len(parts) > 1 else parts[0][1].reshape(-1, d)
+        pads = [p.to(torch.uint8) if p is not None else torch.zeros(B, x.shape[1], dtype=torch.uint8, device=dev)
+                for _, x, p, _ in parts]
+        any_pad = any(p is not None for _, _, p, _ in parts)
+        if any_pad:                                               # x * (1 - padding_mask), :139-142
+            x_mm = ZeroPadFn.apply(x_mm, torch.cat([p.reshape(-1) for p in pads]).contiguous())
+        srcs = [(pi, bs) for pi, (_, _, _, bs) in enumerate(parts) if bs is not None]
+        biases = []
+        if srcs:                                                  # :144-162: per-modality diagonal blocks of one canvas per table
+            n_tab = len(srcs[0][1]["tables"])
+            for j in range(n_tab):
+                blocks = tuple((bs["bucket"], bs["ids"], bs["n"], lay.los[pi]) for pi, bs in srcs)
+                biases.append(BlockBiasFn.apply((H, lay.S, blocks), *[bs["tables"][j] for _, bs in srcs]))
+        # padded keys are excluded only through the bias (-inf fill, :159-160): without a bias they are attended
+        key_pad = torch.cat(pads, dim=1).contiguous() if (any_pad and biases) else None
+        need_grad = torch.is_grad_enabled() and (x_mm.requires_grad or any(q.requires_grad for q in self.parameters()))
+        out = run_general_stack(self, x_mm.to(torch.float32), lay, key_pad, biases, need_grad)
+        feats = []
+        for pi, (m, x, _, _) in enumerate(parts):
+            ln = getattr(self, f"{m}_layer_norm")
+            rows = out[lay.rows(pi)]
+            if ln is not None:
+                rows = FinalNormFn.apply(rows, ln.weight, ln.bias, ln.eps)
+            feats.append(rows.view(B, x.shape[1], d))
+        return feats, [p if p is not None else None for _, _, p, _ in parts]
+
     def forward(self, text_info, image_info, audio_info, return_all_hiddens: bool = False, encoder_type=None):
         if return_all_hiddens:
             raise NotImplementedError("return_all_hiddens is only used by the segmentation/detection heads")

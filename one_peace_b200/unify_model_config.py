@@ -89,6 +89,19 @@ class UnifyModelConfig:
     decoder: AdjustEncDecConfig = field(default_factory=AdjustEncDecConfig)
 
 
+def one_peace_4b_decoder_config(embed_dim=768, ffn_embed_dim=2048, layers=2, attention_heads=12, patch_image_size=256):
+    """Decoder section of run_scripts/pretrain/pretrain_vl_3B.yaml:127-168: no LayerScale, no relative-position bias, no
+    stems (vision_encoder_type none); text + image experts."""
+    c = AdjustEncDecConfig(embed_dim=embed_dim, ffn_embed_dim=ffn_embed_dim, layers=layers, attention_heads=attention_heads,
+                           normalize_before=True, learned_pos=True, drop_path_rate=0.0, dropout=0.0, attention_dropout=0.0,
+                           magneto_scale_attn=True, scale_attn=False, scale_fc=True, scale_heads=False, use_layer_scale=False,
+                           layer_scale_init_value=1e-6, use_audio_moe=False)
+    c.text_adapter = TextAdapterConfig(bucket_size=256, use_attn_bias=False)
+    c.image_adapter = ImageAdapterConfig(bucket_size=patch_image_size // 16, rel_bucket_size=patch_image_size // 16,
+                                         vision_encoder_type="none", use_attn_bias=False)
+    return c
+
+
 def one_peace_4b_encoder_config(layers=40, embed_dim=1536, ffn_embed_dim=6144, attention_heads=24,
                                 patch_image_size=224):
     """Encoder section of run_scripts/finetune_3B.yaml:76-132 (the "4B" config)."""

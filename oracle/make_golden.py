@@ -110,6 +110,32 @@ def main():
                 with_pad=dcl_b.detach(), grad_norm=stu.grad.norm(), grad_head=stu.grad[0, 1:3].clone())},
                os.path.join(OUT, "pretrain_path.pt"))
 
+    # ---- the full image-text pretraining criterion through the reference's own model + criterion files ----
+    # (one_peace_pretrain.py:106-179 incl. preserve_ids gathers, decoder canvas, mask heads; image_text_pretrain_loss.py:76-208)
+    pm = ref_stub.build_reference_pretrain(**synth.PRETRAIN_TINY)
+    psd = synth.make_pretrain_state_dict(**synth.PRETRAIN_TINY, seed=0)
+    missing, unexpected = pm.load_state_dict(psd, strict=False)
+    assert not unexpected and all(k.endswith(("rp_bucket", "position_idx", "version")) for k in missing), (missing, unexpected)
+    sample = synth.pretrain_sample(seed=0, res=synth.PRETRAIN_TINY["res"], vocab=synth.PRETRAIN_TINY["vocab"])
+    pcrit = pre_mod.ImageTextPretrainLossCriterion(task=None, dcl_text_alpha=0.5, dcl_image_alpha=1.0, dcl_vl_text_alpha=0.5,
+                                                   dcl_vl_image_alpha=0.5, dcl_logit_scale=2.5, label_smoothing=0.1)
+    for q in pm.parameters():
+        q.requires_grad_(True)
+    pm.zero_grad(set_to_none=True)
+    ploss, _, plog = pcrit(pm, sample)
+    ploss.backward()
+    ni = sample["net_input"]
+    with torch.no_grad():
+        dec_t, _, _ = pm(src_tokens=ni["src_tokens"], text_preserve_ids=ni["text_preserve_ids"], encoder_type="text")
+        dvt, dvi, _ = pm(src_tokens=ni["src_tokens"], text_preserve_ids=ni["vl_text_preserve_ids"], src_images=ni["src_images"],
+                         image_preserve_ids=ni["vl_image_preserve_ids"], encoder_type="vl")
+        tl, tf = pm(src_tokens=ni["src_tokens"], encoder_type="text")
+    torch.save({"config": synth.PRETRAIN_TINY, "weights_seed": 0, "sample_seed": 0,
+                "log": {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in plog.items()},
+                "student_text": dec_t, "student_vl_text": dvt, "student_vl_image": dvi, "text_logits": tl, "text_features": tf,
+                "grads": {n: synth.grad_summary(n, q.grad) for n, q in pm.named_parameters() if q.grad is not None}},
+               os.path.join(OUT, "pretrain_criterion.pt"))
+
     # ---- retrieval evaluation (metrics/recall.py executed as-is, single process) ----
     rec_mod = ref_stub.ref_module("one_peace.metrics.recall")
     rcases = []

@@ -380,3 +380,196 @@ def recall_eval(image_ids, image_logits, text_ids, text_logits):
         out[f"predict_{tag}"] = pred
     out["r_mean"] = (out["txt_r_mean"] + out["img_r_mean"]) / 2
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# pretraining model + criterion (models/one_peace/one_peace_pretrain.py:106-179, criterions/image_text_pretrain_loss.py:76-208)
+# Pinned by tests/golden/pretrain_criterion.pt (the reference's own model + criterion executed on the same weights / batch).
+# ----------------------------------------------------------------------------------------------------
+def gather_bias(bias, position_ids):
+    """adapter/text.py:96-101: (H,S,S) bias gathered on both axes by per-sample position ids (B,K) -> (B,H,K,K)."""
+    B, Kk = position_ids.shape
+    H, S = bias.shape[0], bias.shape[1]
+    b = bias[None].expand(B, -1, -1, -1)
+    b = b.gather(2, position_ids[:, None, :, None].expand(-1, H, -1, S))
+    return b.gather(3, position_ids[:, None, None, :].expand(-1, H, Kk, -1))
+
+
+def canvas(preserve_ids, preserve_embed, mask_token, seq_len):
+    """adapter/text.py:135-142: mask token at every position, preserved rows scattered to their position ids."""
+    B, Kk, d = preserve_embed.shape
+    out = mask_token.repeat(B * seq_len, 1)
+    right = torch.nonzero(preserve_ids.ne(-1).flatten(), as_tuple=False).flatten()
+    left = (preserve_ids + (torch.arange(B, device=preserve_ids.device) * seq_len).unsqueeze(1)).view(-1)[right]
+    out = out.index_put((left,), preserve_embed.reshape(-1, d)[right])
+    return out.reshape(B, seq_len, d)
+
+
+def text_adapter_general(sd, cfg, src_tokens, preserve_ids=None, preserve_embed=None, mask_token=None,
+                         prefix="encoder_wrapper.text_adapter.", use_bias=True):
+    """adapter/text.py:111-164 incl. the preserve_ids (:146-151) and mask-token (:135-142) branches."""
+    B, T = src_tokens.shape
+    S = T + 1
+    pad = torch.zeros(B, S, dtype=torch.bool, device=src_tokens.device)
+    pad[:, 1:] = src_tokens.eq(cfg.pad_idx)
+    pos = sd[prefix + "embed_positions.weight"][:S][None].expand(B, -1, -1)
+    bias = None
+    if use_bias:
+        bucket = sd.get(prefix + "rp_bucket")
+        if bucket is None:
+            bucket = make_token_bucket_position(cfg.text_bucket_size)
+        bias = rel_pos_bias(sd[prefix + "rel_pos_table_list.0.weight"], bucket, S)
+    if preserve_embed is not None:
+        emb = canvas(preserve_ids, preserve_embed, mask_token, S)
+    else:
+        emb = torch.cat([sd[prefix + "cls_embedding"].expand(B, -1, -1), sd[prefix + "embed_tokens.weight"][src_tokens]], dim=1)
+        if preserve_ids is not None:
+            pad = preserve_ids.eq(-1)
+            pid = preserve_ids.masked_fill(pad, preserve_ids.size(1) - 1)
+            d = emb.size(-1)
+            emb = emb.gather(1, pid[:, :, None].expand(-1, -1, d))
+            pos = pos.gather(1, pid[:, :, None].expand(-1, -1, d))
+            if bias is not None:
+                bias = gather_bias(bias, pid)
+    return emb + pos, pad, bias
+
+
+def image_adapter_general(sd, cfg, src_images, preserve_ids=None, preserve_embed=None, mask_token=None,
+                          prefix="encoder_wrapper.image_adapter.", use_bias=True):
+    """adapter/image.py:206-260 incl. the preserve_ids (:241-246) and mask-token (:230-237) branches."""
+    B = src_images.size(0)
+    w = src_images.size(2) // 16
+    S = w * w + 1
+    pad = torch.zeros(B, S, dtype=torch.bool, device=src_images.device)
+    pos = image_pos_embed(sd[prefix + "pos_embed"], cfg.image_bucket_size, w)[None].expand(B, -1, -1)
+    bias = None
+    if use_bias:
+        bucket = sd.get(prefix + "rp_bucket")
+        if bucket is None:
+            bucket = make_image_bucket_position(cfg.image_rel_bucket_size)
+        bias = sd[prefix + "rel_pos_table_list.0.weight"][bucket].permute(2, 0, 1)
+    if preserve_embed is not None:
+        emb = canvas(preserve_ids, preserve_embed, mask_token, S)
+    else:
+        x, _, _ = image_adapter(sd, cfg, src_images, prefix)          # includes + pos; undo to gather separately
+        emb = x - pos
+        if preserve_ids is not None:
+            pad = preserve_ids.eq(-1)
+            pid = preserve_ids.masked_fill(pad, preserve_ids.size(1) - 1)
+            d = emb.size(-1)
+            emb = emb.gather(1, pid[:, :, None].expand(-1, -1, d))
+            pos = pos.gather(1, pid[:, :, None].expand(-1, -1, d))
+            if bias is not None:
+                bias = gather_bias(bias, pid)
+    return emb + pos, pad, bias
+
+
+def encoder_general(sd, cfg, parts, prefix="encoder_wrapper.fusion_model.", layer_scale=True):
+    """models/transformer/transformer_encoder.py:116-232, every branch: parts = [(x (B,S_p,d), pad (B,S_p) bool, bias (H,S_p,S_p)
+    | (B,H,S_p,S_p) | None, modality)].  Padded keys are excluded only through the bias (:159-160): without any bias they
+    are attended.  `layer_scale=False`: no gamma_1 / gamma_2 (use_layer_scale off, the pretraining decoder)."""
+    x = torch.cat([p[0] for p in parts], dim=1)
+    pad = torch.cat([p[1] for p in parts], dim=1)
+    if pad.any():
+        x = x * (1 - pad.unsqueeze(-1).type_as(x))
+    B, S, d = x.shape
+    H = cfg.attention_heads
+    bias = None
+    bounds, lo = [], 0
+    if any(p[2] is not None for p in parts):
+        bias = x.new_zeros(B, H, S, S)
+    for px, _, pb, _ in parts:
+        hi = lo + px.size(1)
+        if pb is not None:
+            bias[:, :, lo:hi, lo:hi] += pb if pb.dim() == 4 else pb[None]
+        bounds.append((lo, hi))
+        lo = hi
+    if bias is not None and pad.any():
+        bias = bias.masked_fill(pad[:, None, None, :], float("-inf"))
+    hd = d // H
+    for i in range(cfg.layers):
+        p = prefix + f"layers.{i}."
+        h = F.layer_norm(x, (d,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], cfg.ln_eps)
+        a = p + "self_attn."
+        q = F.linear(h, sd[a + "q_proj.weight"], sd[a + "q_proj.bias"]) * hd ** -0.5
+        k = F.linear(h, sd[a + "k_proj.weight"])
+        v = F.linear(h, sd[a + "v_proj.weight"], sd[a + "v_proj.bias"])
+        q, k, v = (t.view(B, S, H, hd).transpose(1, 2) for t in (q, k, v))
+        att = q @ k.transpose(-1, -2)
+        if bias is not None:
+            att = att + bias
+        o = (F.softmax(att, dim=-1, dtype=torch.float32).type_as(att) @ v).transpose(1, 2).reshape(B, S, d)
+        o = F.layer_norm(o, (d,), sd[a + "ln.weight"], sd[a + "ln.bias"], cfg.ln_eps)
+        o = F.linear(o, sd[a + "out_proj.weight"], sd[a + "out_proj.bias"])
+        x = x + (sd[p + "gamma_1"] * o if layer_scale else o)
+        h = F.layer_norm(x, (d,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], cfg.ln_eps)
+        f = torch.cat([geglu_ffn(sd, cfg, h[:, a_:b_], p + f"{m}_ffn.") for (a_, b_), (_, _, _, m) in zip(bounds, parts)], dim=1)
+        x = x + (sd[p + "gamma_2"] * f if layer_scale else f)
+    outs = []
+    for (a_, b_), (_, _, _, m) in zip(bounds, parts):
+        outs.append(F.layer_norm(x[:, a_:b_], (d,), sd[prefix + f"{m}_layer_norm.weight"], sd[prefix + f"{m}_layer_norm.bias"],
+                                 cfg.ln_eps))
+    return outs
+
+
+def pretrain_forward(sd, cfg, dec_cfg, src_tokens=None, text_preserve_ids=None, src_images=None, image_preserve_ids=None,
+                     encoder_type=None):
+    """models/one_peace/one_peace_pretrain.py:106-179 (text / image experts).  cfg / dec_cfg: OracleConfig of the encoder / decoder."""
+    parts = []
+    if encoder_type in ("text", "vl"):
+        parts.append(text_adapter_general(sd, cfg, src_tokens, text_preserve_ids) + ("text",))
+    if encoder_type in ("image", "vl"):
+        parts.append(image_adapter_general(sd, cfg, src_images, image_preserve_ids) + ("image",))
+    feats = dict(zip([p[3] for p in parts], encoder_general(sd, cfg, parts)))
+    if text_preserve_ids is None and image_preserve_ids is None:
+        if encoder_type in ("text", "image"):
+            f = feats[encoder_type]
+            logits = F.normalize(F.linear(f[:, 0, :], sd[f"{encoder_type}_proj.weight"], sd[f"{encoder_type}_proj.bias"]), dim=1)
+            return logits, f
+        return feats["text"], feats["image"]
+    dparts = []
+    if "text" in feats:
+        emb = F.linear(feats["text"], sd["decoder_text_embed.weight"], sd["decoder_text_embed.bias"])
+        dparts.append(text_adapter_general(sd, dec_cfg, src_tokens, text_preserve_ids, emb, sd["text_mask_token"],
+                                           "decoder_wrapper.text_adapter.", use_bias=False) + ("text",))
+    if "image" in feats:
+        emb = F.linear(feats["image"], sd["decoder_image_embed.weight"], sd["decoder_image_embed.bias"])
+        dparts.append(image_adapter_general(sd, dec_cfg, src_images, image_preserve_ids, emb, sd["image_mask_token"],
+                                            "decoder_wrapper.image_adapter.", use_bias=False) + ("image",))
+    dfeats = dict(zip([p[3] for p in dparts], encoder_general(sd, dec_cfg, dparts, "decoder_wrapper.fusion_model.",
+                                                              layer_scale=False)))
+    out = [None, None, None]
+    for i, m in enumerate(("text", "image")):
+        if m in dfeats:
+            out[i] = F.linear(dfeats[m], sd[f"{m}_mask_head.weight"], sd[f"{m}_mask_head.bias"])
+    return tuple(out)
+
+
+def image_text_pretrain_loss(sd, cfg, dec_cfg, net_input, alphas=(0.5, 1.0, 0.5, 0.5), dcl_logit_scale=2.5, label_smoothing=0.0):
+    """criterions/image_text_pretrain_loss.py:76-162 (single process).  Returns (loss, dict of the terms)."""
+    ni = net_input
+    tok, img = ni["src_tokens"], ni["src_images"]
+    text_logits, teacher_text = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, encoder_type="text")
+    image_logits, teacher_image = pretrain_forward(sd, cfg, dec_cfg, src_images=img, encoder_type="image")
+    with torch.no_grad():
+        teacher_vl_text, teacher_vl_image = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, src_images=img, encoder_type="vl")
+    student_text, _, _ = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, text_preserve_ids=ni["text_preserve_ids"],
+                                          encoder_type="text")
+    _, student_image, _ = pretrain_forward(sd, cfg, dec_cfg, src_images=img, image_preserve_ids=ni["image_preserve_ids"],
+                                           encoder_type="image")
+    svt, svi, _ = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, text_preserve_ids=ni["vl_text_preserve_ids"], src_images=img,
+                                   image_preserve_ids=ni["vl_image_preserve_ids"], encoder_type="vl")
+    scale = logit_scale_exp(sd["logit_scale"])
+    pm = tok.eq(cfg.pad_idx)
+    kw = dict(dcl_logit_scale=dcl_logit_scale, label_smoothing=label_smoothing)
+    terms = {
+        "dcl_text_loss": dcl_loss(student_text, teacher_text, ni["text_mask_indices"], pm, **kw),
+        "dcl_image_loss": dcl_loss(student_image, teacher_image, ni["image_mask_indices"], None, **kw),
+        "dcl_vl_text_loss": dcl_loss(svt, teacher_vl_text, ni["vl_text_mask_indices"], pm, **kw),
+        "dcl_vl_image_loss": dcl_loss(svi, teacher_vl_image, ni["vl_image_mask_indices"], None, **kw),
+    }
+    itc, i2t, t2i = itc_loss(image_logits, text_logits, image_logits.detach(), text_logits.detach(), scale, 0, 0.0)
+    terms["itc_loss"], terms["i2t_ncorrect"], terms["t2i_ncorrect"] = itc, i2t, t2i
+    loss = itc + alphas[0] * terms["dcl_text_loss"] + alphas[1] * terms["dcl_image_loss"] + \
+        alphas[2] * terms["dcl_vl_text_loss"] + alphas[3] * terms["dcl_vl_image_loss"]
+    return loss, terms

@@ -149,3 +149,92 @@ def retrieval_set(n_img, captions_per_image, d, seed, noise=0.8):
     txt_ids = img_ids.repeat_interleave(captions_per_image)
     perm = torch.randperm(txt.shape[0], generator=g)
     return img, txt[perm].contiguous(), img_ids, txt_ids[perm].contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pretraining path (one_peace_pretrain.py + image_text_pretrain_loss.py): tiny encoder + decoder, masked sample
+# ----------------------------------------------------------------------------------------------------------------
+PRETRAIN_TINY = dict(embed_dim=256, ffn=1024, layers=2, heads=4, dec_dim=128, dec_ffn=256, dec_layers=2, dec_heads=2, res=64,
+                     vocab=1000)
+
+
+def make_pretrain_state_dict(embed_dim=256, ffn=1024, layers=2, heads=4, dec_dim=128, dec_ffn=256, dec_layers=2, dec_heads=2,
+                             res=64, vocab=1000, seed=0, gamma_range=(0.5, 1.5)):
+    """Parameter names / shapes of the reference ``OnePeacePretrainModel`` with text + image experts (pretrain_vl_3B.yaml
+    structure at a tiny width): encoder as make_state_dict, decoder without LayerScale / relative-position bias / stems,
+    projection heads, decoder_*_embed, *_mask_token, *_mask_head."""
+    w = res // 16
+    sd = make_state_dict(embed_dim=embed_dim, ffn=ffn, layers=layers, heads=heads, modalities=("text", "image"), seed=seed,
+                         vocab=vocab, image_bucket=w, image_rel_bucket=w, gamma_range=gamma_range)
+    dec = make_state_dict(embed_dim=dec_dim, ffn=dec_ffn, layers=dec_layers, heads=dec_heads, modalities=("text", "image"),
+                          seed=seed + 1000, vocab=8, image_bucket=w, image_rel_bucket=w)
+    for k, v in dec.items():
+        if k.startswith("encoder_wrapper.fusion_model.") and ".gamma_" not in k:
+            sd[k.replace("encoder_wrapper.", "decoder_wrapper.", 1)] = v
+    for k in ("text_adapter.cls_embedding", "text_adapter.embed_positions.weight", "image_adapter.cls_embedding",
+              "image_adapter.pos_embed"):
+        sd["decoder_wrapper." + k] = dec["encoder_wrapper." + k]
+    g = torch.Generator().manual_seed(seed + 2000)
+    for m in ("text", "image"):
+        sd[f"decoder_{m}_embed.weight"] = _tn(g, (dec_dim, embed_dim), 0.05)
+        sd[f"decoder_{m}_embed.bias"] = 0.1 * torch.randn(dec_dim, generator=g)
+        sd[f"{m}_mask_token"] = _tn(g, (1, dec_dim), 0.5)
+        sd[f"{m}_mask_head.weight"] = _tn(g, (embed_dim, dec_dim), 0.08)
+        sd[f"{m}_mask_head.bias"] = 0.1 * torch.randn(embed_dim, generator=g)
+    return sd
+
+
+def _preserve(mask_rows):
+    """list of bool [S_i] mask vectors -> (mask (B,S) bool padded False, preserve_ids (B,K) int64 padded -1) as the collate
+    function builds them (data/__init__.py:50-72)."""
+    S = max(len(m) for m in mask_rows)
+    ids = [(~m).nonzero(as_tuple=True)[0] for m in mask_rows]
+    Kk = max(len(i) for i in ids)
+    mask = torch.zeros(len(mask_rows), S, dtype=torch.bool)
+    pres = torch.full((len(mask_rows), Kk), -1, dtype=torch.long)
+    for b, (m, i) in enumerate(zip(mask_rows, ids)):
+        mask[b, :len(m)] = m
+        pres[b, :len(i)] = i
+    return mask, pres
+
+
+def pretrain_sample(seed=0, B=4, T=12, res=64, vocab=1000, text_mask_ratio=0.4, image_mask_ratio=0.75, vl_text_ratio=0.4,
+                    vl_image_ratio=0.6875):
+    """A collated image-text pretraining batch with the masking scheme of data/pretrain_data/image_text_pretrain_dataset.py
+    :69-104 (token-level instead of whole-word masks): ragged captions ending in eos (2), pad id 1, no bos."""
+    g = torch.Generator().manual_seed(seed)
+    n_patch = (res // 16) ** 2
+    tok = torch.ones(B, T, dtype=torch.long)
+    tm, vtm, im, vim = [], [], [], []
+    for b in range(B):
+        n = T - 1 - (b % 3) * 2                                    # caption length without eos
+        tok[b, :n] = torch.randint(4, vocab, (n,), generator=g)
+        tok[b, n] = 2
+        k = max(1, int(n * text_mask_ratio + 0.999))
+        m = torch.zeros(n, dtype=torch.bool)
+        m[torch.randperm(n, generator=g)[:k]] = True
+        kv = int(n * vl_text_ratio)
+        vm = torch.zeros(n, dtype=torch.bool)
+        vm[torch.randn(n, generator=g).masked_fill(m, -float("inf")).argsort(descending=True)[:kv]] = True
+        f = torch.zeros(1, dtype=torch.bool)
+        tm.append(torch.cat([f, m, f]))
+        vtm.append(torch.cat([f, vm, f]))
+        mp = int(n_patch * image_mask_ratio)
+        mi = torch.zeros(n_patch, dtype=torch.bool)
+        mi[torch.randperm(n_patch, generator=g)[:mp]] = True
+        vp = int(n_patch * vl_image_ratio)
+        extra = torch.randn(n_patch, generator=g).masked_fill(~mi, -float("inf")).argsort(descending=True)[:vp - (n_patch - mp)]
+        vmi = torch.zeros(n_patch, dtype=torch.bool)
+        vmi[torch.cat([extra, (~mi).nonzero(as_tuple=True)[0]])] = True
+        im.append(torch.cat([f, mi]))
+        vim.append(torch.cat([f, vmi]))
+    img = torch.randn(B, 3, res, res, generator=g)
+    ni = {"src_tokens": tok, "src_images": img}
+    for name, rows in (("text", tm), ("vl_text", vtm), ("image", im), ("vl_image", vim)):
+        mask, pres = _preserve(rows)
+        if name.endswith("text"):                                  # masks cover (B, T+1) positions
+            full = torch.zeros(B, T + 1, dtype=torch.bool)
+            full[:, :mask.shape[1]] = mask
+            mask = full
+        ni[f"{name}_mask_indices"], ni[f"{name}_preserve_ids"] = mask, pres
+    return {"id": list(range(B)), "nsentences": B, "ntokens": B, "net_input": ni}

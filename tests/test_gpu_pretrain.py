@@ -1,0 +1,128 @@
+"""GPU: the pretraining path (one_peace_pretrain.py:106-179, image_text_pretrain_loss.py:76-208,
+transformer_encoder.py:116-232 'vl' / 'al' branches) against (1) golden outputs of the reference's own files
+(tests/golden/pretrain_path.pt, pretrain_criterion.pt) and (2) the oracle's autograd for every parameter gradient."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import restated as R
+import synth
+
+pytestmark = pytest.mark.gpu
+TINY = dict(embed_dim=256, ffn=1024, layers=2, heads=4)
+
+
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+
+
+def min_cos(a, b):
+    return F.cosine_similarity(a.float().cpu().flatten(1), b.float().flatten(1)).min().item()
+
+
+def test_vl_al_concatenated_encoders_vs_reference_golden(golden_dir):
+    """ModelWrapper.forward(encoder_type='vl' / 'al') (one_peace_base.py:68-129): block-diagonal bias, shared attention,
+    per-modality FFN rows and final norms, vs the reference's own output on the tiny val model."""
+    need_gpu()
+    from one_peace_b200.one_peace.hub_interface import from_pretrained
+    fx = torch.load(os.path.join(golden_dir, "pretrain_path.pt"), weights_only=False)
+    sd = synth.make_state_dict(**TINY, seed=0)
+    hub = from_pretrained(state_dict=sd, head_type="val", layers=2, embed_dim=256, ffn_embed_dim=1024, attention_heads=4,
+                          patch_image_size=224, device="cuda", dtype="float32")
+    tok, img, aud, apm = synth.tiny_inputs(seed=0)
+    ew = hub.model.encoder_wrapper
+    with torch.no_grad():
+        vt, vi, _ = ew(src_tokens=tok[:2].cuda(), src_images=img.cuda(), encoder_type="vl")
+        at, _, aa = ew(src_tokens=tok[2:4].cuda(), src_audios=aud.cuda(), audio_padding_masks=apm.cuda(), encoder_type="al")
+    # per-token features, padded positions excluded (their values are never read by the reference either)
+    tp = torch.zeros(2, 17, dtype=torch.bool); tp[:, 1:] = tok[:2].eq(1)
+    assert min_cos(vt[~tp.cuda()], fx["vl_text"][~tp]) > 0.999
+    assert min_cos(vi.reshape(-1, 256), fx["vl_image"].reshape(-1, 256)) > 0.999
+    tp2 = torch.zeros(2, 17, dtype=torch.bool); tp2[:, 1:] = tok[2:4].eq(1)
+    assert min_cos(at[~tp2.cuda()], fx["al_text"][~tp2]) > 0.999
+    assert min_cos(aa[~apm.cuda()], fx["al_audio"][~apm]) > 0.999
+
+
+def _pretrain_model(sd, dtype="float32"):
+    from one_peace_b200.one_peace.hub_interface import from_pretrained
+    T = synth.PRETRAIN_TINY
+    hub = from_pretrained(state_dict=sd, model_type="one_peace_pretrain", layers=T["layers"], embed_dim=T["embed_dim"],
+                          ffn_embed_dim=T["ffn"], attention_heads=T["heads"], patch_image_size=T["res"], vocab_size=T["vocab"],
+                          decoder=dict(embed_dim=T["dec_dim"], ffn_embed_dim=T["dec_ffn"], layers=T["dec_layers"],
+                                       attention_heads=T["dec_heads"]), device="cuda", dtype=dtype)
+    return hub.model
+
+
+def _cuda_sample(sample):
+    ni = {k: v.cuda() for k, v in sample["net_input"].items()}
+    return dict(sample, net_input=ni)
+
+
+def test_pretrain_model_forward_vs_reference_golden(golden_dir):
+    """preserve_ids student passes through encoder + decoder + mask head, and the contrastive branch, vs the reference."""
+    need_gpu()
+    fx = torch.load(os.path.join(golden_dir, "pretrain_criterion.pt"), weights_only=False)
+    T = synth.PRETRAIN_TINY
+    sd = synth.make_pretrain_state_dict(**T, seed=0)
+    model = _pretrain_model(sd)
+    model.eval()
+    ni = _cuda_sample(synth.pretrain_sample(seed=0, res=T["res"], vocab=T["vocab"]))["net_input"]
+    with torch.no_grad():
+        st, _, _ = model(src_tokens=ni["src_tokens"], text_preserve_ids=ni["text_preserve_ids"], encoder_type="text")
+        vt, vi, _ = model(src_tokens=ni["src_tokens"], text_preserve_ids=ni["vl_text_preserve_ids"], src_images=ni["src_images"],
+                          image_preserve_ids=ni["vl_image_preserve_ids"], encoder_type="vl")
+        tl, tf = model(src_tokens=ni["src_tokens"], encoder_type="text")
+    npad = torch.ones(4, 13, dtype=torch.bool); npad[:, 1:] = ~ni["src_tokens"].eq(1).cpu()
+    assert min_cos(st[npad.cuda()], fx["student_text"][npad]) > 0.999
+    assert min_cos(vt[npad.cuda()], fx["student_vl_text"][npad]) > 0.999
+    assert min_cos(vi.reshape(-1, 256), fx["student_vl_image"].reshape(-1, 256)) > 0.999
+    assert min_cos(tl, fx["text_logits"]) > 0.9995
+    assert min_cos(tf[npad.cuda()], fx["text_features"][npad]) > 0.999
+
+
+def test_image_text_pretrain_criterion_loss_and_gradients(golden_dir):
+    """Full criterion (ITC + 4 DCL terms, six model calls) vs the reference's logged losses (1e-3 relative, north_star) and
+    every parameter gradient vs the oracle's autograd (the oracle's gradients are pinned to the reference's in
+    tests/test_oracle_golden.py)."""
+    need_gpu()
+    from one_peace_b200.criterions.image_text_pretrain_loss import ImageTextPretrainLossCriterion
+    fx = torch.load(os.path.join(golden_dir, "pretrain_criterion.pt"), weights_only=False)
+    T = synth.PRETRAIN_TINY
+    sd = synth.make_pretrain_state_dict(**T, seed=0)
+    model = _pretrain_model(sd)
+    model.train()
+    sample = synth.pretrain_sample(seed=0, res=T["res"], vocab=T["vocab"])
+    crit = ImageTextPretrainLossCriterion(None, label_smoothing=0.1)
+    loss, ssz, log = crit(model, _cuda_sample(sample))
+    assert ssz == 1
+    for k in ("loss", "itc_loss", "dcl_text_loss", "dcl_image_loss", "dcl_vl_text_loss", "dcl_vl_image_loss"):
+        got, want = float(log[k]), float(fx["log"][k])
+        assert abs(got - want) / abs(want) <= 1e-3, (k, got, want)
+    assert float(log["i2t_ncorrect"]) == float(fx["log"]["i2t_ncorrect"]) and float(log["t2i_ncorrect"]) == float(fx["log"]["t2i_ncorrect"])
+    loss.backward()
+    # oracle gradients
+    w = T["res"] // 16
+    cfg = R.OracleConfig(embed_dim=T["embed_dim"], ffn_embed_dim=T["ffn"], layers=T["layers"], attention_heads=T["heads"],
+                         image_bucket_size=w, image_rel_bucket_size=w)
+    dcfg = R.OracleConfig(embed_dim=T["dec_dim"], ffn_embed_dim=T["dec_ffn"], layers=T["dec_layers"], attention_heads=T["dec_heads"],
+                          image_bucket_size=w, image_rel_bucket_size=w)
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    wl, _ = R.image_text_pretrain_loss(sdg, cfg, dcfg, sample["net_input"], label_smoothing=0.1)
+    wl.backward()
+    rows, bad = [], []
+    for name, p in model.named_parameters():
+        ref = sdg[name].grad if name in sdg else None
+        if ref is None or ref.abs().max() == 0:
+            continue
+        assert p.grad is not None, f"{name}: no gradient"
+        g = p.grad.float().cpu()
+        cos = F.cosine_similarity(g.flatten(), ref.flatten(), dim=0).item()
+        ratio = (g.norm() / ref.norm()).item()
+        lim = 0.97 if "rel_pos_table" in name else 0.99
+        rows.append((cos, ratio, name))
+        if cos < lim or abs(ratio - 1) > 0.05:
+            bad.append((name, round(cos, 4), round(ratio, 4)))
+    assert len(rows) > 130 and not bad, bad[:20]

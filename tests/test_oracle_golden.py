@@ -177,3 +177,51 @@ def test_clip_coefficient_matches_fairseq_known_answer():
     # Linear(1,1) step: ||[1, 2]|| = sqrt(5).  Same formula (norm, then clamp(max_norm / (norm + 1e-6), max=1)).
     norm, coef = R.clip_coefficient([torch.tensor([1.0]), torch.tensor([2.0])], max_norm=1.0)
     assert abs(norm - 2.2361) < 1e-4 and abs(coef - 1.0 / (math.sqrt(5) + 1e-6)) < 1e-7
+
+
+def test_pretrain_model_and_criterion_match_the_reference(golden_dir):
+    """oracle/restated.py's pretraining model (preserve_ids gathers, decoder canvas, mask heads) and the full
+    image_text_pretrain_loss vs the reference's own one_peace_pretrain.py + image_text_pretrain_loss.py executed on the same
+    synthetic weights and masked batch (oracle/make_golden.py): every loss term, the student features, every parameter gradient."""
+    fx = torch.load(os.path.join(golden_dir, "pretrain_criterion.pt"), weights_only=False)
+    T = synth.PRETRAIN_TINY
+    assert fx["config"] == T
+    sd = synth.make_pretrain_state_dict(**T, seed=fx["weights_seed"])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    w = T["res"] // 16
+    cfg = R.OracleConfig(embed_dim=T["embed_dim"], ffn_embed_dim=T["ffn"], layers=T["layers"], attention_heads=T["heads"],
+                         image_bucket_size=w, image_rel_bucket_size=w)
+    dcfg = R.OracleConfig(embed_dim=T["dec_dim"], ffn_embed_dim=T["dec_ffn"], layers=T["dec_layers"], attention_heads=T["dec_heads"],
+                          image_bucket_size=w, image_rel_bucket_size=w)
+    sample = synth.pretrain_sample(seed=fx["sample_seed"], res=T["res"], vocab=T["vocab"])
+    ni = sample["net_input"]
+    with torch.no_grad():
+        st, _, _ = R.pretrain_forward(sd, cfg, dcfg, src_tokens=ni["src_tokens"], text_preserve_ids=ni["text_preserve_ids"],
+                                      encoder_type="text")
+        vt, vi, _ = R.pretrain_forward(sd, cfg, dcfg, src_tokens=ni["src_tokens"], text_preserve_ids=ni["vl_text_preserve_ids"],
+                                       src_images=ni["src_images"], image_preserve_ids=ni["vl_image_preserve_ids"], encoder_type="vl")
+        tl, tf = R.pretrain_forward(sd, cfg, dcfg, src_tokens=ni["src_tokens"], encoder_type="text")
+    torch.testing.assert_close(st, fx["student_text"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(vt, fx["student_vl_text"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(vi, fx["student_vl_image"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(tl, fx["text_logits"], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(tf, fx["text_features"], atol=5e-5, rtol=1e-4)
+    loss, terms = R.image_text_pretrain_loss(sdg, cfg, dcfg, ni, label_smoothing=0.1)
+    for k in ("itc_loss", "dcl_text_loss", "dcl_image_loss", "dcl_vl_text_loss", "dcl_vl_image_loss"):
+        torch.testing.assert_close(terms[k].detach(), fx["log"][k], atol=2e-5, rtol=2e-5)
+    torch.testing.assert_close(loss.detach(), fx["log"]["loss"], atol=5e-5, rtol=2e-5)
+    assert float(terms["i2t_ncorrect"]) == float(fx["log"]["i2t_ncorrect"]) and float(terms["t2i_ncorrect"]) == float(fx["log"]["t2i_ncorrect"])
+    loss.backward()
+    checked = 0
+    for name, summ in fx["grads"].items():
+        g = sdg[name].grad
+        if summ["norm"] == 0.0:
+            assert g is None or float(g.norm()) < 1e-7, name
+            continue
+        assert g is not None, name
+        mine = synth.grad_summary(name, g)
+        assert mine["shape"] == summ["shape"], name
+        assert abs(mine["norm"] - summ["norm"]) <= 2e-4 * summ["norm"] + 1e-7, (name, mine["norm"], summ["norm"])
+        torch.testing.assert_close(mine["head"], summ["head"], atol=2e-4 * summ["norm"] + 1e-7, rtol=2e-3)
+        checked += 1
+    assert checked > 100
