@@ -15,6 +15,17 @@ no exchange step: "replicas only", weak scaling); value = all samples / max-over
 One JSON line on stdout (rank 0).  Keys follow the driver contract; `roofline` describes the dominant
 kernel (the tcgen05 GEMM), `cpu_baseline` the oracle port timed on the host cores, `e2e` the same metric
 through the public API with pinned-host inputs (H2D + forward + D2H inside the timed region).
+
+Extra blocks in the same line:
+  contrastive         the path that HAS a collective (BASELINE.json configs[3]), at every N:
+      head            InfoNCE fwd+bwd on synthetic unit-norm embeddings, local b = 1024 / rank: NCCL all-gather of both
+                      modalities + fused loss / gradient kernels -> pairs/s, all-gather ms, parity vs the oracle on rank 0
+      train_step      full image-text training step of the 4B text+image branches (encoder fwd/bwd with activation
+                      recompute + all-gather + InfoNCE + gradient reduce-scatter -> sharded fused Adam -> all-gather)
+  gpu_eager_baseline  (N = 1) the reference's arithmetic (oracle/restated.py) in PyTorch eager bf16 on the same B200
+                      (ATen / cuBLAS) for the config-2 forward: the "reference on the same box" bar
+  hbm_kernels         (N = 1) CUDA-event GB/s of the HBM-bound kernels against MEASURED_PEAKS hbm_gbs
+Skip them with --no-extras (the headline keys are unaffected).
 """
 import argparse
 import json
@@ -237,6 +248,25 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(steps=1, warmup=0, sample_images=8)
 
+    extras = {}
+    if not args.no_extras:
+        del hub, model, dev_images
+        torch.cuda.empty_cache()
+        try:
+            head = contrastive_head_block(dev, world, rank)
+            train = contrastive_train_block(dev, world, rank)
+            extras["contrastive"] = {"head": head, "train_step": train}
+        except Exception as e:                      # the headline must survive a failure of an extra block
+            extras["contrastive"] = {"error": repr(e)[:300]}
+        if rank == 0 and world == 1:
+            for key, fn in (("gpu_eager_baseline", eager_bf16_forward_baseline), ("hbm_kernels", hbm_kernels_block)):
+                try:
+                    extras[key] = fn(dev)
+                except Exception as e:
+                    extras[key] = {"error": repr(e)[:300]}
+            if "forward" in extras.get("gpu_eager_baseline", {}):
+                extras["gpu_eager_baseline"]["repo_over_eager_forward"] = round(value / extras["gpu_eager_baseline"]["forward"]["value"], 3)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -249,9 +279,268 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# extra blocks: contrastive head / train step (all N), eager-bf16 baseline and HBM-bound kernels (N = 1)
+# ----------------------------------------------------------------------------------------------------
+def _ev_ms(fn, iters, torch, pre=None):
+    """Average device ms of fn() over `iters` launches (CUDA events on the current stream, one warm-up)."""
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def contrastive_head_block(dev, world, rank, b=1024, d=D, steps=20):
+    """configs[3] head-only: all_gather of both (b, d) embedding matrices + InfoNCE fwd + bwd."""
+    import math
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restated as R
+    import synth
+    from one_peace_b200 import kernels as K
+    from one_peace_b200.criterions.image_text_retrieval_loss import gather_without_grad, itc_loss
+    a_all, t_all = synth.contrastive_pair(b * world, d, seed=123)
+    a = a_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+    t = t_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+    ls = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+
+    def gather():
+        return (gather_without_grad(a), gather_without_grad(t)) if world > 1 else (a.detach(), t.detach())
+
+    def step():
+        ga, gt = gather()
+        loss, i2t, t2i = itc_loss(a, t, ga, gt, ls.exp(), rank, 0.0)
+        loss.backward()
+        return loss, i2t, t2i
+    loss, i2t, t2i = step()
+    torch.cuda.synchronize()
+    ok, rel = True, None
+    if rank == 0:
+        ao, to = a_all[:b].clone().requires_grad_(True), t_all[:b].clone().requires_grad_(True)
+        lo = torch.tensor(math.log(1 / 0.07), requires_grad=True)
+        torch.set_num_threads(min(os.cpu_count() or 1, 32))
+        want, wi, wt = R.itc_loss(ao, to, a_all, t_all, R.logit_scale_exp(lo), 0, 0.0)
+        want.backward()
+        rel = abs(loss.item() - want.item()) / abs(want.item())
+        gcos = torch.nn.functional.cosine_similarity(a.grad.cpu().flatten(), ao.grad.flatten(), dim=0).item()
+        ok = bool(rel < 1e-3 and float(i2t) == float(wi) and float(t2i) == float(wt) and gcos > 0.9995)
+    for q in (a, t, ls):
+        q.grad = None
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = K.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = (K.LAUNCHES - l0) // steps
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    ag = torch.tensor([_ev_ms(gather, 20, torch) if world > 1 else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+    per = ms.item()
+    n = b * world
+    return {"metric": "contrastive_head_pairs_per_sec", "value": round(n / (per / 1e3), 1), "unit": "pairs/s",
+            "ms_per_step": round(per, 4), "all_gather_ms": round(ag.item(), 4), "kernel_ms": round(per - ag.item(), 4),
+            "local_batch": b, "global_batch": n, "d": d, "launches_per_step": int(launches), "parity_ok": ok,
+            "loss_rel_vs_oracle": None if rel is None else float(f"{rel:.2e}"),
+            "collective": "2 x all_gather_into_tensor (NCCL), forward only, rank-major (image_text_pretrain_loss.py:30-39)",
+            "algorithmic_tflops_per_rank": round(3 * 2 * 2.0 * b * n * d / (per / 1e3) / 1e12, 1)}
+
+
+def contrastive_train_block(dev, world, rank, b=64, text_len=32, steps=3, warmup=2):
+    """configs[3] full-step form: the whole image-text training step of the 4B text + image branches."""
+    import torch
+    import torch.distributed as dist
+    from one_peace_b200 import kernels as K
+    from one_peace_b200.criterions import ImageTextRetrievalCriterion
+    from one_peace_b200.one_peace import OnePeaceRetrievalConfig, OnePeaceRetrievalModel
+    from one_peace_b200.one_peace.hub_interface import _Dictionary
+    from one_peace_b200.optim.distributed_adam import DistributedAdam
+    from one_peace_b200.unify_model_config import one_peace_4b_encoder_config
+    cfg = OnePeaceRetrievalConfig()
+    cfg.encoder = one_peace_4b_encoder_config(layers=LAYERS, embed_dim=D, ffn_embed_dim=FFN, attention_heads=H, patch_image_size=RES)
+    torch.manual_seed(0)                      # identical initial weights on every rank
+    with torch.device(dev):
+        model = OnePeaceRetrievalModel(cfg, _Dictionary(50264), "vl")
+        with torch.no_grad():
+            for n, q in model.named_parameters():
+                if "gamma_" in n:
+                    q.fill_(0.1)
+                elif "rel_pos_table" in n:
+                    q.normal_(0, 0.1)
+    model = model.to(torch.bfloat16)
+    model.train()
+    params = [q for q in model.parameters() if q.requires_grad]
+    opt = DistributedAdam(params, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    crit = ImageTextRetrievalCriterion(task=None, label_smoothing=0.0)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sample = {"nsentences": b, "net_input": {
+        "src_tokens": torch.randint(4, 50264, (b, text_len), device=dev, generator=g),
+        "src_images": torch.randn(b, 3, RES, RES, device=dev, generator=g)}}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(timed=False):
+        for q in params:
+            q.grad = None
+        if timed:
+            ev[0].record()
+        loss, _, _ = crit(model, sample)
+        loss.backward()
+        if timed:
+            ev[1].record()
+        opt.step(max_norm=3.0)               # clip_norm 3.0: pretrain_vl_3B.yaml
+        if timed:
+            ev[2].record()
+        return loss.detach()
+    losses = [round(step().item(), 4) for _ in range(warmup)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = K.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses.append(round(step().item(), 4))
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = (K.LAUNCHES - l0) // steps
+    step(timed=True)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n_params = sum(q.numel() for q in params)
+    out = {"metric": "contrastive_train_step_pairs_per_sec", "value": round(b * world / t[0].item() * 1e3, 2), "unit": "pairs/s",
+           "ms_per_step": round(t[0].item(), 2), "fwd_bwd_ms": round(t[1].item(), 2), "grad_exchange_adam_ms": round(t[2].item(), 2),
+           "pairs_per_rank": b, "global_batch": b * world, "text_len": text_len, "params_b": round(n_params / 1e9, 3), "dtype": "bf16",
+           "losses": losses, "finite": all(x == x for x in losses), "launches_per_step": int(launches),
+           "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+           "collectives": "2 x all_gather (embeddings) + reduce_scatter(AVG) of the flat bf16 gradient + scalar all_reduce (norm) + "
+                          "all_gather of the updated bf16 parameter shards (optim/distributed_adam.py); limiting one: the "
+                          f"{round(n_params * 2 / 1e9, 2)} GB gradient reduce-scatter + parameter all-gather, not overlapped with backward",
+           "includes": "text + image encoder fwd / bwd (activation recompute), InfoNCE, grad-norm clip, sharded fused Adam"}
+    del opt, model, params
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_bf16_forward_baseline(dev, steps=5):
+    """The reference's own arithmetic (oracle/restated.py = models/**/*.py restated, pinned by tests/golden) run as PyTorch eager
+    bf16 on this GPU: bf16 weights / activations / residual stream, ATen + cuBLAS kernels, fp32 softmax as the reference does
+    (multihead_attention.py:112).  Same workload as the headline: 64 x 224^2 images, 40 layers (4 distinct layers cycled)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restated as R
+    import synth
+    distinct = 4
+    sd = synth.make_state_dict(embed_dim=D, ffn=FFN, layers=distinct, heads=H, modalities=("image",), seed=0, gamma_range=(0.05, 0.15))
+    sd = {k: (v.to(dev, torch.bfloat16) if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
+    for i in range(distinct, LAYERS):
+        for k in [k for k in sd if f"layers.{i % distinct}." in k]:
+            sd[k.replace(f"layers.{i % distinct}.", f"layers.{i}.")] = sd[k]
+    cfg = R.OracleConfig(embed_dim=D, ffn_embed_dim=FFN, layers=LAYERS, attention_heads=H)
+    img = torch.randn(BATCH, 3, RES, RES, device=dev, generator=torch.Generator(device=dev).manual_seed(5)).to(torch.bfloat16)
+
+    def fwd():
+        with torch.no_grad():
+            return R.extract_features(sd, cfg, "image", src_images=img)
+    for _ in range(2):
+        fwd()
+    ms = _ev_ms(fwd, steps, torch)
+    del sd
+    torch.cuda.empty_cache()
+    return {"forward": {"value": round(BATCH / (ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms, 3)},
+            "what": "oracle/restated.py (the reference's modules restated) in torch eager bf16 on the same GPU: ATen / cuBLAS, no "
+                    "xformers / apex / flash-attn (the reference ships no Blackwell kernel)", "torch": torch.__version__}
+
+
+def hbm_kernels_block(dev):
+    """Achieved GB/s of the HBM-bound kernels (CUDA events, buffers >> 126 MB L2) vs the measured copy bandwidth."""
+    import ctypes
+    import torch
+    from one_peace_b200 import kernels as K
+    from one_peace_b200.optim.adam import Adam
+    pk, _ = peaks()
+    hbm = pk["hbm_gbs"]
+    out = []
+
+    def rec(name, nbytes, ms, note):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        out.append({"kernel": name, "algorithmic_mb": round(nbytes / 1e6, 1), "ms": round(ms, 4), "gbs": round(gbs, 1),
+                    "frac": round(gbs / hbm, 3), "shape": note})
+    bf, f32 = torch.bfloat16, torch.float32
+    # fused Adam with fp32 master: 28 B / parameter (DESIGN.md 4.4); 1.511 B parameters = the 4B vision branch (BASELINE.md 2)
+    n = 1_511_000_000 // 8 * 8
+    p = torch.nn.Parameter(torch.zeros(n, dtype=bf, device=dev))
+    p.grad = torch.full((n,), 1e-3, dtype=bf, device=dev)
+    opt = Adam([p], lr=1e-4, betas=(0.9, 0.98), weight_decay=0.05, master_weights=True)
+    opt.step()
+    rec("adam_multi_kernel", 28 * n, _ev_ms(opt.step, 5, torch), f"{n / 1e9:.3f} B bf16 params + fp32 master/m/v, 28 B/param")
+    rec("grad_sumsq_kernel (+finalize)", 2 * n, _ev_ms(lambda: opt.grad_norm_and_scale(1.0, 3.0), 5, torch), f"{n / 1e9:.3f} B bf16 grads")
+    del opt, p
+    torch.cuda.empty_cache()
+    rows, d = 4 * 12608, D
+    x = torch.randn(rows, d, device=dev)
+    w, b = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    y = torch.empty(rows, d, dtype=bf, device=dev)
+    rec("layernorm_kernel fp32->bf16", rows * d * 6, _ev_ms(lambda: K.layernorm(x, w, b, y), 10, torch), f"[{rows}, {d}]")
+    dy = torch.randn(rows, d, device=dev).to(bf)
+    dx = torch.zeros(rows, d, device=dev)
+    dg, db = torch.empty(d, device=dev), torch.empty(d, device=dev)
+    rec("layernorm_bwd_kernel (+dgamma/dbeta)", rows * d * (4 + 2 + 4 + 4),
+        _ev_ms(lambda: K.layernorm_bwd(x, dy, w, b, dx, accumulate=True, dgamma=dg, dbeta=db), 10, torch),
+        f"x fp32 + dy bf16 in, dx fp32 read-modify-write, [{rows}, {d}]")
+    u = torch.randn(rows // 2, 2 * FFN, device=dev).to(bf)
+    uo = torch.empty(rows // 2, FFN, dtype=bf, device=dev)
+    rec("geglu_fwd_kernel", (rows // 2) * FFN * 6, _ev_ms(lambda: K.geglu_fwd(u, uo), 10, torch), f"[{rows // 2}, 2 x {FFN}] -> [{rows // 2}, {FFN}] bf16")
+    del u, uo
+    Bt, T = 1024, 71
+    tok = torch.randint(4, 50264, (Bt, T), device=dev)
+    table = torch.randn(50264, d, device=dev).to(bf)
+    pos, cls = torch.randn(514, d, device=dev), torch.randn(d, device=dev)
+    rec("text_embed_kernel", Bt * (T + 1) * d * (2 + 4 + 4), _ev_ms(lambda: K.text_embed(tok, table, pos, cls), 10, torch),
+        f"{Bt} x {T} tokens: bf16 table row + fp32 pos row read, fp32 row written")
+    Ba, N = 16, 240000
+    wav = torch.randn(Ba, N, device=dev)
+    frames = (N - 10) // 5 + 1
+    a0 = torch.empty(Ba * frames, 16, dtype=bf, device=dev)
+    rec("audio_frame10_kernel", Ba * N * 4 + Ba * frames * 32, _ev_ms(lambda: K.audio_frame10(wav, frames, a0), 10, torch),
+        f"{Ba} x 15 s waveform -> [{Ba * frames}, 16] bf16 frames")
+    w0 = torch.randn(512, 16, device=dev).to(bf)
+    y0 = torch.empty(Ba * frames, 512, dtype=bf, device=dev)
+    rec("gemm_bf16_kernel (audio conv layer 0, K = 16)", Ba * frames * (32 + 1024), _ev_ms(lambda: K.gemm(a0, w0, K.EPI_STORE_BF16, y0), 10, torch),
+        f"[{Ba * frames}, 16] x [512, 16]^T -> bf16 [{Ba * frames}, 512]: output-write bound")
+    idx = torch.randperm(rows, device=dev)
+    src = torch.empty(rows, 3 * d, dtype=bf, device=dev).normal_()
+    dst = torch.empty_like(src)
+    rec("row_gather_kernel (qkv modality-major -> batch-major)", rows * 3 * d * 4, _ev_ms(lambda: K.row_gather(src, idx, out=dst), 10, torch),
+        f"[{rows}, {3 * d}] bf16 row permutation")
+    tr = torch.empty(12608, 6144, dtype=bf, device=dev).normal_()
+    rec("transpose_bf16_vec_kernel", 12608 * 6144 * 4, _ev_ms(lambda: K.transpose_bf16(tr), 10, torch), "[12608, 6144] bf16 (dW operand)")
+    return {"peak_gbs": hbm, "kernels": out}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -327,6 +616,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the contrastive / eager-baseline / hbm_kernels blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

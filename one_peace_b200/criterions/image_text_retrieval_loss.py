@@ -35,16 +35,22 @@ class _InfoNCE(torch.autograd.Function):
         d = a_local.shape[1]
         # bf16x3 operand split: logits accurate to ~2^-16 on the bf16 tensor cores (csrc/infonce.cu)
         a3, b3 = K.split_bf16x3(f32(a_local), 0), K.split_bf16x3(f32(b_local), 0)
-        a_all3, b_all3 = K.split_bf16x3(f32(a_all), 1), K.split_bf16x3(f32(b_all), 1)
+        n_cls = a_all.shape[0]
+        fa, fb = f32(a_all), f32(b_all)
+        if n_cls % 8:                 # the GEMM wants N % 8 == 0: zero rows, ignored through n_valid (tiny global batches)
+            padr = torch.zeros((-n_cls) % 8, d, dtype=torch.float32, device=fa.device)
+            fa, fb = torch.cat([fa, padr]), torch.cat([fb, padr])
+        a_all3, b_all3 = K.split_bf16x3(fa, 1), K.split_bf16x3(fb, 1)
         s = scale.detach().to(torch.float32).reshape(1).contiguous()
         bsz, n = a3.shape[0], a_all3.shape[0]
+        nv = n_cls if n_cls != n else 0
         off = bsz * rank
-        lse_a, loss_a, am_a = K.infonce_rows(a3, b_all3, s, off, eps)
-        lse_b, loss_b, am_b = K.infonce_rows(b3, a_all3, s, off, eps)
+        lse_a, loss_a, am_a = K.infonce_rows(a3, b_all3, s, off, eps, n_valid=nv)
+        lse_b, loss_b, am_b = K.infonce_rows(b3, a_all3, s, off, eps, n_valid=nv)
         out = K.infonce_reduce(loss_a, loss_b, am_a, am_b, off)
         if a_local.requires_grad or b_local.requires_grad or scale.requires_grad:
-            ga, ws_a = K.infonce_grad(a3, b_all3, K.transpose_bf16(b_all3, cols=d), s, lse_a, off, eps)
-            gb, ws_b = K.infonce_grad(b3, a_all3, K.transpose_bf16(a_all3, cols=d), s, lse_b, off, eps)
+            ga, ws_a = K.infonce_grad(a3, b_all3, K.transpose_bf16(b_all3, cols=d), s, lse_a, off, eps, n_valid=nv)
+            gb, ws_b = K.infonce_grad(b3, a_all3, K.transpose_bf16(a_all3, cols=d), s, lse_b, off, eps, n_valid=nv)
             dlogit = K.infonce_dscale(ws_a, ws_b, bsz, n)        # d loss / d log(scale)
             ctx.save_for_backward(ga, gb, dlogit, s)
         ctx.dtypes = (a_local.dtype, b_local.dtype, scale.dtype)

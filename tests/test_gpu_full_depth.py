@@ -11,7 +11,7 @@ Two synthetic networks (scripts/parity_depth.py):
     asserted instead: the error-budget control — the sm_100a path must be at least as close to the fp32 oracle as the
     reference's own arithmetic run in bf16 eager on the same GPU (oracle/restated.py on CUDA, bf16 weights + activations).
 Arg-max on every row: candidates are drawn until every row (and column) of the oracle's similarity matrix is decided by a
-margin > 5e-3, then ALL rows are compared (no row is skipped)."""
+margin > 4e-3 (>= 4 sigma of the bf16 path's similarity error), then ALL rows are compared (no row is skipped)."""
 import os
 import sys
 
@@ -38,26 +38,39 @@ def hub_for(sd, dtype="bfloat16", head_type="val"):
                            attention_heads=PD.H, patch_image_size=224, device="cuda", dtype=dtype, vocab_size=PD.VOCAB)
 
 
-def pick_decided(sim, k, margin, seed=0, tries=2000, both_ways=True):
-    """Columns (k of them) of the oracle similarity matrix such that every row's and every column's best match over the
-    selection wins by more than `margin`; rows = queries (k x n_candidates)."""
-    g = torch.Generator().manual_seed(seed)
-    n = sim.shape[1]
-    for _ in range(tries):
-        cols = torch.randperm(n, generator=g)[:k]
-        sub = sim[:, cols]
-        t_r = sub.topk(2, dim=1).values
-        t_c = sub.topk(2, dim=0).values
-        if (t_r[:, 0] - t_r[:, 1]).min() > margin and (both_ways is False or (t_c[0] - t_c[1]).min() > margin):
-            return cols
-    raise AssertionError("no decided candidate set found")
+def pick_decided(sim, k, margin, both_ways=True):
+    """Candidate columns of the ORACLE similarity matrix (rows = queries) such that every row's best match — and, with
+    both_ways, every kept column's best row — wins by more than `margin`: greedy removal of runner-ups / undecided columns,
+    then the rows' winners plus arbitrary other survivors up to k (a subset only widens the margins)."""
+    keep = list(range(sim.shape[1]))
+    changed = True
+    while changed and len(keep) > 1:
+        changed = False
+        sub = sim[:, keep]
+        top = sub.topk(2, dim=1)
+        bad = ((top.values[:, 0] - top.values[:, 1]) <= margin).nonzero().flatten()
+        if bad.numel():
+            keep.pop(int(top.indices[bad[0], 1]))                  # drop the runner-up of the first undecided row
+            changed = True
+            continue
+        if both_ways:
+            tc = sub.topk(2, dim=0).values
+            badc = ((tc[0] - tc[1]) <= margin).nonzero().flatten()
+            if badc.numel():
+                keep.pop(int(badc[0]))
+                changed = True
+    winners = sorted({keep[i] for i in sim[:, keep].argmax(1).tolist()})
+    rest = [c for c in keep if c not in winners]
+    cols = (winners + rest)[:max(k, len(winners))]
+    assert len(cols) >= 2, "no decided candidate set found"
+    return torch.tensor(sorted(cols))
 
 
 def test_config3_trimodal_40_layers_gates_vs_fp32_oracle():
     need_gpu()
     torch.set_num_threads(min(os.cpu_count() or 1, 16))
     sd = PD.build_sd(PD.NETS["conditioned"])
-    tok, img, aud, apm = PD.inputs(n_text=24, audio=True)
+    tok, img, aud, apm = PD.inputs(n_text=48, audio=True)
     want = PD.oracle_embeddings(sd, tok, img, aud, apm)                       # fp32, CPU
     hub = hub_for(sd)
     got = {"text": hub.extract_text_features(tok.cuda()).float().cpu(),
@@ -67,13 +80,13 @@ def test_config3_trimodal_40_layers_gates_vs_fp32_oracle():
         cos = F.cosine_similarity(got[m], want[m]).min().item()
         assert cos >= 0.999, (m, cos)
     scale = R.logit_scale_exp(sd["logit_scale"])
+    from one_peace_b200.criterions.image_text_retrieval_loss import itc_loss
     for a in ("image", "audio"):
-        cols = pick_decided(want[a] @ want["text"].t(), PD.B, 5e-3)
-        wt, gt = want["text"][cols], got["text"][cols]
-        ws, gs = want[a] @ wt.t(), got[a] @ gt.t()
+        cols = pick_decided(want[a] @ want["text"].t(), PD.B, 4e-3)
+        ws, gs = want[a] @ want["text"][cols].t(), got[a] @ got["text"][cols].t()
         assert torch.equal(gs.argmax(1), ws.argmax(1)) and torch.equal(gs.argmax(0), ws.argmax(0)), a      # every row / column
+        wt, gt = want["text"][:PD.B], got["text"][:PD.B]                      # the config's 8 pairs for the loss
         lw = R.itc_loss(want[a], wt, want[a], wt, scale, 0, 0.0)[0].item()
-        from one_peace_b200.criterions.image_text_retrieval_loss import itc_loss
         lg = itc_loss(got[a].cuda(), gt.cuda(), got[a].cuda(), gt.cuda(), scale.cuda(), 0, 0.0)[0].item()
         assert abs(lg - lw) / abs(lw) <= 1e-3, (a, lg, lw)
 
@@ -96,7 +109,7 @@ def test_config2_vision_batch64_40_layers_vs_fp32_oracle():
     assert cos >= 0.999, cos
     # image-to-image retrieval inside the first 16 (self-match removed), gallery drawn until every query is decided by > 5e-3
     ws, gs = want @ want.t() - 2 * torch.eye(16), got[:16] @ got[:16].t() - 2 * torch.eye(16)
-    cols = pick_decided(ws, 8, 5e-3, both_ways=False)
+    cols = pick_decided(ws, 8, 4e-3, both_ways=False)
     assert torch.equal(gs[:, cols].argmax(1), ws[:, cols].argmax(1))
     small = hub.extract_image_features(img[:16].cuda()).float().cpu()
     assert F.cosine_similarity(small, got[:16]).min() > 0.99999           # batch size does not change a sample's embedding
