@@ -155,15 +155,37 @@ grad_sumsq_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict_
   const long off = chunk_off[c];
   long n = t.numel - off;
   if (n > kChunk) n = kChunk;
+  // 16-byte loads, all of a thread's loads of the chunk issued before the first use (the scalar version of round 1 ran
+  // at 0.43 of the HBM peak: 2-byte loads, 32 dependent iterations per chunk).  The summation order per thread and the
+  // tree below are fixed, so the result stays bit-reproducible across ranks and runs.
   float acc = 0.f;
   if (t.g_dtype == 0) {
     const float* g = reinterpret_cast<const float*>(t.g) + off;
-    for (long i = threadIdx.x; i < n; i += kAdamThreads) acc += g[i] * g[i];
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && n == kChunk) {
+      float4 v[kChunk / (kAdamThreads * 4)];
+#pragma unroll
+      for (int k = 0; k < kChunk / (kAdamThreads * 4); ++k) v[k] = reinterpret_cast<const float4*>(g)[k * kAdamThreads + threadIdx.x];
+#pragma unroll
+      for (int k = 0; k < kChunk / (kAdamThreads * 4); ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    } else {
+      for (long i = threadIdx.x; i < n; i += kAdamThreads) acc += g[i] * g[i];
+    }
   } else {
     const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(t.g) + off;
-    for (long i = threadIdx.x; i < n; i += kAdamThreads) {
-      const float x = __bfloat162float(g[i]);
-      acc += x * x;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && n == kChunk) {
+      uint4 v[kChunk / (kAdamThreads * 8)];
+#pragma unroll
+      for (int k = 0; k < kChunk / (kAdamThreads * 8); ++k) v[k] = reinterpret_cast<const uint4*>(g)[k * kAdamThreads + threadIdx.x];
+#pragma unroll
+      for (int k = 0; k < kChunk / (kAdamThreads * 8); ++k) {
+        const float2 a = unpack_bf16x2(v[k].x), b = unpack_bf16x2(v[k].y), c = unpack_bf16x2(v[k].z), d = unpack_bf16x2(v[k].w);
+        acc += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+      }
+    } else {
+      for (long i = threadIdx.x; i < n; i += kAdamThreads) {
+        const float x = __bfloat162float(g[i]);
+        acc += x * x;
+      }
     }
   }
   acc = warp_sum(acc);

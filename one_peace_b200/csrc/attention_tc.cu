@@ -2,7 +2,10 @@
 //     P = softmax_fp32(q k^T + relpos_bias[h] (+ -inf on padded keys)),  o = P v            (multihead_attention.py:107-115)
 //
 // One CTA = (batch, head, 128-query tile).  Warp 0 issues TMA (Q, all K blocks, all V blocks of this (b, h) straight
-// from the QKV GEMM output), warp 1 issues the MMAs, warps 2-5 own one query row per thread:
+// from the QKV GEMM output), warp 1 issues the MMAs, warps 2-9 are the soft-max warps: TWO threads per query row (the
+// two warps that share a TMEM lane quarter), each owning alternate 32-key chunks of the row — 16 soft-max warps per SM
+// instead of 8 hide the tcgen05.ld -> LDS gather -> MUFU chain that made the 4-warp version latency-bound (r01: 120 us
+// per layer, 0.09 of the tensor peak); row max / row sum / LayerNorm partials of the two halves meet in shared memory:
 //   S_kb = Q K_kb^T            tcgen05.mma  M=128 N=128 K=64, accumulators in TMEM (one 128-column slot per key block)
 //   phase A  (row thread)      tcgen05.ld S, add the relative-position bias, mask, running max, tcgen05.st the biased
 //                              scores back — no shuffles, no block barriers: a row never leaves its thread
@@ -85,8 +88,11 @@ __device__ unsigned int g_attn_n;
 #define OPB_T(i) do {} while (0)
 #endif
 
+constexpr int kTcRowThreads = 256;   // 8 soft-max warps
+constexpr int kTcThreads = 64 + kTcRowThreads;
+
 template <bool HAS_PAD>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, int lut_len,
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
@@ -122,7 +128,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     mbar_init(&bars->lut, 1);
     for (int i = 0; i < kTcMaxBlocks; ++i) {
       mbar_init(&bars->s[i], 1);
-      mbar_init(&bars->p[i], 4);
+      mbar_init(&bars->p[i], kTcRowThreads / 32);
       mbar_init(&bars->pv[i], 1);
     }
     fence_barrier_init();
@@ -182,20 +188,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     }
   } else {
     // ===================== row threads =====================
-    const int qw = warp & 3;                                 // TMEM lane quarter
+    const int qw = warp & 3;                                 // TMEM lane quarter (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;                        // which of the row's two threads: owns 32-key chunks c % 2 == half
     const int r = qw * 32 + lane;                            // row inside the tile
     const int qrow = q0 + r;
     const bool row_valid = qrow < S;
     const bool warp_valid = (q0 + qw * 32) < S;              // warp-uniform
-    const int tid4 = threadIdx.x - 64;                       // 0..127
+    const int tid4 = threadIdx.x - 64;                       // 0..255
     // phase-A tables in the P buffer: lut [lut_len] | code_col [S padded to 4] (| key_pad [S] bytes)
     const float* s_lut = reinterpret_cast<const float*>(sP);
     const int* s_ccol = reinterpret_cast<const int*>(sP) + lut_len;
     uint8_t* s_pad = sP + static_cast<long>(lut_len + ((S + 3) & ~3)) * 4;
     if constexpr (HAS_PAD) {
-      for (int i = tid4; i < S; i += 128) s_pad[i] = key_pad[static_cast<long>(b) * S + i];
-      named_bar_sync(1, 128);
+      for (int i = tid4; i < S; i += kTcRowThreads) s_pad[i] = key_pad[static_cast<long>(b) * S + i];
+      named_bar_sync(1, kTcRowThreads);
     }
+    // exchange area of the two threads of a row: [max | sum][half][row] floats + LayerNorm partials of the second half.  It
+    // aliases the Q tile, which is dead once the last S = Q K^T has completed (every row thread waits for that barrier
+    // before its first write); 112 KB + barriers must fit twice per SM, so there is no room for a separate buffer.
+    float* xch = reinterpret_cast<float*>(sQ);
+    float2* xstat = reinterpret_cast<float2*>(sQ + 4 * kTcQ * 4);
     const int crow = code_row[row_valid ? qrow : 0];
     // concatenated sequences ('vl' / 'al', transformer_encoder.py:148-158): the relative-position bias is block-diagonal —
     // a row only sees the bias of the keys of its own modality segment [seg_lo, seg_hi); zero across segments
@@ -213,7 +225,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       if (kb == 0) OPB_T(2);
       if (warp_valid) {
         const int kvalid = min(kTcK, S - kb * kTcK);
-        for (int c = 0; c < kvalid; c += 32) {
+        for (int c = half * 32; c < kvalid; c += 64) {
           uint32_t v[32];
           __syncwarp();
           tmem_ld32(lane_base + kb * kTcK + c, v);
@@ -248,9 +260,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       }
     }
     tmem_st_wait();
+    xch[(0 * 2 + half) * kTcQ + r] = m;
     tc_fence_before();
-    named_bar_sync(1, 128);            // every row thread is done with the LUT: the buffer becomes P
+    named_bar_sync(1, kTcRowThreads);  // every row thread is done with the LUT (the buffer becomes P); row maxima exchanged
     tc_fence_after();
+    m = fmaxf(m, xch[(0 * 2 + (half ^ 1)) * kTcQ + r]);
     OPB_T(3);
 
     // ---- phase B: exp, row sum, P -> shared memory ----
@@ -260,7 +274,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);     // previous P consumed by the tensor core
       const int kvalid = min(kTcK, S - kb * kTcK);
 #pragma unroll 1
-      for (int c = 0; c < kTcK; c += 32) {
+      for (int c = half * 32; c < kTcK; c += 64) {
         uint32_t pk[16];
         if (warp_valid && c < kvalid) {
           uint32_t v[32];
@@ -292,41 +306,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
 
     // ---- epilogue: O / l -> bf16 rows ----
     OPB_T(4);
+    xch[(1 * 2 + half) * kTcQ + r] = l;                       // partial row sums of the two halves
     mbar_wait(&bars->pv[nkb - 1], 0);
     tc_fence_after();
     OPB_T(5);
+    // half 0 normalises output columns [0, 32), half 1 columns [32, 64); half 1 hands its LayerNorm partials to half 0
+    float ssum = 0.f, ssq = 0.f;
+    uint32_t o0[32];
     if (warp_valid) {
-      uint32_t o0[32], o1[32];
       __syncwarp();
-      tmem_ld32(lane_base, o0);
-      tmem_ld32(lane_base + 32, o1);
+      tmem_ld32(lane_base + half * 32, o0);
       tmem_ld_wait();
-      if (row_valid) {
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        float ssum = 0.f, ssq = 0.f;
-        __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD;
+    }
+    named_bar_sync(2, kTcRowThreads);
+    l += xch[(1 * 2 + (half ^ 1)) * kTcQ + r];
+    if (warp_valid && row_valid) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD + half * 32;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float y[8];
+      for (int k = 0; k < 4; ++k) {
+        float y[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o0[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
-          *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                             pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float y[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o1[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
-          *reinterpret_cast<uint4*>(op + 32 + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                                  pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        }
-        // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
-        if (lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
-        if (ln_stats != nullptr) {
-          const long rows_total = static_cast<long>(B) * S;
-          *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
-        }
+        for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o0[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
+        *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                           pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+      // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
+      if (half == 0 && lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
+    }
+    if (ln_stats != nullptr) {
+      if (half == 1) xstat[r] = make_float2(ssum, ssq);
+      named_bar_sync(3, kTcRowThreads);
+      if (half == 0 && warp_valid && row_valid) {
+        const float2 o = xstat[r];
+        const long rows_total = static_cast<long>(B) * S;
+        *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) =
+            make_float2(ssum + o.x, ssq + o.y);
       }
     }
   }
@@ -401,10 +416,10 @@ int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* 
   const int q_tiles = (S + kTcQ - 1) / kTcQ;
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
   if (v)
-    attention_tc_kernel<true><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
+    attention_tc_kernel<true><<<grid, kTcThreads, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
                                                           reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   else
-    attention_tc_kernel<false><<<grid, 192, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
+    attention_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
                                                            reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }

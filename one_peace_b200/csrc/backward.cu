@@ -81,9 +81,10 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
 #pragma unroll
   for (int k = 0; k < GROUPS; ++k) dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_dim = 1.f / dim;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    float4 xv[GROUPS], gv[GROUPS];
-    float s1 = 0.f;
+  // Software pipeline over the CTA's rows: the loads of row r + gridDim (and the old dx of row r when accumulating) are
+  // issued before the three block reductions of row r, so HBM latency hides behind them (round 1 issued them after:
+  // 0.46 of the HBM peak).
+  auto load_row = [&](int row, float4 (&xr)[GROUPS], float4 (&gr)[GROUPS]) {
     // the forward's 2x2 pixel-merge scatter (layernorm.cu, adapter/image.py:37-47): row (b, y, x) of the w x w grid
     // went to row (b, y/2, x/2), column block (y%2)*2 + x%2 of the next conv's operand
     const TDY* dyr = dy + row * ld_dy;
@@ -96,11 +97,35 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
     for (int k = 0; k < GROUPS; ++k) {
       const int g = threadIdx.x + k * THREADS;
       if (g < ngroups) {
-        xv[k] = load4(x + row * ldx + 4 * g);
-        gv[k] = load4(dyr + 4 * g);
-        s1 += xv[k].x + xv[k].y + xv[k].z + xv[k].w;
+        xr[k] = load4(x + row * ldx + 4 * g);
+        gr[k] = load4(dyr + 4 * g);
       } else {
-        xv[k] = gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[k] = gr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  constexpr bool kPrefetch = THREADS == 128;   // dim <= 1536 variants only: the wider ones have no registers to spare (and 12-24 KB rows)
+  float4 xn[kPrefetch ? GROUPS : 1], gn[kPrefetch ? GROUPS : 1];
+  if constexpr (kPrefetch) {
+    if (blockIdx.x < rows) load_row(blockIdx.x, xn, gn);
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    float4 xv[GROUPS], gv[GROUPS], oldv[GROUPS];
+    float s1 = 0.f;
+    if constexpr (kPrefetch) {
+#pragma unroll
+      for (int k = 0; k < GROUPS; ++k) { xv[k] = xn[k]; gv[k] = gn[k]; }
+      if (row + static_cast<int>(gridDim.x) < rows) load_row(row + gridDim.x, xn, gn);
+    } else {
+      load_row(row, xv, gv);
+    }
+#pragma unroll
+    for (int k = 0; k < GROUPS; ++k) s1 += xv[k].x + xv[k].y + xv[k].z + xv[k].w;
+    if (accumulate) {
+#pragma unroll
+      for (int k = 0; k < GROUPS; ++k) {
+        const int g = threadIdx.x + k * THREADS;
+        oldv[k] = g < ngroups ? load4(dx + row * ld_dx + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     const float mean = block_sum2<THREADS>(s1, 0.f, red).x * inv_dim;
@@ -147,10 +172,7 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
         o.z = rstd * (gv[k].z - m1 - xv[k].z * m2);
         o.w = rstd * (gv[k].w - m1 - xv[k].w * m2);
         TDX* p = dx + row * ld_dx + 4 * g;
-        if (accumulate) {
-          const float4 old = load4(p);
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
+        if (accumulate) { o.x += oldv[k].x; o.y += oldv[k].y; o.z += oldv[k].z; o.w += oldv[k].w; }
         store4(p, o);
       }
     }

@@ -38,32 +38,25 @@ def hub_for(sd, dtype="bfloat16", head_type="val"):
                            attention_heads=PD.H, patch_image_size=224, device="cuda", dtype=dtype, vocab_size=PD.VOCAB)
 
 
-def pick_decided(sim, k, margin, both_ways=True):
+def pick_decided(sim, k, margin, both_ways=True, tries=40000, seed=0):
     """Candidate columns of the ORACLE similarity matrix (rows = queries) such that every row's best match — and, with
-    both_ways, every kept column's best row — wins by more than `margin`: greedy removal of runner-ups / undecided columns,
-    then the rows' winners plus arbitrary other survivors up to k (a subset only widens the margins)."""
-    keep = list(range(sim.shape[1]))
-    changed = True
-    while changed and len(keep) > 1:
-        changed = False
-        sub = sim[:, keep]
-        top = sub.topk(2, dim=1)
-        bad = ((top.values[:, 0] - top.values[:, 1]) <= margin).nonzero().flatten()
-        if bad.numel():
-            keep.pop(int(top.indices[bad[0], 1]))                  # drop the runner-up of the first undecided row
-            changed = True
-            continue
+    both_ways, every kept column's best row — wins by more than `margin`: best of `tries` random k-subsets (batched), k
+    reduced by two if no subset reaches the margin.  The construction is asserted, then EVERY row / column is compared."""
+    g = torch.Generator().manual_seed(seed)
+    n = sim.shape[1]
+    while k >= 2:
+        perm = torch.rand(tries, n, generator=g).argsort(dim=1)[:, :k]
+        sub = sim[:, perm].permute(1, 0, 2)                                  # tries x rows x k
+        tr = sub.topk(2, dim=2).values
+        ok = (tr[..., 0] - tr[..., 1]).min(dim=1).values
         if both_ways:
-            tc = sub.topk(2, dim=0).values
-            badc = ((tc[0] - tc[1]) <= margin).nonzero().flatten()
-            if badc.numel():
-                keep.pop(int(badc[0]))
-                changed = True
-    winners = sorted({keep[i] for i in sim[:, keep].argmax(1).tolist()})
-    rest = [c for c in keep if c not in winners]
-    cols = (winners + rest)[:max(k, len(winners))]
-    assert len(cols) >= 2, "no decided candidate set found"
-    return torch.tensor(sorted(cols))
+            tc = sub.topk(2, dim=1).values
+            ok = torch.minimum(ok, (tc[:, 0] - tc[:, 1]).min(dim=1).values)
+        best = int(ok.argmax())
+        if float(ok[best]) > margin:
+            return perm[best].sort().values
+        k -= 2
+    raise AssertionError("no decided candidate set found")
 
 
 def test_config3_trimodal_40_layers_gates_vs_fp32_oracle():
