@@ -2,15 +2,14 @@
 //     P = softmax_fp32(q k^T + relpos_bias[h] (+ -inf on padded keys)),  o = P v            (multihead_attention.py:107-115)
 //
 // One CTA = (batch, head, 128-query tile).  Warp 0 issues TMA (Q, all K blocks, all V blocks of this (b, h) straight
-// from the QKV GEMM output), warp 1 issues the MMAs, warps 2-9 are the soft-max warps: TWO threads per query row (the
-// two warps that share a TMEM lane quarter), each owning alternate 32-key chunks of the row — 16 soft-max warps per SM
-// instead of 8 hide the tcgen05.ld -> LDS gather -> MUFU chain that made the 4-warp version latency-bound (r01: 120 us
-// per layer, 0.09 of the tensor peak); row max / row sum / LayerNorm partials of the two halves meet in shared memory:
+// from the QKV GEMM output), warp 1 issues the MMAs, warps 2-5 own one query row per thread:
 //   S_kb = Q K_kb^T            tcgen05.mma  M=128 N=128 K=64, accumulators in TMEM (one 128-column slot per key block)
-//   phase A  (row thread)      tcgen05.ld S, add the relative-position bias, mask, running max, tcgen05.st the biased
-//                              scores back — no shuffles, no block barriers: a row never leaves its thread
-//   phase B  (row thread)      p = exp2(s log2e - max log2e), row sum, P (bf16) -> shared memory in the K-major 128B-
-//                              swizzled layout the next MMA reads
+//   phase A  (row thread)      tcgen05.ld S, max tree -> m = max_j s_ij + max(lut[h]): an UPPER BOUND of the biased row
+//                              maximum (soft-max is shift invariant; the slack is at most the spread of the head's bias
+//                              table) — no LUT gather, no add, no tcgen05.st here (round 2; round 1 did all three and
+//                              spent a third of the CTA's time in this phase)
+//   phase B  (row thread)      tcgen05.ld S, gather the biases, p = exp2((s + bias) log2e - m log2e) (-inf on padded keys),
+//                              row sum, P (bf16) -> shared memory in the K-major 128B-swizzled layout the next MMA reads
 //   O += P_kb V_kb             tcgen05.mma  M=128 N=64 K=128, V consumed as an MN-major operand exactly as TMA wrote
 //                              it ([key][d] rows of 128 B) — no transpose;  O aliases the first 64 columns of S_0
 //   epilogue (row thread)      tcgen05.ld O, scale by 1/l, bf16, 128-byte row store (+ inner-LN partial statistics)
@@ -23,7 +22,8 @@
 // costs one shared-memory gather instead of a 4-byte read of a 1.9 MB table per (batch, head) — that L2 stream and the
 // shuffle / barrier-bound online softmax made the mma.sync kernel (attention.cu) latency-bound at ~200 us per layer.
 //
-// Shared memory 112 KB (Q 16 + K 32 + V 32 + P 32; the LUT and code tables live in the P buffer during phase A) and
+// Shared memory 112 KB (Q 16 + K 32 + V 32 + P 32; the LUT and code tables land in the P buffer and move into the dead
+// Q tile between the phases) and
 // 256 TMEM columns per CTA -> two CTAs per SM overlap each other's TMA / MMA / softmax phases.
 #include "common.cuh"
 #include "ops.h"
@@ -62,6 +62,14 @@ OPB_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+OPB_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 OPB_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 OPB_DEVICE void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
@@ -88,12 +96,9 @@ __device__ unsigned int g_attn_n;
 #define OPB_T(i) do {} while (0)
 #endif
 
-constexpr int kTcRowThreads = 256;   // 8 soft-max warps
-constexpr int kTcThreads = 64 + kTcRowThreads;
-
 template <bool HAS_PAD>
-__global__ void __launch_bounds__(kTcThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, int lut_len,
+__global__ void __launch_bounds__(192, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, const float* __restrict__ lut_max, int lut_len,
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
                     float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols,
@@ -128,7 +133,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     mbar_init(&bars->lut, 1);
     for (int i = 0; i < kTcMaxBlocks; ++i) {
       mbar_init(&bars->s[i], 1);
-      mbar_init(&bars->p[i], kTcRowThreads / 32);
+      mbar_init(&bars->p[i], 4);
       mbar_init(&bars->pv[i], 1);
     }
     fence_barrier_init();
@@ -188,36 +193,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     }
   } else {
     // ===================== row threads =====================
-    const int qw = warp & 3;                                 // TMEM lane quarter (hardware: warp id % 4)
-    const int half = (warp - 2) >> 2;                        // which of the row's two threads: owns 32-key chunks c % 2 == half
+    const int qw = warp & 3;                                 // TMEM lane quarter
     const int r = qw * 32 + lane;                            // row inside the tile
     const int qrow = q0 + r;
     const bool row_valid = qrow < S;
     const bool warp_valid = (q0 + qw * 32) < S;              // warp-uniform
-    const int tid4 = threadIdx.x - 64;                       // 0..255
-    // phase-A tables in the P buffer: lut [lut_len] | code_col [S padded to 4] (| key_pad [S] bytes)
-    const float* s_lut = reinterpret_cast<const float*>(sP);
-    const int* s_ccol = reinterpret_cast<const int*>(sP) + lut_len;
-    uint8_t* s_pad = sP + static_cast<long>(lut_len + ((S + 3) & ~3)) * 4;
+    const int tid4 = threadIdx.x - 64;                       // 0..127
+    // bias tables: lut [lut_len] | code_col [S padded to 4] (| key_pad [S] bytes).  They land in the P buffer (bulk copy
+    // at kernel start) and are moved into the Q tile once the last S = Q K^T has completed (Q is dead then), because phase B
+    // gathers from them while it fills the P buffer.
+    const int tbl_words = lut_len + ((S + 3) & ~3);
+    const int pad_bytes = HAS_PAD ? ((S + 31) & ~31) : 0;
+    const int tbl_bytes = (tbl_words * 4 + pad_bytes + 15) & ~15;
+    const float* s_lut = reinterpret_cast<const float*>(sQ);
+    const int* s_ccol = reinterpret_cast<const int*>(sQ) + lut_len;
+    const uint8_t* s_pad_w = sQ + static_cast<long>(tbl_words) * 4;    // key-padding bytes, zero beyond S up to the 32-key chunk end
     if constexpr (HAS_PAD) {
-      for (int i = tid4; i < S; i += kTcRowThreads) s_pad[i] = key_pad[static_cast<long>(b) * S + i];
-      named_bar_sync(1, kTcRowThreads);
+      uint8_t* pad_in = sP + static_cast<long>(tbl_words) * 4;
+      for (int i = tid4; i < pad_bytes; i += 128) pad_in[i] = i < S ? key_pad[static_cast<long>(b) * S + i] : 0;
     }
-    // exchange area of the two threads of a row: [max | sum][half][row] floats + LayerNorm partials of the second half.  It
-    // aliases the Q tile, which is dead once the last S = Q K^T has completed (every row thread waits for that barrier
-    // before its first write); 112 KB + barriers must fit twice per SM, so there is no room for a separate buffer.
-    float* xch = reinterpret_cast<float*>(sQ);
-    float2* xstat = reinterpret_cast<float2*>(sQ + 4 * kTcQ * 4);
     const int crow = code_row[row_valid ? qrow : 0];
     // concatenated sequences ('vl' / 'al', transformer_encoder.py:148-158): the relative-position bias is block-diagonal —
     // a row only sees the bias of the keys of its own modality segment [seg_lo, seg_hi); zero across segments
     const int seg_lo = (seg_split > 0 && qrow >= seg_split) ? seg_split : 0;
     const int seg_hi = (seg_split > 0 && qrow < seg_split) ? seg_split : S;
-    mbar_wait(&bars->lut, 0);
     OPB_T(1);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
 
-    // ---- phase A: bias, mask, row max; biased scores written back to TMEM ----
+    // ---- phase A: an upper bound of the row maximum, WITHOUT touching the bias ----
+    // soft-max is shift invariant, so any m >= max_j (s_ij + bias_ij) that is not absurdly loose gives the same result: bf16
+    // P and the fp32 row sum / O accumulators keep full relative precision for exp(x - m) down to ~1e-38.  We use
+    //     m = max_j s_ij  +  max_l lut[h][l]        (slack <= spread of the head's bias table, a few units)
+    // which needs only tcgen05.ld + a max tree per 32-key chunk: no LUT gather, no add, and no tcgen05.st of biased scores
+    // back into TMEM (round 1 did all three here and again loaded the scores in phase B: 3.4 + 3.2 us of a 10.2 us CTA).
+    // Padded keys and the neighbouring sample's rows inside the last block may enter the bound; they only loosen it.
     float m = -INFINITY;
     for (int kb = 0; kb < nkb; ++kb) {
       mbar_wait(&bars->s[kb], 0);
@@ -225,123 +234,155 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       if (kb == 0) OPB_T(2);
       if (warp_valid) {
         const int kvalid = min(kTcK, S - kb * kTcK);
-        for (int c = half * 32; c < kvalid; c += 64) {
+        for (int c = 0; c < kvalid; c += 32) {
           uint32_t v[32];
           __syncwarp();
           tmem_ld32(lane_base + kb * kTcK + c, v);
-          // gather the 32 biases of this row while the TMEM load is in flight: column codes (broadcast, vectorised),
-          // then 32 independent LUT reads
-          const int key0 = kb * kTcK + c;
-          int idx[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int4 cc = *reinterpret_cast<const int4*>(s_ccol + key0 + j);     // rows past S: padded / stale but in-bounds
-            idx[j] = crow - cc.x; idx[j + 1] = crow - cc.y; idx[j + 2] = crow - cc.z; idx[j + 3] = crow - cc.w;
-          }
-          float bia[32];
-          const bool full = key0 + 32 <= S;
-          const bool in_seg = key0 >= seg_lo && key0 + 32 <= seg_hi;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) bia[j] = (in_seg || (key0 + j >= seg_lo && key0 + j < seg_hi)) ? s_lut[idx[j]] : 0.f;
           tmem_ld_wait();
+          float t8[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float sc = __uint_as_float(v[j]) + bia[j];
-            if (!full && key0 + j >= S) sc = -INFINITY;
-            if constexpr (HAS_PAD) {
-              if (key0 + j < S && s_pad[key0 + j] != 0) sc = -INFINITY;
-            }
-            m = fmaxf(m, sc);
-            v[j] = __float_as_uint(sc);
-          }
-          __syncwarp();
-          tmem_st32(lane_base + kb * kTcK + c, v);
+          for (int j = 0; j < 8; ++j)
+            t8[j] = fmaxf(fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 8])), fmaxf(__uint_as_float(v[j + 16]), __uint_as_float(v[j + 24])));
+          m = fmaxf(m, fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7]))));
         }
       }
     }
-    tmem_st_wait();
-    xch[(0 * 2 + half) * kTcQ + r] = m;
-    tc_fence_before();
-    named_bar_sync(1, kTcRowThreads);  // every row thread is done with the LUT (the buffer becomes P); row maxima exchanged
-    tc_fence_after();
-    m = fmaxf(m, xch[(0 * 2 + (half ^ 1)) * kTcQ + r]);
+    m += lut_max[h];
+    // every S_kb has completed: Q is dead.  Move the tables P buffer -> Q tile (16-byte pieces), then the P buffer is free.
+    mbar_wait(&bars->lut, 0);
+    if constexpr (HAS_PAD) named_bar_sync(1, 128);       // pad bytes written by other threads
+    for (int i = tid4 * 16; i < tbl_bytes; i += 128 * 16) sts128u(sQ + i, *reinterpret_cast<const uint4*>(sP + i));
+    named_bar_sync(1, 128);
     OPB_T(3);
 
-    // ---- phase B: exp, row sum, P -> shared memory ----
-    const float mb = (m == -INFINITY) ? 0.f : m * 1.4426950408889634f;
-    float l = 0.f;
+    // ---- phase B: bias gather, exp, row sum, P -> shared memory ----
+    // Software-pipelined over 16-key sub-chunks: while sub-chunk t is exponentiated / packed / stored, the TMEM load and the
+    // LUT gathers of sub-chunk t + 1 are already in flight (the inline-asm tcgen05 statements are compiler barriers, so the
+    // overlap has to be written out; without it the per-chunk chain ld -> gather -> ex2 -> store was fully exposed with only
+    // two soft-max warps per scheduler: 4.9 us of a 9.5 us CTA).
+    const float mb = m * 1.4426950408889634f;
+    float l0 = 0.f, l1 = 0.f;
+    const int nsub = nkb * (kTcK / 16);
+    auto prefetch = [&](int t, uint32_t (&v)[16], float (&add)[16]) {
+      const int key0 = t * 16;                         // TMEM column == key index (128-column slot per key block)
+      __syncwarp();
+      tmem_ld16(lane_base + key0, v);
+      int ii[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const int4 cc = *reinterpret_cast<const int4*>(s_ccol + key0 + j);     // keys past S: padded / stale but in-bounds
+        ii[j] = crow - cc.x; ii[j + 1] = crow - cc.y; ii[j + 2] = crow - cc.z; ii[j + 3] = crow - cc.w;
+      }
+      // warp-uniform fast path: the whole sub-chunk lies inside the row's own modality segment (and the sequence) -> 16
+      // unconditional gathers.  Otherwise the index is clamped and the value selected afterwards — never a conditional
+      // LOAD: the compiler turns those into divergent branch regions (measured: 4x slower loop).
+      const bool fast = __all_sync(0xffffffffu, key0 >= seg_lo && key0 + 16 <= seg_hi);
+      if (fast) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) add[j] = fmaf(s_lut[ii[j]], 1.4426950408889634f, -mb);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = (key0 + j >= seg_lo) & (key0 + j < seg_hi);
+          const float bv = s_lut[ok ? ii[j] : 0];
+          add[j] = fmaf(ok ? bv : 0.f, 1.4426950408889634f, -mb);
+          add[j] = (key0 + j >= S) ? -INFINITY : add[j];
+        }
+      }
+      if constexpr (HAS_PAD) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const uint32_t pw = *reinterpret_cast<const uint32_t*>(s_pad_w + key0 + j);   // 4 mask bytes (zero beyond S)
+          add[j] = (pw & 0xffu) ? -INFINITY : add[j];
+          add[j + 1] = (pw & 0xff00u) ? -INFINITY : add[j + 1];
+          add[j + 2] = (pw & 0xff0000u) ? -INFINITY : add[j + 2];
+          add[j + 3] = (pw & 0xff000000u) ? -INFINITY : add[j + 3];
+        }
+      }
+    };
+    // sub-chunk t is live (has keys < S) iff t * 16 < S; dead sub-chunks of the last block are stored as zeros
+    auto finish = [&](int t, const uint32_t (&v)[16], const float (&add)[16], bool live) {
+      uint32_t pk[8];
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, add[j]));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), 1.4426950408889634f, add[j + 1]));
+          l0 += p0;
+          l1 += p1;
+          pk[j >> 1] = pack_bf16x2(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = 0u;
+      }
+      // 16 keys = 32 B = 16-byte chunks (c/8, c/8 + 1) of this row in atom c / 64, c = column inside the key block
+      const int c = (t * 16) & (kTcK - 1);
+      uint8_t* atom = sP + (c >> 6) * (kTcQ * 128);
+      sts128u(atom + sw128_off(r, ((c & 63) >> 3)), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      sts128u(atom + sw128_off(r, ((c & 63) >> 3) + 1), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+    };
+    uint32_t vA[16], vB[16];
+    float aA[16], aB[16];
+    const bool any = warp_valid;
+    if (any) prefetch(0, vA, aA);
     for (int kb = 0; kb < nkb; ++kb) {
       if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);     // previous P consumed by the tensor core
-      const int kvalid = min(kTcK, S - kb * kTcK);
 #pragma unroll 1
-      for (int c = half * 32; c < kTcK; c += 64) {
-        uint32_t pk[16];
-        if (warp_valid && c < kvalid) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld32(lane_base + kb * kTcK + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), 1.4426950408889634f, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), 1.4426950408889634f, -mb));
-            l += p0 + p1;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
-        }
-        // 32 keys = 64 B = chunks (c/8 .. c/8 + 3) of this row in atom c / 64
-        uint8_t* atom = sP + (c >> 6) * (kTcQ * 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          sts128u(atom + sw128_off(r, ((c & 63) >> 3) + k), make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+      for (int u = 0; u < kTcK / 16; u += 2) {
+        const int t = kb * (kTcK / 16) + u;
+        const bool liveA = any && t * 16 < S, liveB = any && (t + 1) * 16 < S, liveC = any && (t + 2) * 16 < S && t + 2 < nsub;
+        if (liveA) tmem_ld_wait();
+        if (liveB) prefetch(t + 1, vB, aB);
+        finish(t, vA, aA, liveA);
+        if (liveB) tmem_ld_wait();
+        if (liveC) prefetch(t + 2, vA, aA);
+        finish(t + 1, vB, aB, liveB);
       }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p[kb]);
     }
+    const float l = l0 + l1;
 
     // ---- epilogue: O / l -> bf16 rows ----
     OPB_T(4);
-    xch[(1 * 2 + half) * kTcQ + r] = l;                       // partial row sums of the two halves
     mbar_wait(&bars->pv[nkb - 1], 0);
     tc_fence_after();
     OPB_T(5);
-    // half 0 normalises output columns [0, 32), half 1 columns [32, 64); half 1 hands its LayerNorm partials to half 0
-    float ssum = 0.f, ssq = 0.f;
-    uint32_t o0[32];
     if (warp_valid) {
+      uint32_t o0[32], o1[32];
       __syncwarp();
-      tmem_ld32(lane_base + half * 32, o0);
+      tmem_ld32(lane_base, o0);
+      tmem_ld32(lane_base + 32, o1);
       tmem_ld_wait();
-    }
-    named_bar_sync(2, kTcRowThreads);
-    l += xch[(1 * 2 + (half ^ 1)) * kTcQ + r];
-    if (warp_valid && row_valid) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD + half * 32;
+      if (row_valid) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        float ssum = 0.f, ssq = 0.f;
+        __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float y[8];
+        for (int k = 0; k < 4; ++k) {
+          float y[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o0[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
-        *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                           pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-      }
-      // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
-      if (half == 0 && lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
-    }
-    if (ln_stats != nullptr) {
-      if (half == 1) xstat[r] = make_float2(ssum, ssq);
-      named_bar_sync(3, kTcRowThreads);
-      if (half == 0 && warp_valid && row_valid) {
-        const float2 o = xstat[r];
-        const long rows_total = static_cast<long>(B) * S;
-        *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) =
-            make_float2(ssum + o.x, ssq + o.y);
+          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o0[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
+          *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                             pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o1[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
+          *reinterpret_cast<uint4*>(op + 32 + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                                  pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+        // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
+        if (lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
+        if (ln_stats != nullptr) {
+          const long rows_total = static_cast<long>(B) * S;
+          *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
+        }
       }
     }
   }
@@ -388,17 +429,17 @@ int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int 
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
+int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int* code_row, const int* code_col,
                      const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
                      cudaStream_t stream) {
-  if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
+  if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || lut_max == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
   if (seg_split < 0 || seg_split >= S) return OPB_ERR_INVALID;
   const int nkb = (S + kTcK - 1) / kTcK;
   if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
   if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col) & 15) != 0)
     return OPB_ERR_INVALID;     // bulk-copied: 16-byte granularity (code_col must hold (S + 3) & ~3 entries)
-  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((S + 3) & ~3) * 4 + S + 128;
-  if (table_bytes > kTcQ * kTcK * 2) return OPB_ERR_UNSUPPORTED;
+  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((S + 3) & ~3) * 4 + S + 48;
+  if (table_bytes > kTcQ * 128) return OPB_ERR_UNSUPPORTED;      // the tables move into the 16 KB Q tile for phase B
   const int D = H * kTcD;
   CUtensorMap tm;
   int rc = make_tmap_bf16_2d(&tm, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, kTcQ);
@@ -416,10 +457,10 @@ int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* 
   const int q_tiles = (S + kTcQ - 1) / kTcQ;
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
   if (v)
-    attention_tc_kernel<true><<<grid, kTcThreads, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
+    attention_tc_kernel<true><<<grid, 192, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col, key_pad,
                                                           reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   else
-    attention_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(tm, lut, lut_len, code_row, code_col, key_pad,
+    attention_tc_kernel<false><<<grid, 192, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col, key_pad,
                                                            reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }

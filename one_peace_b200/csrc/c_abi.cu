@@ -49,11 +49,11 @@ int opb_attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad
                             static_cast<cudaStream_t>(stream));
 }
 
-int opb_attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int32_t* code_row,
+int opb_attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int32_t* code_row,
                          const int32_t* code_col, const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B,
                          int S, int H, int seg_split, void* stream) {
-  if (!qkv || !lut || !code_row || !code_col || !out) return OPB_ERR_INVALID;
-  return opb::attention_tc_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split,
+  if (!qkv || !lut || !lut_max || !code_row || !code_col || !out) return OPB_ERR_INVALID;
+  return opb::attention_tc_fwd(qkv, lut, lut_max, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split,
                                static_cast<cudaStream_t>(stream));
 }
 

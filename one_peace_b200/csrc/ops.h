@@ -7,7 +7,7 @@ namespace opb {
 
 int attention_fwd(const void* qkv, const float* bias, const uint8_t* key_pad, void* out, float* lse, float* ln_stats,
                   int B, int S, int H, int s_pad, long bias_bstride, cudaStream_t stream);
-int attention_tc_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
+int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int* code_row, const int* code_col,
                      const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
                      cudaStream_t stream);
 int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int H, cudaStream_t stream);

@@ -78,6 +78,7 @@ class RelPosBias:
 
     def __init__(self, dense=None, lut=None, code_row=None, code_col=None, seg_split=0):
         self.dense, self.lut, self.code_row, self.code_col, self.seg_split = dense, lut, code_row, code_col, seg_split
+        self.lut_max = None
 
 
 def build_segmented_lut(parts, device):
@@ -115,7 +116,10 @@ def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None, lse=None):
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
     if out is None:
         out = torch.empty(B * S, D, dtype=torch.bfloat16, device=qkv.device)
-    st = _lib.load().opb_attention_tc_fwd(qkv.data_ptr(), rp.lut.data_ptr(), rp.lut.shape[1], rp.code_row.data_ptr(),
+    if getattr(rp, "lut_max", None) is None:        # per-head bound of the bias (once per table build)
+        mx = rp.lut.amax(dim=1)
+        rp.lut_max = (mx.clamp_min(0.0) if int(getattr(rp, "seg_split", 0)) > 0 else mx).contiguous()
+    st = _lib.load().opb_attention_tc_fwd(qkv.data_ptr(), rp.lut.data_ptr(), rp.lut_max.data_ptr(), rp.lut.shape[1], rp.code_row.data_ptr(),
                                           rp.code_col.data_ptr(), _ptr(key_pad), out.data_ptr(), _ptr(lse), _ptr(ln_stats), B, S,
                                           H, int(getattr(rp, "seg_split", 0)), _stream())
     _lib.check(st, "opb_attention_tc_fwd")

@@ -71,7 +71,7 @@ class LutCache:
         if key not in self._c:
             b = bucket_tensor[:S, :S].detach().cpu().numpy()
             r = build_lut_index(b, codes_fn(S))
-            if r is not None and (r[0].size * 4 + S * 5) > 128 * 128 * 2:
-                r = None                      # would not fit the kernel's 32 KB table buffer
+            if r is not None and (r[0].size * 4 + S * 5 + 32) > 128 * 128:
+                r = None                      # would not fit the kernel's 16 KB table buffer (the dead Q tile)
             self._c[key] = None if r is None else tuple(torch.from_numpy(a).to(device) for a in r)
         return self._c[key]

@@ -25,3 +25,9 @@ t_old = timeit(lambda: K.attention(qkv, dense, None, B, S, H, out=out, ln_stats=
 o_old = out.clone()
 t_new = timeit(lambda: K.attention_tc(qkv, rp, None, B, S, H, out=out, ln_stats=part))
 print(f"mma.sync {t_old:.1f} us | tcgen05 {t_new:.1f} us | max diff {(out.float()-o_old.float()).abs().max().item():.3e}")
+if "timing" in os.environ.get("OPB_LIB_PATH", ""):
+    import ctypes
+    from one_peace_b200 import _lib
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    lib.opb_attn_timing_dump()
