@@ -63,10 +63,24 @@ def from_pretrained(model_name_or_path=None, model_type="one_peace_retrieval", d
 
 
 class OnePeaceHubInterface:
-    def __init__(self, model, device="cuda", text_tokenizer=None, image_transform=None, audio_loader=None):
+    def __init__(self, model, device="cuda", text_tokenizer=None, image_transform=None, audio_loader=None, cuda_graph=False):
+        """cuda_graph=True: every (modality, input shape) is captured once into a CUDA graph and replayed afterwards
+        (one_peace_b200/graphs.py) — the small-batch embedding API is launch-bound otherwise (212 launches per forward)."""
         self.model = model
         self.device = torch.device(device)
         self._tok, self._img, self._aud = text_tokenizer, image_transform, audio_loader
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
+
+    def _forward(self, encoder_type, **inputs):
+        if not self.cuda_graph:
+            return self.model(encoder_type=encoder_type, **inputs)
+        from ..graphs import GraphedForward
+        key = (encoder_type,) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(inputs.items()))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = GraphedForward(lambda **kw: self.model(encoder_type=encoder_type, **kw), inputs)
+        return g(**inputs)
 
     # -- pre-processing stays Python (hub_interface.py:134-210) --
     def process_text(self, text_list):
@@ -99,14 +113,13 @@ class OnePeaceHubInterface:
     # -- the accelerated path (hub_interface.py:212-222) --
     @torch.no_grad()
     def extract_text_features(self, src_tokens, out=None):
-        return self._finish(self.model(src_tokens=self._to_device(src_tokens), encoder_type="text"), out)
+        return self._finish(self._forward("text", src_tokens=self._to_device(src_tokens)), out)
 
     @torch.no_grad()
     def extract_image_features(self, src_images, out=None):
-        return self._finish(self.model(src_images=self._to_device(src_images), encoder_type="image"), out)
+        return self._finish(self._forward("image", src_images=self._to_device(src_images)), out)
 
     @torch.no_grad()
     def extract_audio_features(self, src_audios, audio_padding_masks, out=None):
-        return self._finish(self.model(src_audios=self._to_device(src_audios),
-                                       audio_padding_masks=self._to_device(audio_padding_masks),
-                                       encoder_type="audio"), out)
+        return self._finish(self._forward("audio", src_audios=self._to_device(src_audios),
+                                          audio_padding_masks=self._to_device(audio_padding_masks)), out)

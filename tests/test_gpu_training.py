@@ -127,3 +127,46 @@ def test_contrastive_step_backward_vs_oracle():
     # the InfoNCE gradient (logit_scale = 1/0.07) amplifies the forward's bf16 differences ~14x before they enter the
     # encoder backward, hence the wider band than in the linear-functional test above
     compare(model, want, min_cos=0.97, norm_tol=0.06, relpos=(0.94, 0.12))
+
+
+def test_graphed_train_step_equals_eager_and_tracks_weight_updates():
+    """one_peace_b200/graphs.py GraphedTrainStep: the captured criterion forward + backward gives the eager loss / gradients,
+    and after an (eager) optimizer step the NEXT replay sees the updated weights (kernel-ready packs are rebuilt inside the
+    graph) — checked against a second model trained eagerly with the same data."""
+    need_gpu()
+    from one_peace_b200.criterions import ImageTextRetrievalCriterion
+    from one_peace_b200.graphs import GraphedTrainStep
+    from one_peace_b200.optim import Adam
+    sd = synth.make_state_dict(**CFG, modalities=("text", "image"), seed=4)
+    tok, img, _, _ = synth.tiny_inputs(seed=4, n_text=4, n_img=4)
+    samples = []
+    for k in range(4):
+        g = torch.Generator().manual_seed(50 + k)
+        samples.append({"nsentences": 4, "net_input": {"src_tokens": torch.randint(4, 50264, tok.shape, generator=g).cuda(),
+                                                       "src_images": torch.randn(img.shape, generator=g).cuda()}})
+    runs = {}
+    for mode in ("eager", "graph"):
+        model = build_model(sd, "vl")
+        model.train()
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = Adam(params, lr=1e-3, betas=(0.9, 0.98), weight_decay=0.0)
+        crit = ImageTextRetrievalCriterion(None, label_smoothing=0.0)
+        losses, step = [], None
+        for k, sample in enumerate(samples):
+            if mode == "graph" and k == 1:                       # capture after the first optimizer step
+                step = GraphedTrainStep(model, crit, sample, params, warmup=0)
+            if step is not None:
+                loss, _, _ = step(sample)
+            else:
+                for p in params:
+                    p.grad = None
+                loss, _, _ = crit(model, sample)
+                loss.backward()
+            losses.append(loss.item())
+            opt.step()
+        runs[mode] = (losses, {n: p.detach().float().cpu().clone() for n, p in model.named_parameters()})
+    le, lg = runs["eager"][0], runs["graph"][0]
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg)), (le, lg)     # fp32 atomics order may differ run to run
+    worst = min(torch.nn.functional.cosine_similarity(runs["eager"][1][n].flatten(), runs["graph"][1][n].flatten(), dim=0).item()
+                for n in runs["eager"][1] if runs["eager"][1][n].numel() > 1)
+    assert worst > 0.9999, worst
