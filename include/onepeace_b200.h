@@ -393,6 +393,17 @@ int opb_relpos_bias_block(const float* table, const int64_t* bucket, int64_t ld_
 int opb_relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids,
                               int64_t ids_ld, int Bb, int n, int lo, float* dtable, int S, int s_pad, int H, void* stream);
 
+/*
+ * Fold a LayerNorm into the nn.Linear that follows it (the fused-LN GEMM chain; reference: the four LayerNorm -> Linear pairs
+ * of models/transformer/transformer_layer.py:185-219 and multihead_attention.py:103-124):
+ *   out_w[row(n), k] = bf16(W[n,k] * ln_weight[k]),  colsum[row(n)] = sum_k out_w[row(n), k],
+ *   bias_out[row(n)] = sum_k W[n,k] * ln_bias[k] + bias_in[n]
+ * W fp32 / bf16 [N, K] (dtype tag, row pitch ldw); ln_weight / ln_bias / bias_in fp32 or NULL (1 / 0 / 0).
+ * interleave 0: row(n) = n; 1 / 2: the wi_0 / wi_1 half of the GeGLU tile interleave, row(n) = (n / 128) * 256 [+ 128] + n % 128.
+ */
+int opb_ln_fold(const void* W, int w_dtype, int64_t ldw, const float* ln_weight, const float* ln_bias, const float* bias_in,
+                int N, int K, int interleave, void* out_w, int64_t ldo, float* colsum, float* bias_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

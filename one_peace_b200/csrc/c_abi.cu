@@ -349,4 +349,11 @@ int opb_relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, int64_t
                                     static_cast<cudaStream_t>(stream));
 }
 
+int opb_ln_fold(const void* W, int w_dtype, int64_t ldw, const float* ln_weight, const float* ln_bias, const float* bias_in,
+                int N, int K, int interleave, void* out_w, int64_t ldo, float* colsum, float* bias_out, void* stream) {
+  if (!W || !out_w || !colsum || !bias_out) return OPB_ERR_INVALID;
+  return opb::ln_fold(W, w_dtype, ldw, ln_weight, ln_bias, bias_in, N, K, interleave, out_w, ldo, colsum, bias_out,
+                      static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -114,6 +114,10 @@ int relpos_bias_block(const float* table, const int64_t* bucket, long ld_bucket,
 int relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, long ld_bucket, const int64_t* ids, long ids_ld, int Bb,
                           int n, int lo, float* dtable, int S, int s_pad, int H, cudaStream_t stream);
 
+// ---- parameter preprocessing for the fused-LayerNorm GEMM chain (pack.cu) ----
+int ln_fold(const void* W, int w_dtype, long ldw, const float* g, const float* beta, const float* bias_in, int N, int K,
+            int interleave, void* out_w, long ldo, float* colsum, float* bias_out, cudaStream_t stream);
+
 // ---- retrieval evaluation (recall.cu) ----
 int topk10_rows(const float* sim, long ld, int* idx, float* val, int R, int C, cudaStream_t stream);
 int recall_hits(const int* idx, const int64_t* cand_ids, const int64_t* row_ids, int R, int* hits3, cudaStream_t stream);

@@ -648,3 +648,15 @@ def relpos_bias_block_bwd(dbias, bucket, ids, n, lo, dtable, S, H):
     _lib.check(st, "opb_relpos_bias_block_bwd")
     _count()
     return dtable
+
+
+def ln_fold(weight, ln_w, ln_b, bias, out_w, colsum, bias_out, interleave=0):
+    """Folds LayerNorm(ln_w, ln_b) into the following Linear(weight, bias): writes the bf16 operand rows, their column sums and
+    the fused bias into (views of) out_w / colsum / bias_out.  weight fp32 / bf16 [N, K]; ln_w / ln_b / bias fp32 or None."""
+    _need_cuda(weight, out_w)
+    N, Kd = weight.shape
+    assert weight.stride(1) == 1 and out_w.dtype == torch.bfloat16 and out_w.stride(-1) == 1
+    st = _lib.load().opb_ln_fold(weight.data_ptr(), _dt(weight), weight.stride(0), _ptr(ln_w), _ptr(ln_b), _ptr(bias), N, Kd,
+                                 interleave, out_w.data_ptr(), out_w.stride(0), colsum.data_ptr(), bias_out.data_ptr(), _stream())
+    _lib.check(st, "opb_ln_fold")
+    _count()

@@ -100,15 +100,30 @@ class TransformerEncoderLayer(nn.Module):
         return self.self_attn.ln is not None and ffn_ok and self.attn_ln is None and self.self_attn.c_attn is None
 
     @staticmethod
-    def _fold(weight, ln_w, ln_b, bias):
-        """W [N,K] fp32, LN affine over K -> (bf16 W*diag(g), colsum of the bf16 matrix, bias' = W @ beta + b)."""
-        wf = weight.detach().float()
-        wg = (wf * ln_w.detach().float()[None, :]).to(torch.bfloat16).contiguous()
-        colsum = wg.float().sum(dim=1).contiguous()
-        d = wf @ ln_b.detach().float()
-        if bias is not None:
-            d = d + bias.detach().float()
-        return wg, colsum, d.contiguous()
+    def _fold(weights, ln, biases, interleave=False):
+        """Folds LayerNorm `ln` into the Linear layers `weights` ([N_i, K] each, stacked along N; `interleave`: the GeGLU tile
+        interleave of two weights) -> (bf16 W*diag(g) [sum N_i, K], colsum of the bf16 rows, bias' = W @ beta + b).
+        One `opb_ln_fold` launch per source weight (csrc/pack.cu): the packs are rebuilt after every optimizer step."""
+        dev = weights[0].device
+        N, Kd = sum(w.shape[0] for w in weights), weights[0].shape[1]
+        wg = torch.empty(N, Kd, dtype=torch.bfloat16, device=dev)
+        colsum = torch.empty(N, dtype=torch.float32, device=dev)
+        bias_out = torch.empty(N, dtype=torch.float32, device=dev)
+        g, beta = f32(ln.weight), f32(ln.bias)
+        off = 0
+        for i, (w, b) in enumerate(zip(weights, biases)):
+            wd = w.detach()
+            if wd.dtype not in (torch.float32, torch.bfloat16):
+                wd = wd.float()
+            wd = wd.contiguous()
+            bb = f32(b) if b is not None else None
+            if interleave:
+                K.ln_fold(wd, g, beta, bb, wg, colsum, bias_out, interleave=i + 1)
+            else:
+                n = w.shape[0]
+                K.ln_fold(wd, g, beta, bb, wg[off:off + n], colsum[off:off + n], bias_out[off:off + n])
+                off += n
+        return wg, colsum, bias_out
 
     def _fused_attn_pack(self):
         cache = self._cache.setdefault("_fused_attn", PackCache())
@@ -120,13 +135,11 @@ class TransformerEncoderLayer(nn.Module):
         def build():
             d = self.embed_dim
             dev = a.q_proj.weight.device
-            wqkv = torch.cat([a.q_proj.weight.detach().float(), a.k_proj.weight.detach().float(),
-                              a.v_proj.weight.detach().float()], 0)
-            bqkv = torch.cat([a.q_proj.bias.detach().float(), torch.zeros(d, device=dev), a.v_proj.bias.detach().float()])
-            w, c, dd = self._fold(wqkv, self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias, bqkv)
+            w, c, dd = self._fold([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], self.self_attn_layer_norm,
+                                  [a.q_proj.bias, None, a.v_proj.bias])
             qs = torch.ones(3 * d, device=dev)
             qs[:d] = a.scaling
-            wo, co, do = self._fold(a.out_proj.weight, a.ln.weight, a.ln.bias, a.out_proj.bias)
+            wo, co, do = self._fold([a.out_proj.weight], a.ln, [a.out_proj.bias])
             return dict(wqkv=w, cqkv=c, dqkv=dd, qscale=qs, wo=wo, co=co, do=do,
                         g1=f32(self.gamma_1) if self.gamma_1 is not None else None)
         return cache.get(ps, build)
@@ -139,15 +152,9 @@ class TransformerEncoderLayer(nn.Module):
               ln2.bias] + ([self.gamma_2] if self.gamma_2 is not None else [])
 
         def build():
-            g2 = ln2.weight.detach().float()
-            w0 = ffn[0].wi_0.weight.detach().float()
-            w1 = ffn[0].wi_1.weight.detach().float()
-            w01 = interleave_geglu(w0 * g2[None, :], w1 * g2[None, :])
-            c01 = w01.float().sum(dim=1).contiguous()
-            b2 = ln2.bias.detach().float()
-            F_ = w0.shape[0]
-            d01 = torch.stack([(w0 @ b2).view(F_ // 128, 128), (w1 @ b2).view(F_ // 128, 128)], dim=1).reshape(2 * F_).contiguous()
-            w2, c2, d2 = self._fold(ffn[3].weight, lnf.weight, lnf.bias, ffn[3].bias)
+            assert ffn[0].wi_0.weight.shape[0] % 128 == 0, "ffn_embed_dim must be a multiple of 128"
+            w01, c01, d01 = self._fold([ffn[0].wi_0.weight, ffn[0].wi_1.weight], ln2, [None, None], interleave=True)
+            w2, c2, d2 = self._fold([ffn[3].weight], lnf, [ffn[3].bias])
             return dict(w01=w01, c01=c01, d01=d01, w2=w2, c2=c2, d2=d2, lnf_eps=lnf.eps,
                         g2=f32(self.gamma_2) if self.gamma_2 is not None else None)
         return cache.get(ps, build)
