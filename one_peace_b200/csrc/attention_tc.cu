@@ -28,6 +28,8 @@
 #include "common.cuh"
 #include "ops.h"
 
+#include <stdlib.h>
+
 namespace opb {
 
 constexpr int kTcQ = 128;        // query rows per CTA
@@ -47,7 +49,7 @@ struct TcBars {
 
 OPB_DEVICE float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));     // not volatile: the 16 exponentials of a sub-chunk must be free to issue back to back
   return y;
 }
 OPB_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -96,8 +98,10 @@ __device__ unsigned int g_attn_n;
 #define OPB_T(i) do {} while (0)
 #endif
 
-template <bool HAS_PAD>
-__global__ void __launch_bounds__(192, 2)
+constexpr int kTcTableBytes = 13 * 1024;   // LUT + codes (+ pad mask) inside the Q tile; the remaining 3 KB: row-thread exchange
+
+template <bool HAS_PAD, int HALVES>
+__global__ void __launch_bounds__(64 + 128 * HALVES, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __restrict__ lut, const float* __restrict__ lut_max, int lut_len,
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
@@ -133,7 +137,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     mbar_init(&bars->lut, 1);
     for (int i = 0; i < kTcMaxBlocks; ++i) {
       mbar_init(&bars->s[i], 1);
-      mbar_init(&bars->p[i], 4);
+      mbar_init(&bars->p[i], 4 * HALVES);
       mbar_init(&bars->pv[i], 1);
     }
     fence_barrier_init();
@@ -193,24 +197,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     }
   } else {
     // ===================== row threads =====================
-    const int qw = warp & 3;                                 // TMEM lane quarter
+    // HALVES threads per query row (the HALVES warps that share a TMEM lane quarter); thread `half` owns the 16-key
+    // sub-chunks t with t % HALVES == half.  HALVES = 2 doubles the soft-max warps per SM (16): every pipe of this kernel
+    // runs below 35 % (ncu, profiles/r02_ncu_layer.summary.txt) — it is bound by the dependent ld -> gather -> ex2 -> store
+    // chain with too few warps to interleave.
+    constexpr int kRowThreads = 128 * HALVES;
+    const int qw = warp & 3;                                 // TMEM lane quarter (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;
     const int r = qw * 32 + lane;                            // row inside the tile
     const int qrow = q0 + r;
     const bool row_valid = qrow < S;
     const bool warp_valid = (q0 + qw * 32) < S;              // warp-uniform
-    const int tid4 = threadIdx.x - 64;                       // 0..127
-    // bias tables: lut [lut_len] | code_col [S padded to 4] (| key_pad [S] bytes).  They land in the P buffer (bulk copy
-    // at kernel start) and are moved into the Q tile once the last S = Q K^T has completed (Q is dead then), because phase B
-    // gathers from them while it fills the P buffer.
+    const int tid4 = threadIdx.x - 64;                       // 0 .. kRowThreads - 1
+    // bias tables: lut [lut_len] | code_col [S padded to 4] (| key_pad bytes).  They land in the P buffer (bulk copy at
+    // kernel start) and are moved into the Q tile once the last S = Q K^T has completed (Q is dead then), because phase B
+    // gathers from them while it fills the P buffer.  The last 3 KB of the Q tile are the exchange area of a row's threads.
     const int tbl_words = lut_len + ((S + 3) & ~3);
     const int pad_bytes = HAS_PAD ? ((S + 31) & ~31) : 0;
     const int tbl_bytes = (tbl_words * 4 + pad_bytes + 15) & ~15;
     const float* s_lut = reinterpret_cast<const float*>(sQ);
     const int* s_ccol = reinterpret_cast<const int*>(sQ) + lut_len;
-    const uint8_t* s_pad_w = sQ + static_cast<long>(tbl_words) * 4;    // key-padding bytes, zero beyond S up to the 32-key chunk end
+    const uint8_t* s_pad_w = sQ + static_cast<long>(tbl_words) * 4;    // key-padding bytes, zero beyond S up to a 32-key boundary
+    float* xch = reinterpret_cast<float*>(sQ + kTcTableBytes);         // [max | sum][half][row]
+    float2* xstat = reinterpret_cast<float2*>(sQ + kTcTableBytes + 4 * kTcQ * 4);
     if constexpr (HAS_PAD) {
       uint8_t* pad_in = sP + static_cast<long>(tbl_words) * 4;
-      for (int i = tid4; i < pad_bytes; i += 128) pad_in[i] = i < S ? key_pad[static_cast<long>(b) * S + i] : 0;
+      for (int i = tid4; i < pad_bytes; i += kRowThreads) pad_in[i] = i < S ? key_pad[static_cast<long>(b) * S + i] : 0;
     }
     const int crow = code_row[row_valid ? qrow : 0];
     // concatenated sequences ('vl' / 'al', transformer_encoder.py:148-158): the relative-position bias is block-diagonal —
@@ -219,14 +231,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     const int seg_hi = (seg_split > 0 && qrow < seg_split) ? seg_split : S;
     OPB_T(1);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
+    const int nsub = nkb * (kTcK / 16);
 
     // ---- phase A: an upper bound of the row maximum, WITHOUT touching the bias ----
     // soft-max is shift invariant, so any m >= max_j (s_ij + bias_ij) that is not absurdly loose gives the same result: bf16
     // P and the fp32 row sum / O accumulators keep full relative precision for exp(x - m) down to ~1e-38.  We use
     //     m = max_j s_ij  +  max_l lut[h][l]        (slack <= spread of the head's bias table, a few units)
-    // which needs only tcgen05.ld + a max tree per 32-key chunk: no LUT gather, no add, and no tcgen05.st of biased scores
-    // back into TMEM (round 1 did all three here and again loaded the scores in phase B: 3.4 + 3.2 us of a 10.2 us CTA).
-    // Padded keys and the neighbouring sample's rows inside the last block may enter the bound; they only loosen it.
+    // which needs only tcgen05.ld + a max tree: no LUT gather, no add, and no tcgen05.st of biased scores back into TMEM
+    // (round 1 did all three here and loaded the scores again in phase B).  Padded keys and the neighbouring sample's rows
+    // inside the last block may enter the bound; they only loosen it.
     float m = -INFINITY;
     for (int kb = 0; kb < nkb; ++kb) {
       mbar_wait(&bars->s[kb], 0);
@@ -234,35 +247,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       if (kb == 0) OPB_T(2);
       if (warp_valid) {
         const int kvalid = min(kTcK, S - kb * kTcK);
-        for (int c = 0; c < kvalid; c += 32) {
-          uint32_t v[32];
+        for (int c = half * 16; c < kvalid; c += 16 * HALVES) {
+          uint32_t v[16];
           __syncwarp();
-          tmem_ld32(lane_base + kb * kTcK + c, v);
+          tmem_ld16(lane_base + kb * kTcK + c, v);
           tmem_ld_wait();
-          float t8[8];
+          float t4[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            t8[j] = fmaxf(fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 8])), fmaxf(__uint_as_float(v[j + 16]), __uint_as_float(v[j + 24])));
-          m = fmaxf(m, fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7]))));
+          for (int j = 0; j < 4; ++j)
+            t4[j] = fmaxf(fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 4])), fmaxf(__uint_as_float(v[j + 8]), __uint_as_float(v[j + 12])));
+          m = fmaxf(m, fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3])));
         }
       }
     }
-    m += lut_max[h];
-    // every S_kb has completed: Q is dead.  Move the tables P buffer -> Q tile (16-byte pieces), then the P buffer is free.
+    // every S_kb has completed: Q is dead.  Exchange the partial maxima, move the tables P buffer -> Q tile (16-byte
+    // pieces); after the barrier the P buffer is free.
+    if constexpr (HALVES > 1) xch[half * kTcQ + r] = m;
     mbar_wait(&bars->lut, 0);
-    if constexpr (HAS_PAD) named_bar_sync(1, 128);       // pad bytes written by other threads
-    for (int i = tid4 * 16; i < tbl_bytes; i += 128 * 16) sts128u(sQ + i, *reinterpret_cast<const uint4*>(sP + i));
-    named_bar_sync(1, 128);
+    if constexpr (HAS_PAD) named_bar_sync(1, kRowThreads);       // pad bytes written by other threads
+    for (int i = tid4 * 16; i < tbl_bytes; i += kRowThreads * 16) sts128u(sQ + i, *reinterpret_cast<const uint4*>(sP + i));
+    named_bar_sync(1, kRowThreads);
+    if constexpr (HALVES > 1) m = fmaxf(m, xch[(half ^ 1) * kTcQ + r]);
+    m += lut_max[h];
     OPB_T(3);
 
-    // ---- phase B: bias gather, exp, row sum, P -> shared memory ----
-    // Software-pipelined over 16-key sub-chunks: while sub-chunk t is exponentiated / packed / stored, the TMEM load and the
-    // LUT gathers of sub-chunk t + 1 are already in flight (the inline-asm tcgen05 statements are compiler barriers, so the
-    // overlap has to be written out; without it the per-chunk chain ld -> gather -> ex2 -> store was fully exposed with only
-    // two soft-max warps per scheduler: 4.9 us of a 9.5 us CTA).
+    // ---- phase B: bias gather, exp, row sum, P -> shared memory (16-key sub-chunks) ----
     const float mb = m * 1.4426950408889634f;
     float l0 = 0.f, l1 = 0.f;
-    const int nsub = nkb * (kTcK / 16);
     auto prefetch = [&](int t, uint32_t (&v)[16], float (&add)[16]) {
       const int key0 = t * 16;                         // TMEM column == key index (128-column slot per key block)
       __syncwarp();
@@ -322,67 +333,103 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       sts128u(atom + sw128_off(r, ((c & 63) >> 3)), make_uint4(pk[0], pk[1], pk[2], pk[3]));
       sts128u(atom + sw128_off(r, ((c & 63) >> 3) + 1), make_uint4(pk[4], pk[5], pk[6], pk[7]));
     };
-    uint32_t vA[16], vB[16];
-    float aA[16], aB[16];
     const bool any = warp_valid;
-    if (any) prefetch(0, vA, aA);
-    for (int kb = 0; kb < nkb; ++kb) {
-      if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);     // previous P consumed by the tensor core
+    if constexpr (HALVES == 1) {
+      // one thread per row: software-pipelined (the loads of sub-chunk t + 1 fly while t is exponentiated and stored)
+      uint32_t vA[16], vB[16];
+      float aA[16], aB[16];
+      if (any) prefetch(0, vA, aA);
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);     // previous P consumed by the tensor core
 #pragma unroll 1
-      for (int u = 0; u < kTcK / 16; u += 2) {
-        const int t = kb * (kTcK / 16) + u;
-        const bool liveA = any && t * 16 < S, liveB = any && (t + 1) * 16 < S, liveC = any && (t + 2) * 16 < S && t + 2 < nsub;
-        if (liveA) tmem_ld_wait();
-        if (liveB) prefetch(t + 1, vB, aB);
-        finish(t, vA, aA, liveA);
-        if (liveB) tmem_ld_wait();
-        if (liveC) prefetch(t + 2, vA, aA);
-        finish(t + 1, vB, aB, liveB);
+        for (int u = 0; u < kTcK / 16; u += 2) {
+          const int t = kb * (kTcK / 16) + u;
+          const bool liveA = any && t * 16 < S, liveB = any && (t + 1) * 16 < S, liveC = any && (t + 2) * 16 < S && t + 2 < nsub;
+          if (liveA) tmem_ld_wait();
+          if (liveB) prefetch(t + 1, vB, aB);
+          finish(t, vA, aA, liveA);
+          if (liveB) tmem_ld_wait();
+          if (liveC) prefetch(t + 2, vA, aA);
+          finish(t + 1, vB, aB, liveB);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p[kb]);
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p[kb]);
+    } else {
+      // two threads per row: alternate sub-chunks, latency hidden by the 16 soft-max warps of the SM
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (kb > 0) mbar_wait(&bars->pv[kb - 1], 0);
+#pragma unroll 1
+        for (int u = half; u < kTcK / 16; u += HALVES) {
+          const int t = kb * (kTcK / 16) + u;
+          const bool live = any && t * 16 < S;
+          uint32_t v[16];
+          float add[16];
+          if (live) {
+            prefetch(t, v, add);
+            tmem_ld_wait();
+          }
+          finish(t, v, add, live);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p[kb]);
+      }
     }
-    const float l = l0 + l1;
+    float l = l0 + l1;
 
-    // ---- epilogue: O / l -> bf16 rows ----
+    // ---- epilogue: O / l -> bf16 rows; with two threads per row each normalises 32 of the 64 output columns ----
     OPB_T(4);
+    if constexpr (HALVES > 1) xch[(2 + half) * kTcQ + r] = l;
     mbar_wait(&bars->pv[nkb - 1], 0);
     tc_fence_after();
     OPB_T(5);
+    constexpr int kOutCols = kTcD / HALVES;
+    uint32_t o[kOutCols];
     if (warp_valid) {
-      uint32_t o0[32], o1[32];
       __syncwarp();
-      tmem_ld32(lane_base, o0);
-      tmem_ld32(lane_base + 32, o1);
+      if constexpr (HALVES == 1) {
+        uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
+        uint32_t (&o1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
+        tmem_ld32(lane_base, o0);
+        tmem_ld32(lane_base + 32, o1);
+      } else {
+        uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
+        tmem_ld32(lane_base + half * 32, o0);
+      }
       tmem_ld_wait();
-      if (row_valid) {
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        float ssum = 0.f, ssq = 0.f;
-        __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD;
+    }
+    if constexpr (HALVES > 1) {
+      named_bar_sync(2, kRowThreads);
+      l += xch[(2 + (half ^ 1)) * kTcQ + r];
+    }
+    float ssum = 0.f, ssq = 0.f;
+    if (warp_valid && row_valid) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* op = out + (static_cast<long>(b) * S + qrow) * D + h * kTcD + half * kOutCols;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float y[8];
+      for (int k = 0; k < kOutCols / 8; ++k) {
+        float y[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o0[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
-          *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                             pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float y[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o1[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
-          *reinterpret_cast<uint4*>(op + 32 + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                                  pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        }
-        // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
-        if (lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
-        if (ln_stats != nullptr) {
-          const long rows_total = static_cast<long>(B) * S;
-          *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
-        }
+        for (int e = 0; e < 8; ++e) { y[e] = __uint_as_float(o[8 * k + e]) * inv; ssum += y[e]; ssq += y[e] * y[e]; }
+        *reinterpret_cast<uint4*>(op + 8 * k) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                           pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+      // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
+      if (half == 0 && lse != nullptr) lse[(static_cast<long>(b) * H + h) * S + qrow] = m + __logf(l);
+    }
+    if (ln_stats != nullptr) {
+      if constexpr (HALVES > 1) {
+        if (half == 1) xstat[r] = make_float2(ssum, ssq);
+        named_bar_sync(3, kRowThreads);
+        if (half == 0) { const float2 q2 = xstat[r]; ssum += q2.x; ssq += q2.y; }
+      }
+      if (half == 0 && warp_valid && row_valid) {
+        const long rows_total = static_cast<long>(B) * S;
+        *reinterpret_cast<float2*>(ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
       }
     }
   }
@@ -439,29 +486,26 @@ int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, in
   if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col) & 15) != 0)
     return OPB_ERR_INVALID;     // bulk-copied: 16-byte granularity (code_col must hold (S + 3) & ~3 entries)
   const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((S + 3) & ~3) * 4 + S + 48;
-  if (table_bytes > kTcQ * 128) return OPB_ERR_UNSUPPORTED;      // the tables move into the 16 KB Q tile for phase B
+  if (table_bytes > kTcTableBytes) return OPB_ERR_UNSUPPORTED;   // the tables move into the (dead) 16 KB Q tile for phase B
   const int D = H * kTcD;
   CUtensorMap tm;
   int rc = make_tmap_bf16_2d(&tm, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, kTcQ);
   if (rc != OPB_OK) return rc;
   const size_t smem = kTcQ * 128 + 2ull * nkb * kTcK * 128 + kTcQ * kTcK * 2 + sizeof(TcBars);
   const uint32_t tmem_cols = nkb == 1 ? 128 : (nkb == 2 ? 256 : 512);
-  static size_t configured[2] = {0, 0};
-  const int v = key_pad != nullptr ? 1 : 0;
+  static const char* env_h = getenv("OPB_ATTN_ROW_THREADS");          // 1 or 2 threads per query row (A/B switch), default 2
+  const int halves = (env_h != nullptr && env_h[0] == '1') ? 1 : 2;
+  static size_t configured[4] = {0, 0, 0, 0};
+  const int v = (key_pad != nullptr ? 1 : 0) + 2 * (halves - 1);
+  auto kern = v == 0 ? attention_tc_kernel<false, 1> : (v == 1 ? attention_tc_kernel<true, 1> : (v == 2 ? attention_tc_kernel<false, 2> : attention_tc_kernel<true, 2>));
   if (smem > configured[v]) {
-    cudaError_t e = v ? cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                      : cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return OPB_ERR_CUDA;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return OPB_ERR_CUDA;
     configured[v] = smem;
   }
   const int q_tiles = (S + kTcQ - 1) / kTcQ;
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
-  if (v)
-    attention_tc_kernel<true><<<grid, 192, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col, key_pad,
-                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
-  else
-    attention_tc_kernel<false><<<grid, 192, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col, key_pad,
-                                                           reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
+  kern<<<grid, 64 + 128 * halves, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col, key_pad,
+                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

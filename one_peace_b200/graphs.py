@@ -88,9 +88,15 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             loss, self.sample_size, log = criterion(model, self.static_sample)
-            loss.backward()
+            # torch.autograd.grad instead of loss.backward(): no AccumulateGrad nodes run inside the capture (they are bound to
+            # the stream the parameters were first used on — the legacy stream after eager steps — and the engine's cross-stream
+            # hand-off to it is illegal while capturing)
+            grads = torch.autograd.grad(loss, self.params, allow_unused=True)
         self.static_loss = loss.detach()
         self.static_log = log
+        self.static_grads = grads
+        for p, g in zip(self.params, grads):
+            p.grad = g
 
     def _invalidate_packs(self):
         """Every cached pack must be rebuilt inside the captured region so that replays track the optimizer's updates."""
@@ -127,4 +133,7 @@ class GraphedTrainStep:
     def __call__(self, sample):
         self._copy_sample(self.static_sample, sample)
         self.graph.replay()
+        for p, g in zip(self.params, self.static_grads):      # the optimizer may have dropped them (zero_grad(set_to_none))
+            if p.grad is not g:
+                p.grad = g
         return self.static_loss, self.sample_size, self.static_log

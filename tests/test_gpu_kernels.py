@@ -228,7 +228,15 @@ def test_gemm_fused_layernorm_and_stats(K, cg):
     K.row_stats_cast(x, xb, mu, rstd)
     torch.testing.assert_close(mu, x.mean(1), atol=1e-5, rtol=1e-5)
     torch.testing.assert_close(rstd, (x.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-5, rtol=1e-4)
-    wg, colsum, dd = L._fold(W, lw, lb, b)
+    class _LN:      # stand-in for nn.LayerNorm: the fold reads .weight / .bias
+        def __init__(self, w, b_):
+            self.weight, self.bias = w, b_
+    wg, colsum, dd = L._fold([W], _LN(lw, lb), [b])
+    # the one-pass fold kernel (csrc/pack.cu) equals the torch formulation
+    wg_t = (W * lw[None, :]).to(torch.bfloat16)
+    assert torch.equal(wg, wg_t)
+    torch.testing.assert_close(colsum, wg_t.float().sum(1), atol=1e-4, rtol=1e-5)
+    torch.testing.assert_close(dd, W @ lb + b, atol=1e-4, rtol=1e-5)
     out = torch.empty(M, N, dtype=torch.float32, device="cuda")
     K.gemm_ln(xb, wg, K.EPI_STORE_F32, out, ln_mu=mu, ln_rstd=rstd, ln_colsum=colsum, bias=dd, cta_group=cg)
     want = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (d,), lw, lb), W, b)
@@ -252,7 +260,7 @@ def test_gemm_fused_layernorm_and_stats(K, cg):
     lw2 = 1 + 0.2 * torch.randn(N, device="cuda", generator=g)
     lb2 = 0.1 * torch.randn(N, device="cuda", generator=g)
     b2 = torch.randn(640, device="cuda", generator=g)
-    wg2, cs2, dd2 = L._fold(W2, lw2, lb2, b2)
+    wg2, cs2, dd2 = L._fold([W2], _LN(lw2, lb2), [b2])
     want2 = torch.nn.functional.linear(torch.nn.functional.layer_norm(yb.float(), (N,), lw2, lb2), W2, b2)
     for epi, dt in ((K.EPI_STORE_F32, torch.float32), (K.EPI_STORE_BF16, torch.bfloat16)):
         o_arr = torch.empty(M, 640, dtype=dt, device="cuda")
