@@ -250,7 +250,8 @@ int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, v
  *   opb_infonce_rows      : row_lse / row_loss (label-smoothed NLL per row) / row_argmax, all [b]
  *   opb_infonce_reduce    : out3 = {(mean(loss_a) + mean(loss_b)) / 2, #correct a->b, #correct b->a}
  *   opb_infonce_grad      : grad_a fp32 [b,d] = d(loss)/d(a_local) (local rows only; no gradient to b_all, :30-38);
- *                           bT_all bf16 [d,n] = b_all transposed; g_ws bf16 [b,n] scratch; ws_gz [ceil(n/256), b]
+ *                           bT_all bf16 [d,n] = b_all transposed, or NULL: b_all is then read in place as the MN-major operand
+ *                           of the G . B_all product (no transposed copy); g_ws bf16 [b,n] scratch; ws_gz [ceil(n/256), b]
  *   opb_infonce_dscale    : out[0] = d(loss)/d(logit_scale) from the two directions' ws_gz
  */
 int64_t opb_infonce_ws_floats(int b, int n);
@@ -392,6 +393,16 @@ int opb_relpos_bias_block(const float* table, const int64_t* bucket, int64_t ld_
                           int Bb, int n, int lo, float* bias, int S, int s_pad, int H, void* stream);
 int opb_relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, int64_t ld_bucket, const int64_t* ids,
                               int64_t ids_ld, int Bb, int n, int lo, float* dtable, int S, int s_pad, int H, void* stream);
+
+/*
+ * GEMM with MN-major operands: out[M, N] = A B^T (+ bias[n]) where A is given as [K, M] row-major when a_mn != 0 (else the usual
+ * [M, K]) and B as [K, N] row-major when b_mn != 0 (else [N, K]).  Contractions over the ROWS of activation matrices without a
+ * transposed copy: every dW = dY^T X of the backward pass (torch autograd of the nn.Linear layers of
+ * transformer_layer.py / multihead_attention.py) is opb_gemm_bf16_t(dY, ldy, 1, X, ldx, 1, N_out, K_in, rows, ...); the
+ * InfoNCE gradient G . B_all (image_text_retrieval_loss.py:95-96) uses b_mn = 1.  epilogue: OPB_EPI_STORE_BF16 / _F32.
+ */
+int opb_gemm_bf16_t(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K, int epilogue,
+                    void* out, int64_t ldo, const float* bias, int cta_group, void* stream);
 
 /*
  * Fold a LayerNorm into the nn.Linear that follows it (the fused-LN GEMM chain; reference: the four LayerNorm -> Linear pairs

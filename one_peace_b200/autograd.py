@@ -45,12 +45,20 @@ def _tr(x):
     return K.transpose_bf16(xp)
 
 
+_DW_MN = __import__("os").environ.get("OPB_DW_MN", "1") != "0"      # 0: transposed copies + K-major GEMM (round-1 path, for A/B)
+
+
 def _dw(dy, x, dtype):
-    """dW [N, Kw] = dy[M, N]^T x[M, Kw]  (fp32 accumulate; stored in the parameter's dtype)."""
-    dyT, xT = _tr(dy), _tr(x)
+    """dW [N, Kw] = dy[M, N]^T x[M, Kw]  (fp32 accumulate; stored in the parameter's dtype).  A reduction over the M rows:
+    both operands are MN-major for the tensor cores and are read in place (opb_gemm_bf16_t); no transposed copies."""
     out = torch.empty(dy.shape[1], x.shape[1], dtype=torch.float32 if dtype == torch.float32 else torch.bfloat16,
                       device=dy.device)
-    K.gemm(dyT, xT, K.EPI_STORE_F32 if out.dtype == torch.float32 else K.EPI_STORE_BF16, out)
+    epi = K.EPI_STORE_F32 if out.dtype == torch.float32 else K.EPI_STORE_BF16
+    if _DW_MN and dy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0 and dy.stride(0) % 8 == 0 and x.stride(0) % 8 == 0 \
+            and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0:
+        K.gemm_t(dy, x, epi, out, a_mn=True, b_mn=True)
+    else:
+        K.gemm(_tr(dy), _tr(x), epi, out)
     return out if out.dtype == dtype else out.to(dtype)
 
 

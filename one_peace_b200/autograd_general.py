@@ -416,7 +416,7 @@ class DclLossFn(torch.autograd.Function):
         zeros = torch.zeros_like(row_loss)
         out = K.infonce_reduce(row_loss, zeros, am, am, 0)                               # out[0] = mean(row_loss) / 2
         if student.requires_grad:
-            grad_n, _ = K.infonce_grad(a3, b3, K.transpose_bf16(b3, cols=d), sc, lse, 0, eps, n_valid=n_t, coef=1.0 / n_m)
+            grad_n, _ = K.infonce_grad(a3, b3, None, sc, lse, 0, eps, n_valid=n_t, coef=1.0 / n_m, d=d)
             dx16, dx32 = K.l2_normalize_bwd(s_rows, grad_n, want_f32=True)
             ctx.save_for_backward(dx32, stu_idx)
         ctx.meta = (student.shape, student.dtype)

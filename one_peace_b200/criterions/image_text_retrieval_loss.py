@@ -49,8 +49,8 @@ class _InfoNCE(torch.autograd.Function):
         lse_b, loss_b, am_b = K.infonce_rows(b3, a_all3, s, off, eps, n_valid=nv)
         out = K.infonce_reduce(loss_a, loss_b, am_a, am_b, off)
         if a_local.requires_grad or b_local.requires_grad or scale.requires_grad:
-            ga, ws_a = K.infonce_grad(a3, b_all3, K.transpose_bf16(b_all3, cols=d), s, lse_a, off, eps, n_valid=nv)
-            gb, ws_b = K.infonce_grad(b3, a_all3, K.transpose_bf16(a_all3, cols=d), s, lse_b, off, eps, n_valid=nv)
+            ga, ws_a = K.infonce_grad(a3, b_all3, None, s, lse_a, off, eps, n_valid=nv, d=d)      # G . B_all reads B_all MN-major
+            gb, ws_b = K.infonce_grad(b3, a_all3, None, s, lse_b, off, eps, n_valid=nv, d=d)
             dlogit = K.infonce_dscale(ws_a, ws_b, bsz, n)        # d loss / d log(scale)
             ctx.save_for_backward(ga, gb, dlogit, s)
         ctx.dtypes = (a_local.dtype, b_local.dtype, scale.dtype)

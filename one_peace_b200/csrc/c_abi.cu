@@ -197,7 +197,7 @@ int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all,
                      const float* row_lse, int b, int n, int d, int k_logits, int target_offset,
                      float label_smoothing, void* g_ws, float* ws_gz, float* grad_a, int n_valid, float coef,
                      void* stream) {
-  if (!a_local || !b_all || !bT_all || !scale || !row_lse || !g_ws || !ws_gz || !grad_a) return OPB_ERR_INVALID;
+  if (!a_local || !b_all || !scale || !row_lse || !g_ws || !ws_gz || !grad_a) return OPB_ERR_INVALID;
   return opb::infonce_grad(a_local, b_all, bT_all, scale, row_lse, b, n, d, k_logits, target_offset, label_smoothing,
                            g_ws, ws_gz, grad_a, n_valid, coef, static_cast<cudaStream_t>(stream));
 }
@@ -347,6 +347,17 @@ int opb_relpos_bias_block_bwd(const float* dbias, const int64_t* bucket, int64_t
   if (!dbias || !bucket || !dtable) return OPB_ERR_INVALID;
   return opb::relpos_bias_block_bwd(dbias, bucket, ld_bucket, ids, ids_ld, Bb, n, lo, dtable, S, s_pad, H,
                                     static_cast<cudaStream_t>(stream));
+}
+
+int opb_gemm_bf16_t(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K, int epilogue,
+                    void* out, int64_t ldo, const float* bias, int cta_group, void* stream) {
+  if (!A || !B || !out) return OPB_ERR_INVALID;
+  opb::GemmEpilogue ep;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.bias = bias;
+  return opb::gemm_bf16_t(A, static_cast<int>(lda), a_mn, B, static_cast<int>(ldb), b_mn, M, N, K, epilogue, ep, cta_group,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int opb_ln_fold(const void* W, int w_dtype, int64_t ldw, const float* ln_weight, const float* ln_bias, const float* bias_in,

@@ -70,6 +70,11 @@ struct GemmEpilogue {
 int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epi, const GemmEpilogue& ep,
               int cta_group, cudaStream_t stream);
 
+// Same with MN-major operands: a_mn != 0 -> A is given as [K, M] row-major (C = A^T-stored^T ...), b_mn != 0 -> B as [K, N]
+// row-major.  dW = dY^T X is gemm_bf16_t(dY, ldy, 1, X, ldx, 1, N_out, K_in, rows, ...): no transposed copies.
+int gemm_bf16_t(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int epi,
+                const GemmEpilogue& ep, int cta_group, cudaStream_t stream);
+
 // Grouped "sliding window" GEMM = grouped Conv1d over channel-last activations:
 //   out[r, g*n_per_group + n] = epilogue( sum_{j < taps} sum_{c < c_pad} X[(r + j), g, c] * W[g*n_per_group + n, j*c_pad + c] )
 // X is bf16 [rows + taps - 1, groups, c_pad] (c_pad a multiple of 64), W is bf16 [groups*n_per_group, taps*c_pad].

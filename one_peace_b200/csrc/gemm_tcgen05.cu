@@ -91,7 +91,25 @@ struct GemmGeom {
   int tail_pieces;      // 0 = off
   int kb_per_piece;
   float* tail_ws;
+  // MN-major operands (C = A^T-stored x B^T-stored): the operand is given as [K rows, MN cols] row-major — a contraction over
+  // the ROWS of an activation matrix (dW = dY^T X, transformer backward) or a gathered embedding matrix used as B_all^T
+  // (InfoNCE gradient).  TMA then stages [64 k-rows][64 MN elements = 128 B] boxes (one per 64-wide MN chunk, 8 KB apart)
+  // and the UMMA descriptors / instruction descriptor select the MN-major canonical layout: no transpose kernel.
+  int a_mn;
+  int b_mn;
 };
+
+// MN-major bf16 operand, 128-byte swizzle: atoms of 64 MN elements x 8 k-rows (1024 B); k-groups SBO = 1024 B apart, 64-wide MN
+// chunks LBO = chunk_bytes apart (CUTLASS make_umma_desc<Major::MN>: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+OPB_DEVICE uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(chunk_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 struct SmemBars {
   uint64_t full[8];
@@ -222,12 +240,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           uint8_t* sb = sa + Cfg::kABytes;
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(&full_bar0[stage], Cfg::kStageBytes);
-            tma_load_3d(&tm_a, &full_bar0[stage], sa, a_c0 + kin * kBlockK, tap, a_row);
-            tma_load_2d(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
+            if (geo.a_mn) {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 64; ++i) tma_load_2d(&tm_a, &full_bar0[stage], sa + i * 8192, a_row + 64 * i, kb * kBlockK);
+            } else {
+              tma_load_3d(&tm_a, &full_bar0[stage], sa, a_c0 + kin * kBlockK, tap, a_row);
+            }
+            if (geo.b_mn) {
+#pragma unroll
+              for (int i = 0; i < Cfg::kBRows / 64; ++i) tma_load_2d(&tm_b, &full_bar0[stage], sb + i * 8192, b_row + 64 * i, kb * kBlockK);
+            } else {
+              tma_load_2d(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
+            }
           } else {
             if (is_leader) mbar_arrive_expect_tx(&full_bar0[stage], Cfg::kStageBytes * 2);
-            tma_load_3d_2sm(&tm_a, &full_bar0[stage], sa, a_c0 + kin * kBlockK, tap, a_row);
-            tma_load_2d_2sm(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
+            if (geo.a_mn) {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 64; ++i) tma_load_2d_2sm(&tm_a, &full_bar0[stage], sa + i * 8192, a_row + 64 * i, kb * kBlockK);
+            } else {
+              tma_load_3d_2sm(&tm_a, &full_bar0[stage], sa, a_c0 + kin * kBlockK, tap, a_row);
+            }
+            if (geo.b_mn) {
+#pragma unroll
+              for (int i = 0; i < Cfg::kBRows / 64; ++i) tma_load_2d_2sm(&tm_b, &full_bar0[stage], sb + i * 8192, b_row + 64 * i, kb * kBlockK);
+            } else {
+              tma_load_2d_2sm(&tm_b, &full_bar0[stage], sb, kb * kBlockK, b_row);
+            }
           }
           if (++kin == geo.kb_inner) { kin = 0; ++tap; }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -237,7 +275,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (is_leader && lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM * CG, geo.n_umma);
+      const uint32_t idesc = make_idesc_bf16(kBlockM * CG, geo.n_umma) | (geo.a_mn ? (1u << 15) : 0u) | (geo.b_mn ? (1u << 16) : 0u);
+      // descriptor advance per 16-deep MMA: 32 B inside the swizzle row (K-major) or two 8-row k-groups = 2048 B (MN-major)
+      const uint64_t step_a = geo.a_mn ? (2048 >> 4) : 2, step_b = geo.b_mn ? (2048 >> 4) : 2;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -257,12 +297,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_sw128_kmajor_desc(sa);
-          const uint64_t db = make_sw128_kmajor_desc(sb);
+          const uint64_t da = geo.a_mn ? make_sw128_mn_desc(sa, 8192) : make_sw128_kmajor_desc(sa);
+          const uint64_t db = geo.b_mn ? make_sw128_mn_desc(sb, 8192) : make_sw128_kmajor_desc(sb);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            umma_bf16<CG>(tmem_d, da + step_a * k, db + step_b * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit<CG>(&bars->empty[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -1179,6 +1218,7 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   geo.tail_pieces = 0;
   geo.kb_per_piece = 0;
   geo.tail_ws = nullptr;
+  geo.a_mn = geo.b_mn = 0;
   if (cta_group == 2 && geo.n_umma % 32 != 0) cta_group = 1;   // each CTA of a pair stages n_umma / 2 rows of B
   // M-tail split-K: worth it when dropping the partial row of tiles saves a whole wave
   const int tile_m = kBlockM * cta_group;
@@ -1215,6 +1255,37 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
+// C[M, N] = epilogue(A . B^T) with either operand given MN-major (see GemmGeom::a_mn): A as [K, M] row-major (pitch lda), B as
+// [K, N] row-major (pitch ldb).  K may be any length (TMA zero-fills past the last row); STORE epilogues only.
+int gemm_bf16_t(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int epi,
+                const GemmEpilogue& ep, int cta_group, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || lda % 8 != 0 || ldb % 8 != 0 || N % 8 != 0) return OPB_ERR_INVALID;
+  if (epi != EPI_STORE_BF16 && epi != EPI_STORE_F32) return OPB_ERR_INVALID;
+  if ((!a_mn && K % 8 != 0) || (!b_mn && K % 8 != 0) || (a_mn && M % 8 != 0)) return OPB_ERR_INVALID;
+  if (cta_group == 0) cta_group = (M > 2 * kBlockM) ? 2 : 1;
+  GemmGeom geo;
+  geo.M = M; geo.N = N; geo.K = K;
+  geo.num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  geo.kb_inner = geo.num_k_blocks;
+  geo.groups = 1;
+  geo.a_group_c0 = 0;
+  geo.b_group_rows = 0;
+  geo.n_umma = (N >= kBlockN) ? kBlockN : ((N + 15) / 16) * 16;
+  if (b_mn && geo.n_umma % 64 != 0) geo.n_umma = (geo.n_umma + 63) / 64 * 64;     // whole 64-wide MN chunks
+  geo.tail_pieces = 0;
+  geo.kb_per_piece = 0;
+  geo.tail_ws = nullptr;
+  geo.a_mn = a_mn ? 1 : 0;
+  geo.b_mn = b_mn ? 1 : 0;
+  if (cta_group == 2 && (geo.n_umma % 32 != 0 || (b_mn && geo.n_umma != kBlockN))) cta_group = 1;
+  CUtensorMap ta, tb;
+  int rc = a_mn ? make_tmap_bf16_2d(&ta, A, K, M, lda, 64) : make_tmap_bf16_3d(&ta, A, K, 1, lda, M, lda, kBlockM);
+  if (rc != OPB_OK) return rc;
+  rc = b_mn ? make_tmap_bf16_2d(&tb, B, K, N, ldb, 64) : make_tmap_bf16_2d(&tb, B, N, K, ldb, kBlockN / cta_group);
+  if (rc != OPB_OK) return rc;
+  return dispatch_gemm(cta_group, epi, ta, tb, ep, geo, stream);
+}
+
 int gemm_bf16_grouped_window(const void* X, const void* W, int rows, int groups, int c_pad, int taps, int n_per_group,
                              int epi, const GemmEpilogue& ep, cudaStream_t stream) {
   if (rows <= 0 || groups <= 0 || taps <= 0 || n_per_group <= 0) return OPB_ERR_INVALID;
@@ -1231,6 +1302,7 @@ int gemm_bf16_grouped_window(const void* X, const void* W, int rows, int groups,
   geo.tail_pieces = 0;
   geo.kb_per_piece = 0;
   geo.tail_ws = nullptr;
+  geo.a_mn = geo.b_mn = 0;
   const long row_stride = static_cast<long>(groups) * c_pad;
   CUtensorMap ta, tb;
   // dims {groups*c_pad, taps, rows}: tap j of output row r reads input row r + j (tap stride == row stride)

@@ -231,7 +231,10 @@ int infonce_grad(const void* a_local, const void* b_all, const void* bT_all, con
   GemmEpilogue e2;
   e2.out = grad_a;
   e2.ldo = d;
-  return gemm_bf16(g_ws, n, bT_all, n, b, d, n, EPI_STORE_F32, e2, 0, stream);
+  // grad_a = G . B_all: a contraction over the n gathered rows.  B_all ([n, k_logits], its first d columns = the bf16 "hi" part)
+  // is the MN-major B operand as it stands; the explicit transpose (bT_all) is kept for A/B runs only.
+  if (bT_all != nullptr) return gemm_bf16(g_ws, n, bT_all, n, b, d, n, EPI_STORE_F32, e2, 0, stream);
+  return gemm_bf16_t(g_ws, n, 0, b_all, k_logits, 1, b, d, n, EPI_STORE_F32, e2, 0, stream);
 }
 
 int infonce_dscale(const float* ws_a, const float* ws_b, int b, int n, float* out, cudaStream_t stream) {

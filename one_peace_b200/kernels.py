@@ -383,17 +383,18 @@ def infonce_reduce(loss_a, loss_b, am_a, am_b, target_offset):
     return out
 
 
-def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps, n_valid=0, coef=0.0):
-    """-> (grad_a fp32 [b,d], ws_gz) for one direction; a_local/b_all [.,k] (k = d or 3d), bT_all bf16 [d,n];
+def infonce_grad(a_local, b_all, bT_all, scale, row_lse, target_offset, eps, n_valid=0, coef=0.0, d=None):
+    """-> (grad_a fp32 [b,d], ws_gz) for one direction; a_local/b_all [.,k] (k = d or 3d).  bT_all: bf16 [d,n] transposed copy
+    of b_all's first d columns, or None (then pass d): b_all is read in place as an MN-major operand.
     coef = weight of one row's loss (0 -> 1 / (2 b), the two-direction InfoNCE mean)"""
     b, k = a_local.shape
     n = b_all.shape[0]
-    d = bT_all.shape[0]
+    d = bT_all.shape[0] if bT_all is not None else int(d)
     dev = a_local.device
     g_ws = torch.empty(b, n, dtype=torch.bfloat16, device=dev)
     ws_gz = torch.empty((n + 255) // 256 * b, dtype=torch.float32, device=dev)
     grad = torch.empty(b, d, dtype=torch.float32, device=dev)
-    st = _lib.load().opb_infonce_grad(a_local.data_ptr(), b_all.data_ptr(), bT_all.data_ptr(), scale.data_ptr(),
+    st = _lib.load().opb_infonce_grad(a_local.data_ptr(), b_all.data_ptr(), _ptr(bT_all), scale.data_ptr(),
                                       row_lse.data_ptr(), b, n, d, k, target_offset, eps, g_ws.data_ptr(),
                                       ws_gz.data_ptr(), grad.data_ptr(), int(n_valid), float(coef), _stream())
     _lib.check(st, "opb_infonce_grad")
@@ -660,3 +661,20 @@ def ln_fold(weight, ln_w, ln_b, bias, out_w, colsum, bias_out, interleave=0):
                                  interleave, out_w.data_ptr(), out_w.stride(0), colsum.data_ptr(), bias_out.data_ptr(), _stream())
     _lib.check(st, "opb_ln_fold")
     _count()
+
+
+def gemm_t(a, b, epi, out, a_mn=False, b_mn=False, bias=None, cta_group=0):
+    """out[M, N] = A B^T with MN-major operands: a is [K, M] when a_mn else [M, K]; b is [K, N] when b_mn else [N, K]
+    (bf16, unit column stride, free row pitch).  No transposed copies: TMA + UMMA read the row-contracted layout directly."""
+    _need_cuda(a, b, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    Kd, M = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
+    Kb, N = (b.shape[0], b.shape[1]) if b_mn else (b.shape[1], b.shape[0])
+    assert Kd == Kb and out.shape == (M, N)
+    st = _lib.load().opb_gemm_bf16_t(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), M, N, Kd, epi,
+                                     out.data_ptr(), out.stride(0), _ptr(bias), cta_group, _stream())
+    _lib.check(st, "opb_gemm_bf16_t")
+    _count()
+    if PROFILE_HOOK is not None:
+        PROFILE_HOOK("gemm", 2.0 * M * N * Kd, (M, N, Kd, epi))
+    return out

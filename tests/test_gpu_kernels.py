@@ -566,3 +566,27 @@ def test_dcl_form_of_infonce_kernels(K):
     grad, _ = K.infonce_grad(a3, b3, K.transpose_bf16(b3, cols=d), scale, lse, 0, 0.1, n_valid=nt, coef=1.0 / nm)
     want_rows.mean().backward()
     assert relerr(grad, sa.grad) < 2e-2
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("M,N,Kd", [(512, 768, 1000), (1536, 1536, 12608), (96, 256, 77), (4608, 1536, 333)])
+def test_gemm_mn_major_operands(K, cg, a_mn, b_mn, M, N, Kd):
+    """opb_gemm_bf16_t: contraction over the ROWS of [K, M] / [K, N] matrices without transposed copies (dW = dY^T X)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + Kd)
+    if not (a_mn and b_mn) and Kd % 8:
+        Kd = Kd // 8 * 8                      # a K-major operand needs an 8-element row pitch
+    A = (torch.randn(M, Kd, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, Kd, device="cuda", generator=g) * 0.1).bfloat16()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    K.gemm_t(a, b, K.EPI_STORE_F32, out, a_mn=a_mn, b_mn=b_mn, cta_group=cg)
+    want = A.float() @ B.float().t()
+    assert relerr(out, want) < 2e-5
+    # strided views (columns of a wider matrix), bf16 output
+    wide_b = torch.zeros(b.shape[0], b.shape[1] + 64, dtype=torch.bfloat16, device="cuda")
+    wide_b[:, 32:32 + b.shape[1]] = b
+    out16 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    K.gemm_t(a, wide_b[:, 32:32 + b.shape[1]], K.EPI_STORE_BF16, out16, a_mn=a_mn, b_mn=b_mn, cta_group=cg)
+    assert relerr(out16, want) < 6e-3
