@@ -414,27 +414,47 @@ def contrastive_train_block(dev, world, rank, b=64, text_len=32, steps=3, warmup
             ev[2].record()
         return loss.detach()
     losses = [round(step().item(), 4) for _ in range(warmup)]
+    l0 = K.LAUNCHES
+    step(timed=True)                              # eager step with the phase split (also the launch count)
+    torch.cuda.synchronize()
+    launches = K.LAUNCHES - l0
+    eager_split = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]
+    # the timed steps replay the criterion forward + backward as ONE CUDA graph (one_peace_b200/graphs.py; 4.9 k launches and
+    # ~0.5 s of Python per eager step make the eager loop CPU-bound); the gradient exchange + optimizer stay eager
+    graphed = None
+    if os.environ.get("OPB_BENCH_GRAPH", "1") != "0":
+        try:
+            from one_peace_b200.graphs import GraphedTrainStep
+            graphed = GraphedTrainStep(model, crit, sample, params, warmup=0)
+        except Exception as e:
+            graphed = None
+            graph_error = repr(e)[:200]
+
+    def run():
+        if graphed is None:
+            return step()
+        loss, _, _ = graphed(sample)
+        opt.step(max_norm=3.0)
+        return loss.detach()
+    run()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    l0 = K.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        losses.append(round(step().item(), 4))
+        losses.append(round(run().item(), 4))
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches = (K.LAUNCHES - l0) // steps
-    step(timed=True)
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=dev)
+    t = torch.tensor([e0.elapsed_time(e1) / steps, eager_split[0], eager_split[1]], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     n_params = sum(q.numel() for q in params)
     out = {"metric": "contrastive_train_step_pairs_per_sec", "value": round(b * world / t[0].item() * 1e3, 2), "unit": "pairs/s",
-           "ms_per_step": round(t[0].item(), 2), "fwd_bwd_ms": round(t[1].item(), 2), "grad_exchange_adam_ms": round(t[2].item(), 2),
+           "ms_per_step": round(t[0].item(), 2), "cuda_graph": graphed is not None,
+           "eager_fwd_bwd_ms": round(t[1].item(), 2), "grad_exchange_adam_ms": round(t[2].item(), 2),
            "pairs_per_rank": b, "global_batch": b * world, "text_len": text_len, "params_b": round(n_params / 1e9, 3), "dtype": "bf16",
            "losses": losses, "finite": all(x == x for x in losses), "launches_per_step": int(launches),
            "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
@@ -442,7 +462,9 @@ def contrastive_train_block(dev, world, rank, b=64, text_len=32, steps=3, warmup
                           "all_gather of the updated bf16 parameter shards (optim/distributed_adam.py); limiting one: the "
                           f"{round(n_params * 2 / 1e9, 2)} GB gradient reduce-scatter + parameter all-gather, not overlapped with backward",
            "includes": "text + image encoder fwd / bwd (activation recompute), InfoNCE, grad-norm clip, sharded fused Adam"}
-    del opt, model, params
+    if graphed is None and os.environ.get("OPB_BENCH_GRAPH", "1") != "0":
+        out["cuda_graph_error"] = graph_error
+    del opt, model, params, graphed
     torch.cuda.empty_cache()
     return out
 

@@ -62,10 +62,12 @@ def _dw(dy, x, dtype):
     return out if out.dtype == dtype else out.to(dtype)
 
 
-def _dx(dy, wT, n_out):
-    """dX [M, n_out] = dy[M, N] W[N, n_out], with wT = W^T as a K-major [n_out, N] bf16 operand."""
-    out = torch.empty(dy.shape[0], n_out, dtype=torch.bfloat16, device=dy.device)
-    K.gemm(dy, wT, K.EPI_STORE_BF16, out)
+def _dx(dy, w, n_out, out=None):
+    """dX [M, n_out] = dy[M, N] W[N, n_out]: a contraction over the OUTPUT features of the Linear, for which the weight
+    [N, n_out] as stored is the MN-major B operand (opb_gemm_bf16_t): no transposed weight copies are kept."""
+    if out is None:
+        out = torch.empty(dy.shape[0], n_out, dtype=torch.bfloat16, device=dy.device)
+    K.gemm_t(dy, w, K.EPI_STORE_BF16 if out.dtype == torch.bfloat16 else K.EPI_STORE_F32, out, b_mn=True)
     return out
 
 
@@ -109,8 +111,8 @@ def layer_params(layer, modality):
 
 
 def shared_train_pack(layer):
-    """bf16 operands of the modality-shared half of a layer in both orientations (W for the forward / dW, W^T for dX),
-    rebuilt after each optimizer step."""
+    """bf16 operands of the modality-shared half of a layer (one orientation: dX reads W as an MN-major operand), rebuilt
+    after each optimizer step."""
     cache = layer._cache.setdefault("_train_shared", PackCache())
     ps = shared_params(layer)
 
@@ -122,7 +124,7 @@ def shared_train_pack(layer):
         qs = torch.ones(3 * d, device=dev)
         qs[:d] = layer.self_attn.scaling
         wo = bf16(ps[5])
-        return dict(wqkv=wqkv, wqkvT=K.transpose_bf16(wqkv), bqkv=bqkv, qscale=qs, wo=wo, woT=K.transpose_bf16(wo),
+        return dict(wqkv=wqkv, bqkv=bqkv, qscale=qs, wo=wo,
                     bo=f32(ps[6]), lni_w=f32(ps[7]), lni_b=f32(ps[8]), ln1_w=f32(ps[9]), ln1_b=f32(ps[10]),
                     ln2_w=f32(ps[11]), ln2_b=f32(ps[12]), g1=f32(ps[13]) if ps[13] is not None else None,
                     g2=f32(ps[14]) if ps[14] is not None else None)
@@ -136,7 +138,7 @@ def ffn_train_pack(layer, modality):
     def build():
         w01 = torch.cat([bf16(ps[0]), bf16(ps[1])], 0).contiguous()      # [g | l] halves, not tile-interleaved
         w2 = bf16(ps[4])
-        return dict(w01=w01, w01T=K.transpose_bf16(w01), lnf_w=f32(ps[2]), lnf_b=f32(ps[3]), w2=w2, w2T=K.transpose_bf16(w2),
+        return dict(w01=w01, lnf_w=f32(ps[2]), lnf_b=f32(ps[3]), w2=w2,
                     b2=f32(ps[5]), lnf_eps=getattr(layer, f"{modality}_ffn")[2].eps)
     return cache.get(ps, build)
 
@@ -195,12 +197,12 @@ def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_sc
     dg2, db2 = g(d), g(d)
     df = K.scale_resid_bwd(dx, s["f"], p["g2"], row_scale, e(d), dgamma=dg2, dbias=db2)
     dW2 = _dw(df, s["u2"], ps[19].dtype)
-    du2 = _dx(df, p["w2T"], F_)
+    du2 = _dx(df, p["w2"], F_)
     dlnf_w, dlnf_b = g(F_), g(F_)
     du = K.layernorm_bwd(s["u"], du2, p["lnf_w"], p["lnf_b"], e(F_), eps=p["lnf_eps"], dgamma=dlnf_w, dbeta=dlnf_b)
     dgl = K.geglu_bwd(s["gl"], du, e(2 * F_))
     dW01 = _dw(dgl, s["h2"], ps[15].dtype)
-    dh2 = _dx(dgl, p["w01T"], d)
+    dh2 = _dx(dgl, p["w01"], d)
     dln2_w, dln2_b = g(d), g(d)
     K.layernorm_bwd(s["x2"], dh2, p["ln2_w"], p["ln2_b"], dx, eps=layer.final_layer_norm.eps, accumulate=True,
                     dgamma=dln2_w, dbeta=dln2_b)                                   # dx = dL/dx2
@@ -208,7 +210,7 @@ def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_sc
     dg1, dbo = g(d), g(d)
     do = K.scale_resid_bwd(dx, s["o"], p["g1"], row_scale, e(d), dgamma=dg1, dbias=dbo)
     dWo = _dw(do, s["a2"], ps[5].dtype)
-    da2 = _dx(do, p["woT"], d)
+    da2 = _dx(do, p["wo"], d)
     dlni_w, dlni_b = g(d), g(d)
     datt = K.layernorm_bwd(s["att"], da2, p["lni_w"], p["lni_b"], e(d), eps=layer.self_attn.ln.eps, dgamma=dlni_w,
                            dbeta=dlni_b)
@@ -216,7 +218,7 @@ def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_sc
                            layer.self_attn.scaling)
     dbqkv = K.colsum(dqkv, g(3 * d))
     dWqkv = _dw(dqkv, s["h1"], ps[0].dtype)
-    dh1 = _dx(dqkv, p["wqkvT"], d)
+    dh1 = _dx(dqkv, p["wqkv"], d)
     dln1_w, dln1_b = g(d), g(d)
     K.layernorm_bwd(x, dh1, p["ln1_w"], p["ln1_b"], dx, eps=layer.self_attn_layer_norm.eps, accumulate=True,
                     dgamma=dln1_w, dbeta=dln1_b)                                   # dx = dL/dx
@@ -347,7 +349,7 @@ class HeadFn(torch.autograd.Function):
         dlog = K.l2_normalize_bwd(logits, dy.to(torch.float32).contiguous())
         db = K.colsum(dlog, torch.empty(w.shape[0], dtype=torch.float32, device=x.device))
         dW = _dw(dlog, cls, w.dtype)
-        dcls = _dx(dlog, K.transpose_bf16(bf16(w)), d)
+        dcls = _dx(dlog, bf16(w), d)
         dxf = torch.zeros_like(x)
         dg = torch.empty(d, dtype=torch.float32, device=x.device)
         dbt = torch.empty(d, dtype=torch.float32, device=x.device)
@@ -433,13 +435,13 @@ class ImageEmbedFn(torch.autograd.Function):
         dy3 = K.scale_resid_bwd(dx, None, None, None, torch.empty(B * w * w, d, dtype=torch.bfloat16, device=dev), dbias=db3,
                                 in_period=S, in_valid=w * w, in_shift=1)
         dW3 = _dw(dy3, a3, w3.dtype).view(d, 2, 2, c4).permute(0, 3, 1, 2)
-        da3 = _dx(dy3, K.transpose_bf16(pk["w3"]), 4 * c4)
+        da3 = _dx(dy3, pk["w3"], 4 * c4)
         dln2w, dln2b = g(c4), g(c4)
         dy2 = K.layernorm_bwd(y2, da3, f32(ln2w), f32(ln2b), torch.empty_like(y2), gelu=True, dgamma=dln2w, dbeta=dln2b,
                               dy_merge_w=g2)
         db2 = K.colsum(dy2, g(c4))
         dW2 = _dw(dy2, a2, w2.dtype).view(c4, 2, 2, c4).permute(0, 3, 1, 2)
-        da2 = _dx(dy2, K.transpose_bf16(pk["w2"]), 4 * c4)
+        da2 = _dx(dy2, pk["w2"], 4 * c4)
         dln1w, dln1b = g(c4), g(c4)
         dy1 = K.layernorm_bwd(y1, da2, f32(ln1w), f32(ln1b), torch.empty_like(y1), gelu=True, dgamma=dln1w, dbeta=dln1b,
                               dy_merge_w=g1)
@@ -568,14 +570,14 @@ class AudioEmbedFn(torch.autograd.Function):
             for g in range(G):
                 sl = slice(g * cg, (g + 1) * cg)
                 dW[sl] = _dw(dc[:, sl], Xw[g], pos_w[i].dtype)
-                K.gemm(dc[:, sl], K.transpose_bf16(s["pk"][i][sl]), K.EPI_STORE_BF16, dXw[g])
+                _dx(dc[:, sl], s["pk"][i][sl], pos_k * cg, out=dXw[g])
             dpos_w[i] = dW.view(d, pos_k, cg).permute(0, 2, 1).contiguous()
             dp = K.window_scatter(dXw, B, T, T, 1, pos_k, pos_k // 2)
         dfeats = K.scale_resid_fwd(dbody, dp, None, None, torch.empty_like(dbody))      # direct + through the pos branch
         dproj_b = g32(d)
         dfb = K.scale_resid_bwd(dfeats, None, None, None, e(B * T, d), dbias=dproj_b)
         dproj_w = _dw(dfb, s["yP"], proj_w.dtype)
-        dyP = _dx(dfb, K.transpose_bf16(bf16(proj_w)), C)
+        dyP = _dx(dfb, bf16(proj_w), C)
         dpost_w, dpost_b = g32(C), g32(C)
         dz = K.layernorm_bwd(s["zs"][-1], dyP, f32(post_w), f32(post_b), e(B * T, C), dgamma=dpost_w, dbeta=dpost_b)
         # ---- feature extractor, last layer first ----
@@ -591,7 +593,7 @@ class AudioEmbedFn(torch.autograd.Function):
                 kw, st = spec[k][1], spec[k][2]
                 A = K.window_gather(s["zs"][k - 1], B, frames[k - 1], frames[k], st, kw, 0, 1)[0]
                 dconv[k] = _dw(dy, A, conv_w[k].dtype).view(C, kw, C).permute(0, 2, 1).contiguous()
-                dA = _dx(dy, K.transpose_bf16(s["wk"][k]), kw * C)
+                dA = _dx(dy, s["wk"][k], kw * C)
                 dz = K.window_scatter(dA.view(1, B * frames[k], kw * C), B, frames[k - 1], frames[k], st, kw, 0)
         grads = list(dconv) + dlnw + dlnb + [dpost_w.to(post_w.dtype), dpost_b.to(post_b.dtype), dproj_w, dproj_b.to(proj_b.dtype)] + \
             dpos_w + dpos_b + [dcls.view(cls.shape).to(cls.dtype), dcls.view(cls_pos.shape).to(cls_pos.dtype)]

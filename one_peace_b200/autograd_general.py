@@ -122,12 +122,12 @@ def layer_backward_general(layer, x, s, dx, bias, dbias, key_pad, lay, row_scale
         dfp = df[rs]
         db2 = K.colsum(dfp, g(d))
         dW2 = _dw(dfp, fs["u2"], fps[4].dtype)
-        du2 = _dx(dfp, fp["w2T"], F_)
+        du2 = _dx(dfp, fp["w2"], F_)
         dlnf_w, dlnf_b = g(F_), g(F_)
         du = K.layernorm_bwd(fs["u"], du2, fp["lnf_w"], fp["lnf_b"], e(n, F_), eps=fp["lnf_eps"], dgamma=dlnf_w, dbeta=dlnf_b)
         dgl = K.geglu_bwd(fs["gl"], du, e(n, 2 * F_))
         dW01 = _dw(dgl, s["h2"][rs], fps[0].dtype)
-        K.gemm(dgl, fp["w01T"], K.EPI_STORE_BF16, dh2[rs])
+        _dx(dgl, fp["w01"], d, out=dh2[rs])
         grads = [dW01[:F_], dW01[F_:], dlnf_w, dlnf_b, dW2, db2]
         ffn_grads.append([gr if gr.dtype == prm.dtype else gr.to(prm.dtype) for gr, prm in zip(grads, fps)])
     dln2_w, dln2_b = g(d), g(d)
@@ -138,7 +138,7 @@ def layer_backward_general(layer, x, s, dx, bias, dbias, key_pad, lay, row_scale
     dbo = g(d)
     do = K.scale_resid_bwd(dx, s["o"], p["g1"], row_scale, e(M, d), dgamma=dg1, dbias=dbo)
     dWo = _dw(do, s["a2"], sp[5].dtype)
-    da2 = _dx(do, p["woT"], d)
+    da2 = _dx(do, p["wo"], d)
     dlni_w, dlni_b = g(d), g(d)
     datt = K.layernorm_bwd(s["att_mm"], da2, p["lni_w"], p["lni_b"], e(M, d), eps=layer.self_attn.ln.eps, dgamma=dlni_w,
                            dbeta=dlni_b)
@@ -150,7 +150,7 @@ def layer_backward_general(layer, x, s, dx, bias, dbias, key_pad, lay, row_scale
         dqkv = K.row_gather(dqkv, lay.to_mm)
     dbqkv = K.colsum(dqkv, g(3 * d))
     dWqkv = _dw(dqkv, s["h1"], sp[0].dtype)
-    dh1 = _dx(dqkv, p["wqkvT"], d)
+    dh1 = _dx(dqkv, p["wqkv"], d)
     dln1_w, dln1_b = g(d), g(d)
     K.layernorm_bwd(x, dh1, p["ln1_w"], p["ln1_b"], dx, eps=layer.self_attn_layer_norm.eps, accumulate=True,
                     dgamma=dln1_w, dbeta=dln1_b)                                   # dx = dL/dx
@@ -364,7 +364,7 @@ class LinearFn(torch.autograd.Function):
             db = K.colsum(dyb, torch.empty(w.shape[0], dtype=torch.float32, device=dy.device)).to(b.dtype)
         dW = _dw(dyb, xb, w.dtype)
         dxf = torch.empty(rows, w.shape[1], dtype=torch.float32, device=dy.device)
-        K.gemm(dyb, K.transpose_bf16(bf16(w)), K.EPI_STORE_F32, dxf)
+        _dx(dyb, bf16(w), w.shape[1], out=dxf)
         return dxf.to(ctx.xdt), dW, db
 
 
