@@ -85,6 +85,12 @@ class GraphedTrainStep:
         for p in self.params:
             p.grad = None
         self._invalidate_packs()
+        # No autograd graph of an earlier EAGER step may be alive here (drop every reference to its loss / outputs): the
+        # parameters' AccumulateGrad nodes live as long as such a graph does and are bound to the stream they were created on
+        # — the legacy stream — which the engine would have to synchronise with during capture (illegal).  Once they have
+        # expired, new ones are created inside the capture, on the capture stream.
+        import gc
+        gc.collect()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             loss, self.sample_size, log = criterion(model, self.static_sample)

@@ -163,6 +163,7 @@ def test_graphed_train_step_equals_eager_and_tracks_weight_updates():
                 loss, _, _ = crit(model, sample)
                 loss.backward()
             losses.append(loss.item())
+            del loss                                              # no eager autograd graph may be alive at capture time
             opt.step()
         runs[mode] = (losses, {n: p.detach().float().cpu().clone() for n, p in model.named_parameters()})
     le, lg = runs["eager"][0], runs["graph"][0]
