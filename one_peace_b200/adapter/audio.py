@@ -57,10 +57,23 @@ class AudioAdapter(torch.nn.Module):
         if cfg.layernorm_embedding or cfg.add_type_embedding or cfg.shrink_alpha != 1.0 or cfg.conv_pos_pre_ln:
             raise NotImplementedError("layernorm_embedding / add_type_embedding / shrink_alpha / conv_pos_pre_ln are off "
                                       "in the 4B config")
-        if cfg.abs_pos_type != "conv" or cfg.conv_bias:
-            raise NotImplementedError("only abs_pos_type='conv', conv_bias=False (the 4B config) is built")
+        if cfg.abs_pos_type not in ("conv", "fixed") or cfg.conv_bias:
+            raise NotImplementedError("abs_pos_type must be 'conv' (encoder) or 'fixed' (decoder); conv_bias=False")
         self.embed_dim = embed_dim
         self.attention_heads = attention_heads
+        self.abs_pos_type = cfg.abs_pos_type
+        self._cache = PackCache()
+        if cfg.feature_encoder_spec is None or cfg.abs_pos_type == "fixed":
+            # decoder variant (pretrain_al_3B.yaml decoder.audio_adapter: no feature extractor, Embedding(1026, d) positions,
+            # audio.py:44,87-88): only ever called with preserve_embed (the mask-token canvas)
+            if cfg.feature_encoder_spec is not None or cfg.abs_pos_type != "fixed":
+                raise NotImplementedError("decoder audio adapter = feature_encoder_spec None + abs_pos_type 'fixed'")
+            self.spec = None
+            self.embed_positions = Embedding(1024 + 2, embed_dim)
+            self.cls_embedding = torch.nn.Parameter(torch.zeros(1, 1, embed_dim))
+            self._init_bias_and_mask(cfg, attention_heads, num_layers)
+            trunc_normal_(self.embed_positions.weight)
+            return
         self.spec = eval(cfg.feature_encoder_spec)
         if self.spec[0][1:] != (10, 5) or any(s != 2 or c != self.spec[0][0] for c, _, s in self.spec[1:]):
             raise NotImplementedError("feature extractor kernels are built for [(C,10,5)] + [(C,k,2)]*n")
@@ -82,6 +95,9 @@ class AudioAdapter(torch.nn.Module):
         self.cls_pos_embed = torch.nn.Parameter(torch.zeros(1, 1, embed_dim))
         trunc_normal_(self.cls_pos_embed)
         self.cls_embedding = torch.nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self._init_bias_and_mask(cfg, attention_heads, num_layers)
+
+    def _init_bias_and_mask(self, cfg, attention_heads, num_layers):
         if cfg.use_attn_bias:
             num_rel_dis = 2 * cfg.bucket_size - 1
             rp_bucket = make_token_bucket_position(cfg.bucket_size, max_position=1024)
@@ -93,10 +109,9 @@ class AudioAdapter(torch.nn.Module):
                 [Embedding(num_rel_dis + 3, attention_heads, zero_init=True) for _ in range(num_layers or 1)])
         else:
             self.rel_pos_table_list = None
-        self.mask_embedding = torch.nn.Parameter(torch.zeros(1, embed_dim))
+        self.mask_embedding = torch.nn.Parameter(torch.zeros(1, self.embed_dim))
         trunc_normal_(self.cls_embedding)
         trunc_normal_(self.mask_embedding)
-        self._cache = PackCache()
 
     # ------------------------------------------------------------------------------------------------
     def _pack(self):
@@ -163,18 +178,32 @@ class AudioAdapter(torch.nn.Module):
         return dict(tables=[t.weight for t in self.rel_pos_table_list], bucket=self.rp_bucket, n=n, ids=ids)
 
     def embed_general(self, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None):
-        """General form for the concatenated 'al' encoder (full sequences; the audio preserve_ids / mask-token student passes
-        of audio_text_pretrain_loss.py gather BEFORE the conv positional encoder, audio.py:184-189, and are not built)."""
-        if preserve_ids is not None or preserve_embed is not None:
-            raise NotImplementedError("audio preserve_ids / mask-token student passes are not built")
+        """General (pretraining) form of forward (models/adapter/audio.py:136-207) -> (x fp32, pad uint8, bias source).
+        preserve_ids (B,K) int64, -1 padded: encoder student pass — frame features gathered by id BEFORE the positional
+        convolution (:184-189; padded slots read position K-1 as the reference does).  With preserve_embed (B,K,d): decoder
+        canvas = mask token everywhere, preserved rows scattered to their positions, plus Embedding positions (:172-181)."""
+        B, S = padding_mask.shape
+        if preserve_embed is not None:
+            from ..autograd_general import RowGatherFn
+            from .text import canvas_index
+            if self.abs_pos_type != "fixed":
+                raise RuntimeError("the mask-token canvas needs abs_pos_type='fixed' (audio.py:173: embed_positions(position_ids))")
+            d = self.embed_dim
+            x = RowGatherFn.apply(preserve_embed.reshape(-1, d), canvas_index(preserve_ids, S), mask_token,
+                                  self.embed_positions.weight[:S]).view(B, S, d)
+            return x, padding_mask.to(torch.uint8).contiguous(), self.bias_source(S)
+        if self.spec is None:
+            raise RuntimeError("decoder audio adapter (no feature extractor) needs preserve_embed")
+        if preserve_ids is not None:
+            return self.forward_train(src_audios, padding_mask, preserve_ids)
         x, pad, _ = self.forward(src_audios, padding_mask)
         return x, pad, self.bias_source(x.shape[1])
 
     def forward(self, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None):
         """src_audios (B, N) waveform, padding_mask (B, T+1) bool -> (x fp32 (B,T+1,d) with padded rows zeroed,
         padding_mask uint8, [bias (H,S,S_pad)])"""
-        if preserve_ids is not None or preserve_embed is not None:
-            raise NotImplementedError("preserve_ids / mask-token path belongs to the pretraining (DCL) criterion")
+        if preserve_ids is not None or preserve_embed is not None or self.spec is None:
+            return self.embed_general(src_audios, padding_mask, preserve_ids, preserve_embed, mask_token)
         if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             return self.forward_train(src_audios, padding_mask)
         p = self._pack()
@@ -232,21 +261,37 @@ class AudioAdapter(torch.nn.Module):
         bias = self.get_rel_pos_bias(S) if self.rel_pos_table_list is not None else None
         return x, pad, bias
 
-    def forward_train(self, src_audios, padding_mask):
-        """Same outputs, recorded for autograd (autograd.AudioEmbedFn: materialised-window GEMMs + col2im adjoints)."""
-        from ..autograd import AudioEmbedFn, RelPosBiasFn, TrainBias
+    def _feat_params(self):
+        fe = self.embed_audios[0].conv_layers
+        return [l[0].weight for l in fe] + [l[2][1].weight for l in fe] + [l[2][1].bias for l in fe] + \
+               [self.embed_audios[2].weight, self.embed_audios[2].bias, self.embed_audios[3].weight, self.embed_audios[3].bias]
+
+    def _pos_params(self):
+        return [self.embed_positions[i + 1][0].weight for i in range(self.pos_depth)] + \
+               [self.embed_positions[i + 1][0].bias for i in range(self.pos_depth)] + [self.cls_embedding, self.cls_pos_embed]
+
+    def forward_train(self, src_audios, padding_mask, preserve_ids=None):
+        """Same outputs, recorded for autograd (autograd.AudioFeatFn -> [preserve_ids gather] -> AudioPosFn: materialised-window
+        GEMMs + col2im adjoints).  With preserve_ids (B,K) the frame features are gathered BEFORE the positional convolution
+        (models/adapter/audio.py:184-189) and the relative-position bias source carries the ids."""
+        from ..autograd import AudioFeatFn, AudioPosFn, RelPosBiasFn, TrainBias
         B, N = src_audios.shape
         T = self.frame_counts(N)[-1]
         S = T + 1
         if padding_mask.shape != (B, S):
             raise RuntimeError(f"audio_padding_masks must be (B, frames + 1) = ({B}, {S}), got {tuple(padding_mask.shape)}")
-        fe = self.embed_audios[0].conv_layers
-        ps = [l[0].weight for l in fe] + [l[2][1].weight for l in fe] + [l[2][1].bias for l in fe] + \
-             [self.embed_audios[2].weight, self.embed_audios[2].bias, self.embed_audios[3].weight, self.embed_audios[3].bias] + \
-             [self.embed_positions[i + 1][0].weight for i in range(self.pos_depth)] + \
-             [self.embed_positions[i + 1][0].bias for i in range(self.pos_depth)] + [self.cls_embedding, self.cls_pos_embed]
-        meta = (tuple(self.spec), self.pos_k, self.pos_groups, self.embed_dim)
-        x, pad = AudioEmbedFn.apply(src_audios, padding_mask, meta, *ps)
+        d = self.embed_dim
+        feats = AudioFeatFn.apply(src_audios, (tuple(self.spec), d), *self._feat_params())            # fp32 [B*T, d]
+        if preserve_ids is not None:
+            from ..autograd_general import RowGatherFn
+            Kk = preserve_ids.shape[1]
+            # position_ids[:, 1:] - 1 with padded slots mapped to position K - 1 first (audio.py:150-153,186): frame K - 2
+            pid = preserve_ids.masked_fill(preserve_ids.eq(-1), Kk - 1)[:, 1:] - 1
+            flat = (pid + torch.arange(B, device=pid.device)[:, None] * T).reshape(-1).contiguous()
+            feats = RowGatherFn.apply(feats, flat, None, None)
+            x, pad = AudioPosFn.apply(feats, preserve_ids.eq(-1), (B, Kk - 1, self.pos_k, self.pos_groups, d), *self._pos_params())
+            return x, pad, self.bias_source(Kk, preserve_ids.contiguous())
+        x, pad = AudioPosFn.apply(feats, padding_mask, (B, T, self.pos_k, self.pos_groups, d), *self._pos_params())
         bias = None
         if self.rel_pos_table_list is not None:
             fast = self.get_rel_pos_bias(S)

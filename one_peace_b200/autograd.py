@@ -453,27 +453,20 @@ class ImageEmbedFn(torch.autograd.Function):
                 dcls.view(cls_shape).to(cls_dt))
 
 
-class AudioEmbedFn(torch.autograd.Function):
-    """Waveform -> x fp32 [B, T+1, d] (adapter/audio.py:150-210): wav2vec conv feature extractor (:254-311), post
-    LayerNorm + Linear (:46-55), 5-layer grouped conv positional encoder on the un-normalised features (:57-80,194-199),
-    CLS row, padded rows zeroed.  Training form: every convolution is a GEMM over a MATERIALISED window matrix
-    (opb_window_gather) in compact per-clip frame space, because dW = dY^T . windows needs that matrix K-major anyway;
-    col2im (opb_window_scatter) is the adjoint.  (The inference path, adapter/audio.py here, reads overlapping TMA views
-    instead and never materialises windows.)
+class AudioFeatFn(torch.autograd.Function):
+    """Waveform -> frame features fp32 [B*T, d] (adapter/audio.py:183: `self.embed_audios(src_audios)`): wav2vec conv feature
+    extractor (:254-311) + post LayerNorm + Linear (:46-55).  Training form: every convolution is a GEMM over a MATERIALISED
+    window matrix (opb_window_gather) in compact per-clip frame space; col2im (opb_window_scatter) is the adjoint.  (The
+    inference path, adapter/audio.py here, reads overlapping TMA views instead and never materialises windows.)
 
-    Inputs after (wav, pad, meta): conv weights [n_fe], LN weights [n_fe], LN biases [n_fe], post_ln w, b, proj w, b,
-    pos conv weights [n_pos], pos conv biases [n_pos], cls_embedding, cls_pos_embed."""
+    Inputs after (wav, meta): conv weights [n_fe], LN weights [n_fe], LN biases [n_fe], post_ln w, b, proj w, b."""
 
     @staticmethod
-    def forward(ctx, wav, pad, meta, *ps):
-        spec, pos_k, pos_groups, d = meta
+    def forward(ctx, wav, meta, *ps):
+        spec, d = meta
         n_fe = len(spec)
-        n_pos = (len(ps) - 3 * n_fe - 6) // 2
         conv_w, ln_w, ln_b = ps[:n_fe], ps[n_fe:2 * n_fe], ps[2 * n_fe:3 * n_fe]
         post_w, post_b, proj_w, proj_b = ps[3 * n_fe:3 * n_fe + 4]
-        pos_w = ps[3 * n_fe + 4:3 * n_fe + 4 + n_pos]
-        pos_b = ps[3 * n_fe + 4 + n_pos:3 * n_fe + 4 + 2 * n_pos]
-        cls, cls_pos = ps[-2], ps[-1]
         B, N = wav.shape
         dev = wav.device
         C = spec[0][0]
@@ -482,11 +475,9 @@ class AudioEmbedFn(torch.autograd.Function):
             L = (L - k) // s + 1
             frames.append(L)
         T = frames[-1]
-        S = T + 1
 
         def e(rows, n, dt=torch.bfloat16):
             return torch.empty(rows, n, dtype=dt, device=dev)
-        # ---- feature extractor ----
         wv = wav if wav.dtype in (torch.float32, torch.bfloat16) else wav.float()
         a0 = K.audio_frame10(wv.contiguous(), frames[0], e(B * frames[0], 16))
         w0 = torch.zeros(C, 16, dtype=torch.bfloat16, device=dev)
@@ -503,7 +494,72 @@ class AudioEmbedFn(torch.autograd.Function):
             ys.append(y); zs.append(z)
         yP = K.layernorm(z, f32(post_w), f32(post_b), e(B * T, C))
         feats = K.gemm(yP, bf16(proj_w), K.EPI_STORE_F32, e(B * T, d, torch.float32), bias=f32(proj_b))
-        # ---- conv positional encoder (un-normalised features in, LayerNorm(no affine) + GELU after every conv) ----
+        ctx.saved = dict(a0=a0, wk=wk, ys=ys, zs=zs, yP=yP)
+        ctx.params = ps
+        ctx.meta = (meta, frames, B)
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeats):
+        (spec, d), frames, B = ctx.meta
+        s = ctx.saved
+        ps = ctx.params
+        n_fe = len(spec)
+        conv_w, ln_w, ln_b = ps[:n_fe], ps[n_fe:2 * n_fe], ps[2 * n_fe:3 * n_fe]
+        post_w, post_b, proj_w, proj_b = ps[3 * n_fe:3 * n_fe + 4]
+        C, T = spec[0][0], frames[-1]
+        dev = dfeats.device
+
+        def e(rows, n):
+            return torch.empty(rows, n, dtype=torch.bfloat16, device=dev)
+
+        def g32(n):
+            return torch.empty(n, dtype=torch.float32, device=dev)
+        dfeats = dfeats.to(torch.float32).contiguous()
+        dproj_b = g32(d)
+        dfb = K.scale_resid_bwd(dfeats, None, None, None, e(B * T, d), dbias=dproj_b)
+        dproj_w = _dw(dfb, s["yP"], proj_w.dtype)
+        dyP = _dx(dfb, bf16(proj_w), C)
+        dpost_w, dpost_b = g32(C), g32(C)
+        dz = K.layernorm_bwd(s["zs"][-1], dyP, f32(post_w), f32(post_b), e(B * T, C), dgamma=dpost_w, dbeta=dpost_b)
+        dconv, dlnw, dlnb = [None] * n_fe, [None] * n_fe, [None] * n_fe
+        for k in reversed(range(n_fe)):
+            dg, db = g32(C), g32(C)
+            dy = K.layernorm_bwd(s["ys"][k], dz, f32(ln_w[k]), f32(ln_b[k]), e(B * frames[k], C), gelu=True, dgamma=dg, dbeta=db)
+            dlnw[k], dlnb[k] = dg.to(ln_w[k].dtype), db.to(ln_b[k].dtype)
+            if k == 0:
+                dW0 = _dw(dy, s["a0"], conv_w[0].dtype)                                     # [C, 16]
+                dconv[0] = dW0[:, :spec[0][1]].reshape(C, 1, spec[0][1]).contiguous()
+            else:
+                kw, st = spec[k][1], spec[k][2]
+                A = K.window_gather(s["zs"][k - 1], B, frames[k - 1], frames[k], st, kw, 0, 1)[0]
+                dconv[k] = _dw(dy, A, conv_w[k].dtype).view(C, kw, C).permute(0, 2, 1).contiguous()
+                dA = _dx(dy, s["wk"][k], kw * C)
+                dz = K.window_scatter(dA.view(1, B * frames[k], kw * C), B, frames[k - 1], frames[k], st, kw, 0)
+        grads = list(dconv) + dlnw + dlnb + [dpost_w.to(post_w.dtype), dpost_b.to(post_b.dtype), dproj_w, dproj_b.to(proj_b.dtype)]
+        return (None, None, *grads)
+
+
+class AudioPosFn(torch.autograd.Function):
+    """Frame features fp32 [B*T, d] -> x fp32 [B, T+1, d] (adapter/audio.py:190-199): 5-layer grouped conv positional encoder on
+    the un-normalised features (:57-80), `x = cat(cls, feats) + cat(cls_pos, pos)`, padded rows zeroed
+    (transformer_encoder.py:139-142).  `feats` may be the preserve_ids-gathered sequence of a student pass (:184-189: the
+    gather happens BEFORE the positional convolution).  Every convolution is a GEMM over a materialised window matrix.
+
+    Inputs after (feats, pad, meta): pos conv weights [n_pos], pos conv biases [n_pos], cls_embedding, cls_pos_embed."""
+
+    @staticmethod
+    def forward(ctx, feats, pad, meta, *ps):
+        B, T, pos_k, pos_groups, d = meta
+        n_pos = (len(ps) - 2) // 2
+        pos_w, pos_b = ps[:n_pos], ps[n_pos:2 * n_pos]
+        cls, cls_pos = ps[-2], ps[-1]
+        dev = feats.device
+        S = T + 1
+        feats = feats.to(torch.float32).contiguous()
+
+        def e(rows, n, dt=torch.bfloat16):
+            return torch.empty(rows, n, dtype=dt, device=dev)
         G = pos_groups
         cg = d // G
         pk = [bf16(pos_w[i].permute(0, 2, 1).reshape(d, pos_k * cg)) for i in range(n_pos)]     # [(g, co), (tap, ci)]
@@ -518,32 +574,26 @@ class AudioEmbedFn(torch.autograd.Function):
                 K.gemm(Xw[g], pk[i][g * cg:(g + 1) * cg], K.EPI_STORE_BF16, c[:, g * cg:(g + 1) * cg], bias=bi[g * cg:(g + 1) * cg])
             p_ins.append(p_in); cs.append(c)
             p_in = K.layernorm(c, None, None, e(B * T, d), gelu=True)
-        # ---- assemble: x[:, 1:] = feats + pos, x[:, 0] = cls + cls_pos, padded rows zeroed ----
         body = K.scale_resid_fwd(feats, p_in, None, None, torch.empty_like(feats))
         x = torch.empty(B, S, d, dtype=torch.float32, device=dev)
         x[:, 1:].copy_(body.view(B, T, d))
         K.cls_row_init(f32(cls).view(-1), f32(cls_pos).view(-1), x)
         padu = pad.to(torch.uint8).contiguous()
         K.zero_padded_rows(x, padu)
-        ctx.saved = dict(a0=a0, wk=wk, ys=ys, zs=zs, yP=yP, p_ins=p_ins, cs=cs, pk=pk, padu=padu)
+        ctx.saved = dict(p_ins=p_ins, cs=cs, pk=pk, padu=padu)
         ctx.params = ps
-        ctx.meta = (meta, frames, B)
+        ctx.meta = meta
         ctx.mark_non_differentiable(padu)
         return x, padu
 
     @staticmethod
     def backward(ctx, dxs, _dpad):
-        (spec, pos_k, pos_groups, d), frames, B = ctx.meta
+        B, T, pos_k, pos_groups, d = ctx.meta
         s = ctx.saved
         ps = ctx.params
-        n_fe = len(spec)
         n_pos = len(s["cs"])
-        conv_w, ln_w, ln_b = ps[:n_fe], ps[n_fe:2 * n_fe], ps[2 * n_fe:3 * n_fe]
-        post_w, post_b, proj_w, proj_b = ps[3 * n_fe:3 * n_fe + 4]
-        pos_w = ps[3 * n_fe + 4:3 * n_fe + 4 + n_pos]
-        pos_b = ps[3 * n_fe + 4 + n_pos:3 * n_fe + 4 + 2 * n_pos]
+        pos_w, pos_b = ps[:n_pos], ps[n_pos:2 * n_pos]
         cls, cls_pos = ps[-2], ps[-1]
-        C, T = spec[0][0], frames[-1]
         S = T + 1
         G = pos_groups
         cg = d // G
@@ -559,7 +609,6 @@ class AudioEmbedFn(torch.autograd.Function):
         dcls = K.batch_sum(dxs, g32(d), B, d, S * d)
         dbody = dxs[:, 1:].reshape(B * T, d).contiguous()                   # = d feats (direct) = d pos
         dp = K.scale_resid_bwd(dbody, None, None, None, e(B * T, d))
-        # ---- conv positional encoder, last layer first ----
         dpos_w, dpos_b = [None] * n_pos, [None] * n_pos
         for i in reversed(range(n_pos)):
             dc = K.layernorm_bwd(s["cs"][i], dp, None, None, e(B * T, d), gelu=True)
@@ -574,27 +623,5 @@ class AudioEmbedFn(torch.autograd.Function):
             dpos_w[i] = dW.view(d, pos_k, cg).permute(0, 2, 1).contiguous()
             dp = K.window_scatter(dXw, B, T, T, 1, pos_k, pos_k // 2)
         dfeats = K.scale_resid_fwd(dbody, dp, None, None, torch.empty_like(dbody))      # direct + through the pos branch
-        dproj_b = g32(d)
-        dfb = K.scale_resid_bwd(dfeats, None, None, None, e(B * T, d), dbias=dproj_b)
-        dproj_w = _dw(dfb, s["yP"], proj_w.dtype)
-        dyP = _dx(dfb, bf16(proj_w), C)
-        dpost_w, dpost_b = g32(C), g32(C)
-        dz = K.layernorm_bwd(s["zs"][-1], dyP, f32(post_w), f32(post_b), e(B * T, C), dgamma=dpost_w, dbeta=dpost_b)
-        # ---- feature extractor, last layer first ----
-        dconv, dlnw, dlnb = [None] * n_fe, [None] * n_fe, [None] * n_fe
-        for k in reversed(range(n_fe)):
-            dg, db = g32(C), g32(C)
-            dy = K.layernorm_bwd(s["ys"][k], dz, f32(ln_w[k]), f32(ln_b[k]), e(B * frames[k], C), gelu=True, dgamma=dg, dbeta=db)
-            dlnw[k], dlnb[k] = dg.to(ln_w[k].dtype), db.to(ln_b[k].dtype)
-            if k == 0:
-                dW0 = _dw(dy, s["a0"], conv_w[0].dtype)                                     # [C, 16]
-                dconv[0] = dW0[:, :spec[0][1]].reshape(C, 1, spec[0][1]).contiguous()
-            else:
-                kw, st = spec[k][1], spec[k][2]
-                A = K.window_gather(s["zs"][k - 1], B, frames[k - 1], frames[k], st, kw, 0, 1)[0]
-                dconv[k] = _dw(dy, A, conv_w[k].dtype).view(C, kw, C).permute(0, 2, 1).contiguous()
-                dA = _dx(dy, s["wk"][k], kw * C)
-                dz = K.window_scatter(dA.view(1, B * frames[k], kw * C), B, frames[k - 1], frames[k], st, kw, 0)
-        grads = list(dconv) + dlnw + dlnb + [dpost_w.to(post_w.dtype), dpost_b.to(post_b.dtype), dproj_w, dproj_b.to(proj_b.dtype)] + \
-            dpos_w + dpos_b + [dcls.view(cls.shape).to(cls.dtype), dcls.view(cls_pos.shape).to(cls_pos.dtype)]
-        return (None, None, None, *grads)
+        grads = dpos_w + dpos_b + [dcls.view(cls.shape).to(cls.dtype), dcls.view(cls_pos.shape).to(cls_pos.dtype)]
+        return (dfeats, None, None, *grads)

@@ -27,18 +27,22 @@ class _Dictionary:
 
 def from_pretrained(model_name_or_path=None, model_type="one_peace_retrieval", device="cuda", dtype="float32",
                     state_dict=None, head_type="val", layers=40, embed_dim=1536, ffn_embed_dim=6144,
-                    attention_heads=24, patch_image_size=256, vocab_size=50264, decoder=None, use_audio=None):
+                    attention_heads=24, patch_image_size=256, vocab_size=50264, decoder=None, use_audio=None, use_image=True,
+                    stage2_pretrain=False):
     """hub_interface.py:53-73.  Loads ``one-peace.pt``-style state dicts (same parameter names, strict except for
     pretraining-only keys) into the sm_100a model.  ``model_name_or_path`` may be a torch checkpoint whose
     'model' entry is the state dict (fairseq layout) or a bare state dict; alternatively pass ``state_dict``."""
     if model_type == "one_peace_pretrain":
         # models/one_peace/one_peace_pretrain.py: encoder + lightweight decoder (pretrain_vl_3B.yaml:92-168); `decoder` =
         # dict(embed_dim=, ffn_embed_dim=, layers=, attention_heads=) or None for the 4B recipe's 768 / 2048 / 2 / 12
+        # use_audio / use_image=False / stage2_pretrain: the audio-text recipe (pretrain_al_3B.yaml:91,125-127,165-167)
         cfg = OnePeacePretrainConfig()
+        cfg.stage2_pretrain = bool(stage2_pretrain)
         cfg.encoder = one_peace_4b_encoder_config(layers, embed_dim, ffn_embed_dim, attention_heads, patch_image_size)
         cfg.encoder.image_adapter.bucket_size = patch_image_size // 16
         cfg.decoder = one_peace_4b_decoder_config(patch_image_size=patch_image_size, **(decoder or {}))
         cfg.encoder.use_audio_moe = cfg.decoder.use_audio_moe = bool(use_audio)
+        cfg.encoder.use_image_moe = cfg.decoder.use_image_moe = bool(use_image)
         with torch.device(device):
             model = OnePeacePretrainModel(cfg, _Dictionary(vocab_size))
     elif model_type == "one_peace_retrieval":

@@ -90,8 +90,8 @@ class UnifyModelConfig:
 
 
 def one_peace_4b_decoder_config(embed_dim=768, ffn_embed_dim=2048, layers=2, attention_heads=12, patch_image_size=256):
-    """Decoder section of run_scripts/pretrain/pretrain_vl_3B.yaml:127-168: no LayerScale, no relative-position bias, no
-    stems (vision_encoder_type none); text + image experts."""
+    """Decoder section of run_scripts/pretrain/pretrain_vl_3B.yaml:127-168 (pretrain_al_3B.yaml:129-170 for the audio adapter:
+    no feature extractor, learned 'fixed' positions): no LayerScale, no relative-position bias, no stems."""
     c = AdjustEncDecConfig(embed_dim=embed_dim, ffn_embed_dim=ffn_embed_dim, layers=layers, attention_heads=attention_heads,
                            normalize_before=True, learned_pos=True, drop_path_rate=0.0, dropout=0.0, attention_dropout=0.0,
                            magneto_scale_attn=True, scale_attn=False, scale_fc=True, scale_heads=False, use_layer_scale=False,
@@ -99,6 +99,7 @@ def one_peace_4b_decoder_config(embed_dim=768, ffn_embed_dim=2048, layers=2, att
     c.text_adapter = TextAdapterConfig(bucket_size=256, use_attn_bias=False)
     c.image_adapter = ImageAdapterConfig(bucket_size=patch_image_size // 16, rel_bucket_size=patch_image_size // 16,
                                          vision_encoder_type="none", use_attn_bias=False)
+    c.audio_adapter = AudioAdapterConfig(feature_encoder_spec=None, abs_pos_type="fixed", use_attn_bias=False)
     return c
 
 

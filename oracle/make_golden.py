@@ -20,7 +20,46 @@ import synth  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
+def audio_pretrain():
+    """tests/golden/pretrain_audio_criterion.pt: the audio-text pretraining criterion through the reference's own model +
+    criterion files (one_peace_pretrain.py:106-179 with the audio preserve_ids gather adapter/audio.py:184-189 and the
+    'fixed'-position decoder canvas :172-181; audio_text_pretrain_loss.py:73-208)."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    crit_mod = ref_stub.ref_module("one_peace.criterions.audio_text_pretrain_loss")
+    pm = ref_stub.build_reference_audio_pretrain(**synth.PRETRAIN_AUDIO_TINY)
+    psd = synth.make_audio_pretrain_state_dict(**synth.PRETRAIN_AUDIO_TINY, seed=0)
+    missing, unexpected = pm.load_state_dict(psd, strict=False)
+    assert not unexpected and all(k.endswith(("rp_bucket", "position_idx", "version")) for k in missing), (missing, unexpected)
+    sample = synth.pretrain_audio_sample(seed=0, vocab=synth.PRETRAIN_AUDIO_TINY["vocab"])
+    crit = crit_mod.AudioTextPretrainLossCriterion(task=None, dcl_audio_alpha=1.0, dcl_al_text_alpha=0.5, dcl_al_audio_alpha=0.5,
+                                                   dcl_logit_scale=2.5, label_smoothing=0.1)
+    for q in pm.parameters():
+        q.requires_grad_(True)
+    pm.zero_grad(set_to_none=True)
+    loss, _, log = crit(pm, sample)
+    loss.backward()
+    ni = sample["net_input"]
+    kw = dict(src_audios=ni["src_audios"], audio_padding_masks=ni["audio_padding_masks"])
+    with torch.no_grad():
+        _, _, dec_a = pm(audio_preserve_ids=ni["audio_preserve_ids"], encoder_type="audio", **kw)
+        dat, _, daa = pm(src_tokens=ni["src_tokens"], text_preserve_ids=ni["al_text_preserve_ids"],
+                         audio_preserve_ids=ni["al_audio_preserve_ids"], encoder_type="al", **kw)
+        al, af = pm(encoder_type="audio", **kw)
+        ax, apad, abias = pm.encoder_wrapper.audio_adapter(ni["src_audios"], ni["audio_padding_masks"],
+                                                           preserve_ids=ni["audio_preserve_ids"])
+    torch.save({"config": synth.PRETRAIN_AUDIO_TINY, "weights_seed": 0, "sample_seed": 0,
+                "log": {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in log.items()},
+                "student_audio": dec_a, "student_al_text": dat, "student_al_audio": daa, "audio_logits": al,
+                "audio_features": af[:, :8].clone(), "adapter_student_x": ax, "adapter_student_bias": abias[0][:, :, :8, :8].clone(),
+                "grads": {n: synth.grad_summary(n, q.grad) for n, q in pm.named_parameters() if q.grad is not None}},
+               os.path.join(OUT, "pretrain_audio_criterion.pt"))
+    print("pretrain_audio_criterion.pt", os.path.getsize(os.path.join(OUT, "pretrain_audio_criterion.pt")))
+
+
 def main():
+    if sys.argv[1:] == ["audio_pretrain"]:
+        return audio_pretrain()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     cfgd = dict(embed_dim=256, ffn=1024, layers=2, heads=4)
@@ -174,6 +213,7 @@ def main():
         out[tag] = dict(p0=p0.clone().to(dt), grads=[gi.to(dt) for gi in grads], traj=traj, exp_avg=st["exp_avg"].clone(),
                         exp_avg_sq=st["exp_avg_sq"].clone(), lr=1e-2, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
     torch.save(out, os.path.join(OUT, "adam.pt"))
+    audio_pretrain()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

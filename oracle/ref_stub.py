@@ -253,3 +253,34 @@ def build_reference_pretrain(embed_dim=256, ffn=1024, layers=2, heads=4, dec_dim
     model = pre.OnePeacePretrainModel(cfg, _Dictionary(vocab))
     model.eval()
     return model
+
+
+def build_reference_audio_pretrain(embed_dim=256, ffn=1024, layers=2, heads=4, dec_dim=128, dec_ffn=256, dec_layers=2, dec_heads=2,
+                                   vocab=1000, text_bucket=256, audio_bucket=512, seed=0):
+    """Instantiate the reference OnePeacePretrainModel (text + audio experts) with the flags of pretrain_al_3B.yaml:90-170 at a
+    chosen width / depth: decoder audio adapter without feature extractor, abs_pos_type 'fixed', no attention bias."""
+    install()
+    ref_module("one_peace.models.components").has_flash = False
+    ref_module("one_peace.models.transformer.multihead_attention").has_xformers = False
+    pre = ref_module("one_peace.models.one_peace.one_peace_pretrain")
+    cfg = pre.OnePeacePretrainConfig()
+    for part, (d, f, L, h) in (("encoder", (embed_dim, ffn, layers, heads)), ("decoder", (dec_dim, dec_ffn, dec_layers, dec_heads))):
+        c = getattr(cfg, part)
+        c.embed_dim, c.ffn_embed_dim, c.layers, c.attention_heads = d, f, L, h
+        c.normalize_before, c.learned_pos = True, True
+        c.drop_path_rate = 0.0
+        c.dropout = c.attention_dropout = c.activation_dropout = 0.0
+        c.magneto_scale_attn, c.scale_attn, c.scale_fc, c.scale_heads = True, False, True, False
+        c.use_text_moe, c.use_image_moe, c.use_audio_moe = True, False, True
+        c.checkpoint_activations = False
+        enc = part == "encoder"
+        c.use_layer_scale, c.layer_scale_init_value = enc, 1e-6
+        c.text_adapter.bucket_size, c.text_adapter.use_attn_bias = text_bucket, enc
+        c.audio_adapter.bucket_size, c.audio_adapter.use_attn_bias = audio_bucket, enc
+        if not enc:
+            c.audio_adapter.feature_encoder_spec = None
+            c.audio_adapter.abs_pos_type = "fixed"
+    torch.manual_seed(seed)
+    model = pre.OnePeacePretrainModel(cfg, _Dictionary(vocab))
+    model.eval()
+    return model

@@ -512,21 +512,64 @@ def encoder_general(sd, cfg, parts, prefix="encoder_wrapper.fusion_model.", laye
     return outs
 
 
+def audio_adapter_general(sd, cfg, src_audios, padding_mask, preserve_ids=None, preserve_embed=None, mask_token=None,
+                          prefix="encoder_wrapper.audio_adapter.", use_bias=True):
+    """adapter/audio.py:136-207 incl. the preserve_ids (:184-189; features gathered BEFORE the positional convolution, padded
+    slots reading position K-1) and mask-token (:172-181; Embedding positions of the decoder variant) branches."""
+    B, S = padding_mask.shape
+    eps = cfg.ln_eps
+    bias = None
+    if use_bias:
+        bucket = sd.get(prefix + "rp_bucket")
+        if bucket is None:
+            bucket = make_token_bucket_position(cfg.audio_bucket_size)
+        bias = rel_pos_bias(sd[prefix + "rel_pos_table_list.0.weight"], bucket, S)
+    if preserve_embed is not None:
+        pos = sd[prefix + "embed_positions.weight"][:S][None].expand(B, -1, -1)
+        return canvas(preserve_ids, preserve_embed, mask_token, S) + pos, padding_mask, bias
+    x = src_audios.unsqueeze(1)
+    for i, (dim, k, st) in enumerate(cfg.feature_encoder_spec):
+        p = prefix + f"embed_audios.0.conv_layers.{i}."
+        x = F.conv1d(x, sd[p + "0.weight"], None, stride=st)
+        x = F.gelu(F.layer_norm(x.transpose(1, 2), (dim,), sd[p + "2.1.weight"], sd[p + "2.1.bias"], eps).transpose(1, 2))
+    x = x.transpose(1, 2)
+    x = F.layer_norm(x, (x.size(-1),), sd[prefix + "embed_audios.2.weight"], sd[prefix + "embed_audios.2.bias"], eps)
+    feats = F.linear(x, sd[prefix + "embed_audios.3.weight"], sd[prefix + "embed_audios.3.bias"])
+    if preserve_ids is not None:
+        padding_mask = preserve_ids.eq(-1)
+        pid = preserve_ids.masked_fill(padding_mask, preserve_ids.size(1) - 1)
+        feats = feats.gather(1, pid[:, 1:, None].expand(-1, -1, feats.size(-1)) - 1)
+        if bias is not None:
+            bias = gather_bias(bias, pid)
+    kpos = max(3, cfg.conv_pos_width // cfg.conv_pos_depth)
+    y = feats.transpose(1, 2)
+    for i in range(cfg.conv_pos_depth):
+        p = prefix + f"embed_positions.{i + 1}.0."
+        y = F.conv1d(y, sd[p + "weight"], sd[p + "bias"], padding=kpos // 2, groups=cfg.conv_pos_groups)
+        if kpos % 2 == 0:
+            y = y[:, :, :-1]
+        y = F.gelu(F.layer_norm(y.transpose(1, 2), (y.size(1),), None, None, eps).transpose(1, 2))
+    pos = torch.cat([sd[prefix + "cls_pos_embed"].expand(B, -1, -1), y.transpose(1, 2)], dim=1)
+    return torch.cat([sd[prefix + "cls_embedding"].expand(B, -1, -1), feats], dim=1) + pos, padding_mask, bias
+
+
 def pretrain_forward(sd, cfg, dec_cfg, src_tokens=None, text_preserve_ids=None, src_images=None, image_preserve_ids=None,
-                     encoder_type=None):
-    """models/one_peace/one_peace_pretrain.py:106-179 (text / image experts).  cfg / dec_cfg: OracleConfig of the encoder / decoder."""
+                     src_audios=None, audio_padding_masks=None, audio_preserve_ids=None, encoder_type=None):
+    """models/one_peace/one_peace_pretrain.py:106-179.  cfg / dec_cfg: OracleConfig of the encoder / decoder."""
     parts = []
-    if encoder_type in ("text", "vl"):
+    if encoder_type in ("text", "vl", "al"):
         parts.append(text_adapter_general(sd, cfg, src_tokens, text_preserve_ids) + ("text",))
     if encoder_type in ("image", "vl"):
         parts.append(image_adapter_general(sd, cfg, src_images, image_preserve_ids) + ("image",))
+    if encoder_type in ("audio", "al"):
+        parts.append(audio_adapter_general(sd, cfg, src_audios, audio_padding_masks, audio_preserve_ids) + ("audio",))
     feats = dict(zip([p[3] for p in parts], encoder_general(sd, cfg, parts)))
-    if text_preserve_ids is None and image_preserve_ids is None:
-        if encoder_type in ("text", "image"):
+    if text_preserve_ids is None and image_preserve_ids is None and audio_preserve_ids is None:
+        if encoder_type in ("text", "image", "audio"):
             f = feats[encoder_type]
             logits = F.normalize(F.linear(f[:, 0, :], sd[f"{encoder_type}_proj.weight"], sd[f"{encoder_type}_proj.bias"]), dim=1)
             return logits, f
-        return feats["text"], feats["image"]
+        return feats["text"], feats["image" if encoder_type == "vl" else "audio"]
     dparts = []
     if "text" in feats:
         emb = F.linear(feats["text"], sd["decoder_text_embed.weight"], sd["decoder_text_embed.bias"])
@@ -536,13 +579,44 @@ def pretrain_forward(sd, cfg, dec_cfg, src_tokens=None, text_preserve_ids=None, 
         emb = F.linear(feats["image"], sd["decoder_image_embed.weight"], sd["decoder_image_embed.bias"])
         dparts.append(image_adapter_general(sd, dec_cfg, src_images, image_preserve_ids, emb, sd["image_mask_token"],
                                             "decoder_wrapper.image_adapter.", use_bias=False) + ("image",))
+    if "audio" in feats:
+        emb = F.linear(feats["audio"], sd["decoder_audio_embed.weight"], sd["decoder_audio_embed.bias"])
+        dparts.append(audio_adapter_general(sd, dec_cfg, src_audios, audio_padding_masks, audio_preserve_ids, emb,
+                                            sd["audio_mask_token"], "decoder_wrapper.audio_adapter.", use_bias=False) + ("audio",))
     dfeats = dict(zip([p[3] for p in dparts], encoder_general(sd, dec_cfg, dparts, "decoder_wrapper.fusion_model.",
                                                               layer_scale=False)))
     out = [None, None, None]
-    for i, m in enumerate(("text", "image")):
+    for i, m in enumerate(("text", "image", "audio")):
         if m in dfeats:
             out[i] = F.linear(dfeats[m], sd[f"{m}_mask_head.weight"], sd[f"{m}_mask_head.bias"])
     return tuple(out)
+
+
+def audio_text_pretrain_loss(sd, cfg, dec_cfg, net_input, alphas=(1.0, 0.5, 0.5), dcl_logit_scale=2.5, label_smoothing=0.0):
+    """criterions/audio_text_pretrain_loss.py:73-158 (single process): the text tower is a frozen teacher (:94-95)."""
+    ni = net_input
+    tok, wav, apm = ni["src_tokens"], ni["src_audios"], ni["audio_padding_masks"]
+    kw_a = dict(src_audios=wav, audio_padding_masks=apm)
+    with torch.no_grad():
+        text_logits, _ = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, encoder_type="text")
+    audio_logits, _ = pretrain_forward(sd, cfg, dec_cfg, encoder_type="audio", **kw_a)
+    with torch.no_grad():
+        teacher_al_text, teacher_al_audio = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, encoder_type="al", **kw_a)
+    _, _, student_audio = pretrain_forward(sd, cfg, dec_cfg, audio_preserve_ids=ni["audio_preserve_ids"], encoder_type="audio", **kw_a)
+    sat, _, saa = pretrain_forward(sd, cfg, dec_cfg, src_tokens=tok, text_preserve_ids=ni["al_text_preserve_ids"],
+                                   audio_preserve_ids=ni["al_audio_preserve_ids"], encoder_type="al", **kw_a)
+    scale = logit_scale_exp(sd["logit_scale"])
+    tpm, apad = tok.eq(cfg.pad_idx), apm[:, 1:]
+    kw = dict(dcl_logit_scale=dcl_logit_scale, label_smoothing=label_smoothing)
+    terms = {
+        "dcl_audio_loss": dcl_loss(student_audio, teacher_al_audio, ni["audio_mask_indices"], apad, **kw),
+        "dcl_al_text_loss": dcl_loss(sat, teacher_al_text, ni["al_text_mask_indices"], tpm, **kw),
+        "dcl_al_audio_loss": dcl_loss(saa, teacher_al_audio, ni["al_audio_mask_indices"], apad, **kw),
+    }
+    atc, a2t, t2a = itc_loss(audio_logits, text_logits, audio_logits.detach(), text_logits.detach(), scale, 0, 0.0)
+    terms["atc_loss"], terms["a2t_ncorrect"], terms["t2a_ncorrect"] = atc, a2t, t2a
+    loss = atc + alphas[0] * terms["dcl_audio_loss"] + alphas[1] * terms["dcl_al_text_loss"] + alphas[2] * terms["dcl_al_audio_loss"]
+    return loss, terms
 
 
 def image_text_pretrain_loss(sd, cfg, dec_cfg, net_input, alphas=(0.5, 1.0, 0.5, 0.5), dcl_logit_scale=2.5, label_smoothing=0.0):

@@ -238,3 +238,81 @@ def pretrain_sample(seed=0, B=4, T=12, res=64, vocab=1000, text_mask_ratio=0.4, 
             mask = full
         ni[f"{name}_mask_indices"], ni[f"{name}_preserve_ids"] = mask, pres
     return {"id": list(range(B)), "nsentences": B, "ntokens": B, "net_input": ni}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# audio-text pretraining path (one_peace_pretrain.py + audio_text_pretrain_loss.py; pretrain_al_3B.yaml structure)
+# ----------------------------------------------------------------------------------------------------------------
+PRETRAIN_AUDIO_TINY = dict(embed_dim=256, ffn=1024, layers=2, heads=4, dec_dim=128, dec_ffn=256, dec_layers=2, dec_heads=2,
+                           vocab=1000)
+AUDIO_SPEC = ((512, 10, 5),) + ((512, 3, 2),) * 4 + ((512, 2, 2),) * 2
+
+
+def make_audio_pretrain_state_dict(embed_dim=256, ffn=1024, layers=2, heads=4, dec_dim=128, dec_ffn=256, dec_layers=2, dec_heads=2,
+                                   vocab=1000, seed=0, gamma_range=(0.5, 1.5)):
+    """Parameter names / shapes of the reference ``OnePeacePretrainModel`` with text + audio experts (pretrain_al_3B.yaml:90-170
+    at a tiny width).  Decoder: no LayerScale, no relative-position bias; its audio adapter has no feature extractor and a
+    learned Embedding(1026, d) position table (abs_pos_type 'fixed', models/adapter/audio.py:87-88)."""
+    sd = make_state_dict(embed_dim=embed_dim, ffn=ffn, layers=layers, heads=heads, modalities=("text", "audio"), seed=seed,
+                         vocab=vocab, gamma_range=gamma_range)
+    dec = make_state_dict(embed_dim=dec_dim, ffn=dec_ffn, layers=dec_layers, heads=dec_heads, modalities=("text", "audio"),
+                          seed=seed + 1000, vocab=8)
+    for k, v in dec.items():
+        if k.startswith("encoder_wrapper.fusion_model.") and ".gamma_" not in k:
+            sd[k.replace("encoder_wrapper.", "decoder_wrapper.", 1)] = v
+    for k in ("text_adapter.cls_embedding", "text_adapter.embed_positions.weight", "audio_adapter.cls_embedding",
+              "audio_adapter.mask_embedding"):
+        sd["decoder_wrapper." + k] = dec["encoder_wrapper." + k]
+    g = torch.Generator().manual_seed(seed + 2000)
+    sd["decoder_wrapper.audio_adapter.embed_positions.weight"] = _tn(g, (1026, dec_dim))
+    for m in ("text", "audio"):
+        sd[f"decoder_{m}_embed.weight"] = _tn(g, (dec_dim, embed_dim), 0.05)
+        sd[f"decoder_{m}_embed.bias"] = 0.1 * torch.randn(dec_dim, generator=g)
+        sd[f"{m}_mask_token"] = _tn(g, (1, dec_dim), 0.5)
+        sd[f"{m}_mask_head.weight"] = _tn(g, (embed_dim, dec_dim), 0.08)
+        sd[f"{m}_mask_head.bias"] = 0.1 * torch.randn(embed_dim, generator=g)
+    return sd
+
+
+def pretrain_audio_sample(seed=0, B=4, T=12, max_samples=16000, vocab=1000, audio_mask_ratio=0.55, al_text_ratio=0.4,
+                          al_audio_ratio=0.45):
+    """A collated audio-text pretraining batch shaped like data/pretrain_data/audio_text_pretrain_dataset.py:44-96 +
+    data/__init__.py:59-81: ragged clips (zero-padded waveforms, frame padding mask), ragged captions ending in eos (2), pad 1;
+    block masks replaced by seeded Bernoulli-style masks of fixed count."""
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.ones(B, T, dtype=torch.long)
+    wav = torch.zeros(B, max_samples)
+    lens = [max_samples - (b % 3) * 2400 for b in range(B)]
+
+    def frames(n):
+        for _, k, s in AUDIO_SPEC:
+            n = (n - k) // s + 1
+        return n
+    Tmax = frames(max_samples)
+    apm = torch.zeros(B, Tmax + 1, dtype=torch.bool)
+    vtm, am, vam = [], [], []
+    f = torch.zeros(1, dtype=torch.bool)
+    for b in range(B):
+        n = T - 1 - (b % 3) * 2
+        tok[b, :n] = torch.randint(4, vocab, (n,), generator=g)
+        tok[b, n] = 2
+        kv = max(1, int(n * al_text_ratio))
+        vm = torch.zeros(n, dtype=torch.bool)
+        vm[torch.randperm(n, generator=g)[:kv]] = True
+        vtm.append(torch.cat([f, vm, f]))
+        w = torch.randn(lens[b], generator=g)
+        wav[b, :lens[b]] = (w - w.mean()) / w.std()
+        Tb = frames(lens[b])
+        apm[b, Tb + 1:] = True
+        for ratio, dst in ((audio_mask_ratio, am), (al_audio_ratio, vam)):
+            m = torch.zeros(Tb, dtype=torch.bool)
+            m[torch.randperm(Tb, generator=g)[:int(Tb * ratio)]] = True
+            dst.append(torch.cat([f, m]))
+    ni = {"src_tokens": tok, "src_audios": wav, "audio_padding_masks": apm}
+    for name, rows in (("al_text", vtm), ("audio", am), ("al_audio", vam)):
+        mask, pres = _preserve(rows)
+        width = T + 1 if name.endswith("text") else Tmax + 1
+        full = torch.zeros(B, width, dtype=torch.bool)
+        full[:, :mask.shape[1]] = mask
+        ni[f"{name}_mask_indices"], ni[f"{name}_preserve_ids"] = full, pres
+    return {"id": list(range(B)), "nsentences": B, "ntokens": B, "net_input": ni}

@@ -136,3 +136,113 @@ def test_image_text_pretrain_criterion_loss_and_gradients(golden_dir):
         if cos < lim or abs(ratio - 1) > 0.05:
             bad.append((name, round(cos, 4), round(ratio, 4)))
     assert len(rows) > 130 and not bad, bad[:20]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# audio-text pretraining (pretrain_al_3B.yaml; audio_text_pretrain_loss.py:73-208)
+# ----------------------------------------------------------------------------------------------------------------
+def _audio_pretrain_model(sd, dtype="float32", stage2=False):
+    from one_peace_b200.one_peace.hub_interface import from_pretrained
+    T = synth.PRETRAIN_AUDIO_TINY
+    hub = from_pretrained(state_dict=sd, model_type="one_peace_pretrain", layers=T["layers"], embed_dim=T["embed_dim"],
+                          ffn_embed_dim=T["ffn"], attention_heads=T["heads"], vocab_size=T["vocab"], use_audio=True, use_image=False,
+                          stage2_pretrain=stage2,
+                          decoder=dict(embed_dim=T["dec_dim"], ffn_embed_dim=T["dec_ffn"], layers=T["dec_layers"],
+                                       attention_heads=T["dec_heads"]), device="cuda", dtype=dtype)
+    return hub.model
+
+
+def test_audio_pretrain_model_forward_vs_reference_golden(golden_dir):
+    """Audio student passes: frame features gathered by preserve_ids BEFORE the positional convolution (adapter/audio.py:184-189),
+    per-sample gathered bias, decoder canvas with learned 'fixed' positions (:172-181), mask head — vs the reference's output."""
+    need_gpu()
+    fx = torch.load(os.path.join(golden_dir, "pretrain_audio_criterion.pt"), weights_only=False)
+    T = synth.PRETRAIN_AUDIO_TINY
+    sd = synth.make_audio_pretrain_state_dict(**T, seed=0)
+    model = _audio_pretrain_model(sd)
+    model.eval()
+    ni = _cuda_sample(synth.pretrain_audio_sample(seed=0, vocab=T["vocab"]))["net_input"]
+    kw = dict(src_audios=ni["src_audios"], audio_padding_masks=ni["audio_padding_masks"])
+    with torch.no_grad():
+        ax, apad, _ = model.encoder_wrapper.audio_adapter(ni["src_audios"], ni["audio_padding_masks"],
+                                                          preserve_ids=ni["audio_preserve_ids"])
+        _, _, sa = model(audio_preserve_ids=ni["audio_preserve_ids"], encoder_type="audio", **kw)
+        sat, _, saa = model(src_tokens=ni["src_tokens"], text_preserve_ids=ni["al_text_preserve_ids"],
+                            audio_preserve_ids=ni["al_audio_preserve_ids"], encoder_type="al", **kw)
+        al, af = model(encoder_type="audio", **kw)
+    keep = ni["audio_preserve_ids"].ne(-1)
+    assert torch.equal(apad.bool(), ~keep)
+    assert min_cos(ax[keep], fx["adapter_student_x"][keep.cpu()]) > 0.9995
+    assert float(ax[~keep].abs().max()) == 0.0                                  # padded slots zeroed (transformer_encoder.py:139-142)
+    npad_a = ~ni["audio_padding_masks"]
+    npad_t = torch.ones(4, 13, dtype=torch.bool, device="cuda"); npad_t[:, 1:] = ~ni["src_tokens"].eq(1)
+    assert min_cos(sa[npad_a], fx["student_audio"][npad_a.cpu()]) > 0.999
+    assert min_cos(sat[npad_t], fx["student_al_text"][npad_t.cpu()]) > 0.999
+    assert min_cos(saa[npad_a], fx["student_al_audio"][npad_a.cpu()]) > 0.999
+    assert min_cos(al, fx["audio_logits"]) > 0.9995
+    assert min_cos(af[:, :8].reshape(-1, 256), fx["audio_features"].reshape(-1, 256)) > 0.999
+
+
+def test_audio_text_pretrain_criterion_loss_and_gradients(golden_dir):
+    """Full criterion (ATC + 3 DCL terms, five model calls, frozen text teacher) vs the reference's logged losses and every
+    parameter gradient vs the oracle's autograd (pinned to the reference's in tests/test_oracle_golden.py)."""
+    need_gpu()
+    from one_peace_b200.criterions.audio_text_pretrain_loss import AudioTextPretrainLossCriterion
+    fx = torch.load(os.path.join(golden_dir, "pretrain_audio_criterion.pt"), weights_only=False)
+    T = synth.PRETRAIN_AUDIO_TINY
+    sd = synth.make_audio_pretrain_state_dict(**T, seed=0)
+    model = _audio_pretrain_model(sd)
+    model.train()
+    sample = synth.pretrain_audio_sample(seed=0, vocab=T["vocab"])
+    crit = AudioTextPretrainLossCriterion(None, label_smoothing=0.1)
+    loss, ssz, log = crit(model, _cuda_sample(sample))
+    assert ssz == 1
+    errs = {}
+    for k in ("loss", "atc_loss", "dcl_audio_loss", "dcl_al_text_loss", "dcl_al_audio_loss"):
+        got, want = float(log[k]), float(fx["log"][k])
+        errs[k] = abs(got - want) / abs(want)
+    # 1e-3 relative on the total and the DCL terms; 5e-3 on the 4-sample InfoNCE term (see the image-text twin above)
+    assert all(e <= (5e-3 if k == "atc_loss" else 1e-3) for k, e in errs.items()), errs
+    assert float(log["a2t_ncorrect"]) == float(fx["log"]["a2t_ncorrect"]) and float(log["t2a_ncorrect"]) == float(fx["log"]["t2a_ncorrect"])
+    loss.backward()
+    cfg = R.OracleConfig(embed_dim=T["embed_dim"], ffn_embed_dim=T["ffn"], layers=T["layers"], attention_heads=T["heads"])
+    dcfg = R.OracleConfig(embed_dim=T["dec_dim"], ffn_embed_dim=T["dec_ffn"], layers=T["dec_layers"], attention_heads=T["dec_heads"])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    wl, _ = R.audio_text_pretrain_loss(sdg, cfg, dcfg, sample["net_input"], label_smoothing=0.1)
+    wl.backward()
+    rows, bad = [], []
+    for name, p in model.named_parameters():
+        ref = sdg[name].grad if name in sdg else None
+        if ref is None or ref.abs().max() == 0:
+            continue
+        assert p.grad is not None, f"{name}: no gradient"
+        g = p.grad.float().cpu()
+        if name == "logit_scale":
+            assert abs(g.item() - ref.item()) <= 8e-3, (g.item(), ref.item())
+            continue
+        cos = F.cosine_similarity(g.flatten(), ref.flatten(), dim=0).item()
+        ratio = (g.norm() / ref.norm()).item()
+        lim = 0.97 if "rel_pos_table" in name else 0.99
+        rows.append((cos, ratio, name))
+        if cos < lim or abs(ratio - 1) > 0.05:
+            bad.append((name, round(cos, 4), round(ratio, 4)))
+    assert len(rows) > 130 and not bad, bad[:20]
+
+
+def test_audio_stage2_pretrain_freezes_the_text_tower():
+    """stage2_pretrain (one_peace_pretrain.py:100-106): only the audio adapter, audio FFNs, audio final norm, audio_proj and the
+    decoder train; one criterion step leaves no gradient on the frozen parameters and a gradient on every trainable one."""
+    need_gpu()
+    from one_peace_b200.criterions.audio_text_pretrain_loss import AudioTextPretrainLossCriterion
+    T = synth.PRETRAIN_AUDIO_TINY
+    model = _audio_pretrain_model(synth.make_audio_pretrain_state_dict(**T, seed=0), stage2=True)
+    model.train()
+    loss, _, _ = AudioTextPretrainLossCriterion(None)(model, _cuda_sample(synth.pretrain_audio_sample(seed=1, vocab=T["vocab"])))
+    loss.backward()
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None, name
+            assert name.startswith(("encoder_wrapper.", "text_proj.")) and ".audio_" not in name and "audio_adapter" not in name, name
+        elif "mask_embedding" not in name and "decoder_wrapper.audio_adapter.cls_embedding" not in name \
+                and "decoder_wrapper.text_adapter.cls_embedding" not in name and "decoder_wrapper.text_adapter.embed_tokens" not in name:
+            assert p.grad is not None, name

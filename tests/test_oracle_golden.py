@@ -225,3 +225,51 @@ def test_pretrain_model_and_criterion_match_the_reference(golden_dir):
         torch.testing.assert_close(mine["head"], summ["head"], atol=2e-4 * summ["norm"] + 1e-7, rtol=2e-3)
         checked += 1
     assert checked > 100
+
+
+def test_audio_pretrain_model_and_criterion_match_the_reference(golden_dir):
+    """The audio twin: oracle/restated.py's audio student passes (frame features gathered by preserve_ids BEFORE the positional
+    convolution, 'fixed'-position decoder canvas) and audio_text_pretrain_loss vs the reference's one_peace_pretrain.py +
+    audio_text_pretrain_loss.py executed on the same synthetic weights and masked ragged batch (oracle/make_golden.py)."""
+    fx = torch.load(os.path.join(golden_dir, "pretrain_audio_criterion.pt"), weights_only=False)
+    T = synth.PRETRAIN_AUDIO_TINY
+    assert fx["config"] == T
+    sd = synth.make_audio_pretrain_state_dict(**T, seed=fx["weights_seed"])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    cfg = R.OracleConfig(embed_dim=T["embed_dim"], ffn_embed_dim=T["ffn"], layers=T["layers"], attention_heads=T["heads"])
+    dcfg = R.OracleConfig(embed_dim=T["dec_dim"], ffn_embed_dim=T["dec_ffn"], layers=T["dec_layers"], attention_heads=T["dec_heads"])
+    ni = synth.pretrain_audio_sample(seed=fx["sample_seed"], vocab=T["vocab"])["net_input"]
+    kw = dict(src_audios=ni["src_audios"], audio_padding_masks=ni["audio_padding_masks"])
+    with torch.no_grad():
+        ax, apad, abias = R.audio_adapter_general(sd, cfg, ni["src_audios"], ni["audio_padding_masks"], ni["audio_preserve_ids"])
+        _, _, sa = R.pretrain_forward(sd, cfg, dcfg, audio_preserve_ids=ni["audio_preserve_ids"], encoder_type="audio", **kw)
+        sat, _, saa = R.pretrain_forward(sd, cfg, dcfg, src_tokens=ni["src_tokens"], text_preserve_ids=ni["al_text_preserve_ids"],
+                                         audio_preserve_ids=ni["al_audio_preserve_ids"], encoder_type="al", **kw)
+        al, af = R.pretrain_forward(sd, cfg, dcfg, encoder_type="audio", **kw)
+    torch.testing.assert_close(ax, fx["adapter_student_x"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(abias[:, :, :8, :8], fx["adapter_student_bias"], atol=0, rtol=0)
+    assert torch.equal(apad, ni["audio_preserve_ids"].eq(-1))
+    torch.testing.assert_close(sa, fx["student_audio"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(sat, fx["student_al_text"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(saa, fx["student_al_audio"], atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(al, fx["audio_logits"], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(af[:, :8], fx["audio_features"], atol=5e-5, rtol=1e-4)
+    loss, terms = R.audio_text_pretrain_loss(sdg, cfg, dcfg, ni, label_smoothing=0.1)
+    for k in ("atc_loss", "dcl_audio_loss", "dcl_al_text_loss", "dcl_al_audio_loss"):
+        torch.testing.assert_close(terms[k].detach(), fx["log"][k], atol=2e-5, rtol=2e-5)
+    torch.testing.assert_close(loss.detach(), fx["log"]["loss"], atol=5e-5, rtol=2e-5)
+    assert float(terms["a2t_ncorrect"]) == float(fx["log"]["a2t_ncorrect"]) and float(terms["t2a_ncorrect"]) == float(fx["log"]["t2a_ncorrect"])
+    loss.backward()
+    checked = 0
+    for name, summ in fx["grads"].items():
+        g = sdg[name].grad
+        if summ["norm"] == 0.0:
+            assert g is None or float(g.norm()) < 1e-7, name
+            continue
+        assert g is not None, name
+        mine = synth.grad_summary(name, g)
+        assert mine["shape"] == summ["shape"], name
+        assert abs(mine["norm"] - summ["norm"]) <= 2e-4 * summ["norm"] + 1e-7, (name, mine["norm"], summ["norm"])
+        torch.testing.assert_close(mine["head"], summ["head"], atol=2e-4 * summ["norm"] + 1e-7, rtol=2e-3)
+        checked += 1
+    assert checked > 100
