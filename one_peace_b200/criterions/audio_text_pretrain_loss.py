@@ -52,7 +52,7 @@ class AudioTextPretrainLossCriterion(_PretrainCriterionBase):
         logging_output = {"loss": loss.data, "atc_loss": atc.data, "dcl_audio_loss": dcl_audio.data,
                           "dcl_al_text_loss": dcl_al_text.data, "dcl_al_audio_loss": dcl_al_audio.data,
                           "nsentences": sample["nsentences"], "sample_size": 1, "a2t_ncorrect": a2t_ok, "t2a_ncorrect": t2a_ok,
-                          "logit_scale_exp": logit_scale_exp}
+                          "logit_scale_exp": logit_scale_exp.data}
         return loss, 1, logging_output
 
     def compute_atc_loss(self, audio_logits, text_logits, audio_logits_all, text_logits_all, logit_scale_exp):

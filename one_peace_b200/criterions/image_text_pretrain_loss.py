@@ -100,7 +100,7 @@ class ImageTextPretrainLossCriterion(_PretrainCriterionBase):
         logging_output = {"loss": loss.data, "itc_loss": itc.data, "dcl_text_loss": dcl_text.data,
                           "dcl_image_loss": dcl_image.data, "dcl_vl_text_loss": dcl_vl_text.data,
                           "dcl_vl_image_loss": dcl_vl_image.data, "nsentences": sample["nsentences"], "sample_size": 1,
-                          "i2t_ncorrect": i2t_ok, "t2i_ncorrect": t2i_ok, "logit_scale_exp": logit_scale_exp}
+                          "i2t_ncorrect": i2t_ok, "t2i_ncorrect": t2i_ok, "logit_scale_exp": logit_scale_exp.data}
         return loss, 1, logging_output
 
     def compute_itc_loss(self, image_logits, text_logits, image_logits_all, text_logits_all, logit_scale_exp):

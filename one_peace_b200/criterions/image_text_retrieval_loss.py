@@ -88,7 +88,7 @@ class ImageTextRetrievalCriterion(FairseqCriterion):
         logit_scale_exp = model(return_logit_scale=True)
         loss, a_ok, b_ok = self.compute_itc_loss(other_logits, text_logits, other_all, text_all, logit_scale_exp)
         logging_output = {"loss": loss.data, "nsentences": sample["nsentences"], "sample_size": 1,
-                          self.a2b: a_ok, self.b2a: b_ok, "logit_scale_exp": logit_scale_exp}
+                          self.a2b: a_ok, self.b2a: b_ok, "logit_scale_exp": logit_scale_exp.data}
         return loss, 1, logging_output
 
     def encode_other(self, model, ni):

@@ -475,12 +475,21 @@ int relpos_lut_build(const float* table, const int* idx, float* lut, int L, int 
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int attention_tcp_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
+                      const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
+                      cudaStream_t stream);
 
 int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int* code_row, const int* code_col,
                      const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
                      cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || lut_max == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
   if (seg_split < 0 || seg_split >= S) return OPB_ERR_INVALID;
+  // S <= 224: the persistent kernel (attention_tcp.cu).  OPB_ATTN_PERSIST=0 keeps the one-CTA-per-tile kernel below (A/B switch).
+  const char* env_p = getenv("OPB_ATTN_PERSIST");            // read per call: tests switch it in-process
+  if (S <= 224 && !(env_p != nullptr && env_p[0] == '0')) {
+    const int rc = attention_tcp_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split, stream);
+    if (rc != OPB_ERR_UNSUPPORTED) return rc;
+  }
   const int nkb = (S + kTcK - 1) / kTcK;
   if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
   if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col) & 15) != 0)

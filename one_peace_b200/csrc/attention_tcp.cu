@@ -1,0 +1,567 @@
+// Persistent tcgen05 self-attention for sequences of up to 224 keys (vision S = 197, text, 'vl' = 214):
+//     P = softmax_fp32(q k^T + relpos_bias[h] (+ -inf on padded keys)),  o = P v            (multihead_attention.py:107-115)
+//
+// Round-2 redesign of attention_tc.cu, from measurements on B200 (scripts/microbench, profiles/r02_tmem_ld_bw.txt):
+//   * a tcgen05.ld + wait::ld round trip costs ~250 cycles per warp; TMEM itself delivers > 350 B/clk/SM.  The one-CTA-per-
+//     (b, h, q-tile) kernel paid that latency ~13 times per CTA (one 16-column chunk at a time, twice) and its 3072 short-lived
+//     CTAs paid barrier init / TMEM alloc / table staging / a cold TMA each: 113 us per layer with every pipe below 35 %.
+//   * here ONE CTA PER SM walks a contiguous range of (head, q-tile, batch) tiles.  Per tile a soft-max warp issues ALL loads of
+//     its score rows at once (one round trip), keeps them in registers (104 per thread at S = 197) and never reads them again.
+//   * the relative-position bias of a (head, q-tile) is the same for every batch element: it is kept per thread as packed half2
+//     (pre-multiplied by log2 e, -inf on keys >= S) in a thread-private shared-memory strip (16-byte loads, conflict-free
+//     pitch; 104 score + 52 bias registers would exceed the 168-register budget of a 10-warp CTA; for 208 < S <= 224 half of it
+//     stays in registers to fit the shared memory) and rebuilt from the LUT only when the CTA crosses into another (head, q-tile).
+//     Per score that leaves: unpack, fma, max, sub, ex2, add, half a cvt, half a 4-byte store.
+//   * tcgen05.ld.16x256b hands each thread 2 rows x 2 adjacent columns per 8-column block — the mma.sync accumulator layout — so
+//     the 4 threads of a row sit in one quad: row max / row sum / LayerNorm statistics are two shuffles, no shared-memory
+//     exchange, no named barriers between the soft-max warps.
+//   * everything around the soft-max is pipelined across tiles by warp 0 (TMA: Q/K/V, two stages) and warp 1 (MMA issue):
+//     S_{t+1} = Q K^T is accumulated into the other TMEM score buffer while tile t is exponentiated, O_{t-1} is read out and
+//     stored in the middle of tile t's exponentials, P V of tile t runs under tile t+1's loads and maxima.
+//
+// TMEM (512 columns): S_even @ 0, S_odd @ 224, O @ 448 (64).  Shared memory: 2 x (Q 16 KB + K) + V + P (<= 64 KB) + bias strips
+// (<= 28 KB) <= 208 KB.  (V is single-buffered: V_{t+1} is loaded when P V of tile t has finished and is needed a whole tile later.)
+#include "common.cuh"
+#include "ops.h"
+
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+namespace opb {
+
+constexpr int kPQ = 128;          // query rows per tile
+constexpr int kPD = 64;           // head dim
+constexpr int kPS1 = 224;         // TMEM column of the odd score buffer
+constexpr int kPO = 448;          // TMEM column of the output accumulator
+constexpr int kPSoftWarps = 8;    // 2 per TMEM lane quarter (16 lanes each)
+constexpr int kPThreads = 32 * kPSoftWarps;   // no separate producer warps (see the kernel)
+
+// Bias blocks (8 columns each) kept in registers; the rest lives in a thread-private shared-memory strip (2 words per block:
+// row A, row B; pitch 2 * blocks words = 4 * odd for 26 blocks: conflict-free 16-byte loads).  S <= 208: everything in the strip
+// — with 104 score + 52 bias + 32 output registers live the assembler schedules for register pressure and serialises every
+// MUFU pair (measured: 3000 clocks per tile in the exponentials alone); 208 < S <= 224 has no shared memory left for a strip.
+__host__ __device__ constexpr int tcp_reg_blocks(int nblk8) { return nblk8 <= 26 ? 0 : nblk8; }
+
+struct TcpBars {
+  uint64_t qk_full[2], s_full[2], s_free[2];
+  uint64_t v_full, p_full, pv_done, o_free;
+  uint32_t tmem_base;
+};
+
+OPB_DEVICE float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+OPB_DEVICE void tmem_ld_16x256b_x16(uint32_t taddr, uint32_t* p) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+               : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3]), "=r"(p[4]), "=r"(p[5]), "=r"(p[6]), "=r"(p[7]), "=r"(p[8]), "=r"(p[9]), "=r"(p[10]), "=r"(p[11]), "=r"(p[12]), "=r"(p[13]), "=r"(p[14]), "=r"(p[15]), "=r"(p[16]), "=r"(p[17]), "=r"(p[18]), "=r"(p[19]), "=r"(p[20]), "=r"(p[21]), "=r"(p[22]), "=r"(p[23]), "=r"(p[24]), "=r"(p[25]), "=r"(p[26]), "=r"(p[27]), "=r"(p[28]), "=r"(p[29]), "=r"(p[30]), "=r"(p[31]), "=r"(p[32]), "=r"(p[33]), "=r"(p[34]), "=r"(p[35]), "=r"(p[36]), "=r"(p[37]), "=r"(p[38]), "=r"(p[39]), "=r"(p[40]), "=r"(p[41]), "=r"(p[42]), "=r"(p[43]), "=r"(p[44]), "=r"(p[45]), "=r"(p[46]), "=r"(p[47]), "=r"(p[48]), "=r"(p[49]), "=r"(p[50]), "=r"(p[51]), "=r"(p[52]), "=r"(p[53]), "=r"(p[54]), "=r"(p[55]), "=r"(p[56]), "=r"(p[57]), "=r"(p[58]), "=r"(p[59]), "=r"(p[60]), "=r"(p[61]), "=r"(p[62]), "=r"(p[63])
+               : "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* p) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3]), "=r"(p[4]), "=r"(p[5]), "=r"(p[6]), "=r"(p[7]), "=r"(p[8]), "=r"(p[9]), "=r"(p[10]), "=r"(p[11]), "=r"(p[12]), "=r"(p[13]), "=r"(p[14]), "=r"(p[15]), "=r"(p[16]), "=r"(p[17]), "=r"(p[18]), "=r"(p[19]), "=r"(p[20]), "=r"(p[21]), "=r"(p[22]), "=r"(p[23]), "=r"(p[24]), "=r"(p[25]), "=r"(p[26]), "=r"(p[27]), "=r"(p[28]), "=r"(p[29]), "=r"(p[30]), "=r"(p[31])
+               : "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* p) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3]), "=r"(p[4]), "=r"(p[5]), "=r"(p[6]), "=r"(p[7]), "=r"(p[8]), "=r"(p[9]), "=r"(p[10]), "=r"(p[11]), "=r"(p[12]), "=r"(p[13]), "=r"(p[14]), "=r"(p[15])
+               : "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* p) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3]), "=r"(p[4]), "=r"(p[5]), "=r"(p[6]), "=r"(p[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+OPB_DEVICE void named_bar_sync_all() { asm volatile("bar.sync 1, %0;" ::"n"(32 * 8) : "memory"); }
+
+OPB_DEVICE uint64_t make_sw128_mn_desc64(uint32_t smem_addr) {     // MN-major, one 64-element MN chunk, 8-row groups 1024 B apart
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// all score columns of the warp's 16 lanes: NBLK8 blocks of 8 columns, 4 registers per block (2 rows x 2 columns)
+template <int NBLK8>
+OPB_DEVICE void load_scores(uint32_t taddr, uint32_t (&v)[4 * NBLK8]) {
+  static_assert(NBLK8 % 2 == 0 && NBLK8 <= 28, "");
+  constexpr int n16 = NBLK8 & 16, n8 = NBLK8 & 8, n4 = NBLK8 & 4, n2 = NBLK8 & 2;
+  if constexpr (n16 != 0) tmem_ld_16x256b_x16(taddr, &v[0]);
+  if constexpr (n8 != 0) tmem_ld_16x256b_x8(taddr + n16 * 8, &v[4 * n16]);
+  if constexpr (n4 != 0) tmem_ld_16x256b_x4(taddr + (n16 + n8) * 8, &v[4 * (n16 + n8)]);
+  if constexpr (n2 != 0) tmem_ld_16x256b_x2(taddr + (n16 + n8 + n4) * 8, &v[4 * (n16 + n8 + n4)]);
+}
+
+#ifdef OPB_ATTN_TIMING
+__device__ unsigned long long g_tcp_t[8];
+__device__ unsigned int g_tcp_n;
+#define TCP_T(i) do { if (tprobe) { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define TCP_T(i) do {} while (0)
+#endif
+
+struct TcpArgs {
+  const float* lut; int lut_len;
+  const int* code_row; const int* code_col;
+  const uint8_t* key_pad;
+  __nv_bfloat16* out; float* lse; float* ln_stats;
+  int B, S, H, seg_split, q_tiles;
+  long n_tiles;
+};
+
+template <int NB16, bool HAS_PAD>
+__global__ void __launch_bounds__(kPThreads, 1)
+attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const TcpArgs a) {
+  constexpr int NPAD = NB16 * 16;
+  constexpr int NBLK8 = NB16 * 2;
+  constexpr int P_ATOMS = (NPAD + 63) / 64;
+  constexpr uint32_t KV_BYTES = NPAD * 128;
+  extern __shared__ __align__(1024) uint8_t tcp_smem_raw[];
+  uint8_t* smem = tcp_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                               // 2 stages x 16 KB
+  uint8_t* sK = sQ + 2 * kPQ * 128;                 // 2 stages x NPAD rows x 128 B
+  uint8_t* sV = sK + 2 * KV_BYTES;                  // 1 stage: V of tile t+1 is requested when P V of tile t has completed and is
+                                                    // needed after the exponentials of tile t+1 (which wait for the same event)
+  uint8_t* sP = sV + KV_BYTES;                  // P_ATOMS x [128 rows][128 B]
+  constexpr int RB = tcp_reg_blocks(NBLK8), SB = NBLK8 - RB;
+  static_assert(SB % 2 == 0, "16-byte strip loads");
+  constexpr int RBA = RB > 0 ? RB : 1;
+  uint32_t* sBias = reinterpret_cast<uint32_t*>(sP + P_ATOMS * kPQ * 128);      // [256 threads][2 * SB words]
+  TcpBars* bars = reinterpret_cast<TcpBars*>(sBias + kPThreads * 2 * SB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S, H = a.H, B = a.B, D = a.H * kPD;
+  // contiguous tile range of this CTA; tile w = ((h * q_tiles + qt) * B + b)
+  const long w0 = a.n_tiles * blockIdx.x / gridDim.x, w1 = a.n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int n = static_cast<int>(w1 - w0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->qk_full[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_free[i], kPSoftWarps);
+    }
+    mbar_init(&bars->v_full, 1);
+    mbar_init(&bars->p_full, kPSoftWarps);
+    mbar_init(&bars->pv_done, 1);
+    mbar_init(&bars->o_free, kPSoftWarps);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc<1>(&bars->tmem_base, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // ---- producer duties, carried by lane 0 of warp 0 (TMA) and lane 0 of warp 1 (MMA issue) at fixed points of the tile loop.
+  // A separate producer warp would make the CTA 9-10 warps, which the register allocator treats as 12: 168 registers per
+  // thread instead of 255 — not enough for 104 score + 52 bias registers (measured: spills, serialised code, 150 us). ----
+  const bool tma_thread = threadIdx.x == 0, mma_thread = threadIdx.x == 32;
+  auto tile_coords = [&](int j, int& b, int& h, int& qt) {
+    const long w = w0 + j;
+    b = static_cast<int>(w % B);
+    const int g = static_cast<int>(w / B);
+    qt = g % a.q_tiles;
+    h = g / a.q_tiles;
+  };
+  auto load_qk = [&](int j) {                       // stage j & 1 must be free: Q K^T of tile j - 2 has completed
+    int b, h, qt;
+    tile_coords(j, b, h, qt);
+    const int st = j & 1;
+    mbar_arrive_expect_tx(&bars->qk_full[st], kPQ * 128 + KV_BYTES);
+    tma_load_2d(&tm_q, &bars->qk_full[st], sQ + st * kPQ * 128, h * kPD, b * S + qt * kPQ);
+    tma_load_2d(&tm_kv, &bars->qk_full[st], sK + st * KV_BYTES, D + h * kPD, b * S);
+  };
+  auto load_v = [&](int j) {                        // P V of tile j - 1 must have completed
+    int b, h, qt;
+    tile_coords(j, b, h, qt);
+    mbar_arrive_expect_tx(&bars->v_full, KV_BYTES);
+    tma_load_2d(&tm_kv, &bars->v_full, sV, 2 * D + h * kPD, b * S);
+  };
+  auto issue_qk = [&](int j) {                      // S buffer j & 1 must have been read (s_free) by the soft-max of tile j - 2
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kPQ, NPAD);
+    const int st = j & 1, k = j >> 1;
+    mbar_wait(&bars->qk_full[st], k & 1);
+    if (j >= 2) mbar_wait(&bars->s_free[st], (k - 1) & 1);
+    tc_fence_after();
+    const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + st * kPQ * 128));
+    const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + st * KV_BYTES));
+#pragma unroll
+    for (int kk = 0; kk < kPD / 16; ++kk) umma_bf16<1>(tmem_base + st * kPS1, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk != 0);
+    umma_commit<1>(&bars->s_full[st]);
+  };
+  auto issue_pv = [&](int j) {
+    constexpr uint32_t idesc_pv = make_idesc_bf16(kPQ, kPD) | (1u << 16);      // B (= V) MN-major
+    mbar_wait(&bars->p_full, j & 1);
+    if (j > 0) mbar_wait(&bars->o_free, (j - 1) & 1);
+    mbar_wait(&bars->v_full, j & 1);
+    tc_fence_after();
+    const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV);
+#pragma unroll
+    for (int kk = 0; kk < NB16; ++kk) {
+      // A = P (K-major): 64-key atoms of [128 rows][128 B]; +32 B per 16 keys inside an atom.  B = V (MN-major): 16 keys = 16 rows
+      const uint64_t dp = make_sw128_kmajor_desc(pbase + (kk >> 2) * (kPQ * 128) + (kk & 3) * 32);
+      const uint64_t dv = make_sw128_mn_desc64(vbase + kk * 16 * 128);
+      umma_bf16<1>(tmem_base + kPO, dp, dv, idesc_pv, kk != 0);
+    }
+    umma_commit<1>(&bars->pv_done);
+  };
+  if (tma_thread) {
+    for (int j = 0; j < 2 && j < n; ++j) load_qk(j);
+    if (n > 0) load_v(0);
+  }
+  if (mma_thread) {
+    for (int j = 0; j < 2 && j < n; ++j) issue_qk(j);
+  }
+  __syncwarp();
+
+  // ===================== soft-max (all 8 warps) =====================
+  const int qw = warp & 3;                          // TMEM lane quarter (hardware: warp id % 4)
+  const int hh = warp >> 2;                         // which 16 lanes of the quarter
+  const int q = lane & 3;                           // position inside the row's quad
+  const int rA = qw * 32 + hh * 16 + (lane >> 2);   // tile rows of this thread: rA and rA + 8
+  const uint32_t lane_addr = static_cast<uint32_t>(qw * 32 + hh * 16) << 16;
+  constexpr float kLog2e = 1.4426950408889634f;
+  // P store: row rA, 16-byte chunk (blk & 7) ^ (rA & 7), quad offset; row rA + 8 is 1024 B further (same swizzle)
+  uint8_t* const p_row = sP + rA * 128 + q * 4;
+  const uint32_t p_xor = static_cast<uint32_t>(rA & 7) << 4;
+
+  // half2 (bias * log2e) of columns 8 blk + 2 q + {0, 1} for rows rA / rA + 8; -inf for keys >= S
+  uint32_t biasA[RBA], biasB[RBA];
+  uint32_t* strip = sBias + threadIdx.x * (2 * SB);
+  // deferred epilogue state (tile it - 1)
+  float lA_prev = 0.f, lB_prev = 0.f, mA_prev = 0.f, mB_prev = 0.f;
+  int b_prev = 0, h_prev = 0, q0_prev = 0;
+
+  auto epilogue_store = [&](const uint32_t (&o)[32], int b, int h, int q0, float lA, float lB, float mA, float mB) {
+    const long rows_total = static_cast<long>(B) * S;
+#pragma unroll
+    for (int rsel = 0; rsel < 2; ++rsel) {
+      const int qrow = q0 + rA + 8 * rsel;
+      const float l = rsel ? lB : lA, m2 = rsel ? mB : mA;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      float ssum = 0.f, ssq = 0.f;
+      uint32_t pk[8];
+#pragma unroll
+      for (int blk = 0; blk < 8; ++blk) {
+        const float y0 = __uint_as_float(o[4 * blk + 2 * rsel]) * inv, y1 = __uint_as_float(o[4 * blk + 2 * rsel + 1]) * inv;
+        ssum += y0 + y1;
+        ssq = fmaf(y0, y0, fmaf(y1, y1, ssq));
+        pk[blk] = pack_bf16x2(y0, y1);
+      }
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 2); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+      if (qrow < S) {
+        uint32_t* op = reinterpret_cast<uint32_t*>(a.out + (static_cast<long>(b) * S + qrow) * D + h * kPD + 2 * q);
+#pragma unroll
+        for (int blk = 0; blk < 8; ++blk) op[4 * blk] = pk[blk];
+        if (q == 0) {
+          // log-sum-exp of the biased scores (natural log), kept for the backward pass like attention.cu does
+          if (a.lse != nullptr) a.lse[(static_cast<long>(b) * H + h) * S + qrow] = m2 * 0.6931471805599453f + __logf(l);
+          if (a.ln_stats != nullptr)
+            *reinterpret_cast<float2*>(a.ln_stats + (h * rows_total + static_cast<long>(b) * S + qrow) * 2) = make_float2(ssum, ssq);
+        }
+      }
+    }
+  };
+
+  // (head, q-tile) changed: rebuild the bias from the LUT (bias[h][i][j] = lut[h][code_row[i] - code_col[j]], block-diagonal for
+  // concatenated 'vl' / 'al' sequences, transformer_encoder.py:148-158).  The head's LUT and the column codes are first staged
+  // in the (idle) P buffer: 156 gathers per thread straight from global memory cost ~37 k clocks per rebuild through L1
+  // (measured), from shared memory a few thousand.  All 8 warps rebuild in the same iteration (tile coordinates are CTA-uniform).
+  auto rebuild_bias = [&](int h, int q0, int it) {
+    if (it > 0) mbar_wait(&bars->pv_done, (it - 1) & 1);      // P V of the previous tile still reads the P buffer
+    float* s_lut = reinterpret_cast<float*>(sP);
+    int* s_cc = reinterpret_cast<int*>(sP) + a.lut_len;
+    const float* lut_h = a.lut + static_cast<long>(h) * a.lut_len;
+    for (int i = threadIdx.x; i < a.lut_len; i += kPThreads) s_lut[i] = __ldg(lut_h + i);
+    for (int i = threadIdx.x; i < S; i += kPThreads) s_cc[i] = __ldg(a.code_col + i);
+    named_bar_sync_all();
+    int cc[2 * NBLK8];
+#pragma unroll
+    for (int e = 0; e < 2 * NBLK8; ++e) cc[e] = s_cc[min(8 * (e >> 1) + 2 * q + (e & 1), S - 1)];
+#pragma unroll
+    for (int rsel = 0; rsel < 2; ++rsel) {
+      const int qrow = min(q0 + rA + 8 * rsel, S - 1);
+      const int crow = __ldg(a.code_row + qrow);
+      const int seg_lo = (a.seg_split > 0 && qrow >= a.seg_split) ? a.seg_split : 0;
+      const int seg_hi = (a.seg_split > 0 && qrow < a.seg_split) ? a.seg_split : S;
+#pragma unroll
+      for (int blk = 0; blk < NBLK8; ++blk) {
+        float b2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 8 * blk + 2 * q + j;
+          const bool in_seg = c >= seg_lo && c < seg_hi;
+          const float bv = s_lut[in_seg ? crow - cc[2 * blk + j] : 0];
+          b2[j] = c >= S ? -INFINITY : (in_seg ? bv * kLog2e : 0.f);
+        }
+        const __half2 hb = __floats2half2_rn(b2[0], b2[1]);
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hb);
+        if (blk < RB) (rsel ? biasB : biasA)[blk] = hw;
+        else strip[2 * (blk - RB) + rsel] = hw;
+      }
+    }
+    named_bar_sync_all();                                       // nobody writes P rows before every thread has gathered
+  };
+
+  // tile coordinates, advanced incrementally (no 64-bit division per tile)
+  int b = static_cast<int>(w0 % B), g = static_cast<int>(w0 / B);
+  int qt = g % a.q_tiles, h = g / a.q_tiles;
+  bool fresh = true;
+#ifdef OPB_ATTN_TIMING
+  const bool tprobe = warp == 2 && lane == 0;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
+  for (int it = 0; it < n; ++it) {
+    const int q0 = qt * kPQ;
+    const bool warp_valid = q0 + qw * 32 + hh * 16 < S;      // warp-uniform
+    if (fresh) {
+      rebuild_bias(h, q0, it);
+      fresh = false;
+    }
+    uint32_t pmask[HAS_PAD ? (NPAD + 31) / 32 : 1];
+    if constexpr (HAS_PAD) {
+#pragma unroll
+      for (int wd = 0; wd < (NPAD + 31) / 32; ++wd) {
+        const int c = wd * 32 + lane;
+        const bool pad = c < S && a.key_pad[static_cast<long>(b) * S + c] != 0;
+        pmask[wd] = __ballot_sync(0xffffffffu, pad);
+      }
+    }
+    // ---- scores of tile `it` -> registers (one TMEM round trip) ----
+    const int sb = it & 1;
+    uint32_t v[4 * NBLK8];
+    TCP_T(0);                                      // bias rebuild / pad mask / bookkeeping
+    mbar_wait(&bars->s_full[sb], (it >> 1) & 1);
+    tc_fence_after();
+    TCP_T(1);                                      // waiting for S
+    // Q K^T of tile `it` has completed, so its Q / K stage is free: fetch tile it + 2
+    if (tma_thread && it + 2 < n) load_qk(it + 2);
+    __syncwarp();
+    if (warp_valid) {
+      load_scores<NBLK8>(tmem_base + lane_addr + sb * kPS1, v);
+      tmem_ld_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars->s_free[sb]);
+    TCP_T(2);                                      // TMEM round trip
+
+    // ---- t = s log2e + bias log2e, row maxima ----
+    float mA = -INFINITY, mB = -INFINITY;
+    if (warp_valid) {
+      uint4 sb4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int blk = 0; blk < NBLK8; ++blk) {
+        uint32_t wa, wb;
+        if (blk < RB) {
+          wa = biasA[blk]; wb = biasB[blk];
+        } else {
+          if (((blk - RB) & 1) == 0) sb4 = *reinterpret_cast<const uint4*>(strip + 2 * (blk - RB));     // 2 blocks per 16-byte load
+          wa = ((blk - RB) & 1) ? sb4.z : sb4.x;
+          wb = ((blk - RB) & 1) ? sb4.w : sb4.y;
+        }
+        const float2 ba = __half22float2(*reinterpret_cast<const __half2*>(&wa));
+        const float2 bb = __half22float2(*reinterpret_cast<const __half2*>(&wb));
+        float t0 = fmaf(__uint_as_float(v[4 * blk + 0]), kLog2e, ba.x), t1 = fmaf(__uint_as_float(v[4 * blk + 1]), kLog2e, ba.y);
+        float t2 = fmaf(__uint_as_float(v[4 * blk + 2]), kLog2e, bb.x), t3 = fmaf(__uint_as_float(v[4 * blk + 3]), kLog2e, bb.y);
+        if constexpr (HAS_PAD) {
+          const uint32_t bits = pmask[(8 * blk) >> 5] >> (((8 * blk) & 31) + 2 * q);
+          t0 = (bits & 1u) ? -INFINITY : t0; t2 = (bits & 1u) ? -INFINITY : t2;
+          t1 = (bits & 2u) ? -INFINITY : t1; t3 = (bits & 2u) ? -INFINITY : t3;
+        }
+        v[4 * blk + 0] = __float_as_uint(t0); v[4 * blk + 1] = __float_as_uint(t1);
+        v[4 * blk + 2] = __float_as_uint(t2); v[4 * blk + 3] = __float_as_uint(t3);
+        mA = fmaxf(mA, fmaxf(t0, t1));
+        mB = fmaxf(mB, fmaxf(t2, t3));
+      }
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1)); mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2)); mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+      if (mA == -INFINITY) mA = 0.f;               // every key masked: p = 0, l = 0, output row 0
+      if (mB == -INFINITY) mB = 0.f;
+    }
+    // S of tile it - 1 was read a whole tile ago and Q / K of tile it + 1 were requested then: accumulate S_{it+1} now
+    if (mma_thread && it >= 1 && it + 1 < n) issue_qk(it + 1);
+    __syncwarp();
+    TCP_T(3);                                      // t values + maxima
+    // ---- P buffer free and O_{it-1} complete once P V of tile it-1 has finished ----
+    if (it > 0) {
+      mbar_wait(&bars->pv_done, (it - 1) & 1);
+      tc_fence_after();
+      if (tma_thread) load_v(it);                        // the buffer held V of tile it - 1
+      __syncwarp();
+    }
+    TCP_T(4);                                      // waiting for P V of the previous tile
+    // ---- p = 2^(t - m), row sums, P (bf16) -> shared memory; O_{it-1} is fetched half way through ----
+    float lA = 0.f, lB = 0.f;
+    uint32_t o[32];
+    const bool prev_valid = it > 0 && q0_prev + qw * 32 + hh * 16 < S;
+    auto exp_blocks = [&](auto lo_c, auto hi_c) {
+      constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
+      // groups of 4 blocks (16 scores): all subtractions and exponentials first, then sums / packs / stores — written in this
+      // order (volatile asm) because the compiler otherwise emits sub, sub, ex2, ex2, add pairs that wait out the MUFU latency
+      // 52 times per tile
+#pragma unroll
+      for (int g0 = LO; g0 < HI; g0 += 4) {
+        float e[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int blk = g0 + (k >> 2);
+          if (blk < HI) {
+            const float x = __uint_as_float(v[4 * blk + (k & 3)]) - ((k & 2) ? mB : mA);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(x));
+          }
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int blk = g0 + k4;
+          if (blk < HI) {
+            lA += e[4 * k4] + e[4 * k4 + 1];
+            lB += e[4 * k4 + 2] + e[4 * k4 + 3];
+            uint8_t* dst = p_row + (blk >> 3) * (kPQ * 128) + ((static_cast<uint32_t>(blk & 7) << 4) ^ p_xor);
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(e[4 * k4], e[4 * k4 + 1]);
+            *reinterpret_cast<uint32_t*>(dst + 1024) = pack_bf16x2(e[4 * k4 + 2], e[4 * k4 + 3]);
+          }
+        }
+      }
+    };
+    if (warp_valid) exp_blocks(std::integral_constant<int, 0>{}, std::integral_constant<int, NBLK8 / 2>{});
+    if (prev_valid) tmem_ld_16x256b_x8(tmem_base + lane_addr + kPO, o);
+    if (warp_valid) exp_blocks(std::integral_constant<int, NBLK8 / 2>{}, std::integral_constant<int, NBLK8>{});
+    TCP_T(5);                                      // exponentials + P stores
+    if (prev_valid) tmem_ld_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&bars->p_full);
+      if (it > 0) mbar_arrive(&bars->o_free);
+    }
+    if (mma_thread) issue_pv(it);                  // waits for the other warps' P rows; the rest of warp 1 waits at the shuffles below
+    __syncwarp();
+    lA += __shfl_xor_sync(0xffffffffu, lA, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+    lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+    if (prev_valid) epilogue_store(o, b_prev, h_prev, q0_prev, lA_prev, lB_prev, mA_prev, mB_prev);
+    lA_prev = lA; lB_prev = lB; mA_prev = mA; mB_prev = mB;
+    b_prev = b; h_prev = h; q0_prev = q0;
+    if (++b == B) {                                // next tile: next batch element, or the next (head, q-tile)
+      b = 0;
+      ++g;
+      qt = g % a.q_tiles;
+      h = g / a.q_tiles;
+      fresh = true;
+    }
+    TCP_T(6);                                      // O wait + arrivals + epilogue of the previous tile
+  }
+#ifdef OPB_ATTN_TIMING
+  if (tprobe) {
+    for (int i = 0; i < 7; ++i) atomicAdd(&g_tcp_t[i], static_cast<unsigned long long>(tacc[i]));
+    atomicAdd(&g_tcp_n, static_cast<unsigned int>(n));
+  }
+#endif
+  if (n > 0) {
+    mbar_wait(&bars->pv_done, (n - 1) & 1);
+    tc_fence_after();
+    if (q0_prev + qw * 32 + hh * 16 < S) {
+      uint32_t o[32];
+      tmem_ld_16x256b_x8(tmem_base + lane_addr + kPO, o);
+      tmem_ld_wait();
+      epilogue_store(o, b_prev, h_prev, q0_prev, lA_prev, lB_prev, mA_prev, mB_prev);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+#ifdef OPB_ATTN_TIMING
+extern "C" void opb_tcp_timing_dump() {
+  unsigned long long t[8]; unsigned int n;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(t, g_tcp_t, sizeof(t)); cudaMemcpyFromSymbol(&n, g_tcp_n, sizeof(n));
+  printf("[tcp timing] tiles=%u  avg clocks per tile (warp 2): setup=%.0f wait_S=%.0f tmem_ld=%.0f tvals_max=%.0f wait_PV=%.0f exp_store=%.0f "
+         "o_wait_epilogue=%.0f\n", n, (double)t[0] / n, (double)t[1] / n, (double)t[2] / n, (double)t[3] / n, (double)t[4] / n,
+         (double)t[5] / n, (double)t[6] / n);
+}
+#endif
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+template <int NB16>
+static int launch_tcp(const CUtensorMap& tq, const CUtensorMap& tkv, const TcpArgs& a, bool has_pad, cudaStream_t stream) {
+  constexpr int NPAD = NB16 * 16;
+  constexpr size_t smem = 2ull * kPQ * 128 + 3ull * NPAD * 128 + static_cast<size_t>((NPAD + 63) / 64) * kPQ * 128 +
+                          static_cast<size_t>(kPThreads) * 2 * (2 * NB16 - tcp_reg_blocks(2 * NB16)) * 4 + sizeof(TcpBars);
+  static_assert(smem <= 227 * 1024, "");
+  static bool configured[2] = {false, false};
+  auto kern = has_pad ? attention_tcp_kernel<NB16, true> : attention_tcp_kernel<NB16, false>;
+  if (!configured[has_pad]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return OPB_ERR_CUDA;
+    configured[has_pad] = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const unsigned grid = static_cast<unsigned>(a.n_tiles < sms ? a.n_tiles : sms);
+  kern<<<grid, kPThreads, smem, stream>>>(tq, tkv, a);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// Same contract as attention_tc_fwd (ops.h); S <= 224.  Returns OPB_ERR_UNSUPPORTED for longer sequences.
+int attention_tcp_fwd(const void* qkv, const float* lut, int lut_len, const int* code_row, const int* code_col,
+                      const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
+                      cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
+  if (seg_split < 0 || seg_split >= S) return OPB_ERR_INVALID;
+  if (S > 224) return OPB_ERR_UNSUPPORTED;
+  const int nb16 = (S + 15) / 16;
+  const int inst = nb16 <= 2 ? 2 : nb16 <= 4 ? 4 : nb16 <= 6 ? 6 : nb16 <= 9 ? 9 : nb16 <= 13 ? 13 : 14;
+  // the bias rebuild stages the head's LUT + column codes in the P buffer
+  if (static_cast<size_t>(lut_len + S) * 4 > static_cast<size_t>((inst * 16 + 63) / 64) * kPQ * 128) return OPB_ERR_UNSUPPORTED;
+  const int D = H * kPD;
+  CUtensorMap tq, tkv;
+  int rc = make_tmap_bf16_2d(&tq, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, kPQ);
+  if (rc != OPB_OK) return rc;
+  rc = make_tmap_bf16_2d(&tkv, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, inst * 16);
+  if (rc != OPB_OK) return rc;
+  TcpArgs a;
+  a.lut = lut; a.lut_len = lut_len; a.code_row = code_row; a.code_col = code_col; a.key_pad = key_pad;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse; a.ln_stats = ln_stats;
+  a.B = B; a.S = S; a.H = H; a.seg_split = seg_split; a.q_tiles = (S + kPQ - 1) / kPQ;
+  a.n_tiles = static_cast<long>(B) * H * a.q_tiles;
+  const bool hp = key_pad != nullptr;
+  switch (inst) {
+    case 2: return launch_tcp<2>(tq, tkv, a, hp, stream);
+    case 4: return launch_tcp<4>(tq, tkv, a, hp, stream);
+    case 6: return launch_tcp<6>(tq, tkv, a, hp, stream);
+    case 9: return launch_tcp<9>(tq, tkv, a, hp, stream);
+    case 13: return launch_tcp<13>(tq, tkv, a, hp, stream);
+    default: return launch_tcp<14>(tq, tkv, a, hp, stream);
+  }
+}
+
+}  // namespace opb

@@ -76,8 +76,9 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 for p in self.params:
                     p.grad = None
-                loss, _, _ = criterion(model, self.static_sample)
+                loss = criterion(model, self.static_sample)[0]
                 loss.backward()
+                del loss
                 if optimizer_step is not None:      # leaves every PackCache stale, as in a real training loop
                     optimizer_step()
         torch.cuda.current_stream().wait_stream(side)

@@ -23,11 +23,19 @@ def timeit(f, n=30):
     return e0.elapsed_time(e1) / n * 1000
 t_old = timeit(lambda: K.attention(qkv, dense, None, B, S, H, out=out, ln_stats=part))
 o_old = out.clone()
+os.environ["OPB_ATTN_PERSIST"] = "0"
+t_tc = timeit(lambda: K.attention_tc(qkv, rp, None, B, S, H, out=out, ln_stats=part))
+o_tc, p_tc = out.clone(), part.clone()
+os.environ["OPB_ATTN_PERSIST"] = "1"
 t_new = timeit(lambda: K.attention_tc(qkv, rp, None, B, S, H, out=out, ln_stats=part))
-print(f"mma.sync {t_old:.1f} us | tcgen05 {t_new:.1f} us | max diff {(out.float()-o_old.float()).abs().max().item():.3e}")
+print(f"mma.sync {t_old:.1f} us | tcgen05 per-tile CTAs {t_tc:.1f} us | tcgen05 persistent {t_new:.1f} us | max diff vs mma.sync "
+      f"{(out.float()-o_old.float()).abs().max().item():.3e} vs per-tile {(out.float()-o_tc.float()).abs().max().item():.3e} "
+      f"ln_stats rel diff {((part-p_tc).abs().max()/p_tc.abs().max()).item():.3e}")
 if "timing" in os.environ.get("OPB_LIB_PATH", ""):
     import ctypes
     from one_peace_b200 import _lib
     lib = _lib.load()
     torch.cuda.synchronize()
     lib.opb_attn_timing_dump()
+    if hasattr(lib, "opb_tcp_timing_dump"):
+        lib.opb_tcp_timing_dump()

@@ -154,13 +154,13 @@ def test_graphed_train_step_equals_eager_and_tracks_weight_updates():
         losses, step = [], None
         for k, sample in enumerate(samples):
             if mode == "graph" and k == 1:                       # capture after the first optimizer step
-                step = GraphedTrainStep(model, crit, sample, params, warmup=0)
+                step = GraphedTrainStep(model, crit, sample, params, warmup=1)
             if step is not None:
-                loss, _, _ = step(sample)
+                loss = step(sample)[0]
             else:
                 for p in params:
                     p.grad = None
-                loss, _, _ = crit(model, sample)
+                loss = crit(model, sample)[0]
                 loss.backward()
             losses.append(loss.item())
             del loss                                              # no eager autograd graph may be alive at capture time
