@@ -19,8 +19,13 @@
 //     S_{t+1} = Q K^T is accumulated into the other TMEM score buffer while tile t is exponentiated, O_{t-1} is read out and
 //     stored in the middle of tile t's exponentials, P V of tile t runs under tile t+1's loads and maxima.
 //
-// TMEM (512 columns): S_even @ 0, S_odd @ 224, O @ 448 (64).  Shared memory: 2 x (Q 16 KB + K) + V + P (<= 64 KB) + bias strips
-// (<= 28 KB) <= 208 KB.  (V is single-buffered: V_{t+1} is loaded when P V of tile t has finished and is needed a whole tile later.)
+//   * P never touches shared memory: the bf16 pairs are written back over the tile's own score columns in tensor memory
+//     (tcgen05.st.16x128b lands each thread's words exactly where its score fragment came from) and P V reads its A operand
+//     from there (tcgen05.mma with a TMEM A operand).  No 64 KB P buffer, no generic->async proxy fence, and the exponentials
+//     of tile t no longer wait for P V of tile t-1.
+//
+// TMEM (512 columns): S/P_even @ 0, S/P_odd @ 224, O @ 448 (64).  Shared memory: 2 x (Q 16 KB + K + V) + bias strips (52 KB at
+// S = 197) + two heads' LUT rows <= 200 KB.
 #include "common.cuh"
 #include "ops.h"
 
@@ -38,15 +43,9 @@ constexpr int kPO = 448;          // TMEM column of the output accumulator
 constexpr int kPSoftWarps = 8;    // 2 per TMEM lane quarter (16 lanes each)
 constexpr int kPThreads = 32 * kPSoftWarps;   // no separate producer warps (see the kernel)
 
-// Bias blocks (8 columns each) kept in registers; the rest lives in a thread-private shared-memory strip (2 words per block:
-// row A, row B; pitch 2 * blocks words = 4 * odd for 26 blocks: conflict-free 16-byte loads).  S <= 208: everything in the strip
-// — with 104 score + 52 bias + 32 output registers live the assembler schedules for register pressure and serialises every
-// MUFU pair (measured: 3000 clocks per tile in the exponentials alone); 208 < S <= 224 has no shared memory left for a strip.
-__host__ __device__ constexpr int tcp_reg_blocks(int nblk8) { return nblk8 <= 26 ? 0 : nblk8; }
-
 struct TcpBars {
-  uint64_t qk_full[2], s_full[2], s_free[2];
-  uint64_t v_full, p_full, pv_done, o_free;
+  uint64_t qk_full[2], v_full[2], s_full[2];
+  uint64_t p_full, pv_done, o_free;
   uint32_t tmem_base;
 };
 
@@ -80,6 +79,44 @@ OPB_DEVICE void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* p) {
                : "memory");
 }
 
+OPB_DEVICE void tmem_st_16x128b_x16(uint32_t taddr, const uint32_t* p) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x16.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+               :
+               : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(p[8]), "r"(p[9]), "r"(p[10]), "r"(p[11]), "r"(p[12]), "r"(p[13]), "r"(p[14]), "r"(p[15]), "r"(p[16]), "r"(p[17]), "r"(p[18]), "r"(p[19]), "r"(p[20]), "r"(p[21]), "r"(p[22]), "r"(p[23]), "r"(p[24]), "r"(p[25]), "r"(p[26]), "r"(p[27]), "r"(p[28]), "r"(p[29]), "r"(p[30]), "r"(p[31]), "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t* p) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x8.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+               :
+               : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(p[8]), "r"(p[9]), "r"(p[10]), "r"(p[11]), "r"(p[12]), "r"(p[13]), "r"(p[14]), "r"(p[15]), "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t* p) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+               :
+               : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_st_16x128b_x2(uint32_t taddr, const uint32_t* p) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%4], {%0, %1, %2, %3};"
+               :
+               : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(taddr)
+               : "memory");
+}
+OPB_DEVICE void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (M = 128 rows = lanes, bf16 pairs packed in 32-bit columns) is read from
+// tensor memory (FlashAttention-4's P V form) — P never touches shared memory
+OPB_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 OPB_DEVICE void named_bar_sync_all() { asm volatile("bar.sync 1, %0;" ::"n"(32 * 8) : "memory"); }
 
 OPB_DEVICE uint64_t make_sw128_mn_desc64(uint32_t smem_addr) {     // MN-major, one 64-element MN chunk, 8-row groups 1024 B apart
@@ -111,6 +148,17 @@ __device__ unsigned int g_tcp_n;
 #define TCP_T(i) do {} while (0)
 #endif
 
+// P (bf16 pairs) of blocks [LO, LO + CNT) -> tensor memory, 2 registers per block (row A word, row B word): the 16x128b store
+// shape puts thread (row = lane / 4 (+ 8), packed column = 4 blk + lane % 4) exactly where the score fragment came from
+template <int CNT>
+OPB_DEVICE void store_p_blocks(uint32_t taddr, const uint32_t* pw) {
+  static_assert(CNT == 16 || CNT == 8 || CNT == 4 || CNT == 2, "");
+  if constexpr (CNT == 16) tmem_st_16x128b_x16(taddr, pw);
+  if constexpr (CNT == 8) tmem_st_16x128b_x8(taddr, pw);
+  if constexpr (CNT == 4) tmem_st_16x128b_x4(taddr, pw);
+  if constexpr (CNT == 2) tmem_st_16x128b_x2(taddr, pw);
+}
+
 struct TcpArgs {
   const float* lut; int lut_len;
   const int* code_row; const int* code_col;
@@ -125,37 +173,33 @@ __global__ void __launch_bounds__(kPThreads, 1)
 attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const TcpArgs a) {
   constexpr int NPAD = NB16 * 16;
   constexpr int NBLK8 = NB16 * 2;
-  constexpr int P_ATOMS = (NPAD + 63) / 64;
   constexpr uint32_t KV_BYTES = NPAD * 128;
   extern __shared__ __align__(1024) uint8_t tcp_smem_raw[];
   uint8_t* smem = tcp_smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;                               // 2 stages x 16 KB
   uint8_t* sK = sQ + 2 * kPQ * 128;                 // 2 stages x NPAD rows x 128 B
-  uint8_t* sV = sK + 2 * KV_BYTES;                  // 1 stage: V of tile t+1 is requested when P V of tile t has completed and is
-                                                    // needed after the exponentials of tile t+1 (which wait for the same event)
-  uint8_t* sP = sV + KV_BYTES;                  // P_ATOMS x [128 rows][128 B]
-  constexpr int RB = tcp_reg_blocks(NBLK8), SB = NBLK8 - RB;
-  static_assert(SB % 2 == 0, "16-byte strip loads");
-  constexpr int RBA = RB > 0 ? RB : 1;
-  uint32_t* sBias = reinterpret_cast<uint32_t*>(sP + P_ATOMS * kPQ * 128);      // [256 threads][2 * SB words]
-  TcpBars* bars = reinterpret_cast<TcpBars*>(sBias + kPThreads * 2 * SB);
+  uint8_t* sV = sK + 2 * KV_BYTES;                  // 2 stages
+  uint32_t* sBias = reinterpret_cast<uint32_t*>(sV + 2 * KV_BYTES);            // [256 threads][2 * NBLK8 words]: bias strips
+  float* sLut = reinterpret_cast<float*>(sBias + kPThreads * 2 * NBLK8);        // [2 heads][lut_len]
+  int* sCc = reinterpret_cast<int*>(sLut + 2 * a.lut_len);                      // [NPAD] column codes
+  TcpBars* bars = reinterpret_cast<TcpBars*>(sCc + NPAD);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.S, H = a.H, B = a.B, D = a.H * kPD;
   // contiguous tile range of this CTA; tile w = ((h * q_tiles + qt) * B + b)
   const long w0 = a.n_tiles * blockIdx.x / gridDim.x, w1 = a.n_tiles * (blockIdx.x + 1) / gridDim.x;
   const int n = static_cast<int>(w1 - w0);
+  const int h_first = static_cast<int>(w0 / B) / a.q_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->qk_full[i], 1);
+      mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->s_free[i], kPSoftWarps);
     }
-    mbar_init(&bars->v_full, 1);
     mbar_init(&bars->p_full, kPSoftWarps);
     mbar_init(&bars->pv_done, 1);
     mbar_init(&bars->o_free, kPSoftWarps);
@@ -165,6 +209,13 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     __syncwarp();
     tmem_alloc<1>(&bars->tmem_base, 512);
   }
+  // A CTA's <= ~21 consecutive tiles touch at most two heads (B >= 11 tiles per (head, q-tile) is checked by the host): stage
+  // their LUT rows and the column codes once; the per-(head, q-tile) bias rebuild then gathers from shared memory only.
+  for (int i = threadIdx.x; i < 2 * a.lut_len; i += kPThreads) {
+    const int hh2 = min(h_first + i / a.lut_len, H - 1);
+    sLut[i] = __ldg(a.lut + static_cast<long>(hh2) * a.lut_len + i % a.lut_len);
+  }
+  for (int i = threadIdx.x; i < NPAD; i += kPThreads) sCc[i] = __ldg(a.code_col + min(i, S - 1));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,7 +223,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   // ---- producer duties, carried by lane 0 of warp 0 (TMA) and lane 0 of warp 1 (MMA issue) at fixed points of the tile loop.
   // A separate producer warp would make the CTA 9-10 warps, which the register allocator treats as 12: 168 registers per
-  // thread instead of 255 — not enough for 104 score + 52 bias registers (measured: spills, serialised code, 150 us). ----
+  // thread instead of 255 — not enough for 104 score registers plus working set (measured: spills, serialised code, 150 us). ----
   const bool tma_thread = threadIdx.x == 0, mma_thread = threadIdx.x == 32;
   auto tile_coords = [&](int j, int& b, int& h, int& qt) {
     const long w = w0 + j;
@@ -189,17 +240,18 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tma_load_2d(&tm_q, &bars->qk_full[st], sQ + st * kPQ * 128, h * kPD, b * S + qt * kPQ);
     tma_load_2d(&tm_kv, &bars->qk_full[st], sK + st * KV_BYTES, D + h * kPD, b * S);
   };
-  auto load_v = [&](int j) {                        // P V of tile j - 1 must have completed
+  auto load_v = [&](int j) {                        // stage j & 1 must be free: P V of tile j - 2 has completed
     int b, h, qt;
     tile_coords(j, b, h, qt);
-    mbar_arrive_expect_tx(&bars->v_full, KV_BYTES);
-    tma_load_2d(&tm_kv, &bars->v_full, sV, 2 * D + h * kPD, b * S);
+    const int st = j & 1;
+    mbar_arrive_expect_tx(&bars->v_full[st], KV_BYTES);
+    tma_load_2d(&tm_kv, &bars->v_full[st], sV + st * KV_BYTES, 2 * D + h * kPD, b * S);
   };
-  auto issue_qk = [&](int j) {                      // S buffer j & 1 must have been read (s_free) by the soft-max of tile j - 2
+  auto issue_qk = [&](int j) {                      // score buffer j & 1 held P of tile j - 2: its P V must have completed
     constexpr uint32_t idesc_qk = make_idesc_bf16(kPQ, NPAD);
-    const int st = j & 1, k = j >> 1;
-    mbar_wait(&bars->qk_full[st], k & 1);
-    if (j >= 2) mbar_wait(&bars->s_free[st], (k - 1) & 1);
+    const int st = j & 1;
+    mbar_wait(&bars->qk_full[st], (j >> 1) & 1);
+    if (j >= 2) mbar_wait(&bars->pv_done, (j - 2) & 1);
     tc_fence_after();
     const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + st * kPQ * 128));
     const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + st * KV_BYTES));
@@ -209,23 +261,22 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   };
   auto issue_pv = [&](int j) {
     constexpr uint32_t idesc_pv = make_idesc_bf16(kPQ, kPD) | (1u << 16);      // B (= V) MN-major
+    const int st = j & 1;
     mbar_wait(&bars->p_full, j & 1);
     if (j > 0) mbar_wait(&bars->o_free, (j - 1) & 1);
-    mbar_wait(&bars->v_full, j & 1);
+    mbar_wait(&bars->v_full[st], (j >> 1) & 1);
     tc_fence_after();
-    const uint32_t pbase = smem_u32(sP), vbase = smem_u32(sV);
+    const uint32_t vbase = smem_u32(sV + st * KV_BYTES);
 #pragma unroll
     for (int kk = 0; kk < NB16; ++kk) {
-      // A = P (K-major): 64-key atoms of [128 rows][128 B]; +32 B per 16 keys inside an atom.  B = V (MN-major): 16 keys = 16 rows
-      const uint64_t dp = make_sw128_kmajor_desc(pbase + (kk >> 2) * (kPQ * 128) + (kk & 3) * 32);
+      // A = P from tensor memory: 16 keys = 8 packed columns of the tile's score buffer.  B = V (MN-major): 16 keys = 16 rows
       const uint64_t dv = make_sw128_mn_desc64(vbase + kk * 16 * 128);
-      umma_bf16<1>(tmem_base + kPO, dp, dv, idesc_pv, kk != 0);
+      umma_bf16_ts(tmem_base + kPO, tmem_base + st * kPS1 + 8 * kk, dv, idesc_pv, kk != 0);
     }
     umma_commit<1>(&bars->pv_done);
   };
   if (tma_thread) {
-    for (int j = 0; j < 2 && j < n; ++j) load_qk(j);
-    if (n > 0) load_v(0);
+    for (int j = 0; j < 2 && j < n; ++j) { load_qk(j); load_v(j); }
   }
   if (mma_thread) {
     for (int j = 0; j < 2 && j < n; ++j) issue_qk(j);
@@ -239,13 +290,10 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int rA = qw * 32 + hh * 16 + (lane >> 2);   // tile rows of this thread: rA and rA + 8
   const uint32_t lane_addr = static_cast<uint32_t>(qw * 32 + hh * 16) << 16;
   constexpr float kLog2e = 1.4426950408889634f;
-  // P store: row rA, 16-byte chunk (blk & 7) ^ (rA & 7), quad offset; row rA + 8 is 1024 B further (same swizzle)
-  uint8_t* const p_row = sP + rA * 128 + q * 4;
-  const uint32_t p_xor = static_cast<uint32_t>(rA & 7) << 4;
 
-  // half2 (bias * log2e) of columns 8 blk + 2 q + {0, 1} for rows rA / rA + 8; -inf for keys >= S
-  uint32_t biasA[RBA], biasB[RBA];
-  uint32_t* strip = sBias + threadIdx.x * (2 * SB);
+  // the thread's bias strip: per 8-column block two half2 words (row rA, row rA + 8) = (bias * log2e) of columns
+  // 8 blk + 2 q + {0, 1}, -inf for keys >= S.  Pitch 2 * NBLK8 words (4 * odd for 26 blocks: conflict-free 16-byte loads).
+  uint32_t* strip = sBias + threadIdx.x * (2 * NBLK8);
   // deferred epilogue state (tile it - 1)
   float lA_prev = 0.f, lB_prev = 0.f, mA_prev = 0.f, mB_prev = 0.f;
   int b_prev = 0, h_prev = 0, q0_prev = 0;
@@ -282,44 +330,45 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
   };
 
-  // (head, q-tile) changed: rebuild the bias from the LUT (bias[h][i][j] = lut[h][code_row[i] - code_col[j]], block-diagonal for
-  // concatenated 'vl' / 'al' sequences, transformer_encoder.py:148-158).  The head's LUT and the column codes are first staged
-  // in the (idle) P buffer: 156 gathers per thread straight from global memory cost ~37 k clocks per rebuild through L1
-  // (measured), from shared memory a few thousand.  All 8 warps rebuild in the same iteration (tile coordinates are CTA-uniform).
-  auto rebuild_bias = [&](int h, int q0, int it) {
-    if (it > 0) mbar_wait(&bars->pv_done, (it - 1) & 1);      // P V of the previous tile still reads the P buffer
-    float* s_lut = reinterpret_cast<float*>(sP);
-    int* s_cc = reinterpret_cast<int*>(sP) + a.lut_len;
-    const float* lut_h = a.lut + static_cast<long>(h) * a.lut_len;
-    for (int i = threadIdx.x; i < a.lut_len; i += kPThreads) s_lut[i] = __ldg(lut_h + i);
-    for (int i = threadIdx.x; i < S; i += kPThreads) s_cc[i] = __ldg(a.code_col + i);
-    named_bar_sync_all();
-    int cc[2 * NBLK8];
-#pragma unroll
-    for (int e = 0; e < 2 * NBLK8; ++e) cc[e] = s_cc[min(8 * (e >> 1) + 2 * q + (e & 1), S - 1)];
+  // (head, q-tile) changed: rebuild the thread's strip from the staged LUT (bias[h][i][j] = lut[h][code_row[i] - code_col[j]],
+  // block-diagonal for concatenated 'vl' / 'al' sequences, transformer_encoder.py:148-158).  Thread-private: no barrier.
+  auto rebuild_bias = [&](int h, int q0) {
+    const float* s_lut = sLut + (h - h_first) * a.lut_len;
 #pragma unroll
     for (int rsel = 0; rsel < 2; ++rsel) {
       const int qrow = min(q0 + rA + 8 * rsel, S - 1);
       const int crow = __ldg(a.code_row + qrow);
-      const int seg_lo = (a.seg_split > 0 && qrow >= a.seg_split) ? a.seg_split : 0;
-      const int seg_hi = (a.seg_split > 0 && qrow < a.seg_split) ? a.seg_split : S;
+      if (a.seg_split == 0) {
+        // single-modality fast path: no segment test (sCc is clamped to the last valid column beyond S)
 #pragma unroll
-      for (int blk = 0; blk < NBLK8; ++blk) {
-        float b2[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = 8 * blk + 2 * q + j;
-          const bool in_seg = c >= seg_lo && c < seg_hi;
-          const float bv = s_lut[in_seg ? crow - cc[2 * blk + j] : 0];
-          b2[j] = c >= S ? -INFINITY : (in_seg ? bv * kLog2e : 0.f);
+        for (int blk = 0; blk < NBLK8; ++blk) {
+          const int2 cc = *reinterpret_cast<const int2*>(sCc + 8 * blk + 2 * q);
+          float b0 = s_lut[crow - cc.x] * kLog2e, b1 = s_lut[crow - cc.y] * kLog2e;
+          if (8 * blk + 8 > S) {                     // warp-uniform: blocks that reach past the sequence
+            b0 = 8 * blk + 2 * q >= S ? -INFINITY : b0;
+            b1 = 8 * blk + 2 * q + 1 >= S ? -INFINITY : b1;
+          }
+          const __half2 hb = __floats2half2_rn(b0, b1);
+          strip[2 * blk + rsel] = *reinterpret_cast<const uint32_t*>(&hb);
         }
-        const __half2 hb = __floats2half2_rn(b2[0], b2[1]);
-        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hb);
-        if (blk < RB) (rsel ? biasB : biasA)[blk] = hw;
-        else strip[2 * (blk - RB) + rsel] = hw;
+      } else {
+        const int seg_lo = qrow >= a.seg_split ? a.seg_split : 0;
+        const int seg_hi = qrow < a.seg_split ? a.seg_split : S;
+#pragma unroll
+        for (int blk = 0; blk < NBLK8; ++blk) {
+          float b2[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = 8 * blk + 2 * q + j;
+            const bool in_seg = c >= seg_lo && c < seg_hi;
+            const float bv = s_lut[in_seg ? crow - sCc[c] : 0];        // clamped index + select, never a conditional load
+            b2[j] = c >= S ? -INFINITY : (in_seg ? bv * kLog2e : 0.f);
+          }
+          const __half2 hb = __floats2half2_rn(b2[0], b2[1]);
+          strip[2 * blk + rsel] = *reinterpret_cast<const uint32_t*>(&hb);
+        }
       }
     }
-    named_bar_sync_all();                                       // nobody writes P rows before every thread has gathered
   };
 
   // tile coordinates, advanced incrementally (no 64-bit division per tile)
@@ -334,7 +383,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int q0 = qt * kPQ;
     const bool warp_valid = q0 + qw * 32 + hh * 16 < S;      // warp-uniform
     if (fresh) {
-      rebuild_bias(h, q0, it);
+      rebuild_bias(h, q0);
       fresh = false;
     }
     uint32_t pmask[HAS_PAD ? (NPAD + 31) / 32 : 1];
@@ -348,6 +397,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     // ---- scores of tile `it` -> registers (one TMEM round trip) ----
     const int sb = it & 1;
+    const uint32_t s_addr = tmem_base + lane_addr + sb * kPS1;
     uint32_t v[4 * NBLK8];
     TCP_T(0);                                      // bias rebuild / pad mask / bookkeeping
     mbar_wait(&bars->s_full[sb], (it >> 1) & 1);
@@ -357,12 +407,9 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (tma_thread && it + 2 < n) load_qk(it + 2);
     __syncwarp();
     if (warp_valid) {
-      load_scores<NBLK8>(tmem_base + lane_addr + sb * kPS1, v);
+      load_scores<NBLK8>(s_addr, v);
       tmem_ld_wait();
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars->s_free[sb]);
     TCP_T(2);                                      // TMEM round trip
 
     // ---- t = s log2e + bias log2e, row maxima ----
@@ -371,14 +418,8 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       uint4 sb4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int blk = 0; blk < NBLK8; ++blk) {
-        uint32_t wa, wb;
-        if (blk < RB) {
-          wa = biasA[blk]; wb = biasB[blk];
-        } else {
-          if (((blk - RB) & 1) == 0) sb4 = *reinterpret_cast<const uint4*>(strip + 2 * (blk - RB));     // 2 blocks per 16-byte load
-          wa = ((blk - RB) & 1) ? sb4.z : sb4.x;
-          wb = ((blk - RB) & 1) ? sb4.w : sb4.y;
-        }
+        if ((blk & 1) == 0) sb4 = *reinterpret_cast<const uint4*>(strip + 2 * blk);      // 2 blocks per 16-byte load
+        const uint32_t wa = (blk & 1) ? sb4.z : sb4.x, wb = (blk & 1) ? sb4.w : sb4.y;
         const float2 ba = __half22float2(*reinterpret_cast<const __half2*>(&wa));
         const float2 bb = __half22float2(*reinterpret_cast<const __half2*>(&wb));
         float t0 = fmaf(__uint_as_float(v[4 * blk + 0]), kLog2e, ba.x), t1 = fmaf(__uint_as_float(v[4 * blk + 1]), kLog2e, ba.y);
@@ -398,57 +439,53 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       if (mA == -INFINITY) mA = 0.f;               // every key masked: p = 0, l = 0, output row 0
       if (mB == -INFINITY) mB = 0.f;
     }
-    // S of tile it - 1 was read a whole tile ago and Q / K of tile it + 1 were requested then: accumulate S_{it+1} now
+    // the score buffer of tile it + 1 held P of tile it - 1 (its P V was issued a tile ago), Q / K of tile it + 1 were
+    // requested a tile ago: accumulate S_{it+1} now
     if (mma_thread && it >= 1 && it + 1 < n) issue_qk(it + 1);
     __syncwarp();
     TCP_T(3);                                      // t values + maxima
-    // ---- P buffer free and O_{it-1} complete once P V of tile it-1 has finished ----
-    if (it > 0) {
-      mbar_wait(&bars->pv_done, (it - 1) & 1);
-      tc_fence_after();
-      if (tma_thread) load_v(it);                        // the buffer held V of tile it - 1
-      __syncwarp();
-    }
-    TCP_T(4);                                      // waiting for P V of the previous tile
-    // ---- p = 2^(t - m), row sums, P (bf16) -> shared memory; O_{it-1} is fetched half way through ----
+    // ---- p = 2^(t - m), row sums, P (bf16 pairs) -> tensor memory, over the scores of this tile (they are in registers);
+    //      O_{it-1} is fetched on the way ----
     float lA = 0.f, lB = 0.f;
     uint32_t o[32];
     const bool prev_valid = it > 0 && q0_prev + qw * 32 + hh * 16 < S;
-    auto exp_blocks = [&](auto lo_c, auto hi_c) {
-      constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
-      // groups of 4 blocks (16 scores): all subtractions and exponentials first, then sums / packs / stores — written in this
-      // order (volatile asm) because the compiler otherwise emits sub, sub, ex2, ex2, add pairs that wait out the MUFU latency
-      // 52 times per tile
+    auto exp_blocks = [&](auto lo_c, auto cnt_c) {
+      constexpr int LO = decltype(lo_c)::value, CNT = decltype(cnt_c)::value;
+      uint32_t pw[2 * CNT];
 #pragma unroll
-      for (int g0 = LO; g0 < HI; g0 += 4) {
-        float e[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int blk = g0 + (k >> 2);
-          if (blk < HI) {
-            const float x = __uint_as_float(v[4 * blk + (k & 3)]) - ((k & 2) ? mB : mA);
-            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(x));
-          }
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const int blk = g0 + k4;
-          if (blk < HI) {
-            lA += e[4 * k4] + e[4 * k4 + 1];
-            lB += e[4 * k4 + 2] + e[4 * k4 + 3];
-            uint8_t* dst = p_row + (blk >> 3) * (kPQ * 128) + ((static_cast<uint32_t>(blk & 7) << 4) ^ p_xor);
-            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(e[4 * k4], e[4 * k4 + 1]);
-            *reinterpret_cast<uint32_t*>(dst + 1024) = pack_bf16x2(e[4 * k4 + 2], e[4 * k4 + 3]);
-          }
-        }
+      for (int k = 0; k < CNT; ++k) {
+        const int blk = LO + k;
+        const float p0 = ex2_fast(__uint_as_float(v[4 * blk + 0]) - mA), p1 = ex2_fast(__uint_as_float(v[4 * blk + 1]) - mA);
+        const float p2 = ex2_fast(__uint_as_float(v[4 * blk + 2]) - mB), p3 = ex2_fast(__uint_as_float(v[4 * blk + 3]) - mB);
+        lA += p0 + p1;
+        lB += p2 + p3;
+        pw[2 * k] = pack_bf16x2(p0, p1);
+        pw[2 * k + 1] = pack_bf16x2(p2, p3);
       }
+      store_p_blocks<CNT>(s_addr + 4 * LO, pw);
     };
-    if (warp_valid) exp_blocks(std::integral_constant<int, 0>{}, std::integral_constant<int, NBLK8 / 2>{});
-    if (prev_valid) tmem_ld_16x256b_x8(tmem_base + lane_addr + kPO, o);
-    if (warp_valid) exp_blocks(std::integral_constant<int, NBLK8 / 2>{}, std::integral_constant<int, NBLK8>{});
+    constexpr int n16 = NBLK8 & 16, n8 = NBLK8 & 8, n4 = NBLK8 & 4, n2 = NBLK8 & 2;
+    if (warp_valid) {
+      if constexpr (n16 != 0) exp_blocks(std::integral_constant<int, 0>{}, std::integral_constant<int, 16>{});
+      else if constexpr (n8 != 0) exp_blocks(std::integral_constant<int, 0>{}, std::integral_constant<int, 8>{});
+    }
+    TCP_T(4);                                      // first part of the exponentials
+    if (it > 0) {
+      // O_{it-1} is complete once P V of tile it-1 has finished; its V stage is free for tile it + 1
+      mbar_wait(&bars->pv_done, (it - 1) & 1);
+      tc_fence_after();
+      if (tma_thread && it + 1 < n) load_v(it + 1);
+      __syncwarp();
+      if (prev_valid) tmem_ld_16x256b_x8(tmem_base + lane_addr + kPO, o);
+    }
+    if (warp_valid) {
+      if constexpr (n16 != 0 && n8 != 0) exp_blocks(std::integral_constant<int, n16>{}, std::integral_constant<int, 8>{});
+      if constexpr (n4 != 0) exp_blocks(std::integral_constant<int, n16 + n8>{}, std::integral_constant<int, 4>{});
+      if constexpr (n2 != 0) exp_blocks(std::integral_constant<int, n16 + n8 + n4>{}, std::integral_constant<int, 2>{});
+      tmem_st_wait_all();
+    }
     TCP_T(5);                                      // exponentials + P stores
     if (prev_valid) tmem_ld_wait();
-    fence_proxy_async();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -511,14 +548,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 template <int NB16>
 static int launch_tcp(const CUtensorMap& tq, const CUtensorMap& tkv, const TcpArgs& a, bool has_pad, cudaStream_t stream) {
   constexpr int NPAD = NB16 * 16;
-  constexpr size_t smem = 2ull * kPQ * 128 + 3ull * NPAD * 128 + static_cast<size_t>((NPAD + 63) / 64) * kPQ * 128 +
-                          static_cast<size_t>(kPThreads) * 2 * (2 * NB16 - tcp_reg_blocks(2 * NB16)) * 4 + sizeof(TcpBars);
-  static_assert(smem <= 227 * 1024, "");
-  static bool configured[2] = {false, false};
+  const size_t smem = 2ull * kPQ * 128 + 4ull * NPAD * 128 + static_cast<size_t>(kPThreads) * 4 * NB16 * 4 +
+                      2ull * a.lut_len * 4 + NPAD * 4 + sizeof(TcpBars);
+  if (smem > 227 * 1024) return OPB_ERR_UNSUPPORTED;
+  static size_t configured[2] = {0, 0};
   auto kern = has_pad ? attention_tcp_kernel<NB16, true> : attention_tcp_kernel<NB16, false>;
-  if (!configured[has_pad]) {
+  if (smem > configured[has_pad]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return OPB_ERR_CUDA;
-    configured[has_pad] = true;
+    configured[has_pad] = smem;
   }
   static int sms = 0;
   if (sms == 0) {
@@ -540,8 +577,10 @@ int attention_tcp_fwd(const void* qkv, const float* lut, int lut_len, const int*
   if (S > 224) return OPB_ERR_UNSUPPORTED;
   const int nb16 = (S + 15) / 16;
   const int inst = nb16 <= 2 ? 2 : nb16 <= 4 ? 4 : nb16 <= 6 ? 6 : nb16 <= 9 ? 9 : nb16 <= 13 ? 13 : 14;
-  // the bias rebuild stages the head's LUT + column codes in the P buffer
-  if (static_cast<size_t>(lut_len + S) * 4 > static_cast<size_t>((inst * 16 + 63) / 64) * kPQ * 128) return OPB_ERR_UNSUPPORTED;
+  // a CTA stages the LUT rows of two consecutive heads: its tile range must not span a third one, and the rows are 16-byte
+  // multiples so that the strips after them stay aligned
+  if (lut_len % 4 != 0) return OPB_ERR_INVALID;
+  if (H > 128) return OPB_ERR_UNSUPPORTED;
   const int D = H * kPD;
   CUtensorMap tq, tkv;
   int rc = make_tmap_bf16_2d(&tq, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, kPQ);
