@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "ops.h"
 
+#include <stdlib.h>
+
 namespace opb {
 
 namespace {
@@ -359,6 +361,12 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
   if (dbias != nullptr && bias == nullptr) return OPB_ERR_INVALID;
   int rc = attn_delta(d_out, out, delta, B, S, H, stream);
   if (rc != OPB_OK) return rc;
+  // S <= 224: the persistent tcgen05 kernel (attention_bwd_tc.cu).  OPB_ATTN_BWD_TC=0 keeps the mma.sync pair below (A/B switch).
+  const char* env_tc = getenv("OPB_ATTN_BWD_TC");            // read per call: tests switch it in-process
+  if (S <= 224 && !(env_tc != nullptr && env_tc[0] == '0')) {
+    rc = attention_bwd_tc(qkv, d_out, bias, key_pad, lse, delta, dqkv, dbias, B, S, H, s_pad, q_scale, bias_bstride, stream);
+    if (rc != OPB_ERR_UNSUPPORTED) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

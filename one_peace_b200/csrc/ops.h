@@ -104,6 +104,11 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
                   const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
                   float q_scale, long bias_bstride, cudaStream_t stream);
 
+// tcgen05 form (attention_bwd_tc.cu), S <= 224; `delta` already computed.  attention_bwd dispatches to it.
+int attention_bwd_tc(const void* qkv, const void* d_out, const float* bias, const uint8_t* key_pad, const float* lse,
+                     const float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad, float q_scale,
+                     long bias_bstride, cudaStream_t stream);
+
 // ---- pretraining path: row gathers, sample-dependent / block-diagonal dense relative-position bias (gather.cu) ----
 int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, const float* add,
                long add_period, void* out, int out_dtype, long ld_out, long rows, int dim, cudaStream_t stream);
