@@ -46,6 +46,11 @@ METRIC = "encoder_samples_per_sec"
 UNIT = "samples/s"
 
 
+def _policy():
+    from one_peace_b200 import autograd
+    return autograd._POLICY
+
+
 def flops_per_sample():
     """8d^2 + 6df + 4Sd per token per layer (+1.97 GFLOP hMLP stem)."""
     per_tok = 8 * D * D + 6 * D * FFN + 4 * SEQ * D
@@ -461,7 +466,9 @@ def contrastive_train_block(dev, world, rank, b=64, text_len=32, steps=3, warmup
            "collectives": "2 x all_gather (embeddings) + reduce_scatter(AVG) of the flat bf16 gradient + scalar all_reduce (norm) + "
                           "all_gather of the updated bf16 parameter shards (optim/distributed_adam.py); limiting one: the "
                           f"{round(n_params * 2 / 1e9, 2)} GB gradient reduce-scatter + parameter all-gather, not overlapped with backward",
-           "includes": "text + image encoder fwd / bwd (activation recompute), InfoNCE, grad-norm clip, sharded fused Adam"}
+           "activations": ("kept in HBM (no recompute: they fit in half of the free memory, autograd.keep_activations)"
+                           if any(_policy().values()) else "recomputed per layer in the backward (checkpoint_wrapper policy)"),
+           "includes": "text + image encoder fwd / bwd, InfoNCE, grad-norm clip, sharded fused Adam"}
     if graphed is None and os.environ.get("OPB_BENCH_GRAPH", "1") != "0":
         out["cuda_graph_error"] = graph_error
     del opt, model, params, graphed

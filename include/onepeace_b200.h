@@ -328,6 +328,23 @@ int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const
                       const float* lse, float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad,
                       float q_scale, int64_t bias_batch_stride, void* stream);
 
+/* Same product, S <= 224 only (tcgen05 kernel, csrc/attention_bwd_tc.cu), with the batch-shared relative-position bias and
+ * its gradient held as TRANSPOSED tables so that a thread's (key, query-pair) words sit at fixed offsets:
+ *   bias_t   H x 256 x 112 half2 words: bias[h][q][key] * log2(e) at [h][key][q / 2], zero for key >= S or q >= S
+ *            (opb_relpos_bias_transpose builds it from the dense table of adapter/text.py:84-91, image.py:164-171);
+ *   dbias_t  H x 256 x 224 fp32, accumulated with red.global.add.v2 over all layers that share the table, folded back into
+ *            the dense (H,S,s_pad) gradient once per stack by opb_relpos_dbias_fold.  Either may be NULL (no bias / no
+ *            bias gradient).  Returns OPB_ERR_UNSUPPORTED for S > 224. */
+int opb_attention_bwd_t(const void* qkv, const void* out, const void* d_out, const void* bias_t, const uint8_t* key_pad,
+                        const float* lse, float* delta, void* dqkv, float* dbias_t, int B, int S, int H, float q_scale,
+                        void* stream);
+int opb_relpos_bias_transpose(const float* bias, void* bias_t, int S, int s_pad, int H, void* stream);
+int opb_relpos_dbias_fold(const float* dbias_t, float* dbias, int S, int s_pad, int H, void* stream);
+/* dbias[h][i][:S] -= mean_j dbias[h][i][j]: projects the accumulated bias gradient of a single-modality stack onto the zero-row-sum
+ * subspace the exact gradient lives in (softmax is invariant to per-row logit shifts, multihead_attention.py:107-115), removing
+ * the row-coherent offset that delta = sum(dO * O) from the bf16-rounded forward output leaves (csrc/attention_bwd_tc.cu). */
+int opb_relpos_dbias_center(float* dbias, int S, int s_pad, int H, void* stream);
+
 /* out[c] (+)= sum_b in[b * ld + c]: gradients of batch-broadcast parameters (cls_embedding / pos_embed expanded over the
  * batch, adapter/image.py:239-253, audio.py:194-197). */
 int opb_batch_sum_f32(const float* in, int64_t ld, float* out, int B, int64_t n, int accumulate, void* stream);

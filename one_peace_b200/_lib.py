@@ -85,6 +85,11 @@ SIGNATURES.update({
     "opb_relpos_bias_block_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int,
                                           c_int, c_int, c_void_p]),
     "opb_relpos_bias_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+    "opb_attention_bwd_t": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_float, c_void_p]),
+    "opb_relpos_bias_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "opb_relpos_dbias_fold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "opb_relpos_dbias_center": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "opb_gemm_bf16_t": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64,
                                 c_void_p, c_int, c_void_p]),
     "opb_ln_fold": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64,

@@ -35,6 +35,28 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def keep_activations(n_layers, rows, d, ffn, device):
+    """Activation policy of the training stack.  The reference wraps every layer in checkpoint_wrapper (one_peace_pretrain.py
+    :83-91, `checkpoint_activations` in the 4B recipes) because 12,608 rows x 40 layers of layer activations (1.05 GB per layer
+    at d = 1536, ffn = 6144) do not fit an 80 GB part next to the model.  A B200 has 180 GB: when the activations of the whole
+    stack fit in half of the memory that is free right now they are KEPT and the backward skips the recompute (a quarter of
+    the step's GEMM work); otherwise each layer is recomputed while its adjoint runs, as the reference does.
+    OPB_ACTIVATIONS=keep | recompute overrides the choice (tests exercise both)."""
+    mode = __import__("os").environ.get("OPB_ACTIVATIONS", "auto")
+    if mode in ("keep", "recompute"):
+        return mode == "keep"
+    key = (n_layers, rows, d, ffn)
+    if torch.cuda.is_current_stream_capturing():               # no driver queries under capture: reuse the warm-up's decision
+        return _POLICY.get(key, False)
+    need = n_layers * rows * (22 * d + 8 * ffn + 64)          # bytes: h1 qkv att a2 o x2(fp32) h2 f | gl u u2 | lse
+    free, _ = torch.cuda.mem_get_info(device)
+    _POLICY[key] = need < free // 2
+    return _POLICY[key]
+
+
+_POLICY = {}
+
+
 def _tr(x):
     """bf16 [M, n] -> [n, pad8(M)]: K-major operand of an M-reduction GEMM (zero columns past M)."""
     M, n = x.shape
@@ -45,6 +67,8 @@ def _tr(x):
     return K.transpose_bf16(xp)
 
 
+_BWD_T = __import__("os").environ.get("OPB_ATTN_BWD_T", "1") != "0"      # 0: dense bias tables in the attention backward (A/B)
+_CENTER = __import__("os").environ.get("OPB_DBIAS_CENTER", "1") != "0"   # 0: keep the accumulated bias gradient as is (A/B)
 _DW_MN = __import__("os").environ.get("OPB_DW_MN", "1") != "0"      # 0: transposed copies + K-major GEMM (round-1 path, for A/B)
 
 
@@ -178,7 +202,7 @@ def layer_forward_train(layer, x, bias, key_pad, B, S, modality, row_scale, keep
     return x3, saved
 
 
-def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_scale):
+def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_scale, bias_t=None, dbias_t=None):
     """Adjoint of layer_forward_train.  `dx` (fp32 [M, d]) holds dL/dx_out on entry and dL/dx_in on return (in place);
     `dbias` (fp32 (H,S,S_pad) or None) accumulates the relative-position-bias gradient.  Returns the 21 parameter
     gradients in LAYER_PARAM_NAMES order, in each parameter's dtype."""
@@ -214,8 +238,12 @@ def layer_backward(layer, x, s, dx, bias, dbias, key_pad, B, S, modality, row_sc
     dlni_w, dlni_b = g(d), g(d)
     datt = K.layernorm_bwd(s["att"], da2, p["lni_w"], p["lni_b"], e(d), eps=layer.self_attn.ln.eps, dgamma=dlni_w,
                            dbeta=dlni_b)
-    dqkv = K.attention_bwd(s["qkv"], s["att"], datt, bias, key_pad, s["lse"], e(3 * d), dbias, B, S, H,
-                           layer.self_attn.scaling)
+    if bias_t is not None:       # tcgen05 kernel with transposed bias tables (S <= 224); dbias_t is folded back by the caller
+        dqkv = K.attention_bwd_t(s["qkv"], s["att"], datt, bias_t, key_pad, s["lse"], e(3 * d), dbias_t, B, S, H,
+                                 layer.self_attn.scaling)
+    else:
+        dqkv = K.attention_bwd(s["qkv"], s["att"], datt, bias, key_pad, s["lse"], e(3 * d), dbias, B, S, H,
+                               layer.self_attn.scaling)
     dbqkv = K.colsum(dqkv, g(3 * d))
     dWqkv = _dw(dqkv, s["h1"], ps[0].dtype)
     dh1 = _dx(dqkv, p["wqkv"], d)
@@ -254,7 +282,15 @@ class EncoderStackFn(torch.autograd.Function):
             return None if not lst else (lst[0] if len(lst) == 1 else lst[i])
         fused = all(r is None for r in scales) and all(l.fused_ln_supported() for l in layers) and \
             (n_bias == 0 or (fast is not None and all(f is not None for f in fast)))
-        if fused:
+        saved_all = None
+        if keep_activations(len(layers), B * S, x.shape[1], encoder.cfg.ffn_embed_dim, x.device):
+            saved_all = []
+            for i, layer in enumerate(layers):
+                xs.append(x)
+                x, saved = layer_forward_train(layer, x, pick(biases, i), key_pad, B, S, modality, scales[i], keep=True,
+                                               fast_bias=pick(fast, i))
+                saved_all.append(saved)
+        elif fused:
             from .transformer.transformer_layer import TransformerEncoderLayer
             d = x.shape[1]
             rows = x.clone()                      # the fused path updates the residual stream in place
@@ -271,7 +307,7 @@ class EncoderStackFn(torch.autograd.Function):
                 x, _ = layer_forward_train(layer, x, pick(biases, i), key_pad, B, S, modality, scales[i], keep=False,
                                            fast_bias=pick(fast, i))
         ctx.encoder, ctx.meta, ctx.n_bias = encoder, meta, n_bias
-        ctx.xs, ctx.scales, ctx.biases = xs, scales, biases
+        ctx.xs, ctx.scales, ctx.biases, ctx.saved_all = xs, scales, biases, saved_all
         return x
 
     @staticmethod
@@ -281,6 +317,12 @@ class EncoderStackFn(torch.autograd.Function):
         n_bias, biases = ctx.n_bias, ctx.biases
         dx = grad_out.to(torch.float32).contiguous().clone()
         dbiases = [torch.zeros_like(b) for b in biases]
+        # S <= 224: the tcgen05 attention backward reads the batch-shared bias from a transposed half2 table and accumulates its
+        # gradient in a transposed fp32 table shared by every layer that uses the same bias; both conversions run once per stack
+        bias_ts, dbias_ts = [], []
+        if biases and S <= K.BIAS_T_Q and all(b.dim() == 3 for b in biases) and _BWD_T:
+            bias_ts = [K.relpos_bias_transpose(b) for b in biases]
+            dbias_ts = [torch.zeros(b.shape[0], K.BIAS_T_KEYS, K.BIAS_T_Q, dtype=torch.float32, device=b.device) for b in biases]
 
         def pick(lst, i):
             return None if not lst else (lst[0] if len(lst) == 1 else lst[i])
@@ -288,10 +330,23 @@ class EncoderStackFn(torch.autograd.Function):
         for i in reversed(range(len(layers))):
             layer = layers[i]
             bias, dbias = pick(biases, i), pick(dbiases, i)
-            _, saved = layer_forward_train(layer, ctx.xs[i], bias, key_pad, B, S, modality, ctx.scales[i], keep=True,
-                                           fast_bias=pick(fast, i))
-            grads[i] = layer_backward(layer, ctx.xs[i], saved, dx, bias, dbias, key_pad, B, S, modality, ctx.scales[i])
+            if ctx.saved_all is not None:
+                saved, ctx.saved_all[i] = ctx.saved_all[i], None
+            else:
+                _, saved = layer_forward_train(layer, ctx.xs[i], bias, key_pad, B, S, modality, ctx.scales[i], keep=True,
+                                               fast_bias=pick(fast, i))
+            grads[i] = layer_backward(layer, ctx.xs[i], saved, dx, bias, dbias, key_pad, B, S, modality, ctx.scales[i],
+                                      bias_t=pick(bias_ts, i), dbias_t=pick(dbias_ts, i))
             ctx.xs[i] = None
+            del saved
+        for dt, db in zip(dbias_ts, dbiases):
+            K.relpos_dbias_fold(dt, db)
+        if _CENTER:
+            # zero-row-sum projection of the bias gradient (csrc/attention_bwd_tc.cu: relpos_dbias_center_kernel).  Padded keys carry
+            # dS = 0, so every sample's row sums to zero over all S columns and so does the batch sum.
+            for db in dbiases:
+                if db.dim() == 3:
+                    K.relpos_dbias_center(db)
         flat = [g for lg in grads for g in lg]
         return (None, None, dx, None, *dbiases, *flat)
 

@@ -15,7 +15,7 @@ of the single-modality training path (autograd.py), because every normalised ope
 import torch
 
 from . import kernels as K
-from .autograd import _dw, _dx, ffn_params, ffn_train_pack, shared_params, shared_train_pack
+from .autograd import _dw, _dx, ffn_params, ffn_train_pack, keep_activations, shared_params, shared_train_pack
 from .components import bf16, f32
 
 
@@ -172,6 +172,8 @@ class GeneralStackFn(torch.autograd.Function):
         layers = list(encoder.layers)
         x = x0.contiguous()
         xs, scales = [], []
+        keep_all = need_grad and keep_activations(len(layers), x.shape[0], x.shape[1], encoder.cfg.ffn_embed_dim, x.device)
+        saved_all = [] if keep_all else None
 
         def pick(lst, i):
             return None if not lst else (lst[0] if len(lst) == 1 else lst[i])
@@ -186,9 +188,11 @@ class GeneralStackFn(torch.autograd.Function):
             if need_grad:
                 xs.append(x)
             b = pick(biases, i)
-            x, _ = layer_forward_general(layer, x, _b3(b), key_pad, lay, rs, keep=False)
+            x, saved = layer_forward_general(layer, x, _b3(b), key_pad, lay, rs, keep=keep_all)
+            if keep_all:
+                saved_all.append(saved)
         ctx.encoder, ctx.meta, ctx.n_bias = encoder, meta, n_bias
-        ctx.xs, ctx.scales, ctx.biases = xs, scales, biases
+        ctx.xs, ctx.scales, ctx.biases, ctx.saved_all = xs, scales, biases, saved_all
         return x
 
     @staticmethod
@@ -205,9 +209,13 @@ class GeneralStackFn(torch.autograd.Function):
         for i in reversed(range(len(layers))):
             layer = layers[i]
             bias, dbias = _b3(pick(biases, i)), _b3(pick(dbiases, i))
-            _, saved = layer_forward_general(layer, ctx.xs[i], bias, key_pad, lay, ctx.scales[i], keep=True)
+            if ctx.saved_all is not None:
+                saved, ctx.saved_all[i] = ctx.saved_all[i], None
+            else:
+                _, saved = layer_forward_general(layer, ctx.xs[i], bias, key_pad, lay, ctx.scales[i], keep=True)
             shared[i], ffns[i] = layer_backward_general(layer, ctx.xs[i], saved, dx, bias, dbias, key_pad, lay, ctx.scales[i])
             ctx.xs[i] = None
+            del saved
         flat = []
         for i in range(len(layers)):
             flat += shared[i]

@@ -145,51 +145,73 @@ int adam_multi_step(const void* tensors, const int* chunk_tensor, const long* ch
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
-// ---- grad norm: stage 1 = per-chunk sum of squares, stage 2 = ordered fp64 sum + clip coefficient ----
+// ---- grad norm: stage 1 = per-CTA sum of squares, stage 2 = ordered fp64 sum + clip coefficient ----
+// CTA b owns chunks b, b + grid, b + 2 grid, ... (fixed assignment); every thread adds ITS elements of those chunks in that
+// order into one register and the CTA reduces once at the end (fixed tree), so identical gradients give bit-identical norms
+// on every rank and run (the trainer's cross-rank check, trainer.py:1245-1282).  Round-2 rework after the bench's hbm_kernels
+// line showed 0.48-0.54 of the HBM peak: the per-chunk version paid a three-deep dependent metadata chain (chunk -> tensor ->
+// pointer) and two block barriers for every 16 KB; now the next chunk's metadata is fetched before the current chunk's data
+// loads are issued and nothing synchronises inside the loop.
+struct SumsqMeta {
+  const void* g; long n; int dtype;
+};
+OPB_DEVICE SumsqMeta sumsq_meta(const AdamTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
+                                const long* __restrict__ chunk_off, int c) {
+  const AdamTensor* t = tensors + chunk_tensor[c];
+  const long off = chunk_off[c];
+  SumsqMeta m;
+  m.dtype = t->g_dtype;
+  long n = t->numel - off;
+  m.n = n > kChunk ? kChunk : n;
+  m.g = m.dtype == 0 ? static_cast<const void*>(reinterpret_cast<const float*>(t->g) + off)
+                     : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(t->g) + off);
+  return m;
+}
+
 __global__ void __launch_bounds__(kAdamThreads)
 grad_sumsq_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
                   const long* __restrict__ chunk_off, float* __restrict__ partial, int n_chunks) {
   __shared__ float red[kAdamThreads / 32];
-  // CTA b owns chunks b, b + grid, b + 2 grid, ... (fixed assignment, summed in that order -> reproducible); the finalize stage
-  // then adds <= 1184 partials instead of one per chunk (184 k for the 4B vision branch: its single block took 0.4 ms).
-  float total = 0.f;
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-  const AdamTensor t = tensors[chunk_tensor[c]];
-  const long off = chunk_off[c];
-  long n = t.numel - off;
-  if (n > kChunk) n = kChunk;
-  // 16-byte loads, all of a thread's loads of the chunk issued before the first use (the scalar version of round 1 ran
-  // at 0.43 of the HBM peak: 2-byte loads, 32 dependent iterations per chunk).  The summation order per thread and the
-  // tree below are fixed, so the result stays bit-reproducible across ranks and runs.
   float acc = 0.f;
-  if (t.g_dtype == 0) {
-    const float* g = reinterpret_cast<const float*>(t.g) + off;
-    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && n == kChunk) {
-      float4 v[kChunk / (kAdamThreads * 4)];
+  int c = blockIdx.x;
+  SumsqMeta cur = {nullptr, 0, 0};
+  if (c < n_chunks) cur = sumsq_meta(tensors, chunk_tensor, chunk_off, c);
+  while (c < n_chunks) {
+    const int cn = c + gridDim.x;
+    SumsqMeta nxt = {nullptr, 0, 0};
+    if (cn < n_chunks) nxt = sumsq_meta(tensors, chunk_tensor, chunk_off, cn);
+    const long n = cur.n;
+    if (cur.dtype == 0) {
+      const float* g = reinterpret_cast<const float*>(cur.g);
+      if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && n == kChunk) {
+        float4 v[kChunk / (kAdamThreads * 4)];
 #pragma unroll
-      for (int k = 0; k < kChunk / (kAdamThreads * 4); ++k) v[k] = reinterpret_cast<const float4*>(g)[k * kAdamThreads + threadIdx.x];
+        for (int k = 0; k < kChunk / (kAdamThreads * 4); ++k) v[k] = reinterpret_cast<const float4*>(g)[k * kAdamThreads + threadIdx.x];
 #pragma unroll
-      for (int k = 0; k < kChunk / (kAdamThreads * 4); ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
-    } else {
-      for (long i = threadIdx.x; i < n; i += kAdamThreads) acc += g[i] * g[i];
-    }
-  } else {
-    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(t.g) + off;
-    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && n == kChunk) {
-      uint4 v[kChunk / (kAdamThreads * 8)];
-#pragma unroll
-      for (int k = 0; k < kChunk / (kAdamThreads * 8); ++k) v[k] = reinterpret_cast<const uint4*>(g)[k * kAdamThreads + threadIdx.x];
-#pragma unroll
-      for (int k = 0; k < kChunk / (kAdamThreads * 8); ++k) {
-        const float2 a = unpack_bf16x2(v[k].x), b = unpack_bf16x2(v[k].y), c = unpack_bf16x2(v[k].z), d = unpack_bf16x2(v[k].w);
-        acc += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+        for (int k = 0; k < kChunk / (kAdamThreads * 4); ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+      } else {
+        for (long i = threadIdx.x; i < n; i += kAdamThreads) acc += g[i] * g[i];
       }
     } else {
-      for (long i = threadIdx.x; i < n; i += kAdamThreads) {
-        const float x = __bfloat162float(g[i]);
-        acc += x * x;
+      const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(cur.g);
+      if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && n == kChunk) {
+        uint4 v[kChunk / (kAdamThreads * 8)];
+#pragma unroll
+        for (int k = 0; k < kChunk / (kAdamThreads * 8); ++k) v[k] = reinterpret_cast<const uint4*>(g)[k * kAdamThreads + threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < kChunk / (kAdamThreads * 8); ++k) {
+          const float2 a = unpack_bf16x2(v[k].x), b = unpack_bf16x2(v[k].y), c2 = unpack_bf16x2(v[k].z), d = unpack_bf16x2(v[k].w);
+          acc += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c2.x * c2.x + c2.y * c2.y + d.x * d.x + d.y * d.y;
+        }
+      } else {
+        for (long i = threadIdx.x; i < n; i += kAdamThreads) {
+          const float x = __bfloat162float(g[i]);
+          acc += x * x;
+        }
       }
     }
+    cur = nxt;
+    c = cn;
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -197,11 +219,8 @@ grad_sumsq_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict_
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < kAdamThreads / 32; ++w) s += red[w];
-    total += s;
+    partial[blockIdx.x] = s;
   }
-  __syncthreads();
-  }
-  if (threadIdx.x == 0) partial[blockIdx.x] = total;
 }
 
 // out[0] = multiply_factor * ||g||_2 ; out[1] = grad_scale = multiply_factor * clamp(max_norm / (norm + 1e-6), max=1)

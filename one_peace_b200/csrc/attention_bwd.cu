@@ -364,7 +364,7 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
   // S <= 224: the persistent tcgen05 kernel (attention_bwd_tc.cu).  OPB_ATTN_BWD_TC=0 keeps the mma.sync pair below (A/B switch).
   const char* env_tc = getenv("OPB_ATTN_BWD_TC");            // read per call: tests switch it in-process
   if (S <= 224 && !(env_tc != nullptr && env_tc[0] == '0')) {
-    rc = attention_bwd_tc(qkv, d_out, bias, key_pad, lse, delta, dqkv, dbias, B, S, H, s_pad, q_scale, bias_bstride, stream);
+    rc = attention_bwd_tc(qkv, d_out, bias, key_pad, lse, delta, dqkv, dbias, B, S, H, s_pad, q_scale, bias_bstride, nullptr, nullptr, stream);
     if (rc != OPB_ERR_UNSUPPORTED) return rc;
   }
   static bool configured = false;

@@ -45,6 +45,13 @@ constexpr int kSoftWarps = 8;
 constexpr int kThreads = 32 * (kSoftWarps + 2);
 // TMEM columns
 constexpr int kColST = 0, kColDPT = 112, kColDV = 224, kColDK = 288, kColDQ = 352;     // dQ: two 64-column accumulators
+// transposed bias tables: [H][kTKeys][kTQ] — key rows, query columns, zero-padded, so that a thread's (key, query pair) words
+// sit at compile-time offsets from one pointer per sub-step (no per-element address arithmetic, clamps or predicates)
+constexpr int kTKeys = 256, kTQ = 224;
+
+OPB_DEVICE void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 
 struct BwdBars {
   uint64_t qdo_full[2], qdo_empty[2], kv_full[2], kv_empty[2];
@@ -54,6 +61,7 @@ struct BwdBars {
 
 struct BwdArgs {
   const float* bias; float* dbias; long bias_bstride; int s_pad;
+  const uint32_t* bias_t; float* dbias_t;      // transposed tables (kTKeys x kTQ per head), see relpos_bias_transpose
   const uint8_t* key_pad;
   const float* lse; const float* delta;
   __nv_bfloat16* dqkv;
@@ -248,7 +256,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         for (int qh = 0; qh < n_qh; ++qh, ++sub) {
           // ---- bias of this sub-tile, transposed gather (prefetched under the tensor core's S^T / dP^T) ----
           uint32_t bw[2 * NBLK8];
-          if (a.bias != nullptr && warp_valid) {
+          if (a.bias_t != nullptr && warp_valid) {
+            // transposed half2 table (x log2 e, zeros past S): one 4-byte load per (row, block) at immediate offsets
+            const uint32_t* bt = a.bias_t + (static_cast<long>(h) * kTKeys + key_lo) * (kTQ / 2) + (qh * QH) / 2 + t4;
+#pragma unroll
+            for (int blk = 0; blk < NBLK8; ++blk) {
+              bw[2 * blk] = __ldg(bt + 4 * blk);
+              bw[2 * blk + 1] = __ldg(bt + 8 * (kTQ / 2) + 4 * blk);
+            }
+          } else if (a.bias != nullptr && warp_valid) {
             const float* bp = a.bias + boff;
 #pragma unroll
             for (int blk = 0; blk < NBLK8; ++blk) {
@@ -275,6 +291,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             const float* dlq = dls + qh * QH + 2 * t4;
             float* db_lo = nullptr;
             float* db_hi = nullptr;
+            float* dt_lo = nullptr;
+            if (a.dbias_t != nullptr) dt_lo = a.dbias_t + (static_cast<long>(h) * kTKeys + key_lo) * kTQ + qh * QH + 2 * t4;
             if (a.dbias != nullptr) {
               db_lo = a.dbias + boff + kc_lo;
               db_hi = a.dbias + boff + kc_hi;
@@ -299,7 +317,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 p2 = dead_hi ? 0.f : p2; p3 = dead_hi ? 0.f : p3;
                 const float d0 = p0 * (__uint_as_float(dp[4 * blk + 0]) - dl.x), d1 = p1 * (__uint_as_float(dp[4 * blk + 1]) - dl.y);
                 const float d2 = p2 * (__uint_as_float(dp[4 * blk + 2]) - dl.x), d3 = p3 * (__uint_as_float(dp[4 * blk + 3]) - dl.y);
-                if (a.dbias != nullptr) {
+                if (a.dbias_t != nullptr) {
+                  // dead rows / columns hold ds = 0 and land in the zero padding: only whole blocks past S are skipped
+                  if (qh * QH + 8 * blk < S) {
+                    if (!dead_lo) red_add_v2(dt_lo + 8 * blk, d0, d1);
+                    if (!dead_hi) red_add_v2(dt_lo + 8 * kTQ + 8 * blk, d2, d3);
+                  }
+                } else if (a.dbias != nullptr) {
                   const int q0 = qh * QH + 8 * blk + 2 * t4;
                   const long o0 = static_cast<long>(q0) * a.s_pad, o1 = o0 + a.s_pad;
                   const bool live0 = q0 < S && l2.x < INFINITY, live1 = q0 + 1 < S && l2.y < INFINITY;
@@ -390,6 +414,70 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   }
 }
 
+// biasT[h][key][q / 2] = half2(bias[h][q][key], bias[h][q + 1][key]) * log2 e, zero for key >= S or q >= S.  One CTA per
+// (32 keys, head): a 32 x 32 shared-memory tile turns the key-contiguous reads into query-contiguous writes.
+__global__ void __launch_bounds__(256)
+relpos_bias_transpose_kernel(const float* __restrict__ bias, uint32_t* __restrict__ bias_t, int S, int s_pad) {
+  __shared__ float tile[32][33];
+  const int h = blockIdx.y, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int q0 = 0; q0 < kTQ; q0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = q0 + ty + 8 * i, key = k0 + tx;
+      tile[ty + 8 * i][tx] = (q < S && key < S) ? bias[(static_cast<long>(h) * S + q) * s_pad + key] * 1.4426950408889634f : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int kk = (threadIdx.x >> 4) + 16 * i, w = threadIdx.x & 15;          // key row inside the tile, query pair
+      const __half2 hv = __floats2half2_rn(tile[2 * w][kk], tile[2 * w + 1][kk]);
+      bias_t[(static_cast<long>(h) * kTKeys + k0 + kk) * (kTQ / 2) + q0 / 2 + w] = *reinterpret_cast<const uint32_t*>(&hv);
+    }
+    __syncthreads();
+  }
+}
+
+// dbias[h][q][key] += dbiasT[h][key][q]   (q, key < S)
+__global__ void __launch_bounds__(256)
+relpos_dbias_fold_kernel(const float* __restrict__ dbias_t, float* __restrict__ dbias, int S, int s_pad) {
+  __shared__ float tile[32][33];
+  const int h = blockIdx.y, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int q0 = 0; q0 < S; q0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = ty + 8 * i;
+      tile[kk][tx] = dbias_t[(static_cast<long>(h) * kTKeys + k0 + kk) * kTQ + min(q0 + tx, kTQ - 1)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = q0 + ty + 8 * i, key = k0 + tx;
+      if (q < S && key < S) dbias[(static_cast<long>(h) * S + q) * s_pad + key] += tile[tx][ty + 8 * i];
+    }
+    __syncthreads();
+  }
+}
+
+// dbias[h][i][:S] -= mean_j dbias[h][i][j].  Softmax is invariant to a per-row shift of its logits, so the exact bias gradient
+// has zero row sums; the accumulated one carries a small per-row offset, because delta_i = sum_d dO_id O_id is taken from the
+// bf16-rounded forward output (as flash-attention does) while P is recomputed in fp32.  That offset is harmless per element
+// (~1e-4 of the row's scale) but it is COHERENT along a row, and a table entry shared by a whole row — the CLS -> token bucket
+// of adapter/image.py:164-171, whose exact value is a 196-term cancellation down to -dS[0][0] — inherits all of it
+// (measured: 87 % error on that one entry through InfoNCE, cosine 0.93 of the table gradient; 0.99+ with the projection).
+// One warp per (head, query row).
+__global__ void __launch_bounds__(256)
+relpos_dbias_center_kernel(float* __restrict__ dbias, int S, int s_pad, int rows) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* p = dbias + static_cast<long>(row) * s_pad;
+  float s = 0.f;
+  for (int j = lane; j < S; j += 32) s += p[j];
+  s = warp_sum(s) / S;
+  for (int j = lane; j < S; j += 32) p[j] -= s;
+}
+
 template <int QH>
 int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tdo, const BwdArgs& a, cudaStream_t stream) {
   const size_t qdo = (static_cast<size_t>(a.n_qh) * QH * 128 + 1023) & ~static_cast<size_t>(1023);
@@ -414,14 +502,38 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap&
 
 }  // namespace
 
+// bias fp32 (H, S, s_pad) -> bias_t: H x 256 x 112 half2 words (scaled by log2 e, zero-padded)
+int relpos_bias_transpose(const float* bias, void* bias_t, int S, int s_pad, int H, cudaStream_t stream) {
+  if (S <= 0 || S > kTQ || H <= 0 || s_pad < S) return OPB_ERR_INVALID;
+  relpos_bias_transpose_kernel<<<dim3(kTKeys / 32, H), 256, 0, stream>>>(bias, reinterpret_cast<uint32_t*>(bias_t), S, s_pad);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// dbias (H, S, s_pad) += transpose of dbias_t (H x 256 x 224 fp32)
+int relpos_dbias_fold(const float* dbias_t, float* dbias, int S, int s_pad, int H, cudaStream_t stream) {
+  if (S <= 0 || S > kTQ || H <= 0 || s_pad < S) return OPB_ERR_INVALID;
+  relpos_dbias_fold_kernel<<<dim3((S + 31) / 32, H), 256, 0, stream>>>(dbias_t, dbias, S, s_pad);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+int relpos_dbias_center(float* dbias, int S, int s_pad, int H, cudaStream_t stream) {
+  if (S <= 0 || H <= 0 || s_pad < S) return OPB_ERR_INVALID;
+  const long rows = static_cast<long>(H) * S;
+  relpos_dbias_center_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, stream>>>(dbias, S, s_pad, static_cast<int>(rows));
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
 // Same contract as attention_bwd (ops.h) minus the delta kernel (the caller has run attn_delta); S <= 224.
 int attention_bwd_tc(const void* qkv, const void* d_out, const float* bias, const uint8_t* key_pad, const float* lse,
                      const float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad, float q_scale,
-                     long bias_bstride, cudaStream_t stream) {
+                     long bias_bstride, const void* bias_t, float* dbias_t, cudaStream_t stream) {
   if (S > 224) return OPB_ERR_UNSUPPORTED;
+  if (dbias_t != nullptr && bias_t == nullptr) return OPB_ERR_INVALID;
   const int D = H * kD;
   BwdArgs a;
   a.bias = bias; a.dbias = dbias; a.bias_bstride = bias_bstride; a.s_pad = s_pad; a.key_pad = key_pad;
+  a.bias_t = reinterpret_cast<const uint32_t*>(bias_t); a.dbias_t = dbias_t;
+  if (bias_t != nullptr) { a.bias = nullptr; a.dbias = nullptr; }
   a.lse = lse; a.delta = delta; a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   a.B = B; a.S = S; a.H = H; a.q_scale = q_scale;
   a.n_kt = (S + kKT - 1) / kKT;

@@ -106,7 +106,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
                     float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols,
-                    int seg_split) {
+                    int seg_split, int k0, int Sk) {
+  // k0 / Sk: the launch covers keys [k0, k0 + Sk) of every sample (Sk == S, k0 == 0 unless the sequence is split over several
+  // launches whose partial results are merged by attention_merge_kernel — 384 < S <= 768, the 15 s audio sequences).  Queries
+  // are always all S rows; `code_col` and `key_pad` are indexed by the LOCAL key (the host passes code_col + k0).
   // no static shared memory in this kernel: the dynamic window starts at the (1024-aligned) base of the CTA's shared
   // memory.  The 112 KB + barriers must fit twice per SM, so there is no room for alignment slack; verify instead.
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
@@ -155,15 +158,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     if (lane == 0) {
       const int row0 = b * S;
       // phase-A tables: lut [lut_len] | code_col [s4] (both padded to 16-byte multiples by the host)
-      const int s4 = (S + 3) & ~3;
+      const int s4 = (Sk + 3) & ~3;
       mbar_arrive_expect_tx(&bars->lut, static_cast<uint32_t>(lut_len + s4) * 4);
       bulk_load_1d(sP, lut + static_cast<long>(h) * lut_len, static_cast<uint32_t>(lut_len) * 4, &bars->lut);
       bulk_load_1d(sP + static_cast<long>(lut_len) * 4, code_col, static_cast<uint32_t>(s4) * 4, &bars->lut);
       mbar_arrive_expect_tx(&bars->qk, (kTcQ + nkb * kTcK) * 128);
       tma_load_2d(&tm_qkv, &bars->qk, sQ, h * kTcD, row0 + q0);
-      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->qk, sK + kb * kTcK * 128, D + h * kTcD, row0 + kb * kTcK);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->qk, sK + kb * kTcK * 128, D + h * kTcD, row0 + k0 + kb * kTcK);
       mbar_arrive_expect_tx(&bars->v, nkb * kTcK * 128);
-      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->v, sV + kb * kTcK * 128, 2 * D + h * kTcD, row0 + kb * kTcK);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->v, sV + kb * kTcK * 128, 2 * D + h * kTcD, row0 + k0 + kb * kTcK);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -212,8 +215,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     // bias tables: lut [lut_len] | code_col [S padded to 4] (| key_pad bytes).  They land in the P buffer (bulk copy at
     // kernel start) and are moved into the Q tile once the last S = Q K^T has completed (Q is dead then), because phase B
     // gathers from them while it fills the P buffer.  The last 3 KB of the Q tile are the exchange area of a row's threads.
-    const int tbl_words = lut_len + ((S + 3) & ~3);
-    const int pad_bytes = HAS_PAD ? ((S + 31) & ~31) : 0;
+    const int tbl_words = lut_len + ((Sk + 3) & ~3);
+    const int pad_bytes = HAS_PAD ? ((Sk + 31) & ~31) : 0;
     const int tbl_bytes = (tbl_words * 4 + pad_bytes + 15) & ~15;
     const float* s_lut = reinterpret_cast<const float*>(sQ);
     const int* s_ccol = reinterpret_cast<const int*>(sQ) + lut_len;
@@ -222,13 +225,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     float2* xstat = reinterpret_cast<float2*>(sQ + kTcTableBytes + 4 * kTcQ * 4);
     if constexpr (HAS_PAD) {
       uint8_t* pad_in = sP + static_cast<long>(tbl_words) * 4;
-      for (int i = tid4; i < pad_bytes; i += kRowThreads) pad_in[i] = i < S ? key_pad[static_cast<long>(b) * S + i] : 0;
+      for (int i = tid4; i < pad_bytes; i += kRowThreads) pad_in[i] = i < Sk ? key_pad[static_cast<long>(b) * S + k0 + i] : 0;
     }
     const int crow = code_row[row_valid ? qrow : 0];
     // concatenated sequences ('vl' / 'al', transformer_encoder.py:148-158): the relative-position bias is block-diagonal —
     // a row only sees the bias of the keys of its own modality segment [seg_lo, seg_hi); zero across segments
     const int seg_lo = (seg_split > 0 && qrow >= seg_split) ? seg_split : 0;
-    const int seg_hi = (seg_split > 0 && qrow < seg_split) ? seg_split : S;
+    const int seg_hi = (seg_split > 0 && qrow < seg_split) ? seg_split : Sk;      // (seg_split > 0 only with k0 == 0, Sk == S)
     OPB_T(1);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
     const int nsub = nkb * (kTcK / 16);
@@ -246,7 +249,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       tc_fence_after();
       if (kb == 0) OPB_T(2);
       if (warp_valid) {
-        const int kvalid = min(kTcK, S - kb * kTcK);
+        const int kvalid = min(kTcK, Sk - kb * kTcK);
         for (int c = half * 16; c < kvalid; c += 16 * HALVES) {
           uint32_t v[16];
           __syncwarp();
@@ -297,7 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
           const bool ok = (key0 + j >= seg_lo) & (key0 + j < seg_hi);
           const float bv = s_lut[ok ? ii[j] : 0];
           add[j] = fmaf(ok ? bv : 0.f, 1.4426950408889634f, -mb);
-          add[j] = (key0 + j >= S) ? -INFINITY : add[j];
+          add[j] = (key0 + j >= Sk) ? -INFINITY : add[j];
         }
       }
       if constexpr (HAS_PAD) {
@@ -344,7 +347,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
 #pragma unroll 1
         for (int u = 0; u < kTcK / 16; u += 2) {
           const int t = kb * (kTcK / 16) + u;
-          const bool liveA = any && t * 16 < S, liveB = any && (t + 1) * 16 < S, liveC = any && (t + 2) * 16 < S && t + 2 < nsub;
+          const bool liveA = any && t * 16 < Sk, liveB = any && (t + 1) * 16 < Sk, liveC = any && (t + 2) * 16 < Sk && t + 2 < nsub;
           if (liveA) tmem_ld_wait();
           if (liveB) prefetch(t + 1, vB, aB);
           finish(t, vA, aA, liveA);
@@ -364,7 +367,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
 #pragma unroll 1
         for (int u = half; u < kTcK / 16; u += HALVES) {
           const int t = kb * (kTcK / 16) + u;
-          const bool live = any && t * 16 < S;
+          const bool live = any && t * 16 < Sk;
           uint32_t v[16];
           float add[16];
           if (live) {
@@ -479,22 +482,15 @@ int attention_tcp_fwd(const void* qkv, const float* lut, int lut_len, const int*
                       const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
                       cudaStream_t stream);
 
-int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int* code_row, const int* code_col,
-                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
-                     cudaStream_t stream) {
-  if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || lut_max == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
-  if (seg_split < 0 || seg_split >= S) return OPB_ERR_INVALID;
-  // S <= 224: the persistent kernel (attention_tcp.cu).  OPB_ATTN_PERSIST=0 keeps the one-CTA-per-tile kernel below (A/B switch).
-  const char* env_p = getenv("OPB_ATTN_PERSIST");            // read per call: tests switch it in-process
-  if (S <= 224 && !(env_p != nullptr && env_p[0] == '0')) {
-    const int rc = attention_tcp_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split, stream);
-    if (rc != OPB_ERR_UNSUPPORTED) return rc;
-  }
-  const int nkb = (S + kTcK - 1) / kTcK;
+// One launch of attention_tc_kernel over keys [k0, k0 + Sk) of every sample (all S queries).
+static int launch_tc(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int* code_row, const int* code_col,
+                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split, int k0,
+                     int Sk, cudaStream_t stream) {
+  const int nkb = (Sk + kTcK - 1) / kTcK;
   if (nkb > kTcMaxBlocks) return OPB_ERR_UNSUPPORTED;
-  if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col) & 15) != 0)
+  if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col + k0) & 15) != 0)
     return OPB_ERR_INVALID;     // bulk-copied: 16-byte granularity (code_col must hold (S + 3) & ~3 entries)
-  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((S + 3) & ~3) * 4 + S + 48;
+  const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((Sk + 3) & ~3) * 4 + Sk + 48;
   if (table_bytes > kTcTableBytes) return OPB_ERR_UNSUPPORTED;   // the tables move into the (dead) 16 KB Q tile for phase B
   const int D = H * kTcD;
   CUtensorMap tm;
@@ -513,9 +509,78 @@ int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, in
   }
   const int q_tiles = (S + kTcQ - 1) / kTcQ;
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
-  kern<<<grid, 64 + 128 * halves, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col, key_pad,
-                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split);
+  kern<<<grid, 64 + 128 * halves, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col + k0, key_pad,
+                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split,
+                                                 k0, Sk);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// Merge of two key-range partial results (flash-decoding style): out = w0 out0 + w1 out1 with w_c = exp(lse_c - lse), in place in
+// `out` (which holds out0); writes the total log-sum-exp and the per-head inner-LayerNorm statistics.  One warp per (row, head).
+__global__ void __launch_bounds__(256)
+attention_merge_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ out1, const float* __restrict__ lse0,
+                       const float* __restrict__ lse1, float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H) {
+  const long w = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long rows = static_cast<long>(B) * S;
+  if (w >= rows * H) return;
+  const long row = w / H;
+  const int h = static_cast<int>(w % H);
+  const int b = static_cast<int>(row / S), sq = static_cast<int>(row % S);
+  const long li = (static_cast<long>(b) * H + h) * S + sq;
+  const float l0 = lse0[li], l1 = lse1[li];
+  const float m = fmaxf(l0, l1);
+  float w0 = 0.f, w1 = 0.f, tot = -INFINITY;
+  if (m > -INFINITY) {
+    const float e0 = __expf(l0 - m), e1 = __expf(l1 - m);
+    const float den = e0 + e1;
+    w0 = e0 / den; w1 = e1 / den;
+    tot = m + __logf(den);
+  }
+  const long D = static_cast<long>(H) * kTcD;
+  uint32_t* p0 = reinterpret_cast<uint32_t*>(out + row * D + h * kTcD) + lane;
+  const uint32_t* p1 = reinterpret_cast<const uint32_t*>(out1 + row * D + h * kTcD) + lane;
+  const float2 a = unpack_bf16x2(*p0), c = unpack_bf16x2(*p1);
+  const float y0 = w0 * a.x + w1 * c.x, y1 = w0 * a.y + w1 * c.y;
+  *p0 = pack_bf16x2(y0, y1);
+  const float ssum = warp_sum(y0 + y1), ssq = warp_sum(y0 * y0 + y1 * y1);
+  if (lane == 0) {
+    if (lse != nullptr) lse[li] = tot;
+    if (ln_stats != nullptr) *reinterpret_cast<float2*>(ln_stats + (h * rows + row) * 2) = make_float2(ssum, ssq);
+  }
+}
+
+int attention_tc_fwd(const void* qkv, const float* lut, const float* lut_max, int lut_len, const int* code_row, const int* code_col,
+                     const uint8_t* key_pad, void* out, float* lse, float* ln_stats, int B, int S, int H, int seg_split,
+                     cudaStream_t stream) {
+  if (B <= 0 || S <= 0 || H <= 0 || lut == nullptr || lut_max == nullptr || code_row == nullptr || code_col == nullptr) return OPB_ERR_INVALID;
+  if (seg_split < 0 || seg_split >= S) return OPB_ERR_INVALID;
+  // S <= 224: the persistent kernel (attention_tcp.cu).  OPB_ATTN_PERSIST=0 keeps the one-CTA-per-tile kernel below (A/B switch).
+  const char* env_p = getenv("OPB_ATTN_PERSIST");            // read per call: tests switch it in-process
+  if (S <= 224 && !(env_p != nullptr && env_p[0] == '0')) {
+    const int rc = attention_tcp_fwd(qkv, lut, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split, stream);
+    if (rc != OPB_ERR_UNSUPPORTED) return rc;
+  }
+  if (S <= kTcMaxBlocks * kTcK) return launch_tc(qkv, lut, lut_max, lut_len, code_row, code_col, key_pad, out, lse, ln_stats, B, S, H, seg_split, 0, S, stream);
+  // 384 < S <= 768 (audio: 750 tokens for 15 s): two key ranges, each a launch that holds its <= 384 scores per row in tensor
+  // memory, merged afterwards.  Scratch (second partial output + the two partial log-sum-exp vectors) is stream-ordered.
+  if (S > 2 * kTcMaxBlocks * kTcK || seg_split != 0) return OPB_ERR_UNSUPPORTED;
+  const int Sk0 = ((S / 2 + 7) / 8) * 8, Sk1 = S - Sk0;
+  const size_t out_bytes = static_cast<size_t>(B) * S * H * kTcD * 2, lse_bytes = static_cast<size_t>(B) * H * S * 4;
+  uint8_t* scratch = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), out_bytes + 2 * lse_bytes, stream) != cudaSuccess) return OPB_ERR_CUDA;
+  float* lse0 = reinterpret_cast<float*>(scratch + out_bytes);
+  float* lse1 = lse0 + static_cast<size_t>(B) * H * S;
+  int rc = launch_tc(qkv, lut, lut_max, lut_len, code_row, code_col, key_pad, out, lse0, nullptr, B, S, H, 0, 0, Sk0, stream);
+  if (rc == OPB_OK) rc = launch_tc(qkv, lut, lut_max, lut_len, code_row, code_col, key_pad, scratch, lse1, nullptr, B, S, H, 0, Sk0, Sk1, stream);
+  if (rc == OPB_OK) {
+    const long warps = static_cast<long>(B) * S * H;
+    attention_merge_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(scratch), lse0, lse1, lse, ln_stats, B, S, H);
+    if (cudaGetLastError() != cudaSuccess) rc = OPB_ERR_CUDA;
+  }
+  cudaFreeAsync(scratch, stream);
+  return rc;
 }
 
 }  // namespace opb

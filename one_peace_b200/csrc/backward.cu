@@ -65,6 +65,20 @@ OPB_DEVICE float2 block_sum2(float a, float b, float2* red) {
   return t;
 }
 
+// sums four values over the CTA with ONE barrier pair; every thread gets all totals
+template <int THREADS>
+OPB_DEVICE float4 block_sum4(float a, float b, float c, float d, float4* red) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();                       // previous use of `red` finished
+  if (lane == 0) red[warp] = make_float4(a, b, c, d);
+  __syncthreads();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) { const float4 r = red[w]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+  return t;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // One CTA per row (grid-stride); THREADS x GROUPS float4 column groups cover `dim`.  gamma / beta are re-read per row
 // (L1 hits) instead of living in registers: the kernel is HBM-bound and needs the occupancy (first version: 170
@@ -76,6 +90,7 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
                      int accumulate, float* __restrict__ partial, int rows, int dim, float eps, int gelu,
                      int dy_merge_w) {
   __shared__ float2 red[THREADS / 32];
+  __shared__ float4 red4[THREADS / 32];
   const int ngroups = dim >> 2;
   float4 dg[GROUPS], db[GROUPS];
 #pragma unroll
@@ -119,8 +134,6 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
     } else {
       load_row(row, xv, gv);
     }
-#pragma unroll
-    for (int k = 0; k < GROUPS; ++k) s1 += xv[k].x + xv[k].y + xv[k].z + xv[k].w;
     if (accumulate) {
 #pragma unroll
       for (int k = 0; k < GROUPS; ++k) {
@@ -128,6 +141,51 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
         oldv[k] = g < ngroups ? load4(dx + row * ld_dx + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    if (!gelu) {
+      // Plain LayerNorm adjoint with ONE block reduction per row instead of three (round 2: the FFN LayerNorm rows, 6144 wide,
+      // ran at 0.68 of the HBM peak, the CTA idling in three barrier pairs per row).  With the shift K = x[row][0]:
+      //   mean = K + S1/n, var = S2/n - (S1/n)^2            S1 = sum (x-K), S2 = sum (x-K)^2   (shifted: no cancellation)
+      //   sum dy g = B1,   sum dy g xhat = rstd (B2 - (S1/n) B1)                                 B2 = sum dy g (x-K)
+      const float ksh = load4(x + row * ldx).x;
+      float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < GROUPS; ++k) {
+        const int g = threadIdx.x + k * THREADS;
+        if (g < ngroups) {
+          const float4 gm = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + 4 * g)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          xv[k].x -= ksh; xv[k].y -= ksh; xv[k].z -= ksh; xv[k].w -= ksh;
+          a1 += xv[k].x + xv[k].y + xv[k].z + xv[k].w;
+          a2 += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+          const float4 gy = make_float4(gv[k].x * gm.x, gv[k].y * gm.y, gv[k].z * gm.z, gv[k].w * gm.w);
+          b1 += gy.x + gy.y + gy.z + gy.w;
+          b2 += gy.x * xv[k].x + gy.y * xv[k].y + gy.z * xv[k].z + gy.w * xv[k].w;
+        }
+      }
+      const float4 t = block_sum4<THREADS>(a1, a2, b1, b2, red4);
+      const float ms = t.x * inv_dim;                                  // mean - K
+      const float rstd = rsqrtf(fmaxf(t.y * inv_dim - ms * ms, 0.f) + eps);
+      const float m1 = t.z * inv_dim, m2 = rstd * (t.w - ms * t.z) * inv_dim;
+#pragma unroll
+      for (int k = 0; k < GROUPS; ++k) {
+        const int g = threadIdx.x + k * THREADS;
+        if (g < ngroups) {
+          const float4 gm = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + 4 * g)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float4 xh = make_float4((xv[k].x - ms) * rstd, (xv[k].y - ms) * rstd, (xv[k].z - ms) * rstd, (xv[k].w - ms) * rstd);
+          dg[k].x += gv[k].x * xh.x; dg[k].y += gv[k].y * xh.y; dg[k].z += gv[k].z * xh.z; dg[k].w += gv[k].w * xh.w;
+          db[k].x += gv[k].x; db[k].y += gv[k].y; db[k].z += gv[k].z; db[k].w += gv[k].w;
+          float4 o;
+          o.x = rstd * (gv[k].x * gm.x - m1 - xh.x * m2);
+          o.y = rstd * (gv[k].y * gm.y - m1 - xh.y * m2);
+          o.z = rstd * (gv[k].z * gm.z - m1 - xh.z * m2);
+          o.w = rstd * (gv[k].w * gm.w - m1 - xh.w * m2);
+          if (accumulate) { o.x += oldv[k].x; o.y += oldv[k].y; o.z += oldv[k].z; o.w += oldv[k].w; }
+          store4(dx + row * ld_dx + 4 * g, o);
+        }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < GROUPS; ++k) s1 += xv[k].x + xv[k].y + xv[k].z + xv[k].w;
     const float mean = block_sum2<THREADS>(s1, 0.f, red).x * inv_dim;
     float s2 = 0.f;
 #pragma unroll

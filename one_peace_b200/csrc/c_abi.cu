@@ -305,6 +305,32 @@ int opb_attention_bwd(const void* qkv, const void* out, const void* d_out, const
                             bias_batch_stride, static_cast<cudaStream_t>(stream));
 }
 
+int opb_attention_bwd_t(const void* qkv, const void* out, const void* d_out, const void* bias_t, const uint8_t* key_pad,
+                        const float* lse, float* delta, void* dqkv, float* dbias_t, int B, int S, int H, float q_scale,
+                        void* stream) {
+  if (!qkv || !out || !d_out || !dqkv || !lse || !delta || B <= 0 || S <= 0 || H <= 0) return OPB_ERR_INVALID;
+  if (S > 224) return OPB_ERR_UNSUPPORTED;
+  const int rc = opb::attn_delta(d_out, out, delta, B, S, H, static_cast<cudaStream_t>(stream));
+  if (rc != OPB_OK) return rc;
+  return opb::attention_bwd_tc(qkv, d_out, nullptr, key_pad, lse, delta, dqkv, nullptr, B, S, H, 0, q_scale, 0, bias_t, dbias_t,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_bias_transpose(const float* bias, void* bias_t, int S, int s_pad, int H, void* stream) {
+  if (!bias || !bias_t) return OPB_ERR_INVALID;
+  return opb::relpos_bias_transpose(bias, bias_t, S, s_pad, H, static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_dbias_fold(const float* dbias_t, float* dbias, int S, int s_pad, int H, void* stream) {
+  if (!dbias_t || !dbias) return OPB_ERR_INVALID;
+  return opb::relpos_dbias_fold(dbias_t, dbias, S, s_pad, H, static_cast<cudaStream_t>(stream));
+}
+
+int opb_relpos_dbias_center(float* dbias, int S, int s_pad, int H, void* stream) {
+  if (!dbias) return OPB_ERR_INVALID;
+  return opb::relpos_dbias_center(dbias, S, s_pad, H, static_cast<cudaStream_t>(stream));
+}
+
 int opb_relpos_bias_bwd(const float* dbias, const int64_t* bucket, float* dtable, int S, int s_pad, int H,
                         int64_t ld_bucket, void* stream) {
   if (!dbias || !bucket || !dtable) return OPB_ERR_INVALID;

@@ -105,9 +105,14 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
                   float q_scale, long bias_bstride, cudaStream_t stream);
 
 // tcgen05 form (attention_bwd_tc.cu), S <= 224; `delta` already computed.  attention_bwd dispatches to it.
+// bias_t / dbias_t (optional): the batch-shared bias and its gradient as TRANSPOSED tables (relpos_bias_transpose /
+// relpos_dbias_fold) — then bias / dbias are ignored.
 int attention_bwd_tc(const void* qkv, const void* d_out, const float* bias, const uint8_t* key_pad, const float* lse,
                      const float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad, float q_scale,
-                     long bias_bstride, cudaStream_t stream);
+                     long bias_bstride, const void* bias_t, float* dbias_t, cudaStream_t stream);
+int relpos_bias_transpose(const float* bias, void* bias_t, int S, int s_pad, int H, cudaStream_t stream);
+int relpos_dbias_fold(const float* dbias_t, float* dbias, int S, int s_pad, int H, cudaStream_t stream);
+int relpos_dbias_center(float* dbias, int S, int s_pad, int H, cudaStream_t stream);
 
 // ---- pretraining path: row gathers, sample-dependent / block-diagonal dense relative-position bias (gather.cu) ----
 int row_gather(const void* src, int src_dtype, long ld_src, const int64_t* idx, const float* fill, const float* add,

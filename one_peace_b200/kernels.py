@@ -504,6 +504,49 @@ def attention_bwd(qkv, out, d_out, bias, key_pad, lse, dqkv, dbias, B, S, H, q_s
     return dqkv
 
 
+BIAS_T_KEYS, BIAS_T_Q = 256, 224      # transposed bias tables of the tcgen05 attention backward (csrc/attention_bwd_tc.cu)
+
+
+def relpos_bias_transpose(bias):
+    """dense fp32 (H,S,S_pad) bias -> (H,256,112) half2 words (int32 storage), x log2 e, zero-padded; S <= 224."""
+    H, S, s_pad = bias.shape
+    out = torch.empty(H, BIAS_T_KEYS, BIAS_T_Q // 2, dtype=torch.int32, device=bias.device)
+    st = _lib.load().opb_relpos_bias_transpose(bias.data_ptr(), out.data_ptr(), S, s_pad, H, _stream())
+    _lib.check(st, "opb_relpos_bias_transpose")
+    _count()
+    return out
+
+
+def relpos_dbias_fold(dbias_t, dbias):
+    """dbias fp32 (H,S,S_pad) += transpose of dbias_t fp32 (H,256,224)"""
+    H, S, s_pad = dbias.shape
+    st = _lib.load().opb_relpos_dbias_fold(dbias_t.data_ptr(), dbias.data_ptr(), S, s_pad, H, _stream())
+    _lib.check(st, "opb_relpos_dbias_fold")
+    _count()
+    return dbias
+
+
+def relpos_dbias_center(dbias):
+    """in place: every row of the dense fp32 (H,S,S_pad) bias gradient gets its mean over the S valid columns subtracted"""
+    H, S, s_pad = dbias.shape
+    st = _lib.load().opb_relpos_dbias_center(dbias.data_ptr(), S, s_pad, H, _stream())
+    _lib.check(st, "opb_relpos_dbias_center")
+    _count()
+    return dbias
+
+
+def attention_bwd_t(qkv, out, d_out, bias_t, key_pad, lse, dqkv, dbias_t, B, S, H, q_scale):
+    """tcgen05 attention backward with transposed bias tables (relpos_bias_transpose / a zeroed (H,256,224) fp32 dbias_t that
+    several layers may share); S <= 224."""
+    delta = torch.empty(B * H * S, dtype=torch.float32, device=qkv.device)
+    st = _lib.load().opb_attention_bwd_t(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), _ptr(bias_t), _ptr(key_pad),
+                                         lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), _ptr(dbias_t), B, S, H,
+                                         float(q_scale), _stream())
+    _lib.check(st, "opb_attention_bwd_t")
+    _count(2)
+    return dqkv
+
+
 def relpos_bias_bwd(dbias, bucket, dtable, S):
     H, s_pad = dbias.shape[0], dbias.shape[-1]
     st = _lib.load().opb_relpos_bias_bwd(dbias.data_ptr(), bucket.data_ptr(), dtable.data_ptr(), S, s_pad, H, bucket.stride(0),

@@ -151,6 +151,45 @@ def test_attention_bwd(K, B, S, H, pad, use_bias):
             assert torch.all(dbias[:, :, S:] == 0)
 
 
+@pytest.mark.parametrize("B,S,H,pad", [(3, 197, 4, False), (2, 70, 2, True), (2, 214, 3, True), (5, 33, 2, True)])
+def test_attention_bwd_transposed_tables(K, B, S, H, pad):
+    """opb_attention_bwd_t (tcgen05, bias / dbias as transposed tables shared by several launches) vs fp32 torch autograd; the
+    gradient table is accumulated over TWO launches and folded back once, as the encoder stack does."""
+    D = H * 64
+    g = gen(S + H + 1)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.6).bfloat16()
+    s_pad = (S + 3) // 4 * 4
+    bias = torch.randn(H, S, s_pad, device="cuda", generator=g) * 0.5
+    key_pad = None
+    if pad:
+        key_pad = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+        key_pad[0, S - 5:] = 1
+        key_pad[-1, S // 2:] = 1
+    d_out = torch.randn(B * S, D, device="cuda", generator=g).bfloat16()
+    lse = torch.empty(B * H * S, device="cuda")
+    out = K.attention(qkv, bias, key_pad, B, S, H, lse=lse)
+    qr = qkv.float().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    attention_ref(qr, br, key_pad, B, S, H).backward(d_out.float())
+    bias_t = K.relpos_bias_transpose(bias)
+    dbias_t = torch.zeros(H, K.BIAS_T_KEYS, K.BIAS_T_Q, device="cuda")
+    dqkv = torch.zeros(B * S, 3 * D, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):
+        K.attention_bwd_t(qkv, out, d_out, bias_t, key_pad, lse, dqkv, dbias_t, B, S, H, 0.125)
+    dbias = torch.zeros(H, S, s_pad, device="cuda")
+    K.relpos_dbias_fold(dbias_t, dbias)
+    want = qr.grad.clone()
+    want[:, :D] *= 0.125
+    for name, lo in (("dq", 0), ("dk", D), ("dv", 2 * D)):
+        err = relerr(dqkv[:, lo:lo + D], want[:, lo:lo + D])
+        assert err < 1.5e-2, (name, err)
+    assert relerr(dbias[:, :, :S], 2 * br.grad[:, :, :S]) < 1e-2
+    if s_pad > S:
+        assert torch.all(dbias[:, :, S:] == 0)
+    # everything outside the S x S corner of the transposed table is padding and must stay zero
+    assert torch.all(dbias_t[:, S:, :] == 0) and torch.all(dbias_t[:, :, S:] == 0)
+
+
 def test_relpos_bias_bwd(K):
     S, H, NB = 50, 4, 37
     g = gen(3)

@@ -1,8 +1,8 @@
 """GPU: the hand-written backward (one_peace_b200/autograd.py) vs torch autograd through the CPU fp32 oracle
 (oracle/restated.py) on the same seeded weights and inputs.
 
-Bars: every parameter gradient must point the same way as the oracle's (cosine >= 0.99 over the whole tensor) with
-a matching norm (within 3 %).  Activations and matmul operands are bf16 in the product path (2^-9 per rounding), so
+Bars: every parameter gradient must point the same way as the oracle's (cosine >= 0.995 over the whole tensor, 0.99 through
+the InfoNCE head whose logit scale amplifies the forward's bf16 differences ~14x) with a matching norm (within 3 % / 5 %).  Activations and matmul operands are bf16 in the product path (2^-9 per rounding), so
 element-wise equality is not the bar; the training forward obeys the forward bars (cosine >= 0.999, InfoNCE loss 1e-3)."""
 import pytest
 import torch
@@ -68,9 +68,13 @@ def compare(model, want, min_cos=0.99, norm_tol=0.03, relpos=None):
     assert len(rows) > 20
 
 
+@pytest.mark.parametrize("policy", ["keep", "recompute"])
 @pytest.mark.parametrize("modality", ["text", "image", "audio"])
-def test_encoder_backward_vs_oracle(modality):
+def test_encoder_backward_vs_oracle(modality, policy, monkeypatch):
+    """policy: activations of the stack kept in HBM (the B200 default when they fit) or recomputed per layer in the backward
+    (the reference's checkpoint_wrapper) — autograd.keep_activations."""
     need_gpu()
+    monkeypatch.setenv("OPB_ACTIVATIONS", policy)
     mods = ("text", "audio") if modality == "audio" else ("text", "image")
     sd = synth.make_state_dict(**CFG, modalities=mods, seed=3)
     tok, img, aud, apm = synth.tiny_inputs(seed=5, n_text=8, n_img=2, n_audio=2)
@@ -91,9 +95,10 @@ def test_encoder_backward_vs_oracle(modality):
     loss = (emb.float() * target.cuda()).sum()
     loss.backward()
     # relative-position tables: dS = P o (dP - delta) with delta = sum(dO * O) taken from the bf16-rounded forward output
-    # (as flash-attention does); at S = 197 the rows are diffuse, dP - delta is a small difference and the table gradient
-    # inherits that rounding — measured 0.98-0.99 cosine, every other tensor >= 0.996
-    compare(model, want, relpos=(0.97, 0.06))
+    # (as flash-attention does) leaves a row-coherent offset in the bias gradient; the stack projects the accumulated table
+    # onto zero row sums (the exact gradient's subspace, csrc/attention_bwd_tc.cu) — measured 0.9999+ with it, 0.98-0.99
+    # without; every other tensor >= 0.996
+    compare(model, want, min_cos=0.995, relpos=(0.995, 0.03))
     # parameters of the other modality's branch must be untouched
     other = {"text": "image" if "image" in mods else "audio", "image": "text", "audio": "text"}[modality]
     for name, p in model.named_parameters():
@@ -124,9 +129,24 @@ def test_contrastive_step_backward_vs_oracle():
     loss, _, _ = itc_loss(i, t, i.detach(), t.detach(), scale, 0, 0.0)
     assert abs(loss.item() - want_loss.item()) <= 1e-3 * abs(want_loss.item()), (loss.item(), want_loss.item())
     loss.backward()
+    # Error-budget control for the most noise-sensitive tensor, the relative-position table (a signed sum over every (batch,
+    # query, key) of softmax-gradient terms): the reference's OWN arithmetic in bf16 (oracle/restated.py on CUDA, bf16 weights
+    # and activations, torch autograd) is run on the same step; the hand-written backward must meet the absolute bar or be no
+    # further from the fp32 oracle than that.
+    sdb = {k: (v.cuda().bfloat16().requires_grad_(True) if v.is_floating_point() else v.cuda()) for k, v in sd.items()}
+    teb = R.extract_features(sdb, cfg, "text", src_tokens=tok.cuda())
+    ieb = R.extract_features(sdb, cfg, "image", src_images=img.cuda().bfloat16())
+    lb, _, _ = R.itc_loss(ieb.float(), teb.float(), ieb.detach().float(), teb.detach().float(),
+                          R.logit_scale_exp(sdb["logit_scale"].float()), 0, 0.0)
+    lb.backward()
+    key = "encoder_wrapper.image_adapter.rel_pos_table_list.0.weight"
+    eg = sdb[key].grad.float().cpu()
+    cos_eager = torch.nn.functional.cosine_similarity(eg.flatten(), want[key].flatten(), dim=0).item()
+    ratio_eager = abs((eg.norm() / want[key].norm()).item() - 1)
+    print(f"eager-bf16 control, {key}: cos {cos_eager:.4f}  | |g|/|g_ref| - 1 | {ratio_eager:.4f}")
     # the InfoNCE gradient (logit_scale = 1/0.07) amplifies the forward's bf16 differences ~14x before they enter the
     # encoder backward, hence the wider band than in the linear-functional test above
-    compare(model, want, min_cos=0.97, norm_tol=0.06, relpos=(0.94, 0.12))
+    compare(model, want, min_cos=0.99, norm_tol=0.05, relpos=(min(0.985, cos_eager - 0.005), max(0.05, ratio_eager + 0.02)))
 
 
 def test_graphed_train_step_equals_eager_and_tracks_weight_updates():
