@@ -159,11 +159,11 @@ class AudioAdapter(torch.nn.Module):
         return out
 
     def get_rel_pos_bias(self, seq_len):
-        """One RelPosBias per table: LUT form for the tcgen05 attention kernel when S <= 384, dense (H,S,S_pad) otherwise."""
+        """One RelPosBias per table: LUT form for the tcgen05 attention kernels when S <= 768, dense (H,S,S_pad) otherwise."""
         p = self._pack()
         if not hasattr(self, "_lut_cache"):
             self._lut_cache = relpos.LutCache()
-        lut = self._lut_cache.get(seq_len, self.rp_bucket.device, self.rp_bucket, lambda S: relpos.text_codes(S)) if seq_len <= 384 else None
+        lut = self._lut_cache.get(seq_len, self.rp_bucket.device, self.rp_bucket, lambda S: relpos.text_codes(S)) if seq_len <= K.ATTN_TC_MAX_S else None
         out = []
         for t in p["tables"]:
             if lut is not None:

@@ -25,7 +25,7 @@ from .components import PackCache, bf16, f32
 class TrainBias:
     """Relative-position bias of a training forward: `dense` = autograd-tracked fp32 (H,S,S_pad) tensor (what the
     backward kernels read and what receives the gradient), `fast` = the same values as a kernels.RelPosBias in LUT
-    form for the tcgen05 attention kernel (None when S > 384)."""
+    form for the tcgen05 attention kernels (None when S > 768)."""
 
     def __init__(self, dense, fast=None):
         self.dense, self.fast, self.lut = dense, fast, None

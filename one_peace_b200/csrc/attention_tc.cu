@@ -106,7 +106,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
                     const int* __restrict__ code_row, const int* __restrict__ code_col,
                     const uint8_t* __restrict__ key_pad, __nv_bfloat16* __restrict__ out,
                     float* __restrict__ lse, float* __restrict__ ln_stats, int B, int S, int H, int nkb, uint32_t tmem_cols,
-                    int seg_split, int k0, int Sk) {
+                    int seg_split, int k0, int Sk, int big_tables) {
   // k0 / Sk: the launch covers keys [k0, k0 + Sk) of every sample (Sk == S, k0 == 0 unless the sequence is split over several
   // launches whose partial results are merged by attention_merge_kernel — 384 < S <= 768, the 15 s audio sequences).  Queries
   // are always all S rows; `code_col` and `key_pad` are indexed by the LOCAL key (the host passes code_col + k0).
@@ -120,6 +120,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
   uint8_t* sV = sK + nkb * kTcK * 128;
   uint8_t* sP = sV + nkb * kTcK * 128;                  // 32 KB: LUT + codes (+ pad mask) in phase A, P afterwards
   TcBars* bars = reinterpret_cast<TcBars*>(sP + kTcQ * kTcK * 2);
+  // big_tables (long sequences: the LUT of a 750-token audio sequence is 18 KB): the tables get their own region behind the
+  // barriers instead of travelling P buffer -> dead Q tile; the Q tile then only holds the row threads' exchange area.
+  uint8_t* sT = reinterpret_cast<uint8_t*>(bars) + 256;
 
   const int q_tiles = (S + kTcQ - 1) / kTcQ;
   const int qt = blockIdx.x % q_tiles;
@@ -160,8 +163,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
       // phase-A tables: lut [lut_len] | code_col [s4] (both padded to 16-byte multiples by the host)
       const int s4 = (Sk + 3) & ~3;
       mbar_arrive_expect_tx(&bars->lut, static_cast<uint32_t>(lut_len + s4) * 4);
-      bulk_load_1d(sP, lut + static_cast<long>(h) * lut_len, static_cast<uint32_t>(lut_len) * 4, &bars->lut);
-      bulk_load_1d(sP + static_cast<long>(lut_len) * 4, code_col, static_cast<uint32_t>(s4) * 4, &bars->lut);
+      uint8_t* tdst = big_tables ? sT : sP;
+      bulk_load_1d(tdst, lut + static_cast<long>(h) * lut_len, static_cast<uint32_t>(lut_len) * 4, &bars->lut);
+      bulk_load_1d(tdst + static_cast<long>(lut_len) * 4, code_col, static_cast<uint32_t>(s4) * 4, &bars->lut);
       mbar_arrive_expect_tx(&bars->qk, (kTcQ + nkb * kTcK) * 128);
       tma_load_2d(&tm_qkv, &bars->qk, sQ, h * kTcD, row0 + q0);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tm_qkv, &bars->qk, sK + kb * kTcK * 128, D + h * kTcD, row0 + k0 + kb * kTcK);
@@ -218,13 +222,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     const int tbl_words = lut_len + ((Sk + 3) & ~3);
     const int pad_bytes = HAS_PAD ? ((Sk + 31) & ~31) : 0;
     const int tbl_bytes = (tbl_words * 4 + pad_bytes + 15) & ~15;
-    const float* s_lut = reinterpret_cast<const float*>(sQ);
-    const int* s_ccol = reinterpret_cast<const int*>(sQ) + lut_len;
-    const uint8_t* s_pad_w = sQ + static_cast<long>(tbl_words) * 4;    // key-padding bytes, zero beyond S up to a 32-key boundary
+    const uint8_t* tbl = big_tables ? sT : sQ;
+    const float* s_lut = reinterpret_cast<const float*>(tbl);
+    const int* s_ccol = reinterpret_cast<const int*>(tbl) + lut_len;
+    const uint8_t* s_pad_w = tbl + static_cast<long>(tbl_words) * 4;   // key-padding bytes, zero beyond S up to a 32-key boundary
     float* xch = reinterpret_cast<float*>(sQ + kTcTableBytes);         // [max | sum][half][row]
     float2* xstat = reinterpret_cast<float2*>(sQ + kTcTableBytes + 4 * kTcQ * 4);
     if constexpr (HAS_PAD) {
-      uint8_t* pad_in = sP + static_cast<long>(tbl_words) * 4;
+      uint8_t* pad_in = (big_tables ? sT : sP) + static_cast<long>(tbl_words) * 4;
       for (int i = tid4; i < pad_bytes; i += kRowThreads) pad_in[i] = i < Sk ? key_pad[static_cast<long>(b) * S + k0 + i] : 0;
     }
     const int crow = code_row[row_valid ? qrow : 0];
@@ -268,7 +273,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const float* __r
     if constexpr (HALVES > 1) xch[half * kTcQ + r] = m;
     mbar_wait(&bars->lut, 0);
     if constexpr (HAS_PAD) named_bar_sync(1, kRowThreads);       // pad bytes written by other threads
-    for (int i = tid4 * 16; i < tbl_bytes; i += kRowThreads * 16) sts128u(sQ + i, *reinterpret_cast<const uint4*>(sP + i));
+    if (!big_tables)
+      for (int i = tid4 * 16; i < tbl_bytes; i += kRowThreads * 16) sts128u(sQ + i, *reinterpret_cast<const uint4*>(sP + i));
     named_bar_sync(1, kRowThreads);
     if constexpr (HALVES > 1) m = fmaxf(m, xch[(half ^ 1) * kTcQ + r]);
     m += lut_max[h];
@@ -491,12 +497,15 @@ static int launch_tc(const void* qkv, const float* lut, const float* lut_max, in
   if (lut_len % 4 != 0 || (reinterpret_cast<uintptr_t>(lut) & 15) != 0 || (reinterpret_cast<uintptr_t>(code_col + k0) & 15) != 0)
     return OPB_ERR_INVALID;     // bulk-copied: 16-byte granularity (code_col must hold (S + 3) & ~3 entries)
   const long table_bytes = static_cast<long>(lut_len) * 4 + static_cast<long>((Sk + 3) & ~3) * 4 + Sk + 48;
-  if (table_bytes > kTcTableBytes) return OPB_ERR_UNSUPPORTED;   // the tables move into the (dead) 16 KB Q tile for phase B
+  // small tables move into the (dead) 16 KB Q tile for phase B; larger ones (long sequences) get their own region
+  const int big_tables = table_bytes > kTcTableBytes ? 1 : 0;
+  if (table_bytes > 40 * 1024) return OPB_ERR_UNSUPPORTED;
   const int D = H * kTcD;
   CUtensorMap tm;
   int rc = make_tmap_bf16_2d(&tm, qkv, static_cast<uint64_t>(B) * S, 3ull * D, 3ull * D, kTcQ);
   if (rc != OPB_OK) return rc;
-  const size_t smem = kTcQ * 128 + 2ull * nkb * kTcK * 128 + kTcQ * kTcK * 2 + sizeof(TcBars);
+  const size_t smem = kTcQ * 128 + 2ull * nkb * kTcK * 128 + kTcQ * kTcK * 2 + (big_tables ? 256 + ((table_bytes + 63) & ~63L) : sizeof(TcBars));
+  static_assert(sizeof(TcBars) <= 256, "");
   const uint32_t tmem_cols = nkb == 1 ? 128 : (nkb == 2 ? 256 : 512);
   static const char* env_h = getenv("OPB_ATTN_ROW_THREADS");          // 1 or 2 threads per query row (A/B switch), default 2
   const int halves = (env_h != nullptr && env_h[0] == '1') ? 1 : 2;
@@ -511,7 +520,7 @@ static int launch_tc(const void* qkv, const float* lut, const float* lut_max, in
   const unsigned grid = static_cast<unsigned>(static_cast<long>(B) * H * q_tiles);
   kern<<<grid, 64 + 128 * halves, smem, stream>>>(tm, lut, lut_max, lut_len, code_row, code_col + k0, key_pad,
                                                  reinterpret_cast<__nv_bfloat16*>(out), lse, ln_stats, B, S, H, nkb, tmem_cols, seg_split,
-                                                 k0, Sk);
+                                                 k0, Sk, big_tables);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

@@ -74,7 +74,7 @@ def gemm(a, w, epi, out, *, bias=None, colscale=None, gamma=None, resid=None, ou
 
 class RelPosBias:
     """Relative-position bias of one forward in both forms the attention kernels take: the dense fp32 (H,S,S_pad)
-    table (mma.sync kernel, any S) and the LUT form (tcgen05 kernel, S <= 384)."""
+    table (mma.sync kernel, any S) and the LUT form (tcgen05 kernels, S <= 768)."""
 
     def __init__(self, dense=None, lut=None, code_row=None, code_col=None, seg_split=0):
         self.dense, self.lut, self.code_row, self.code_col, self.seg_split = dense, lut, code_row, code_col, seg_split
@@ -109,9 +109,12 @@ def relpos_lut_build(table, idx):
     return lut
 
 
+ATTN_TC_MAX_S = 768      # tcgen05 attention forward: persistent kernel S <= 224, per-tile kernel S <= 384, two key ranges + merge S <= 768
+
+
 def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None, lse=None):
-    """tcgen05 attention (S <= 384).  rp: RelPosBias with the LUT form (rp.seg_split > 0: two concatenated modalities,
-    block-diagonal bias)."""
+    """tcgen05 attention (S <= 768).  rp: RelPosBias with the LUT form (rp.seg_split > 0: two concatenated modalities,
+    block-diagonal bias; S <= 384 then)."""
     D = H * 64
     assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * S, 3 * D) and qkv.is_contiguous()
     if out is None:

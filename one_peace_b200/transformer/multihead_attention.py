@@ -50,7 +50,7 @@ class MultiheadAttention(nn.Module):
         return self._cache.get(ps, build)
 
     def run_attention(self, qkv, bias, key_pad, B, S, out=None, ln_stats=None, lse=None):
-        """bias: kernels.RelPosBias (or None).  tcgen05 kernel when the bias is in LUT form (S <= 384), else mma.sync."""
+        """bias: kernels.RelPosBias (or None).  tcgen05 kernels when the bias is in LUT form (S <= 768), else mma.sync."""
         if bias is not None and bias.lut is not None:
             return K.attention_tc(qkv, bias, key_pad, B, S, self.num_heads, out=out, ln_stats=ln_stats, lse=lse)
         dense = bias.dense if bias is not None else None

@@ -31,6 +31,19 @@ t_new = timeit(lambda: K.attention_tc(qkv, rp, None, B, S, H, out=out, ln_stats=
 print(f"mma.sync {t_old:.1f} us | tcgen05 per-tile CTAs {t_tc:.1f} us | tcgen05 persistent {t_new:.1f} us | max diff vs mma.sync "
       f"{(out.float()-o_old.float()).abs().max().item():.3e} vs per-tile {(out.float()-o_tc.float()).abs().max().item():.3e} "
       f"ln_stats rel diff {((part-p_tc).abs().max()/p_tc.abs().max()).item():.3e}")
+# 15 s audio: 750 tokens (adapter/audio.py), 1-D relative positions: mma.sync flash kernel (dense bias) vs two tcgen05 key ranges + merge
+Ba, Sa = 16, 750
+qa = (torch.randn(Ba * Sa, 3 * D, device="cuda") * 0.5).bfloat16()
+ba = R.make_token_bucket_position(256)[:Sa, :Sa]
+ta = torch.randn(514, H, device="cuda")
+la = relpos.build_lut_index(ba.numpy(), relpos.text_codes(Sa))
+rpa = K.RelPosBias(lut=K.relpos_lut_build(ta, torch.from_numpy(la[0]).cuda()), code_row=torch.from_numpy(la[1]).cuda(), code_col=torch.from_numpy(la[2]).cuda())
+da = K.relpos_bias_build(ta, ba.cuda(), Sa, H)
+oa = torch.empty(Ba * Sa, D, dtype=torch.bfloat16, device="cuda")
+t_a0 = timeit(lambda: K.attention(qa, da, None, Ba, Sa, H, out=oa))
+o_a0 = oa.clone()
+t_a1 = timeit(lambda: K.attention_tc(qa, rpa, None, Ba, Sa, H, out=oa))
+print(f"audio B={Ba} S={Sa}: mma.sync {t_a0:.1f} us | tcgen05 two key ranges + merge {t_a1:.1f} us | max diff {(oa.float()-o_a0.float()).abs().max().item():.3e}")
 if "timing" in os.environ.get("OPB_LIB_PATH", ""):
     import ctypes
     from one_peace_b200 import _lib

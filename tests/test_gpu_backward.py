@@ -190,6 +190,20 @@ def test_attention_bwd_transposed_tables(K, B, S, H, pad):
     assert torch.all(dbias_t[:, S:, :] == 0) and torch.all(dbias_t[:, :, S:] == 0)
 
 
+def test_relpos_dbias_center(K):
+    """zero-row-sum projection of the accumulated bias gradient: every (head, query) row loses its mean over the S valid columns,
+    the padding columns stay untouched"""
+    H, S, s_pad = 3, 197, 200
+    g = gen(21)
+    db = torch.randn(H, S, s_pad, device="cuda", generator=g)
+    db[:, :, S:] = 7.0
+    want = db.clone()
+    want[:, :, :S] -= want[:, :, :S].mean(-1, keepdim=True)
+    K.relpos_dbias_center(db)
+    torch.testing.assert_close(db, want, atol=1e-5, rtol=1e-5)
+    assert db[:, :, :S].sum(-1).abs().max() < 1e-3
+
+
 def test_relpos_bias_bwd(K):
     S, H, NB = 50, 4, 37
     g = gen(3)

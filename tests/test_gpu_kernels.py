@@ -286,9 +286,13 @@ def test_attention_ln_stats(K):
 
 
 @pytest.mark.parametrize("kind,B,S,H,use_pad", [("text", 3, 17, 4, True), ("text", 2, 72, 4, True), ("image", 3, 197, 24, False),
-                                                 ("image", 2, 257, 4, False), ("text", 2, 384, 2, True), ("text", 5, 128, 4, False)])
+                                                 ("image", 2, 257, 4, False), ("text", 2, 384, 2, True), ("text", 5, 128, 4, False),
+                                                 ("text", 2, 750, 3, True), ("text", 3, 500, 2, False), ("text", 1, 768, 2, True),
+                                                 ("text", 2, 385, 2, True)])
 def test_attention_tc(K, kind, B, S, H, use_pad):
-    """tcgen05 attention with the LUT-form relative-position bias vs a plain fp32 reference on the dense bias."""
+    """tcgen05 attention with the LUT-form relative-position bias vs a plain fp32 reference on the dense bias.  S <= 224: the
+    persistent kernel; S <= 384: one CTA per (batch, head, q-tile); 384 < S <= 768 (the 10-15 s audio sequences, whose buckets
+    are the 1-D text scheme, adapter/audio.py:20-32): two key ranges + merge."""
     import numpy as np
     import restated as R
     from one_peace_b200 import relpos
