@@ -49,8 +49,10 @@ constexpr int kColST = 0, kColDPT = 112, kColDV = 224, kColDK = 288, kColDQ = 35
 // sit at compile-time offsets from one pointer per sub-step (no per-element address arithmetic, clamps or predicates)
 constexpr int kTKeys = 256, kTQ = 224;
 
+// no "memory" clobber: the table is only ever touched by these reductions, and a clobber would pin every block's shared-memory loads
+// behind the previous block's reduction (no overlap between the 8 blocks of a sub-step)
 OPB_DEVICE void red_add_v2(float* p, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b));
 }
 
 struct BwdBars {

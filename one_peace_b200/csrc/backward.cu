@@ -99,7 +99,8 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
   // Software pipeline over the CTA's rows: the loads of row r + gridDim (and the old dx of row r when accumulating) are
   // issued before the three block reductions of row r, so HBM latency hides behind them (round 1 issued them after:
   // 0.46 of the HBM peak).
-  auto load_row = [&](int row, float4 (&xr)[GROUPS], float4 (&gr)[GROUPS]) {
+  auto load_row = [&](int row, float4 (&xr)[GROUPS], float4 (&gr)[GROUPS], float& shift) {
+    shift = load4(x + row * ldx).x;          // x[row][0]: the shift of the single-pass statistics, fetched with the row (broadcast)
     // the forward's 2x2 pixel-merge scatter (layernorm.cu, adapter/image.py:37-47): row (b, y, x) of the w x w grid
     // went to row (b, y/2, x/2), column block (y%2)*2 + x%2 of the next conv's operand
     const TDY* dyr = dy + row * ld_dy;
@@ -121,18 +122,20 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
   };
   constexpr bool kPrefetch = THREADS == 128;   // dim <= 1536 variants only: the wider ones have no registers to spare (and 12-24 KB rows)
   float4 xn[kPrefetch ? GROUPS : 1], gn[kPrefetch ? GROUPS : 1];
+  float kn = 0.f;
   if constexpr (kPrefetch) {
-    if (blockIdx.x < rows) load_row(blockIdx.x, xn, gn);
+    if (blockIdx.x < rows) load_row(blockIdx.x, xn, gn, kn);
   }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     float4 xv[GROUPS], gv[GROUPS], oldv[GROUPS];
-    float s1 = 0.f;
+    float s1 = 0.f, ksh = 0.f;
     if constexpr (kPrefetch) {
 #pragma unroll
       for (int k = 0; k < GROUPS; ++k) { xv[k] = xn[k]; gv[k] = gn[k]; }
-      if (row + static_cast<int>(gridDim.x) < rows) load_row(row + gridDim.x, xn, gn);
+      ksh = kn;
+      if (row + static_cast<int>(gridDim.x) < rows) load_row(row + gridDim.x, xn, gn, kn);
     } else {
-      load_row(row, xv, gv);
+      load_row(row, xv, gv, ksh);
     }
     if (accumulate) {
 #pragma unroll
@@ -146,7 +149,6 @@ layernorm_bwd_kernel(const TX* __restrict__ x, long ldx, const TDY* __restrict__
       // ran at 0.68 of the HBM peak, the CTA idling in three barrier pairs per row).  With the shift K = x[row][0]:
       //   mean = K + S1/n, var = S2/n - (S1/n)^2            S1 = sum (x-K), S2 = sum (x-K)^2   (shifted: no cancellation)
       //   sum dy g = B1,   sum dy g xhat = rstd (B2 - (S1/n) B1)                                 B2 = sum dy g (x-K)
-      const float ksh = load4(x + row * ldx).x;
       float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
       for (int k = 0; k < GROUPS; ++k) {

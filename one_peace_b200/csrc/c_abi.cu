@@ -5,6 +5,8 @@
 #include "gemm.h"
 #include "ops.h"
 
+#include <stdlib.h>
+
 extern "C" {
 
 int opb_abi_version(void) { return 2; }
@@ -312,8 +314,13 @@ int opb_attention_bwd_t(const void* qkv, const void* out, const void* d_out, con
   if (S > 224) return OPB_ERR_UNSUPPORTED;
   const int rc = opb::attn_delta(d_out, out, delta, B, S, H, static_cast<cudaStream_t>(stream));
   if (rc != OPB_OK) return rc;
-  return opb::attention_bwd_tc(qkv, d_out, nullptr, key_pad, lse, delta, dqkv, nullptr, B, S, H, 0, q_scale, 0, bias_t, dbias_t,
-                               static_cast<cudaStream_t>(stream));
+  // OPB_ATTN_BWD_V=1: the single-buffered kernel (attention_bwd_tc.cu); default: the double-buffered one (attention_bwd_tc2.cu)
+  const char* env_v = getenv("OPB_ATTN_BWD_V");              // read per call: tests switch it in-process
+  if (env_v != nullptr && env_v[0] == '1')
+    return opb::attention_bwd_tc(qkv, d_out, nullptr, key_pad, lse, delta, dqkv, nullptr, B, S, H, 0, q_scale, 0, bias_t, dbias_t,
+                                 static_cast<cudaStream_t>(stream));
+  return opb::attention_bwd_tc2(qkv, d_out, key_pad, lse, delta, dqkv, B, S, H, q_scale, bias_t, dbias_t,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int opb_relpos_bias_transpose(const float* bias, void* bias_t, int S, int s_pad, int H, void* stream) {

@@ -110,6 +110,9 @@ int attention_bwd(const void* qkv, const void* out, const void* d_out, const flo
 int attention_bwd_tc(const void* qkv, const void* d_out, const float* bias, const uint8_t* key_pad, const float* lse,
                      const float* delta, void* dqkv, float* dbias, int B, int S, int H, int s_pad, float q_scale,
                      long bias_bstride, const void* bias_t, float* dbias_t, cudaStream_t stream);
+// double-buffered form (attention_bwd_tc2.cu): transposed tables only
+int attention_bwd_tc2(const void* qkv, const void* d_out, const uint8_t* key_pad, const float* lse, const float* delta, void* dqkv,
+                      int B, int S, int H, float q_scale, const void* bias_t, float* dbias_t, cudaStream_t stream);
 int relpos_bias_transpose(const float* bias, void* bias_t, int S, int s_pad, int H, cudaStream_t stream);
 int relpos_dbias_fold(const float* dbias_t, float* dbias, int S, int s_pad, int H, cudaStream_t stream);
 int relpos_dbias_center(float* dbias, int S, int s_pad, int H, cudaStream_t stream);

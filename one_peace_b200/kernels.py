@@ -109,7 +109,12 @@ def relpos_lut_build(table, idx):
     return lut
 
 
-ATTN_TC_MAX_S = 768      # tcgen05 attention forward: persistent kernel S <= 224, per-tile kernel S <= 384, two key ranges + merge S <= 768
+# tcgen05 attention forward: persistent kernel S <= 224, per-tile kernel S <= 384.  384 < S <= 768 also runs on tcgen05 (two key
+# ranges + merge, csrc/attention_tc.cu) but measured SLOWER than the flash-style mma.sync kernel at the audio shape (B = 16,
+# S = 750, H = 24: 601 us vs 465 us, profiles/r02_attention_fwd_bwd.txt): with 384 keys per launch the per-tile kernel runs one CTA
+# per SM and its TMA / MMA / soft-max phases no longer overlap.  The adapters therefore keep the dense-bias kernel for S > 384 unless
+# OPB_ATTN_LONG_TC=1.
+ATTN_TC_MAX_S = 768 if __import__("os").environ.get("OPB_ATTN_LONG_TC", "0") == "1" else 384
 
 
 def attention_tc(qkv, rp, key_pad, B, S, H, out=None, ln_stats=None, lse=None):

@@ -28,28 +28,33 @@ class _Table:
 
     def __init__(self):
         self.key = None
+        self.shape_key = None
 
     def build(self, entries, device):
-        """entries: list of (p, g, m, v, master_or_None, group_index)"""
+        """entries: list of (p, g, m, v, master_or_None, group_index).  The chunk tables depend on the tensor sizes only and are
+        kept while those do not change; a moved pointer (a re-allocated .grad) costs one small record upload."""
         key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 0 if ms is None else ms.data_ptr(), gi)
                     for p, g, m, v, ms, gi in entries)
         if key == self.key:
             return
-        chunk = _lib.load().opb_adam_chunk_elems()
         rec = np.zeros(len(entries), dtype=_REC)
-        ct, co = [], []
         for i, (p, g, m, v, ms, gi) in enumerate(entries):
             rec[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 0 if ms is None else ms.data_ptr(),
                       p.numel(), gi, _DT[p.dtype], _DT[g.dtype], 0)
-            n = p.numel()
-            offs = np.arange(0, n, chunk, dtype=np.int64)
-            ct.append(np.full(len(offs), i, dtype=np.int32))
-            co.append(offs)
         self.tensors = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
-        self.chunk_tensor = torch.from_numpy(np.concatenate(ct)).to(device)
-        self.chunk_off = torch.from_numpy(np.concatenate(co)).to(device)
-        self.n_chunks = int(self.chunk_tensor.numel())
-        self.partial = torch.empty(self.n_chunks, dtype=torch.float32, device=device)
+        shape_key = (str(device),) + tuple(p.numel() for p, *_ in entries)
+        if shape_key != self.shape_key:
+            chunk = _lib.load().opb_adam_chunk_elems()
+            ct, co = [], []
+            for i, (p, *_rest) in enumerate(entries):
+                offs = np.arange(0, p.numel(), chunk, dtype=np.int64)
+                ct.append(np.full(len(offs), i, dtype=np.int32))
+                co.append(offs)
+            self.chunk_tensor = torch.from_numpy(np.concatenate(ct)).to(device)
+            self.chunk_off = torch.from_numpy(np.concatenate(co)).to(device)
+            self.n_chunks = int(self.chunk_tensor.numel())
+            self.partial = torch.empty(self.n_chunks, dtype=torch.float32, device=device)
+            self.shape_key = shape_key
         self.key = key
 
 
@@ -62,6 +67,7 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.master_weights = master_weights
         self._table = _Table()
+        self._norm_table = _Table()
         self._norm_out = None
 
     @property
@@ -176,8 +182,8 @@ class Adam(torch.optim.Optimizer):
         if not entries:
             return None
         dev = entries[0][0].device
-        tab = _Table()
-        tab.build(entries, dev)
+        tab = self._norm_table        # cached: rebuilding the chunk tables (184 k chunks for the 4B vision branch) every step cost
+        tab.build(entries, dev)       # 0.3 ms of host work + three synchronous uploads, as much as the reduction itself
         out = torch.empty(2, dtype=torch.float32, device=dev)
         st = _lib.load().opb_grad_norm_clip(tab.tensors.data_ptr(), tab.chunk_tensor.data_ptr(), tab.chunk_off.data_ptr(),
                                             tab.n_chunks, tab.partial.data_ptr(), float(multiply_factor), float(max_norm),
