@@ -20,10 +20,11 @@ Extra blocks in the same line:
   contrastive         the path that HAS a collective (BASELINE.json configs[3]), at every N:
       head            InfoNCE fwd+bwd on synthetic unit-norm embeddings, local b = 1024 / rank: NCCL all-gather of both
                       modalities + fused loss / gradient kernels -> pairs/s, all-gather ms, parity vs the oracle on rank 0
-      train_step      full image-text training step of the 4B text+image branches (encoder fwd/bwd with activation
-                      recompute + all-gather + InfoNCE + gradient reduce-scatter -> sharded fused Adam -> all-gather)
+      train_step      full image-text training step of the 4B text+image branches (encoder fwd/bwd, activations kept in HBM
+                      when they fit + all-gather + InfoNCE + gradient reduce-scatter -> sharded fused Adam -> all-gather)
   gpu_eager_baseline  (N = 1) the reference's arithmetic (oracle/restated.py) in PyTorch eager bf16 on the same B200
-                      (ATen / cuBLAS) for the config-2 forward: the "reference on the same box" bar
+                      (ATen / cuBLAS) for the config-2 forward AND the image-text training step (torch autograd + activation
+                      checkpointing + fused torch AdamW): the "reference on the same box" bar
   hbm_kernels         (N = 1) CUDA-event GB/s of the HBM-bound kernels against MEASURED_PEAKS hbm_gbs
 Skip them with --no-extras (the headline keys are unaffected).
 """
@@ -271,6 +272,14 @@ def run_b200(args):
                     extras[key] = {"error": repr(e)[:300]}
             if "forward" in extras.get("gpu_eager_baseline", {}):
                 extras["gpu_eager_baseline"]["repo_over_eager_forward"] = round(value / extras["gpu_eager_baseline"]["forward"]["value"], 3)
+                try:
+                    et = eager_bf16_train_baseline(dev)
+                    extras["gpu_eager_baseline"]["train_step"] = et
+                    ts = extras.get("contrastive", {}).get("train_step", {})
+                    if "value" in ts:
+                        extras["gpu_eager_baseline"]["repo_over_eager_train_step"] = round(ts["value"] / et["value"], 3)
+                except Exception as e:
+                    extras["gpu_eager_baseline"]["train_step"] = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {
@@ -506,6 +515,64 @@ def eager_bf16_forward_baseline(dev, steps=5):
                     "xformers / apex / flash-attn (the reference ships no Blackwell kernel)", "torch": torch.__version__}
 
 
+def eager_bf16_train_baseline(dev, b=64, text_len=32, steps=3):
+    """The reference's training arithmetic for the image-text contrastive step, as PyTorch eager bf16 on this GPU: oracle/restated.py
+    text + image encoders (40 DISTINCT layers each branch's FFN, 2.73 B bf16 parameters drawn on the device), torch autograd with
+    per-layer activation checkpointing (the recipes' checkpoint_activations), InfoNCE, clip_grad_norm_ and torch's fused Adam.
+    No apex / xformers / flash-attn (not in the image; the reference ships no Blackwell kernel).  Same pairs, text length and
+    parameter count as contrastive.train_step."""
+    import torch
+    from torch.utils.checkpoint import checkpoint
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restated as R
+    import synth
+    sd1 = synth.make_state_dict(embed_dim=D, ffn=FFN, layers=1, heads=H, modalities=("text", "image"), seed=0, gamma_range=(0.05, 0.15))
+    g = torch.Generator(device=dev).manual_seed(11)
+    sd = {}
+    for k, v in sd1.items():
+        if "layers.0." in k:
+            for i in range(LAYERS):
+                t = v.to(dev, torch.bfloat16) if i == 0 else \
+                    (torch.randn(v.shape, device=dev, generator=g) * float(v.float().std().clamp_min(1e-3)) + float(v.float().mean())).to(torch.bfloat16)
+                sd[k.replace("layers.0.", f"layers.{i}.")] = t.requires_grad_(True)
+        else:
+            t = v.to(dev, torch.bfloat16) if v.is_floating_point() else v.to(dev)
+            sd[k] = t.requires_grad_(True) if t.is_floating_point() else t
+    cfg = R.OracleConfig(embed_dim=D, ffn_embed_dim=FFN, layers=LAYERS, attention_heads=H)
+    params = [v for v in sd.values() if torch.is_tensor(v) and v.requires_grad]
+    n_params = sum(q.numel() for q in params)
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05, fused=True)
+    tok = torch.randint(4, 50264, (b, text_len), device=dev, generator=g)
+    img = torch.randn(b, 3, RES, RES, device=dev, generator=g).to(torch.bfloat16)
+    orig = R.encoder_layer
+
+    def ckpt_layer(sd_, cfg_, x, bias, pad, modality, pfx):
+        return checkpoint(lambda xx: orig(sd_, cfg_, xx, bias, pad, modality, pfx), x, use_reentrant=False)
+    R.encoder_layer = ckpt_layer
+    try:
+        def step():
+            opt.zero_grad(set_to_none=True)
+            te = R.extract_features(sd, cfg, "text", src_tokens=tok)
+            ie = R.extract_features(sd, cfg, "image", src_images=img)
+            loss, _, _ = R.itc_loss(ie.float(), te.float(), ie.detach().float(), te.detach().float(),
+                                    R.logit_scale_exp(sd["logit_scale"].float()), 0, 0.0)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 3.0, foreach=True)
+            opt.step()
+            return loss
+        step()
+        ms = _ev_ms(step, steps, torch)
+    finally:
+        R.encoder_layer = orig
+    mem = round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)
+    del opt, sd, params
+    torch.cuda.empty_cache()
+    return {"value": round(b / (ms / 1e3), 2), "unit": "pairs/s", "ms_per_step": round(ms, 2), "pairs": b, "text_len": text_len,
+            "params_b": round(n_params / 1e9, 3), "max_mem_gb": mem,
+            "what": "oracle/restated.py text + image branches, torch autograd + per-layer activation checkpointing, InfoNCE, "
+                    "clip_grad_norm_, fused torch AdamW; eager bf16 (ATen / cuBLAS)"}
+
+
 def hbm_kernels_block(dev):
     """Achieved GB/s of the HBM-bound kernels (CUDA events, buffers >> 126 MB L2) vs the measured copy bandwidth."""
     import ctypes
@@ -602,10 +669,12 @@ def cpu_reference(steps, warmup, sample_images):
         for th in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
             torch.set_num_threads(th)
             R.encoder_layer(sd, cfg, xp, None, padp, "image", "encoder_wrapper.fusion_model.layers.0.")
-            t0 = time.perf_counter()
-            R.encoder_layer(sd, cfg, xp, None, padp, "image", "encoder_wrapper.fusion_model.layers.1.")
-            dt = time.perf_counter() - t0
-            if dt < best[1]:
+            dt = float("inf")
+            for rep in range(3):            # best of three: a single probe made the two arms pick different counts (r01: 32 vs 16)
+                t0 = time.perf_counter()
+                R.encoder_layer(sd, cfg, xp, None, padp, "image", f"encoder_wrapper.fusion_model.layers.{1 + rep}.")
+                dt = min(dt, time.perf_counter() - t0)
+            if dt < best[1] * 0.97:         # ties go to the larger thread count tried first
                 best = (th, dt)
         threads = best[0]
         torch.set_num_threads(threads)

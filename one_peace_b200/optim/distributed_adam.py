@@ -110,12 +110,19 @@ class DistributedAdam(torch.optim.Optimizer):
         """flat gradient buffer -> reduce-scatter (mean) -> this rank's shard; then the global gradient norm from the
         shard norms (deterministic two-stage kernel + one scalar all-reduce).  -> fp32 device scalar ||g||_2."""
         self._has_grad = [p.grad is not None for _, p in self._plist]
-        for (gi, p), off in zip(self._plist, self.offsets):
-            dst = self.flat_grad[off:off + p.numel()]
+        # one multi-tensor copy instead of ~1900 small launches (26 -> 13 ms of the step at 2.73 B parameters, where the
+        # per-parameter loop was bound by Python and launch latency, not by the 11 GB it moves)
+        if getattr(self, "_flat_views", None) is None:
+            self._flat_views = [self.flat_grad[off:off + p.numel()].view(p.shape) for (_, p), off in zip(self._plist, self.offsets)]
+        dsts, srcs = [], []
+        for (gi, p), view in zip(self._plist, self._flat_views):
             if p.grad is None:
-                dst.zero_()
+                view.zero_()
             else:
-                dst.copy_(p.grad.reshape(-1))
+                dsts.append(view)
+                srcs.append(p.grad if p.grad.dtype == view.dtype else p.grad.to(view.dtype))
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
         if self.world > 1:
             dist.reduce_scatter_tensor(self.gshard, self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
         else:
