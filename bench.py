@@ -47,6 +47,23 @@ METRIC = "encoder_samples_per_sec"
 UNIT = "samples/s"
 
 
+def _ncu_traffic_bytes():
+    """DRAM bytes of the dominant GEMM launch (GeGLU epilogue, the `<2, 1, 1>` instantiation) from the committed ncu capture."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02_ncu_layer_full.raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if "gemm_bf16_kernel<2, 1, 1>" in r[ik] or "gemm_bf16_kernel<(int)2, (int)1, (bool)1>" in r[ik]:
+                return float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
+    except Exception:
+        pass
+    return None
+
+
 def _policy():
     from one_peace_b200 import autograd
     return autograd._POLICY
@@ -244,7 +261,10 @@ def run_b200(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE GeGLU launch (the dominant shape, 12608x12288x1536)
                 # from the `ncu --set full` capture summarised in profiles/r01_ncu_gemm_full_final.summary.txt; its
                 # algorithmic bytes are A 38.7 + W 37.7 + out 154.9 = 231.4 MB: no wasted re-reads
-                "traffic": 225.08e6, "traffic_kernel": "gemm_bf16_kernel<2,GEGLU,TMA> (12608 x 12288 x 1536)",
+                "traffic": _ncu_traffic_bytes(), "traffic_kernel": "gemm_bf16_kernel<2,GEGLU,TMA> (12608 x 12288 x 1536)",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch in profiles/r02_ncu_layer_full.raw.csv "
+                                  "(ncu --set full; parsed at run time, not re-measured: ncu cannot run inside the bench); algorithmic "
+                                  "bytes of the launch: A 38.7 + W 37.7 + out 154.9 = 231.4 MB",
                 "launches": len(recs), "avg_launch_ms": round(gemm_ms / max(1, len(recs)), 4),
                 "gemm_share_of_step": round(gemm_ms / step_ms, 4),
                 "per_shape_tflops": {k: round(v[1] / (v[0] / 1e3) / 1e12, 1) for k, v in by_shape.items()},

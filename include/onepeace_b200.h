@@ -266,6 +266,21 @@ int opb_infonce_grad(const void* a_local, const void* b_all, const void* bT_all,
                      void* stream);
 int opb_infonce_dscale(const float* ws_gz_a, const float* ws_gz_b, int b, int n, float* out, void* stream);
 
+/* The two-direction step with fewer launches (9 instead of 14; same arithmetic as the entries above):
+ *   opb_split_bf16x3_x4       the four operand splits (a_local, b_local: side 0; a_all, b_all: side 1) in one launch;
+ *                             xs / outs / rows / sides: HOST arrays of 4
+ *   opb_infonce_lse_gemm      the LSE_PARTIAL GEMM of one direction (what opb_infonce_rows runs before its merge kernel)
+ *   opb_infonce_merge_reduce  merges both directions' partials (row_lse_a / row_lse_b out, needed by opb_infonce_grad) and writes
+ *                             out3 as opb_infonce_reduce does, in one launch: the last block to finish performs the fixed-order
+ *                             reduction.  Scratch: loss_ab fp32 [2 b], argmax_ab int32 [2 b], ticket = one uint32 that must be
+ *                             zero on entry and is left at zero. */
+int opb_split_bf16x3_x4(const float* const* xs, void* const* outs, const int64_t* rows, const int* sides, int d, void* stream);
+int opb_infonce_lse_gemm(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
+                         float* ws, int n_valid, void* stream);
+int opb_infonce_merge_reduce(const float* ws_a, const float* ws_b, int b, int n, int n_valid, float label_smoothing,
+                             int target_offset, float* row_lse_a, float* row_lse_b, float* loss_ab, int* argmax_ab, float* out3,
+                             uint32_t* ticket, void* stream);
+
 /*
  * Fused multi-tensor Adam (optim/adam.py:173-253 python form; optional fp32 master as optim/adam_fused.py:45-50)
  * and global grad-norm + clip coefficient (optim/fp16_optimizer_memory_efficent.py:96-116, bf16 branch).

@@ -33,21 +33,19 @@ class _InfoNCE(torch.autograd.Function):
     def forward(ctx, a_local, b_local, a_all, b_all, scale, rank, eps):
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         d = a_local.shape[1]
-        # bf16x3 operand split: logits accurate to ~2^-16 on the bf16 tensor cores (csrc/infonce.cu)
-        a3, b3 = K.split_bf16x3(f32(a_local), 0), K.split_bf16x3(f32(b_local), 0)
+        # bf16x3 operand split: logits accurate to ~2^-16 on the bf16 tensor cores (csrc/infonce.cu); the four splits are one launch
         n_cls = a_all.shape[0]
         fa, fb = f32(a_all), f32(b_all)
         if n_cls % 8:                 # the GEMM wants N % 8 == 0: zero rows, ignored through n_valid (tiny global batches)
             padr = torch.zeros((-n_cls) % 8, d, dtype=torch.float32, device=fa.device)
             fa, fb = torch.cat([fa, padr]), torch.cat([fb, padr])
-        a_all3, b_all3 = K.split_bf16x3(fa, 1), K.split_bf16x3(fb, 1)
+        a3, b3, a_all3, b_all3 = K.split_bf16x3_x4([f32(a_local), f32(b_local), fa, fb], [0, 0, 1, 1])
         s = scale.detach().to(torch.float32).reshape(1).contiguous()
         bsz, n = a3.shape[0], a_all3.shape[0]
         nv = n_cls if n_cls != n else 0
         off = bsz * rank
-        lse_a, loss_a, am_a = K.infonce_rows(a3, b_all3, s, off, eps, n_valid=nv)
-        lse_b, loss_b, am_b = K.infonce_rows(b3, a_all3, s, off, eps, n_valid=nv)
-        out = K.infonce_reduce(loss_a, loss_b, am_a, am_b, off)
+        # two LSE GEMMs + ONE merge / reduce kernel for both directions (the last block to finish does the fixed-order reduction)
+        lse_a, lse_b, out = K.infonce_forward2(a3, b3, a_all3, b_all3, s, off, eps, n_valid=nv)
         if a_local.requires_grad or b_local.requires_grad or scale.requires_grad:
             ga, ws_a = K.infonce_grad(a3, b_all3, None, s, lse_a, off, eps, n_valid=nv, d=d)      # G . B_all reads B_all MN-major
             gb, ws_b = K.infonce_grad(b3, a_all3, None, s, lse_b, off, eps, n_valid=nv, d=d)

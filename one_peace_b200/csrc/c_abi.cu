@@ -180,6 +180,27 @@ int opb_split_bf16x3(const float* x, void* out, int64_t rows, int d, int side, v
 
 int64_t opb_infonce_ws_floats(int b, int n) { return opb::infonce_ws_floats(b, n); }
 
+int opb_split_bf16x3_x4(const float* const* xs, void* const* outs, const int64_t* rows, const int* sides, int d, void* stream) {
+  if (!xs || !outs || !rows || !sides) return OPB_ERR_INVALID;
+  long r[4];
+  for (int t = 0; t < 4; ++t) r[t] = static_cast<long>(rows[t]);
+  return opb::split_bf16x3_x4(xs, outs, r, sides, d, static_cast<cudaStream_t>(stream));
+}
+
+int opb_infonce_lse_gemm(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
+                         float* ws, int n_valid, void* stream) {
+  if (!a_local || !b_all || !scale || !ws) return OPB_ERR_INVALID;
+  return opb::infonce_lse_gemm(a_local, b_all, scale, b, n, d, target_offset, ws, n_valid, static_cast<cudaStream_t>(stream));
+}
+
+int opb_infonce_merge_reduce(const float* ws_a, const float* ws_b, int b, int n, int n_valid, float label_smoothing,
+                             int target_offset, float* row_lse_a, float* row_lse_b, float* loss_ab, int* argmax_ab, float* out3,
+                             uint32_t* ticket, void* stream) {
+  if (!ws_a || !ws_b || !row_lse_a || !row_lse_b || !loss_ab || !argmax_ab || !out3 || !ticket) return OPB_ERR_INVALID;
+  return opb::infonce_merge_reduce(ws_a, ws_b, b, n, n_valid, label_smoothing, target_offset, row_lse_a, row_lse_b, loss_ab,
+                                   argmax_ab, out3, ticket, static_cast<cudaStream_t>(stream));
+}
+
 int opb_infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d,
                      int target_offset, float label_smoothing, float* ws, float* row_lse, float* row_loss,
                      int* row_argmax, int n_valid, void* stream) {

@@ -320,14 +320,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       if (tile >= num_main) {
-        // ---- M-tail piece: add the raw partial accumulators of the valid rows into the fp32 workspace ----
+        // ---- M-tail piece: the raw partial accumulators of the valid rows go to THIS PIECE's slab of the fp32 workspace
+        // ([piece][tile row][N], plain stores); the fix-up kernel adds the slabs in piece order — deterministic, no memset, no
+        // atomics (round 1 added all pieces into one tile with fp32 atomics: run-to-run different low bits) ----
         const int n_blk_t = (tile - num_main) / geo.tail_pieces;
+        const int piece = (tile - num_main) % geo.tail_pieces;
         const int rl = static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;     // row inside the tail tile
         const bool rv = rl < (M - num_m_tiles * tile_m_rows);
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr_t = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBlockN;
-        float* wrow = geo.tail_ws + static_cast<long>(rl) * N + n_blk_t * kBlockN;
+        float* wrow = geo.tail_ws + (static_cast<long>(piece) * tile_m_rows + rl) * N + n_blk_t * kBlockN;
 #pragma unroll 1
         for (int c = 0; c < kBlockN; c += 32) {
           uint32_t v[32];
@@ -343,8 +346,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (n_blk_t * kBlockN + c + j < N)
-                atomicAdd(reinterpret_cast<float4*>(wrow + c + j),
-                          make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                *reinterpret_cast<float4*>(wrow + c + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
           }
         }
@@ -978,9 +981,11 @@ extern "C" void opb_gemm_timing_dump(int reset) {
 
 // Epilogue of the split-K M-tail rows: x = resid + gamma * (rstd * (acc - mu * colsum) + bias) from the summed raw
 // accumulators; writes the fp32 row, its bf16 copy and the per-256-column (sum, sum of squares) statistics records.
-// One CTA (256 threads) per tail row; thread t owns column t of every 256-column tile.
+// One CTA (256 threads) per (tail row, 256-column tile) — grid (rows, n_tiles): the round-1 kernel walked the tiles of a row
+// serially (6 dependent ~1 us iterations; 18 for the q/k/v projection of a small batch).
 __global__ void __launch_bounds__(256)
-gemm_tail_epilogue_kernel(const float* __restrict__ ws, const GemmEpilogue ep, int M, int N, int row0, int n_tiles) {
+gemm_tail_epilogue_kernel(const float* __restrict__ ws, const GemmEpilogue ep, int M, int N, int row0, int n_tiles, int pieces,
+                          int tile_rows, int epi) {
   __shared__ float red[2][8];
   const int row = row0 + blockIdx.x;
   float mu, rs;
@@ -1003,17 +1008,24 @@ gemm_tail_epilogue_kernel(const float* __restrict__ ws, const GemmEpilogue ep, i
     load_ln_stats(ep, row, M, mu, rs);
   }
   const float* w = ws + static_cast<long>(blockIdx.x) * N;
-  for (int t = 0; t < n_tiles; ++t) {
+  const long slab = static_cast<long>(tile_rows) * N;
+  {
+    const int t = blockIdx.y;
     const int col = t * kBlockN + threadIdx.x;
     float x = 0.f;
     if (col < N) {
-      x = w[col];
+      for (int p = 0; p < pieces; ++p) x += w[p * slab + col];          // fixed piece order
       if (ep.ln_colsum) x = rs * (x - mu * ep.ln_colsum[col]);
       if (ep.bias) x += ep.bias[col];
-      if (ep.gamma) x *= ep.gamma[col];
-      if (ep.resid) x += ep.resid[static_cast<long>(row) * ep.ldr + col];
-      reinterpret_cast<float*>(ep.out)[static_cast<long>(row) * ep.ldo + col] = x;
-      if (ep.out_bf16) reinterpret_cast<__nv_bfloat16*>(ep.out_bf16)[static_cast<long>(row) * ep.ldo_bf16 + col] = __float2bfloat16(x);
+      if (epi == EPI_STORE_BF16) {          // q/k/v projection of a small batch: (LN-folded acc + bias) * colscale -> bf16
+        if (ep.colscale) x *= ep.colscale[col];
+        reinterpret_cast<__nv_bfloat16*>(ep.out)[static_cast<long>(row) * ep.ldo + col] = __float2bfloat16(x);
+      } else {
+        if (ep.gamma) x *= ep.gamma[col];
+        if (ep.resid) x += ep.resid[static_cast<long>(row) * ep.ldr + col];
+        reinterpret_cast<float*>(ep.out)[static_cast<long>(row) * ep.ldo + col] = x;
+        if (ep.out_bf16) reinterpret_cast<__nv_bfloat16*>(ep.out_bf16)[static_cast<long>(row) * ep.ldo_bf16 + col] = __float2bfloat16(x);
+      }
     }
     if (ep.stats_out != nullptr) {
       float s1 = warp_sum(x), s2 = warp_sum(x * x);
@@ -1221,26 +1233,36 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   geo.a_mn = geo.b_mn = 0;
   if (cta_group == 2 && geo.n_umma % 32 != 0) cta_group = 1;   // each CTA of a pair stages n_umma / 2 rows of B
   // M-tail split-K: worth it when dropping the partial row of tiles saves a whole wave
+  static const char* env_tail = getenv("OPB_GEMM_TAIL_SPLITK");
+  const bool tail_ok = epi == EPI_RESID_F32 && ep.workspace != nullptr && ep.out_group == 0 && ep.resid_period == 0 &&
+                       !(env_tail != nullptr && env_tail[0] == '0');
+  // Small-M mode (M < 256: a handful of texts through the 4B stack): N / 256 = 6 output tiles would leave 142 SMs idle while six
+  // CTAs stream the whole weight (fc2: 18.9 MB at ~40 GB/s per CTA — 8 texts took 150 us per layer, launch-free or not).  The
+  // GEMM becomes ONE 256-row "tail" (CTA pairs) whose K range is split over all clusters; the fix-up kernel applies the epilogue.
+  const bool small_ok = (epi == EPI_RESID_F32 || (epi == EPI_STORE_BF16 && ep.stats_out == nullptr)) && ep.workspace != nullptr &&
+                        ep.out_group == 0 && ep.resid_period == 0 && !(env_tail != nullptr && env_tail[0] == '0');
+  const bool small_m = small_ok && M < 2 * kBlockM && N >= kBlockN && geo.num_k_blocks >= 8 &&
+                       ep.workspace_bytes >= 2L * (2 * kBlockM) * N * 4;
+  if (small_m) cta_group = 2;
   const int tile_m = kBlockM * cta_group;
   const int m_full = M / tile_m, tail_rows = M % tile_m;
   const int n_t = (N + kBlockN - 1) / kBlockN;
-  static const char* env_tail = getenv("OPB_GEMM_TAIL_SPLITK");
   // (measured: pays for K >= 3072 — fc2 232 -> 212 us; for K = 1536 the memset + atomics + tail kernel cost more than
-  //  the saved wave — out_proj 78 -> 89 us — so short-K GEMMs keep the plain schedule)
-  if (epi == EPI_RESID_F32 && tail_rows > 0 && m_full > 0 && ep.workspace != nullptr && geo.num_k_blocks >= 48 &&
-      ep.workspace_bytes >= static_cast<long>(tile_m) * N * 4 && ep.out_group == 0 && ep.resid_period == 0 &&
-      !(env_tail != nullptr && env_tail[0] == '0')) {
+  //  the saved wave — out_proj 78 -> 89 us — so short-K GEMMs keep the plain schedule unless the whole GEMM is one small tile)
+  if ((tail_ok || small_m) && tail_rows > 0 && (small_m || (m_full > 0 && geo.num_k_blocks >= 48)) &&
+      ep.workspace_bytes >= 2L * tile_m * N * 4) {
     const int clusters = sm_count() / cta_group;
     const int waves_all = ((m_full + 1) * n_t + clusters - 1) / clusters;
     const int waves_main = (m_full * n_t + clusters - 1) / clusters;
-    if (waves_main < waves_all) {
+    if (small_m || waves_main < waves_all) {
       int pieces = clusters / n_t;
       if (pieces > geo.num_k_blocks) pieces = geo.num_k_blocks;
+      const long slabs = ep.workspace_bytes / (static_cast<long>(tile_m) * N * 4);      // one fp32 [tile_m, N] slab per piece
+      if (pieces > slabs) pieces = static_cast<int>(slabs);
       if (pieces >= 2) {
         geo.kb_per_piece = (geo.num_k_blocks + pieces - 1) / pieces;
         geo.tail_pieces = (geo.num_k_blocks + geo.kb_per_piece - 1) / geo.kb_per_piece;
         geo.tail_ws = reinterpret_cast<float*>(ep.workspace);
-        if (cudaMemsetAsync(ep.workspace, 0, static_cast<size_t>(tail_rows) * N * 4, stream) != cudaSuccess) return OPB_ERR_CUDA;
       }
     }
   }
@@ -1251,7 +1273,7 @@ int gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   if (rc != OPB_OK) return rc;
   rc = dispatch_gemm(cta_group, epi, ta, tb, ep, geo, stream);
   if (rc != OPB_OK || geo.tail_pieces == 0) return rc;
-  gemm_tail_epilogue_kernel<<<tail_rows, 256, 0, stream>>>(geo.tail_ws, ep, M, N, m_full * tile_m, n_t);
+  gemm_tail_epilogue_kernel<<<dim3(tail_rows, n_t), 256, 0, stream>>>(geo.tail_ws, ep, M, N, m_full * tile_m, n_t, geo.tail_pieces, tile_m, epi);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

@@ -180,6 +180,113 @@ int split_bf16x3(const float* x, void* out, long rows, int d, int side, cudaStre
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
+// the four operand splits of one InfoNCE step (a_local, b_local: side 0; a_all, b_all: side 1) in ONE launch: blockIdx.y selects
+// the tensor (round 2: the head was 14 launches for 0.36 ms of work)
+struct Split4 {
+  const float* x[4];
+  __nv_bfloat16* out[4];
+  long total[4];
+  int side[4];
+};
+__global__ void split_bf16x3_x4_kernel(const Split4 sp, int d) {
+  const int t = blockIdx.y;
+  const float* __restrict__ x = sp.x[t];
+  __nv_bfloat16* __restrict__ out = sp.out[t];
+  const long total = sp.total[t];
+  const int side = sp.side[t];
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / d;
+    const int c = i % d;
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * 3L * d + c;
+    o[0] = hi;
+    o[d] = side == 0 ? hi : lo;
+    o[2L * d] = side == 0 ? lo : hi;
+  }
+}
+
+int split_bf16x3_x4(const float* const* xs, void* const* outs, const long* rows, const int* sides, int d, cudaStream_t stream) {
+  if (d <= 0) return OPB_ERR_INVALID;
+  Split4 sp;
+  long mx = 0;
+  for (int t = 0; t < 4; ++t) {
+    if (xs[t] == nullptr || outs[t] == nullptr || rows[t] <= 0 || (sides[t] != 0 && sides[t] != 1)) return OPB_ERR_INVALID;
+    sp.x[t] = xs[t]; sp.out[t] = reinterpret_cast<__nv_bfloat16*>(outs[t]); sp.total[t] = rows[t] * d; sp.side[t] = sides[t];
+    if (sp.total[t] > mx) mx = sp.total[t];
+  }
+  long blocks = (mx + 255) / 256;
+  if (blocks > 148L * 4) blocks = 148L * 4;
+  split_bf16x3_x4_kernel<<<dim3(static_cast<unsigned>(blocks), 4), 256, 0, stream>>>(sp, d);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// merge of BOTH directions' per-tile partials + the step's scalar outputs in one launch.  blockIdx.y = direction; every block
+// merges 128 rows (as infonce_merge_kernel) and takes a ticket; the LAST block to finish sums all 2 b row losses / hit flags in a
+// fixed order (the result does not depend on which block that is) and resets the ticket counter for the next call.
+__global__ void __launch_bounds__(128)
+infonce_merge2_reduce_kernel(const float* __restrict__ ws_a, const float* __restrict__ ws_b, int n_tiles, int b, int n, float eps,
+                             int target_offset, float* __restrict__ lse_a, float* __restrict__ lse_b, float* __restrict__ loss_ab,
+                             int* __restrict__ am_ab, float* __restrict__ out3, unsigned int* __restrict__ ticket) {
+  __shared__ float red[3][4];
+  __shared__ bool last;
+  const int dir = blockIdx.y;
+  const float* __restrict__ ws = dir == 0 ? ws_a : ws_b;
+  float* __restrict__ row_lse = dir == 0 ? lse_a : lse_b;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < b) {
+    float m = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) m = fmaxf(m, ws[(static_cast<long>(t) * b + row) * 8]);
+    float s = 0.f, zsum = 0.f, best = -INFINITY, ztgt = 0.f;
+    int best_idx = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const float* w = ws + (static_cast<long>(t) * b + row) * 8;
+      const float4 p0 = *reinterpret_cast<const float4*>(w);
+      const float4 p1 = *reinterpret_cast<const float4*>(w + 4);
+      s += p0.y * __expf(p0.x - m);
+      zsum += p0.z;
+      if (p0.w > best) { best = p0.w; best_idx = __float_as_int(p1.x); }
+      if (p1.z != 0.f) ztgt = p1.y;
+    }
+    const float lse = m + logf(s);
+    const float nll = lse - ztgt;
+    float loss = nll;
+    if (eps != 0.f) {
+      const float eps_i = eps / (n - 1);
+      loss = (1.f - eps - eps_i) * nll + eps_i * (n * lse - zsum);
+    }
+    row_lse[row] = lse;
+    loss_ab[dir * b + row] = loss;
+    am_ab[dir * b + row] = best_idx;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float la = 0.f, ca = 0.f, cb = 0.f;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    la += __ldcg(loss_ab + i) + __ldcg(loss_ab + b + i);
+    ca += (__ldcg(am_ab + i) == i + target_offset) ? 1.f : 0.f;
+    cb += (__ldcg(am_ab + b + i) == i + target_offset) ? 1.f : 0.f;
+  }
+  la = warp_sum(la); ca = warp_sum(ca); cb = warp_sum(cb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = la; red[1][warp] = ca; red[2][warp] = cb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < 4; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    out3[0] = t0 / (2.f * b);
+    out3[1] = t1;
+    out3[2] = t2;
+    *ticket = 0u;
+  }
+}
+
 static int n_tiles_of(int n) { return (n + 255) / 256; }
 
 long infonce_ws_floats(int b, int n) { return static_cast<long>(n_tiles_of(n)) * b * 8; }
@@ -199,6 +306,29 @@ int infonce_rows(const void* a_local, const void* b_all, const float* scale, int
   if (rc != OPB_OK) return rc;
   infonce_merge_kernel<<<(b + 127) / 128, 128, 0, stream>>>(ws, n_tiles_of(n), b, n_cls, eps, row_lse, row_loss,
                                                             row_argmax);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+}
+
+// LSE_PARTIAL GEMM of one direction only (the merge runs later, for both directions at once: infonce_merge_reduce)
+int infonce_lse_gemm(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset, float* ws,
+                     int n_valid, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || d <= 0 || d % 8 != 0 || n % 8 != 0 || n_valid < 0 || n_valid > n) return OPB_ERR_INVALID;
+  GemmEpilogue ep;
+  ep.out = ws;
+  ep.scale_ptr = scale;
+  ep.ws = ws;
+  ep.target_offset = target_offset;
+  ep.n_valid = n_valid;
+  return gemm_bf16(a_local, d, b_all, d, b, n, d, EPI_LSE_PARTIAL, ep, 0, stream);
+}
+
+// scratch: loss_ab fp32 [2 b], am_ab int32 [2 b], ticket: one zero-initialised uint32 (left at zero)
+int infonce_merge_reduce(const float* ws_a, const float* ws_b, int b, int n, int n_valid, float eps, int target_offset, float* lse_a,
+                         float* lse_b, float* loss_ab, int* am_ab, float* out3, unsigned int* ticket, cudaStream_t stream) {
+  if (b <= 0 || n <= 0 || n_valid < 0 || n_valid > n) return OPB_ERR_INVALID;
+  const int n_cls = n_valid > 0 ? n_valid : n;
+  infonce_merge2_reduce_kernel<<<dim3((b + 127) / 128, 2), 128, 0, stream>>>(ws_a, ws_b, n_tiles_of(n), b, n_cls, eps, target_offset,
+                                                                             lse_a, lse_b, loss_ab, am_ab, out3, ticket);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 

@@ -40,6 +40,11 @@ int zero_padded_rows(float* x, const uint8_t* pad_mask, int rows, int D, cudaStr
 
 int transpose_bf16(const void* in, long ld_in, void* out, int rows, int cols, cudaStream_t stream);
 int split_bf16x3(const float* x, void* out, long rows, int d, int side, cudaStream_t stream);
+int split_bf16x3_x4(const float* const* xs, void* const* outs, const long* rows, const int* sides, int d, cudaStream_t stream);
+int infonce_lse_gemm(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset, float* ws,
+                     int n_valid, cudaStream_t stream);
+int infonce_merge_reduce(const float* ws_a, const float* ws_b, int b, int n, int n_valid, float eps, int target_offset, float* lse_a,
+                         float* lse_b, float* loss_ab, int* am_ab, float* out3, unsigned int* ticket, cudaStream_t stream);
 long infonce_ws_floats(int b, int n);
 int infonce_rows(const void* a_local, const void* b_all, const float* scale, int b, int n, int d, int target_offset,
                  float eps, float* ws, float* row_lse, float* row_loss, int* row_argmax, int n_valid, cudaStream_t stream);

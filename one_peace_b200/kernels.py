@@ -360,6 +360,58 @@ def split_bf16x3(x, side):
     return out
 
 
+def split_bf16x3_x4(xs, sides):
+    """four fp32 [r_i, d] tensors -> four bf16 [r_i, 3d] splits in ONE launch (the operands of one InfoNCE step)"""
+    import ctypes
+    assert len(xs) == 4 and len(sides) == 4
+    d = xs[0].shape[1]
+    for x in xs:
+        _need_cuda(x)
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[1] == d
+    outs = [torch.empty(x.shape[0], 3 * d, dtype=torch.bfloat16, device=x.device) for x in xs]
+    px = (ctypes.c_void_p * 4)(*[x.data_ptr() for x in xs])
+    po = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in outs])
+    pr = (ctypes.c_int64 * 4)(*[x.shape[0] for x in xs])
+    ps = (ctypes.c_int * 4)(*[int(v) for v in sides])
+    st = _lib.load().opb_split_bf16x3_x4(ctypes.cast(px, ctypes.c_void_p), ctypes.cast(po, ctypes.c_void_p),
+                                         ctypes.cast(pr, ctypes.c_void_p), ctypes.cast(ps, ctypes.c_void_p), d, _stream())
+    _lib.check(st, "opb_split_bf16x3_x4")
+    _count()
+    return outs
+
+
+_TICKETS = {}
+
+
+def infonce_forward2(a3, b3, a_all3, b_all3, scale, target_offset, eps, n_valid=0):
+    """Both directions of the InfoNCE forward in 3 launches (two LSE_PARTIAL GEMMs + one merge / reduce kernel).
+    -> (lse_a [b], lse_b [b], out3 = {loss, #correct a->b, #correct b->a})"""
+    lib = _lib.load()
+    b, k = a3.shape
+    n = a_all3.shape[0]
+    dev = a3.device
+    ws_a = torch.empty(lib.opb_infonce_ws_floats(b, n), dtype=torch.float32, device=dev)
+    ws_b = torch.empty_like(ws_a)
+    for x, y, ws in ((a3, b_all3, ws_a), (b3, a_all3, ws_b)):
+        st = lib.opb_infonce_lse_gemm(x.data_ptr(), y.data_ptr(), scale.data_ptr(), b, n, k, target_offset, ws.data_ptr(), int(n_valid),
+                                      _stream())
+        _lib.check(st, "opb_infonce_lse_gemm")
+    lse_a = torch.empty(b, dtype=torch.float32, device=dev)
+    lse_b = torch.empty(b, dtype=torch.float32, device=dev)
+    loss_ab = torch.empty(2 * b, dtype=torch.float32, device=dev)
+    am_ab = torch.empty(2 * b, dtype=torch.int32, device=dev)
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _TICKETS:
+        _TICKETS[key] = torch.zeros(1, dtype=torch.int32, device=dev)       # the kernel leaves it at zero
+    st = lib.opb_infonce_merge_reduce(ws_a.data_ptr(), ws_b.data_ptr(), b, n, int(n_valid), float(eps), target_offset, lse_a.data_ptr(),
+                                      lse_b.data_ptr(), loss_ab.data_ptr(), am_ab.data_ptr(), out3.data_ptr(), _TICKETS[key].data_ptr(),
+                                      _stream())
+    _lib.check(st, "opb_infonce_merge_reduce")
+    _count(3)
+    return lse_a, lse_b, out3
+
+
 def infonce_rows(a_local, b_all, scale, target_offset, eps, n_valid=0):
     """One direction of the InfoNCE forward.  a_local bf16 [b,k], b_all bf16 [n,k], scale fp32 device scalar.
     n_valid > 0: only the first n_valid rows of b_all are classes (the rest is zero padding to n % 8 == 0).

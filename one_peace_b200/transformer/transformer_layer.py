@@ -171,7 +171,8 @@ class TransformerEncoderLayer(nn.Module):
         f = self._fused_ffn_pack(modality)
         n_t = (d + 255) // 256
         # LN1 -> QKV (+bias, q scale)
-        K.gemm_ln(xb, a["wqkv"], K.EPI_STORE_BF16, ws["qkv"], ln_colsum=a["cqkv"], bias=a["dqkv"], colscale=a["qscale"], **ln1)
+        K.gemm_ln(xb, a["wqkv"], K.EPI_STORE_BF16, ws["qkv"], ln_colsum=a["cqkv"], bias=a["dqkv"], colscale=a["qscale"],
+                  workspace=ws["tail"], **ln1)          # workspace: split-K slabs when M < 256 (small batches)
         # attention; emits per-head partial statistics of its output rows (inner LN)
         self.self_attn.run_attention(ws["qkv"], bias, key_pad, B, S, out=ws["o"], ln_stats=ws["part_a"])
         # inner LN -> out_proj -> LayerScale + residual; emits x, xb and the partial statistics for LN2
@@ -200,7 +201,7 @@ class TransformerEncoderLayer(nn.Module):
         f32 = torch.float32
         return dict(qkv=e(M, 3 * d), o=e(M, d), u=e(M, F_), xb=e(M, d), part_a=e(H * M * 2, dt=f32),
                     part_b=e(n_t * M * 2, dt=f32), part_c=e(2 * ((2 * F_) // 256) * M * 2, dt=f32), part_d=e(n_t * M * 2, dt=f32),
-                    tail=e(256 * d, dt=torch.float32),
+                    tail=e(16 * 256 * d, dt=torch.float32),      # split-K slabs of the residual GEMMs: one fp32 [256, d] slab per piece
                     mu=e(M, dt=torch.float32), rstd=e(M, dt=torch.float32), mu2=e(M, dt=torch.float32),
                     rstd2=e(M, dt=torch.float32))
 

@@ -336,6 +336,60 @@ def test_attention_tc(K, kind, B, S, H, use_pad):
     torch.testing.assert_close(mu, out.float().mean(1), atol=2e-3, rtol=1e-2)
 
 
+@pytest.mark.parametrize("M,d,N", [(136, 1536, 1536), (136, 6144, 1536), (40, 1024, 256), (255, 512, 512)])
+def test_gemm_resid_small_m_splitk(K, M, d, N):
+    """M < 256 (a few texts): with a workspace the whole fp32-residual GEMM runs as ONE 256-row split-K "tail" spread over all
+    clusters + the fix-up kernel (gemm_bf16 small-M mode); result, bf16 copy and LN statistics must match the plain schedule."""
+    g = torch.Generator(device="cuda").manual_seed(M + d)
+    a = (torch.randn(M, d, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, d, device="cuda", generator=g) * 0.05).bfloat16()
+    mu = torch.randn(M, device="cuda", generator=g) * 0.1
+    rs = torch.rand(M, device="cuda", generator=g) + 0.5
+    cs = torch.randn(N, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    n_t = (N + 255) // 256
+    outs = []
+    for use_ws in (False, True):
+        y = res.clone()
+        yb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        part = torch.zeros(n_t * M * 2, device="cuda")
+        wsb = torch.empty(16 * 256 * N, device="cuda") if use_ws else None          # one fp32 [256, N] slab per split-K piece
+        K.gemm_ln(a, w, K.EPI_RESID_F32, y, ln_mu=mu, ln_rstd=rs, ln_colsum=cs, bias=bias, gamma=gamma, resid=y,
+                  stats_out=part, out_bf16=yb, workspace=wsb)
+        outs.append((y, yb, part))
+    want = res + gamma * (rs[:, None] * (a.float() @ w.float().t() - mu[:, None] * cs) + bias)
+    for y, yb, part in outs:
+        assert relerr(y, want) < 1e-4
+        assert torch.equal(yb, y.bfloat16())
+    torch.testing.assert_close(outs[1][2].view(n_t, M, 2), outs[0][2].view(n_t, M, 2), atol=2e-2, rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,d,N", [(136, 1536, 4608), (17, 1024, 768)])
+def test_gemm_store_small_m_splitk(K, M, d, N):
+    """the q/k/v projection of a small batch (bf16 store epilogue with fused LayerNorm, bias and column scale): with a workspace
+    its K range is split over all clusters and the fix-up kernel applies the epilogue; must match the plain schedule."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = (torch.randn(M, d, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, d, device="cuda", generator=g) * 0.05).bfloat16()
+    mu = torch.randn(M, device="cuda", generator=g) * 0.1
+    rs = torch.rand(M, device="cuda", generator=g) + 0.5
+    cs = torch.randn(N, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    scale = torch.rand(N, device="cuda", generator=g) + 0.5
+    outs = []
+    for use_ws in (False, True):
+        y = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        wsb = torch.empty(16 * 256 * 1536, device="cuda") if use_ws else None
+        K.gemm_ln(a, w, K.EPI_STORE_BF16, y, ln_mu=mu, ln_rstd=rs, ln_colsum=cs, bias=bias, colscale=scale, workspace=wsb)
+        outs.append(y)
+    want = (rs[:, None] * (a.float() @ w.float().t() - mu[:, None] * cs) + bias) * scale
+    for y in outs:
+        assert relerr(y, want) < 8e-3
+    assert relerr(outs[1], outs[0]) < 8e-3
+
+
 def test_gemm_resid_m_tail_splitk(K):
     """M = 49 * 256 + 64 rows, N = 1536: the 64-row tail is scheduled as split-K pieces (fp32 atomics into a scratch tile)
     and finished by the tail-epilogue kernel; result, bf16 copy and LN statistics must match the plain path.
@@ -355,7 +409,7 @@ def test_gemm_resid_m_tail_splitk(K):
         y = res.clone()
         yb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
         part = torch.zeros(6 * M * 2, device="cuda")
-        wsb = torch.empty(256 * N, device="cuda") if use_ws else None
+        wsb = torch.empty(16 * 256 * N, device="cuda") if use_ws else None          # one fp32 [256, N] slab per split-K piece
         K.gemm_ln(a, w, K.EPI_RESID_F32, y, ln_mu=mu, ln_rstd=rs, ln_colsum=cs, bias=bias, gamma=gamma, resid=y,
                   stats_out=part, out_bf16=yb, workspace=wsb)
         outs.append((y, yb, part))
@@ -377,7 +431,7 @@ def test_gemm_resid_m_tail_splitk(K):
     res2 = []
     for kw in (dict(ln_mu=m2, ln_rstd=r2), dict(ln_partial=(rec.view(-1), parts, dim, 1e-5))):
         y = res.clone()
-        K.gemm_ln(a, w, K.EPI_RESID_F32, y, ln_colsum=cs, bias=bias, gamma=gamma, resid=y, workspace=torch.empty(256 * N, device="cuda"), **kw)
+        K.gemm_ln(a, w, K.EPI_RESID_F32, y, ln_colsum=cs, bias=bias, gamma=gamma, resid=y, workspace=torch.empty(16 * 256 * N, device="cuda"), **kw)
         res2.append(y)
     assert relerr(res2[1], res2[0]) < 1e-5
 
