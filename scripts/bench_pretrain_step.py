@@ -57,3 +57,13 @@ print(f"image-text pretraining step, {B} pairs, {L}-layer 4B-width encoder + dec
       f"{sum(p.numel() for p in params) / 1e9:.2f} B parameters, peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GB, loss {float(loss):.4f} "
       f"(itc {float(log['itc_loss']):.3f}, dcl {float(log['dcl_text_loss']):.3f} / {float(log['dcl_image_loss']):.3f} / "
       f"{float(log['dcl_vl_text_loss']):.3f} / {float(log['dcl_vl_image_loss']):.3f})")
+if os.environ.get("OPB_PROFILE", "0") == "1":
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    ka = prof.key_averages()
+    tot = sum(k.self_device_time_total for k in ka) / 1e3
+    print(f"CUDA kernel time of one step (torch.profiler): {tot:.1f} ms; top kernels:")
+    for k in sorted(ka, key=lambda k: -k.self_device_time_total)[:12]:
+        print(f"   {k.self_device_time_total / 1e3:8.2f} ms  n={k.count:5d}  {k.key[:100]}")
