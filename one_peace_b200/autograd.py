@@ -2,16 +2,18 @@
 
 The reference trains through torch autograd (transformer_layer.py:165-228, multihead_attention.py:103-126, with
 ``checkpoint_activations`` in the 4B recipes).  Here every adjoint is an sm_100a kernel behind the C-ABI
-(csrc/backward.cu, csrc/attention_bwd.cu + the tcgen05 GEMM for all dX / dW products); autograd only carries the
+(csrc/backward.cu, csrc/attention_bwd*.cu + the tcgen05 GEMM for all dX / dW products); autograd only carries the
 graph edges between five ``Function`` nodes:
 
-    TextEmbedFn / ImageEmbedFn  ->  EncoderStackFn (L layers, activation recompute)  ->  HeadFn  ->  criterion
+    TextEmbedFn / ImageEmbedFn  ->  EncoderStackFn (L layers, activations kept or recomputed)  ->  HeadFn  ->  criterion
     RelPosBiasFn (table -> dense (H,S,S_pad) bias, shared by the layers) ----^
 
-Activation policy = the reference's checkpointing: the forward keeps only each layer's fp32 input rows; the backward
-re-runs one layer forward (un-fused LayerNorm form, so the normalised operands the dW GEMMs need exist in HBM) and
-walks its adjoint.  dW = dY^T X is an M-reduction: both operands are transposed to K-major by the transpose kernel
-and go through the same TMA + tcgen05 GEMM as everything else.
+Activation policy (keep_activations below): when the whole stack's activations fit in half of the free HBM they are KEPT (the
+training forward then runs the un-fused LayerNorm form, whose normalised operands the dW GEMMs need) and the backward is the
+adjoint only; otherwise the forward runs the inference kernels and keeps each layer's fp32 input rows, and the backward re-runs
+one layer forward per step — the reference's checkpoint_wrapper.  dW = dY^T X is an M-reduction whose operands the tcgen05 GEMM
+reads in place as MN-major tiles (opb_gemm_bf16_t); dX = dY W reads the forward weight the same way: nothing is transposed in
+memory.  Attention backward: csrc/attention_bwd_tc2.cu (tcgen05, S <= 224, transposed bias tables shared by the stack).
 
 torch is used here for what the task calls plumbing only: allocation, dtype / layout copies (`.to`, `cat`, slicing
 `copy_`), the drop-path Bernoulli draw, and autograd's own accumulation of gradients that reach a tensor twice.
@@ -25,7 +27,7 @@ from .components import PackCache, bf16, f32
 class TrainBias:
     """Relative-position bias of a training forward: `dense` = autograd-tracked fp32 (H,S,S_pad) tensor (what the
     backward kernels read and what receives the gradient), `fast` = the same values as a kernels.RelPosBias in LUT
-    form for the tcgen05 attention kernels (None when S > 768)."""
+    form for the tcgen05 attention kernels (None when S > kernels.ATTN_TC_MAX_S)."""
 
     def __init__(self, dense, fast=None):
         self.dense, self.fast, self.lut = dense, fast, None
