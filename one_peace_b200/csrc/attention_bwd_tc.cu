@@ -498,8 +498,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const unsigned grid = static_cast<unsigned>(a.n_items < sms ? a.n_items : sms);
-  kern<<<grid, kThreads, smem, stream>>>(tq, tkv, tdo, a);
-  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+  return launch_maybe_cluster(kern, dim3(grid), dim3(kThreads), smem, stream, tq, tkv, tdo, a) == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
 }  // namespace

@@ -466,8 +466,8 @@ int attention_bwd_tc2(const void* qkv, const void* d_out, const uint8_t* key_pad
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const unsigned grid = static_cast<unsigned>(a.n_items < sms ? a.n_items : sms);
-  attention_bwd_tc2_kernel<<<grid, kThreads, smem, stream>>>(tq, tkv, tdo, a);
-  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+  return launch_maybe_cluster(attention_bwd_tc2_kernel, dim3(grid), dim3(kThreads), smem, stream, tq, tkv, tdo, a) == cudaSuccess
+             ? OPB_OK : OPB_ERR_CUDA;
 }
 
 }  // namespace opb

@@ -476,8 +476,7 @@ static int launch_tcp(const CUtensorMap& tq, const CUtensorMap& tkv, const TcpAr
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const unsigned grid = static_cast<unsigned>(a.n_tiles < sms ? a.n_tiles : sms);
-  kern<<<grid, kPThreads, smem, stream>>>(tq, tkv, a);
-  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+  return launch_maybe_cluster(kern, dim3(grid), dim3(kPThreads), smem, stream, tq, tkv, a) == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
 }
 
 // Same contract as attention_tc_fwd (ops.h); S <= 224.  Returns OPB_ERR_UNSUPPORTED for longer sequences.

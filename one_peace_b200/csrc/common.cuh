@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #define OPB_DEVICE __device__ __forceinline__
 
@@ -347,6 +348,29 @@ OPB_DEVICE float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Host: launch `kern` as a thread-block cluster of ONE CTA when OPB_ATTN_CLUSTER_LAUNCH=1 (default: a plain launch).  Why the switch
+// exists: two micro-benchmarks of the same tcgen05.mma chain on the same box differ by 2.4x (52 vs 127 cycles per N = 64 instruction,
+// profiles/r02_tcgen05_mma_issue_cost*.txt) and the only difference found between them is that the fast one is launched through
+// cudaLaunchKernelEx with a cluster dimension (of 1), the way the GEMM kernel is, and the slow one with <<<>>>, the way the attention
+// kernels are.  The round's GPU budget ended before the attention kernels could be timed both ways, so the validated plain launch
+// stays the default and the cluster launch is opt-in (falls back to the plain launch if the runtime rejects the configuration).
+template <typename Kern, typename... Args>
+inline cudaError_t launch_maybe_cluster(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  static const char* env = getenv("OPB_ATTN_CLUSTER_LAUNCH");
+  if (env != nullptr && env[0] == '1') {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, args...) == cudaSuccess) return cudaSuccess;
+    (void)cudaGetLastError();           // rejected: clear the error and launch the plain way
+  }
+  kern<<<grid, block, smem, stream>>>(args...);
+  return cudaGetLastError();
 }
 
 }  // namespace opb
